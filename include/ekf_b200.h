@@ -1,0 +1,183 @@
+/* include/ekf_b200.h — C ABI of the B200-native MonoSLAM EKF hot path.
+ *
+ * Drop-in boundary for ONE path of engyasin/EKF-MonoSLAM_for_3D-reconstruction: the per-frame EKF
+ * of `class VSlamFilter` (mono-slam/src/vslamRansac.hpp:27-141, vslamRansac.cpp) together with the
+ * active-search matcher `Patch::findMatch` (mono-slam/src/Patch.cpp:215-329) and the camera model
+ * (mono-slam/src/camModel.cpp).  The reference has no FFI of its own; its seam is the C++ class.
+ * Each entry point below names the reference member it replaces.  A C++ class with the reference's
+ * method names over this ABI lives in ekf-monoslam_for_3d-reconstruction_b200/host/vslam_filter.hpp;
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain C types only; every function returns an int status (EKF_OK or a negative error) unless
+ *    it mirrors a reference function with its own return value (documented per function);
+ *  - all arithmetic is fp64 on the GPU (the reference is fp32 Eigen; BASELINE.json asks for fp64);
+ *  - matrices cross the boundary row-major; the state layout is the reference's:
+ *    mu = [ r(3) q(4, w first) v(3) w(3) map_scale | features... ], STATE_DIM 14
+ *    (vslamRansac.cpp:22,163-164), inverse-depth feature = (x y z theta phi rho), XYZ = (x y z);
+ *  - a handle owns all device state, is bound to one CUDA device and one stream, and is not
+ *    thread-safe (the reference is a single-threaded ros::spin loop, monoslam_ransac.cpp:865);
+ *  - there is NO CPU fallback: every call fails with EKF_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef EKF_B200_H_
+#define EKF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EKF_STATE_DIM 14 /* vslamRansac.cpp:22 */
+
+enum {
+  EKF_OK = 0,
+  EKF_ERR_ARG = -1,         /* bad argument */
+  EKF_ERR_CUDA = -2,        /* CUDA runtime error, see ekf_last_error() */
+  EKF_ERR_CAPACITY = -3,    /* feature / state capacity of the handle exceeded */
+  EKF_ERR_UNSUPPORTED = -4, /* configuration asks for a reference feature outside this path */
+  EKF_ERR_STATE = -5        /* call order violated (e.g. update before predict) */
+};
+
+/* ConfigVSLAM (mono-slam/src/ConfigVSLAM.h:23-48, defaults ConfigVSLAM.cpp:27-47) + camConfig
+ * (camModel.hpp:9-11, defaults camModel.hpp:25-33) + the constants the reference hard-codes,
+ * each named with its source line.  ekf_config_default() fills the reference values. */
+typedef struct ekf_config {
+  double sigma_vx, sigma_vy, sigma_vz; /* ConfigVSLAM.cpp:28 */
+  double sigma_wx, sigma_wy, sigma_wz; /* ConfigVSLAM.cpp:29 */
+  double rho_0, sigma_rho_0;           /* ConfigVSLAM.cpp:34-35 */
+  double T_camera;                     /* ConfigVSLAM.cpp:39 */
+  double fx, fy, u0, v0, k1, k2, k3, p1, p2; /* camModel.hpp:25-33 */
+  double ncc_threshold;        /* Patch.cpp:14          0.8   */
+  double search_clamp;         /* Patch.cpp:240-241     20 px */
+  double ransac_p;             /* vslamRansac.cpp:967   0.99  */
+  double li_threshold_factor;  /* vslamRansac.cpp:968   2 (x sigma_pixel) */
+  double hi_chi2_threshold;    /* vslamRansac.cpp:1066  1     */
+  double quality_ratio;        /* Patch.hpp:39          0.2   */
+  double linearity_threshold;  /* vslamRansac.cpp:701   0.01  */
+  int32_t window_size;         /* ConfigVSLAM.cpp:31    21    */
+  int32_t sigma_pixel;         /* ConfigVSLAM.cpp:32    2     */
+  int32_t kernel_size;         /* no default in the reference (ConfigVSLAM.cpp:76); here 1e9 = blur off */
+  int32_t sigma_size;          /* ConfigVSLAM.cpp:41    2     */
+  int32_t scale;               /* ConfigVSLAM.cpp:37    1     */
+  int32_t nInitFeatures, min_features, max_features, forsePlane; /* ConfigVSLAM.cpp:43-48 */
+  int32_t ransac_nhyp0;        /* vslamRansac.cpp:966   10000 */
+  int32_t xyz_conversion;      /* vslamRansac.cpp:1317  1 = convert2XYZ_ifLinearAll() every update */
+  int32_t abs_int_quirk;       /* vslamRansac.cpp:719   0 = abs(float) is fabs (modern libstdc++) */
+} ekf_config;
+
+/* One feature as RosVSLAM / the ROS node read it (Patch.hpp:18-106; RosVSLAMRansac.cpp:177-183). */
+typedef struct ekf_feature_info {
+  int32_t position_in_state, position_in_z, coding /* 0 = inverse depth, 1 = XYZ */;
+  int32_t n_tot, n_find, real_index;
+  int32_t is_in_innovation, is_in_li, is_in_hi, remove_flag;
+  float center[2];     /* Patch::center (cv::Point2f) */
+  float quality_index; /* Patch::quality_index */
+  float last_ncc;      /* best NCC of the last findMatch (diagnostic) */
+  double z[2], h[2];   /* Patch::z, Patch::h */
+  double H[26];        /* Patch::H, compact 2 x 13: columns [0,7) = d/d(r,q), [7,13) = d/d(feature) */
+  double state[6];     /* mu[pos .. pos+6) (3 used when XYZ) */
+  double cov[36];      /* Sigma[pos.., pos..] row-major 6 x 6 (3 x 3 top-left when XYZ) */
+} ekf_feature_info;
+
+/* Counters of the last completed step (diagnostics; not in the reference). */
+typedef struct ekf_step_stats {
+  int32_t n_in_innovation_predict; /* features that passed the gate in predict (vslamRansac.cpp:529) */
+  int32_t n_matched;               /* vslamRansac.cpp:984 */
+  int32_t n_li, n_hi;              /* rows/2 of the two updates */
+  int32_t ransac_hypotheses;       /* loop trips of vslamRansac.cpp:986 */
+  int32_t n_removed;               /* features dropped by vslamRansac.cpp:1296-1299 */
+  int32_t topup_request;           /* argument vslamRansac.cpp:1314 would pass to findNewFeatures */
+  int32_t blur_requests;           /* always 0: blur is rejected at create time */
+  int64_t kernel_launches;         /* kernels of this library launched on the handle so far */
+} ekf_step_stats;
+
+typedef struct ekf_handle ekf_handle;
+
+/* ---- life cycle ------------------------------------------------------------------------------ */
+/* Fills *cfg with the reference defaults (ConfigVSLAM.cpp:27-47, camModel.hpp:25-33). */
+void ekf_config_default(ekf_config* cfg);
+/* VSlamFilter::VSlamFilter (vslamRansac.cpp:142-223).  `feature_capacity` bounds the number of
+ * simultaneously tracked features (device buffers are sized for n = 14 + 6*capacity). `device` is
+ * a CUDA ordinal.  Configs that need blur (kernel_size < 100000), scale != 1 or an even
+ * window_size > 64 return EKF_ERR_UNSUPPORTED. */
+int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_handle** out);
+int ekf_destroy(ekf_handle* h);
+/* Use `cuda_stream` (a cudaStream_t) for all work of this handle; NULL = the handle's own stream. */
+int ekf_set_stream(ekf_handle* h, void* cuda_stream);
+/* Blocks until all work queued on the handle is done. */
+int ekf_sync(ekf_handle* h);
+const char* ekf_last_error(const ekf_handle* h);
+
+/* ---- the per-frame path ---------------------------------------------------------------------- */
+/* VSlamFilter::captureNewFrame(cv::Mat, double) (vslamRansac.cpp:226-245): 8-bit gray, HOST
+ * memory, copied to the device inside the call.  stamp < 0 = the no-stamp overload. */
+int ekf_capture_frame(ekf_handle* h, const uint8_t* gray, int width, int height, int stride, double stamp);
+/* Same, for a frame already resident in DEVICE memory (copied device-to-device). */
+int ekf_capture_frame_device(ekf_handle* h, const uint8_t* gray_dev, int width, int height, int stride, double stamp);
+/* VSlamFilter::predict (vslamRansac.cpp:451-603). */
+int ekf_predict(ekf_handle* h, const double dv[3], const double dw[3], int vcontrol);
+/* The active-search loop at the top of VSlamFilter::update (vslamRansac.cpp:870-880), split out so
+ * it can be timed and so matches can be injected.  Returns the matched count in *n_matched if not
+ * NULL (forces a device sync). */
+int ekf_match(ekf_handle* h, int* n_matched);
+/* The rest of VSlamFilter::update (vslamRansac.cpp:964-1341).  `picks` replaces rand()
+ * (vslamRansac.cpp:970,989): hypothesis k draws picks[k % n_picks] % candidates (0 if n_picks==0). */
+int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks);
+/* VSlamFilter::update = ekf_match + ekf_update_after_match. */
+int ekf_update(ekf_handle* h, const uint32_t* picks, int n_picks);
+/* Overrides Patch::z / center of feature idx and marks it matched (test hook for injected matches). */
+int ekf_inject_match(ekf_handle* h, int idx, double zu, double zv, int accepted);
+
+/* ---- map management -------------------------------------------------------------------------- */
+/* VSlamFilter::addFeature (vslamRansac.cpp:309-371): returns 1 added, 0 rejected, <0 error. */
+int ekf_add_feature(ekf_handle* h, float u, float v);
+/* VSlamFilter::removeFeature (vslamRansac.cpp:373-421). */
+int ekf_remove_feature(ekf_handle* h, int index);
+/* VSlamFilter::convert2XYZ_ifLinear / convert2XYZ_ifLinearAll (vslamRansac.cpp:741-780). */
+int ekf_convert2xyz_if_linear(ekf_handle* h, int index);
+int ekf_convert2xyz_if_linear_all(ekf_handle* h);
+
+/* ---- accessors the ROS node / RosVSLAM read ---------------------------------------------------- */
+int ekf_num_features(const ekf_handle* h);                     /* numOfFeatures, vslamRansac.cpp:127 */
+int ekf_state_dim(const ekf_handle* h);                        /* mu.rows() */
+int ekf_get_state(ekf_handle* h, double out[EKF_STATE_DIM]);   /* getState, vslamRansac.cpp:135-140 */
+int ekf_get_sigma(ekf_handle* h, double out[EKF_STATE_DIM * EKF_STATE_DIM]); /* getSigma, :131-133 */
+int ekf_covariance_parameter(ekf_handle* h, double* out);      /* Covariance_Parameter, :841-866 */
+double ekf_get_dt(const ekf_handle* h);                        /* getDt, :247 */
+int ekf_get_center(ekf_handle* h, int idx, float out[2]);      /* returnCentrPatchIndx, vslamRansac.hpp:136 */
+int ekf_get_feature(ekf_handle* h, int idx, ekf_feature_info* out);
+/* which: 0 = Patch::patch, 1 = Patch::matching_patch; out holds window_size^2 bytes */
+int ekf_get_template(ekf_handle* h, int idx, int which, uint8_t* out);
+int ekf_get_step_stats(ekf_handle* h, ekf_step_stats* out);
+
+/* ---- whole-state get / set (checkpoint-resume and per-step parity with identical inputs) ------- */
+/* mu: n doubles; sigma: n x n row-major with leading dimension ld >= n. */
+int ekf_get_full(ekf_handle* h, double* mu, double* sigma, int ld);
+int ekf_set_full(ekf_handle* h, const double* mu, const double* sigma, int ld);
+/* Innovation covariance after predict (St of vslamRansac.cpp:598): the 2x2 diagonal block of every
+ * feature (4 doubles each, row-major, zeros if not in innovation).  Only these blocks are consumed
+ * by the reference (vslamRansac.cpp:875). */
+int ekf_get_S_blocks(ekf_handle* h, double* out /* 4 * num_features */);
+
+/* ---- stateless batched matcher (BASELINE config 5) --------------------------------------------- */
+/* Patch::findMatch (Patch.cpp:215-291) for F frames x M features, everything in DEVICE memory:
+ *   frames    F x height x stride u8
+ *   templates F*M x w x w u8        (Patch::matching_patch)
+ *   h         F*M x 2 doubles       (Patch::h)
+ *   S         F*M x 4 doubles       (2x2 block of St, row-major)
+ *   out_uv    F*M x 2 int32         (Patch::center / z; -1,-1 when rejected)
+ *   out_score F*M floats            (best NCC; -1 when no candidate)
+ * `stream` is a cudaStream_t (NULL = default stream). */
+int ekf_match_batch(const uint8_t* frames, int n_frames, int width, int height, int stride,
+                    const uint8_t* templates, int features_per_frame, int window_size,
+                    const double* h, const double* S, float sigma_size, float ncc_threshold,
+                    float search_clamp, int32_t* out_uv, float* out_score, void* stream);
+
+/* Library version / build info: returns a static string naming the compiled arch. */
+const char* ekf_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EKF_B200_H_ */
