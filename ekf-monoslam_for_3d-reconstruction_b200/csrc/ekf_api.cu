@@ -1,0 +1,596 @@
+// csrc/ekf_api.cu — the C ABI of include/ekf_b200.h: handle, host-side sequencing of the kernels,
+// feature-table management (add / remove), accessors.  No CPU fallback: every entry point needs a
+// CUDA device and fails with EKF_ERR_CUDA otherwise.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ekf_b200.h"
+#include "ekf_kernels.h"
+
+struct DeletedPatch {  // Patch archived by removeFeature (vslamRansac.cpp:394-404)
+  int real_index;
+  double XYZ_pos[3];
+  double cov_4_delete[9];
+};
+
+struct ekf_handle {
+  ekf_config cfg;
+  DevCfg dcfg;
+  int device = 0;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  int Ncap = 0, ncap = 0, ld = 0, N = 0, n = EKF_CAM;
+  double *mu = nullptr, *muB = nullptr, *Sigma = nullptr, *SigmaB = nullptr;
+  double *W = nullptr, *nu = nullptr, *Lb = nullptr, *Dinv = nullptr, *yb = nullptr, *delta = nullptr, *mu_i = nullptr;
+  int *cand = nullptr, *map_dev = nullptr, *keep_dev = nullptr, *newpos_dev = nullptr;
+  DevCtl* ctl = nullptr;
+  FeatTab ft{}, ftB{};
+  uint8_t* frame = nullptr;
+  size_t frame_cap = 0;
+  FrameView fv{nullptr, 0, 0, 0};
+  uint32_t* picks_dev = nullptr;
+  int picks_cap = 0;
+  double* out_dev = nullptr;   // packed step record (device)
+  double* out_host = nullptr;  // pinned mirror
+  size_t out_bytes = 0;
+  double dT = 1.0, old_ts = -1.0;
+  int patchnumbre = 1, noise_cov_factor = 0;
+  bool predicted = false, have_frame = false;
+  int lower_only = 0;
+  ekf_step_stats stats{};
+  long long launches = 0;
+  std::string err;
+  std::vector<DeletedPatch> deleted;
+  // host cache of the feature table (valid when cache_ok)
+  bool cache_ok = false;
+  std::vector<int> c_pos, c_coding, c_innov, c_li, c_hi, c_removef, c_ntot, c_nfind, c_real, c_posz;
+  std::vector<float> c_center, c_quality, c_ncc;
+  std::vector<double> c_z, c_h, c_Hc, c_S2;
+  // host mirror maintained by add/remove (always valid)
+  std::vector<int> m_pos, m_coding;
+};
+
+static int ekf_fail_cuda(ekf_handle* h, cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  if (h) h->err = buf;
+  return EKF_ERR_CUDA;
+}
+static int ekf_fail(ekf_handle* h, int code, const char* msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+template <class T>
+static cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, sizeof(T) * std::max<size_t>(count, 1)); }
+
+static cudaError_t alloc_feattab(FeatTab& t, int cap, int w2) {
+  cudaError_t e;
+#define A(field, cnt) if ((e = dalloc(&t.field, (size_t)(cnt))) != cudaSuccess) return e;
+  A(pos, cap) A(coding, cap) A(innov, cap) A(li, cap) A(hi, cap) A(removef, cap) A(n_tot, cap) A(n_find, cap)
+  A(real_index, cap) A(pos_in_z, cap) A(sel, cap) A(center, 2 * cap) A(quality, cap) A(last_ncc, cap)
+  A(z, 2 * cap) A(h, 2 * cap) A(Hc, 26 * cap) A(S2, 4 * cap) A(patch, (size_t)cap * w2) A(mpatch, (size_t)cap * w2)
+#undef A
+  return cudaSuccess;
+}
+static void free_feattab(FeatTab& t) {
+  cudaFree(t.pos); cudaFree(t.coding); cudaFree(t.innov); cudaFree(t.li); cudaFree(t.hi); cudaFree(t.removef);
+  cudaFree(t.n_tot); cudaFree(t.n_find); cudaFree(t.real_index); cudaFree(t.pos_in_z); cudaFree(t.sel);
+  cudaFree(t.center); cudaFree(t.quality); cudaFree(t.last_ncc); cudaFree(t.z); cudaFree(t.h); cudaFree(t.Hc);
+  cudaFree(t.S2); cudaFree(t.patch); cudaFree(t.mpatch);
+  t = FeatTab{};
+}
+
+extern "C" {
+
+const char* ekf_build_info(void) { return "libekf_b200: sm_100a, fp64, update block " "128" " rows, built " __DATE__; }
+
+void ekf_config_default(ekf_config* c) {
+  if (!c) return;
+  c->sigma_vx = c->sigma_vy = c->sigma_vz = 0.01;
+  c->sigma_wx = c->sigma_wy = c->sigma_wz = 0.01;
+  c->rho_0 = 0.1; c->sigma_rho_0 = 0.25; c->T_camera = 0.5;
+  c->fx = 592.2860; c->fy = 584.9968; c->u0 = 362.1059; c->v0 = 275.9642;
+  c->k1 = -0.3954; c->k2 = 0.5521; c->k3 = 0; c->p1 = -0.0075; c->p2 = 0.0140;
+  c->ncc_threshold = 0.8; c->search_clamp = 20; c->ransac_p = 0.99; c->li_threshold_factor = 2;
+  c->hi_chi2_threshold = 1; c->quality_ratio = 0.2; c->linearity_threshold = 0.01;
+  c->window_size = 21; c->sigma_pixel = 2; c->kernel_size = 1000000000; c->sigma_size = 2; c->scale = 1;
+  c->nInitFeatures = 5; c->min_features = 30; c->max_features = 100; c->forsePlane = 0;
+  c->ransac_nhyp0 = 10000; c->xyz_conversion = 1; c->abs_int_quirk = 0;
+}
+
+const char* ekf_last_error(const ekf_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int ekf_destroy(ekf_handle* h) {
+  if (!h) return EKF_OK;
+  cudaSetDevice(h->device);
+  if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  cudaFree(h->mu); cudaFree(h->muB); cudaFree(h->Sigma); cudaFree(h->SigmaB); cudaFree(h->W); cudaFree(h->nu);
+  cudaFree(h->Lb); cudaFree(h->Dinv); cudaFree(h->yb); cudaFree(h->delta); cudaFree(h->mu_i); cudaFree(h->cand);
+  cudaFree(h->map_dev); cudaFree(h->keep_dev); cudaFree(h->newpos_dev); cudaFree(h->ctl); cudaFree(h->frame);
+  cudaFree(h->picks_dev); cudaFree(h->out_dev);
+  if (h->out_host) cudaFreeHost(h->out_host);
+  free_feattab(h->ft); free_feattab(h->ftB);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return EKF_OK;
+}
+
+int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_handle** out) {
+  if (!cfg || !out || feature_capacity < 1 || feature_capacity > 8192) return EKF_ERR_ARG;
+  *out = nullptr;
+  // parts of the reference outside this path are rejected, never emulated on the CPU
+  if (cfg->kernel_size < 100000) return EKF_ERR_UNSUPPORTED;   // motion-blur templates (libblur.cpp)
+  if (cfg->scale != 1) return EKF_ERR_UNSUPPORTED;             // cv::resize in captureNewFrame
+  if (cfg->forsePlane != 0) return EKF_ERR_UNSUPPORTED;        // plane pseudo-measurement (V:1250-1263)
+  if (cfg->xyz_conversion != 0) return EKF_ERR_UNSUPPORTED;    // convert2XYZ_ifLinear (V:741-780)
+  if (cfg->window_size < 3 || cfg->window_size > 31) return EKF_ERR_UNSUPPORTED;
+  if (cfg->search_clamp > 20 || cfg->search_clamp < 0) return EKF_ERR_UNSUPPORTED;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || device < 0 || device >= ndev) return EKF_ERR_CUDA;
+  ekf_handle* h = new ekf_handle;
+  h->cfg = *cfg;
+  h->device = device;
+  auto bail = [&](cudaError_t ee, const char* what) {
+    ekf_fail_cuda(h, ee, what, __FILE__, __LINE__);
+    fprintf(stderr, "ekf_create: %s\n", h->err.c_str());
+    ekf_destroy(h);
+    return EKF_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+  if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+  h->stream = h->own_stream;
+  if (update_kernels_init() != 0) return bail(cudaGetLastError(), "kernel attributes");
+  h->Ncap = feature_capacity;
+  h->ncap = EKF_CAM + 6 * feature_capacity;
+  h->ld = (h->ncap + 7) & ~7;
+  const int w2 = cfg->window_size * cfg->window_size;
+  const size_t ssz = (size_t)h->ncap * h->ld;
+#define TRY(x) if ((e = (x)) != cudaSuccess) return bail(e, #x);
+  TRY(dalloc(&h->mu, h->ld)) TRY(dalloc(&h->muB, h->ld)) TRY(dalloc(&h->Sigma, ssz)) TRY(dalloc(&h->SigmaB, ssz))
+  TRY(dalloc(&h->W, (size_t)(h->ncap + 1) * EKF_UB)) TRY(dalloc(&h->nu, EKF_UB)) TRY(dalloc(&h->Lb, EKF_UB * EKF_UB))
+  TRY(dalloc(&h->Dinv, 4 * 32 * 32)) TRY(dalloc(&h->yb, EKF_UB)) TRY(dalloc(&h->delta, h->ld)) TRY(dalloc(&h->mu_i, h->ld))
+  TRY(dalloc(&h->cand, h->Ncap)) TRY(dalloc(&h->map_dev, h->ncap)) TRY(dalloc(&h->keep_dev, h->Ncap))
+  TRY(dalloc(&h->newpos_dev, h->Ncap)) TRY(dalloc(&h->ctl, 1))
+  TRY(alloc_feattab(h->ft, h->Ncap, w2)) TRY(alloc_feattab(h->ftB, h->Ncap, w2))
+  h->out_bytes = sizeof(double) * 210 + sizeof(int) * (16 + 3 * (size_t)h->Ncap);
+  TRY(cudaMalloc((void**)&h->out_dev, h->out_bytes)) TRY(cudaMallocHost((void**)&h->out_host, h->out_bytes))
+  TRY(cudaMemsetAsync(h->ctl, 0, sizeof(DevCtl), h->stream))
+  TRY(cudaMemsetAsync(h->Sigma, 0, sizeof(double) * ssz, h->stream))
+  TRY(cudaMemsetAsync(h->SigmaB, 0, sizeof(double) * ssz, h->stream))
+  TRY(cudaMemsetAsync(h->mu, 0, sizeof(double) * h->ld, h->stream))
+  // device copy of the configuration scalars
+  DevCfg& d = h->dcfg;
+  d.cam = CamParams{cfg->fx, cfg->fy, cfg->u0, cfg->v0, cfg->k1, cfg->k2, cfg->k3, cfg->p1, cfg->p2};
+  d.Vmax[0] = cfg->sigma_vx * cfg->sigma_vx; d.Vmax[1] = cfg->sigma_vy * cfg->sigma_vy; d.Vmax[2] = cfg->sigma_vz * cfg->sigma_vz;
+  d.Vmax[3] = cfg->sigma_wx * cfg->sigma_wx; d.Vmax[4] = cfg->sigma_wy * cfg->sigma_wy; d.Vmax[5] = cfg->sigma_wz * cfg->sigma_wz;
+  d.sigma_pixel_2 = (double)(cfg->sigma_pixel * cfg->sigma_pixel);
+  d.th_low = cfg->li_threshold_factor * cfg->sigma_pixel;
+  d.th_hi = cfg->hi_chi2_threshold;
+  d.ransac_p = cfg->ransac_p;
+  d.linearity_threshold = cfg->linearity_threshold;
+  d.rho_0 = cfg->rho_0; d.sigma_rho_0 = cfg->sigma_rho_0;
+  d.ncc_threshold = (float)cfg->ncc_threshold; d.search_clamp = (float)cfg->search_clamp;
+  d.sigma_size_f = (float)cfg->sigma_size; d.quality_ratio = (float)cfg->quality_ratio;
+  d.window = cfg->window_size; d.sigma_pixel = cfg->sigma_pixel; d.nhyp0 = cfg->ransac_nhyp0;
+  d.forsePlane = cfg->forsePlane; d.abs_int_quirk = cfg->abs_int_quirk;
+  // initial state (vslamRansac.cpp:163-216)
+  double mu0[EKF_CAM] = {0};
+  mu0[3] = 0.0; mu0[4] = 0.0; mu0[5] = -0.707106781; mu0[6] = 0.707106781; mu0[13] = 1;
+  std::vector<double> S0((size_t)EKF_CAM * EKF_CAM, 0.0);
+  for (int i = 0; i < EKF_CAM; ++i) S0[i * EKF_CAM + i] = 0.0000000004 * 1.0;
+  S0[13 * EKF_CAM + 13] = 0.09;
+  const double svv = 0.0004, sww = 0.0004;
+  for (int i = 0; i < 3; ++i) { S0[(7 + i) * EKF_CAM + 7 + i] = svv * svv * 1.0; S0[(10 + i) * EKF_CAM + 10 + i] = sww * sww * 1.0; }
+  TRY(cudaMemcpyAsync(h->mu, mu0, sizeof mu0, cudaMemcpyHostToDevice, h->stream))
+  TRY(cudaMemcpy2DAsync(h->Sigma, sizeof(double) * h->ld, S0.data(), sizeof(double) * EKF_CAM, sizeof(double) * EKF_CAM, EKF_CAM,
+                        cudaMemcpyHostToDevice, h->stream))
+  TRY(cudaStreamSynchronize(h->stream))
+#undef TRY
+  h->n = EKF_CAM; h->N = 0;
+  *out = h;
+  return EKF_OK;
+}
+
+int ekf_set_stream(ekf_handle* h, void* s) {
+  if (!h) return EKF_ERR_ARG;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->stream = s ? (cudaStream_t)s : h->own_stream;
+  return EKF_OK;
+}
+int ekf_sync(ekf_handle* h) {
+  if (!h) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return EKF_OK;
+}
+
+static int capture_common(ekf_handle* h, const uint8_t* gray, int width, int height, int stride, double stamp, bool device_src) {
+  if (!h || !gray || width < 8 || height < 8 || stride < width) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  if (stamp >= 0) {  // captureNewFrame(Mat, double), vslamRansac.cpp:226-233
+    if (h->old_ts > 0) h->dT = (stamp - h->old_ts);
+    h->old_ts = stamp;
+  }
+  const int dstride = (width + 15) & ~15;
+  const size_t need = (size_t)dstride * height;
+  if (need > h->frame_cap) {
+    EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->frame);
+    h->frame = nullptr;
+    EKF_CUDA_CHECK(cudaMalloc((void**)&h->frame, need));
+    h->frame_cap = need;
+  }
+  EKF_CUDA_CHECK(cudaMemcpy2DAsync(h->frame, dstride, gray, stride, width, height,
+                                   device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  h->fv = FrameView{h->frame, width, height, dstride};
+  h->have_frame = true;
+  return EKF_OK;
+}
+int ekf_capture_frame(ekf_handle* h, const uint8_t* gray, int width, int height, int stride, double stamp) {
+  return capture_common(h, gray, width, height, stride, stamp, false);
+}
+int ekf_capture_frame_device(ekf_handle* h, const uint8_t* gray, int width, int height, int stride, double stamp) {
+  return capture_common(h, gray, width, height, stride, stamp, true);
+}
+
+int ekf_predict(ekf_handle* h, const double dv[3], const double dw[3], int vcontrol) {
+  if (!h) return EKF_ERR_ARG;
+  if (!h->have_frame) return ekf_fail(h, EKF_ERR_STATE, "predict before captureNewFrame");
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  const double z3[3] = {0, 0, 0};
+  if (vcontrol) h->noise_cov_factor = 0; else h->noise_cov_factor++;
+  launch_predict(h->stream, h->Sigma, h->ld, h->n, h->mu, h->ft, h->N, h->fv, h->ctl, h->dcfg, h->dT, dv ? dv : z3, dw ? dw : z3,
+                 vcontrol, &h->launches);
+  EKF_CUDA_CHECK(cudaGetLastError());
+  h->predicted = true;
+  h->cache_ok = false;
+  return EKF_OK;
+}
+
+static int refresh_cache(ekf_handle* h) {
+  if (h->cache_ok) return EKF_OK;
+  const int N = h->N;
+  auto get = [&](auto& vec, const auto* src, size_t cnt) -> cudaError_t {
+    vec.resize(cnt);
+    if (cnt == 0) return cudaSuccess;
+    return cudaMemcpyAsync(vec.data(), src, cnt * sizeof(vec[0]), cudaMemcpyDeviceToHost, h->stream);
+  };
+  EKF_CUDA_CHECK(get(h->c_pos, h->ft.pos, N)); EKF_CUDA_CHECK(get(h->c_coding, h->ft.coding, N));
+  EKF_CUDA_CHECK(get(h->c_innov, h->ft.innov, N)); EKF_CUDA_CHECK(get(h->c_li, h->ft.li, N));
+  EKF_CUDA_CHECK(get(h->c_hi, h->ft.hi, N)); EKF_CUDA_CHECK(get(h->c_removef, h->ft.removef, N));
+  EKF_CUDA_CHECK(get(h->c_ntot, h->ft.n_tot, N)); EKF_CUDA_CHECK(get(h->c_nfind, h->ft.n_find, N));
+  EKF_CUDA_CHECK(get(h->c_real, h->ft.real_index, N)); EKF_CUDA_CHECK(get(h->c_posz, h->ft.pos_in_z, N));
+  EKF_CUDA_CHECK(get(h->c_center, h->ft.center, 2 * (size_t)N)); EKF_CUDA_CHECK(get(h->c_quality, h->ft.quality, N));
+  EKF_CUDA_CHECK(get(h->c_ncc, h->ft.last_ncc, N)); EKF_CUDA_CHECK(get(h->c_z, h->ft.z, 2 * (size_t)N));
+  EKF_CUDA_CHECK(get(h->c_h, h->ft.h, 2 * (size_t)N)); EKF_CUDA_CHECK(get(h->c_Hc, h->ft.Hc, 26 * (size_t)N));
+  EKF_CUDA_CHECK(get(h->c_S2, h->ft.S2, 4 * (size_t)N));
+  EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->cache_ok = true;
+  return EKF_OK;
+}
+
+int ekf_match(ekf_handle* h, int* n_matched) {
+  if (!h) return EKF_ERR_ARG;
+  if (!h->predicted) return ekf_fail(h, EKF_ERR_STATE, "match before predict");
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  launch_match_filter(h->stream, h->ft, h->N, h->fv, h->dcfg, &h->launches);
+  EKF_CUDA_CHECK(cudaGetLastError());
+  h->cache_ok = false;
+  if (n_matched) {
+    int rc = refresh_cache(h);
+    if (rc) return rc;
+    int c = 0;
+    for (int i = 0; i < h->N; ++i) c += h->c_innov[i] ? 1 : 0;
+    *n_matched = c;
+  }
+  return EKF_OK;
+}
+
+// removeFeature for a set of feature indices at once (vslamRansac.cpp:373-421; order-independent).
+static int remove_features(ekf_handle* h, const std::vector<int>& victims) {
+  if (victims.empty()) return EKF_OK;
+  int rc = refresh_cache(h);
+  if (rc) return rc;
+  std::vector<char> dead(h->N, 0);
+  for (int v : victims) {
+    if (v < 0 || v >= h->N) return EKF_ERR_ARG;
+    dead[v] = 1;
+  }
+  // archive good XYZ features (V:394-404)
+  for (int v = 0; v < h->N; ++v) {
+    if (!dead[v] || !(h->c_nfind[v] > 5 && h->m_coding[v] == 1)) continue;
+    DeletedPatch dp;
+    dp.real_index = h->c_real[v];
+    const int pos = h->m_pos[v];
+    EKF_CUDA_CHECK(cudaMemcpyAsync(dp.XYZ_pos, h->mu + pos, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    double blk[9];
+    EKF_CUDA_CHECK(cudaMemcpy2DAsync(blk, 3 * sizeof(double), h->Sigma + (size_t)pos * h->ld + pos, h->ld * sizeof(double),
+                                     3 * sizeof(double), 3, cudaMemcpyDeviceToHost, h->stream));
+    EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    for (int c = 0; c < 3; ++c)
+      for (int r = 0; r < 3; ++r) dp.cov_4_delete[c * 3 + r] = blk[c * 3 + r];
+    h->deleted.push_back(dp);
+  }
+  std::vector<int> keep, newpos, map;
+  for (int i = 0; i < EKF_CAM; ++i) map.push_back(i);
+  std::vector<int> npos2, ncod2;
+  for (int f = 0; f < h->N; ++f) {
+    if (dead[f]) continue;
+    const int fs = h->m_coding[f] ? 3 : 6;
+    keep.push_back(f);
+    newpos.push_back((int)map.size());
+    npos2.push_back((int)map.size());
+    ncod2.push_back(h->m_coding[f]);
+    for (int c = 0; c < fs; ++c) map.push_back(h->m_pos[f] + c);
+  }
+  const int n2 = (int)map.size(), N2 = (int)keep.size();
+  EKF_CUDA_CHECK(cudaMemcpyAsync(h->map_dev, map.data(), sizeof(int) * n2, cudaMemcpyHostToDevice, h->stream));
+  if (N2 > 0) {
+    EKF_CUDA_CHECK(cudaMemcpyAsync(h->keep_dev, keep.data(), sizeof(int) * N2, cudaMemcpyHostToDevice, h->stream));
+    EKF_CUDA_CHECK(cudaMemcpyAsync(h->newpos_dev, newpos.data(), sizeof(int) * N2, cudaMemcpyHostToDevice, h->stream));
+  }
+  launch_gather_state(h->stream, h->Sigma, h->SigmaB, h->ld, h->mu, h->muB, n2, h->map_dev, &h->launches);
+  launch_gather_features(h->stream, h->ft, h->ftB, N2, h->keep_dev, h->newpos_dev, h->cfg.window_size * h->cfg.window_size, &h->launches);
+  EKF_CUDA_CHECK(cudaGetLastError());
+  EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));  // host vectors above go out of scope
+  std::swap(h->Sigma, h->SigmaB);
+  std::swap(h->mu, h->muB);
+  std::swap(h->ft, h->ftB);
+  h->n = n2; h->N = N2;
+  h->m_pos = npos2; h->m_coding = ncod2;
+  h->cache_ok = false;
+  return EKF_OK;
+}
+
+int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
+  if (!h || n_picks < 0 || (n_picks > 0 && !picks)) return EKF_ERR_ARG;
+  if (!h->predicted) return ekf_fail(h, EKF_ERR_STATE, "update before predict");
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  if (n_picks > h->picks_cap) {
+    EKF_CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(h->picks_dev);
+    h->picks_dev = nullptr;
+    EKF_CUDA_CHECK(cudaMalloc((void**)&h->picks_dev, sizeof(uint32_t) * n_picks));
+    h->picks_cap = n_picks;
+  }
+  if (n_picks > 0) EKF_CUDA_CHECK(cudaMemcpyAsync(h->picks_dev, picks, sizeof(uint32_t) * n_picks, cudaMemcpyHostToDevice, st));
+  DevCtl hc;
+  // 1-point RANSAC, then the low-innovation update
+  launch_ransac(st, h->Sigma, h->ld, h->n, h->mu, h->ft, h->N, h->ctl, h->dcfg, h->picks_dev, n_picks, h->mu_i, h->cand, &h->launches);
+  EKF_CUDA_CHECK(cudaMemcpyAsync(&hc, h->ctl, sizeof hc, cudaMemcpyDeviceToHost, st));
+  EKF_CUDA_CHECK(cudaStreamSynchronize(st));
+  const int n_li = hc.n_li;
+  if (n_li > 0) {
+    int rc = launch_stacked_update(st, h->Sigma, h->ld, h->n, h->mu, h->ft, n_li, h->ctl, h->dcfg, h->W, h->nu, h->Lb, h->Dinv,
+                                   h->yb, h->delta, h->lower_only, &h->launches);
+    if (rc) return ekf_fail_cuda(h, (cudaError_t)rc, "stacked update (li)", __FILE__, __LINE__);
+    launch_quat_normalize(st, h->Sigma, h->ld, h->n, h->mu, h->ctl, &h->launches);
+  }
+  // high-innovation rescue and second update
+  launch_hi_rescue(st, h->Sigma, h->ld, h->mu, h->ft, h->N, h->ctl, h->dcfg, &h->launches);
+  EKF_CUDA_CHECK(cudaMemcpyAsync(&hc, h->ctl, sizeof hc, cudaMemcpyDeviceToHost, st));
+  EKF_CUDA_CHECK(cudaStreamSynchronize(st));
+  const int n_hi = hc.n_hi;
+  if (n_hi > 0) {
+    int rc = launch_stacked_update(st, h->Sigma, h->ld, h->n, h->mu, h->ft, n_hi, h->ctl, h->dcfg, h->W, h->nu, h->Lb, h->Dinv,
+                                   h->yb, h->delta, h->lower_only, &h->launches);
+    if (rc) return ekf_fail_cuda(h, (cudaError_t)rc, "stacked update (hi)", __FILE__, __LINE__);
+    launch_quat_normalize(st, h->Sigma, h->ld, h->n, h->mu, h->ctl, &h->launches);
+  }
+  // book-keeping + packed result record
+  int* outi_dev = reinterpret_cast<int*>(h->out_dev + 210);
+  launch_bookkeeping(st, h->Sigma, h->ld, h->mu, h->ft, h->N, h->ctl, h->dcfg, h->out_dev, outi_dev, &h->launches);
+  EKF_CUDA_CHECK(cudaGetLastError());
+  const size_t bytes = sizeof(double) * 210 + sizeof(int) * (16 + 3 * (size_t)h->N);
+  EKF_CUDA_CHECK(cudaMemcpyAsync(h->out_host, h->out_dev, bytes, cudaMemcpyDeviceToHost, st));
+  EKF_CUDA_CHECK(cudaStreamSynchronize(st));
+  const int* outi = reinterpret_cast<const int*>(h->out_host + 210);
+  h->stats.n_in_innovation_predict = outi[0];
+  h->stats.n_matched = outi[1];
+  h->stats.n_li = n_li;
+  h->stats.n_hi = n_hi;
+  h->stats.ransac_hypotheses = outi[4];
+  h->stats.blur_requests = 0;
+  if (outi[5]) return ekf_fail(h, EKF_ERR_STATE, "innovation covariance not positive definite");
+  h->cache_ok = false;
+  // delete flagged features (V:1296-1299), then the visibility top-up hook (V:1301-1315)
+  std::vector<int> victims;
+  const int N = h->N;
+  for (int i = 0; i < N; ++i)
+    if (outi[16 + i] & 8) victims.push_back(i);
+  int nvis = 0;
+  for (int i = 0; i < N; ++i)
+    if ((outi[16 + i] & 1) && !(outi[16 + i] & 8)) nvis++;
+  h->stats.n_removed = (int)victims.size();
+  int rc = remove_features(h, victims);
+  if (rc) return rc;
+  h->stats.topup_request = 0;
+  if (nvis < h->cfg.min_features) {
+    if (h->N > h->cfg.max_features) {
+      rc = remove_features(h, std::vector<int>{0});
+      if (rc) return rc;
+      h->stats.n_removed += 1;
+    }
+    h->stats.topup_request = h->cfg.min_features - nvis;  // findNewFeatures(...) is the caller's job
+  }
+  h->stats.kernel_launches = h->launches;
+  h->predicted = false;
+  return EKF_OK;
+}
+
+int ekf_update(ekf_handle* h, const uint32_t* picks, int n_picks) {
+  int rc = ekf_match(h, nullptr);
+  if (rc) return rc;
+  return ekf_update_after_match(h, picks, n_picks);
+}
+
+int ekf_inject_match(ekf_handle* h, int idx, double zu, double zv, int accepted) {
+  if (!h || idx < 0 || idx >= h->N) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  const int one = accepted ? 1 : 0, zero = 0;
+  const double z[2] = {zu, zv};
+  const float c[2] = {accepted ? (float)zu : -1.0f, accepted ? (float)zv : -1.0f};
+  cudaStream_t st = h->stream;
+  EKF_CUDA_CHECK(cudaMemcpyAsync(h->ft.innov + idx, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+  EKF_CUDA_CHECK(cudaMemcpyAsync(h->ft.li + idx, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+  EKF_CUDA_CHECK(cudaMemcpyAsync(h->ft.hi + idx, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+  if (accepted) EKF_CUDA_CHECK(cudaMemcpyAsync(h->ft.z + 2 * idx, z, sizeof z, cudaMemcpyHostToDevice, st));
+  EKF_CUDA_CHECK(cudaMemcpyAsync(h->ft.center + 2 * idx, c, sizeof c, cudaMemcpyHostToDevice, st));
+  EKF_CUDA_CHECK(cudaStreamSynchronize(st));
+  h->cache_ok = false;
+  return EKF_OK;
+}
+
+int ekf_add_feature(ekf_handle* h, float u, float v) {
+  if (!h) return EKF_ERR_ARG;
+  if (!h->have_frame) return ekf_fail(h, EKF_ERR_STATE, "addFeature before captureNewFrame");
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  const int half = h->cfg.window_size / 2;
+  // isInsideImage (vslamRansac.cpp:314,1644-1652); in the fp64 build hd is (double)pf
+  const double x = (double)u, y = (double)v;
+  if (!(x > half && y > half && x < h->fv.w - half && y < h->fv.h - half)) return 0;
+  if (h->N >= h->Ncap || h->n + 6 > h->ncap) return ekf_fail(h, EKF_ERR_CAPACITY, "feature capacity exceeded");
+  launch_add_feature(h->stream, h->Sigma, h->ld, h->n, h->mu, h->ft, h->N, h->fv, h->dcfg, u, v, h->patchnumbre, &h->launches);
+  EKF_CUDA_CHECK(cudaGetLastError());
+  h->m_pos.push_back(h->n);
+  h->m_coding.push_back(0);
+  h->patchnumbre += 1;
+  h->N += 1;
+  h->n += 6;
+  h->cache_ok = false;
+  return 1;
+}
+
+int ekf_remove_feature(ekf_handle* h, int index) {
+  if (!h || index < 0 || index >= h->N) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  return remove_features(h, std::vector<int>{index});
+}
+
+int ekf_convert2xyz_if_linear(ekf_handle* h, int) { return ekf_fail(h, EKF_ERR_UNSUPPORTED, "convert2XYZ_ifLinear: SURVEY.md 8(f) next row"); }
+int ekf_convert2xyz_if_linear_all(ekf_handle* h) { return ekf_fail(h, EKF_ERR_UNSUPPORTED, "convert2XYZ_ifLinearAll: SURVEY.md 8(f) next row"); }
+
+int ekf_num_features(const ekf_handle* h) { return h ? h->N : EKF_ERR_ARG; }
+int ekf_state_dim(const ekf_handle* h) { return h ? h->n : EKF_ERR_ARG; }
+double ekf_get_dt(const ekf_handle* h) { return h ? h->dT : 0.0; }
+
+int ekf_get_state(ekf_handle* h, double out[EKF_STATE_DIM]) {
+  if (!h || !out) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  EKF_CUDA_CHECK(cudaMemcpyAsync(out, h->mu, sizeof(double) * EKF_CAM, cudaMemcpyDeviceToHost, h->stream));
+  EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return EKF_OK;
+}
+int ekf_get_sigma(ekf_handle* h, double out[EKF_STATE_DIM * EKF_STATE_DIM]) {
+  if (!h || !out) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  EKF_CUDA_CHECK(cudaMemcpy2DAsync(out, sizeof(double) * EKF_CAM, h->Sigma, sizeof(double) * h->ld, sizeof(double) * EKF_CAM, EKF_CAM,
+                                   cudaMemcpyDeviceToHost, h->stream));
+  EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return EKF_OK;
+}
+int ekf_covariance_parameter(ekf_handle* h, double* out) {
+  if (!h || !out) return EKF_ERR_ARG;
+  double S[EKF_CAM * EKF_CAM];
+  int rc = ekf_get_sigma(h, S);
+  if (rc) return rc;
+  double P = 0;  // vslamRansac.cpp:854-855
+  P += S[0 * 14 + 0] + S[1 * 14 + 1] + S[2 * 14 + 2];
+  P += S[4 * 14 + 4] + S[5 * 14 + 5] + S[6 * 14 + 6] + S[3 * 14 + 3];
+  *out = P;
+  return EKF_OK;
+}
+int ekf_get_center(ekf_handle* h, int idx, float out[2]) {
+  if (!h || !out || idx < 0 || idx >= h->N) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  int rc = refresh_cache(h);
+  if (rc) return rc;
+  out[0] = h->c_center[2 * idx]; out[1] = h->c_center[2 * idx + 1];
+  return EKF_OK;
+}
+int ekf_get_feature(ekf_handle* h, int idx, ekf_feature_info* o) {
+  if (!h || !o || idx < 0 || idx >= h->N) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  int rc = refresh_cache(h);
+  if (rc) return rc;
+  memset(o, 0, sizeof *o);
+  const int pos = h->c_pos[idx], fs = h->c_coding[idx] ? 3 : 6;
+  o->position_in_state = pos; o->position_in_z = h->c_posz[idx]; o->coding = h->c_coding[idx];
+  o->n_tot = h->c_ntot[idx]; o->n_find = h->c_nfind[idx]; o->real_index = h->c_real[idx];
+  o->is_in_innovation = h->c_innov[idx]; o->is_in_li = h->c_li[idx]; o->is_in_hi = h->c_hi[idx]; o->remove_flag = h->c_removef[idx];
+  o->center[0] = h->c_center[2 * idx]; o->center[1] = h->c_center[2 * idx + 1];
+  o->quality_index = h->c_quality[idx]; o->last_ncc = h->c_ncc[idx];
+  for (int a = 0; a < 2; ++a) { o->z[a] = h->c_z[2 * idx + a]; o->h[a] = h->c_h[2 * idx + a]; }
+  for (int a = 0; a < 26; ++a) o->H[a] = h->c_Hc[26 * idx + a];
+  EKF_CUDA_CHECK(cudaMemcpyAsync(o->state, h->mu + pos, sizeof(double) * fs, cudaMemcpyDeviceToHost, h->stream));
+  double blk[36];
+  EKF_CUDA_CHECK(cudaMemcpy2DAsync(blk, sizeof(double) * fs, h->Sigma + (size_t)pos * h->ld + pos, sizeof(double) * h->ld,
+                                   sizeof(double) * fs, fs, cudaMemcpyDeviceToHost, h->stream));
+  EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  for (int a = 0; a < fs; ++a)
+    for (int b = 0; b < fs; ++b) o->cov[a * 6 + b] = blk[a * fs + b];
+  return EKF_OK;
+}
+int ekf_get_template(ekf_handle* h, int idx, int which, uint8_t* out) {
+  if (!h || !out || idx < 0 || idx >= h->N) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  const int w2 = h->cfg.window_size * h->cfg.window_size;
+  const uint8_t* src = (which ? h->ft.mpatch : h->ft.patch) + (size_t)idx * w2;
+  EKF_CUDA_CHECK(cudaMemcpyAsync(out, src, w2, cudaMemcpyDeviceToHost, h->stream));
+  EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return EKF_OK;
+}
+int ekf_get_step_stats(ekf_handle* h, ekf_step_stats* out) {
+  if (!h || !out) return EKF_ERR_ARG;
+  h->stats.kernel_launches = h->launches;
+  *out = h->stats;
+  return EKF_OK;
+}
+int ekf_get_full(ekf_handle* h, double* mu, double* sigma, int ld) {
+  if (!h || !mu || (sigma && ld < h->n)) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  EKF_CUDA_CHECK(cudaMemcpyAsync(mu, h->mu, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
+  if (sigma)
+    EKF_CUDA_CHECK(cudaMemcpy2DAsync(sigma, sizeof(double) * ld, h->Sigma, sizeof(double) * h->ld, sizeof(double) * h->n, h->n,
+                                     cudaMemcpyDeviceToHost, h->stream));
+  EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return EKF_OK;
+}
+int ekf_set_full(ekf_handle* h, const double* mu, const double* sigma, int ld) {
+  if (!h || !mu || !sigma || ld < h->n) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  EKF_CUDA_CHECK(cudaMemcpyAsync(h->mu, mu, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
+  EKF_CUDA_CHECK(cudaMemcpy2DAsync(h->Sigma, sizeof(double) * h->ld, sigma, sizeof(double) * ld, sizeof(double) * h->n, h->n,
+                                   cudaMemcpyHostToDevice, h->stream));
+  EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return EKF_OK;
+}
+int ekf_get_S_blocks(ekf_handle* h, double* out) {
+  if (!h || !out) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  int rc = refresh_cache(h);
+  if (rc) return rc;
+  for (int i = 0; i < h->N; ++i)
+    for (int c = 0; c < 4; ++c) out[4 * i + c] = h->c_innov[i] ? h->c_S2[4 * i + c] : 0.0;
+  return EKF_OK;
+}
+
+int ekf_match_batch(const uint8_t* frames, int n_frames, int width, int height, int stride, const uint8_t* templates,
+                    int features_per_frame, int window_size, const double* hh, const double* S, float sigma_size,
+                    float ncc_threshold, float search_clamp, int32_t* out_uv, float* out_score, void* stream) {
+  if (!frames || !templates || !hh || !S || !out_uv || !out_score || n_frames < 0 || features_per_frame < 0) return EKF_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return EKF_ERR_CUDA;
+  const int rc = launch_match_batch((cudaStream_t)stream, frames, n_frames, width, height, stride, templates, features_per_frame,
+                                    window_size, hh, S, sigma_size, ncc_threshold, search_clamp, out_uv, out_score);
+  if (rc < 0) return EKF_ERR_UNSUPPORTED;
+  return cudaGetLastError() == cudaSuccess ? EKF_OK : EKF_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,124 @@
+// csrc/ekf_common.cuh — device-side data layout shared by all kernels of libekf_b200.
+//
+// HBM layout of one filter (all fp64 unless noted):
+//   mu      [n_cap]            state vector, reference order (vslamRansac.hpp:27-92)
+//   Sigma   [n_cap x ld]       covariance, ROW-major, ld = n_cap rounded up to 8 doubles (64 B rows)
+//   SigmaB  [n_cap x ld]       second buffer; removeFeature compacts into it and swaps
+//   W       [(n_cap+1) x ldw]  W = Sigma H^T (n x k), then V = W L^-T in place; row n holds z-h
+//   Sm      [k_cap x lds]      innovation covariance S, then its Cholesky factor L (lower)
+//   feature table (SoA, capacity N_cap): pos, coding, flags, counters, h, z, compact H (2 x 13),
+//           2x2 S blocks, u8 templates (patch / matching_patch)
+//   frame   [h x stride] u8
+// Sizes known only on the device (matched rows, inlier counts ...) live in DevCtl; every kernel
+// downstream reads them there and exits early, so a whole step is enqueued without host syncs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define EKF_CAM 14  // STATE_DIM (vslamRansac.cpp:22)
+
+struct CamParams {
+  double fx, fy, u0, v0, k1, k2, k3, p1, p2;
+};
+
+// Scalars of ekf_config the kernels need.
+struct DevCfg {
+  CamParams cam;
+  double Vmax[6];  // diag(sigma_v^2, sigma_w^2) (vslamRansac.cpp:194-200)
+  double sigma_pixel_2;
+  double th_low;       // li_threshold_factor * sigma_pixel (vslamRansac.cpp:968)
+  double th_hi;        // vslamRansac.cpp:1066
+  double ransac_p;
+  double linearity_threshold;
+  double rho_0, sigma_rho_0;
+  float ncc_threshold, search_clamp, sigma_size_f, quality_ratio;
+  int window, sigma_pixel, nhyp0, forsePlane, abs_int_quirk;
+};
+
+// Device-resident control block.
+struct DevCtl {
+  double mu_cam_new[13];  // Predict_State output, committed by k_predict_features
+  double cam_old[7];      // r,q of mu before the low-innovation update (vslamRansac.cpp:1069-1072)
+  int m_innov;            // features in innovation after predict
+  int n_matched;          // after matching (vslamRansac.cpp:984)
+  int n_li, n_hi;
+  int k_rows;             // rows of the stacked update being processed
+  int ransac_hyps;
+  int n_visible;          // vslamRansac.cpp:1301-1303
+  int n_remove;           // features flagged by update_quality_index / rho <= 0
+  unsigned int ticket;    // last-block-done counter (self-resetting)
+  int chol_fail;          // non-positive pivot seen
+  int pad[2];
+};
+
+// Feature table (structure of arrays, device pointers).
+struct FeatTab {
+  int* pos;         // position_in_state
+  int* coding;      // 0 inverse depth, 1 XYZ
+  int* innov;       // isInInnovation
+  int* li;          // isInLi
+  int* hi;          // isInHi
+  int* removef;     // removeFlag
+  int* n_tot;
+  int* n_find;
+  int* real_index;
+  int* pos_in_z;
+  int* sel;         // compacted list of selected features (innovation / Li / Hi), in patch order
+  float* center;    // 2 per feature
+  float* quality;
+  float* last_ncc;
+  double* z;        // 2 per feature
+  double* h;        // 2 per feature
+  double* Hc;       // 26 per feature: 2 x 13 row-major, cols [0,7) camera, [7,13) feature
+  double* S2;       // 4 per feature: 2x2 block of St
+  uint8_t* patch;   // w*w per feature
+  uint8_t* mpatch;  // w*w per feature (matching_patch)
+};
+
+struct FrameView {
+  const uint8_t* px;
+  int w, h, stride;
+};
+
+#define EKF_CUDA_CHECK(expr)                                                     \
+  do {                                                                           \
+    cudaError_t _e = (expr);                                                     \
+    if (_e != cudaSuccess) return ekf_fail_cuda(h, _e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+// 13-entry index list of the state entries a feature's measurement depends on:
+// camera r,q (0..6) and the feature block.  XYZ features use 10 entries.
+__device__ __forceinline__ int ekf_idx13(int c, int pos) { return c < 7 ? c : pos + (c - 7); }
+
+// Ordered compaction of flag[0..N) into list / pos_in_z by ONE block (blockDim multiple of 32).
+// Returns the count to every thread.  list may be null.
+static __device__ __noinline__ int block_compact(const int* flag, int N, int* list, int* pos_in_z) {
+  __shared__ int warp_cnt[32];
+  __shared__ int base_s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  for (int start = 0; start < N; start += blockDim.x) {
+    const int i = start + threadIdx.x;
+    const int f = (i < N) ? (flag[i] != 0) : 0;
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) warp_cnt[wid] = __popc(m);
+    __syncthreads();
+    int off = base_s;
+    for (int w = 0; w < wid; ++w) off += warp_cnt[w];
+    off += __popc(m & ((1u << lane) - 1u));
+    if (f) {
+      if (list) list[off] = i;
+      if (pos_in_z) pos_in_z[i] = 2 * off;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < nw; ++w) tot += warp_cnt[w];
+      base_s += tot;
+    }
+    __syncthreads();
+  }
+  return base_s;
+}
+

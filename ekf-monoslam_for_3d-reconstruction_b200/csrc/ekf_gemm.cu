@@ -1,0 +1,149 @@
+// csrc/ekf_gemm.cu — K4d: covariance downdate  Sigma <- Sigma - V V^T  on the fp64 tensor pipe.
+//
+// the reference forms (I - K H) Sigma as a dense n x n x n product
+// (vslamRansac.cpp:1060,1279).  With V = W L^-T (W = Sigma H^T, S = L L^T) the same update is the
+// rank-k downdate Sigma - V V^T: 2 n^2 k flops, read + write of Sigma (16 n^2 bytes).
+//
+// sm_100a has no tcgen05 kind for fp64; the fp64 tensor path is mma.sync.m8n8k4.f64 (SASS
+// DMMA.8x8x4).  Kernel shape: 128 x 128 output tile per CTA, 8 warps (2 x 4), each warp a 64 x 32
+// sub-tile = 8 x 4 DMMA tiles (64 accumulator doubles per thread); K is consumed in 16-wide slabs
+// staged global -> shared with cp.async (3 stages), rows padded to 20 doubles so the 8-row x 4-col
+// fragment reads are bank-conflict free (row*20 mod 16 covers 0,4,8,12).
+#include "ekf_kernels.h"
+
+#define GT_M 128
+#define GT_N 128
+#define GT_K 16
+#define GT_LD 20
+#define GT_STAGES 3
+#define GT_THREADS 256
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// C[M x N] (ldc) -= A[M x K] (lda, K contiguous) * B[N x K]^T (ldb, K contiguous).
+// K is read from *kdev when kdev != nullptr (device-known row count), else from kconst; it must be
+// a multiple of 2 and the buffers must be readable (zero padded) up to the next multiple of GT_K.
+// lower_only: skip tiles strictly above the diagonal and mirror the strictly-lower tiles into the
+// upper triangle (C symmetric on input => symmetric on output).
+__global__ void __launch_bounds__(GT_THREADS, 1)
+k_gemm_nt_sub(double* __restrict__ C, int ldc, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+              int M, int N, int kconst, const int* __restrict__ kdev, int lower_only) {
+  extern __shared__ __align__(16) double gsm[];
+  const int K = kdev ? *kdev : kconst;
+  if (K <= 0) return;
+  const int tm = blockIdx.y, tn = blockIdx.x;
+  if (lower_only && tn > tm) return;
+  const int m0 = tm * GT_M, n0 = tn * GT_N;
+  double* As = gsm;                                   // [stages][128][20]
+  double* Bs = gsm + GT_STAGES * GT_M * GT_LD;        // [stages][128][20]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;            // 2 x 4 warps
+  const int g = lane >> 2, t4 = lane & 3;
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+  const int ktiles = (K + GT_K - 1) / GT_K;
+  auto load_stage = [&](int kt, int stage) {
+    const int k0 = kt * GT_K;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int chunk = tid + it * GT_THREADS;       // 0..1023
+      const int row = chunk >> 3, cc = (chunk & 7) * 2;
+      {
+        const int gr = m0 + row;
+        const bool ok = (gr < M) && (k0 + cc < K);
+        const double* src = A + (size_t)(ok ? gr : 0) * lda + (ok ? k0 + cc : 0);
+        cp_async16(As + ((size_t)stage * GT_M + row) * GT_LD + cc, src, ok ? 16 : 0);
+      }
+      {
+        const int gr = n0 + row;
+        const bool ok = (gr < N) && (k0 + cc < K);
+        const double* src = B + (size_t)(ok ? gr : 0) * ldb + (ok ? k0 + cc : 0);
+        cp_async16(Bs + ((size_t)stage * GT_N + row) * GT_LD + cc, src, ok ? 16 : 0);
+      }
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < GT_STAGES - 1; ++s) {
+    if (s < ktiles) load_stage(s, s);
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < ktiles; ++kt) {
+    cp_async_wait<GT_STAGES - 2>();
+    __syncthreads();
+    const int nk = kt + GT_STAGES - 1;
+    if (nk < ktiles) load_stage(nk, nk % GT_STAGES);
+    cp_async_commit();
+    const double* as = As + (size_t)(kt % GT_STAGES) * GT_M * GT_LD + (size_t)(wm * 64 + g) * GT_LD + t4;
+    const double* bs = Bs + (size_t)(kt % GT_STAGES) * GT_N * GT_LD + (size_t)(wn * 32 + g) * GT_LD + t4;
+#pragma unroll
+    for (int k4 = 0; k4 < GT_K / 4; ++k4) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) af[i] = as[(size_t)i * 8 * GT_LD + k4 * 4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = bs[(size_t)j * 8 * GT_LD + k4 * 4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+  // epilogue: C -= acc.  Thread holds rows g (+8 i), column pairs 2*t4 (+8 j).
+  const bool mirror = lower_only && (tn < tm);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = m0 + wm * 64 + i * 8 + g;
+    if (r >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = n0 + wn * 32 + j * 8 + 2 * t4;
+      if (c >= N) continue;
+      double* p = C + (size_t)r * ldc + c;
+      if (c + 1 < N) {
+        double2 v = *reinterpret_cast<double2*>(p);
+        v.x -= acc[i][j][0]; v.y -= acc[i][j][1];
+        *reinterpret_cast<double2*>(p) = v;
+        if (mirror) { C[(size_t)c * ldc + r] = v.x; C[(size_t)(c + 1) * ldc + r] = v.y; }
+      } else {
+        const double v = *p - acc[i][j][0];
+        *p = v;
+        if (mirror) C[(size_t)c * ldc + r] = v;
+      }
+    }
+  }
+}
+
+static const size_t kGemmSmem = (size_t)GT_STAGES * (GT_M + GT_N) * GT_LD * sizeof(double);
+
+int launch_gemm_nt_sub(cudaStream_t st, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M, int N,
+                       int kconst, const int* kdev, int lower_only, long long* launches) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_nt_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  if (M <= 0 || N <= 0) return 0;
+  dim3 grid((N + GT_N - 1) / GT_N, (M + GT_M - 1) / GT_M);
+  k_gemm_nt_sub<<<grid, GT_THREADS, kGemmSmem, st>>>(C, ldc, A, lda, B, ldb, M, N, kconst, kdev, lower_only);
+  if (launches) *launches += 1;
+  return 0;
+}

@@ -1,0 +1,36 @@
+// csrc/ekf_kernels.h — host-side launch wrappers of the kernels in ekf_*.cu (internal to libekf_b200).
+#pragma once
+#include "ekf_common.cuh"
+
+#define EKF_UB 128  // rows per update block (64 features): K of the rank-b downdate GEMM
+
+// ekf_predict.cu
+void launch_predict(cudaStream_t st, double* Sigma, int ld, int n, double* mu, FeatTab ft, int N, FrameView fr,
+                    DevCtl* ctl, const DevCfg& cfg, double dT, const double dv[3], const double dw[3], int vcontrol,
+                    long long* launches);
+void launch_quat_normalize(cudaStream_t st, double* Sigma, int ld, int n, double* mu, const DevCtl* ctl, long long* launches);
+void launch_add_feature(cudaStream_t st, double* Sigma, int ld, int n, double* mu, FeatTab ft, int fidx, FrameView fr,
+                        const DevCfg& cfg, float pfx, float pfy, int real_index, long long* launches);
+void launch_gather_state(cudaStream_t st, const double* Ssrc, double* Sdst, int ld, const double* musrc, double* mudst,
+                         int n2, const int* map, long long* launches);
+void launch_gather_features(cudaStream_t st, FeatTab src, FeatTab dst, int N2, const int* keep, const int* newpos, int w2,
+                            long long* launches);
+// ekf_match.cu
+void launch_match_filter(cudaStream_t st, FeatTab ft, int N, FrameView fr, const DevCfg& cfg, long long* launches);
+int launch_match_batch(cudaStream_t st, const uint8_t* frames, int n_frames, int width, int height, int stride,
+                       const uint8_t* templates, int fpf, int w, const double* h, const double* S, float sigma_size,
+                       float thr, float clampv, int32_t* out_uv, float* out_score);
+// ekf_update.cu
+int update_kernels_init();
+void launch_ransac(cudaStream_t st, const double* Sigma, int ld, int n, const double* mu, FeatTab ft, int N, DevCtl* ctl,
+                   const DevCfg& cfg, const uint32_t* picks, int n_picks, double* mu_i, int* cand, long long* launches);
+void launch_hi_rescue(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, DevCtl* ctl,
+                      const DevCfg& cfg, long long* launches);
+int launch_stacked_update(cudaStream_t st, double* Sigma, int ld, int n, double* mu, FeatTab ft, int cnt, DevCtl* ctl,
+                          const DevCfg& cfg, double* W, double* nu, double* Lb, double* Dinv, double* yb, double* delta,
+                          int lower_only, long long* launches);
+void launch_bookkeeping(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, DevCtl* ctl,
+                        const DevCfg& cfg, double* outd, int* outi, long long* launches);
+// ekf_gemm.cu
+int launch_gemm_nt_sub(cudaStream_t st, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M, int N,
+                       int kconst, const int* kdev, int lower_only, long long* launches);

@@ -1,0 +1,416 @@
+// csrc/ekf_predict.cu — K1 (motion model + block covariance propagation), K2 (batched h(x), compact H,
+// gating, 2x2 innovation blocks), K4e (quaternion renormalisation), K6 (add / remove feature edits).
+// SURVEY.md §8(a) rows a3-a10, a16, a21, a22.  Citations V: = mono-slam/src/vslamRansac.cpp.
+#include "ekf_kernels.h"
+#include "ekf_math.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// K1: Sigma <- Fc Sigma Fc^T + Qtot, Fc = I with a 13x13 corner (V:451-480).  Only the 13 camera
+// rows and 13 camera columns change: algorithmic traffic 4*13*n*8 B instead of the dense 4 n^3 flops.
+//   block 0            : 13x13 corner  (F C F^T + Q) and Predict_State -> ctl->mu_cam_new
+//   blocks 1..         : thread j (>= 13): column j of rows 0:13  <- F * Sigma[0:13, j]
+//                                          row j of cols 0:13     <- Sigma[j, 0:13] * F^T
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_predict_cov(double* __restrict__ Sigma, int ld, int n,
+                                                     const double* __restrict__ mu, DevCtl* ctl, DevCfg cfg,
+                                                     double dT, double3 dv, double3 dw, int vcontrol) {
+  __shared__ double F[169];
+  __shared__ double C[169], T[169], Q[169];
+  if (threadIdx.x == 0) {
+    const double ctrl[3] = {dw.x, dw.y, dw.z};
+    double mu13[13];
+    for (int i = 0; i < 13; ++i) mu13[i] = mu[i];
+    d_system_jacobian(mu13, dT, ctrl, F);
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    for (int e = threadIdx.x; e < 169; e += blockDim.x) C[e] = Sigma[(size_t)(e / 13) * ld + (e % 13)];
+    __syncthreads();
+    // Q = (F6 * Vs) * F6^T, Vs = (V/dT)/dT diagonal, F6 = F[:, 7:13] (V:463-473)
+    for (int e = threadIdx.x; e < 169; e += blockDim.x) {
+      const int a = e / 13, b = e % 13;
+      double s = 0;
+      for (int k = 0; k < 6; ++k) {
+        const double vmax = vcontrol ? cfg.Vmax[k] : cfg.Vmax[k] * 2.0;
+        const double vs = (vmax / dT) / dT;
+        // (F6*Vs)[a,k] = sum_c F6[a,c]*Vs[c,k]: only c == k is non-zero (exact zeros elsewhere)
+        s += (F[a * 13 + 7 + k] * vs) * F[b * 13 + 7 + k];
+      }
+      Q[e] = s;
+      double t = 0;
+      for (int k = 0; k < 13; ++k) t += F[a * 13 + k] * C[k * 13 + b];
+      T[e] = t;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 169; e += blockDim.x) {
+      const int a = e / 13, b = e % 13;
+      double s = 0;
+      for (int k = 0; k < 13; ++k) s += T[a * 13 + k] * F[b * 13 + k];
+      Sigma[(size_t)a * ld + b] = s + Q[e];
+    }
+    if (threadIdx.x == 0) {
+      double X[13];
+      for (int i = 0; i < 13; ++i) X[i] = mu[i];
+      const double a[3] = {dv.x, dv.y, dv.z}, b[3] = {dw.x, dw.y, dw.z};
+      d_predict_state(X, a, b, dT);
+      for (int i = 0; i < 13; ++i) ctl->mu_cam_new[i] = X[i];
+    }
+    return;
+  }
+  const int j = 13 + (blockIdx.x - 1) * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double x[13], y[13];
+  // column j of the camera rows (coalesced across threads)
+  for (int c = 0; c < 13; ++c) x[c] = Sigma[(size_t)c * ld + j];
+  for (int a = 0; a < 13; ++a) {
+    double s = 0;
+    for (int c = 0; c < 13; ++c) s += F[a * 13 + c] * x[c];
+    y[a] = s;
+  }
+  for (int a = 0; a < 13; ++a) Sigma[(size_t)a * ld + j] = y[a];
+  // row j of the camera columns
+  double* row = Sigma + (size_t)j * ld;
+  for (int c = 0; c < 13; ++c) x[c] = row[c];
+  for (int a = 0; a < 13; ++a) {
+    double s = 0;
+    for (int c = 0; c < 13; ++c) s += x[c] * F[a * 13 + c];
+    y[a] = s;
+  }
+  for (int a = 0; a < 13; ++a) row[a] = y[a];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: per-feature prediction (V:482-602): rho <= 0 guard, h, compact H, in-image / in-front gate,
+// template reset (Patch::blur with blur disabled, Patch.cpp:50-57), 2x2 diagonal block of
+// St = H Sigma H^T + sigma_px^2 I (the only part of St the reference consumes, V:875), and — by the
+// last block to finish — the ordered compaction that assigns position_in_z (V:584-592).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_predict_features(const double* __restrict__ Sigma, int ld, double* __restrict__ mu,
+                                                          FeatTab ft, int N, FrameView fr, DevCtl* ctl, DevCfg cfg) {
+  __shared__ int is_last;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double cam[13];
+  for (int c = 0; c < 13; ++c) cam[c] = ctl->mu_cam_new[c];
+  int ok = 0;
+  if (i < N) {
+    const int pos = ft.pos[i], coding = ft.coding[i];
+    const int fsz = coding ? 3 : 6;
+    double fs[6];
+    for (int c = 0; c < fsz; ++c) fs[c] = mu[pos + c];
+    bool skip = false;
+    if (!coding && fs[5] <= 0) {  // V:517-522
+      ft.removef[i] = 1;
+      skip = true;
+    }
+    if (!skip) {
+      double qc[4] = {cam[3], -cam[4], -cam[5], -cam[6]}, Rcw[9], hi[2], Hc[26], hcz;
+      d_quat2rot(qc, Rcw);
+      d_feature_hH(cfg.cam, fs, coding, cam, qc, Rcw, hi, Hc, &hcz);
+      const int half = cfg.window / 2;
+      ok = (hi[0] > half && hi[1] > half && hi[0] < fr.w - half && hi[1] < fr.h - half) && (hcz >= 0);  // V:529,1644-1652
+      if (ok) {
+        ft.h[2 * i] = hi[0]; ft.h[2 * i + 1] = hi[1];
+        for (int c = 0; c < 26; ++c) ft.Hc[26 * i + c] = Hc[c];
+        // S block: (Hc * Sigma_sub) * Hc^T + sigma^2 I, Sigma_sub over the 13 (10) dependent states
+        const int nd = 7 + fsz;
+        double Tm[26];
+        for (int b = 0; b < nd; ++b) {
+          const int jb = ekf_idx13(b, pos);
+          double t0 = 0, t1 = 0;
+          for (int c = 0; c < nd; ++c) {
+            const double s = Sigma[(size_t)ekf_idx13(c, pos) * ld + jb];
+            t0 += Hc[c] * s; t1 += Hc[13 + c] * s;
+          }
+          Tm[b] = t0; Tm[13 + b] = t1;
+        }
+        double S[4] = {0, 0, 0, 0};
+        for (int b = 0; b < nd; ++b) {
+          S[0] += Tm[b] * Hc[b]; S[1] += Tm[b] * Hc[13 + b];
+          S[2] += Tm[13 + b] * Hc[b]; S[3] += Tm[13 + b] * Hc[13 + b];
+        }
+        S[0] += cfg.sigma_pixel_2; S[3] += cfg.sigma_pixel_2;
+        for (int c = 0; c < 4; ++c) ft.S2[4 * i + c] = S[c];
+      }
+    }
+    ft.innov[i] = ok; ft.li[i] = 0; ft.hi[i] = 0;  // Patch::setIsInInnovation (Patch.cpp:123-132)
+  }
+  // matching_patch <- patch for gated-in features (Patch.cpp:54-56), cooperative byte copy
+  {
+    __shared__ int okflags[128];
+    okflags[threadIdx.x] = ok;
+    __syncthreads();
+    const int w2 = cfg.window * cfg.window;
+    const int base = blockIdx.x * blockDim.x;
+    for (int e = threadIdx.x; e < (int)blockDim.x * w2; e += blockDim.x) {
+      const int fl = e / w2;
+      if (base + fl < N && okflags[fl]) ft.mpatch[(size_t)(base + fl) * w2 + (e % w2)] = ft.patch[(size_t)(base + fl) * w2 + (e % w2)];
+    }
+  }
+  // last block: commit the predicted camera state and compact
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(&ctl->ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x < 13) mu[threadIdx.x] = cam[threadIdx.x];
+  const int m = block_compact(ft.innov, N, ft.sel, ft.pos_in_z);
+  if (threadIdx.x == 0) {
+    ctl->m_innov = m;
+    ctl->ticket = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4e: normalizeQuaternion (V:1625-1642): q <- q/|q|, Sigma <- Qc Sigma Qc^T with Qc = I except the
+// 4x4 block J = (|q|^2 I - q q^T)/|q|^3 on rows/cols 3:7.  Structured: 4 rows + 4 columns.
+// Runs only when the preceding stacked update had rows (ctl->k_rows > 0), as in the reference.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_quat_normalize(double* __restrict__ Sigma, int ld, int n, double* __restrict__ mu,
+                                                        const DevCtl* ctl) {
+  if (ctl->k_rows <= 0) return;
+  __shared__ double J[16];
+  __shared__ double C[16], T[16];
+  __shared__ double qn[4];
+  if (threadIdx.x == 0) {
+    // every block recomputes J from the pre-normalisation q; block 0 writes the normalised q at the end
+    double q[4];
+    for (int i = 0; i < 4; ++i) q[i] = mu[3 + i];
+    const double norma = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int i = 0; i < 4; ++i) qn[i] = q[i] / norma;
+    const double sc = 1 / (norma * norma * norma);
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) J[i * 4 + j] = ((norma * norma) * (i == j ? 1.0 : 0.0) - q[i] * q[j]) * sc;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < 16) C[threadIdx.x] = Sigma[(size_t)(3 + threadIdx.x / 4) * ld + 3 + (threadIdx.x % 4)];
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      const int a = threadIdx.x / 4, b = threadIdx.x % 4;
+      double t = 0;
+      for (int k = 0; k < 4; ++k) t += J[a * 4 + k] * C[k * 4 + b];
+      T[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      const int a = threadIdx.x / 4, b = threadIdx.x % 4;
+      double s = 0;
+      for (int k = 0; k < 4; ++k) s += T[a * 4 + k] * J[b * 4 + k];
+      Sigma[(size_t)(3 + a) * ld + 3 + b] = s;
+    }
+    return;
+  }
+  // all blocks > 0 read mu[3:7] before block-last writes it: the write happens in a separate tiny
+  // kernel (k_quat_commit) to avoid the race.
+  int j = (blockIdx.x - 1) * blockDim.x + threadIdx.x;  // index over states outside 3..6
+  if (j >= 3) j += 4;
+  if (j >= n) return;
+  double x[4], y[4];
+  for (int c = 0; c < 4; ++c) x[c] = Sigma[(size_t)(3 + c) * ld + j];
+  for (int a = 0; a < 4; ++a) {
+    double s = 0;
+    for (int c = 0; c < 4; ++c) s += J[a * 4 + c] * x[c];
+    y[a] = s;
+  }
+  for (int a = 0; a < 4; ++a) Sigma[(size_t)(3 + a) * ld + j] = y[a];
+  double* row = Sigma + (size_t)j * ld + 3;
+  for (int c = 0; c < 4; ++c) x[c] = row[c];
+  for (int a = 0; a < 4; ++a) {
+    double s = 0;
+    for (int c = 0; c < 4; ++c) s += x[c] * J[a * 4 + c];
+    y[a] = s;
+  }
+  for (int a = 0; a < 4; ++a) row[a] = y[a];
+}
+__global__ void k_quat_commit(double* __restrict__ mu, const DevCtl* ctl) {
+  if (ctl->k_rows <= 0) return;
+  if (threadIdx.x == 0) {
+    double q[4];
+    for (int i = 0; i < 4; ++i) q[i] = mu[3 + i];
+    const double norma = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int i = 0; i < 4; ++i) mu[3 + i] = q[i] / norma;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6a: addFeature (V:309-371).  New state entries and the 6 new rows / columns of
+// Sigma' = Js blkdiag(Sigma, sigma_px^2 I2, sigma_rho_0) Js^T, evaluated in the reference's
+// association (Js*S)*Js^T with the exact-zero terms dropped:
+//   rows  n+a, j<n : sum_{c<7} A[a,c] Sigma[c,j]          cols i<n, n+b : sum_{c<7} Sigma[i,c] A[b,c]
+//   corner         : sum_{c<7} T[a,c] A[b,c] + sum_e (Ap[a,e] s_e) Ap[b,e]
+// A = [I3 0 ; Jf*Jq (rows theta,phi) ; 0], Ap = [Jf*R*J2d | e6].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_add_feature(double* __restrict__ Sigma, int ld, int n, double* __restrict__ mu,
+                                                     FeatTab ft, int fidx, FrameView fr, DevCfg cfg, float pfx, float pfy,
+                                                     int real_index) {
+  __shared__ double A[6 * 7], Ap[6 * 3], fnew[6];
+  if (threadIdx.x == 0) {
+    double r[3] = {mu[0], mu[1], mu[2]}, q[4] = {mu[3], mu[4], mu[5], mu[6]};
+    const double hd[2] = {(double)pfx, (double)pfy};
+    double hC[3], J2d[6], Rot[9], hW[3];
+    d_cam_unproject_J(cfg.cam, hd, hC, J2d);
+    d_quat2rot(q, Rot);
+    for (int i = 0; i < 3; ++i) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += Rot[i * 3 + k] * hC[k];
+      hW[i] = s;
+    }
+    const double hx = hW[0], hy = hW[1], hz = hW[2];
+    fnew[0] = r[0]; fnew[1] = r[1]; fnew[2] = r[2];
+    fnew[3] = atan2(hx, hz);
+    fnew[4] = atan2(-hy, sqrt(hx * hx + hz * hz));
+    fnew[5] = cfg.rho_0;
+    double Jt[3], Jp[3], Jq[12];
+    d_jac_f_hW(hW, Jt, Jp);
+    d_jac_hW_q(q, hC, Jq);
+    for (int i = 0; i < 42; ++i) A[i] = 0;
+    for (int i = 0; i < 18; ++i) Ap[i] = 0;
+    for (int i = 0; i < 3; ++i) A[i * 7 + i] = 1;
+    // (Jf*Jq): rows 3,4 = Jt*Jq, Jp*Jq (other rows are sums of exact zeros)
+    for (int b = 0; b < 4; ++b) {
+      double s3 = 0, s4 = 0;
+      for (int k = 0; k < 3; ++k) { s3 += Jt[k] * Jq[k * 4 + b]; s4 += Jp[k] * Jq[k * 4 + b]; }
+      A[3 * 7 + 3 + b] = s3; A[4 * 7 + 3 + b] = s4;
+    }
+    // (Jf*Rot)*J2d
+    double JR3[3], JR4[3];
+    for (int b = 0; b < 3; ++b) {
+      double s3 = 0, s4 = 0;
+      for (int k = 0; k < 3; ++k) { s3 += Jt[k] * Rot[k * 3 + b]; s4 += Jp[k] * Rot[k * 3 + b]; }
+      JR3[b] = s3; JR4[b] = s4;
+    }
+    for (int b = 0; b < 2; ++b) {
+      double s3 = 0, s4 = 0;
+      for (int k = 0; k < 3; ++k) { s3 += JR3[k] * J2d[k * 2 + b]; s4 += JR4[k] * J2d[k * 2 + b]; }
+      Ap[3 * 3 + b] = s3; Ap[4 * 3 + b] = s4;
+    }
+    Ap[5 * 3 + 2] = 1;
+  }
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    // new rows, column t; new columns, row t
+    double col[7], rowv[7];
+    for (int c = 0; c < 7; ++c) { col[c] = Sigma[(size_t)c * ld + t]; rowv[c] = Sigma[(size_t)t * ld + c]; }
+    for (int a = 0; a < 6; ++a) {
+      double s = 0, u = 0;
+      for (int c = 0; c < 7; ++c) { s += A[a * 7 + c] * col[c]; u += rowv[c] * A[a * 7 + c]; }
+      Sigma[(size_t)(n + a) * ld + t] = s;
+      Sigma[(size_t)t * ld + n + a] = u;
+    }
+  }
+  if (blockIdx.x == 0) {
+    __shared__ double Tc[6 * 7];
+    __syncthreads();
+    for (int e = threadIdx.x; e < 42; e += blockDim.x) {
+      const int a = e / 7, c = e % 7;
+      double s = 0;
+      for (int k = 0; k < 7; ++k) s += A[a * 7 + k] * Sigma[(size_t)k * ld + c];
+      Tc[e] = s;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 36; e += blockDim.x) {
+      const int a = e / 6, b = e % 6;
+      double s = 0;
+      for (int c = 0; c < 7; ++c) s += Tc[a * 7 + c] * A[b * 7 + c];
+      for (int k = 0; k < 3; ++k) {
+        const double sd = (k < 2) ? cfg.sigma_pixel_2 : cfg.sigma_rho_0;  // V:362,365
+        s += (Ap[a * 3 + k] * sd) * Ap[b * 3 + k];
+      }
+      Sigma[(size_t)(n + a) * ld + n + b] = s;
+    }
+    if (threadIdx.x < 6) mu[n + threadIdx.x] = fnew[threadIdx.x];
+    // Patch constructor (Patch.cpp:78-103): template = frame ROI at (int)(pf - w/2)
+    const int w = cfg.window, w2 = w * w;
+    const int x0 = (int)(pfx - w / 2), y0 = (int)(pfy - w / 2);
+    for (int e = threadIdx.x; e < w2; e += blockDim.x)
+      ft.patch[(size_t)fidx * w2 + e] = fr.px[(size_t)(y0 + e / w) * fr.stride + x0 + (e % w)];
+    if (threadIdx.x == 0) {
+      ft.pos[fidx] = n; ft.coding[fidx] = 0; ft.innov[fidx] = 0; ft.li[fidx] = 0; ft.hi[fidx] = 0;
+      ft.removef[fidx] = 0; ft.n_tot[fidx] = 1; ft.n_find[fidx] = 1; ft.real_index[fidx] = real_index;
+      ft.pos_in_z[fidx] = 0; ft.center[2 * fidx] = pfx; ft.center[2 * fidx + 1] = pfy;
+      ft.quality[fidx] = 0.0f; ft.last_ncc[fidx] = -1.0f;
+      ft.z[2 * fidx] = 0; ft.z[2 * fidx + 1] = 0; ft.h[2 * fidx] = 0; ft.h[2 * fidx + 1] = 0;
+      for (int c = 0; c < 26; ++c) ft.Hc[26 * fidx + c] = 0;
+      for (int c = 0; c < 4; ++c) ft.S2[4 * fidx + c] = 0;
+    }
+  }
+}
+
+// K6b: removeFeature (V:373-421) for a set of features at once: Sigma'[i,j] = Sigma[map[i], map[j]].
+__global__ void k_gather_sigma(const double* __restrict__ src, double* __restrict__ dst, int ld, int n2,
+                               const int* __restrict__ map) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j < n2) dst[(size_t)i * ld + j] = src[(size_t)map[i] * ld + map[j]];
+}
+__global__ void k_gather_vec(const double* __restrict__ src, double* __restrict__ dst, int n2, const int* __restrict__ map) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n2) dst[j] = src[map[j]];
+}
+// Compacts the feature table in place order-preserving: keep[] lists surviving old indices
+// (ascending), newpos[] their new position_in_state.  src/dst are distinct tables.
+__global__ void k_gather_features(FeatTab src, FeatTab dst, int N2, const int* __restrict__ keep,
+                                  const int* __restrict__ newpos, int w2) {
+  const int f = blockIdx.x;
+  if (f >= N2) return;
+  const int o = keep[f];
+  for (int e = threadIdx.x; e < w2; e += blockDim.x) {
+    dst.patch[(size_t)f * w2 + e] = src.patch[(size_t)o * w2 + e];
+    dst.mpatch[(size_t)f * w2 + e] = src.mpatch[(size_t)o * w2 + e];
+  }
+  for (int e = threadIdx.x; e < 26; e += blockDim.x) dst.Hc[26 * f + e] = src.Hc[26 * o + e];
+  if (threadIdx.x == 0) {
+    dst.pos[f] = newpos[f]; dst.coding[f] = src.coding[o]; dst.innov[f] = src.innov[o];
+    dst.li[f] = src.li[o]; dst.hi[f] = src.hi[o]; dst.removef[f] = src.removef[o];
+    dst.n_tot[f] = src.n_tot[o]; dst.n_find[f] = src.n_find[o]; dst.real_index[f] = src.real_index[o];
+    dst.pos_in_z[f] = src.pos_in_z[o]; dst.quality[f] = src.quality[o]; dst.last_ncc[f] = src.last_ncc[o];
+    for (int c = 0; c < 2; ++c) {
+      dst.center[2 * f + c] = src.center[2 * o + c]; dst.z[2 * f + c] = src.z[2 * o + c];
+      dst.h[2 * f + c] = src.h[2 * o + c];
+    }
+    for (int c = 0; c < 4; ++c) dst.S2[4 * f + c] = src.S2[4 * o + c];
+  }
+}
+
+// ---- launch wrappers ---------------------------------------------------------------------------
+void launch_predict(cudaStream_t st, double* Sigma, int ld, int n, double* mu, FeatTab ft, int N, FrameView fr,
+                    DevCtl* ctl, const DevCfg& cfg, double dT, const double dv[3], const double dw[3], int vcontrol,
+                    long long* launches) {
+  const int nb = 1 + (n - 13 + 255) / 256;
+  k_predict_cov<<<nb, 256, 0, st>>>(Sigma, ld, n, mu, ctl, cfg, dT, make_double3(dv[0], dv[1], dv[2]),
+                                   make_double3(dw[0], dw[1], dw[2]), vcontrol);
+  const int fb = N > 0 ? (N + 127) / 128 : 1;
+  k_predict_features<<<fb, 128, 0, st>>>(Sigma, ld, mu, ft, N, fr, ctl, cfg);
+  *launches += 2;
+}
+void launch_quat_normalize(cudaStream_t st, double* Sigma, int ld, int n, double* mu, const DevCtl* ctl, long long* launches) {
+  const int nb = 1 + (n - 4 + 255) / 256;
+  k_quat_normalize<<<nb, 256, 0, st>>>(Sigma, ld, n, mu, ctl);
+  k_quat_commit<<<1, 32, 0, st>>>(mu, ctl);
+  *launches += 2;
+}
+void launch_add_feature(cudaStream_t st, double* Sigma, int ld, int n, double* mu, FeatTab ft, int fidx, FrameView fr,
+                        const DevCfg& cfg, float pfx, float pfy, int real_index, long long* launches) {
+  const int nb = (n + 255) / 256;
+  k_add_feature<<<nb, 256, 0, st>>>(Sigma, ld, n, mu, ft, fidx, fr, cfg, pfx, pfy, real_index);
+  *launches += 1;
+}
+void launch_gather_state(cudaStream_t st, const double* Ssrc, double* Sdst, int ld, const double* musrc, double* mudst,
+                         int n2, const int* map, long long* launches) {
+  if (n2 <= 0) return;
+  dim3 g((n2 + 255) / 256, n2);
+  k_gather_sigma<<<g, 256, 0, st>>>(Ssrc, Sdst, ld, n2, map);
+  k_gather_vec<<<(n2 + 255) / 256, 256, 0, st>>>(musrc, mudst, n2, map);
+  *launches += 2;
+}
+void launch_gather_features(cudaStream_t st, FeatTab src, FeatTab dst, int N2, const int* keep, const int* newpos, int w2,
+                            long long* launches) {
+  if (N2 <= 0) return;
+  k_gather_features<<<N2, 64, 0, st>>>(src, dst, N2, keep, newpos, w2);
+  *launches += 1;
+}

@@ -1,0 +1,484 @@
+// csrc/ekf_update.cu — K5 (1-point RANSAC), K4a-c (innovation covariance, Cholesky gain) and the
+// high-innovation rescue / book-keeping of VSlamFilter::update (vslamRansac.cpp:964-1341).
+// SURVEY.md §8(a) rows a14-a19.  V: = mono-slam/src/vslamRansac.cpp.
+//
+// Stacked update algebra.  The reference forms St = H Sigma H^T + R for all k selected rows, inverts
+// it by LU and applies Kt = Sigma H^T St^-1, Sigma <- (I - Kt H) Sigma (V:1053-1060).  Here the k
+// rows are consumed in blocks of EKF_UB rows: for each block b
+//     W_b = Sigma H_b^T                       (gather GEMM: H has 13 non-zeros per row)
+//     S_b = H_b W_b + sigma_px^2 I = L_b L_b^T (Cholesky, one CTA, shared memory)
+//     V_b = W_b L_b^-T,  y_b = L_b^-1 (z_b - h_b - H_b delta)
+//     Sigma <- Sigma - V_b V_b^T              (DMMA, ekf_gemm.cu),   delta <- delta + V_b y_b
+// and mu <- mu + delta at the end.  S_b computed from the already-downdated Sigma is the Schur
+// complement of the preceding blocks, so the sequence is exactly a right-looking blocked Cholesky
+// of the full St whose trailing updates are carried by the covariance downdate; in exact arithmetic
+// it equals the reference's one-shot update (R is diagonal, H is evaluated once at the prior mean).
+#include "ekf_kernels.h"
+#include "ekf_math.cuh"
+
+
+// ------------------------------------------------------------------------------------------------
+// K5: 1-point RANSAC (V:964-1034) — one persistent CTA runs the whole adaptive loop on the device.
+// picks[] replaces rand() (V:970,989).  The Li flags left behind are those of the LAST hypothesis
+// evaluated (quirk V:1022), and S_i equals the 2x2 block computed in predict (same Sigma, same H).
+// ------------------------------------------------------------------------------------------------
+#define RANSAC_THREADS 1024
+__global__ void __launch_bounds__(RANSAC_THREADS) k_ransac(const double* __restrict__ Sigma, int ld, int n,
+                                                           const double* __restrict__ mu, FeatTab ft, int N, DevCtl* ctl,
+                                                           DevCfg cfg, const uint32_t* __restrict__ picks, int n_picks,
+                                                           double* __restrict__ mu_i, int* __restrict__ cand) {
+  __shared__ double Hs[26], Sinv[4], inn[2], rr[3], Rcw[9];
+  __shared__ int s_p, s_sel, s_pos, s_nd, s_nhyp, s_numzli;
+  const int tid = threadIdx.x;
+  int cnt = block_compact(ft.innov, N, cand, nullptr);
+  const int matched = cnt;
+  if (tid == 0) {
+    ctl->n_matched = cnt;
+    for (int i = 0; i < 7; ++i) ctl->cam_old[i] = mu[i];
+    s_nhyp = cfg.nhyp0;
+    s_numzli = 0;
+  }
+  int it = 0;
+  while (true) {
+    __syncthreads();
+    if (!(it < s_nhyp && cnt > 0)) break;
+    if (tid == 0) {
+      const uint32_t rv = n_picks > 0 ? picks[it % n_picks] : 0u;
+      s_p = (int)(rv % (uint32_t)cnt);
+      s_sel = cand[s_p];
+    }
+    __syncthreads();
+    const int p = s_p, sel = s_sel;
+    {  // erase cand[p] (V:991)
+      int tmp[8];
+      int c = 0;
+      for (int idx = p + tid; idx < cnt - 1 && c < 8; idx += RANSAC_THREADS) tmp[c++] = cand[idx + 1];
+      __syncthreads();
+      c = 0;
+      for (int idx = p + tid; idx < cnt - 1 && c < 8; idx += RANSAC_THREADS) cand[idx] = tmp[c++];
+      cnt -= 1;
+    }
+    if (tid < 26) Hs[tid] = ft.Hc[26 * sel + tid];
+    if (tid == 32) {
+      double S[4];
+      for (int c = 0; c < 4; ++c) S[c] = ft.S2[4 * sel + c];
+      double X[4];
+      d_inv2_pplu(S, X);
+      for (int c = 0; c < 4; ++c) Sinv[c] = X[c];
+      inn[0] = ft.z[2 * sel] - ft.h[2 * sel];
+      inn[1] = ft.z[2 * sel + 1] - ft.h[2 * sel + 1];
+      s_pos = ft.pos[sel];
+      s_nd = 7 + (ft.coding[sel] ? 3 : 6);
+    }
+    __syncthreads();
+    {  // mu_i = mu + (Sigma H^T) S^-1 (z - h)   (V:995-996)
+      const int pos = s_pos, nd = s_nd;
+      for (int i = tid; i < n; i += RANSAC_THREADS) {
+        const double* row = Sigma + (size_t)i * ld;
+        double w0 = 0, w1 = 0;
+        for (int c = 0; c < nd; ++c) {
+          const double s = row[ekf_idx13(c, pos)];
+          w0 += s * Hs[c]; w1 += s * Hs[13 + c];
+        }
+        const double k0 = w0 * Sinv[0] + w1 * Sinv[2];
+        const double k1 = w0 * Sinv[1] + w1 * Sinv[3];
+        mu_i[i] = mu[i] + (k0 * inn[0] + k1 * inn[1]);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int c = 0; c < 3; ++c) rr[c] = mu_i[c];
+      double q[4] = {mu_i[3], mu_i[4], mu_i[5], mu_i[6]};
+      const double qn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+      double qc[4];
+      qc[0] = q[0] / qn; qc[1] = -(q[1] / qn); qc[2] = -(q[2] / qn); qc[3] = -(q[3] / qn);
+      double R[9];
+      d_quat2rot(qc, R);
+      for (int c = 0; c < 9; ++c) Rcw[c] = R[c];
+    }
+    __syncthreads();
+    int actual = 0;
+    for (int start = 0; start < N; start += RANSAC_THREADS) {
+      const int i = start + tid;
+      int flag = 0;
+      if (i < N && ft.innov[i]) {
+        const int pos = ft.pos[i], coding = ft.coding[i];
+        double fs[6], hi[2], r3[3] = {rr[0], rr[1], rr[2]}, R[9];
+        for (int c = 0; c < 9; ++c) R[c] = Rcw[c];
+        if (!coding) for (int c = 0; c < 6; ++c) fs[c] = mu_i[pos + c];
+        else for (int c = 0; c < 3; ++c) fs[c] = mu[pos + c];  // quirk V:1016: mu, not mu_i
+        d_feature_h(cfg.cam, fs, coding, r3, R, hi);
+        const double e0 = ft.z[2 * i] - hi[0], e1 = ft.z[2 * i + 1] - hi[1];
+        flag = (sqrt(e0 * e0 + e1 * e1) <= cfg.th_low) ? 1 : 0;
+        ft.li[i] = flag;
+      }
+      actual += __syncthreads_count(flag);
+    }
+    if (tid == 0 && actual > s_numzli) {
+      s_numzli = actual;
+      s_nhyp = (int)(log(1 - cfg.ransac_p) / (log(1 - (actual / (matched + 0.0)))));  // V:1030
+    }
+    ++it;
+  }
+  __syncthreads();
+  const int nli = block_compact(ft.li, N, ft.sel, ft.pos_in_z);  // V:1040-1048
+  if (tid == 0) {
+    ctl->ransac_hyps = it;
+    ctl->n_li = nli;
+    ctl->k_rows = 2 * nli;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// High-innovation rescue (V:1066-1130): camera pose from the OLD mu (ctl->cam_old), feature
+// parameters from mu_tmp (= mu after the low-innovation update), S_hi = H Sigma_tmp H^T without R,
+// chi^2 <= th_hi.  The last block compacts the Hi list.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_hi_rescue(const double* __restrict__ Sigma, int ld, const double* __restrict__ mu,
+                                                   FeatTab ft, int N, DevCtl* ctl, DevCfg cfg) {
+  __shared__ int is_last;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) {
+    int flag = 0;
+    if (!ft.li[i] && ft.innov[i]) {
+      const int pos = ft.pos[i], coding = ft.coding[i];
+      const int fsz = coding ? 3 : 6, nd = 7 + fsz;
+      double fs[6], r[3], qc[4], Rcw[9], hi[2], Hc[26], hcz;
+      for (int c = 0; c < fsz; ++c) fs[c] = mu[pos + c];
+      for (int c = 0; c < 3; ++c) r[c] = ctl->cam_old[c];
+      qc[0] = ctl->cam_old[3]; qc[1] = -ctl->cam_old[4]; qc[2] = -ctl->cam_old[5]; qc[3] = -ctl->cam_old[6];
+      d_quat2rot(qc, Rcw);
+      d_feature_hH(cfg.cam, fs, coding, r, qc, Rcw, hi, Hc, &hcz);
+      ft.h[2 * i] = hi[0]; ft.h[2 * i + 1] = hi[1];
+      for (int c = 0; c < 26; ++c) ft.Hc[26 * i + c] = Hc[c];
+      double Tm[26];
+      for (int b = 0; b < nd; ++b) {
+        const int jb = ekf_idx13(b, pos);
+        double t0 = 0, t1 = 0;
+        for (int c = 0; c < nd; ++c) {
+          const double s = Sigma[(size_t)ekf_idx13(c, pos) * ld + jb];
+          t0 += Hc[c] * s; t1 += Hc[13 + c] * s;
+        }
+        Tm[b] = t0; Tm[13 + b] = t1;
+      }
+      double S[4] = {0, 0, 0, 0};
+      for (int b = 0; b < nd; ++b) {
+        S[0] += Tm[b] * Hc[b]; S[1] += Tm[b] * Hc[13 + b];
+        S[2] += Tm[13 + b] * Hc[b]; S[3] += Tm[13 + b] * Hc[13 + b];
+      }
+      // fixed-size 2x2 inverse(): closed form (V:1114)
+      const double det = S[0] * S[3] - S[2] * S[1];
+      const double invdet = 1.0 / det;
+      const double i00 = S[3] * invdet, i10 = -S[2] * invdet, i01 = -S[1] * invdet, i11 = S[0] * invdet;
+      const double e0 = hi[0] - ft.z[2 * i], e1 = hi[1] - ft.z[2 * i + 1];
+      const double t0 = e0 * i00 + e1 * i10;
+      const double t1 = e0 * i01 + e1 * i11;
+      const double chi = t0 * e0 + t1 * e1;
+      flag = (chi <= cfg.th_hi) ? 1 : 0;
+    }
+    ft.hi[i] = flag;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(&ctl->ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int nhi = block_compact(ft.hi, N, ft.sel, ft.pos_in_z);  // V:1122-1130
+  if (threadIdx.x == 0) {
+    ctl->n_hi = nhi;
+    ctl->k_rows = 2 * nhi;
+    ctl->ticket = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4a: W_b = Sigma H_b^T for the block of <= 64 selected features starting at sel[f0]
+// (n x EKF_UB, row-major), and nu_b = (z - h) - H_b delta.  One pass over the needed columns of Sigma.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ Sigma, int ld, int n, FeatTab ft, int f0, int cnt,
+                                                    const double* __restrict__ delta, double* __restrict__ W,
+                                                    double* __restrict__ nu) {
+  __shared__ double Hs[EKF_UB / 2][27];
+  __shared__ int poss[EKF_UB / 2], nds[EKF_UB / 2], fids[EKF_UB / 2];
+  const int nb = min(EKF_UB / 2, cnt - f0);
+  const int tid = threadIdx.x;
+  for (int a = tid; a < EKF_UB / 2; a += blockDim.x) {
+    if (a < nb) {
+      const int f = ft.sel[f0 + a];
+      fids[a] = f; poss[a] = ft.pos[f]; nds[a] = 7 + (ft.coding[f] ? 3 : 6);
+    } else { fids[a] = -1; poss[a] = 0; nds[a] = 0; }
+  }
+  __syncthreads();
+  for (int e = tid; e < (EKF_UB / 2) * 26; e += blockDim.x) {
+    const int a = e / 26, c = e % 26;
+    Hs[a][c] = (a < nb) ? ft.Hc[26 * fids[a] + c] : 0.0;
+  }
+  __syncthreads();
+  const int a = tid & (EKF_UB / 2 - 1), rl = tid / (EKF_UB / 2);
+  const int rows_per_cta = 32, rstep = 256 / (EKF_UB / 2);
+  const int pos = poss[a], nd = nds[a];
+  for (int rq = rl; rq < rows_per_cta; rq += rstep) {
+    const int i = blockIdx.x * rows_per_cta + rq;
+    if (i >= n) break;
+    const double* row = Sigma + (size_t)i * ld;
+    double w0 = 0, w1 = 0;
+    for (int c = 0; c < nd; ++c) {
+      const double s = row[ekf_idx13(c, pos)];
+      w0 += s * Hs[a][c]; w1 += s * Hs[a][13 + c];
+    }
+    reinterpret_cast<double2*>(W + (size_t)i * EKF_UB)[a] = make_double2(w0, w1);
+  }
+  if (blockIdx.x == 0 && tid < EKF_UB / 2) {
+    double v0 = 0, v1 = 0;
+    if (tid < nb) {
+      const int f = fids[tid];
+      double hd0 = 0, hd1 = 0;
+      for (int c = 0; c < nds[tid]; ++c) {
+        const double d = delta[ekf_idx13(c, poss[tid])];
+        hd0 += Hs[tid][c] * d; hd1 += Hs[tid][13 + c] * d;
+      }
+      v0 = (ft.z[2 * f] - ft.h[2 * f]) - hd0;
+      v1 = (ft.z[2 * f + 1] - ft.h[2 * f + 1]) - hd1;
+    }
+    nu[2 * tid] = v0; nu[2 * tid + 1] = v1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4b: S_b = H_b W_b + sigma_px^2 I, Cholesky S_b = L L^T in shared memory (right-looking, one CTA),
+// inverses of the four 32x32 diagonal blocks of L, and y = L^-1 nu.  Unused rows (partial block) are
+// identity so they contribute nothing.
+// ------------------------------------------------------------------------------------------------
+#define FACT_THREADS 512
+#define FACT_LD (EKF_UB + 1)
+__global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __restrict__ W, FeatTab ft, int f0, int cnt,
+                                                             const double* __restrict__ nu, double sigma_pixel_2,
+                                                             double* __restrict__ Lout, double* __restrict__ Dinv,
+                                                             double* __restrict__ yout, DevCtl* ctl) {
+  extern __shared__ __align__(16) double fsm[];
+  double* A = fsm;                          // [EKF_UB][FACT_LD]
+  double* Di = A + EKF_UB * FACT_LD;        // [4][32][33]
+  double* ys = Di + 4 * 32 * 33;            // [EKF_UB]
+  double* ts = ys + EKF_UB;                 // [EKF_UB]
+  const int tid = threadIdx.x;
+  const int nb = min(EKF_UB / 2, cnt - f0), kr = 2 * nb;
+  // S_b (lower triangle suffices)
+  for (int e = tid; e < EKF_UB * EKF_UB; e += FACT_THREADS) {
+    const int r = e / EKF_UB, s = e % EKF_UB;
+    double v = (r == s) ? 1.0 : 0.0;
+    if (r < kr && s < kr) {
+      const int f = ft.sel[f0 + (r >> 1)];
+      const int pos = ft.pos[f], nd = 7 + (ft.coding[f] ? 3 : 6);
+      const double* hc = ft.Hc + 26 * f + 13 * (r & 1);
+      double acc = 0;
+      for (int c = 0; c < nd; ++c) acc += hc[c] * W[(size_t)ekf_idx13(c, pos) * EKF_UB + s];
+      v = acc + ((r == s) ? sigma_pixel_2 : 0.0);
+    }
+    A[r * FACT_LD + s] = v;
+  }
+  for (int e = tid; e < EKF_UB; e += FACT_THREADS) ys[e] = nu[e];
+  // Cholesky, column by column
+  for (int j = 0; j < EKF_UB; ++j) {
+    __syncthreads();
+    const double ajj = A[j * FACT_LD + j];
+    const double d = sqrt(ajj);
+    if (tid == 0 && !(ajj > 0.0)) ctl->chol_fail = 1;
+    for (int i = j + 1 + tid; i < EKF_UB; i += FACT_THREADS) A[i * FACT_LD + j] = A[i * FACT_LD + j] / d;
+    __syncthreads();
+    if (tid == 0) A[j * FACT_LD + j] = d;
+    const int m = EKF_UB - j - 1;
+    for (int e = tid; e < m * m; e += FACT_THREADS) {
+      const int i = j + 1 + e / m, c = j + 1 + e % m;
+      if (c <= i) A[i * FACT_LD + c] -= A[i * FACT_LD + j] * A[c * FACT_LD + j];
+    }
+  }
+  __syncthreads();
+  // inverses of the diagonal 32x32 blocks: thread (J, col) solves L_JJ x = e_col
+  if (tid < 128) {
+    const int J = tid >> 5, col = tid & 31;
+    double* X = Di + J * 32 * 33;
+    const double* Lj = A + (J * 32) * FACT_LD + J * 32;
+    for (int i = 0; i < 32; ++i) {
+      double s = (i == col) ? 1.0 : 0.0;
+      if (i < col) { X[i * 33 + col] = 0.0; continue; }
+      for (int dd = col; dd < i; ++dd) s -= Lj[i * FACT_LD + dd] * X[dd * 33 + col];
+      X[i * 33 + col] = s / Lj[i * FACT_LD + i];
+    }
+  }
+  __syncthreads();
+  // y = L^-1 nu, block forward substitution
+  for (int J = 0; J < 4; ++J) {
+    if (tid < 32) {
+      const int r = J * 32 + tid;
+      double s = ys[r];
+      for (int dd = 0; dd < J * 32; ++dd) s -= A[r * FACT_LD + dd] * ys[dd];
+      ts[tid] = s;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      const double* X = Di + J * 32 * 33;
+      double s = 0;
+      for (int dd = 0; dd <= tid; ++dd) s += X[tid * 33 + dd] * ts[dd];
+      ys[J * 32 + tid] = s;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < EKF_UB * EKF_UB; e += FACT_THREADS) {
+    const int r = e / EKF_UB, s = e % EKF_UB;
+    Lout[e] = (s <= r) ? A[r * FACT_LD + s] : 0.0;
+  }
+  for (int e = tid; e < 4 * 32 * 32; e += FACT_THREADS) {
+    const int J = e >> 10, r = (e >> 5) & 31, c = e & 31;
+    Dinv[e] = Di[J * 32 * 33 + r * 33 + c];
+  }
+  for (int e = tid; e < EKF_UB; e += FACT_THREADS) yout[e] = ys[e];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4c: V_b = W_b L^-T in place (rows are independent; 32 rows per CTA, L and the diagonal-block
+// inverses staged in shared memory), and delta += V_b y.
+// ------------------------------------------------------------------------------------------------
+#define VT_ROWS 32
+#define VT_THREADS 256
+__global__ void __launch_bounds__(VT_THREADS) k_blk_V(double* __restrict__ W, int n, const double* __restrict__ Lg,
+                                                      const double* __restrict__ Dinvg, const double* __restrict__ yg,
+                                                      double* __restrict__ delta) {
+  extern __shared__ __align__(16) double vsm[];
+  double* Ls = vsm;                          // [EKF_UB][FACT_LD]
+  double* Di = Ls + EKF_UB * FACT_LD;        // [4][32][33]
+  double* Ws = Di + 4 * 32 * 33;             // [VT_ROWS][FACT_LD]
+  double* ys = Ws + VT_ROWS * FACT_LD;       // [EKF_UB]
+  const int tid = threadIdx.x;
+  const int row0 = blockIdx.x * VT_ROWS;
+  for (int e = tid; e < EKF_UB * EKF_UB; e += VT_THREADS) Ls[(e / EKF_UB) * FACT_LD + (e % EKF_UB)] = Lg[e];
+  for (int e = tid; e < 4 * 32 * 32; e += VT_THREADS) Di[(e >> 10) * 32 * 33 + ((e >> 5) & 31) * 33 + (e & 31)] = Dinvg[e];
+  for (int e = tid; e < VT_ROWS * EKF_UB; e += VT_THREADS) {
+    const int r = e / EKF_UB, c = e % EKF_UB;
+    Ws[r * FACT_LD + c] = (row0 + r < n) ? W[(size_t)(row0 + r) * EKF_UB + c] : 0.0;
+  }
+  for (int e = tid; e < EKF_UB; e += VT_THREADS) ys[e] = yg[e];
+  __syncthreads();
+  const int r = tid >> 3, cg = (tid & 7) * 4;  // 32 rows x 8 column groups of 4
+  for (int J = 0; J < 4; ++J) {
+    double u[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) u[q] = Ws[r * FACT_LD + J * 32 + cg + q];
+    for (int dd = 0; dd < J * 32; ++dd) {
+      const double v = Ws[r * FACT_LD + dd];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) u[q] -= v * Ls[(J * 32 + cg + q) * FACT_LD + dd];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) Ws[r * FACT_LD + J * 32 + cg + q] = u[q];
+    __syncthreads();
+    double vv[4] = {0, 0, 0, 0};
+    const double* X = Di + J * 32 * 33;
+    for (int dd = 0; dd < 32; ++dd) {
+      const double uu = Ws[r * FACT_LD + J * 32 + dd];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) vv[q] += uu * X[(cg + q) * 33 + dd];  // X lower: zero for dd > cg+q
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) Ws[r * FACT_LD + J * 32 + cg + q] = vv[q];
+    __syncthreads();
+  }
+  for (int e = tid; e < VT_ROWS * EKF_UB; e += VT_THREADS) {
+    const int rr = e / EKF_UB, c = e % EKF_UB;
+    if (row0 + rr < n) W[(size_t)(row0 + rr) * EKF_UB + c] = Ws[rr * FACT_LD + c];
+  }
+  if (tid < VT_ROWS && row0 + tid < n) {
+    double s = 0;
+    for (int c = 0; c < EKF_UB; ++c) s += Ws[tid * FACT_LD + c] * ys[c];
+    delta[row0 + tid] += s;
+  }
+}
+
+__global__ void k_apply_delta(double* __restrict__ mu, const double* __restrict__ delta, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) mu[i] += delta[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Book-keeping (V:1296-1303, Patch.cpp:143-150) and the packed per-step output record.
+//   out: [0,14) state, [14,210) Sigma 14x14 (as doubles), then ints: 16 counters, 3N per feature
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bookkeeping(const double* __restrict__ Sigma, int ld, const double* __restrict__ mu,
+                                                     FeatTab ft, int N, DevCtl* ctl, DevCfg cfg, double* __restrict__ outd,
+                                                     int* __restrict__ outi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) {
+    int nfind = ft.n_find[i];
+    const int ntot = ft.n_tot[i];
+    if (ft.hi[i] || ft.li[i]) nfind++;
+    ft.n_find[i] = nfind;
+    const float qi = (float)(ntot - nfind) / ((float)nfind);
+    ft.quality[i] = qi;
+    if (qi > cfg.quality_ratio) ft.removef[i] = 1;
+    const int fl = (ft.innov[i] ? 1 : 0) | (ft.li[i] ? 2 : 0) | (ft.hi[i] ? 4 : 0) | (ft.removef[i] ? 8 : 0);
+    outi[16 + i] = fl;
+    outi[16 + N + i] = ntot;
+    outi[16 + 2 * N + i] = nfind;
+  }
+  if (blockIdx.x == 0) {
+    for (int e = threadIdx.x; e < 14; e += blockDim.x) outd[e] = mu[e];
+    for (int e = threadIdx.x; e < 196; e += blockDim.x) outd[14 + e] = Sigma[(size_t)(e / 14) * ld + (e % 14)];
+    if (threadIdx.x == 0) {
+      outi[0] = ctl->m_innov; outi[1] = ctl->n_matched; outi[2] = ctl->n_li; outi[3] = ctl->n_hi;
+      outi[4] = ctl->ransac_hyps; outi[5] = ctl->chol_fail;
+    }
+  }
+}
+
+// ---- launch wrappers ---------------------------------------------------------------------------
+static const size_t kFactSmem = (size_t)(EKF_UB * FACT_LD + 4 * 32 * 33 + 2 * EKF_UB) * sizeof(double);
+static const size_t kVSmem = (size_t)(EKF_UB * FACT_LD + 4 * 32 * 33 + VT_ROWS * FACT_LD + EKF_UB) * sizeof(double);
+
+int update_kernels_init() {
+  cudaError_t e = cudaFuncSetAttribute(k_blk_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFactSmem);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_blk_V, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVSmem);
+  return (int)e;
+}
+
+void launch_ransac(cudaStream_t st, const double* Sigma, int ld, int n, const double* mu, FeatTab ft, int N, DevCtl* ctl,
+                   const DevCfg& cfg, const uint32_t* picks, int n_picks, double* mu_i, int* cand, long long* launches) {
+  k_ransac<<<1, RANSAC_THREADS, 0, st>>>(Sigma, ld, n, mu, ft, N, ctl, cfg, picks, n_picks, mu_i, cand);
+  *launches += 1;
+}
+void launch_hi_rescue(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, DevCtl* ctl,
+                      const DevCfg& cfg, long long* launches) {
+  const int fb = N > 0 ? (N + 127) / 128 : 1;
+  k_hi_rescue<<<fb, 128, 0, st>>>(Sigma, ld, mu, ft, N, ctl, cfg);
+  *launches += 1;
+}
+// One stacked update over `cnt` selected features (ft.sel), block by block.
+int launch_stacked_update(cudaStream_t st, double* Sigma, int ld, int n, double* mu, FeatTab ft, int cnt, DevCtl* ctl,
+                          const DevCfg& cfg, double* W, double* nu, double* Lb, double* Dinv, double* yb, double* delta,
+                          int lower_only, long long* launches) {
+  if (cnt <= 0) return 0;
+  cudaMemsetAsync(delta, 0, sizeof(double) * (size_t)n, st);
+  const int half = EKF_UB / 2;
+  for (int f0 = 0; f0 < cnt; f0 += half) {
+    k_blk_gather<<<(n + 31) / 32, 256, 0, st>>>(Sigma, ld, n, ft, f0, cnt, delta, W, nu);
+    k_blk_factor<<<1, FACT_THREADS, kFactSmem, st>>>(W, ft, f0, cnt, nu, cfg.sigma_pixel_2, Lb, Dinv, yb, ctl);
+    k_blk_V<<<(n + VT_ROWS - 1) / VT_ROWS, VT_THREADS, kVSmem, st>>>(W, n, Lb, Dinv, yb, delta);
+    *launches += 3;
+    const int rc = launch_gemm_nt_sub(st, Sigma, ld, W, EKF_UB, W, EKF_UB, n, n, EKF_UB, nullptr, lower_only, launches);
+    if (rc) return rc;
+  }
+  k_apply_delta<<<(n + 255) / 256, 256, 0, st>>>(mu, delta, n);
+  *launches += 1;
+  return 0;
+}
+void launch_bookkeeping(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, DevCtl* ctl,
+                        const DevCfg& cfg, double* outd, int* outi, long long* launches) {
+  const int fb = N > 0 ? (N + 255) / 256 : 1;
+  k_bookkeeping<<<fb, 256, 0, st>>>(Sigma, ld, mu, ft, N, ctl, cfg, outd, outi);
+  *launches += 1;
+}

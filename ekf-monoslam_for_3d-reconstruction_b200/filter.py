@@ -1,0 +1,169 @@
+"""Python mirror of the reference's `class VSlamFilter` (mono-slam/src/vslamRansac.hpp:27-141) over
+the C ABI.  Same method names, argument meaning and call order as the reference class; Eigen / OpenCV
+types become numpy arrays.  Used by the tests and bench.py; the C++ twin is host/vslam_filter.hpp.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._lib import lib
+
+
+class EkfError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class VSlamFilter:
+    """VSlamFilter(cfg) — cfg is an EkfConfig (see default_config) instead of a libconfig file name
+    (vslamRansac.cpp:142).  feature_capacity bounds the map size of this handle."""
+
+    def __init__(self, cfg=None, feature_capacity=128, device=0):
+        self.L = lib()
+        self.cfg = cfg if cfg is not None else _abi.default_config()
+        h = C.c_void_p()
+        rc = self.L.ekf_create(C.byref(self.cfg), int(feature_capacity), int(device), C.byref(h))
+        if rc != 0:
+            raise EkfError(f"ekf_create failed with {rc} "
+                           f"({'unsupported configuration' if rc == _abi.EKF_ERR_UNSUPPORTED else 'see stderr'})")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ekf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise EkfError(f"ekf error {rc}: {self.L.ekf_last_error(self.h).decode()}")
+        return rc
+
+    # ---- the per-frame path ------------------------------------------------------------------
+    def captureNewFrame(self, img, stamp=-1.0):
+        """vslamRansac.cpp:226-245; img is an HxW uint8 numpy array (host) — copied inside the call."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        self._ck(self.L.ekf_capture_frame(self.h, _ptr(img), img.shape[1], img.shape[0], img.strides[0], float(stamp)))
+
+    def captureNewFrame_device(self, dev_ptr, width, height, stride, stamp=-1.0):
+        """Same for a frame already in device memory (raw pointer, e.g. tensor.data_ptr())."""
+        self._ck(self.L.ekf_capture_frame_device(self.h, C.c_void_p(int(dev_ptr)), width, height, stride, float(stamp)))
+
+    def predict(self, dv=(0.0, 0.0, 0.0), dw=(0.0, 0.0, 0.0), vcontrol=False):
+        a = np.asarray(dv, dtype=np.float64); b = np.asarray(dw, dtype=np.float64)
+        self._ck(self.L.ekf_predict(self.h, _ptr(a), _ptr(b), int(bool(vcontrol))))
+
+    def match(self, want_count=True):
+        n = C.c_int(0)
+        self._ck(self.L.ekf_match(self.h, C.byref(n) if want_count else None))
+        return n.value
+
+    def update_after_match(self, picks=None):
+        p = np.ascontiguousarray(picks if picks is not None else np.zeros(0), dtype=np.uint32)
+        self._ck(self.L.ekf_update_after_match(self.h, _ptr(p), int(p.size)))
+
+    def update(self, picks=None):
+        """vslamRansac.cpp:868; `picks` replaces rand() (vslamRansac.cpp:989)."""
+        p = np.ascontiguousarray(picks if picks is not None else np.zeros(0), dtype=np.uint32)
+        self._ck(self.L.ekf_update(self.h, _ptr(p), int(p.size)))
+
+    def inject_match(self, i, zu, zv, accepted=True):
+        self._ck(self.L.ekf_inject_match(self.h, int(i), float(zu), float(zv), int(bool(accepted))))
+
+    # ---- map management ----------------------------------------------------------------------
+    def addFeature(self, u, v):
+        return self._ck(self.L.ekf_add_feature(self.h, float(u), float(v)))
+
+    def removeFeature(self, i):
+        self._ck(self.L.ekf_remove_feature(self.h, int(i)))
+
+    # ---- accessors ---------------------------------------------------------------------------
+    def numOfFeatures(self):
+        return self.L.ekf_num_features(self.h)
+
+    def state_dim(self):
+        return self.L.ekf_state_dim(self.h)
+
+    def getState(self):
+        out = np.zeros(14)
+        self._ck(self.L.ekf_get_state(self.h, _ptr(out)))
+        return out
+
+    def getSigma(self):
+        out = np.zeros((14, 14))
+        self._ck(self.L.ekf_get_sigma(self.h, _ptr(out)))
+        return out
+
+    def Covariance_Parameter(self):
+        v = C.c_double(0)
+        self._ck(self.L.ekf_covariance_parameter(self.h, C.byref(v)))
+        return v.value
+
+    def getDt(self):
+        return self.L.ekf_get_dt(self.h)
+
+    def returnCentrPatchIndx(self, i):
+        out = np.zeros(2, dtype=np.float32)
+        self._ck(self.L.ekf_get_center(self.h, int(i), _ptr(out)))
+        return out
+
+    def feature(self, i):
+        o = _abi.EkfFeatureInfo()
+        self._ck(self.L.ekf_get_feature(self.h, int(i), C.byref(o)))
+        return o
+
+    def template(self, i, which=0):
+        w = self.cfg.window_size
+        out = np.zeros((w, w), dtype=np.uint8)
+        self._ck(self.L.ekf_get_template(self.h, int(i), int(which), _ptr(out)))
+        return out
+
+    def stats(self):
+        s = _abi.EkfStepStats()
+        self._ck(self.L.ekf_get_step_stats(self.h, C.byref(s)))
+        return s
+
+    def get_full(self):
+        n = self.state_dim()
+        mu = np.zeros(n); S = np.zeros((n, n))
+        self._ck(self.L.ekf_get_full(self.h, _ptr(mu), _ptr(S), n))
+        return mu, S
+
+    def set_full(self, mu, S):
+        mu = np.ascontiguousarray(mu, dtype=np.float64); S = np.ascontiguousarray(S, dtype=np.float64)
+        n = self.state_dim()
+        if mu.size != n or S.shape != (n, n):
+            raise ValueError("set_full: shape mismatch")
+        self._ck(self.L.ekf_set_full(self.h, _ptr(mu), _ptr(S), n))
+
+    def S_blocks(self):
+        out = np.zeros((self.numOfFeatures(), 2, 2))
+        self._ck(self.L.ekf_get_S_blocks(self.h, _ptr(out)))
+        return out
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.L.ekf_set_stream(self.h, C.c_void_p(int(cuda_stream_ptr) if cuda_stream_ptr else 0)))
+
+    def sync(self):
+        self._ck(self.L.ekf_sync(self.h))
+
+
+def match_batch(frames_dev, n_frames, width, height, stride, templates_dev, features_per_frame, window,
+                h_dev, S_dev, out_uv_dev, out_score_dev, sigma_size=3.0, ncc_threshold=0.8, search_clamp=20.0,
+                stream=0):
+    """ekf_match_batch on raw device pointers (ints)."""
+    rc = lib().ekf_match_batch(C.c_void_p(frames_dev), n_frames, width, height, stride, C.c_void_p(templates_dev),
+                               features_per_frame, window, C.c_void_p(h_dev), C.c_void_p(S_dev), float(sigma_size),
+                               float(ncc_threshold), float(search_clamp), C.c_void_p(out_uv_dev),
+                               C.c_void_p(out_score_dev), C.c_void_p(stream))
+    if rc != 0:
+        raise EkfError(f"ekf_match_batch failed: {rc}")

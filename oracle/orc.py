@@ -1,7 +1,6 @@
 """ctypes binding of the CPU oracle (oracle/liborc*.so).  TEST INFRASTRUCTURE ONLY: importable
 from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
 import ctypes as C
-import importlib.util
 import os
 import subprocess
 import sys
@@ -12,19 +11,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 
 
-def _abi():
-    name = "ekf_b200_abi"
-    if name in sys.modules:
-        return sys.modules[name]
-    path = os.path.join(_ROOT, "ekf-monoslam_for_3d-reconstruction_b200", "_abi.py")
-    spec = importlib.util.spec_from_file_location(name, path)
-    mod = importlib.util.module_from_spec(spec)
-    sys.modules[name] = mod
-    spec.loader.exec_module(mod)
-    return mod
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+import ekfb200  # noqa: E402  (import shim at the repository root)
 
-
-abi = _abi()
+abi = ekfb200.load_package()._abi
 
 
 def build(force=False):

@@ -1,0 +1,42 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    import ekfb200
+    return ekfb200.load_package()
+
+
+@pytest.fixture(scope="session")
+def orc():
+    import orc as _orc
+    _orc.build()
+    return _orc
+
+
+@pytest.fixture(scope="session")
+def gpu_pkg(pkg):
+    """The product package with its CUDA library loaded; fails loudly if the build is missing."""
+    pkg.build()
+    pkg.lib()
+    return pkg
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    d = np.linalg.norm(a - b)
+    s = np.linalg.norm(b)
+    return d / s if s > 0 else d

@@ -1,0 +1,133 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): integer match coordinates and accept/reject decisions
+bit-exact; state and covariance within 1e-9 relative (Frobenius / 2-norm, per step from identical
+inputs).
+"""
+import numpy as np
+import pytest
+
+from helpers import TOL, assert_state_close, assert_tables_equal, make_pair, relerr, seed_features
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(pkg, **kw):
+    return pkg.synth.Scene(**kw)
+
+
+def test_init_and_add_feature(gpu_pkg, orc):
+    sc = _scene(gpu_pkg, n_features=20, n_frames=2, seed=11)
+    g, o = make_pair(gpu_pkg, orc, sc)
+    assert relerr(g.getState(), o.getState()) == 0.0
+    assert relerr(g.getSigma(), o.getSigma()) == 0.0
+    rg, ro = seed_features(g, sc), seed_features(o, sc)
+    assert rg == ro and sum(rg) == 20
+    # a point outside the gate is rejected by both (vslamRansac.cpp:314)
+    assert g.addFeature(2.0, 3.0) == 0 and o.addFeature(2.0, 3.0) == 0
+    assert g.state_dim() == o.state_dim() == 14 + 6 * 20
+    assert_state_close(g, o, ctx="after addFeature")
+    assert_tables_equal(g, o, ctx="after addFeature")
+    for i in range(20):
+        assert np.array_equal(g.template(i), o.template(i))
+        assert np.array_equal(g.returnCentrPatchIndx(i), np.array(o.feature(i).center))
+
+
+@pytest.mark.parametrize("n_features,hard", [(12, False), (50, False), (70, True)])
+def test_step_by_step_parity(gpu_pkg, orc, n_features, hard):
+    """predict / match / update, each stage compared, GPU state re-seeded from the oracle each frame."""
+    sc = _scene(gpu_pkg, n_features=n_features, n_frames=7, seed=100 + n_features, hard=hard)
+    g, o = make_pair(gpu_pkg, orc, sc)
+    seed_features(g, sc); seed_features(o, sc)
+    worst = [0.0, 0.0]
+    for t in range(1, sc.n_frames):
+        mu, S = o.get_full()
+        g.set_full(mu, S)  # identical inputs
+        img = sc.frame(t)
+        g.captureNewFrame(img, sc.stamps[t]); o.captureNewFrame(img, sc.stamps[t])
+        assert g.getDt() == o.getDt()
+        g.predict(); o.predict()
+        assert_state_close(g, o, ctx=f"frame {t} predict")
+        assert_tables_equal(g, o, fields=("is_in_innovation", "position_in_z", "remove_flag"), ctx=f"frame {t} predict")
+        Sg, So = g.S_blocks(), o.S_blocks()
+        assert relerr(Sg, So) <= TOL
+        for i in range(g.numOfFeatures()):
+            a, b = g.feature(i), o.feature(i)
+            if b.is_in_innovation:
+                assert relerr(list(a.h), list(b.h)) <= TOL
+                assert relerr(list(a.H), list(b.H)) <= TOL, f"H of feature {i}"
+        ng = g.match(); no = o.match()
+        assert ng == no
+        for i in range(g.numOfFeatures()):
+            a, b = g.feature(i), o.feature(i)
+            assert a.is_in_innovation == b.is_in_innovation and a.n_tot == b.n_tot
+            assert tuple(a.center) == tuple(b.center), f"frame {t} feature {i} match {tuple(a.center)} vs {tuple(b.center)}"
+            assert tuple(a.z) == tuple(b.z)
+            assert a.last_ncc == b.last_ncc, "NCC score must be bit-identical"
+            if b.is_in_innovation:
+                assert np.array_equal(g.template(i, 1), o.template(i, 1))
+        picks = sc.picks(t, n_features)
+        g.update_after_match(picks); o.update_after_match(picks)
+        sg, so = g.stats(), o.stats()
+        for f in ("n_matched", "n_li", "n_hi", "ransac_hypotheses", "n_removed", "topup_request"):
+            assert getattr(sg, f) == getattr(so, f), f"frame {t} stat {f}: {getattr(sg, f)} vs {getattr(so, f)}"
+        assert_tables_equal(g, o, ctx=f"frame {t} update")
+        em, es = assert_state_close(g, o, ctx=f"frame {t} update")
+        worst = [max(worst[0], em), max(worst[1], es)]
+    print(f"N={n_features} hard={hard}: worst per-step rel err mu {worst[0]:.2e} Sigma {worst[1]:.2e}; "
+          f"oracle min decision margin {o.min_margin():.3g}")
+
+
+def test_free_running_trajectory(gpu_pkg, orc):
+    """No re-seeding: both filters run 12 frames on their own state; drift must stay inside tolerance."""
+    sc = _scene(gpu_pkg, n_features=40, n_frames=13, seed=77)
+    g, o = make_pair(gpu_pkg, orc, sc)
+    seed_features(g, sc); seed_features(o, sc)
+    for t in range(1, sc.n_frames):
+        img = sc.frame(t)
+        for f in (g, o):
+            f.captureNewFrame(img, sc.stamps[t])
+            f.predict()
+            f.update(sc.picks(t, 40))
+        assert_tables_equal(g, o, ctx=f"frame {t}")
+        assert_state_close(g, o, tol=1e-8, ctx=f"frame {t} free-running")
+    assert abs(g.Covariance_Parameter() - o.Covariance_Parameter()) <= 1e-9 * abs(o.Covariance_Parameter())
+
+
+def test_multi_block_update(gpu_pkg, orc):
+    """More than 64 matched features: the stacked update spans several 128-row blocks."""
+    sc = _scene(gpu_pkg, n_features=150, n_frames=3, seed=5)
+    g, o = make_pair(gpu_pkg, orc, sc)
+    seed_features(g, sc); seed_features(o, sc)
+    for t in range(1, 3):
+        mu, S = o.get_full(); g.set_full(mu, S)
+        img = sc.frame(t)
+        for f in (g, o):
+            f.captureNewFrame(img, sc.stamps[t]); f.predict(); f.update(sc.picks(t, 150))
+        assert g.stats().n_li == o.stats().n_li and g.stats().n_li > 64
+        assert_tables_equal(g, o, ctx=f"frame {t}")
+        assert_state_close(g, o, ctx=f"frame {t} multi-block")
+
+
+def test_remove_feature_and_controls(gpu_pkg, orc):
+    sc = _scene(gpu_pkg, n_features=16, n_frames=3, seed=9)
+    g, o = make_pair(gpu_pkg, orc, sc)
+    seed_features(g, sc); seed_features(o, sc)
+    for f in (g, o):
+        f.removeFeature(3); f.removeFeature(0); f.removeFeature(f.numOfFeatures() - 1)
+    assert_tables_equal(g, o, ctx="after remove"); assert_state_close(g, o, ctx="after remove")
+    img = sc.frame(1)
+    for f in (g, o):
+        f.captureNewFrame(img, sc.stamps[1])
+        f.predict(dv=(0.01, -0.02, 0.005), dw=(0.002, 0.001, -0.003), vcontrol=True)
+    assert_state_close(g, o, ctx="predict with controls")
+    for f in (g, o):
+        f.update(sc.picks(1, 16))
+    assert_tables_equal(g, o, ctx="update after remove"); assert_state_close(g, o, ctx="update after remove")
+
+
+def test_unsupported_configs_fail_loudly(gpu_pkg):
+    for over in (dict(kernel_size=3), dict(scale=2), dict(forsePlane=1)):
+        cfg = gpu_pkg.default_config(xyz_conversion=0, **over)
+        with pytest.raises(gpu_pkg.EkfError):
+            gpu_pkg.VSlamFilter(cfg)
