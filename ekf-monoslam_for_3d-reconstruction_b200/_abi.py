@@ -52,3 +52,11 @@ class EkfStepStats(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "n_in_innovation_predict", "n_matched", "n_li", "n_hi", "ransac_hypotheses", "n_removed",
         "topup_request", "blur_requests")] + [("kernel_launches", C.c_int64)]
+
+
+PROF_CLASSES = ("predict", "match", "ransac", "gather_W", "factor_S", "V_trsm", "downdate_gemm", "quat_normalise",
+                "hi_rescue", "bookkeeping", "add_remove", "spare")
+
+
+class EkfProfile(C.Structure):
+    _fields_ = [("ms", C.c_double * 12), ("launches", C.c_int64 * 12)]

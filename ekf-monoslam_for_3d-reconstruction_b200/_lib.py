@@ -46,6 +46,9 @@ SIGNATURES = {
     "ekf_set_full": (_i, [_vp, _vp, _vp, _i]),
     "ekf_get_S_blocks": (_i, [_vp, _vp]),
     "ekf_match_batch": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _f, _f, _f, _vp, _vp, _vp]),
+    "ekf_set_profiling": (_i, [_vp, _i]),
+    "ekf_get_profile": (_i, [_vp, _P(_abi.EkfProfile), _i]),
+    "ekf_set_symmetric_downdate": (_i, [_vp, _i]),
     "ekf_build_info": (C.c_char_p, []),
 }
 

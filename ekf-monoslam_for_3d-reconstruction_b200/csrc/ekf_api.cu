@@ -43,6 +43,13 @@ struct ekf_handle {
   long long launches = 0;
   std::string err;
   std::vector<DeletedPatch> deleted;
+  // per-kernel-class CUDA-event timing (ekf_set_profiling)
+  bool prof_on = false;
+  struct ProfRec { int cls; int nl; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[EKF_PROF_CLASSES] = {0};
+  long long prof_launches[EKF_PROF_CLASSES] = {0};
   // host cache of the feature table (valid when cache_ok)
   bool cache_ok = false;
   std::vector<int> c_pos, c_coding, c_innov, c_li, c_hi, c_removef, c_ntot, c_nfind, c_real, c_posz;
@@ -61,6 +68,34 @@ static int ekf_fail_cuda(ekf_handle* h, cudaError_t e, const char* what, const c
 static int ekf_fail(ekf_handle* h, int code, const char* msg) {
   if (h) h->err = msg;
   return code;
+}
+
+// ---- profiling helpers: one event pair per kernel class instance -----------------------------
+static cudaEvent_t prof_event(ekf_handle* h) {
+  if (!h->prof_pool.empty()) { cudaEvent_t e = h->prof_pool.back(); h->prof_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct ProfScope {
+  ekf_handle* h; int cls; long long l0; cudaEvent_t a;
+  ProfScope(ekf_handle* hh, int c) : h(hh), cls(c), l0(hh->launches), a(nullptr) {
+    if (h->prof_on) { a = prof_event(h); cudaEventRecord(a, h->stream); }
+  }
+  ~ProfScope() {
+    if (h->prof_on) {
+      cudaEvent_t b = prof_event(h);
+      cudaEventRecord(b, h->stream);
+      h->prof_pending.push_back({cls, (int)(h->launches - l0), a, b});
+    }
+  }
+};
+// call after a stream synchronize
+static void prof_flush(ekf_handle* h) {
+  for (auto& r : h->prof_pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { h->prof_ms[r.cls] += ms; h->prof_launches[r.cls] += r.nl; }
+    h->prof_pool.push_back(r.a); h->prof_pool.push_back(r.b);
+  }
+  h->prof_pending.clear();
 }
 
 template <class T>
@@ -107,6 +142,8 @@ int ekf_destroy(ekf_handle* h) {
   if (!h) return EKF_OK;
   cudaSetDevice(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  for (auto& r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : h->prof_pool) cudaEventDestroy(e);
   cudaFree(h->mu); cudaFree(h->muB); cudaFree(h->Sigma); cudaFree(h->SigmaB); cudaFree(h->W); cudaFree(h->nu);
   cudaFree(h->Lb); cudaFree(h->Dinv); cudaFree(h->yb); cudaFree(h->delta); cudaFree(h->mu_i); cudaFree(h->cand);
   cudaFree(h->map_dev); cudaFree(h->keep_dev); cudaFree(h->newpos_dev); cudaFree(h->ctl); cudaFree(h->frame);
@@ -244,8 +281,11 @@ int ekf_predict(ekf_handle* h, const double dv[3], const double dw[3], int vcont
   EKF_CUDA_CHECK(cudaSetDevice(h->device));
   const double z3[3] = {0, 0, 0};
   if (vcontrol) h->noise_cov_factor = 0; else h->noise_cov_factor++;
-  launch_predict(h->stream, h->Sigma, h->ld, h->n, h->mu, h->ft, h->N, h->fv, h->ctl, h->dcfg, h->dT, dv ? dv : z3, dw ? dw : z3,
-                 vcontrol, &h->launches);
+  {
+    ProfScope ps(h, 0);
+    launch_predict(h->stream, h->Sigma, h->ld, h->n, h->mu, h->ft, h->N, h->fv, h->ctl, h->dcfg, h->dT, dv ? dv : z3, dw ? dw : z3,
+                   vcontrol, &h->launches);
+  }
   EKF_CUDA_CHECK(cudaGetLastError());
   h->predicted = true;
   h->cache_ok = false;
@@ -278,7 +318,10 @@ int ekf_match(ekf_handle* h, int* n_matched) {
   if (!h) return EKF_ERR_ARG;
   if (!h->predicted) return ekf_fail(h, EKF_ERR_STATE, "match before predict");
   EKF_CUDA_CHECK(cudaSetDevice(h->device));
-  launch_match_filter(h->stream, h->ft, h->N, h->fv, h->dcfg, &h->launches);
+  {
+    ProfScope ps(h, 1);
+    launch_match_filter(h->stream, h->ft, h->N, h->fv, h->dcfg, &h->launches);
+  }
   EKF_CUDA_CHECK(cudaGetLastError());
   h->cache_ok = false;
   if (n_matched) {
@@ -347,6 +390,30 @@ static int remove_features(ekf_handle* h, const std::vector<int>& victims) {
   return EKF_OK;
 }
 
+// One stacked update over `cnt` selected features (ft.sel), block by block (see ekf_update.cu).
+static int stacked_update(ekf_handle* h, int cnt) {
+  if (cnt <= 0) return 0;
+  cudaStream_t st = h->stream;
+  cudaMemsetAsync(h->delta, 0, sizeof(double) * (size_t)h->n, st);
+  for (int f0 = 0; f0 < cnt; f0 += EKF_UB / 2) {
+    { ProfScope ps(h, 3); launch_blk_gather(st, h->Sigma, h->ld, h->n, h->ft, f0, cnt, h->delta, h->W, h->nu, &h->launches); }
+    { ProfScope ps(h, 4); launch_blk_factor(st, h->W, h->ft, f0, cnt, h->nu, h->dcfg, h->Lb, h->Dinv, h->yb, h->ctl, &h->launches); }
+    { ProfScope ps(h, 5); launch_blk_V(st, h->W, h->n, h->Lb, h->Dinv, h->yb, h->delta, &h->launches); }
+    {
+      ProfScope ps(h, 6);
+      const int rc = launch_gemm_nt_sub(st, h->Sigma, h->ld, h->W, EKF_UB, h->W, EKF_UB, h->n, h->n, EKF_UB, nullptr, h->lower_only,
+                                        &h->launches);
+      if (rc) return rc;
+    }
+  }
+  {
+    ProfScope ps(h, 7);
+    launch_apply_delta(st, h->mu, h->delta, h->n, &h->launches);
+    launch_quat_normalize(st, h->Sigma, h->ld, h->n, h->mu, h->ctl, &h->launches);
+  }
+  return 0;
+}
+
 int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
   if (!h || n_picks < 0 || (n_picks > 0 && !picks)) return EKF_ERR_ARG;
   if (!h->predicted) return ekf_fail(h, EKF_ERR_STATE, "update before predict");
@@ -362,34 +429,40 @@ int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
   if (n_picks > 0) EKF_CUDA_CHECK(cudaMemcpyAsync(h->picks_dev, picks, sizeof(uint32_t) * n_picks, cudaMemcpyHostToDevice, st));
   DevCtl hc;
   // 1-point RANSAC, then the low-innovation update
-  launch_ransac(st, h->Sigma, h->ld, h->n, h->mu, h->ft, h->N, h->ctl, h->dcfg, h->picks_dev, n_picks, h->mu_i, h->cand, &h->launches);
+  {
+    ProfScope ps(h, 2);
+    launch_ransac(st, h->Sigma, h->ld, h->n, h->mu, h->ft, h->N, h->ctl, h->dcfg, h->picks_dev, n_picks, h->mu_i, h->cand, &h->launches);
+  }
   EKF_CUDA_CHECK(cudaMemcpyAsync(&hc, h->ctl, sizeof hc, cudaMemcpyDeviceToHost, st));
   EKF_CUDA_CHECK(cudaStreamSynchronize(st));
   const int n_li = hc.n_li;
   if (n_li > 0) {
-    int rc = launch_stacked_update(st, h->Sigma, h->ld, h->n, h->mu, h->ft, n_li, h->ctl, h->dcfg, h->W, h->nu, h->Lb, h->Dinv,
-                                   h->yb, h->delta, h->lower_only, &h->launches);
+    int rc = stacked_update(h, n_li);
     if (rc) return ekf_fail_cuda(h, (cudaError_t)rc, "stacked update (li)", __FILE__, __LINE__);
-    launch_quat_normalize(st, h->Sigma, h->ld, h->n, h->mu, h->ctl, &h->launches);
   }
   // high-innovation rescue and second update
-  launch_hi_rescue(st, h->Sigma, h->ld, h->mu, h->ft, h->N, h->ctl, h->dcfg, &h->launches);
+  {
+    ProfScope ps(h, 8);
+    launch_hi_rescue(st, h->Sigma, h->ld, h->mu, h->ft, h->N, h->ctl, h->dcfg, &h->launches);
+  }
   EKF_CUDA_CHECK(cudaMemcpyAsync(&hc, h->ctl, sizeof hc, cudaMemcpyDeviceToHost, st));
   EKF_CUDA_CHECK(cudaStreamSynchronize(st));
   const int n_hi = hc.n_hi;
   if (n_hi > 0) {
-    int rc = launch_stacked_update(st, h->Sigma, h->ld, h->n, h->mu, h->ft, n_hi, h->ctl, h->dcfg, h->W, h->nu, h->Lb, h->Dinv,
-                                   h->yb, h->delta, h->lower_only, &h->launches);
+    int rc = stacked_update(h, n_hi);
     if (rc) return ekf_fail_cuda(h, (cudaError_t)rc, "stacked update (hi)", __FILE__, __LINE__);
-    launch_quat_normalize(st, h->Sigma, h->ld, h->n, h->mu, h->ctl, &h->launches);
   }
   // book-keeping + packed result record
   int* outi_dev = reinterpret_cast<int*>(h->out_dev + 210);
-  launch_bookkeeping(st, h->Sigma, h->ld, h->mu, h->ft, h->N, h->ctl, h->dcfg, h->out_dev, outi_dev, &h->launches);
+  {
+    ProfScope ps(h, 9);
+    launch_bookkeeping(st, h->Sigma, h->ld, h->mu, h->ft, h->N, h->ctl, h->dcfg, h->out_dev, outi_dev, &h->launches);
+  }
   EKF_CUDA_CHECK(cudaGetLastError());
   const size_t bytes = sizeof(double) * 210 + sizeof(int) * (16 + 3 * (size_t)h->N);
   EKF_CUDA_CHECK(cudaMemcpyAsync(h->out_host, h->out_dev, bytes, cudaMemcpyDeviceToHost, st));
   EKF_CUDA_CHECK(cudaStreamSynchronize(st));
+  prof_flush(h);
   const int* outi = reinterpret_cast<const int*>(h->out_host + 210);
   h->stats.n_in_innovation_predict = outi[0];
   h->stats.n_matched = outi[1];
@@ -550,6 +623,28 @@ int ekf_get_step_stats(ekf_handle* h, ekf_step_stats* out) {
   if (!h || !out) return EKF_ERR_ARG;
   h->stats.kernel_launches = h->launches;
   *out = h->stats;
+  return EKF_OK;
+}
+int ekf_set_profiling(ekf_handle* h, int on) {
+  if (!h) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  prof_flush(h);
+  h->prof_on = on != 0;
+  return EKF_OK;
+}
+int ekf_get_profile(ekf_handle* h, ekf_profile* out, int reset) {
+  if (!h || !out) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  prof_flush(h);
+  for (int c = 0; c < EKF_PROF_CLASSES; ++c) { out->ms[c] = h->prof_ms[c]; out->launches[c] = h->prof_launches[c]; }
+  if (reset) for (int c = 0; c < EKF_PROF_CLASSES; ++c) { h->prof_ms[c] = 0; h->prof_launches[c] = 0; }
+  return EKF_OK;
+}
+int ekf_set_symmetric_downdate(ekf_handle* h, int on) {
+  if (!h) return EKF_ERR_ARG;
+  h->lower_only = on ? 1 : 0;
   return EKF_OK;
 }
 int ekf_get_full(ekf_handle* h, double* mu, double* sigma, int ld) {

@@ -457,24 +457,24 @@ void launch_hi_rescue(cudaStream_t st, const double* Sigma, int ld, const double
   k_hi_rescue<<<fb, 128, 0, st>>>(Sigma, ld, mu, ft, N, ctl, cfg);
   *launches += 1;
 }
-// One stacked update over `cnt` selected features (ft.sel), block by block.
-int launch_stacked_update(cudaStream_t st, double* Sigma, int ld, int n, double* mu, FeatTab ft, int cnt, DevCtl* ctl,
-                          const DevCfg& cfg, double* W, double* nu, double* Lb, double* Dinv, double* yb, double* delta,
-                          int lower_only, long long* launches) {
-  if (cnt <= 0) return 0;
-  cudaMemsetAsync(delta, 0, sizeof(double) * (size_t)n, st);
-  const int half = EKF_UB / 2;
-  for (int f0 = 0; f0 < cnt; f0 += half) {
-    k_blk_gather<<<(n + 31) / 32, 256, 0, st>>>(Sigma, ld, n, ft, f0, cnt, delta, W, nu);
-    k_blk_factor<<<1, FACT_THREADS, kFactSmem, st>>>(W, ft, f0, cnt, nu, cfg.sigma_pixel_2, Lb, Dinv, yb, ctl);
-    k_blk_V<<<(n + VT_ROWS - 1) / VT_ROWS, VT_THREADS, kVSmem, st>>>(W, n, Lb, Dinv, yb, delta);
-    *launches += 3;
-    const int rc = launch_gemm_nt_sub(st, Sigma, ld, W, EKF_UB, W, EKF_UB, n, n, EKF_UB, nullptr, lower_only, launches);
-    if (rc) return rc;
-  }
+void launch_blk_gather(cudaStream_t st, const double* Sigma, int ld, int n, FeatTab ft, int f0, int cnt, const double* delta,
+                       double* W, double* nu, long long* launches) {
+  k_blk_gather<<<(n + 31) / 32, 256, 0, st>>>(Sigma, ld, n, ft, f0, cnt, delta, W, nu);
+  *launches += 1;
+}
+void launch_blk_factor(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const double* nu, const DevCfg& cfg,
+                       double* Lb, double* Dinv, double* yb, DevCtl* ctl, long long* launches) {
+  k_blk_factor<<<1, FACT_THREADS, kFactSmem, st>>>(W, ft, f0, cnt, nu, cfg.sigma_pixel_2, Lb, Dinv, yb, ctl);
+  *launches += 1;
+}
+void launch_blk_V(cudaStream_t st, double* W, int n, const double* Lb, const double* Dinv, const double* yb, double* delta,
+                  long long* launches) {
+  k_blk_V<<<(n + VT_ROWS - 1) / VT_ROWS, VT_THREADS, kVSmem, st>>>(W, n, Lb, Dinv, yb, delta);
+  *launches += 1;
+}
+void launch_apply_delta(cudaStream_t st, double* mu, const double* delta, int n, long long* launches) {
   k_apply_delta<<<(n + 255) / 256, 256, 0, st>>>(mu, delta, n);
   *launches += 1;
-  return 0;
 }
 void launch_bookkeeping(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, DevCtl* ctl,
                         const DevCfg& cfg, double* outd, int* outi, long long* launches) {

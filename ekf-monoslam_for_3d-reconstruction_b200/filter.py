@@ -150,6 +150,18 @@ class VSlamFilter:
         self._ck(self.L.ekf_get_S_blocks(self.h, _ptr(out)))
         return out
 
+    def set_profiling(self, on=True):
+        self._ck(self.L.ekf_set_profiling(self.h, int(bool(on))))
+
+    def profile(self, reset=True):
+        """dict class -> (ms, launches) accumulated since the last reset."""
+        p = _abi.EkfProfile()
+        self._ck(self.L.ekf_get_profile(self.h, C.byref(p), int(bool(reset))))
+        return {name: (p.ms[i], p.launches[i]) for i, name in enumerate(_abi.PROF_CLASSES)}
+
+    def set_symmetric_downdate(self, on=True):
+        self._ck(self.L.ekf_set_symmetric_downdate(self.h, int(bool(on))))
+
     def set_stream(self, cuda_stream_ptr):
         self._ck(self.L.ekf_set_stream(self.h, C.c_void_p(int(cuda_stream_ptr) if cuda_stream_ptr else 0)))
 

@@ -174,6 +174,21 @@ int ekf_match_batch(const uint8_t* frames, int n_frames, int width, int height, 
                     const double* h, const double* S, float sigma_size, float ncc_threshold,
                     float search_clamp, int32_t* out_uv, float* out_score, void* stream);
 
+/* ---- per-kernel timing (CUDA events on the handle's stream; off by default) ---------------------- */
+#define EKF_PROF_CLASSES 12
+typedef struct ekf_profile {
+  /* classes: 0 predict_cov+features, 1 match, 2 ransac, 3 gather W, 4 factor S, 5 V=W L^-T,
+   * 6 downdate GEMM (DMMA), 7 quat normalise, 8 hi rescue, 9 bookkeeping, 10 add/remove, 11 spare */
+  double ms[EKF_PROF_CLASSES];
+  int64_t launches[EKF_PROF_CLASSES];
+} ekf_profile;
+/* on != 0: bracket every kernel class with CUDA events; totals accumulate until read. */
+int ekf_set_profiling(ekf_handle* h, int on);
+/* Copies the accumulated totals and, if reset != 0, clears them. */
+int ekf_get_profile(ekf_handle* h, ekf_profile* out, int reset);
+/* 0 = full-square downdate; 1 = lower-triangle tiles + mirrored store (Sigma is symmetrised). */
+int ekf_set_symmetric_downdate(ekf_handle* h, int on);
+
 /* Library version / build info: returns a static string naming the compiled arch. */
 const char* ekf_build_info(void);
 

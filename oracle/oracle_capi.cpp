@@ -57,6 +57,8 @@ struct Base {
   virtual double cov_param() = 0;
   virtual double dt() = 0;
   virtual double min_margin() = 0;
+  virtual void import_state(int, int, const double*, const double*, const int*, const int*, const int*, const int*,
+                            const int*, const float*, const uint8_t*, int) = 0;
 };
 
 template <class S, class MF>
@@ -164,6 +166,26 @@ struct Impl : Base {
   double cov_param() override { return double(f.Covariance_Parameter()); }
   double dt() override { return f.dT; }
   double min_margin() override { return f.min_margin; }
+  // Replace mu / Sigma / the patch list wholesale (tests and the bench baseline seed large maps this
+  // way: the dense addFeature of the reference costs O(n^3) per feature).
+  void import_state(int n, int N, const double* mu, const double* sg, const int* pos, const int* coding, const int* ntot,
+                    const int* nfind, const int* real, const float* centers, const uint8_t* tmpl, int patchnumbre) override {
+    f.mu = Mat<S>(n, 1);
+    f.Sigma = Mat<S>(n, n);
+    for (int i = 0; i < n; ++i) f.mu[i] = S(mu[i]);
+    for (size_t i = 0; i < size_t(n) * n; ++i) f.Sigma.d[i] = S(sg[i]);
+    f.patches.clear();
+    const int w = f.windowsSize;
+    for (int i = 0; i < N; ++i) {
+      Patch<S> p;
+      p.w = w;
+      p.patch.assign(tmpl + size_t(i) * w * w, tmpl + size_t(i + 1) * w * w);
+      p.position_in_state = pos[i]; p.coding = coding[i] != 0; p.n_tot = ntot[i]; p.n_find = nfind[i];
+      p.real_index = real[i]; p.center_x = centers[2 * i]; p.center_y = centers[2 * i + 1];
+      f.patches.push_back(p);
+    }
+    f.patchnumbre = patchnumbre;
+  }
 };
 
 }  // namespace
@@ -229,6 +251,12 @@ void orc_match_batch(const uint8_t* frames, int n_frames, int width, int height,
     if (kind_mf == 1) { Filter<double, double> filt(c); run(filt); }
     else { Filter<double, float> filt(c); run(filt); }
   }
+}
+
+void orc_import_state(void* h, int n, int N, const double* mu, const double* sg, const int* pos, const int* coding,
+                      const int* ntot, const int* nfind, const int* real, const float* centers, const uint8_t* tmpl,
+                      int patchnumbre) {
+  static_cast<Base*>(h)->import_state(n, N, mu, sg, pos, coding, ntot, nfind, real, centers, tmpl, patchnumbre);
 }
 
 int orc_num_threads() {

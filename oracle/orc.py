@@ -63,6 +63,7 @@ def lib(omp=False):
         "orc_get_dt": (f64, [vp]),
         "orc_min_margin": (f64, [vp]),
         "orc_match_batch": (None, [vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, f32, f32, f32, vp, vp, i32]),
+        "orc_import_state": (None, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]),
         "orc_num_threads": (i32, []),
         "orc_set_num_threads": (None, [i32]),
     }
@@ -184,6 +185,23 @@ class OracleFilter:
 
     def min_margin(self):
         return self.L.orc_min_margin(self.h)
+
+    def import_from(self, other):
+        """Copy mu, Sigma and the feature table of another filter object (product or oracle) that
+        offers get_full / feature / template.  Used to seed large maps without the dense O(n^3)
+        addFeature of the reference."""
+        mu, S = other.get_full()
+        N = other.numOfFeatures()
+        w = self.cfg.window_size
+        feats = [other.feature(i) for i in range(N)]
+        i32 = lambda f: np.ascontiguousarray([getattr(x, f) for x in feats], dtype=np.int32)  # noqa: E731
+        pos, cod, ntot, nfind, real = (i32(f) for f in ("position_in_state", "coding", "n_tot", "n_find", "real_index"))
+        cen = np.ascontiguousarray([[x.center[0], x.center[1]] for x in feats], dtype=np.float32).reshape(-1)
+        tm = np.ascontiguousarray(np.stack([other.template(i) for i in range(N)]) if N else np.zeros((0, w, w)), dtype=np.uint8)
+        mu = np.ascontiguousarray(mu); S = np.ascontiguousarray(S)
+        nxt = int(real.max()) + 1 if N else 1
+        self.L.orc_import_state(self.h, mu.size, N, _ptr(mu), _ptr(S), _ptr(pos), _ptr(cod), _ptr(ntot), _ptr(nfind),
+                                _ptr(real), _ptr(cen), _ptr(tm), nxt)
 
 
 def match_batch(frames, templates, h, S, sigma_size=3.0, ncc_threshold=0.8, search_clamp=20.0, kind_mf=0, omp=True):
