@@ -5,18 +5,18 @@
 // rank-k downdate Sigma - V V^T: 2 n^2 k flops, read + write of Sigma (16 n^2 bytes).
 //
 // sm_100a has no tcgen05 kind for fp64; the fp64 tensor path is mma.sync.m8n8k4.f64 (SASS
-// DMMA.8x8x4).  Kernel shape: 128 x 128 output tile per CTA, 8 warps (2 x 4), each warp a 64 x 32
+// DMMA.8x8x4).  Kernel shape: 128 x 64 output tile per CTA, 4 warps (2 x 2), each warp a 64 x 32
 // sub-tile = 8 x 4 DMMA tiles (64 accumulator doubles per thread); K is consumed in 16-wide slabs
 // staged global -> shared with cp.async (3 stages), rows padded to 20 doubles so the 8-row x 4-col
 // fragment reads are bank-conflict free (row*20 mod 16 covers 0,4,8,12).
 #include "ekf_kernels.h"
 
 #define GT_M 128
-#define GT_N 128
+#define GT_N 64
 #define GT_K 16
 #define GT_LD 20
 #define GT_STAGES 3
-#define GT_THREADS 256
+#define GT_THREADS 128
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -33,56 +33,67 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 }
 
 // C[M x N] (ldc) -= A[M x K] (lda, K contiguous) * B[N x K]^T (ldb, K contiguous).
-// K is read from *kdev when kdev != nullptr (device-known row count), else from kconst; it must be
-// a multiple of 2 and the buffers must be readable (zero padded) up to the next multiple of GT_K.
-// lower_only: skip tiles strictly above the diagonal and mirror the strictly-lower tiles into the
-// upper triangle (C symmetric on input => symmetric on output).
-__global__ void __launch_bounds__(GT_THREADS, 1)
+// K (kconst, or *kdev when kdev != nullptr) must be even; operands are zero-filled past K.
+// The accumulators are initialised with the C tile (loaded while the first cp.async stages are in
+// flight) and the B fragments are negated, so D = C + A (-B)^T needs no read in the epilogue.
+// Two CTAs per SM (128 threads, 92 KB smem each) overlap one tile's C traffic with the other's DMMAs.
+// lower_only: skip tiles entirely above the diagonal and mirror the strictly-lower elements into
+// the upper triangle (C symmetric on input => symmetric on output).
+__global__ void __launch_bounds__(GT_THREADS, 2)
 k_gemm_nt_sub(double* __restrict__ C, int ldc, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
               int M, int N, int kconst, const int* __restrict__ kdev, int lower_only) {
   extern __shared__ __align__(16) double gsm[];
   const int K = kdev ? *kdev : kconst;
   if (K <= 0) return;
   const int tm = blockIdx.y, tn = blockIdx.x;
-  if (lower_only && tn > tm) return;
   const int m0 = tm * GT_M, n0 = tn * GT_N;
-  double* As = gsm;                                   // [stages][128][20]
-  double* Bs = gsm + GT_STAGES * GT_M * GT_LD;        // [stages][128][20]
+  if (lower_only && n0 > m0 + GT_M - 1) return;
+  double* As = gsm;                                   // [stages][GT_M][GT_LD]
+  double* Bs = gsm + GT_STAGES * GT_M * GT_LD;        // [stages][GT_N][GT_LD]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;            // 2 x 4 warps
+  const int wm = warp >> 1, wn = warp & 1;            // 2 x 2 warps, each 64 x 32
   const int g = lane >> 2, t4 = lane & 3;
-
-  double acc[8][4][2];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
   const int ktiles = (K + GT_K - 1) / GT_K;
   auto load_stage = [&](int kt, int stage) {
     const int k0 = kt * GT_K;
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int chunk = tid + it * GT_THREADS;       // 0..1023
+    for (int it = 0; it < (GT_M * 8) / GT_THREADS; ++it) {
+      const int chunk = tid + it * GT_THREADS;
       const int row = chunk >> 3, cc = (chunk & 7) * 2;
-      {
-        const int gr = m0 + row;
-        const bool ok = (gr < M) && (k0 + cc < K);
-        const double* src = A + (size_t)(ok ? gr : 0) * lda + (ok ? k0 + cc : 0);
-        cp_async16(As + ((size_t)stage * GT_M + row) * GT_LD + cc, src, ok ? 16 : 0);
-      }
-      {
-        const int gr = n0 + row;
-        const bool ok = (gr < N) && (k0 + cc < K);
-        const double* src = B + (size_t)(ok ? gr : 0) * ldb + (ok ? k0 + cc : 0);
-        cp_async16(Bs + ((size_t)stage * GT_N + row) * GT_LD + cc, src, ok ? 16 : 0);
-      }
+      const int gr = m0 + row;
+      const bool ok = (gr < M) && (k0 + cc < K);
+      const double* src = A + (size_t)(ok ? gr : 0) * lda + (ok ? k0 + cc : 0);
+      cp_async16(As + ((size_t)stage * GT_M + row) * GT_LD + cc, src, ok ? 16 : 0);
+    }
+#pragma unroll
+    for (int it = 0; it < (GT_N * 8) / GT_THREADS; ++it) {
+      const int chunk = tid + it * GT_THREADS;
+      const int row = chunk >> 3, cc = (chunk & 7) * 2;
+      const int gr = n0 + row;
+      const bool ok = (gr < N) && (k0 + cc < K);
+      const double* src = B + (size_t)(ok ? gr : 0) * ldb + (ok ? k0 + cc : 0);
+      cp_async16(Bs + ((size_t)stage * GT_N + row) * GT_LD + cc, src, ok ? 16 : 0);
     }
   };
 #pragma unroll
   for (int s = 0; s < GT_STAGES - 1; ++s) {
     if (s < ktiles) load_stage(s, s);
     cp_async_commit();
+  }
+  // accumulators <- C tile
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = m0 + wm * 64 + i * 8 + g;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = n0 + wn * 32 + j * 8 + 2 * t4;
+      double2 v = make_double2(0.0, 0.0);
+      if (r < M && c + 1 < N) v = *reinterpret_cast<const double2*>(C + (size_t)r * ldc + c);
+      else if (r < M && c < N) v.x = C[(size_t)r * ldc + c];
+      acc[i][j][0] = v.x; acc[i][j][1] = v.y;
+    }
   }
   for (int kt = 0; kt < ktiles; ++kt) {
     cp_async_wait<GT_STAGES - 2>();
@@ -98,7 +109,7 @@ k_gemm_nt_sub(double* __restrict__ C, int ldc, const double* __restrict__ A, int
 #pragma unroll
       for (int i = 0; i < 8; ++i) af[i] = as[(size_t)i * 8 * GT_LD + k4 * 4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bf[j] = bs[(size_t)j * 8 * GT_LD + k4 * 4];
+      for (int j = 0; j < 4; ++j) bf[j] = -bs[(size_t)j * 8 * GT_LD + k4 * 4];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -106,8 +117,7 @@ k_gemm_nt_sub(double* __restrict__ C, int ldc, const double* __restrict__ A, int
     }
   }
   cp_async_wait<0>();
-  // epilogue: C -= acc.  Thread holds rows g (+8 i), column pairs 2*t4 (+8 j).
-  const bool mirror = lower_only && (tn < tm);
+  // epilogue: store.  Thread holds rows g (+8 i), column pairs 2*t4 (+8 j).
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = m0 + wm * 64 + i * 8 + g;
@@ -117,15 +127,19 @@ k_gemm_nt_sub(double* __restrict__ C, int ldc, const double* __restrict__ A, int
       const int c = n0 + wn * 32 + j * 8 + 2 * t4;
       if (c >= N) continue;
       double* p = C + (size_t)r * ldc + c;
-      if (c + 1 < N) {
-        double2 v = *reinterpret_cast<double2*>(p);
-        v.x -= acc[i][j][0]; v.y -= acc[i][j][1];
-        *reinterpret_cast<double2*>(p) = v;
-        if (mirror) { C[(size_t)c * ldc + r] = v.x; C[(size_t)(c + 1) * ldc + r] = v.y; }
+      if (!lower_only) {
+        if (c + 1 < N) *reinterpret_cast<double2*>(p) = make_double2(acc[i][j][0], acc[i][j][1]);
+        else *p = acc[i][j][0];
       } else {
-        const double v = *p - acc[i][j][0];
-        *p = v;
-        if (mirror) C[(size_t)c * ldc + r] = v;
+        // only the lower triangle (col <= row) is authoritative; strictly-lower values are mirrored
+        if (c + 1 <= r && c + 1 < N) {
+          *reinterpret_cast<double2*>(p) = make_double2(acc[i][j][0], acc[i][j][1]);
+          C[(size_t)c * ldc + r] = acc[i][j][0];
+          if (c + 1 < r) C[(size_t)(c + 1) * ldc + r] = acc[i][j][1];
+        } else if (c <= r) {
+          *p = acc[i][j][0];
+          if (c < r) C[(size_t)c * ldc + r] = acc[i][j][0];
+        }
       }
     }
   }

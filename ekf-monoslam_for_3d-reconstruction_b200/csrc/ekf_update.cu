@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(128) k_hi_rescue(const double* __restrict__ Si
 // K4a: W_b = Sigma H_b^T for the block of <= 64 selected features starting at sel[f0]
 // (n x EKF_UB, row-major), and nu_b = (z - h) - H_b delta.  One pass over the needed columns of Sigma.
 // ------------------------------------------------------------------------------------------------
+#define GATHER_ROWS 8
 __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ Sigma, int ld, int n, FeatTab ft, int f0, int cnt,
                                                     const double* __restrict__ delta, double* __restrict__ W,
                                                     double* __restrict__ nu) {
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ S
   }
   __syncthreads();
   const int a = tid & (EKF_UB / 2 - 1), rl = tid / (EKF_UB / 2);
-  const int rows_per_cta = 32, rstep = 256 / (EKF_UB / 2);
+  const int rows_per_cta = GATHER_ROWS, rstep = 256 / (EKF_UB / 2);
   const int pos = poss[a], nd = nds[a];
   for (int rq = rl; rq < rows_per_cta; rq += rstep) {
     const int i = blockIdx.x * rows_per_cta + rq;
@@ -249,153 +250,199 @@ __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ S
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4b: S_b = H_b W_b + sigma_px^2 I, Cholesky S_b = L L^T in shared memory (right-looking, one CTA),
-// inverses of the four 32x32 diagonal blocks of L, and y = L^-1 nu.  Unused rows (partial block) are
-// identity so they contribute nothing.
+// K4b(1): S_b = H_b W_b + sigma_px^2 I (EKF_UB x EKF_UB, row-major), one CTA per row.  Unused rows of
+// a partial block are identity so they contribute nothing downstream.
 // ------------------------------------------------------------------------------------------------
-#define FACT_THREADS 512
-#define FACT_LD (EKF_UB + 1)
-__global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __restrict__ W, FeatTab ft, int f0, int cnt,
-                                                             const double* __restrict__ nu, double sigma_pixel_2,
-                                                             double* __restrict__ Lout, double* __restrict__ Dinv,
-                                                             double* __restrict__ yout, DevCtl* ctl) {
-  extern __shared__ __align__(16) double fsm[];
-  double* A = fsm;                          // [EKF_UB][FACT_LD]
-  double* Di = A + EKF_UB * FACT_LD;        // [4][32][33]
-  double* ys = Di + 4 * 32 * 33;            // [EKF_UB]
-  double* ts = ys + EKF_UB;                 // [EKF_UB]
-  const int tid = threadIdx.x;
+__global__ void __launch_bounds__(EKF_UB) k_blk_S(const double* __restrict__ W, FeatTab ft, int f0, int cnt,
+                                                  double sigma_pixel_2, double* __restrict__ Sb) {
+  const int r = blockIdx.x, s = threadIdx.x;
   const int nb = min(EKF_UB / 2, cnt - f0), kr = 2 * nb;
-  // S_b (lower triangle suffices)
-  for (int e = tid; e < EKF_UB * EKF_UB; e += FACT_THREADS) {
-    const int r = e / EKF_UB, s = e % EKF_UB;
-    double v = (r == s) ? 1.0 : 0.0;
-    if (r < kr && s < kr) {
-      const int f = ft.sel[f0 + (r >> 1)];
-      const int pos = ft.pos[f], nd = 7 + (ft.coding[f] ? 3 : 6);
-      const double* hc = ft.Hc + 26 * f + 13 * (r & 1);
-      double acc = 0;
-      for (int c = 0; c < nd; ++c) acc += hc[c] * W[(size_t)ekf_idx13(c, pos) * EKF_UB + s];
-      v = acc + ((r == s) ? sigma_pixel_2 : 0.0);
-    }
-    A[r * FACT_LD + s] = v;
+  double v = (r == s) ? 1.0 : 0.0;
+  if (r < kr && s < kr) {
+    const int f = ft.sel[f0 + (r >> 1)];
+    const int pos = ft.pos[f], nd = 7 + (ft.coding[f] ? 3 : 6);
+    const double* hc = ft.Hc + 26 * f + 13 * (r & 1);
+    double acc = 0;
+    for (int c = 0; c < nd; ++c) acc += hc[c] * W[(size_t)ekf_idx13(c, pos) * EKF_UB + s];
+    v = acc + ((r == s) ? sigma_pixel_2 : 0.0);
   }
-  for (int e = tid; e < EKF_UB; e += FACT_THREADS) ys[e] = nu[e];
-  // Cholesky, column by column
-  for (int j = 0; j < EKF_UB; ++j) {
-    __syncthreads();
-    const double ajj = A[j * FACT_LD + j];
-    const double d = sqrt(ajj);
-    if (tid == 0 && !(ajj > 0.0)) ctl->chol_fail = 1;
-    for (int i = j + 1 + tid; i < EKF_UB; i += FACT_THREADS) A[i * FACT_LD + j] = A[i * FACT_LD + j] / d;
-    __syncthreads();
-    if (tid == 0) A[j * FACT_LD + j] = d;
-    const int m = EKF_UB - j - 1;
-    for (int e = tid; e < m * m; e += FACT_THREADS) {
-      const int i = j + 1 + e / m, c = j + 1 + e % m;
-      if (c <= i) A[i * FACT_LD + c] -= A[i * FACT_LD + j] * A[c * FACT_LD + j];
-    }
-  }
-  __syncthreads();
-  // inverses of the diagonal 32x32 blocks: thread (J, col) solves L_JJ x = e_col
-  if (tid < 128) {
-    const int J = tid >> 5, col = tid & 31;
-    double* X = Di + J * 32 * 33;
-    const double* Lj = A + (J * 32) * FACT_LD + J * 32;
-    for (int i = 0; i < 32; ++i) {
-      double s = (i == col) ? 1.0 : 0.0;
-      if (i < col) { X[i * 33 + col] = 0.0; continue; }
-      for (int dd = col; dd < i; ++dd) s -= Lj[i * FACT_LD + dd] * X[dd * 33 + col];
-      X[i * 33 + col] = s / Lj[i * FACT_LD + i];
-    }
-  }
-  __syncthreads();
-  // y = L^-1 nu, block forward substitution
-  for (int J = 0; J < 4; ++J) {
-    if (tid < 32) {
-      const int r = J * 32 + tid;
-      double s = ys[r];
-      for (int dd = 0; dd < J * 32; ++dd) s -= A[r * FACT_LD + dd] * ys[dd];
-      ts[tid] = s;
-    }
-    __syncthreads();
-    if (tid < 32) {
-      const double* X = Di + J * 32 * 33;
-      double s = 0;
-      for (int dd = 0; dd <= tid; ++dd) s += X[tid * 33 + dd] * ts[dd];
-      ys[J * 32 + tid] = s;
-    }
-    __syncthreads();
-  }
-  for (int e = tid; e < EKF_UB * EKF_UB; e += FACT_THREADS) {
-    const int r = e / EKF_UB, s = e % EKF_UB;
-    Lout[e] = (s <= r) ? A[r * FACT_LD + s] : 0.0;
-  }
-  for (int e = tid; e < 4 * 32 * 32; e += FACT_THREADS) {
-    const int J = e >> 10, r = (e >> 5) & 31, c = e & 31;
-    Dinv[e] = Di[J * 32 * 33 + r * 33 + c];
-  }
-  for (int e = tid; e < EKF_UB; e += FACT_THREADS) yout[e] = ys[e];
+  Sb[r * EKF_UB + s] = v;
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4c: V_b = W_b L^-T in place (rows are independent; 32 rows per CTA, L and the diagonal-block
-// inverses staged in shared memory), and delta += V_b y.
+// K4b(2): Cholesky S_b = L L^T in shared memory (one CTA, right-looking, one barrier pair per
+// column), then Linv = L^-1 by 32x32 blocks (diagonal blocks by substitution, off-diagonal blocks
+// Linv[J][I] = -Dinv_J sum_P L[J][P] Linv[P][I], parked transposed in the unused upper triangle) and
+// y = Linv nu.  Outputs Linv (row-major, zero above the diagonal) and y.
+// ------------------------------------------------------------------------------------------------
+#define FACT_THREADS 1024
+#define FACT_LD (EKF_UB + 1)
+__global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __restrict__ Sb, const double* __restrict__ nu,
+                                                             double* __restrict__ Linv, double* __restrict__ yout, DevCtl* ctl) {
+  extern __shared__ __align__(16) double fsm[];
+  double* A = fsm;                          // [EKF_UB][FACT_LD]; lower: L, strictly upper: Linv^T blocks
+  double* Di = A + EKF_UB * FACT_LD;        // [4][32][33] inverses of the diagonal blocks
+  double* col = Di + 4 * 32 * 33;           // [EKF_UB] scaled pivot column
+  double* Tb = col + EKF_UB;                // [3][32][33] block products
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  for (int e = tid; e < EKF_UB * EKF_UB; e += FACT_THREADS) A[(e >> 7) * FACT_LD + (e & 127)] = Sb[e];
+  for (int j = 0; j < EKF_UB; ++j) {
+    __syncthreads();
+    const double ajj = A[j * FACT_LD + j];
+    if (tid == 0 && !(ajj > 0.0)) ctl->chol_fail = 1;
+    const double d = sqrt(ajj);
+    if (tid > j && tid < EKF_UB) {
+      const double l = A[tid * FACT_LD + j] / d;
+      A[tid * FACT_LD + j] = l;
+      col[tid] = l;
+    }
+    __syncthreads();
+    if (tid == 0) A[j * FACT_LD + j] = d;
+    for (int i0 = j + 1; i0 < EKF_UB; i0 += 32) {
+      const int i = i0 + ty;
+      if (i >= EKF_UB) continue;
+      const double li = col[i];
+      for (int c0 = j + 1; c0 <= i0 + 31 && c0 < EKF_UB; c0 += 32) {
+        const int c = c0 + tx;
+        if (c <= i) A[i * FACT_LD + c] -= li * col[c];
+      }
+    }
+  }
+  __syncthreads();
+  // diagonal-block inverses: thread (J, colm) solves L_JJ x = e_colm
+  if (tid < 128) {
+    const int J = tid >> 5, cm = tid & 31;
+    double* X = Di + J * 32 * 33;
+    const double* Lj = A + (J * 32) * FACT_LD + J * 32;
+    for (int i = 0; i < 32; ++i) {
+      if (i < cm) { X[i * 33 + cm] = 0.0; continue; }
+      double s = (i == cm) ? 1.0 : 0.0;
+      for (int dd = cm; dd < i; ++dd) s -= Lj[i * FACT_LD + dd] * X[dd * 33 + cm];
+      X[i * 33 + cm] = s / Lj[i * FACT_LD + i];
+    }
+  }
+  __syncthreads();
+  // off-diagonal blocks of Linv, by distance from the diagonal.  X(P,I): P == I -> Di[I], else the
+  // block parked at A[(32 I + c)][32 P + r] = Linv[32 P + r][32 I + c].
+  for (int dist = 1; dist < 4; ++dist) {
+    const int nblk = 4 - dist;
+    for (int b = 0; b < nblk; ++b) {       // T = sum_P L[J][P] X(P,I)
+      const int I = b, J = b + dist;
+      double t = 0;
+      for (int P = I; P < J; ++P) {
+        const double* Lrow = A + (size_t)(J * 32 + ty) * FACT_LD + P * 32;
+        if (P == I) {
+          const double* X = Di + I * 32 * 33;
+          for (int dd = 0; dd < 32; ++dd) t += Lrow[dd] * X[dd * 33 + tx];
+        } else {
+          for (int dd = 0; dd < 32; ++dd) t += Lrow[dd] * A[(size_t)(I * 32 + tx) * FACT_LD + P * 32 + dd];
+        }
+      }
+      Tb[(b * 32 + ty) * 33 + tx] = t;
+    }
+    __syncthreads();
+    for (int b = 0; b < nblk; ++b) {       // Linv[J][I] = -Dinv_J T
+      const int I = b, J = b + dist;
+      const double* X = Di + J * 32 * 33;
+      double v = 0;
+      for (int dd = 0; dd <= ty; ++dd) v += X[ty * 33 + dd] * Tb[(b * 32 + dd) * 33 + tx];
+      A[(size_t)(I * 32 + tx) * FACT_LD + J * 32 + ty] = -v;
+    }
+    __syncthreads();
+  }
+  // write Linv and y = Linv nu (one warp per 4 rows, lanes split the dot product)
+  for (int e = tid; e < EKF_UB * EKF_UB; e += FACT_THREADS) {
+    const int r = e >> 7, c = e & 127;
+    double v = 0.0;
+    if (c <= r) {
+      const int J = r >> 5, I = c >> 5;
+      v = (J == I) ? Di[J * 32 * 33 + (r & 31) * 33 + (c & 31)] : A[(size_t)c * FACT_LD + r];
+    }
+    Linv[e] = v;
+  }
+  for (int r = ty; r < EKF_UB; r += 32) {
+    double part = 0;
+    for (int c = tx; c <= r; c += 32) {
+      const int J = r >> 5, I = c >> 5;
+      const double lv = (J == I) ? Di[J * 32 * 33 + (r & 31) * 33 + (c & 31)] : A[(size_t)c * FACT_LD + r];
+      part += lv * nu[c];
+    }
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (tx == 0) yout[r] = part;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4c: V_b = W_b Linv^T in place on the fp64 tensor pipe (DMMA.8x8x4) and delta += V_b y.
+// One CTA = 32 rows x 128 columns, K <= 128 (Linv is lower triangular: column tile c0 only needs
+// k < c0 + 8).  8 warps, warp w owns column tiles 2w, 2w+1 for all four 8-row tiles.
 // ------------------------------------------------------------------------------------------------
 #define VT_ROWS 32
 #define VT_THREADS 256
-__global__ void __launch_bounds__(VT_THREADS) k_blk_V(double* __restrict__ W, int n, const double* __restrict__ Lg,
-                                                      const double* __restrict__ Dinvg, const double* __restrict__ yg,
-                                                      double* __restrict__ delta) {
+#define VT_LD (EKF_UB + 4)
+__device__ __forceinline__ void dmma884u(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(VT_THREADS) k_blk_V(double* __restrict__ W, int n, const double* __restrict__ Linvg,
+                                                      const double* __restrict__ yg, double* __restrict__ delta) {
   extern __shared__ __align__(16) double vsm[];
-  double* Ls = vsm;                          // [EKF_UB][FACT_LD]
-  double* Di = Ls + EKF_UB * FACT_LD;        // [4][32][33]
-  double* Ws = Di + 4 * 32 * 33;             // [VT_ROWS][FACT_LD]
-  double* ys = Ws + VT_ROWS * FACT_LD;       // [EKF_UB]
-  const int tid = threadIdx.x;
+  double* Ls = vsm;                          // [EKF_UB][VT_LD]  Linv
+  double* Ws = Ls + EKF_UB * VT_LD;          // [VT_ROWS][VT_LD] W rows, then V rows
+  double* ys = Ws + VT_ROWS * VT_LD;         // [EKF_UB]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
   const int row0 = blockIdx.x * VT_ROWS;
-  for (int e = tid; e < EKF_UB * EKF_UB; e += VT_THREADS) Ls[(e / EKF_UB) * FACT_LD + (e % EKF_UB)] = Lg[e];
-  for (int e = tid; e < 4 * 32 * 32; e += VT_THREADS) Di[(e >> 10) * 32 * 33 + ((e >> 5) & 31) * 33 + (e & 31)] = Dinvg[e];
-  for (int e = tid; e < VT_ROWS * EKF_UB; e += VT_THREADS) {
-    const int r = e / EKF_UB, c = e % EKF_UB;
-    Ws[r * FACT_LD + c] = (row0 + r < n) ? W[(size_t)(row0 + r) * EKF_UB + c] : 0.0;
+  for (int e = tid; e < EKF_UB * EKF_UB / 2; e += VT_THREADS) {
+    const int r = e >> 6, c = (e & 63) * 2;
+    *reinterpret_cast<double2*>(Ls + r * VT_LD + c) = *reinterpret_cast<const double2*>(Linvg + r * EKF_UB + c);
+  }
+  for (int e = tid; e < VT_ROWS * EKF_UB / 2; e += VT_THREADS) {
+    const int r = e >> 6, c = (e & 63) * 2;
+    double2 v = make_double2(0.0, 0.0);
+    if (row0 + r < n) v = *reinterpret_cast<const double2*>(W + (size_t)(row0 + r) * EKF_UB + c);
+    *reinterpret_cast<double2*>(Ws + r * VT_LD + c) = v;
   }
   for (int e = tid; e < EKF_UB; e += VT_THREADS) ys[e] = yg[e];
   __syncthreads();
-  const int r = tid >> 3, cg = (tid & 7) * 4;  // 32 rows x 8 column groups of 4
-  for (int J = 0; J < 4; ++J) {
-    double u[4];
+  double acc[4][2][2];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) u[q] = Ws[r * FACT_LD + J * 32 + cg + q];
-    for (int dd = 0; dd < J * 32; ++dd) {
-      const double v = Ws[r * FACT_LD + dd];
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) u[q] -= v * Ls[(J * 32 + cg + q) * FACT_LD + dd];
-    }
-    __syncthreads();
+    for (int j = 0; j < 2; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  const int c0 = warp * 16;                  // first column of this warp's two tiles
+  const int kmax = c0 + 16;                  // Linv[c][k] = 0 for k > c
+  for (int k = 0; k < kmax; k += 4) {
+    double af[4], bf[2];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) Ws[r * FACT_LD + J * 32 + cg + q] = u[q];
-    __syncthreads();
-    double vv[4] = {0, 0, 0, 0};
-    const double* X = Di + J * 32 * 33;
-    for (int dd = 0; dd < 32; ++dd) {
-      const double uu = Ws[r * FACT_LD + J * 32 + dd];
+    for (int i = 0; i < 4; ++i) af[i] = Ws[(i * 8 + g) * VT_LD + k + t4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) vv[q] += uu * X[(cg + q) * 33 + dd];  // X lower: zero for dd > cg+q
-    }
-    __syncthreads();
+    for (int j = 0; j < 2; ++j) bf[j] = Ls[(c0 + j * 8 + g) * VT_LD + k + t4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) Ws[r * FACT_LD + J * 32 + cg + q] = vv[q];
-    __syncthreads();
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) dmma884u(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
   }
-  for (int e = tid; e < VT_ROWS * EKF_UB; e += VT_THREADS) {
-    const int rr = e / EKF_UB, c = e % EKF_UB;
-    if (row0 + rr < n) W[(size_t)(row0 + rr) * EKF_UB + c] = Ws[rr * FACT_LD + c];
+  __syncthreads();  // everyone is done reading W rows from Ws
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      *reinterpret_cast<double2*>(Ws + (i * 8 + g) * VT_LD + c0 + j * 8 + 2 * t4) = make_double2(acc[i][j][0], acc[i][j][1]);
+  __syncthreads();
+  for (int e = tid; e < VT_ROWS * EKF_UB / 2; e += VT_THREADS) {
+    const int r = e >> 6, c = (e & 63) * 2;
+    if (row0 + r < n)
+      *reinterpret_cast<double2*>(W + (size_t)(row0 + r) * EKF_UB + c) = *reinterpret_cast<const double2*>(Ws + r * VT_LD + c);
   }
-  if (tid < VT_ROWS && row0 + tid < n) {
-    double s = 0;
-    for (int c = 0; c < EKF_UB; ++c) s += Ws[tid * FACT_LD + c] * ys[c];
-    delta[row0 + tid] += s;
+  // delta += V y: warp w handles rows 4w .. 4w+3
+  for (int rr = 0; rr < 4; ++rr) {
+    const int r = warp * 4 + rr;
+    double part = 0;
+    for (int c = lane; c < EKF_UB; c += 32) part += Ws[r * VT_LD + c] * ys[c];
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0 && row0 + r < n) delta[row0 + r] += part;
   }
 }
 
@@ -436,8 +483,8 @@ __global__ void __launch_bounds__(256) k_bookkeeping(const double* __restrict__ 
 }
 
 // ---- launch wrappers ---------------------------------------------------------------------------
-static const size_t kFactSmem = (size_t)(EKF_UB * FACT_LD + 4 * 32 * 33 + 2 * EKF_UB) * sizeof(double);
-static const size_t kVSmem = (size_t)(EKF_UB * FACT_LD + 4 * 32 * 33 + VT_ROWS * FACT_LD + EKF_UB) * sizeof(double);
+static const size_t kFactSmem = (size_t)(EKF_UB * FACT_LD + 4 * 32 * 33 + EKF_UB + 3 * 32 * 33) * sizeof(double);
+static const size_t kVSmem = (size_t)(EKF_UB * VT_LD + VT_ROWS * VT_LD + EKF_UB) * sizeof(double);
 
 int update_kernels_init() {
   cudaError_t e = cudaFuncSetAttribute(k_blk_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFactSmem);
@@ -459,17 +506,17 @@ void launch_hi_rescue(cudaStream_t st, const double* Sigma, int ld, const double
 }
 void launch_blk_gather(cudaStream_t st, const double* Sigma, int ld, int n, FeatTab ft, int f0, int cnt, const double* delta,
                        double* W, double* nu, long long* launches) {
-  k_blk_gather<<<(n + 31) / 32, 256, 0, st>>>(Sigma, ld, n, ft, f0, cnt, delta, W, nu);
+  k_blk_gather<<<(n + GATHER_ROWS - 1) / GATHER_ROWS, 256, 0, st>>>(Sigma, ld, n, ft, f0, cnt, delta, W, nu);
   *launches += 1;
 }
 void launch_blk_factor(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const double* nu, const DevCfg& cfg,
-                       double* Lb, double* Dinv, double* yb, DevCtl* ctl, long long* launches) {
-  k_blk_factor<<<1, FACT_THREADS, kFactSmem, st>>>(W, ft, f0, cnt, nu, cfg.sigma_pixel_2, Lb, Dinv, yb, ctl);
-  *launches += 1;
+                       double* Sb, double* Linv, double* yb, DevCtl* ctl, long long* launches) {
+  k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(W, ft, f0, cnt, cfg.sigma_pixel_2, Sb);
+  k_blk_factor<<<1, FACT_THREADS, kFactSmem, st>>>(Sb, nu, Linv, yb, ctl);
+  *launches += 2;
 }
-void launch_blk_V(cudaStream_t st, double* W, int n, const double* Lb, const double* Dinv, const double* yb, double* delta,
-                  long long* launches) {
-  k_blk_V<<<(n + VT_ROWS - 1) / VT_ROWS, VT_THREADS, kVSmem, st>>>(W, n, Lb, Dinv, yb, delta);
+void launch_blk_V(cudaStream_t st, double* W, int n, const double* Linv, const double* yb, double* delta, long long* launches) {
+  k_blk_V<<<(n + VT_ROWS - 1) / VT_ROWS, VT_THREADS, kVSmem, st>>>(W, n, Linv, yb, delta);
   *launches += 1;
 }
 void launch_apply_delta(cudaStream_t st, double* mu, const double* delta, int n, long long* launches) {
