@@ -139,6 +139,7 @@ def run_ours(args):
     def new_filter():
         f = pkg.VSlamFilter(cfg, feature_capacity=nfeat + 4, device=local)
         f.set_stream(stream.cuda_stream)
+        f.set_symmetric_downdate(not args.full_square)
         added = seed_filter(f, scene)
         assert added == nfeat, f"seeded {added} of {nfeat}"
         return f
@@ -223,7 +224,9 @@ def run_ours(args):
     out = None
     if rank == 0:
         gemm_ms, gemm_launches = prof["downdate_gemm"]
-        flops_per_launch = 2.0 * n_state * n_state * 128
+        # algorithmic flops of one rank-128 downdate launch: 2 n^2 k for the full square, n (n + 128) k
+        # when only tiles touching the lower triangle are computed (SYRK form)
+        flops_per_launch = 2.0 * n_state * n_state * 128 if args.full_square else 1.0 * n_state * (n_state + 128) * 128
         peak = dgemm_peak_tflops(torch)
         achieved = flops_per_launch * gemm_launches / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
         traffic = None
@@ -246,7 +249,8 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "k_gemm_nt_sub (Sigma -= V V^T, DMMA.8x8x4, K=128 per launch)", "bound": "tensor",
+            "roofline": {"kernel": "k_gemm_nt_sub (Sigma -= V V^T, DMMA.8x8x4, K=128 per launch, "
+                                   + ("full square" if args.full_square else "lower-triangle tiles + mirror") + ")", "bound": "tensor",
                          "achieved": round(achieved, 3), "peak": round(peak, 2), "unit": "TFLOP/s",
                          "frac": round(achieved / peak, 4) if peak > 0 else None, "traffic": traffic,
                          "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no fp64 entry; "
@@ -364,6 +368,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2_n500", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-square", action="store_true", help="downdate all n x n tiles instead of lower triangle + mirror")
     ap.add_argument("--cpu-budget", type=float, default=30.0)
     ap.add_argument("--ref-budget", type=float, default=150.0)
     args = ap.parse_args()

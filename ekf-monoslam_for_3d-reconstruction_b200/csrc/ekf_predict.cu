@@ -111,25 +111,6 @@ __global__ void __launch_bounds__(128) k_predict_features(const double* __restri
       if (ok) {
         ft.h[2 * i] = hi[0]; ft.h[2 * i + 1] = hi[1];
         for (int c = 0; c < 26; ++c) ft.Hc[26 * i + c] = Hc[c];
-        // S block: (Hc * Sigma_sub) * Hc^T + sigma^2 I, Sigma_sub over the 13 (10) dependent states
-        const int nd = 7 + fsz;
-        double Tm[26];
-        for (int b = 0; b < nd; ++b) {
-          const int jb = ekf_idx13(b, pos);
-          double t0 = 0, t1 = 0;
-          for (int c = 0; c < nd; ++c) {
-            const double s = Sigma[(size_t)ekf_idx13(c, pos) * ld + jb];
-            t0 += Hc[c] * s; t1 += Hc[13 + c] * s;
-          }
-          Tm[b] = t0; Tm[13 + b] = t1;
-        }
-        double S[4] = {0, 0, 0, 0};
-        for (int b = 0; b < nd; ++b) {
-          S[0] += Tm[b] * Hc[b]; S[1] += Tm[b] * Hc[13 + b];
-          S[2] += Tm[13 + b] * Hc[b]; S[3] += Tm[13 + b] * Hc[13 + b];
-        }
-        S[0] += cfg.sigma_pixel_2; S[3] += cfg.sigma_pixel_2;
-        for (int c = 0; c < 4; ++c) ft.S2[4 * i + c] = S[c];
       }
     }
     ft.innov[i] = ok; ft.li[i] = 0; ft.hi[i] = 0;  // Patch::setIsInInnovation (Patch.cpp:123-132)
@@ -161,6 +142,34 @@ __global__ void __launch_bounds__(128) k_predict_features(const double* __restri
   if (threadIdx.x == 0) {
     ctl->m_innov = m;
     ctl->ticket = 0;
+  }
+}
+
+// 2x2 diagonal block of St = H Sigma H^T + sigma_px^2 I for every gated-in feature (V:598 restricted
+// to what V:875 consumes).  One warp per feature: lane b < nd forms column b of Hc * Sigma_sub
+// (13 coalesced loads), the 2x2 sums are reduced over lanes with shuffles.
+__global__ void __launch_bounds__(128) k_predict_S2(const double* __restrict__ Sigma, int ld, FeatTab ft, int N, DevCfg cfg) {
+  const int f = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (f >= N || !ft.innov[f]) return;
+  const int pos = ft.pos[f], nd = 7 + (ft.coding[f] ? 3 : 6);
+  const double* hc = ft.Hc + 26 * f;
+  double t0 = 0, t1 = 0, h0 = 0, h1 = 0;
+  if (lane < nd) {
+    const int jb = ekf_idx13(lane, pos);
+    for (int c = 0; c < nd; ++c) {
+      const double sg = Sigma[(size_t)ekf_idx13(c, pos) * ld + jb];
+      t0 += hc[c] * sg; t1 += hc[13 + c] * sg;
+    }
+    h0 = hc[lane]; h1 = hc[13 + lane];
+  }
+  double s00 = t0 * h0, s01 = t0 * h1, s10 = t1 * h0, s11 = t1 * h1;
+  for (int o = 8; o > 0; o >>= 1) {
+    s00 += __shfl_down_sync(0xffffffffu, s00, o, 16); s01 += __shfl_down_sync(0xffffffffu, s01, o, 16);
+    s10 += __shfl_down_sync(0xffffffffu, s10, o, 16); s11 += __shfl_down_sync(0xffffffffu, s11, o, 16);
+  }
+  if (lane == 0) {
+    ft.S2[4 * f + 0] = s00 + cfg.sigma_pixel_2; ft.S2[4 * f + 1] = s01;
+    ft.S2[4 * f + 2] = s10; ft.S2[4 * f + 3] = s11 + cfg.sigma_pixel_2;
   }
 }
 
@@ -387,6 +396,10 @@ void launch_predict(cudaStream_t st, double* Sigma, int ld, int n, double* mu, F
   const int fb = N > 0 ? (N + 127) / 128 : 1;
   k_predict_features<<<fb, 128, 0, st>>>(Sigma, ld, mu, ft, N, fr, ctl, cfg);
   *launches += 2;
+  if (N > 0) {
+    k_predict_S2<<<(N + 3) / 4, 128, 0, st>>>(Sigma, ld, ft, N, cfg);
+    *launches += 1;
+  }
 }
 void launch_quat_normalize(cudaStream_t st, double* Sigma, int ld, int n, double* mu, const DevCtl* ctl, long long* launches) {
   const int nb = 1 + (n - 4 + 255) / 256;

@@ -285,29 +285,59 @@ __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __res
   double* col = Di + 4 * 32 * 33;           // [EKF_UB] scaled pivot column
   double* Tb = col + EKF_UB;                // [3][32][33] block products
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  for (int e = tid; e < EKF_UB * EKF_UB; e += FACT_THREADS) A[(e >> 7) * FACT_LD + (e & 127)] = Sb[e];
-  for (int j = 0; j < EKF_UB; ++j) {
-    __syncthreads();
-    const double ajj = A[j * FACT_LD + j];
-    if (tid == 0 && !(ajj > 0.0)) ctl->chol_fail = 1;
-    const double d = sqrt(ajj);
-    if (tid > j && tid < EKF_UB) {
-      const double l = A[tid * FACT_LD + j] / d;
-      A[tid * FACT_LD + j] = l;
-      col[tid] = l;
-    }
-    __syncthreads();
-    if (tid == 0) A[j * FACT_LD + j] = d;
-    for (int i0 = j + 1; i0 < EKF_UB; i0 += 32) {
-      const int i = i0 + ty;
-      if (i >= EKF_UB) continue;
-      const double li = col[i];
-      for (int c0 = j + 1; c0 <= i0 + 31 && c0 < EKF_UB; c0 += 32) {
-        const int c = c0 + tx;
-        if (c <= i) A[i * FACT_LD + c] -= li * col[c];
+  // The matrix lives in registers during the factorisation: thread (ty, tx) owns the 16 elements
+  // (ty + 32 a, tx + 32 b), a, b in 0..3 (block-cyclic, so every warp stays busy as j advances).
+  // Per column: pivot thread -> sqrt / reciprocal -> barrier -> the 32 owners of column j scale it and
+  // publish it in shared memory -> barrier -> rank-1 update of the registers.  No shared-memory
+  // traffic for the O(k^3) part.
+  __shared__ double s_dinv;
+  double R[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) R[a][b] = Sb[(ty + 32 * a) * EKF_UB + tx + 32 * b];
+#pragma unroll
+  for (int qa = 0; qa < 4; ++qa) {
+    for (int rj = 0; rj < 32; ++rj) {
+      const int j = 32 * qa + rj;
+      if (ty == rj && tx == rj) {
+        const double ajj = R[qa][qa];
+        if (!(ajj > 0.0)) ctl->chol_fail = 1;
+        const double d = sqrt(ajj);
+        R[qa][qa] = d;
+        s_dinv = 1.0 / d;
+      }
+      __syncthreads();
+      if (tx == rj) {
+        const double dinv = s_dinv;
+#pragma unroll
+        for (int a = qa; a < 4; ++a) {
+          const int i = ty + 32 * a;
+          if (i > j) {
+            R[a][qa] *= dinv;
+            col[i] = R[a][qa];
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int a = qa; a < 4; ++a) {
+        const int i = ty + 32 * a;
+        if (i > j) {  // warp-uniform
+          const double li = col[i];
+#pragma unroll
+          for (int b = qa; b <= a; ++b) {
+            const int c = tx + 32 * b;
+            if (c > j && c <= i) R[a][b] -= li * col[c];
+          }
+        }
       }
     }
   }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b <= a; ++b) A[(ty + 32 * a) * FACT_LD + tx + 32 * b] = R[a][b];
   __syncthreads();
   // diagonal-block inverses: thread (J, colm) solves L_JJ x = e_colm
   if (tid < 128) {

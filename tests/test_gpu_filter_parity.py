@@ -94,10 +94,13 @@ def test_free_running_trajectory(gpu_pkg, orc):
     assert abs(g.Covariance_Parameter() - o.Covariance_Parameter()) <= 1e-9 * abs(o.Covariance_Parameter())
 
 
-def test_multi_block_update(gpu_pkg, orc):
-    """More than 64 matched features: the stacked update spans several 128-row blocks."""
+@pytest.mark.parametrize("symmetric", [False, True])
+def test_multi_block_update(gpu_pkg, orc, symmetric):
+    """More than 64 matched features: the stacked update spans several 128-row blocks.  Both
+    downdate modes (full square / lower triangle + mirror) must stay inside the tolerance."""
     sc = _scene(gpu_pkg, n_features=150, n_frames=3, seed=5)
     g, o = make_pair(gpu_pkg, orc, sc)
+    g.set_symmetric_downdate(symmetric)
     seed_features(g, sc); seed_features(o, sc)
     for t in range(1, 3):
         mu, S = o.get_full(); g.set_full(mu, S)
