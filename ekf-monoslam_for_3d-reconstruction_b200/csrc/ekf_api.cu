@@ -184,7 +184,7 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
   h->Ncap = feature_capacity;
   h->ncap = EKF_CAM + 6 * feature_capacity;
   h->ld = (h->ncap + 7) & ~7;
-  const int w2 = cfg->window_size * cfg->window_size;
+  const int w2 = (cfg->window_size * cfg->window_size + 15) & ~15;  // template record stride
   const size_t ssz = (size_t)h->ncap * h->ld;
 #define TRY(x) if ((e = (x)) != cudaSuccess) return bail(e, #x);
   TRY(dalloc(&h->mu, h->ld)) TRY(dalloc(&h->muB, h->ld)) TRY(dalloc(&h->Sigma, ssz)) TRY(dalloc(&h->SigmaB, ssz))
@@ -214,6 +214,7 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
   d.sigma_size_f = (float)cfg->sigma_size; d.quality_ratio = (float)cfg->quality_ratio;
   d.window = cfg->window_size; d.sigma_pixel = cfg->sigma_pixel; d.nhyp0 = cfg->ransac_nhyp0;
   d.forsePlane = cfg->forsePlane; d.abs_int_quirk = cfg->abs_int_quirk;
+  d.tstride = w2;
   // initial state (vslamRansac.cpp:163-216)
   double mu0[EKF_CAM] = {0};
   mu0[3] = 0.0; mu0[4] = 0.0; mu0[5] = -0.707106781; mu0[6] = 0.707106781; mu0[13] = 1;
@@ -378,7 +379,7 @@ static int remove_features(ekf_handle* h, const std::vector<int>& victims) {
     EKF_CUDA_CHECK(cudaMemcpyAsync(h->newpos_dev, newpos.data(), sizeof(int) * N2, cudaMemcpyHostToDevice, h->stream));
   }
   launch_gather_state(h->stream, h->Sigma, h->SigmaB, h->ld, h->mu, h->muB, n2, h->map_dev, &h->launches);
-  launch_gather_features(h->stream, h->ft, h->ftB, N2, h->keep_dev, h->newpos_dev, h->cfg.window_size * h->cfg.window_size, &h->launches);
+  launch_gather_features(h->stream, h->ft, h->ftB, N2, h->keep_dev, h->newpos_dev, h->dcfg.tstride, &h->launches);
   EKF_CUDA_CHECK(cudaGetLastError());
   EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));  // host vectors above go out of scope
   std::swap(h->Sigma, h->SigmaB);
@@ -614,7 +615,7 @@ int ekf_get_template(ekf_handle* h, int idx, int which, uint8_t* out) {
   if (!h || !out || idx < 0 || idx >= h->N) return EKF_ERR_ARG;
   EKF_CUDA_CHECK(cudaSetDevice(h->device));
   const int w2 = h->cfg.window_size * h->cfg.window_size;
-  const uint8_t* src = (which ? h->ft.mpatch : h->ft.patch) + (size_t)idx * w2;
+  const uint8_t* src = (which ? h->ft.mpatch : h->ft.patch) + (size_t)idx * h->dcfg.tstride;
   EKF_CUDA_CHECK(cudaMemcpyAsync(out, src, w2, cudaMemcpyDeviceToHost, h->stream));
   EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   return EKF_OK;

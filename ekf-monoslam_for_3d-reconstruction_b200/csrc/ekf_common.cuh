@@ -33,6 +33,7 @@ struct DevCfg {
   double rho_0, sigma_rho_0;
   float ncc_threshold, search_clamp, sigma_size_f, quality_ratio;
   int window, sigma_pixel, nhyp0, forsePlane, abs_int_quirk;
+  int tstride;  // bytes per template record (window^2 rounded up to 16)
 };
 
 // Device-resident control block.
@@ -71,8 +72,8 @@ struct FeatTab {
   double* h;        // 2 per feature
   double* Hc;       // 26 per feature: 2 x 13 row-major, cols [0,7) camera, [7,13) feature
   double* S2;       // 4 per feature: 2x2 block of St
-  uint8_t* patch;   // w*w per feature
-  uint8_t* mpatch;  // w*w per feature (matching_patch)
+  uint8_t* patch;   // cfg.tstride bytes per feature (w*w used)
+  uint8_t* mpatch;  // cfg.tstride bytes per feature (matching_patch)
 };
 
 struct FrameView {

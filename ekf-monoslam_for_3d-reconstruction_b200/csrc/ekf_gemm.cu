@@ -9,6 +9,8 @@
 // sub-tile = 8 x 4 DMMA tiles (64 accumulator doubles per thread); K is consumed in 16-wide slabs
 // staged global -> shared with cp.async (3 stages), rows padded to 20 doubles so the 8-row x 4-col
 // fragment reads are bank-conflict free (row*20 mod 16 covers 0,4,8,12).
+#include <cstdlib>
+
 #include "ekf_kernels.h"
 
 #define GT_M 128
@@ -41,13 +43,19 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // the upper triangle (C symmetric on input => symmetric on output).
 __global__ void __launch_bounds__(GT_THREADS, 2)
 k_gemm_nt_sub(double* __restrict__ C, int ldc, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
-              int M, int N, int kconst, const int* __restrict__ kdev, int lower_only) {
+              int M, int N, int kconst, const int* __restrict__ kdev, int lower_only, unsigned stagger_ns) {
   extern __shared__ __align__(16) double gsm[];
   const int K = kdev ? *kdev : kconst;
   if (K <= 0) return;
   const int tm = blockIdx.y, tn = blockIdx.x;
   const int m0 = tm * GT_M, n0 = tn * GT_N;
   if (lower_only && n0 > m0 + GT_M - 1) return;
+  // Two CTAs share an SM and would otherwise run their load / store phases in lock-step; staggering
+  // every other 148-CTA wave of the first launch wave by about half a tile de-synchronises them.
+  if (stagger_ns > 0) {
+    const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x;
+    if (lin < 296u && ((lin / 148u) & 1u)) __nanosleep(stagger_ns);
+  }
   double* As = gsm;                                   // [stages][GT_M][GT_LD]
   double* Bs = gsm + GT_STAGES * GT_M * GT_LD;        // [stages][GT_N][GT_LD]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -157,7 +165,9 @@ int launch_gemm_nt_sub(cudaStream_t st, double* C, int ldc, const double* A, int
   }
   if (M <= 0 || N <= 0) return 0;
   dim3 grid((N + GT_N - 1) / GT_N, (M + GT_M - 1) / GT_M);
-  k_gemm_nt_sub<<<grid, GT_THREADS, kGemmSmem, st>>>(C, ldc, A, lda, B, ldb, M, N, kconst, kdev, lower_only);
+  static int stagger = -1;
+  if (stagger < 0) { const char* e = getenv("EKF_GEMM_STAGGER_NS"); stagger = e ? atoi(e) : 0; }
+  k_gemm_nt_sub<<<grid, GT_THREADS, kGemmSmem, st>>>(C, ldc, A, lda, B, ldb, M, N, kconst, kdev, lower_only, (unsigned)stagger);
   if (launches) *launches += 1;
   return 0;
 }

@@ -115,17 +115,12 @@ __global__ void __launch_bounds__(128) k_predict_features(const double* __restri
     }
     ft.innov[i] = ok; ft.li[i] = 0; ft.hi[i] = 0;  // Patch::setIsInInnovation (Patch.cpp:123-132)
   }
-  // matching_patch <- patch for gated-in features (Patch.cpp:54-56), cooperative byte copy
-  {
-    __shared__ int okflags[128];
-    okflags[threadIdx.x] = ok;
-    __syncthreads();
-    const int w2 = cfg.window * cfg.window;
-    const int base = blockIdx.x * blockDim.x;
-    for (int e = threadIdx.x; e < (int)blockDim.x * w2; e += blockDim.x) {
-      const int fl = e / w2;
-      if (base + fl < N && okflags[fl]) ft.mpatch[(size_t)(base + fl) * w2 + (e % w2)] = ft.patch[(size_t)(base + fl) * w2 + (e % w2)];
-    }
+  // matching_patch <- patch for gated-in features (Patch.cpp:54-56): 16-byte chunks of the record
+  if (ok) {
+    const int chunks = cfg.tstride >> 4;
+    const uint4* src = reinterpret_cast<const uint4*>(ft.patch + (size_t)i * cfg.tstride);
+    uint4* dst = reinterpret_cast<uint4*>(ft.mpatch + (size_t)i * cfg.tstride);
+    for (int c = 0; c < chunks; ++c) dst[c] = src[c];
   }
   // last block: commit the predicted camera state and compact
   __threadfence();
@@ -337,7 +332,7 @@ __global__ void __launch_bounds__(256) k_add_feature(double* __restrict__ Sigma,
     const int w = cfg.window, w2 = w * w;
     const int x0 = (int)(pfx - w / 2), y0 = (int)(pfy - w / 2);
     for (int e = threadIdx.x; e < w2; e += blockDim.x)
-      ft.patch[(size_t)fidx * w2 + e] = fr.px[(size_t)(y0 + e / w) * fr.stride + x0 + (e % w)];
+      ft.patch[(size_t)fidx * cfg.tstride + e] = fr.px[(size_t)(y0 + e / w) * fr.stride + x0 + (e % w)];
     if (threadIdx.x == 0) {
       ft.pos[fidx] = n; ft.coding[fidx] = 0; ft.innov[fidx] = 0; ft.li[fidx] = 0; ft.hi[fidx] = 0;
       ft.removef[fidx] = 0; ft.n_tot[fidx] = 1; ft.n_find[fidx] = 1; ft.real_index[fidx] = real_index;
@@ -368,9 +363,9 @@ __global__ void k_gather_features(FeatTab src, FeatTab dst, int N2, const int* _
   const int f = blockIdx.x;
   if (f >= N2) return;
   const int o = keep[f];
-  for (int e = threadIdx.x; e < w2; e += blockDim.x) {
-    dst.patch[(size_t)f * w2 + e] = src.patch[(size_t)o * w2 + e];
-    dst.mpatch[(size_t)f * w2 + e] = src.mpatch[(size_t)o * w2 + e];
+  for (int e = threadIdx.x; e < (w2 >> 4); e += blockDim.x) {  // w2 = record stride in bytes
+    reinterpret_cast<uint4*>(dst.patch + (size_t)f * w2)[e] = reinterpret_cast<const uint4*>(src.patch + (size_t)o * w2)[e];
+    reinterpret_cast<uint4*>(dst.mpatch + (size_t)f * w2)[e] = reinterpret_cast<const uint4*>(src.mpatch + (size_t)o * w2)[e];
   }
   for (int e = threadIdx.x; e < 26; e += blockDim.x) dst.Hc[26 * f + e] = src.Hc[26 * o + e];
   if (threadIdx.x == 0) {

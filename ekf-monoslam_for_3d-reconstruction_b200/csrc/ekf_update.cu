@@ -283,61 +283,63 @@ __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __res
   double* A = fsm;                          // [EKF_UB][FACT_LD]; lower: L, strictly upper: Linv^T blocks
   double* Di = A + EKF_UB * FACT_LD;        // [4][32][33] inverses of the diagonal blocks
   double* col = Di + 4 * 32 * 33;           // [EKF_UB] scaled pivot column
-  double* Tb = col + EKF_UB;                // [3][32][33] block products
+  double* Tb = col + 2 * EKF_UB;            // [3][32][33] block products
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  // The matrix lives in registers during the factorisation: thread (ty, tx) owns the 16 elements
-  // (ty + 32 a, tx + 32 b), a, b in 0..3 (block-cyclic, so every warp stays busy as j advances).
-  // Per column: pivot thread -> sqrt / reciprocal -> barrier -> the 32 owners of column j scale it and
-  // publish it in shared memory -> barrier -> rank-1 update of the registers.  No shared-memory
-  // traffic for the O(k^3) part.
-  __shared__ double s_dinv;
+  // The matrix lives in registers during the factorisation: thread (warp ty, lane tx) owns the 16
+  // elements (row tx + 32 a, column ty + 32 b), a, b in 0..3.  A column belongs to ONE warp, so the
+  // pivot -> rsqrt -> scale chain is warp-local (one shuffle, no barrier); the scaled column is
+  // published in a double-buffered shared array and one barrier per column separates publication
+  // from the rank-1 update of the registers.  No shared-memory traffic for the O(k^3) part.
+  for (int e = tid; e < EKF_UB * EKF_UB; e += FACT_THREADS) A[(e >> 7) * FACT_LD + (e & 127)] = Sb[e];
+  __syncthreads();
   double R[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) R[a][b] = Sb[(ty + 32 * a) * EKF_UB + tx + 32 * b];
+    for (int b = 0; b < 4; ++b) R[a][b] = A[(tx + 32 * a) * FACT_LD + ty + 32 * b];
+  __syncthreads();
+  double* colb = col;  // [2][EKF_UB]
 #pragma unroll
   for (int qa = 0; qa < 4; ++qa) {
     for (int rj = 0; rj < 32; ++rj) {
       const int j = 32 * qa + rj;
-      if (ty == rj && tx == rj) {
-        const double ajj = R[qa][qa];
-        if (!(ajj > 0.0)) ctl->chol_fail = 1;
-        const double d = sqrt(ajj);
-        R[qa][qa] = d;
-        s_dinv = 1.0 / d;
-      }
-      __syncthreads();
-      if (tx == rj) {
-        const double dinv = s_dinv;
+      double* cj = colb + (j & 1) * EKF_UB;
+      if (ty == rj) {  // owner warp of column j
+        const double piv = __shfl_sync(0xffffffffu, R[qa][qa], rj);
+        if (tx == 0 && !(piv > 0.0)) ctl->chol_fail = 1;
+        const double rinv = rsqrt(piv);
 #pragma unroll
         for (int a = qa; a < 4; ++a) {
-          const int i = ty + 32 * a;
+          const int i = tx + 32 * a;
           if (i > j) {
-            R[a][qa] *= dinv;
-            col[i] = R[a][qa];
+            R[a][qa] *= rinv;
+            cj[i] = R[a][qa];
+          } else if (i == j) {
+            R[a][qa] = piv * rinv;
           }
         }
       }
       __syncthreads();
+      double ci[4];
 #pragma unroll
-      for (int a = qa; a < 4; ++a) {
-        const int i = ty + 32 * a;
-        if (i > j) {  // warp-uniform
-          const double li = col[i];
+      for (int a = 0; a < 4; ++a) ci[a] = cj[tx + 32 * a];
 #pragma unroll
-          for (int b = qa; b <= a; ++b) {
-            const int c = tx + 32 * b;
-            if (c > j && c <= i) R[a][b] -= li * col[c];
-          }
+      for (int b = qa; b < 4; ++b) {
+        const int c = ty + 32 * b;
+        if (c > j) {  // warp-uniform
+          const double lc = cj[c];
+#pragma unroll
+          for (int a = b; a < 4; ++a)
+            if (tx + 32 * a >= c) R[a][b] -= ci[a] * lc;
         }
       }
     }
   }
+  __syncthreads();
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b <= a; ++b) A[(ty + 32 * a) * FACT_LD + tx + 32 * b] = R[a][b];
+    for (int b = 0; b <= a; ++b) A[(tx + 32 * a) * FACT_LD + ty + 32 * b] = R[a][b];
   __syncthreads();
   // diagonal-block inverses: thread (J, colm) solves L_JJ x = e_colm
   if (tid < 128) {
@@ -513,7 +515,7 @@ __global__ void __launch_bounds__(256) k_bookkeeping(const double* __restrict__ 
 }
 
 // ---- launch wrappers ---------------------------------------------------------------------------
-static const size_t kFactSmem = (size_t)(EKF_UB * FACT_LD + 4 * 32 * 33 + EKF_UB + 3 * 32 * 33) * sizeof(double);
+static const size_t kFactSmem = (size_t)(EKF_UB * FACT_LD + 4 * 32 * 33 + 2 * EKF_UB + 3 * 32 * 33) * sizeof(double);
 static const size_t kVSmem = (size_t)(EKF_UB * VT_LD + VT_ROWS * VT_LD + EKF_UB) * sizeof(double);
 
 int update_kernels_init() {
