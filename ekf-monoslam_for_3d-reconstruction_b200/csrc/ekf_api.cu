@@ -24,7 +24,7 @@ struct ekf_handle {
   int Ncap = 0, ncap = 0, ld = 0, N = 0, n = EKF_CAM;
   double *mu = nullptr, *muB = nullptr, *Sigma = nullptr, *SigmaB = nullptr;
   double *W = nullptr, *nu = nullptr, *Lb = nullptr, *Dinv = nullptr, *yb = nullptr, *delta = nullptr, *mu_i = nullptr;
-  int *cand = nullptr, *map_dev = nullptr, *keep_dev = nullptr, *newpos_dev = nullptr;
+  int *cand = nullptr, *map_dev = nullptr, *keep_dev = nullptr, *newpos_dev = nullptr, *gemm_counters = nullptr;
   DevCtl* ctl = nullptr;
   FeatTab ft{}, ftB{};
   uint8_t* frame = nullptr;
@@ -147,7 +147,7 @@ int ekf_destroy(ekf_handle* h) {
   cudaFree(h->mu); cudaFree(h->muB); cudaFree(h->Sigma); cudaFree(h->SigmaB); cudaFree(h->W); cudaFree(h->nu);
   cudaFree(h->Lb); cudaFree(h->Dinv); cudaFree(h->yb); cudaFree(h->delta); cudaFree(h->mu_i); cudaFree(h->cand);
   cudaFree(h->map_dev); cudaFree(h->keep_dev); cudaFree(h->newpos_dev); cudaFree(h->ctl); cudaFree(h->frame);
-  cudaFree(h->picks_dev); cudaFree(h->out_dev);
+  cudaFree(h->picks_dev); cudaFree(h->out_dev); cudaFree(h->gemm_counters);
   if (h->out_host) cudaFreeHost(h->out_host);
   free_feattab(h->ft); free_feattab(h->ftB);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -191,11 +191,12 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
   TRY(dalloc(&h->W, (size_t)(h->ncap + 1) * EKF_UB)) TRY(dalloc(&h->nu, EKF_UB)) TRY(dalloc(&h->Lb, EKF_UB * EKF_UB))
   TRY(dalloc(&h->Dinv, EKF_UB * EKF_UB)) TRY(dalloc(&h->yb, EKF_UB)) TRY(dalloc(&h->delta, h->ld)) TRY(dalloc(&h->mu_i, h->ld))
   TRY(dalloc(&h->cand, h->Ncap)) TRY(dalloc(&h->map_dev, h->ncap)) TRY(dalloc(&h->keep_dev, h->Ncap))
-  TRY(dalloc(&h->newpos_dev, h->Ncap)) TRY(dalloc(&h->ctl, 1))
+  TRY(dalloc(&h->newpos_dev, h->Ncap)) TRY(dalloc(&h->ctl, 1)) TRY(dalloc(&h->gemm_counters, 2))
   TRY(alloc_feattab(h->ft, h->Ncap, w2)) TRY(alloc_feattab(h->ftB, h->Ncap, w2))
   h->out_bytes = sizeof(double) * 210 + sizeof(int) * (16 + 3 * (size_t)h->Ncap);
   TRY(cudaMalloc((void**)&h->out_dev, h->out_bytes)) TRY(cudaMallocHost((void**)&h->out_host, h->out_bytes))
   TRY(cudaMemsetAsync(h->ctl, 0, sizeof(DevCtl), h->stream))
+  TRY(cudaMemsetAsync(h->gemm_counters, 0, 2 * sizeof(int), h->stream))
   TRY(cudaMemsetAsync(h->Sigma, 0, sizeof(double) * ssz, h->stream))
   TRY(cudaMemsetAsync(h->SigmaB, 0, sizeof(double) * ssz, h->stream))
   TRY(cudaMemsetAsync(h->mu, 0, sizeof(double) * h->ld, h->stream))
@@ -403,7 +404,7 @@ static int stacked_update(ekf_handle* h, int cnt) {
     {
       ProfScope ps(h, 6);
       const int rc = launch_gemm_nt_sub(st, h->Sigma, h->ld, h->W, EKF_UB, h->W, EKF_UB, h->n, h->n, EKF_UB, nullptr, h->lower_only,
-                                        &h->launches);
+                                        h->gemm_counters, &h->launches);
       if (rc) return rc;
     }
   }

@@ -36,4 +36,4 @@ void launch_bookkeeping(cudaStream_t st, const double* Sigma, int ld, const doub
                         const DevCfg& cfg, double* outd, int* outi, long long* launches);
 // ekf_gemm.cu
 int launch_gemm_nt_sub(cudaStream_t st, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M, int N,
-                       int kconst, const int* kdev, int lower_only, long long* launches);
+                       int kconst, const int* kdev, int lower_only, int* counters, long long* launches);

@@ -275,72 +275,101 @@ __global__ void __launch_bounds__(EKF_UB) k_blk_S(const double* __restrict__ W, 
 // Linv[J][I] = -Dinv_J sum_P L[J][P] Linv[P][I], parked transposed in the unused upper triangle) and
 // y = Linv nu.  Outputs Linv (row-major, zero above the diagonal) and y.
 // ------------------------------------------------------------------------------------------------
-#define FACT_THREADS 1024
+#define FACT_THREADS 512
+#define FACT_WARPS (FACT_THREADS / 32)
 #define FACT_LD (EKF_UB + 1)
 __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __restrict__ Sb, const double* __restrict__ nu,
                                                              double* __restrict__ Linv, double* __restrict__ yout, DevCtl* ctl) {
   extern __shared__ __align__(16) double fsm[];
   double* A = fsm;                          // [EKF_UB][FACT_LD]; lower: L, strictly upper: Linv^T blocks
   double* Di = A + EKF_UB * FACT_LD;        // [4][32][33] inverses of the diagonal blocks
-  double* col = Di + 4 * 32 * 33;           // [EKF_UB] scaled pivot column
+  double* col = Di + 4 * 32 * 33;           // [2 * EKF_UB] scratch (pivot reciprocals)
   double* Tb = col + 2 * EKF_UB;            // [3][32][33] block products
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  // The matrix lives in registers during the factorisation: thread (warp ty, lane tx) owns the 16
-  // elements (row tx + 32 a, column ty + 32 b), a, b in 0..3.  A column belongs to ONE warp, so the
-  // pivot -> rsqrt -> scale chain is warp-local (one shuffle, no barrier); the scaled column is
-  // published in a double-buffered shared array and one barrier per column separates publication
-  // from the rank-1 update of the registers.  No shared-memory traffic for the O(k^3) part.
+  // Blocked right-looking Cholesky, 32-column panels.  Per panel:
+  //  (a) warp 0 factors the 32x32 diagonal block entirely in registers (lane = row; pivots and column
+  //      entries travel by warp shuffle, so the per-column dependency chain has no block barrier);
+  //  (b) the rows below solve X L_JJ^T = A_panel by substitution, lane = row, L_JJ broadcast from
+  //      shared memory, reciprocals of the pivots reused;
+  //  (c) all threads apply the rank-32 update to the trailing block with 4x4 register tiles.
   for (int e = tid; e < EKF_UB * EKF_UB; e += FACT_THREADS) A[(e >> 7) * FACT_LD + (e & 127)] = Sb[e];
+  double* rinvs = col;  // [EKF_UB] reciprocals of the pivots
   __syncthreads();
-  double R[4][4];
+  for (int J = 0; J < 4; ++J) {
+    const int o = 32 * J;
+    if (ty == 0) {
+      double Rr[32];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+      for (int c = 0; c < 32; ++c) Rr[c] = A[(o + tx) * FACT_LD + o + c];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) R[a][b] = A[(tx + 32 * a) * FACT_LD + ty + 32 * b];
-  __syncthreads();
-  double* colb = col;  // [2][EKF_UB]
-#pragma unroll
-  for (int qa = 0; qa < 4; ++qa) {
-    for (int rj = 0; rj < 32; ++rj) {
-      const int j = 32 * qa + rj;
-      double* cj = colb + (j & 1) * EKF_UB;
-      if (ty == rj) {  // owner warp of column j
-        const double piv = __shfl_sync(0xffffffffu, R[qa][qa], rj);
+      for (int j = 0; j < 32; ++j) {
+        const double piv = __shfl_sync(0xffffffffu, Rr[j], j);
         if (tx == 0 && !(piv > 0.0)) ctl->chol_fail = 1;
         const double rinv = rsqrt(piv);
+        const double lij = (tx > j) ? Rr[j] * rinv : ((tx == j) ? piv * rinv : 0.0);
+        Rr[j] = lij;
+        if (tx == j) rinvs[o + j] = rinv;
 #pragma unroll
-        for (int a = qa; a < 4; ++a) {
-          const int i = tx + 32 * a;
-          if (i > j) {
-            R[a][qa] *= rinv;
-            cj[i] = R[a][qa];
-          } else if (i == j) {
-            R[a][qa] = piv * rinv;
-          }
+        for (int c = j + 1; c < 32; ++c) {
+          const double lc = __shfl_sync(0xffffffffu, lij, c);
+          Rr[c] -= lij * lc;  // rows < c compute values that are never read
         }
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c <= tx) A[(o + tx) * FACT_LD + o + c] = Rr[c];
+    }
+    __syncthreads();
+    const int m = EKF_UB - o - 32;  // rows below the panel
+    if (m > 0) {
+      if (ty < (m >> 5)) {
+        const int r = o + 32 + ty * 32 + tx;
+        double x[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) x[c] = A[r * FACT_LD + o + c];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          double sx = x[c];
+#pragma unroll
+          for (int dd = 0; dd < c; ++dd) sx -= x[dd] * A[(o + c) * FACT_LD + o + dd];
+          x[c] = sx * rinvs[o + c];
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) A[r * FACT_LD + o + c] = x[c];
       }
       __syncthreads();
-      double ci[4];
+      // trailing block: rows 4 ti .. 4 ti + 3 (same for most lanes: broadcast reads), columns
+      // tj + nt q (consecutive lanes -> consecutive banks)
+      const int nt = m >> 2, base = o + 32;
+      for (int t = tid; t < nt * nt; t += FACT_THREADS) {
+        const int ti = t / nt, tj = t - ti * nt;
+        double acc[4][4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) ci[a] = cj[tx + 32 * a];
+        for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = qa; b < 4; ++b) {
-        const int c = ty + 32 * b;
-        if (c > j) {  // warp-uniform
-          const double lc = cj[c];
+          for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+        const double* Pa = A + (size_t)(base + 4 * ti) * FACT_LD + o;
+        const double* Pb = A + (size_t)(base + tj) * FACT_LD + o;
+        for (int dd = 0; dd < 32; ++dd) {
+          double av[4], bv[4];
 #pragma unroll
-          for (int a = b; a < 4; ++a)
-            if (tx + 32 * a >= c) R[a][b] -= ci[a] * lc;
+          for (int q = 0; q < 4; ++q) { av[q] = Pa[q * FACT_LD + dd]; bv[q] = Pb[(size_t)q * nt * FACT_LD + dd]; }
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] += av[a] * bv[b];
         }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int i = base + 4 * ti + a, c = base + tj + nt * b;
+            if (c <= i) A[i * FACT_LD + c] -= acc[a][b];
+          }
       }
+      __syncthreads();
     }
   }
-  __syncthreads();
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b <= a; ++b) A[(tx + 32 * a) * FACT_LD + ty + 32 * b] = R[a][b];
-  __syncthreads();
   // diagonal-block inverses: thread (J, colm) solves L_JJ x = e_colm
   if (tid < 128) {
     const int J = tid >> 5, cm = tid & 31;
@@ -360,25 +389,29 @@ __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __res
     const int nblk = 4 - dist;
     for (int b = 0; b < nblk; ++b) {       // T = sum_P L[J][P] X(P,I)
       const int I = b, J = b + dist;
-      double t = 0;
-      for (int P = I; P < J; ++P) {
-        const double* Lrow = A + (size_t)(J * 32 + ty) * FACT_LD + P * 32;
-        if (P == I) {
-          const double* X = Di + I * 32 * 33;
-          for (int dd = 0; dd < 32; ++dd) t += Lrow[dd] * X[dd * 33 + tx];
-        } else {
-          for (int dd = 0; dd < 32; ++dd) t += Lrow[dd] * A[(size_t)(I * 32 + tx) * FACT_LD + P * 32 + dd];
+      for (int yy = ty; yy < 32; yy += FACT_WARPS) {
+        double t = 0;
+        for (int P = I; P < J; ++P) {
+          const double* Lrow = A + (size_t)(J * 32 + yy) * FACT_LD + P * 32;
+          if (P == I) {
+            const double* X = Di + I * 32 * 33;
+            for (int dd = 0; dd < 32; ++dd) t += Lrow[dd] * X[dd * 33 + tx];
+          } else {
+            for (int dd = 0; dd < 32; ++dd) t += Lrow[dd] * A[(size_t)(I * 32 + tx) * FACT_LD + P * 32 + dd];
+          }
         }
+        Tb[(b * 32 + yy) * 33 + tx] = t;
       }
-      Tb[(b * 32 + ty) * 33 + tx] = t;
     }
     __syncthreads();
     for (int b = 0; b < nblk; ++b) {       // Linv[J][I] = -Dinv_J T
       const int I = b, J = b + dist;
       const double* X = Di + J * 32 * 33;
-      double v = 0;
-      for (int dd = 0; dd <= ty; ++dd) v += X[ty * 33 + dd] * Tb[(b * 32 + dd) * 33 + tx];
-      A[(size_t)(I * 32 + tx) * FACT_LD + J * 32 + ty] = -v;
+      for (int yy = ty; yy < 32; yy += FACT_WARPS) {
+        double v = 0;
+        for (int dd = 0; dd <= yy; ++dd) v += X[yy * 33 + dd] * Tb[(b * 32 + dd) * 33 + tx];
+        A[(size_t)(I * 32 + tx) * FACT_LD + J * 32 + yy] = -v;
+      }
     }
     __syncthreads();
   }
@@ -392,7 +425,7 @@ __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __res
     }
     Linv[e] = v;
   }
-  for (int r = ty; r < EKF_UB; r += 32) {
+  for (int r = ty; r < EKF_UB; r += FACT_WARPS) {
     double part = 0;
     for (int c = tx; c <= r; c += 32) {
       const int J = r >> 5, I = c >> 5;
