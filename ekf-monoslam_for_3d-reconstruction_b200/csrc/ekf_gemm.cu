@@ -9,6 +9,8 @@
 // sub-tile = 8 x 4 DMMA tiles (64 accumulator doubles per thread); K is consumed in 16-wide slabs
 // staged global -> shared with cp.async (3 stages), rows padded to 20 doubles so the 8-row x 4-col
 // fragment reads are bank-conflict free (row*20 mod 16 covers 0,4,8,12).
+#include <cstdlib>
+
 #include "ekf_kernels.h"
 
 #define GT_M 128
@@ -36,38 +38,29 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // K (kconst, or *kdev when kdev != nullptr) must be even; operands are zero-filled past K.
 // The accumulators are initialised with the C tile (loaded while the first cp.async stages are in
 // flight) and the B fragments are negated, so D = C + A (-B)^T needs no read in the epilogue.
-// Persistent CTAs (two per SM, 128 threads, 92 KB smem each) pull 128 x 64 tiles from an atomic
-// counter: no wave quantisation, and the two co-resident CTAs drift out of phase so one tile's C
-// traffic overlaps the other's DMMAs.
-// lower_only: only tiles touching the lower triangle are enumerated; strictly-lower elements are
-// mirrored into the upper triangle (C symmetric on input => symmetric on output).
+// Two CTAs per SM (128 threads, 92 KB smem each) overlap one tile's C traffic with the other's DMMAs.
+// lower_only: skip tiles entirely above the diagonal and mirror the strictly-lower elements into
+// the upper triangle (C symmetric on input => symmetric on output).
 __global__ void __launch_bounds__(GT_THREADS, 2)
 k_gemm_nt_sub(double* __restrict__ C, int ldc, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
-              int M, int N, int kconst, const int* __restrict__ kdev, int lower_only, int* __restrict__ counters, int ntiles,
-              int tiles_n) {
+              int M, int N, int kconst, const int* __restrict__ kdev, int lower_only, unsigned stagger_ns) {
   extern __shared__ __align__(16) double gsm[];
-  __shared__ int s_tile;
   const int K = kdev ? *kdev : kconst;
+  if (K <= 0) return;
+  const int tm = blockIdx.y, tn = blockIdx.x;
+  const int m0 = tm * GT_M, n0 = tn * GT_N;
+  if (lower_only && n0 > m0 + GT_M - 1) return;
+  // Two CTAs share an SM and would otherwise run their load / store phases in lock-step; staggering
+  // every other 148-CTA wave of the first launch wave by about half a tile de-synchronises them.
+  if (stagger_ns > 0) {
+    const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x;
+    if (lin < 296u && ((lin / 148u) & 1u)) __nanosleep(stagger_ns);
+  }
+  double* As = gsm;                                   // [stages][GT_M][GT_LD]
+  double* Bs = gsm + GT_STAGES * GT_M * GT_LD;        // [stages][GT_N][GT_LD]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;            // 2 x 2 warps, each 64 x 32
   const int g = lane >> 2, t4 = lane & 3;
-  double* As = gsm;                                   // [stages][GT_M][GT_LD]
-  double* Bs = gsm + GT_STAGES * GT_M * GT_LD;        // [stages][GT_N][GT_LD]
-  while (K > 0) {
-  if (tid == 0) s_tile = atomicAdd(&counters[0], 1);
-  __syncthreads();
-  const int tile = s_tile;
-  if (tile >= ntiles) break;
-  int tm, tn;
-  if (lower_only) {  // row tm holds tiles tn = 0 .. 2 tm + 1; rows before it hold tm^2 + tm tiles
-    tm = (int)((sqrtf(4.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
-    while (tm * tm + tm > tile) --tm;
-    while ((tm + 1) * (tm + 1) + (tm + 1) <= tile) ++tm;
-    tn = tile - (tm * tm + tm);
-  } else {
-    tm = tile / tiles_n; tn = tile - tm * tiles_n;
-  }
-  const int m0 = tm * GT_M, n0 = tn * GT_N;
 
   const int ktiles = (K + GT_K - 1) / GT_K;
   auto load_stage = [&](int kt, int stage) {
@@ -110,6 +103,10 @@ k_gemm_nt_sub(double* __restrict__ C, int ldc, const double* __restrict__ A, int
       acc[i][j][0] = v.x; acc[i][j][1] = v.y;
     }
   }
+  // warps whose 64 x 32 sub-tile lies outside the matrix, or (lower_only) entirely above the
+  // diagonal, skip the tensor work (they still help with the loads): edge and diagonal tiles cost
+  // half, which also removes most of the last partial wave.
+  const bool warp_active = (m0 + wm * 64 < M) && (n0 + wn * 32 < N) && !(lower_only && (n0 + wn * 32 > m0 + wm * 64 + 63));
   for (int kt = 0; kt < ktiles; ++kt) {
     cp_async_wait<GT_STAGES - 2>();
     __syncthreads();
@@ -118,6 +115,7 @@ k_gemm_nt_sub(double* __restrict__ C, int ldc, const double* __restrict__ A, int
     cp_async_commit();
     const double* as = As + (size_t)(kt % GT_STAGES) * GT_M * GT_LD + (size_t)(wm * 64 + g) * GT_LD + t4;
     const double* bs = Bs + (size_t)(kt % GT_STAGES) * GT_N * GT_LD + (size_t)(wn * 32 + g) * GT_LD + t4;
+    if (warp_active)
 #pragma unroll
     for (int k4 = 0; k4 < GT_K / 4; ++k4) {
       double af[8], bf[4];
@@ -158,41 +156,24 @@ k_gemm_nt_sub(double* __restrict__ C, int ldc, const double* __restrict__ A, int
       }
     }
   }
-  __syncthreads();  // smem stages and s_tile are reused by the next tile
-  }
-  // the last CTA to leave resets the counters for the next launch
-  if (tid == 0) {
-    __threadfence();
-    const int done = atomicAdd(&counters[1], 1);
-    if (done == (int)gridDim.x - 1) { counters[0] = 0; counters[1] = 0; __threadfence(); }
-  }
 }
 
 static const size_t kGemmSmem = (size_t)GT_STAGES * (GT_M + GT_N) * GT_LD * sizeof(double);
 
 int launch_gemm_nt_sub(cudaStream_t st, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M, int N,
                        int kconst, const int* kdev, int lower_only, int* counters, long long* launches) {
+  (void)counters;
   static bool attr_done = false;
-  static int num_sms = 0;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(k_gemm_nt_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
     if (e != cudaSuccess) return (int)e;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     attr_done = true;
   }
   if (M <= 0 || N <= 0) return 0;
-  const int tiles_m = (M + GT_M - 1) / GT_M, tiles_n = (N + GT_N - 1) / GT_N;
-  int ntiles = tiles_m * tiles_n;
-  if (lower_only) {  // requires M == N: row tm has min(2 tm + 2, tiles_n) tiles
-    if (M != N) return (int)cudaErrorInvalidValue;
-    ntiles = 0;
-    for (int tm = 0; tm < tiles_m; ++tm) ntiles += 2 * tm + 2;
-  }
-  const int grid = ntiles < 2 * num_sms ? ntiles : 2 * num_sms;
-  k_gemm_nt_sub<<<grid, GT_THREADS, kGemmSmem, st>>>(C, ldc, A, lda, B, ldb, M, N, kconst, kdev, lower_only, counters, ntiles,
-                                                    tiles_n);
+  dim3 grid((N + GT_N - 1) / GT_N, (M + GT_M - 1) / GT_M);
+  static int stagger = -1;
+  if (stagger < 0) { const char* e = getenv("EKF_GEMM_STAGGER_NS"); stagger = e ? atoi(e) : 0; }
+  k_gemm_nt_sub<<<grid, GT_THREADS, kGemmSmem, st>>>(C, ldc, A, lda, B, ldb, M, N, kconst, kdev, lower_only, (unsigned)stagger);
   if (launches) *launches += 1;
   return 0;
 }

@@ -276,41 +276,82 @@ __global__ void __launch_bounds__(EKF_UB) k_blk_S(const double* __restrict__ W, 
 // y = Linv nu.  Outputs Linv (row-major, zero above the diagonal) and y.
 // ------------------------------------------------------------------------------------------------
 #define FACT_THREADS 512
+#ifdef FACT_DEBUG
+__device__ long long g_fact_stamp[32];
+#define FSTAMP(i) do { if (threadIdx.x == 0) g_fact_stamp[i] = clock64(); } while (0)
+#else
+#define FSTAMP(i) do {} while (0)
+#endif
 #define FACT_WARPS (FACT_THREADS / 32)
 #define FACT_LD (EKF_UB + 1)
+__device__ __forceinline__ void dmma884f(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+// One warp: 8x8 tile D = sum_{k<32} A(r,k) B(k,n), A(r,k) = Ap[r*ar + k*ak], B(k,n) = Bp[k*bk + n*bn].
+// All 16 fragments are loaded first and the 8 DMMAs run as 4 independent chains of 2 (the DMMA
+// accumulate latency, not its issue rate, bounds these tiny products).  Returns the thread's two
+// elements (row lane/4, columns 2*(lane%4), +1).
+__device__ __forceinline__ void warp_tile_mma32(const double* Ap, int ar, int ak, const double* Bp, int bk, int bn,
+                                                double& d0, double& d1) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  double af[8], bf[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { af[q] = Ap[g * ar + (4 * q + t4) * ak]; bf[q] = Bp[(4 * q + t4) * bk + g * bn]; }
+  double c[4][2];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { c[q][0] = 0.0; c[q][1] = 0.0; }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) dmma884f(c[q & 3][0], c[q & 3][1], af[q], bf[q]);
+  d0 = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
+  d1 = (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
+}
+
 __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __restrict__ Sb, const double* __restrict__ nu,
                                                              double* __restrict__ Linv, double* __restrict__ yout, DevCtl* ctl) {
   extern __shared__ __align__(16) double fsm[];
   double* A = fsm;                          // [EKF_UB][FACT_LD]; lower: L, strictly upper: Linv^T blocks
   double* Di = A + EKF_UB * FACT_LD;        // [4][32][33] inverses of the diagonal blocks
-  double* col = Di + 4 * 32 * 33;           // [2 * EKF_UB] scratch (pivot reciprocals)
-  double* Tb = col + 2 * EKF_UB;            // [3][32][33] block products
+  double* col = Di + 4 * 32 * 33;           // [2 * EKF_UB] scratch (pivot reciprocals, nu)
+  double* Tb = col + 2 * EKF_UB;            // [4][32][33] block products
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   // Blocked right-looking Cholesky, 32-column panels.  Per panel:
   //  (a) warp 0 factors the 32x32 diagonal block entirely in registers (lane = row; pivots and column
-  //      entries travel by warp shuffle, so the per-column dependency chain has no block barrier);
+  //      entries travel by warp shuffle, so the per-column dependency chain has no block barrier; the
+  //      next pivot's rsqrt is started as soon as its element is final, in the shadow of the remaining
+  //      rank-1 updates of the current column);
   //  (b) the rows below solve X L_JJ^T = A_panel by substitution, lane = row, L_JJ broadcast from
   //      shared memory, reciprocals of the pivots reused;
-  //  (c) all threads apply the rank-32 update to the trailing block with 4x4 register tiles.
+  //  (c) all threads apply the rank-32 update to the trailing block with register tiles.
   for (int e = tid; e < EKF_UB * EKF_UB; e += FACT_THREADS) A[(e >> 7) * FACT_LD + (e & 127)] = Sb[e];
+  for (int e = tid; e < EKF_UB; e += FACT_THREADS) col[EKF_UB + e] = nu[e];
   double* rinvs = col;  // [EKF_UB] reciprocals of the pivots
+  FSTAMP(0);
   __syncthreads();
+  FSTAMP(1);
   for (int J = 0; J < 4; ++J) {
     const int o = 32 * J;
     if (ty == 0) {
       double Rr[32];
 #pragma unroll
       for (int c = 0; c < 32; ++c) Rr[c] = A[(o + tx) * FACT_LD + o + c];
+      double piv = __shfl_sync(0xffffffffu, Rr[0], 0);
+      double rinv = rsqrt(piv);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const double piv = __shfl_sync(0xffffffffu, Rr[j], j);
         if (tx == 0 && !(piv > 0.0)) ctl->chol_fail = 1;
-        const double rinv = rsqrt(piv);
         const double lij = (tx > j) ? Rr[j] * rinv : ((tx == j) ? piv * rinv : 0.0);
         Rr[j] = lij;
         if (tx == j) rinvs[o + j] = rinv;
+        if (j + 1 < 32) {
+          const double l1 = __shfl_sync(0xffffffffu, lij, j + 1);
+          Rr[j + 1] -= lij * l1;
+          piv = __shfl_sync(0xffffffffu, Rr[j + 1], j + 1);
+          rinv = rsqrt(piv);
+        }
 #pragma unroll
-        for (int c = j + 1; c < 32; ++c) {
+        for (int c = j + 2; c < 32; ++c) {
           const double lc = __shfl_sync(0xffffffffu, lij, c);
           Rr[c] -= lij * lc;  // rows < c compute values that are never read
         }
@@ -320,6 +361,7 @@ __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __res
         if (c <= tx) A[(o + tx) * FACT_LD + o + c] = Rr[c];
     }
     __syncthreads();
+    FSTAMP(2 + 3 * J);
     const int m = EKF_UB - o - 32;  // rows below the panel
     if (m > 0) {
       if (ty < (m >> 5)) {
@@ -338,103 +380,101 @@ __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __res
         for (int c = 0; c < 32; ++c) A[r * FACT_LD + o + c] = x[c];
       }
       __syncthreads();
-      // trailing block: rows 4 ti .. 4 ti + 3 (same for most lanes: broadcast reads), columns
-      // tj + nt q (consecutive lanes -> consecutive banks)
-      const int nt = m >> 2, base = o + 32;
-      for (int t = tid; t < nt * nt; t += FACT_THREADS) {
-        const int ti = t / nt, tj = t - ti * nt;
-        double acc[4][4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-        const double* Pa = A + (size_t)(base + 4 * ti) * FACT_LD + o;
-        const double* Pb = A + (size_t)(base + tj) * FACT_LD + o;
-        for (int dd = 0; dd < 32; ++dd) {
-          double av[4], bv[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) { av[q] = Pa[q * FACT_LD + dd]; bv[q] = Pb[(size_t)q * nt * FACT_LD + dd]; }
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] += av[a] * bv[b];
+      FSTAMP(3 + 3 * J);
+      // trailing block on the tensor pipe: lower 8x8 tiles (ti >= tj) of A22 -= P P^T, K = 32,
+      // round-robin over the 16 warps
+      {
+        const int base = o + 32, nt8 = m >> 3, g = tx >> 2, t4 = tx & 3;
+        const int ntile = nt8 * (nt8 + 1) / 2;
+        for (int t = ty; t < ntile; t += FACT_WARPS) {
+          int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+          while (ti * (ti + 1) / 2 > t) --ti;
+          while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+          const int tj = t - ti * (ti + 1) / 2;
+          double d0, d1;
+          const double* Pa = A + (size_t)(base + 8 * ti) * FACT_LD + o;
+          const double* Pb = A + (size_t)(base + 8 * tj) * FACT_LD + o;
+          warp_tile_mma32(Pa, FACT_LD, 1, Pb, 1, FACT_LD, d0, d1);
+          double* dst = A + (size_t)(base + 8 * ti + g) * FACT_LD + base + 8 * tj + 2 * t4;
+          dst[0] -= d0;
+          dst[1] -= d1;
         }
+      }
+      __syncthreads();
+      FSTAMP(4 + 3 * J);
+    }
+  }
+  // Inverses of the four diagonal blocks: warp J solves X L_JJ^T = I by the same substitution as
+  // the panel solve (lane = row r of X = L_JJ^-T, i.e. column r of L_JJ^-1).
+  if (ty < 4) {
+    const int o = 32 * ty;
+    double x[32];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+    for (int c = 0; c < 32; ++c) {
+      double sx = (c == tx) ? 1.0 : 0.0;
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const int i = base + 4 * ti + a, c = base + tj + nt * b;
-            if (c <= i) A[i * FACT_LD + c] -= acc[a][b];
-          }
+      for (int dd = 0; dd < c; ++dd) sx -= x[dd] * A[(o + c) * FACT_LD + o + dd];
+      x[c] = sx * rinvs[o + c];
+    }
+    double* X = Di + ty * 32 * 33;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) X[c * 33 + tx] = x[c];  // Linv[c][r] = X[r][c]
+  }
+  __syncthreads();
+  FSTAMP(14);
+  // Off-diagonal blocks of Linv on the tensor pipe, by distance from the diagonal:
+  //   Linv[J][I] = -Dinv_J sum_{P=I..J-1} L[J][P] X(P,I),  X(I,I) = Dinv_I, X(P,I) for P > I parked
+  //   transposed in the unused upper triangle: A[32 I + c][32 P + r] = Linv[32 P + r][32 I + c].
+  // 16 warps = the 16 8x8 tiles of a 32x32 block.
+  {
+    const int wti = ty >> 2, wtj = ty & 3, g = tx >> 2, t4 = tx & 3;
+    for (int dist = 1; dist < 4; ++dist) {
+      const int nblk = 4 - dist;
+      for (int b = 0; b < nblk; ++b) {
+        const int I = b, J = b + dist;
+        double a0 = 0.0, a1 = 0.0;
+        for (int P = I; P < J; ++P) {
+          double d0, d1;
+          const double* Ap = A + (size_t)(J * 32 + wti * 8) * FACT_LD + P * 32;
+          if (P == I) warp_tile_mma32(Ap, FACT_LD, 1, Di + I * 32 * 33 + wtj * 8, 33, 1, d0, d1);
+          else warp_tile_mma32(Ap, FACT_LD, 1, A + (size_t)(I * 32 + wtj * 8) * FACT_LD + P * 32, 1, FACT_LD, d0, d1);
+          a0 += d0; a1 += d1;
+        }
+        double* T = Tb + b * 32 * 33;
+        T[(wti * 8 + g) * 33 + wtj * 8 + 2 * t4] = a0;
+        T[(wti * 8 + g) * 33 + wtj * 8 + 2 * t4 + 1] = a1;
+      }
+      __syncthreads();
+      for (int b = 0; b < nblk; ++b) {
+        const int I = b, J = b + dist;
+        double d0, d1;
+        warp_tile_mma32(Di + J * 32 * 33 + (wti * 8) * 33, 33, 1, Tb + b * 32 * 33 + wtj * 8, 33, 1, d0, d1);
+        const int r = wti * 8 + g, c = wtj * 8 + 2 * t4;
+        A[(size_t)(I * 32 + c) * FACT_LD + J * 32 + r] = -d0;
+        A[(size_t)(I * 32 + c + 1) * FACT_LD + J * 32 + r] = -d1;
       }
       __syncthreads();
     }
   }
-  // diagonal-block inverses: thread (J, colm) solves L_JJ x = e_colm
-  if (tid < 128) {
-    const int J = tid >> 5, cm = tid & 31;
-    double* X = Di + J * 32 * 33;
-    const double* Lj = A + (J * 32) * FACT_LD + J * 32;
-    for (int i = 0; i < 32; ++i) {
-      if (i < cm) { X[i * 33 + cm] = 0.0; continue; }
-      double s = (i == cm) ? 1.0 : 0.0;
-      for (int dd = cm; dd < i; ++dd) s -= Lj[i * FACT_LD + dd] * X[dd * 33 + cm];
-      X[i * 33 + cm] = s / Lj[i * FACT_LD + i];
-    }
-  }
-  __syncthreads();
-  // off-diagonal blocks of Linv, by distance from the diagonal.  X(P,I): P == I -> Di[I], else the
-  // block parked at A[(32 I + c)][32 P + r] = Linv[32 P + r][32 I + c].
-  for (int dist = 1; dist < 4; ++dist) {
-    const int nblk = 4 - dist;
-    for (int b = 0; b < nblk; ++b) {       // T = sum_P L[J][P] X(P,I)
-      const int I = b, J = b + dist;
-      for (int yy = ty; yy < 32; yy += FACT_WARPS) {
-        double t = 0;
-        for (int P = I; P < J; ++P) {
-          const double* Lrow = A + (size_t)(J * 32 + yy) * FACT_LD + P * 32;
-          if (P == I) {
-            const double* X = Di + I * 32 * 33;
-            for (int dd = 0; dd < 32; ++dd) t += Lrow[dd] * X[dd * 33 + tx];
-          } else {
-            for (int dd = 0; dd < 32; ++dd) t += Lrow[dd] * A[(size_t)(I * 32 + tx) * FACT_LD + P * 32 + dd];
-          }
-        }
-        Tb[(b * 32 + yy) * 33 + tx] = t;
-      }
-    }
-    __syncthreads();
-    for (int b = 0; b < nblk; ++b) {       // Linv[J][I] = -Dinv_J T
-      const int I = b, J = b + dist;
-      const double* X = Di + J * 32 * 33;
-      for (int yy = ty; yy < 32; yy += FACT_WARPS) {
-        double v = 0;
-        for (int dd = 0; dd <= yy; ++dd) v += X[yy * 33 + dd] * Tb[(b * 32 + dd) * 33 + tx];
-        A[(size_t)(I * 32 + tx) * FACT_LD + J * 32 + yy] = -v;
-      }
-    }
-    __syncthreads();
-  }
-  // write Linv and y = Linv nu (one warp per 4 rows, lanes split the dot product)
-  for (int e = tid; e < EKF_UB * EKF_UB; e += FACT_THREADS) {
-    const int r = e >> 7, c = e & 127;
-    double v = 0.0;
-    if (c <= r) {
-      const int J = r >> 5, I = c >> 5;
-      v = (J == I) ? Di[J * 32 * 33 + (r & 31) * 33 + (c & 31)] : A[(size_t)c * FACT_LD + r];
-    }
-    Linv[e] = v;
-  }
+  FSTAMP(15);
+  // write Linv (row r by warp r mod 16: coalesced stores, conflict-free transposed reads) and
+  // y = Linv nu from the same values
   for (int r = ty; r < EKF_UB; r += FACT_WARPS) {
-    double part = 0;
-    for (int c = tx; c <= r; c += 32) {
-      const int J = r >> 5, I = c >> 5;
-      const double lv = (J == I) ? Di[J * 32 * 33 + (r & 31) * 33 + (c & 31)] : A[(size_t)c * FACT_LD + r];
-      part += lv * nu[c];
+    const int Jr = r >> 5;
+    double part = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = tx + 32 * q;
+      double v = 0.0;
+      if (q < Jr) v = A[(size_t)c * FACT_LD + r];
+      else if (q == Jr) v = Di[Jr * 32 * 33 + (r & 31) * 33 + tx];  // zero above the diagonal
+      Linv[r * EKF_UB + c] = v;
+      part += v * col[EKF_UB + c];
     }
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    for (int o2 = 16; o2 > 0; o2 >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o2);
     if (tx == 0) yout[r] = part;
   }
+  FSTAMP(16);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -548,7 +588,7 @@ __global__ void __launch_bounds__(256) k_bookkeeping(const double* __restrict__ 
 }
 
 // ---- launch wrappers ---------------------------------------------------------------------------
-static const size_t kFactSmem = (size_t)(EKF_UB * FACT_LD + 4 * 32 * 33 + 2 * EKF_UB + 3 * 32 * 33) * sizeof(double);
+static const size_t kFactSmem = (size_t)(EKF_UB * FACT_LD + 4 * 32 * 33 + 2 * EKF_UB + 4 * 32 * 33) * sizeof(double);
 static const size_t kVSmem = (size_t)(EKF_UB * VT_LD + VT_ROWS * VT_LD + EKF_UB) * sizeof(double);
 
 int update_kernels_init() {
