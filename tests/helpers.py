@@ -25,6 +25,13 @@ def make_pair(pkg, orc, scene, capacity=None, **cfg_over):
     return g, o
 
 
+def make_oracle(pkg, orc, scene, kind=0, omp=False, **cfg_over):
+    """A CPU oracle filter configured for `scene` (no GPU needed)."""
+    over = scene.config_overrides()
+    over.update(cfg_over)
+    return orc.OracleFilter(pkg.default_config(**over), kind=kind, omp=omp)
+
+
 def seed_features(filt, scene):
     filt.captureNewFrame(scene.frame(0), scene.stamps[0])
     return [filt.addFeature(*p) for p in scene.feature_pixels]

@@ -29,11 +29,6 @@ def _dense_H(o):
     return np.vstack(rows), np.array(hs).reshape(-1), np.array(zs).reshape(-1), idx
 
 
-def _h_of_state(pkg, cfg_scene, mu, Sigma, img, stamp0, stamp1, orc):
-    """h(mu) of every feature through the oracle's predict with v = w = 0 (pose unchanged)."""
-    raise NotImplementedError
-
-
 def test_init_state_matches_reference_constructor(pkg, orc):
     """vslamRansac.cpp:163-216."""
     sc = _scene(pkg, n_features=4, n_frames=2)
