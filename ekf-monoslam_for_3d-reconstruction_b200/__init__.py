@@ -6,12 +6,12 @@ The directory name is not a valid Python identifier; import it with `load_packag
 repository root's `ekfb200.py` shim, which registers it as module `ekf_b200`.
 """
 from . import _abi, synth  # noqa: F401
-from ._abi import EkfConfig, EkfFeatureInfo, EkfStepStats, default_config  # noqa: F401
+from ._abi import EkfBatchDesc, EkfConfig, EkfFeatureInfo, EkfStepStats, default_config  # noqa: F401
 from .build import build  # noqa: F401
 
 
 def __getattr__(name):  # lazy: importing the package must not require the built library
-    if name in ("VSlamFilter", "EkfError", "match_batch"):
+    if name in ("VSlamFilter", "EkfError", "match_batch", "FilterBatch"):
         from . import filter as _f
         return getattr(_f, name)
     if name == "lib":

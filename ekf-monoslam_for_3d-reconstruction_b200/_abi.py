@@ -60,3 +60,12 @@ PROF_CLASSES = ("predict", "match", "ransac", "gather_W", "factor_S", "V_trsm", 
 
 class EkfProfile(C.Structure):
     _fields_ = [("ms", C.c_double * 12), ("launches", C.c_int64 * 12)]
+
+
+class EkfBatchDesc(C.Structure):
+    _fields_ = [("n_filters", C.c_int32), ("feature_capacity", C.c_int32), ("state_capacity", C.c_int32), ("ld", C.c_int32),
+                ("device", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+BATCH_STAT_FIELDS = 8
+BSTAT = dict(innov=0, matched=1, li=2, hi=3, hyps=4, chol_fail=5, removed=6, topup=7)

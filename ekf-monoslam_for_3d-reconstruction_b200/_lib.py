@@ -46,6 +46,25 @@ SIGNATURES = {
     "ekf_set_full": (_i, [_vp, _vp, _vp, _i]),
     "ekf_get_S_blocks": (_i, [_vp, _vp]),
     "ekf_match_batch": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _f, _f, _f, _vp, _vp, _vp]),
+    "ekf_batch_create": (_i, [_P(_abi.EkfConfig), _i, _i, _i, _P(_vp)]),
+    "ekf_batch_destroy": (_i, [_vp]),
+    "ekf_batch_describe": (_i, [_vp, _P(_abi.EkfBatchDesc)]),
+    "ekf_batch_set_stream": (_i, [_vp, _vp]),
+    "ekf_batch_sync": (_i, [_vp]),
+    "ekf_batch_last_error": (C.c_char_p, [_vp]),
+    "ekf_batch_seed_from": (_i, [_vp, _vp]),
+    "ekf_batch_set_camera_states": (_i, [_vp, _vp]),
+    "ekf_batch_capture_frame": (_i, [_vp, _vp, _i, _i, _i, _d]),
+    "ekf_batch_capture_frame_device": (_i, [_vp, _vp, _i, _i, _i, _d]),
+    "ekf_batch_step": (_i, [_vp, _vp, _vp, _i, _vp, _i]),
+    "ekf_batch_get_camera_states": (_i, [_vp, _vp, _vp, _vp]),
+    "ekf_batch_num_features": (_i, [_vp, _i]),
+    "ekf_batch_state_dim": (_i, [_vp, _i]),
+    "ekf_batch_get_full": (_i, [_vp, _i, _vp, _vp, _i]),
+    "ekf_batch_set_full": (_i, [_vp, _i, _vp, _vp, _i]),
+    "ekf_batch_get_feature": (_i, [_vp, _i, _i, _P(_abi.EkfFeatureInfo)]),
+    "ekf_batch_kernel_launches": (C.c_int64, [_vp]),
+    "ekf_batch_last_step_ms": (_i, [_vp, _vp]),
     "ekf_set_profiling": (_i, [_vp, _i]),
     "ekf_get_profile": (_i, [_vp, _P(_abi.EkfProfile), _i]),
     "ekf_set_symmetric_downdate": (_i, [_vp, _i]),

@@ -8,56 +8,8 @@
 #include <vector>
 
 #include "../../include/ekf_b200.h"
+#include "ekf_handle.h"
 #include "ekf_kernels.h"
-
-struct DeletedPatch {  // Patch archived by removeFeature (vslamRansac.cpp:394-404)
-  int real_index;
-  double XYZ_pos[3];
-  double cov_4_delete[9];
-};
-
-struct ekf_handle {
-  ekf_config cfg;
-  DevCfg dcfg;
-  int device = 0;
-  cudaStream_t stream = nullptr, own_stream = nullptr;
-  int Ncap = 0, ncap = 0, ld = 0, N = 0, n = EKF_CAM;
-  double *mu = nullptr, *muB = nullptr, *Sigma = nullptr, *SigmaB = nullptr;
-  double *W = nullptr, *nu = nullptr, *Lb = nullptr, *Dinv = nullptr, *yb = nullptr, *delta = nullptr, *mu_i = nullptr;
-  int *cand = nullptr, *map_dev = nullptr, *keep_dev = nullptr, *newpos_dev = nullptr, *gemm_counters = nullptr;
-  DevCtl* ctl = nullptr;
-  FeatTab ft{}, ftB{};
-  uint8_t* frame = nullptr;
-  size_t frame_cap = 0;
-  FrameView fv{nullptr, 0, 0, 0};
-  uint32_t* picks_dev = nullptr;
-  int picks_cap = 0;
-  double* out_dev = nullptr;   // packed step record (device)
-  double* out_host = nullptr;  // pinned mirror
-  size_t out_bytes = 0;
-  double dT = 1.0, old_ts = -1.0;
-  int patchnumbre = 1, noise_cov_factor = 0;
-  bool predicted = false, have_frame = false;
-  int lower_only = 0;
-  ekf_step_stats stats{};
-  long long launches = 0;
-  std::string err;
-  std::vector<DeletedPatch> deleted;
-  // per-kernel-class CUDA-event timing (ekf_set_profiling)
-  bool prof_on = false;
-  struct ProfRec { int cls; int nl; cudaEvent_t a, b; };
-  std::vector<ProfRec> prof_pending;
-  std::vector<cudaEvent_t> prof_pool;
-  double prof_ms[EKF_PROF_CLASSES] = {0};
-  long long prof_launches[EKF_PROF_CLASSES] = {0};
-  // host cache of the feature table (valid when cache_ok)
-  bool cache_ok = false;
-  std::vector<int> c_pos, c_coding, c_innov, c_li, c_hi, c_removef, c_ntot, c_nfind, c_real, c_posz;
-  std::vector<float> c_center, c_quality, c_ncc;
-  std::vector<double> c_z, c_h, c_Hc, c_S2;
-  // host mirror maintained by add/remove (always valid)
-  std::vector<int> m_pos, m_coding;
-};
 
 static int ekf_fail_cuda(ekf_handle* h, cudaError_t e, const char* what, const char* file, int line) {
   char buf[512];

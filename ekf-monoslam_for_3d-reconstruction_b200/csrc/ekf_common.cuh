@@ -76,6 +76,18 @@ struct FeatTab {
   uint8_t* mpatch;  // cfg.tstride bytes per feature (matching_patch)
 };
 
+// Feature table of filter b inside a batch of tables laid out [filter][Ncap] per field.
+__host__ __device__ __forceinline__ FeatTab feattab_slice(const FeatTab& t, int b, int Ncap, int tstride) {
+  FeatTab o;
+  const size_t k = (size_t)b * Ncap;
+  o.pos = t.pos + k; o.coding = t.coding + k; o.innov = t.innov + k; o.li = t.li + k; o.hi = t.hi + k;
+  o.removef = t.removef + k; o.n_tot = t.n_tot + k; o.n_find = t.n_find + k; o.real_index = t.real_index + k;
+  o.pos_in_z = t.pos_in_z + k; o.sel = t.sel + k; o.center = t.center + 2 * k; o.quality = t.quality + k;
+  o.last_ncc = t.last_ncc + k; o.z = t.z + 2 * k; o.h = t.h + 2 * k; o.Hc = t.Hc + 26 * k; o.S2 = t.S2 + 4 * k;
+  o.patch = t.patch + k * tstride; o.mpatch = t.mpatch + k * tstride;
+  return o;
+}
+
 struct FrameView {
   const uint8_t* px;
   int w, h, stride;

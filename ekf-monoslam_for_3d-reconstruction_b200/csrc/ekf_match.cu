@@ -245,10 +245,7 @@ __device__ MatchResult match_one(const MatchJob& jb, int w, float sigma_size, fl
 static size_t match_smem_bytes(int w, float clampv) { return match_smem_plan(w, (int)clampv).total; }
 
 // Filter-attached matcher: the loop V:870-880 with one CTA per feature.
-__global__ void __launch_bounds__(MATCH_THREADS) k_match_filter(FeatTab ft, int N, FrameView fr, DevCfg cfg) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int f = blockIdx.x;
-  if (f >= N || !ft.innov[f]) return;
+__device__ __forceinline__ void match_filter_feature(FeatTab ft, int f, FrameView fr, const DevCfg& cfg, unsigned char* smem_raw) {
   const int w = cfg.window, w2 = w * w;
   MatchJob jb;
   jb.frame = fr.px; jb.fw = fr.w; jb.fh = fr.h; jb.fstride = fr.stride;
@@ -275,6 +272,21 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_filter(FeatTab ft, int 
       ft.z[2 * f] = (double)(float)r.bi; ft.z[2 * f + 1] = (double)(float)r.bj;
     }
   }
+}
+__global__ void __launch_bounds__(MATCH_THREADS) k_match_filter(FeatTab ft, int N, FrameView fr, DevCfg cfg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int f = blockIdx.x;
+  if (f >= N || !ft.innov[f]) return;
+  match_filter_feature(ft, f, fr, cfg, smem_raw);
+}
+// Batched filters (BASELINE config 3): grid = (feature capacity, filters); the frame is shared.
+__global__ void __launch_bounds__(MATCH_THREADS) k_match_filter_batch(FeatTab base, int Ncap, const int* __restrict__ Nper,
+                                                                      FrameView fr, DevCfg cfg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int f = blockIdx.x, b = blockIdx.y;
+  const FeatTab ft = feattab_slice(base, b, Ncap, cfg.tstride);
+  if (f >= Nper[b] || !ft.innov[f]) return;
+  match_filter_feature(ft, f, fr, cfg, smem_raw);
 }
 
 // Stateless batch (BASELINE config 5): grid = frames x features.
@@ -310,6 +322,19 @@ void launch_match_filter(cudaStream_t st, FeatTab ft, int N, FrameView fr, const
     attr_smem = smem;
   }
   k_match_filter<<<N, MATCH_THREADS, smem, st>>>(ft, N, fr, cfg);
+  *launches += 1;
+}
+
+void launch_match_filter_batch(cudaStream_t st, FeatTab base, int Ncap, const int* Nper, int B, FrameView fr, const DevCfg& cfg,
+                               long long* launches) {
+  if (B <= 0 || Ncap <= 0) return;
+  static size_t attr_smem = 0;
+  const size_t smem = match_smem_bytes(cfg.window, cfg.search_clamp);
+  if (smem > attr_smem) {
+    cudaFuncSetAttribute(k_match_filter_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_smem = smem;
+  }
+  k_match_filter_batch<<<dim3(Ncap, B), MATCH_THREADS, smem, st>>>(base, Ncap, Nper, fr, cfg);
   *launches += 1;
 }
 

@@ -15,6 +15,7 @@
 // it equals the reference's one-shot update (R is diagonal, H is evaluated once at the prior mean).
 #include "ekf_kernels.h"
 #include "ekf_math.cuh"
+#include "ekf_cta.cuh"
 
 
 // ------------------------------------------------------------------------------------------------
@@ -27,106 +28,7 @@ __global__ void __launch_bounds__(RANSAC_THREADS) k_ransac(const double* __restr
                                                            const double* __restrict__ mu, FeatTab ft, int N, DevCtl* ctl,
                                                            DevCfg cfg, const uint32_t* __restrict__ picks, int n_picks,
                                                            double* __restrict__ mu_i, int* __restrict__ cand) {
-  __shared__ double Hs[26], Sinv[4], inn[2], rr[3], Rcw[9];
-  __shared__ int s_p, s_sel, s_pos, s_nd, s_nhyp, s_numzli;
-  const int tid = threadIdx.x;
-  int cnt = block_compact(ft.innov, N, cand, nullptr);
-  const int matched = cnt;
-  if (tid == 0) {
-    ctl->n_matched = cnt;
-    for (int i = 0; i < 7; ++i) ctl->cam_old[i] = mu[i];
-    s_nhyp = cfg.nhyp0;
-    s_numzli = 0;
-  }
-  int it = 0;
-  while (true) {
-    __syncthreads();
-    if (!(it < s_nhyp && cnt > 0)) break;
-    if (tid == 0) {
-      const uint32_t rv = n_picks > 0 ? picks[it % n_picks] : 0u;
-      s_p = (int)(rv % (uint32_t)cnt);
-      s_sel = cand[s_p];
-    }
-    __syncthreads();
-    const int p = s_p, sel = s_sel;
-    {  // erase cand[p] (V:991)
-      int tmp[8];
-      int c = 0;
-      for (int idx = p + tid; idx < cnt - 1 && c < 8; idx += RANSAC_THREADS) tmp[c++] = cand[idx + 1];
-      __syncthreads();
-      c = 0;
-      for (int idx = p + tid; idx < cnt - 1 && c < 8; idx += RANSAC_THREADS) cand[idx] = tmp[c++];
-      cnt -= 1;
-    }
-    if (tid < 26) Hs[tid] = ft.Hc[26 * sel + tid];
-    if (tid == 32) {
-      double S[4];
-      for (int c = 0; c < 4; ++c) S[c] = ft.S2[4 * sel + c];
-      double X[4];
-      d_inv2_pplu(S, X);
-      for (int c = 0; c < 4; ++c) Sinv[c] = X[c];
-      inn[0] = ft.z[2 * sel] - ft.h[2 * sel];
-      inn[1] = ft.z[2 * sel + 1] - ft.h[2 * sel + 1];
-      s_pos = ft.pos[sel];
-      s_nd = 7 + (ft.coding[sel] ? 3 : 6);
-    }
-    __syncthreads();
-    {  // mu_i = mu + (Sigma H^T) S^-1 (z - h)   (V:995-996)
-      const int pos = s_pos, nd = s_nd;
-      for (int i = tid; i < n; i += RANSAC_THREADS) {
-        const double* row = Sigma + (size_t)i * ld;
-        double w0 = 0, w1 = 0;
-        for (int c = 0; c < nd; ++c) {
-          const double s = row[ekf_idx13(c, pos)];
-          w0 += s * Hs[c]; w1 += s * Hs[13 + c];
-        }
-        const double k0 = w0 * Sinv[0] + w1 * Sinv[2];
-        const double k1 = w0 * Sinv[1] + w1 * Sinv[3];
-        mu_i[i] = mu[i] + (k0 * inn[0] + k1 * inn[1]);
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      for (int c = 0; c < 3; ++c) rr[c] = mu_i[c];
-      double q[4] = {mu_i[3], mu_i[4], mu_i[5], mu_i[6]};
-      const double qn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-      double qc[4];
-      qc[0] = q[0] / qn; qc[1] = -(q[1] / qn); qc[2] = -(q[2] / qn); qc[3] = -(q[3] / qn);
-      double R[9];
-      d_quat2rot(qc, R);
-      for (int c = 0; c < 9; ++c) Rcw[c] = R[c];
-    }
-    __syncthreads();
-    int actual = 0;
-    for (int start = 0; start < N; start += RANSAC_THREADS) {
-      const int i = start + tid;
-      int flag = 0;
-      if (i < N && ft.innov[i]) {
-        const int pos = ft.pos[i], coding = ft.coding[i];
-        double fs[6], hi[2], r3[3] = {rr[0], rr[1], rr[2]}, R[9];
-        for (int c = 0; c < 9; ++c) R[c] = Rcw[c];
-        if (!coding) for (int c = 0; c < 6; ++c) fs[c] = mu_i[pos + c];
-        else for (int c = 0; c < 3; ++c) fs[c] = mu[pos + c];  // quirk V:1016: mu, not mu_i
-        d_feature_h(cfg.cam, fs, coding, r3, R, hi);
-        const double e0 = ft.z[2 * i] - hi[0], e1 = ft.z[2 * i + 1] - hi[1];
-        flag = (sqrt(e0 * e0 + e1 * e1) <= cfg.th_low) ? 1 : 0;
-        ft.li[i] = flag;
-      }
-      actual += __syncthreads_count(flag);
-    }
-    if (tid == 0 && actual > s_numzli) {
-      s_numzli = actual;
-      s_nhyp = (int)(log(1 - cfg.ransac_p) / (log(1 - (actual / (matched + 0.0)))));  // V:1030
-    }
-    ++it;
-  }
-  __syncthreads();
-  const int nli = block_compact(ft.li, N, ft.sel, ft.pos_in_z);  // V:1040-1048
-  if (tid == 0) {
-    ctl->ransac_hyps = it;
-    ctl->n_li = nli;
-    ctl->k_rows = 2 * nli;
-  }
+  cta_ransac(Sigma, ld, n, mu, ft, N, ctl, cfg, picks, n_picks, mu_i, cand);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -275,206 +177,12 @@ __global__ void __launch_bounds__(EKF_UB) k_blk_S(const double* __restrict__ W, 
 // Linv[J][I] = -Dinv_J sum_P L[J][P] Linv[P][I], parked transposed in the unused upper triangle) and
 // y = Linv nu.  Outputs Linv (row-major, zero above the diagonal) and y.
 // ------------------------------------------------------------------------------------------------
-#define FACT_THREADS 512
-#ifdef FACT_DEBUG
-__device__ long long g_fact_stamp[32];
-#define FSTAMP(i) do { if (threadIdx.x == 0) g_fact_stamp[i] = clock64(); } while (0)
-#else
-#define FSTAMP(i) do {} while (0)
-#endif
-#define FACT_WARPS (FACT_THREADS / 32)
+#include "ekf_factor.cuh"
 #define FACT_LD (EKF_UB + 1)
-__device__ __forceinline__ void dmma884f(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(d0), "+d"(d1)
-               : "d"(a), "d"(b));
-}
-// One warp: 8x8 tile D = sum_{k<32} A(r,k) B(k,n), A(r,k) = Ap[r*ar + k*ak], B(k,n) = Bp[k*bk + n*bn].
-// All 16 fragments are loaded first and the 8 DMMAs run as 4 independent chains of 2 (the DMMA
-// accumulate latency, not its issue rate, bounds these tiny products).  Returns the thread's two
-// elements (row lane/4, columns 2*(lane%4), +1).
-__device__ __forceinline__ void warp_tile_mma32(const double* Ap, int ar, int ak, const double* Bp, int bk, int bn,
-                                                double& d0, double& d1) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
-  double af[8], bf[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) { af[q] = Ap[g * ar + (4 * q + t4) * ak]; bf[q] = Bp[(4 * q + t4) * bk + g * bn]; }
-  double c[4][2];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) { c[q][0] = 0.0; c[q][1] = 0.0; }
-#pragma unroll
-  for (int q = 0; q < 8; ++q) dmma884f(c[q & 3][0], c[q & 3][1], af[q], bf[q]);
-  d0 = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
-  d1 = (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
-}
-
 __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __restrict__ Sb, const double* __restrict__ nu,
                                                              double* __restrict__ Linv, double* __restrict__ yout, DevCtl* ctl) {
   extern __shared__ __align__(16) double fsm[];
-  double* A = fsm;                          // [EKF_UB][FACT_LD]; lower: L, strictly upper: Linv^T blocks
-  double* Di = A + EKF_UB * FACT_LD;        // [4][32][33] inverses of the diagonal blocks
-  double* col = Di + 4 * 32 * 33;           // [2 * EKF_UB] scratch (pivot reciprocals, nu)
-  double* Tb = col + 2 * EKF_UB;            // [4][32][33] block products
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  // Blocked right-looking Cholesky, 32-column panels.  Per panel:
-  //  (a) warp 0 factors the 32x32 diagonal block entirely in registers (lane = row; pivots and column
-  //      entries travel by warp shuffle, so the per-column dependency chain has no block barrier; the
-  //      next pivot's rsqrt is started as soon as its element is final, in the shadow of the remaining
-  //      rank-1 updates of the current column);
-  //  (b) the rows below solve X L_JJ^T = A_panel by substitution, lane = row, L_JJ broadcast from
-  //      shared memory, reciprocals of the pivots reused;
-  //  (c) all threads apply the rank-32 update to the trailing block with register tiles.
-  for (int e = tid; e < EKF_UB * EKF_UB; e += FACT_THREADS) A[(e >> 7) * FACT_LD + (e & 127)] = Sb[e];
-  for (int e = tid; e < EKF_UB; e += FACT_THREADS) col[EKF_UB + e] = nu[e];
-  double* rinvs = col;  // [EKF_UB] reciprocals of the pivots
-  FSTAMP(0);
-  __syncthreads();
-  FSTAMP(1);
-  for (int J = 0; J < 4; ++J) {
-    const int o = 32 * J;
-    if (ty == 0) {
-      double Rr[32];
-#pragma unroll
-      for (int c = 0; c < 32; ++c) Rr[c] = A[(o + tx) * FACT_LD + o + c];
-      double piv = __shfl_sync(0xffffffffu, Rr[0], 0);
-      double rinv = rsqrt(piv);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (tx == 0 && !(piv > 0.0)) ctl->chol_fail = 1;
-        const double lij = (tx > j) ? Rr[j] * rinv : ((tx == j) ? piv * rinv : 0.0);
-        Rr[j] = lij;
-        if (tx == j) rinvs[o + j] = rinv;
-        if (j + 1 < 32) {
-          const double l1 = __shfl_sync(0xffffffffu, lij, j + 1);
-          Rr[j + 1] -= lij * l1;
-          piv = __shfl_sync(0xffffffffu, Rr[j + 1], j + 1);
-          rinv = rsqrt(piv);
-        }
-#pragma unroll
-        for (int c = j + 2; c < 32; ++c) {
-          const double lc = __shfl_sync(0xffffffffu, lij, c);
-          Rr[c] -= lij * lc;  // rows < c compute values that are never read
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < 32; ++c)
-        if (c <= tx) A[(o + tx) * FACT_LD + o + c] = Rr[c];
-    }
-    __syncthreads();
-    FSTAMP(2 + 3 * J);
-    const int m = EKF_UB - o - 32;  // rows below the panel
-    if (m > 0) {
-      if (ty < (m >> 5)) {
-        const int r = o + 32 + ty * 32 + tx;
-        double x[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) x[c] = A[r * FACT_LD + o + c];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          double sx = x[c];
-#pragma unroll
-          for (int dd = 0; dd < c; ++dd) sx -= x[dd] * A[(o + c) * FACT_LD + o + dd];
-          x[c] = sx * rinvs[o + c];
-        }
-#pragma unroll
-        for (int c = 0; c < 32; ++c) A[r * FACT_LD + o + c] = x[c];
-      }
-      __syncthreads();
-      FSTAMP(3 + 3 * J);
-      // trailing block on the tensor pipe: lower 8x8 tiles (ti >= tj) of A22 -= P P^T, K = 32,
-      // round-robin over the 16 warps
-      {
-        const int base = o + 32, nt8 = m >> 3, g = tx >> 2, t4 = tx & 3;
-        const int ntile = nt8 * (nt8 + 1) / 2;
-        for (int t = ty; t < ntile; t += FACT_WARPS) {
-          int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-          while (ti * (ti + 1) / 2 > t) --ti;
-          while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-          const int tj = t - ti * (ti + 1) / 2;
-          double d0, d1;
-          const double* Pa = A + (size_t)(base + 8 * ti) * FACT_LD + o;
-          const double* Pb = A + (size_t)(base + 8 * tj) * FACT_LD + o;
-          warp_tile_mma32(Pa, FACT_LD, 1, Pb, 1, FACT_LD, d0, d1);
-          double* dst = A + (size_t)(base + 8 * ti + g) * FACT_LD + base + 8 * tj + 2 * t4;
-          dst[0] -= d0;
-          dst[1] -= d1;
-        }
-      }
-      __syncthreads();
-      FSTAMP(4 + 3 * J);
-    }
-  }
-  // Inverses of the four diagonal blocks: warp J solves X L_JJ^T = I by the same substitution as
-  // the panel solve (lane = row r of X = L_JJ^-T, i.e. column r of L_JJ^-1).
-  if (ty < 4) {
-    const int o = 32 * ty;
-    double x[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      double sx = (c == tx) ? 1.0 : 0.0;
-#pragma unroll
-      for (int dd = 0; dd < c; ++dd) sx -= x[dd] * A[(o + c) * FACT_LD + o + dd];
-      x[c] = sx * rinvs[o + c];
-    }
-    double* X = Di + ty * 32 * 33;
-#pragma unroll
-    for (int c = 0; c < 32; ++c) X[c * 33 + tx] = x[c];  // Linv[c][r] = X[r][c]
-  }
-  __syncthreads();
-  FSTAMP(14);
-  // Off-diagonal blocks of Linv on the tensor pipe, by distance from the diagonal:
-  //   Linv[J][I] = -Dinv_J sum_{P=I..J-1} L[J][P] X(P,I),  X(I,I) = Dinv_I, X(P,I) for P > I parked
-  //   transposed in the unused upper triangle: A[32 I + c][32 P + r] = Linv[32 P + r][32 I + c].
-  // 16 warps = the 16 8x8 tiles of a 32x32 block.
-  {
-    const int wti = ty >> 2, wtj = ty & 3, g = tx >> 2, t4 = tx & 3;
-    for (int dist = 1; dist < 4; ++dist) {
-      const int nblk = 4 - dist;
-      for (int b = 0; b < nblk; ++b) {
-        const int I = b, J = b + dist;
-        double a0 = 0.0, a1 = 0.0;
-        for (int P = I; P < J; ++P) {
-          double d0, d1;
-          const double* Ap = A + (size_t)(J * 32 + wti * 8) * FACT_LD + P * 32;
-          if (P == I) warp_tile_mma32(Ap, FACT_LD, 1, Di + I * 32 * 33 + wtj * 8, 33, 1, d0, d1);
-          else warp_tile_mma32(Ap, FACT_LD, 1, A + (size_t)(I * 32 + wtj * 8) * FACT_LD + P * 32, 1, FACT_LD, d0, d1);
-          a0 += d0; a1 += d1;
-        }
-        double* T = Tb + b * 32 * 33;
-        T[(wti * 8 + g) * 33 + wtj * 8 + 2 * t4] = a0;
-        T[(wti * 8 + g) * 33 + wtj * 8 + 2 * t4 + 1] = a1;
-      }
-      __syncthreads();
-      for (int b = 0; b < nblk; ++b) {
-        const int I = b, J = b + dist;
-        double d0, d1;
-        warp_tile_mma32(Di + J * 32 * 33 + (wti * 8) * 33, 33, 1, Tb + b * 32 * 33 + wtj * 8, 33, 1, d0, d1);
-        const int r = wti * 8 + g, c = wtj * 8 + 2 * t4;
-        A[(size_t)(I * 32 + c) * FACT_LD + J * 32 + r] = -d0;
-        A[(size_t)(I * 32 + c + 1) * FACT_LD + J * 32 + r] = -d1;
-      }
-      __syncthreads();
-    }
-  }
-  FSTAMP(15);
-  // write Linv (row r by warp r mod 16: coalesced stores, conflict-free transposed reads) and
-  // y = Linv nu from the same values
-  for (int r = ty; r < EKF_UB; r += FACT_WARPS) {
-    const int Jr = r >> 5;
-    double part = 0.0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int c = tx + 32 * q;
-      double v = 0.0;
-      if (q < Jr) v = A[(size_t)c * FACT_LD + r];
-      else if (q == Jr) v = Di[Jr * 32 * 33 + (r & 31) * 33 + tx];  // zero above the diagonal
-      Linv[r * EKF_UB + c] = v;
-      part += v * col[EKF_UB + c];
-    }
-    for (int o2 = 16; o2 > 0; o2 >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o2);
-    if (tx == 0) yout[r] = part;
-  }
-  FSTAMP(16);
+  cta_factor<EKF_UB>(fsm, Sb, EKF_UB, nu, Linv, EKF_UB, yout, &ctl->chol_fail);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -588,7 +296,7 @@ __global__ void __launch_bounds__(256) k_bookkeeping(const double* __restrict__ 
 }
 
 // ---- launch wrappers ---------------------------------------------------------------------------
-static const size_t kFactSmem = (size_t)(EKF_UB * FACT_LD + 4 * 32 * 33 + 2 * EKF_UB + 4 * 32 * 33) * sizeof(double);
+static const size_t kFactSmem = (size_t)cta_factor_smem_doubles<EKF_UB>() * sizeof(double);
 static const size_t kVSmem = (size_t)(EKF_UB * VT_LD + VT_ROWS * VT_LD + EKF_UB) * sizeof(double);
 
 int update_kernels_init() {

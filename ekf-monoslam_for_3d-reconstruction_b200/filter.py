@@ -179,3 +179,106 @@ def match_batch(frames_dev, n_frames, width, height, stride, templates_dev, feat
                                C.c_void_p(out_score_dev), C.c_void_p(stream))
     if rc != 0:
         raise EkfError(f"ekf_match_batch failed: {rc}")
+
+
+class FilterBatch:
+    """B independent VSlamFilter instances stepped together on one device (BASELINE config 3).
+    Seed it from a single VSlamFilter, optionally perturb the camera states, then call
+    captureNewFrame / step once per frame."""
+
+    def __init__(self, cfg, n_filters, feature_capacity=32, device=0):
+        self.L = lib()
+        self.cfg = cfg
+        h = C.c_void_p()
+        rc = self.L.ekf_batch_create(C.byref(cfg), int(n_filters), int(feature_capacity), int(device), C.byref(h))
+        if rc != 0:
+            raise EkfError(f"ekf_batch_create failed with {rc}")
+        self.h = h
+        self.B = int(n_filters)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ekf_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise EkfError(f"ekf batch error {rc}: {self.L.ekf_batch_last_error(self.h).decode()}")
+        return rc
+
+    def describe(self):
+        d = _abi.EkfBatchDesc()
+        self._ck(self.L.ekf_batch_describe(self.h, C.byref(d)))
+        return d
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.L.ekf_batch_set_stream(self.h, C.c_void_p(int(cuda_stream_ptr) if cuda_stream_ptr else 0)))
+
+    def sync(self):
+        self._ck(self.L.ekf_batch_sync(self.h))
+
+    def seed_from(self, filt):
+        self._ck(self.L.ekf_batch_seed_from(self.h, filt.h))
+
+    def set_camera_states(self, mu14):
+        a = np.ascontiguousarray(mu14, dtype=np.float64)
+        if a.shape != (self.B, 14):
+            raise ValueError("set_camera_states expects (n_filters, 14)")
+        self._ck(self.L.ekf_batch_set_camera_states(self.h, _ptr(a)))
+
+    def captureNewFrame(self, img, stamp=-1.0):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        self._ck(self.L.ekf_batch_capture_frame(self.h, _ptr(img), img.shape[1], img.shape[0], img.strides[0], float(stamp)))
+
+    def captureNewFrame_device(self, dev_ptr, width, height, stride, stamp=-1.0):
+        self._ck(self.L.ekf_batch_capture_frame_device(self.h, C.c_void_p(int(dev_ptr)), width, height, stride, float(stamp)))
+
+    def step(self, picks=None, dv=(0.0, 0.0, 0.0), dw=(0.0, 0.0, 0.0), vcontrol=False):
+        """predict + update of every filter."""
+        p = np.ascontiguousarray(picks if picks is not None else np.zeros(0), dtype=np.uint32)
+        a = np.asarray(dv, dtype=np.float64); b = np.asarray(dw, dtype=np.float64)
+        self._ck(self.L.ekf_batch_step(self.h, _ptr(a), _ptr(b), int(bool(vcontrol)), _ptr(p), int(p.size)))
+
+    def camera_states(self, want_sigma=False):
+        mu = np.zeros((self.B, 14)); st = np.zeros((self.B, _abi.BATCH_STAT_FIELDS), dtype=np.int32)
+        S = np.zeros((self.B, 14, 14)) if want_sigma else None
+        self._ck(self.L.ekf_batch_get_camera_states(self.h, _ptr(mu), _ptr(S) if want_sigma else None, _ptr(st)))
+        return (mu, S, st) if want_sigma else (mu, st)
+
+    def numOfFeatures(self, f):
+        return self._ck(self.L.ekf_batch_num_features(self.h, int(f)))
+
+    def state_dim(self, f):
+        return self._ck(self.L.ekf_batch_state_dim(self.h, int(f)))
+
+    def get_full(self, f):
+        n = self.state_dim(f)
+        mu = np.zeros(n); S = np.zeros((n, n))
+        self._ck(self.L.ekf_batch_get_full(self.h, int(f), _ptr(mu), _ptr(S), n))
+        return mu, S
+
+    def set_full(self, f, mu, S):
+        mu = np.ascontiguousarray(mu, dtype=np.float64); S = np.ascontiguousarray(S, dtype=np.float64)
+        n = self.state_dim(f)
+        if mu.size != n or S.shape != (n, n):
+            raise ValueError("set_full: shape mismatch")
+        self._ck(self.L.ekf_batch_set_full(self.h, int(f), _ptr(mu), _ptr(S), n))
+
+    def feature(self, f, i):
+        o = _abi.EkfFeatureInfo()
+        self._ck(self.L.ekf_batch_get_feature(self.h, int(f), int(i), C.byref(o)))
+        return o
+
+    def kernel_launches(self):
+        return int(self.L.ekf_batch_kernel_launches(self.h))
+
+    def last_step_ms(self):
+        out = np.zeros(3, dtype=np.float32)
+        self._ck(self.L.ekf_batch_last_step_ms(self.h, _ptr(out)))
+        return dict(predict=float(out[0]), match=float(out[1]), update=float(out[2]))

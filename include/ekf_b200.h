@@ -174,6 +174,57 @@ int ekf_match_batch(const uint8_t* frames, int n_frames, int width, int height, 
                     const double* h, const double* S, float sigma_size, float ncc_threshold,
                     float search_clamp, int32_t* out_uv, float* out_score, void* stream);
 
+/* ---- batch of independent filters (BASELINE config 3: multi-hypothesis / Monte-Carlo) ----------- */
+/* B filters with the same configuration, stepped together on one device: one fused CTA per filter
+ * for predict (vslamRansac.cpp:451-603) and for update (:964-1341), one CTA per (filter, feature)
+ * for the active search (:870-880).  All filters see the same frame (one camera, many hypotheses).
+ * Every filter runs exactly the single-filter algorithm; there is no exchange between filters, so a
+ * batch shards across GPUs by filter index with no collective (one ekf_batch per device / rank).
+ * feature_capacity <= 32 (the stacked update of one filter is kept in shared memory). */
+typedef struct ekf_batch ekf_batch;
+typedef struct ekf_batch_desc {
+  int32_t n_filters, feature_capacity, state_capacity /* 14 + 6 * feature_capacity */, ld /* Sigma row stride */;
+  int32_t device;
+  int32_t reserved[3];
+} ekf_batch_desc;
+/* per-filter counters of the last step, EKF_BATCH_STAT_FIELDS int32 each */
+#define EKF_BATCH_STAT_FIELDS 8
+enum { EKF_BSTAT_INNOV = 0, EKF_BSTAT_MATCHED = 1, EKF_BSTAT_LI = 2, EKF_BSTAT_HI = 3, EKF_BSTAT_HYPS = 4,
+       EKF_BSTAT_CHOL_FAIL = 5, EKF_BSTAT_REMOVED = 6, EKF_BSTAT_TOPUP = 7 };
+
+int ekf_batch_create(const ekf_config* cfg, int n_filters, int feature_capacity, int device, ekf_batch** out);
+int ekf_batch_destroy(ekf_batch* b);
+int ekf_batch_describe(const ekf_batch* b, ekf_batch_desc* out);
+int ekf_batch_set_stream(ekf_batch* b, void* cuda_stream);
+int ekf_batch_sync(ekf_batch* b);
+const char* ekf_batch_last_error(const ekf_batch* b);
+/* Every filter of the batch becomes a copy of `src` (state, covariance, feature table, templates,
+ * time stamps); src must live on the same device and hold <= feature_capacity features. */
+int ekf_batch_seed_from(ekf_batch* b, ekf_handle* src);
+/* Overwrites the 14 camera entries of every filter's state (HOST array, n_filters x 14, row-major):
+ * the per-hypothesis perturbation of a Monte-Carlo ensemble. */
+int ekf_batch_set_camera_states(ekf_batch* b, const double* mu14);
+/* captureNewFrame for the whole batch (vslamRansac.cpp:226-245): HOST / DEVICE source. */
+int ekf_batch_capture_frame(ekf_batch* b, const uint8_t* gray, int width, int height, int stride, double stamp);
+int ekf_batch_capture_frame_device(ekf_batch* b, const uint8_t* gray_dev, int width, int height, int stride, double stamp);
+/* predict + update (match, 1-point RANSAC, both corrections, book-keeping, feature deletion) for
+ * every filter.  dv / dw / vcontrol as ekf_predict; picks as ekf_update (every filter draws from the
+ * same sequence).  Returns after the per-filter counters have reached the host. */
+int ekf_batch_step(ekf_batch* b, const double dv[3], const double dw[3], int vcontrol, const uint32_t* picks, int n_picks);
+/* Results of the last step, HOST output arrays: camera state (n_filters x 14), 14 x 14 covariance
+ * block (n_filters x 196, may be NULL), counters (n_filters x EKF_BATCH_STAT_FIELDS, may be NULL). */
+int ekf_batch_get_camera_states(ekf_batch* b, double* mu14, double* sigma14, int32_t* stats);
+/* Single-filter views for parity tests and checkpointing. */
+int ekf_batch_num_features(ekf_batch* b, int filter);
+int ekf_batch_state_dim(ekf_batch* b, int filter);
+int ekf_batch_get_full(ekf_batch* b, int filter, double* mu, double* sigma, int ld);
+int ekf_batch_set_full(ekf_batch* b, int filter, const double* mu, const double* sigma, int ld);
+int ekf_batch_get_feature(ekf_batch* b, int filter, int idx, ekf_feature_info* out);
+/* Kernels of this library launched on the batch so far. */
+int64_t ekf_batch_kernel_launches(const ekf_batch* b);
+/* CUDA-event time (ms) of the three kernel classes of the last step: predict, match, update. */
+int ekf_batch_last_step_ms(ekf_batch* b, float out[3]);
+
 /* ---- per-kernel timing (CUDA events on the handle's stream; off by default) ---------------------- */
 #define EKF_PROF_CLASSES 12
 typedef struct ekf_profile {

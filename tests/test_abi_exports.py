@@ -51,8 +51,12 @@ def test_sass_is_sm100a_with_dmma(pkg):
     if out.returncode != 0:
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in out.stdout
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "k_gemm_nt_sub", path], capture_output=True, text=True).stdout
-    assert "DMMA" in sass
+    sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+    fn = sass.split("Function : ")
+    gemm = [f for f in fn if f.startswith("_Z13k_gemm_nt_sub")]
+    upd = [f for f in fn if f.startswith("_Z14k_batch_update")]
+    assert gemm and "DMMA.8x8x4" in gemm[0]
+    assert upd and "DMMA.8x8x4" in upd[0]
 
 
 def test_ctypes_structs_match_c_layout(pkg, tmp_path):
