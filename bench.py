@@ -38,7 +38,12 @@ WORKLOADS = {
     # name: (features, width, height)
     "cfg1_n50": (50, 640, 480),
     "cfg2_n500": (500, 640, 480),
+    # BASELINE configs[2]: 4096 independent filters x 30 features per GPU, sharded by filter
+    "cfg3_batch4096": (30, 640, 480),
 }
+BATCH_FILTERS = 4096
+METRIC_BATCH = "batched EKF filter-steps/s (predict+match+update), 4096 independent filters x N=30 features per GPU"
+UNIT_BATCH = "filter-steps/s"
 
 
 def log(*a):
@@ -269,6 +274,179 @@ def run_ours(args):
         print(json.dumps(out), flush=True)
 
 
+def run_batch(args):
+    """BASELINE configs[2]: a Monte-Carlo ensemble of independent filters, sharded by filter across
+    ranks with no data-path collective (weak scaling: BATCH_FILTERS filters per GPU)."""
+    import torch
+    import ekfb200
+    pkg = ekfb200.load_package()
+    pkg.lib()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    K, Wm = args.steps, max(args.warmup, 3)
+    B = args.filters
+    nfeat, width, height = WORKLOADS[args.workload]
+    scene = make_scene(pkg, args.workload, 1 + Wm + K, seed=1235)
+    frames = [scene.frame(t) for t in range(scene.n_frames)]
+    cfg = pkg.default_config(**scene.config_overrides())
+    stream = torch.cuda.current_stream()
+
+    def new_batch():
+        f = pkg.VSlamFilter(cfg, feature_capacity=nfeat + 2, device=local)
+        added = seed_filter(f, scene)
+        assert added == nfeat
+        b = pkg.FilterBatch(cfg, B, feature_capacity=nfeat + 2, device=local)
+        b.set_stream(stream.cuda_stream)
+        b.seed_from(f)
+        # per-hypothesis perturbation of the camera state: filters [rank*B, (rank+1)*B) of the ensemble
+        b.set_camera_states(pkg.dist.ensemble_camera_states(f.getState(), pkg.dist.ensemble_slice(rank, world, B)))
+        del f
+        return b
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    picks = [scene.picks(t, nfeat) for t in range(scene.n_frames)]
+
+    def timed(step_fn, batch):
+        times, cls = [], {"predict": 0.0, "match": 0.0, "update": 0.0}
+        for t in range(1, 1 + Wm):
+            step_fn(batch, t)
+        torch.cuda.synchronize()
+        l0 = batch.kernel_launches()
+        barrier()
+        for t in range(1 + Wm, 1 + Wm + K):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step_fn(batch, t)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+            for k, v in batch.last_step_ms().items():
+                cls[k] += v
+        barrier()
+        return np.array(times), batch.kernel_launches() - l0, {k: v / K for k, v in cls.items()}
+
+    dev_frames = [torch.from_numpy(f).cuda() for f in frames]
+
+    def step_resident(b, t):
+        b.captureNewFrame_device(dev_frames[t].data_ptr(), width, height, width, scene.stamps[t])
+        b.step(picks[t])
+
+    batch = new_batch()
+    sampler = ClockSampler(local)
+    sampler.start()
+    tA, launches, cls = timed(step_resident, batch)
+    clocks = sampler.stop()
+    mu14, st = batch.camera_states()
+    n_state = batch.state_dim(0)
+    li_mean = float(st[:, 2].mean())
+    del batch
+
+    pinned = [torch.from_numpy(f).pin_memory() for f in frames]
+    last = {}
+
+    def step_e2e(b, t):
+        b.captureNewFrame(pinned[t].numpy(), scene.stamps[t])   # H2D inside the step
+        b.step(picks[t])                                        # D2H of camera states + counters inside
+        last["mu"], last["st"] = b.camera_states()
+
+    batch = new_batch()
+    tB, _, _ = timed(step_e2e, batch)
+    del batch
+    h2d = width * height + 4 * nfeat
+    d2h = B * 14 * 8 + B * 8 * 4
+
+    def agg(times):
+        return pkg.dist.max_over_ranks(float(times.sum()), dist, "cuda")
+
+    totA, totB = agg(tA), agg(tB)
+    all_cams = pkg.dist.gather_camera_states(last["mu"], dist, "cuda")   # reporting only (SURVEY.md 8(e))
+    assert all_cams.shape == (world * B, 14) and np.isfinite(all_cams).all()
+    out = None
+    if rank == 0:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        hbm_peak = float(peaks.get("hbm_gbs", 6456.5))
+        # k_batch_update: algorithmic bytes = read + write of every filter's covariance (SURVEY.md 8(d): 16 n^2)
+        bytes_per_launch = 16.0 * n_state * n_state * B
+        upd_ms = cls["update"]
+        achieved = bytes_per_launch / (upd_ms / 1e3) / 1e9 if upd_ms > 0 else 0.0
+        out = {
+            "metric": METRIC_BATCH, "value": round(world * B * K / (totA / 1e3), 1), "unit": UNIT_BATCH, "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": round(totA / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {B} independent filters per GPU x {nfeat} inverse-depth features (n={n_state}), "
+                                   f"one shared {width}x{height} u8 frame per step, predict+match+update per filter "
+                                   f"(mean n_li={li_mean:.1f})",
+                       "l2": f"inputs larger than L2 ({B * n_state * n_state * 8 / 1e6:.0f} MB of covariance per step vs 126 MB)",
+                       "multi_gpu": "sharded by filter, no data-path collective" if world > 1 else "n/a",
+                       "filters_per_gpu": B},
+            "e2e": {"value": round(world * B * K / (totB / 1e3), 1), "unit": UNIT_BATCH, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"kernel": "k_batch_update (one CTA per filter: RANSAC, W = Sigma H^T, Cholesky gain, DMMA downdate from smem)",
+                         "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+                         "frac": round(achieved / hbm_peak, 4), "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs", "bytes_per_launch": bytes_per_launch,
+                         "avg_launch_ms": round(upd_ms, 4), "share_of_step": round(upd_ms / float(tA.mean()), 4)},
+            "kernel_ms_per_step": {k: round(v, 4) for k, v in cls.items()},
+        }
+        tfile = os.path.join(ROOT, "profiles", "batch_update_traffic.json")
+        if os.path.exists(tfile):
+            try:
+                out["roofline"]["traffic"] = json.load(open(tfile)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_batch(pkg, args.workload, budget_s=args.cpu_budget)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out), flush=True)
+
+
+def cpu_baseline_batch(pkg, workload, budget_s=20.0):
+    """The oracle (dense reference algebra) on a bounded sample of the ensemble: filters are
+    independent, so they are spread over the host cores with one oracle filter per thread."""
+    import concurrent.futures as cf
+    import orc
+    orc.build()
+    nfeat = WORKLOADS[workload][0]
+    scene = make_scene(pkg, workload, 3)
+    cfg = pkg.default_config(**scene.config_overrides())
+    cores = os.cpu_count() or 1
+    L = orc.lib(omp=False)
+
+    def one(_):
+        o = orc.OracleFilter(cfg, kind=0, omp=False)
+        seed_filter(o, scene)
+        t0 = time.perf_counter()
+        n = 0
+        for t in (1, 2):
+            o.captureNewFrame(scene.frame(t), scene.stamps[t]); o.predict(); o.update(scene.picks(t, nfeat))
+            n += 1
+        return n, time.perf_counter() - t0
+
+    nfil = max(cores, 8)
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(max_workers=cores) as ex:   # ctypes releases the GIL inside the oracle calls
+        res = list(ex.map(one, range(nfil)))
+    wall = time.perf_counter() - t0
+    steps = sum(r[0] for r in res)
+    busy = sum(r[1] for r in res)
+    return {"value": round(steps / (busy / cores), 3), "unit": UNIT_BATCH, "cores": cores, "kind": "port",
+            "sample": f"{nfil} filters x 2 steps of {workload} on {cores} threads (one oracle filter per thread, dense reference "
+                      f"algebra, fp64), {busy / steps * 1e3:.1f} ms per filter-step per core, wall {wall:.1f} s incl. seeding"}
+
+
 def _oracle_seeded(pkg, orc, workload, n_frames, omp=True):
     """An oracle filter holding the workload's seeded map.  Seeding goes through a structured
     (O(n)-per-feature) twin when a GPU is present, else through the oracle's own dense addFeature."""
@@ -369,11 +547,14 @@ def main():
     ap.add_argument("--workload", default="cfg2_n500", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-square", action="store_true", help="downdate all n x n tiles instead of lower triangle + mirror")
+    ap.add_argument("--filters", type=int, default=BATCH_FILTERS, help="filters per GPU of the batched workload")
     ap.add_argument("--cpu-budget", type=float, default=30.0)
     ap.add_argument("--ref-budget", type=float, default=150.0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload.startswith("cfg3"):
+        run_batch(args)
     else:
         run_ours(args)
 
