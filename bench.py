@@ -33,6 +33,11 @@ for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, _p)
 
 METRIC = "EKF frames/s (predict+match+update), single filter, N=500 features"
+
+
+def metric_for(workload):
+    n = WORKLOADS[workload][0]
+    return f"EKF frames/s (predict+match+update), single filter, N={n} features"
 UNIT = "frames/s"
 WORKLOADS = {
     # name: (features, width, height)
@@ -40,7 +45,14 @@ WORKLOADS = {
     "cfg2_n500": (500, 640, 480),
     # BASELINE configs[2]: 4096 independent filters x 30 features per GPU, sharded by filter
     "cfg3_batch4096": (30, 640, 480),
+    # BASELINE configs[3]: large map, 2000 features (n = 12014, Sigma = 1.15 GB), un-partitioned on one B200
+    "cfg4_n2000": (2000, 1920, 1080),
+    # BASELINE configs[4]: stateless active-search NCC matching, 256 frames x 200 features, 11x11 patches
+    "cfg5_match": (200, 1920, 1080),
 }
+MATCH_FRAMES = 256
+METRIC_MATCH = "active-search NCC matches/s (Patch::findMatch, 11x11 templates, 200 features per 1920x1080 frame, 256 frames)"
+UNIT_MATCH = "matches/s"
 BATCH_FILTERS = 4096
 METRIC_BATCH = "batched EKF filter-steps/s (predict+match+update), 4096 independent filters x N=30 features per GPU"
 UNIT_BATCH = "filter-steps/s"
@@ -243,7 +255,7 @@ def run_ours(args):
                 traffic = None
         step_ms = float(tA.mean())
         out = {
-            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "metric": metric_for(args.workload), "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": round(totA / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload}: single filter, {nfeat} inverse-depth features (n={n_state}), "
@@ -266,7 +278,123 @@ def run_ours(args):
             "kernel_ms_per_step": {k: round(v[0] / K, 5) for k, v in prof.items() if v[1] > 0},
         }
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(pkg, args.workload, budget_s=args.cpu_budget)
+            if nfeat > 600:
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                       "sample": "not run: one dense reference frame at n = 12014 is ~2.8e13 flops (minutes per frame); "
+                                                 "see the cfg2 line for the measured CPU baseline"}
+            else:
+                out["cpu_baseline"] = cpu_baseline(pkg, args.workload, budget_s=args.cpu_budget)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out), flush=True)
+
+
+def run_match(args):
+    """BASELINE configs[4]: the stateless batched matcher (ekf_match_batch), frames sharded across ranks."""
+    import torch
+    import ekfb200
+    pkg = ekfb200.load_package()
+    pkg.lib()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    K, Wm = args.steps, max(args.warmup, 3)
+    M, width, height = WORKLOADS[args.workload]
+    F = args.frames
+    w = 11
+    d = pkg.synth.match_batch_inputs(n_frames=F, features_per_frame=M, width=width, height=height, window=w, seed=1239 + rank)
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+    host = {k: torch.from_numpy(np.ascontiguousarray(d[k])).pin_memory() for k in ("frames", "templates", "h", "S")}
+    res = {k: host[k].to(dev) for k in host}
+    uv = torch.zeros((F * M, 2), dtype=torch.int32, device=dev); sc = torch.zeros(F * M, dtype=torch.float32, device=dev)
+    uv_h = torch.zeros((F * M, 2), dtype=torch.int32).pin_memory(); sc_h = torch.zeros(F * M, dtype=torch.float32).pin_memory()
+
+    def launch(t):
+        pkg.match_batch(t["frames"].data_ptr(), F, width, height, width, t["templates"].data_ptr(), M, w, t["h"].data_ptr(),
+                        t["S"].data_ptr(), uv.data_ptr(), sc.data_ptr(), sigma_size=3.0, stream=stream.cuda_stream)
+
+    def step_resident():
+        launch(res)
+
+    stage = {k: torch.empty_like(res[k]) for k in res}
+
+    def step_e2e():
+        for k in stage:
+            stage[k].copy_(host[k], non_blocking=True)          # H2D inside the step
+        launch(stage)
+        uv_h.copy_(uv, non_blocking=True); sc_h.copy_(sc, non_blocking=True)   # D2H inside the step
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for _ in range(Wm):
+            fn()
+        barrier()
+        ts = []
+        for _ in range(K):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream); fn(); e1.record(stream)
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        barrier()
+        return np.array(ts)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    tA = timed(step_resident)
+    clocks = sampler.stop()
+    tB = timed(step_e2e)
+    found = int((uv_h[:, 0] >= 0).sum())
+    assert np.array_equal(uv_h.numpy()[uv_h.numpy()[:, 0] >= 0], d["truth"][uv_h.numpy()[:, 0] >= 0]), "matches differ from the planted truth"
+    totA = pkg.dist.max_over_ranks(float(tA.sum()), dist, "cuda"); totB = pkg.dist.max_over_ranks(float(tB.sum()), dist, "cuda")
+    out = None
+    if rank == 0:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        hbm_peak = float(peaks.get("hbm_gbs", 6456.5))
+        delta = 12  # 3 sigma of S = diag(16,16)
+        win_bytes = (2 * delta + w) * (2 * delta + w) + w * w + 16 + 32 + 12
+        bytes_per_launch = float(win_bytes) * F * M
+        ms = float(tA.mean())
+        cand = 3.14159 * delta * delta            # in-ellipse candidates per feature
+        dp_ops = cand * w * w * 5.0 * F * M      # SURVEY.md 8(d): 5 DP ops per pixel per candidate
+        out = {"metric": METRIC_MATCH, "value": round(world * F * M * K / (totA / 1e3), 1), "unit": UNIT_MATCH, "n_gpus": world,
+               "steps": K, "warmup": Wm, "ms_per_step": round(totA / K, 4), "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": f"{args.workload}: {F} frames {width}x{height} u8 per GPU x {M} features, 11x11 templates, "
+                                      f"S = diag(16,16) +- 10 % => ~{cand:.0f} in-ellipse candidates per feature; {found} of {F * M} accepted",
+                          "l2": f"inputs larger than L2 ({F * width * height / 1e6:.0f} MB of frames)",
+                          "multi_gpu": "sharded by frame, no collective" if world > 1 else "n/a"},
+               "e2e": {"value": round(world * F * M * K / (totB / 1e3), 1), "unit": UNIT_MATCH,
+                       "h2d_bytes_per_step": int(sum(host[k].numel() * host[k].element_size() for k in host)),
+                       "d2h_bytes_per_step": int(uv_h.numel() * 4 + sc_h.numel() * 4)},
+               "gpu_launches": K, "clocks": clocks,
+               "roofline": {"kernel": "k_match_batch (one CTA per feature; fp64-ALU bound, not HBM: see alu)", "bound": "hbm",
+                            "achieved": round(bytes_per_launch / (ms / 1e3) / 1e9, 2), "peak": hbm_peak, "unit": "GB/s",
+                            "frac": round(bytes_per_launch / (ms / 1e3) / 1e9 / hbm_peak, 5), "traffic": None,
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs", "bytes_per_launch": bytes_per_launch,
+                            "avg_launch_ms": round(ms, 4), "share_of_step": 1.0,
+                            "alu": {"dp_ops_per_launch": dp_ops, "achieved_tops": round(dp_ops / (ms / 1e3) / 1e12, 3),
+                                    "peak_tops": 18.3, "peak_source": "tools/fp64_probe dadd/dmul issue rate (no FMA: parity needs separate roundings)"}}}
+        if world == 1 and not args.no_cpu_baseline:
+            import orc
+            orc.build()
+            nf = 2
+            t0 = time.perf_counter()
+            orc.match_batch(d["frames"][:nf], d["templates"][:nf * M], d["h"][:nf * M], d["S"][:nf * M], sigma_size=3.0, omp=True)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": round(nf * M / dt, 1), "unit": UNIT_MATCH, "cores": orc.lib(omp=True).orc_num_threads(), "kind": "port",
+                                   "sample": f"{nf} frames x {M} features through the oracle's Patch::findMatch (OpenMP over features), {dt:.2f} s"}
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -526,7 +654,7 @@ def run_reference(args):
     per = float(np.mean(times))
     val = 1.0 / per
     n_state = o.state_dim()
-    out = {"impl": "reference", "metric": METRIC, "value": round(val, 5), "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+    out = {"impl": "reference", "metric": metric_for(args.workload), "value": round(val, 5), "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
            "steps": len(times), "warmup": done_w, "ms_per_step": round(per * 1e3, 2), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": f"{args.workload}: single filter, {nfeat} inverse-depth features (n={n_state}), CPU oracle of the "
@@ -547,6 +675,7 @@ def main():
     ap.add_argument("--workload", default="cfg2_n500", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-square", action="store_true", help="downdate all n x n tiles instead of lower triangle + mirror")
+    ap.add_argument("--frames", type=int, default=MATCH_FRAMES, help="frames per GPU of the matcher workload")
     ap.add_argument("--filters", type=int, default=BATCH_FILTERS, help="filters per GPU of the batched workload")
     ap.add_argument("--cpu-budget", type=float, default=30.0)
     ap.add_argument("--ref-budget", type=float, default=150.0)
@@ -555,6 +684,8 @@ def main():
         run_reference(args)
     elif args.workload.startswith("cfg3"):
         run_batch(args)
+    elif args.workload.startswith("cfg5"):
+        run_match(args)
     else:
         run_ours(args)
 

@@ -97,7 +97,7 @@ int ekf_destroy(ekf_handle* h) {
   for (auto& r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->prof_pool) cudaEventDestroy(e);
   cudaFree(h->mu); cudaFree(h->muB); cudaFree(h->Sigma); cudaFree(h->SigmaB); cudaFree(h->W); cudaFree(h->nu);
-  cudaFree(h->Lb); cudaFree(h->Dinv); cudaFree(h->yb); cudaFree(h->delta); cudaFree(h->mu_i); cudaFree(h->cand);
+  cudaFree(h->Lb); cudaFree(h->Dinv); cudaFree(h->Dblk); cudaFree(h->yb); cudaFree(h->delta); cudaFree(h->mu_i); cudaFree(h->cand);
   cudaFree(h->map_dev); cudaFree(h->keep_dev); cudaFree(h->newpos_dev); cudaFree(h->ctl); cudaFree(h->frame);
   cudaFree(h->picks_dev); cudaFree(h->out_dev); cudaFree(h->gemm_counters);
   if (h->out_host) cudaFreeHost(h->out_host);
@@ -141,7 +141,7 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
 #define TRY(x) if ((e = (x)) != cudaSuccess) return bail(e, #x);
   TRY(dalloc(&h->mu, h->ld)) TRY(dalloc(&h->muB, h->ld)) TRY(dalloc(&h->Sigma, ssz)) TRY(dalloc(&h->SigmaB, ssz))
   TRY(dalloc(&h->W, (size_t)(h->ncap + 1) * EKF_UB)) TRY(dalloc(&h->nu, EKF_UB)) TRY(dalloc(&h->Lb, EKF_UB * EKF_UB))
-  TRY(dalloc(&h->Dinv, EKF_UB * EKF_UB)) TRY(dalloc(&h->yb, EKF_UB)) TRY(dalloc(&h->delta, h->ld)) TRY(dalloc(&h->mu_i, h->ld))
+  TRY(dalloc(&h->Dinv, EKF_UB * EKF_UB)) TRY(dalloc(&h->Dblk, EKF_UB * 32)) TRY(dalloc(&h->yb, EKF_UB)) TRY(dalloc(&h->delta, h->ld)) TRY(dalloc(&h->mu_i, h->ld))
   TRY(dalloc(&h->cand, h->Ncap)) TRY(dalloc(&h->map_dev, h->ncap)) TRY(dalloc(&h->keep_dev, h->Ncap))
   TRY(dalloc(&h->newpos_dev, h->Ncap)) TRY(dalloc(&h->ctl, 1)) TRY(dalloc(&h->gemm_counters, 2))
   TRY(alloc_feattab(h->ft, h->Ncap, w2)) TRY(alloc_feattab(h->ftB, h->Ncap, w2))
@@ -351,8 +351,8 @@ static int stacked_update(ekf_handle* h, int cnt) {
   cudaMemsetAsync(h->delta, 0, sizeof(double) * (size_t)h->n, st);
   for (int f0 = 0; f0 < cnt; f0 += EKF_UB / 2) {
     { ProfScope ps(h, 3); launch_blk_gather(st, h->Sigma, h->ld, h->n, h->ft, f0, cnt, h->delta, h->W, h->nu, &h->launches); }
-    { ProfScope ps(h, 4); launch_blk_factor(st, h->W, h->ft, f0, cnt, h->nu, h->dcfg, h->Lb, h->Dinv, h->yb, h->ctl, &h->launches);  /* Lb = S_b scratch, Dinv = Linv */ }
-    { ProfScope ps(h, 5); launch_blk_V(st, h->W, h->n, h->Dinv, h->yb, h->delta, &h->launches); }
+    { ProfScope ps(h, 4); launch_blk_factor(st, h->W, h->ft, f0, cnt, h->nu, h->dcfg, h->Lb, h->Dinv, h->Dblk, h->yb, h->ctl, &h->launches);  /* Lb = S_b scratch, Dinv = L, Dblk = diagonal-block inverses */ }
+    { ProfScope ps(h, 5); launch_blk_V(st, h->W, h->n, h->Dinv, h->Dblk, h->yb, h->delta, &h->launches); }
     {
       ProfScope ps(h, 6);
       const int rc = launch_gemm_nt_sub(st, h->Sigma, h->ld, h->W, EKF_UB, h->W, EKF_UB, h->n, h->n, EKF_UB, nullptr, h->lower_only,

@@ -148,10 +148,12 @@ __global__ void __launch_bounds__(BPRED_THREADS) k_batch_predict(BatchView bv, F
     double t0 = 0, t1 = 0, h0 = 0, h1 = 0;
     if (lane < nd) {
       const int jb = ekf_idx13(lane, pos);
-      for (int c = 0; c < nd; ++c) {
-        const double sg = Sigma[(size_t)ekf_idx13(c, pos) * ld + jb];
-        t0 += hc[c] * sg; t1 += hc[13 + c] * sg;
-      }
+      double sg[13];
+#pragma unroll
+      for (int c = 0; c < 13; ++c) sg[c] = (c < nd) ? Sigma[(size_t)ekf_idx13(c, pos) * ld + jb] : 0.0;  // independent loads in flight
+#pragma unroll
+      for (int c = 0; c < 13; ++c)
+        if (c < nd) { t0 += hc[c] * sg[c]; t1 += hc[13 + c] * sg[c]; }
       h0 = hc[lane]; h1 = hc[13 + lane];
     }
     double s00 = t0 * h0, s01 = t0 * h1, s10 = t1 * h0, s11 = t1 * h1;
@@ -171,8 +173,9 @@ __global__ void __launch_bounds__(BPRED_THREADS) k_batch_predict(BatchView bv, F
 // ------------------------------------------------------------------------------------------------
 struct UpdSmem {
   double* W;      // [BNMAX][BLDW]   W = Sigma H^T, then V = W L^-T
-  double* fact;   // cta_factor_smem_doubles<BK>()
-  double* Sb;     // [BK][BLDW]      S, then Linv
+  double* fact;   // Cholesky workspace / row staging of the W gather (kFactDoubles)
+  double* Dv;     // [BK / 32][32][BLDD] inverses of the diagonal blocks of L
+  double* Sb;     // [BK][BLDW]      S, then L
   double* nu;     // [BK]
   double* y;      // [BK]
   double* mu_i;   // [BNMAX]
@@ -180,8 +183,10 @@ struct UpdSmem {
   double* qj;     // [48] quaternion-normalisation scratch: J[16], C[16], T[16]
   int* ibuf;      // cand[BNCAP], fids[BNCAP], poss[BNCAP], nds[BNCAP]
 };
+#define BLDD 36
+static constexpr size_t kFactDoubles = 2 * 16 * BNMAX > cta_chol22_smem_doubles<BK>() ? 2 * 16 * BNMAX : cta_chol22_smem_doubles<BK>();
 static constexpr size_t kUpdSmemDoubles =
-    (size_t)BNMAX * BLDW + cta_factor_smem_doubles<BK>() + (size_t)BK * BLDW + BK + BK + BNMAX + BNCAP * 27 + 48 + (4 * BNCAP) / 2;
+    (size_t)BNMAX * BLDW + kFactDoubles + (BK / 32) * 32 * BLDD + (size_t)BK * BLDW + BK + BK + BNMAX + BNCAP * 27 + 48 + (4 * BNCAP) / 2;
 static constexpr size_t kUpdSmemBytes = kUpdSmemDoubles * sizeof(double);
 
 // One stacked update over the `cnt` features listed in ft.sel (V:1036-1064 / V:1245-1284).
@@ -207,20 +212,50 @@ __device__ void cta_stacked_update(const UpdSmem& sm, double* __restrict__ Sigma
     sm.nu[tid] = v;
   }
   __syncthreads();
-  // W = Sigma H^T (n x k), zero-padded to BNMAX x BK
-  for (int e = tid; e < BNMAX * (BK / 2); e += BUPD_THREADS) {
-    const int i = e / (BK / 2), a = e % (BK / 2);
-    double w0 = 0, w1 = 0;
-    if (i < n && a < cnt) {
-      const double* row = Sigma + (size_t)i * ld;
-      const int pos = poss[a], nd = nds[a];
-      const double* hs = sm.Hs + a * 27;
-      for (int c = 0; c < nd; ++c) {
-        const double s = row[ekf_idx13(c, pos)];
-        w0 += s * hs[c]; w1 += s * hs[13 + c];
+  // W = Sigma H^T (n x k), zero-padded to BNMAX x BK.  Sigma rows are staged through shared memory
+  // (the Cholesky workspace is idle here) in chunks of 16 rows with cp.async, double buffered, so the
+  // 13-column gathers hit shared memory instead of 13 dependent L2 round trips; thread = (row, feature).
+  {
+    constexpr int CH = 16;
+    double* stage = sm.fact;                      // 2 x CH x ld doubles (ld <= 208)
+    const int nchunk = (n + CH - 1) / CH;
+    const int vec_per_row = ld >> 1;              // 16-byte pieces per row (ld is a multiple of 8)
+    auto issue = [&](int ck) {
+      const int r0 = ck * CH;
+      double* dst = stage + (size_t)(ck & 1) * CH * ld;
+      for (int e = tid; e < CH * vec_per_row; e += BUPD_THREADS) {
+        const int r = e / vec_per_row, v = e - r * vec_per_row;
+        if (r0 + r < n) {
+          const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + (size_t)r * ld + 2 * v);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(Sigma + (size_t)(r0 + r) * ld + 2 * v));
+        }
       }
+      asm volatile("cp.async.commit_group;\n" ::);
+    };
+    issue(0);
+    const int rl = tid >> 5, a = tid & 31;       // 16 rows x 32 features per chunk
+    const int pos = poss[a], nd = nds[a];
+    const double* hs = sm.Hs + a * 27;
+    for (int ck = 0; ck < nchunk; ++ck) {
+      if (ck + 1 < nchunk) { issue(ck + 1); asm volatile("cp.async.wait_group 1;\n" ::); }
+      else asm volatile("cp.async.wait_group 0;\n" ::);
+      __syncthreads();
+      const int i = ck * CH + rl;
+      double w0 = 0, w1 = 0;
+      if (i < n && a < cnt) {
+        const double* row = stage + (size_t)(ck & 1) * CH * ld + (size_t)rl * ld;
+        for (int c = 0; c < nd; ++c) {
+          const double s = row[ekf_idx13(c, pos)];
+          w0 += s * hs[c]; w1 += s * hs[13 + c];
+        }
+      }
+      if (i < BNMAX) *reinterpret_cast<double2*>(sm.W + (size_t)i * BLDW + 2 * a) = make_double2(w0, w1);
+      __syncthreads();
     }
-    *reinterpret_cast<double2*>(sm.W + (size_t)i * BLDW + 2 * a) = make_double2(w0, w1);
+    for (int e = tid; e < (BNMAX - nchunk * CH) * (BK / 2); e += BUPD_THREADS) {   // zero rows past the last chunk
+      const int i = nchunk * CH + e / (BK / 2), aa = e % (BK / 2);
+      *reinterpret_cast<double2*>(sm.W + (size_t)i * BLDW + 2 * aa) = make_double2(0.0, 0.0);
+    }
   }
   __syncthreads();
   // S = H W + sigma_px^2 I; rows / columns past k are identity
@@ -238,26 +273,10 @@ __device__ void cta_stacked_update(const UpdSmem& sm, double* __restrict__ Sigma
     sm.Sb[r * BLDW + s] = v;
   }
   __syncthreads();
-  cta_factor<BK>(sm.fact, sm.Sb, BLDW, sm.nu, sm.Sb, BLDW, sm.y, &ctl->chol_fail);
-  __syncthreads();
-  // V = W Linv^T in place: warp owns 8-row tiles; Linv lower triangular => column tile ct needs k < 8 ct + 8
+  cta_chol22<BK>(sm.fact, sm.Sb, BLDW, sm.nu, sm.Sb, BLDW, sm.Dv, BLDD, sm.y, &ctl->chol_fail);
+  // V = W L^-T in place: every warp owns 8-row tiles for the whole blocked triangular solve
   for (int rt = warp; rt < BNMAX / 8; rt += BUPD_THREADS / 32) {
-    double af[BK / 4];
-    const double* wr = sm.W + (size_t)(rt * 8 + g) * BLDW + t4;
-#pragma unroll
-    for (int q = 0; q < BK / 4; ++q) af[q] = wr[4 * q];
-    __syncwarp();
-    double part = 0.0;
-#pragma unroll
-    for (int ct = 0; ct < BK / 8; ++ct) {
-      double d0 = 0.0, d1 = 0.0;
-      const double* lr = sm.Sb + (size_t)(ct * 8 + g) * BLDW + t4;
-#pragma unroll
-      for (int q = 0; q < 2 * ct + 2; ++q) dmma884f(d0, d1, af[q], lr[4 * q]);
-      double* dst = sm.W + (size_t)(rt * 8 + g) * BLDW + ct * 8 + 2 * t4;
-      *reinterpret_cast<double2*>(dst) = make_double2(d0, d1);
-      part += d0 * sm.y[ct * 8 + 2 * t4] + d1 * sm.y[ct * 8 + 2 * t4 + 1];
-    }
+    double part = warp_trsm_tile<BK>(sm.W + (size_t)rt * 8 * BLDW, BLDW, sm.Sb, BLDW, sm.Dv, BLDD, sm.y);
     // mu += V y: the four lanes of a row hold its partial sums
     part += __shfl_xor_sync(0xffffffffu, part, 1);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
@@ -265,22 +284,35 @@ __device__ void cta_stacked_update(const UpdSmem& sm, double* __restrict__ Sigma
     if (t4 == 0 && i < n) mu[i] += part;
   }
   __syncthreads();
-  // Sigma -= V V^T on the fp64 tensor pipe: 16 x 16 warp tiles (2 x 2 DMMA tiles), K = ceil(k / 4) * 4
+  // Sigma -= V V^T on the fp64 tensor pipe: 16 x 16 warp tiles (2 x 2 DMMA tiles), K = ceil(k / 4) * 4.
+  // The C tile of a warp's next tile is loaded before the DMMAs of the current one (L2 latency hidden).
   {
-    const int nt = (n + 15) >> 4, ksteps = (k + 3) >> 2;
-    for (int t = warp; t < nt * nt; t += BUPD_THREADS / 32) {
+    const int nt = (n + 15) >> 4, ksteps = (k + 3) >> 2, ntile = nt * nt;
+    auto load_c = [&](int t, double (&c)[2][2][2]) {
+      const int ti = t / nt, tj = t - ti * nt;
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int r = ti * 16 + a * 8 + g, col = tj * 16 + cc * 8 + 2 * t4;
+          double2 v = make_double2(0.0, 0.0);
+          if (t < ntile) {
+            if (r < n && col + 1 < n) v = *reinterpret_cast<const double2*>(Sigma + (size_t)r * ld + col);
+            else if (r < n && col < n) v.x = Sigma[(size_t)r * ld + col];
+          }
+          c[a][cc][0] = v.x; c[a][cc][1] = v.y;
+        }
+    };
+    double nxt[2][2][2];
+    load_c(warp, nxt);
+    for (int t = warp; t < ntile; t += BUPD_THREADS / 32) {
       const int ti = t / nt, tj = t - ti * nt;
       double acc[2][2][2];
 #pragma unroll
       for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int r = ti * 16 + a * 8 + g, col = tj * 16 + c * 8 + 2 * t4;
-          double2 v = make_double2(0.0, 0.0);
-          if (r < n && col + 1 < n) v = *reinterpret_cast<const double2*>(Sigma + (size_t)r * ld + col);
-          else if (r < n && col < n) v.x = Sigma[(size_t)r * ld + col];
-          acc[a][c][0] = v.x; acc[a][c][1] = v.y;
-        }
+        for (int cc = 0; cc < 2; ++cc) { acc[a][cc][0] = nxt[a][cc][0]; acc[a][cc][1] = nxt[a][cc][1]; }
+      load_c(t + BUPD_THREADS / 32, nxt);
       const double* va = sm.W + (size_t)(ti * 16 + g) * BLDW + t4;
       const double* vb = sm.W + (size_t)(tj * 16 + g) * BLDW + t4;
       for (int q = 0; q < ksteps; ++q) {
@@ -294,10 +326,10 @@ __device__ void cta_stacked_update(const UpdSmem& sm, double* __restrict__ Sigma
 #pragma unroll
       for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int r = ti * 16 + a * 8 + g, col = tj * 16 + c * 8 + 2 * t4;
-          if (r < n && col + 1 < n) *reinterpret_cast<double2*>(Sigma + (size_t)r * ld + col) = make_double2(acc[a][c][0], acc[a][c][1]);
-          else if (r < n && col < n) Sigma[(size_t)r * ld + col] = acc[a][c][0];
+        for (int cc = 0; cc < 2; ++cc) {
+          const int r = ti * 16 + a * 8 + g, col = tj * 16 + cc * 8 + 2 * t4;
+          if (r < n && col + 1 < n) *reinterpret_cast<double2*>(Sigma + (size_t)r * ld + col) = make_double2(acc[a][cc][0], acc[a][cc][1]);
+          else if (r < n && col < n) Sigma[(size_t)r * ld + col] = acc[a][cc][0];
         }
     }
   }
@@ -358,7 +390,8 @@ __global__ void __launch_bounds__(BUPD_THREADS, 1) k_batch_update(BatchView bv, 
   UpdSmem sm;
   sm.W = usm;
   sm.fact = sm.W + (size_t)BNMAX * BLDW;
-  sm.Sb = sm.fact + cta_factor_smem_doubles<BK>();
+  sm.Dv = sm.fact + kFactDoubles;
+  sm.Sb = sm.Dv + (BK / 32) * 32 * BLDD;
   sm.nu = sm.Sb + (size_t)BK * BLDW;
   sm.y = sm.nu + BK;
   sm.mu_i = sm.y + BK;
@@ -394,11 +427,13 @@ __global__ void __launch_bounds__(BUPD_THREADS, 1) k_batch_update(BatchView bv, 
       double Tm[26];
       for (int bb = 0; bb < nd; ++bb) {
         const int jb = ekf_idx13(bb, pos);
+        double sg[13];
+#pragma unroll
+        for (int c = 0; c < 13; ++c) sg[c] = (c < nd) ? Sigma[(size_t)ekf_idx13(c, pos) * ld + jb] : 0.0;
         double t0 = 0, t1 = 0;
-        for (int c = 0; c < nd; ++c) {
-          const double s = Sigma[(size_t)ekf_idx13(c, pos) * ld + jb];
-          t0 += Hc[c] * s; t1 += Hc[13 + c] * s;
-        }
+#pragma unroll
+        for (int c = 0; c < 13; ++c)
+          if (c < nd) { t0 += Hc[c] * sg[c]; t1 += Hc[13 + c] * sg[c]; }
         Tm[bb] = t0; Tm[13 + bb] = t1;
       }
       double S[4] = {0, 0, 0, 0};

@@ -60,11 +60,13 @@ static __device__ __noinline__ void cta_ransac(const double* __restrict__ Sigma,
       const int pos = s_pos, nd = s_nd;
       for (int i = tid; i < n; i += nthr) {
         const double* row = Sigma + (size_t)i * ld;
+        double sg[13];
+#pragma unroll
+        for (int c = 0; c < 13; ++c) sg[c] = (c < nd) ? row[ekf_idx13(c, pos)] : 0.0;  // independent loads in flight
         double w0 = 0, w1 = 0;
-        for (int c = 0; c < nd; ++c) {
-          const double s = row[ekf_idx13(c, pos)];
-          w0 += s * Hs[c]; w1 += s * Hs[13 + c];
-        }
+#pragma unroll
+        for (int c = 0; c < 13; ++c)
+          if (c < nd) { w0 += sg[c] * Hs[c]; w1 += sg[c] * Hs[13 + c]; }
         const double k0 = w0 * Sinv[0] + w1 * Sinv[2];
         const double k1 = w0 * Sinv[1] + w1 * Sinv[3];
         mu_i[i] = mu[i] + (k0 * inn[0] + k1 * inn[1]);

@@ -1,22 +1,30 @@
 // csrc/ekf_match.cu — K3: active-search NCC matcher (Patch::findMatch, Patch.cpp:215-291, and
 // computeCorrelation, Patch.cpp:293-329).  SURVEY.md §8(a) rows a11-a13.
 //
-// One CTA per feature.  Staged in shared memory: the template as d1 = (float)pixel - mean (doubles),
-// the search window ((2*delta_u + w) x (2*delta_v + w), at most 72 x 72 at the reference's +-20 px
-// clamp) converted ONCE to doubles, and its summed-area table (exact integer sums give every
-// candidate's mean without a pass over its pixels).  Each thread owns two vertically adjacent
-// candidates and walks their w x w pixels in the reference's row-major order with
-// __dadd_rn/__dmul_rn (never contracted), so every candidate's double-precision score is produced
-// by the same IEEE operation sequence as the reference; template statistics are hoisted (identical
-// for every candidate).  The score is rounded to float and compared in float exactly as
-// Patch.cpp:243,252,278 do.  Warp shuffles carry the arg-max with the reference's tie-break: the
-// first candidate in scan order (u outer, v inner) wins.  fp64-ALU bound: 5 DP ops per pixel per
-// candidate, one 8-byte shared load per 10 DP ops.
+// One CTA per feature.  The reference scores every in-ellipse candidate with a sequential
+// double-precision two-pass NCC, rounds the score to float and keeps the first strict maximum.
+// Reproducing that bit for bit does not require running its 5 x w^2 DP operations for every
+// candidate: pixels are 8-bit integers, so
+//     ncc* = (n Stp - T P) / sqrt((n Stt - T^2)(n Spp - P^2))          (n = w^2)
+// is available EXACTLY from integer sums, and the reference's floating-point value differs from it
+// by < 1e-13 (121 roundings of 1e-16 relative).  Rounding to float is monotonic, so only candidates
+// whose ncc* lies within two float ulps (+ that error bound) of the largest ncc* can be, or tie
+// with, the reference's float maximum.  Hence:
+//   fast pass : u8 search window (<= 72 x 72), its summed-area tables of p and p^2 (exact ints) and the
+//               template packed 4 bytes per word live in shared memory; each thread scores 4
+//               horizontally adjacent candidates at a time with DP4A (u8 x u8 dot products) on
+//               funnel-shifted window words -> Stp; P, Spp from the tables; ncc* in double.
+//   exact pass: the handful of candidates inside the guard band (normally one) are re-scored with the
+//               reference's own operation sequence (__dadd_rn/__dmul_rn, row-major, never contracted)
+//               and compared as floats with the reference's first-wins tie-break.
+// The result (match coordinates, accept / reject, float score) is bit-identical to the reference's;
+// if the guard band ever overflows its list (pathological ties) every candidate takes the exact pass.
 #include "ekf_kernels.h"
 #include "ekf_math.cuh"
 
 #define MATCH_THREADS 256
-#define MATCH_MAX_W 31  // largest template side
+#define MATCH_MAX_W 31   // largest template side
+#define MATCH_LIST 128   // guard-band list capacity
 
 struct MatchJob {
   const uint8_t* frame;  // frame base
@@ -34,20 +42,76 @@ struct MatchResult {
 // shared-memory plan for template side w and search clamp cl (pixels)
 struct MatchSmem {
   int side;      // max window side = 2 cl + w
-  int wsd;       // window row stride in doubles
-  size_t off_win, off_sat, off_red, total;
+  int wsb;       // window row stride in bytes (multiple of 4, >= side + 8)
+  int tw;        // template words per row
+  int ncmax;     // max candidates = (2 cl + 1)^2
+  size_t off_tpk, off_tb, off_win, off_sat1, off_sat2, off_score, off_list, off_red, total;
 };
 __host__ __device__ inline MatchSmem match_smem_plan(int w, int cl) {
   MatchSmem p;
   p.side = 2 * cl + w;
-  p.wsd = p.side + 1;
-  size_t o = (size_t)((w * w + 1) & ~1) * sizeof(double);               // d1
-  p.off_win = o; o += (size_t)(p.side + 1) * p.wsd * sizeof(double);     // window (one spare row)
-  p.off_sat = o; o += (size_t)(p.side + 1) * (p.side + 1) * sizeof(int); // summed-area table
+  p.wsb = (p.side + 8 + 3) & ~3;
+  p.tw = (w + 3) >> 2;
+  p.ncmax = (2 * cl + 1) * (2 * cl + 1);
+  size_t o = 0;
+  p.off_tpk = o; o += (size_t)w * p.tw * 4;                                   // packed template
+  p.off_tb = o; o += (size_t)((w * w + 15) & ~15);                            // template bytes
+  o = (o + 15) & ~(size_t)15;
+  p.off_win = o; o += (size_t)(p.side + 1) * p.wsb;                           // u8 window (+1 spare row)
+  o = (o + 15) & ~(size_t)15;
+  p.off_sat1 = o; o += (size_t)(p.side + 1) * (p.side + 1) * 4;               // box sums of p   (horizontal, then w x w)
+  p.off_sat2 = o; o += (size_t)(p.side + 1) * (p.side + 1) * 4;               // box sums of p^2
   o = (o + 7) & ~(size_t)7;
-  p.off_red = o; o += 2 * sizeof(double) + 8 * sizeof(float) + 8 * sizeof(int);
+  p.off_score = o; o += (size_t)p.ncmax * 8;                                  // ncc* per candidate
+  p.off_list = o; o += (size_t)MATCH_LIST * 4;                                // guard-band candidate keys
+  o = (o + 7) & ~(size_t)7;
+  p.off_red = o; o += 16 * sizeof(double) + 16 * sizeof(float) + 16 * sizeof(int);
   p.total = o;
   return p;
+}
+
+// The reference's computeCorrelation for one candidate (window ROI at byte offset `roi`), exact
+// operation order; n1 = sum (t - m1)^2 is hoisted (identical for every candidate).
+__device__ __forceinline__ float match_exact_score(const uint8_t* tmpl, const uint8_t* win, int wsb, int roi, int w, double m1,
+                                                   double n1, int P) {
+  const double m2 = __ddiv_rn((double)P, (double)(w * w));
+  double n2 = 0, corr = 0;
+  for (int r = 0; r < w; ++r) {
+    const uint8_t* wr = win + roi + r * wsb;
+    const uint8_t* tr = tmpl + r * w;
+#pragma unroll 11
+    for (int x = 0; x < w; ++x) {
+      const double da = __dsub_rn((double)(float)tr[x], m1);
+      const double db = __dsub_rn((double)(float)wr[x], m2);
+      n2 = __dadd_rn(n2, __dmul_rn(db, db));
+      corr = __dadd_rn(corr, __dmul_rn(da, db));
+    }
+  }
+  return (float)__ddiv_rn(corr, __dsqrt_rn(__dmul_rn(n2, n1)));
+}
+
+// Stp of four horizontally adjacent candidates: u8 x u8 dot products (DP4A) of the packed template
+// rows with funnel-shifted window words.  WC > 0 fixes the template side at compile time.
+template <int WC>
+__device__ __forceinline__ void match_dots4(const uint8_t* win0, int wsb, const unsigned* tpk, int w_rt, unsigned acc[4]) {
+  const int w = WC > 0 ? WC : w_rt;
+  const int tw = (w + 3) >> 2;
+#pragma unroll
+  for (int r = 0; r < w; ++r) {
+    const unsigned* wr = reinterpret_cast<const unsigned*>(win0 + r * wsb);
+    const unsigned* tr = tpk + r * tw;
+    unsigned lo = wr[0];
+#pragma unroll
+    for (int k = 0; k < tw; ++k) {
+      const unsigned hi = wr[k + 1];
+      const unsigned t = tr[k];
+      acc[0] = __dp4a(lo, t, acc[0]);
+      acc[1] = __dp4a(__funnelshift_r(lo, hi, 8), t, acc[1]);
+      acc[2] = __dp4a(__funnelshift_r(lo, hi, 16), t, acc[2]);
+      acc[3] = __dp4a(__funnelshift_r(lo, hi, 24), t, acc[3]);
+      lo = hi;
+    }
+  }
 }
 
 // Core search for one feature by one CTA.  All threads must call.
@@ -86,137 +150,180 @@ __device__ MatchResult match_one(const MatchJob& jb, int w, float sigma_size, fl
   if (ch > pl.side - w + 1) ch = pl.side - w + 1;
   const bool any = cw > 0 && ch > 0;
   const int ww = any ? cw + w - 1 : 0, wh = any ? ch + w - 1 : 0;
-  const int wsd = pl.wsd, sst = pl.side + 1;
+  const int wsb = pl.wsb, tw = pl.tw;
 
-  double* d1 = reinterpret_cast<double*>(smem_raw);
-  double* wind = reinterpret_cast<double*>(smem_raw + pl.off_win);
-  int* sat = reinterpret_cast<int*>(smem_raw + pl.off_sat);
-  double* red_n1 = reinterpret_cast<double*>(smem_raw + pl.off_red);
-  float* red_s = reinterpret_cast<float*>(red_n1 + 2);
-  int* red_k = reinterpret_cast<int*>(red_s + 8);
-  int* isum = reinterpret_cast<int*>(red_n1 + 1);
+  unsigned* tpk = reinterpret_cast<unsigned*>(smem_raw + pl.off_tpk);
+  uint8_t* tb = smem_raw + pl.off_tb;
+  uint8_t* win = smem_raw + pl.off_win;
+  unsigned* sat1 = reinterpret_cast<unsigned*>(smem_raw + pl.off_sat1);
+  unsigned* sat2 = reinterpret_cast<unsigned*>(smem_raw + pl.off_sat2);
+  double* score = reinterpret_cast<double*>(smem_raw + pl.off_score);
+  int* list = reinterpret_cast<int*>(smem_raw + pl.off_list);
+  double* red_d = reinterpret_cast<double*>(smem_raw + pl.off_red);   // [0..7] warp maxima, [8] n1, [9] M*
+  float* red_s = reinterpret_cast<float*>(red_d + 16);
+  int* red_k = reinterpret_cast<int*>(red_s + 16);                     // [0..7] keys, [8] T, [9] TT, [10] list count
 
-  // --- template mean (integer sum: exact in any order) ---
-  if (tid == 0) *isum = 0;
+  // --- template: packed words (zero padded), integer sums T = sum t, TT = sum t^2 ---
+  if (tid < 16) red_k[tid] = 0;
   __syncthreads();
   {
-    int part = 0;
-    for (int e = tid; e < w2; e += MATCH_THREADS) part += jb.tmpl[e];
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if ((tid & 31) == 0 && part) atomicAdd(isum, part);
+    int pt = 0, ptt = 0;
+    for (int e = tid; e < w * tw; e += MATCH_THREADS) {
+      const int r = e / tw, k4 = (e - r * tw) * 4;
+      unsigned word = 0;
+      for (int c = 0; c < 4; ++c)
+        if (k4 + c < w) {
+          const unsigned v = jb.tmpl[r * w + k4 + c];
+          word |= v << (8 * c);
+          pt += (int)v; ptt += (int)(v * v);
+        }
+      tpk[e] = word;
+    }
+    for (int e = tid; e < w2; e += MATCH_THREADS) tb[e] = jb.tmpl[e];
+    for (int o = 16; o > 0; o >>= 1) { pt += __shfl_xor_sync(0xffffffffu, pt, o); ptt += __shfl_xor_sync(0xffffffffu, ptt, o); }
+    if ((tid & 31) == 0 && (pt | ptt)) { atomicAdd(&red_k[8], pt); atomicAdd(&red_k[9], ptt); }
   }
-  // --- stage the window as doubles (u8 -> float -> double is exact) ---
+  // --- stage the window as bytes; columns past ww and the spare row are zero ---
   if (any) {
     const int x0 = ilo - half, y0 = jlo - half;
-    for (int yy = tid / 64; yy < wh; yy += MATCH_THREADS / 64)
-      for (int xx = tid & 63; xx < wsd; xx += 64)
-        wind[yy * wsd + xx] = (xx < ww) ? (double)(float)jb.frame[(size_t)(y0 + yy) * jb.fstride + x0 + xx] : 0.0;
-    for (int xx = tid; xx < wsd; xx += MATCH_THREADS) wind[wh * wsd + xx] = 0.0;  // spare row
-  }
-  __syncthreads();
-  const double m1 = __ddiv_rn((double)(*isum), (double)w2);
-  for (int e = tid; e < w2; e += MATCH_THREADS) d1[e] = __dsub_rn((double)(float)jb.tmpl[e], m1);
-  // --- summed-area table: row prefix sums, then column prefix sums (ints, exact) ---
-  if (any) {
-    for (int yy = tid; yy < wh; yy += MATCH_THREADS) {
-      int run = 0;
-      sat[(yy + 1) * sst] = 0;
-      for (int xx = 0; xx < ww; ++xx) { run += (int)wind[yy * wsd + xx]; sat[(yy + 1) * sst + xx + 1] = run; }
+    for (int e = tid; e < (wh + 1) * wsb; e += MATCH_THREADS) {
+      const int yy = e / wsb, xx = e - yy * wsb;
+      win[e] = (yy < wh && xx < ww) ? jb.frame[(size_t)(y0 + yy) * jb.fstride + x0 + xx] : (uint8_t)0;
     }
-    for (int xx = tid; xx <= ww; xx += MATCH_THREADS) sat[xx] = 0;
   }
   __syncthreads();
+  const int T = red_k[8], TT = red_k[9];
+  const double dn = (double)w2;
+  const double m1 = __ddiv_rn((double)T, dn);
+  // --- w x w box sums of p and p^2 for every candidate (exact unsigned ints), separable: horizontal
+  //     sums H[y][iu] over w pixels, then vertical sums over w rows, written to B[jv][iu] ---
+  unsigned* H1 = sat1; unsigned* H2 = sat2;                 // [wh][cw]
   if (tid == MATCH_THREADS - 1) {
-    // n1 = sum (s1 - m1)^2 sequentially in the reference order; overlaps the column pass below
+    // n1 = sum (s1 - m1)^2 sequentially in the reference order; overlaps the horizontal pass
     double n1 = 0;
-    for (int e = 0; e < w2; ++e) n1 = __dadd_rn(n1, __dmul_rn(d1[e], d1[e]));
-    *red_n1 = n1;
+#pragma unroll 11
+    for (int e = 0; e < w2; ++e) {
+      const double d = __dsub_rn((double)(float)tb[e], m1);
+      n1 = __dadd_rn(n1, __dmul_rn(d, d));
+    }
+    red_d[8] = n1;
   } else if (any) {
-    for (int xx = tid; xx <= ww; xx += MATCH_THREADS - 1) {
-      int run = 0;
-      for (int yy = 1; yy <= wh; ++yy) { run += sat[yy * sst + xx]; sat[yy * sst + xx] = run; }
+    for (int e = tid; e < wh * cw; e += MATCH_THREADS - 1) {
+      const int yy = e / cw, iu = e - yy * cw;
+      const uint8_t* pr = win + yy * wsb + iu;
+      unsigned r1 = 0, r2 = 0;
+      for (int x = 0; x < w; ++x) { const unsigned v = pr[x]; r1 += v; r2 += v * v; }
+      H1[e] = r1; H2[e] = r2;
     }
   }
   __syncthreads();
-  const double n1 = *red_n1;
+  // vertical pass into registers, then (after a barrier) back over the same arrays as B[jv][iu]
+  {
+    unsigned b1[8], b2[8];   // ncand <= 1681 -> at most 7 candidates per thread
+    int cnt = 0;
+    for (int c = tid; c < cw * ch && cnt < 8; c += MATCH_THREADS, ++cnt) {
+      const int jv = c / cw, iu = c - jv * cw;
+      unsigned r1 = 0, r2 = 0;
+      for (int r = 0; r < w; ++r) { r1 += H1[(jv + r) * cw + iu]; r2 += H2[(jv + r) * cw + iu]; }
+      b1[cnt] = r1; b2[cnt] = r2;
+    }
+    __syncthreads();
+    cnt = 0;
+    for (int c = tid; c < cw * ch && cnt < 8; c += MATCH_THREADS, ++cnt) { H1[c] = b1[cnt]; H2[c] = b2[cnt]; }
+  }
+  __syncthreads();
+  const double n1 = red_d[8];
+  const double d1 = dn * (double)TT - (double)T * (double)T;   // exact (< 2^53)
 
+  // --- fast pass: ncc* of every in-ellipse candidate ---
+  const double kNone = -1.0e300;
+  double lmax = kNone;
+  if (any) {
+    const int gx = (cw + 3) >> 2, ngroups = gx * ch;
+    for (int gq = tid; gq < ngroups; gq += MATCH_THREADS) {
+      const int jv = gq / gx, iu4 = (gq - jv * gx) * 4;
+      const int ja = jlo + jv;
+      // ellipse gate in float, same association as Patch.cpp:247
+      bool valid[4];
+      bool anyv = false;
+      const float dj = (float)(ja - vc);
+      const float ey = __fmul_rn(__fmul_rn(y_2_coeff, dj), dj);
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int iu = iu4 + s;
+        const float fdi = (float)(ilo + iu - uc);
+        const float e = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(x_2_coeff, fdi), fdi), ey), __fmul_rn(__fmul_rn(yx_coeff, fdi), dj));
+        valid[s] = (iu < cw) && (e <= sigma_2);
+        anyv |= valid[s];
+      }
+      if (!anyv) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          if (iu4 + s < cw) score[jv * cw + iu4 + s] = kNone;
+        continue;
+      }
+      unsigned acc[4] = {0u, 0u, 0u, 0u};
+      if (w == 11) match_dots4<11>(win + jv * wsb + iu4, wsb, tpk, w, acc);   // the benchmark / synthetic-scene template size
+      else if (w == 21) match_dots4<21>(win + jv * wsb + iu4, wsb, tpk, w, acc);  // reference default (ConfigVSLAM.cpp:31)
+      else match_dots4<0>(win + jv * wsb + iu4, wsb, tpk, w, acc);
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int iu = iu4 + s;
+        if (iu >= cw) continue;
+        double v = kNone;
+        if (valid[s]) {
+          const unsigned P = H1[jv * cw + iu];
+          const unsigned PP = H2[jv * cw + iu];
+          const double d2 = dn * (double)PP - (double)P * (double)P;
+          if (d1 > 0.0 && d2 > 0.0) {
+            const double num = dn * (double)acc[s] - (double)T * (double)P;
+            v = num / sqrt(d1 * d2);
+            if (v > lmax) lmax = v;
+          } else {
+            v = kNone;  // flat template or flat window: 0/0 in the reference, never selected
+          }
+        }
+        score[jv * cw + iu] = v;
+      }
+    }
+  }
+  // --- block maximum of ncc* ---
+  for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  if ((tid & 31) == 0) red_d[tid >> 5] = lmax;
+  __syncthreads();
+  if (tid == 0) {
+    double m = red_d[0];
+    for (int wv = 1; wv < MATCH_THREADS / 32; ++wv) m = fmax(m, red_d[wv]);
+    red_d[9] = m;
+  }
+  __syncthreads();
+  const double Mstar = red_d[9];
   float best = -1.0f;
   int bestkey = 0x7fffffff;
-  if (any) {
-    const int chp = (ch + 1) >> 1;
-    const int npair = cw * chp;
-    const double dw2 = (double)w2;
-    for (int c = tid; c < npair; c += MATCH_THREADS) {
-      // consecutive lanes take consecutive u (conflict-free 8-byte window reads); the two candidates
-      // of a thread are vertical neighbours and share every window row they both touch
-      const int jp = c / cw, iu = c - jp * cw;
-      const int jv = 2 * jp;
-      const int i = ilo + iu, ja = jlo + jv;
-      const int di = i - uc;
-      const bool hasB = (jv + 1 < ch);
-      bool va, vb;
-      {
-        const float fdi = (float)di;
-        const float ex = __fmul_rn(__fmul_rn(x_2_coeff, fdi), fdi);
-        const float dja = (float)(ja - vc), djb = (float)(ja + 1 - vc);
-        // ellipse gate in float, same association as Patch.cpp:247
-        const float ea = __fadd_rn(__fadd_rn(ex, __fmul_rn(__fmul_rn(y_2_coeff, dja), dja)), __fmul_rn(__fmul_rn(yx_coeff, fdi), dja));
-        const float eb = __fadd_rn(__fadd_rn(ex, __fmul_rn(__fmul_rn(y_2_coeff, djb), djb)), __fmul_rn(__fmul_rn(yx_coeff, fdi), djb));
-        va = (ea <= sigma_2);
-        vb = hasB && (eb <= sigma_2);
+  if (any && Mstar > kNone) {
+    // guard band: two float ulps at |M*| plus the bound on |reference - ncc*|
+    const float fm = fabsf((float)Mstar);
+    const double ulp = (double)(nextafterf(fm, 3.0e38f) - fm);
+    const double thr = Mstar - (2.0 * ulp + 4.0e-12);
+    const int ncand = cw * ch;
+    for (int c = tid; c < ncand; c += MATCH_THREADS) {
+      if (score[c] >= thr) {
+        const int slot = atomicAdd(&red_k[10], 1);
+        if (slot < MATCH_LIST) list[slot] = c;
       }
-      if (!va && !vb) continue;
-      const int* sa = sat + jv * sst + iu;
-      const int suma = sa[w * sst + w] - sa[w] - sa[w * sst] + sa[0];
-      const int sumb = hasB ? sa[(w + 1) * sst + w] - sa[sst + w] - sa[(w + 1) * sst] + sa[sst] : 0;
-      const double m2a = __ddiv_rn((double)suma, dw2);
-      const double m2b = __ddiv_rn((double)sumb, dw2);
-      double n2a = 0, ca = 0, n2b = 0, cb = 0;
-      const double* wr = wind + jv * wsd + iu;
-      {  // window row 0: candidate A only
-        const double* t = d1;
-#pragma unroll 4
-        for (int x = 0; x < w; ++x) {
-          const double da = __dsub_rn(wr[x], m2a);
-          n2a = __dadd_rn(n2a, __dmul_rn(da, da));
-          ca = __dadd_rn(ca, __dmul_rn(t[x], da));
-        }
-      }
-      for (int r = 1; r < w; ++r) {  // rows shared by A (template row r) and B (template row r-1)
-        const double* row = wr + r * wsd;
-        const double* ta = d1 + r * w;
-        const double* tb = ta - w;
-#pragma unroll 4
-        for (int x = 0; x < w; ++x) {
-          const double pv = row[x];
-          const double da = __dsub_rn(pv, m2a);
-          n2a = __dadd_rn(n2a, __dmul_rn(da, da));
-          ca = __dadd_rn(ca, __dmul_rn(ta[x], da));
-          const double db = __dsub_rn(pv, m2b);
-          n2b = __dadd_rn(n2b, __dmul_rn(db, db));
-          cb = __dadd_rn(cb, __dmul_rn(tb[x], db));
-        }
-      }
-      {  // window row w: candidate B only (the spare row keeps the read in bounds when B is absent)
-        const double* row = wr + w * wsd;
-        const double* tb = d1 + (w - 1) * w;
-#pragma unroll 4
-        for (int x = 0; x < w; ++x) {
-          const double db = __dsub_rn(row[x], m2b);
-          n2b = __dadd_rn(n2b, __dmul_rn(db, db));
-          cb = __dadd_rn(cb, __dmul_rn(tb[x], db));
-        }
-      }
-      if (va) {
-        const float sc = (float)__ddiv_rn(ca, __dsqrt_rn(__dmul_rn(n2a, n1)));
-        const int key = (i - i0) * nv + (ja - j0);  // position in the reference's scan order
-        if (sc > best || (sc == best && key < bestkey)) { best = sc; bestkey = key; }
-      }
-      if (vb) {
-        const float sc = (float)__ddiv_rn(cb, __dsqrt_rn(__dmul_rn(n2b, n1)));
-        const int key = (i - i0) * nv + (ja + 1 - j0);
-        if (sc > best || (sc == best && key < bestkey)) { best = sc; bestkey = key; }
-      }
+    }
+    __syncthreads();
+    const int nlist = red_k[10];
+    const bool overflow = nlist > MATCH_LIST;
+    const int nwork = overflow ? ncand : nlist;
+    for (int q = tid; q < nwork; q += MATCH_THREADS) {
+      const int c = overflow ? q : list[q];
+      if (overflow && !(score[c] > kNone)) continue;
+      const int jv = c / cw, iu = c - jv * cw;
+      const int P = (int)H1[c];
+      const float sc = match_exact_score(tb, win, wsb, jv * wsb + iu, w, m1, n1, P);
+      const int key = (ilo + iu - i0) * nv + (jlo + jv - j0);  // position in the reference's scan order (u outer, v inner)
+      if (sc > best || (sc == best && key < bestkey)) { best = sc; bestkey = key; }
     }
   }
   // --- arg-max: higher score wins, ties go to the earlier key (strict '>' in a sequential scan) ---

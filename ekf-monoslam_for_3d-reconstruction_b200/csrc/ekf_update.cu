@@ -178,38 +178,39 @@ __global__ void __launch_bounds__(EKF_UB) k_blk_S(const double* __restrict__ W, 
 // y = Linv nu.  Outputs Linv (row-major, zero above the diagonal) and y.
 // ------------------------------------------------------------------------------------------------
 #include "ekf_factor.cuh"
-#define FACT_LD (EKF_UB + 1)
 __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __restrict__ Sb, const double* __restrict__ nu,
-                                                             double* __restrict__ Linv, double* __restrict__ yout, DevCtl* ctl) {
+                                                             double* __restrict__ Lout, double* __restrict__ Dblk,
+                                                             double* __restrict__ yout, DevCtl* ctl) {
   extern __shared__ __align__(16) double fsm[];
-  cta_factor<EKF_UB>(fsm, Sb, EKF_UB, nu, Linv, EKF_UB, yout, &ctl->chol_fail);
+  cta_chol22<EKF_UB>(fsm, Sb, EKF_UB, nu, Lout, EKF_UB, Dblk, 32, yout, &ctl->chol_fail);
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4c: V_b = W_b Linv^T in place on the fp64 tensor pipe (DMMA.8x8x4) and delta += V_b y.
-// One CTA = 32 rows x 128 columns, K <= 128 (Linv is lower triangular: column tile c0 only needs
-// k < c0 + 8).  8 warps, warp w owns column tiles 2w, 2w+1 for all four 8-row tiles.
+// K4c: V_b = W_b L^-T in place (blocked triangular solve on the fp64 tensor pipe, DMMA.8x8x4) and
+// delta += V_b y.  One CTA = 32 rows; each of its 4 warps owns one 8-row tile for the whole solve
+// (warp_trsm_tile, ekf_factor.cuh), so there is no block barrier after the operands are staged.
 // ------------------------------------------------------------------------------------------------
 #define VT_ROWS 32
-#define VT_THREADS 256
+#define VT_THREADS 128
 #define VT_LD (EKF_UB + 4)
-__device__ __forceinline__ void dmma884u(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(d0), "+d"(d1)
-               : "d"(a), "d"(b));
-}
-__global__ void __launch_bounds__(VT_THREADS) k_blk_V(double* __restrict__ W, int n, const double* __restrict__ Linvg,
-                                                      const double* __restrict__ yg, double* __restrict__ delta) {
+#define VT_LDD 36
+__global__ void __launch_bounds__(VT_THREADS) k_blk_V(double* __restrict__ W, int n, const double* __restrict__ Lg,
+                                                      const double* __restrict__ Dg, const double* __restrict__ yg,
+                                                      double* __restrict__ delta) {
   extern __shared__ __align__(16) double vsm[];
-  double* Ls = vsm;                          // [EKF_UB][VT_LD]  Linv
-  double* Ws = Ls + EKF_UB * VT_LD;          // [VT_ROWS][VT_LD] W rows, then V rows
+  double* Ls = vsm;                          // [EKF_UB][VT_LD]  L (lower)
+  double* Ds = Ls + EKF_UB * VT_LD;          // [EKF_UB / 32][32][VT_LDD] inverses of the diagonal blocks
+  double* Ws = Ds + (EKF_UB / 32) * 32 * VT_LDD;  // [VT_ROWS][VT_LD] W rows, then V rows
   double* ys = Ws + VT_ROWS * VT_LD;         // [EKF_UB]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t4 = lane & 3;
   const int row0 = blockIdx.x * VT_ROWS;
   for (int e = tid; e < EKF_UB * EKF_UB / 2; e += VT_THREADS) {
     const int r = e >> 6, c = (e & 63) * 2;
-    *reinterpret_cast<double2*>(Ls + r * VT_LD + c) = *reinterpret_cast<const double2*>(Linvg + r * EKF_UB + c);
+    *reinterpret_cast<double2*>(Ls + r * VT_LD + c) = *reinterpret_cast<const double2*>(Lg + r * EKF_UB + c);
+  }
+  for (int e = tid; e < (EKF_UB / 32) * 32 * 16; e += VT_THREADS) {
+    const int r = e >> 4, c = (e & 15) * 2;   // r = block * 32 + row
+    *reinterpret_cast<double2*>(Ds + r * VT_LDD + c) = *reinterpret_cast<const double2*>(Dg + r * 32 + c);
   }
   for (int e = tid; e < VT_ROWS * EKF_UB / 2; e += VT_THREADS) {
     const int r = e >> 6, c = (e & 63) * 2;
@@ -219,43 +220,16 @@ __global__ void __launch_bounds__(VT_THREADS) k_blk_V(double* __restrict__ W, in
   }
   for (int e = tid; e < EKF_UB; e += VT_THREADS) ys[e] = yg[e];
   __syncthreads();
-  double acc[4][2][2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 2; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-  const int c0 = warp * 16;                  // first column of this warp's two tiles
-  const int kmax = c0 + 16;                  // Linv[c][k] = 0 for k > c
-  for (int k = 0; k < kmax; k += 4) {
-    double af[4], bf[2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) af[i] = Ws[(i * 8 + g) * VT_LD + k + t4];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) bf[j] = Ls[(c0 + j * 8 + g) * VT_LD + k + t4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) dmma884u(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-  }
-  __syncthreads();  // everyone is done reading W rows from Ws
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-      *reinterpret_cast<double2*>(Ws + (i * 8 + g) * VT_LD + c0 + j * 8 + 2 * t4) = make_double2(acc[i][j][0], acc[i][j][1]);
+  double part = warp_trsm_tile<EKF_UB>(Ws + (size_t)warp * 8 * VT_LD, VT_LD, Ls, VT_LD, Ds, VT_LDD, ys);
+  part += __shfl_xor_sync(0xffffffffu, part, 1);
+  part += __shfl_xor_sync(0xffffffffu, part, 2);
+  const int i = row0 + warp * 8 + (lane >> 2);
+  if ((lane & 3) == 0 && i < n) delta[i] += part;
   __syncthreads();
   for (int e = tid; e < VT_ROWS * EKF_UB / 2; e += VT_THREADS) {
     const int r = e >> 6, c = (e & 63) * 2;
     if (row0 + r < n)
       *reinterpret_cast<double2*>(W + (size_t)(row0 + r) * EKF_UB + c) = *reinterpret_cast<const double2*>(Ws + r * VT_LD + c);
-  }
-  // delta += V y: warp w handles rows 4w .. 4w+3
-  for (int rr = 0; rr < 4; ++rr) {
-    const int r = warp * 4 + rr;
-    double part = 0;
-    for (int c = lane; c < EKF_UB; c += 32) part += Ws[r * VT_LD + c] * ys[c];
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if (lane == 0 && row0 + r < n) delta[row0 + r] += part;
   }
 }
 
@@ -296,8 +270,8 @@ __global__ void __launch_bounds__(256) k_bookkeeping(const double* __restrict__ 
 }
 
 // ---- launch wrappers ---------------------------------------------------------------------------
-static const size_t kFactSmem = (size_t)cta_factor_smem_doubles<EKF_UB>() * sizeof(double);
-static const size_t kVSmem = (size_t)(EKF_UB * VT_LD + VT_ROWS * VT_LD + EKF_UB) * sizeof(double);
+static const size_t kFactSmem = (size_t)cta_chol22_smem_doubles<EKF_UB>() * sizeof(double);
+static const size_t kVSmem = (size_t)(EKF_UB * VT_LD + (EKF_UB / 32) * 32 * VT_LDD + VT_ROWS * VT_LD + EKF_UB) * sizeof(double);
 
 int update_kernels_init() {
   cudaError_t e = cudaFuncSetAttribute(k_blk_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFactSmem);
@@ -323,13 +297,14 @@ void launch_blk_gather(cudaStream_t st, const double* Sigma, int ld, int n, Feat
   *launches += 1;
 }
 void launch_blk_factor(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const double* nu, const DevCfg& cfg,
-                       double* Sb, double* Linv, double* yb, DevCtl* ctl, long long* launches) {
+                       double* Sb, double* Lb, double* Dblk, double* yb, DevCtl* ctl, long long* launches) {
   k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(W, ft, f0, cnt, cfg.sigma_pixel_2, Sb);
-  k_blk_factor<<<1, FACT_THREADS, kFactSmem, st>>>(Sb, nu, Linv, yb, ctl);
+  k_blk_factor<<<1, FACT_THREADS, kFactSmem, st>>>(Sb, nu, Lb, Dblk, yb, ctl);
   *launches += 2;
 }
-void launch_blk_V(cudaStream_t st, double* W, int n, const double* Linv, const double* yb, double* delta, long long* launches) {
-  k_blk_V<<<(n + VT_ROWS - 1) / VT_ROWS, VT_THREADS, kVSmem, st>>>(W, n, Linv, yb, delta);
+void launch_blk_V(cudaStream_t st, double* W, int n, const double* Lb, const double* Dblk, const double* yb, double* delta,
+                  long long* launches) {
+  k_blk_V<<<(n + VT_ROWS - 1) / VT_ROWS, VT_THREADS, kVSmem, st>>>(W, n, Lb, Dblk, yb, delta);
   *launches += 1;
 }
 void launch_apply_delta(cudaStream_t st, double* mu, const double* delta, int n, long long* launches) {

@@ -1,28 +1,24 @@
-"""Top source lines / SASS instructions by warp-stall samples for one launch of an .ncu-rep.
-usage: ncu_source_hot.py rep launch_index [topn] [cuda|sass]"""
-import csv, subprocess, sys
+"""Top source lines by warp-stall samples / executed instructions for one launch of an .ncu-rep.
+usage: ncu_source_hot.py rep launch_index [topn]"""
+import csv, os, subprocess, sys
 rep, kid = sys.argv[1], sys.argv[2]
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 25
-view = sys.argv[4] if len(sys.argv) > 4 else "cuda"
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", view, "--launch-skip", kid,
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--launch-skip", kid,
                       "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-hdr = None
-for i, r in enumerate(rows):
-    if "Source" in r and "# Samples" in r:
-        hdr = r; start = i + 1; break
-if hdr is None:
-    print(out[:1500]); sys.exit(1)
-si, sa, ie = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
-first = hdr[0]
-tot = 0; items = []
-for r in rows[start:]:
-    if len(r) <= sa: continue
-    try: v = float(r[sa])
+cur = "?"; fn = ""; items = []; hdr = None
+for r in rows:
+    if not r: continue
+    if r[0] == "File Path": cur = os.path.basename(r[1]); continue
+    if r[0] == "Function Name": fn = r[1]; continue
+    if r[0] == "Line No": hdr = r; continue
+    if hdr is None or len(r) < 8 or r[2] != "-": continue
+    try: s = float(r[hdr.index("# Samples")]); n = float(r[hdr.index("Instructions Executed")])
     except Exception: continue
-    tot += v
-    items.append((v, r[0], r[si].strip(), r[ie]))
-items.sort(reverse=True)
-print(rows[0][1] if len(rows[0]) > 1 else "", "| total samples", tot)
-for v, l, s, n in items[:topn]:
-    print(f"{v:7.0f} {100*v/max(tot,1):5.1f}% inst={n:>9s} {first}={l[-6:]:>6s} {s[:120]}")
+    sb = {k: r[hdr.index(k)] for k in ("stall_barrier", "stall_long_sb", "stall_short_sb", "stall_math", "stall_mio", "stall_wait", "stall_lg") if k in hdr}
+    items.append((s, n, cur, r[0], r[1].strip(), sb))
+tot = sum(i[0] for i in items); toti = sum(i[1] for i in items)
+print(fn[:60], "| samples", tot, "| warp instr", toti)
+for s, n, f, l, src, sb in sorted(items, reverse=True)[:topn]:
+    top = sorted(((float(v), k[6:]) for k, v in sb.items()), reverse=True)[:2]
+    print(f"{100*s/max(tot,1):5.1f}% smp {100*n/max(toti,1):5.1f}% ins {f}:{l:>4s} {src[:90]}  [{', '.join(f'{k} {int(v)}' for v, k in top)}]")
