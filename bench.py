@@ -391,6 +391,7 @@ def run_match(args):
             orc.build()
             nf = 2
             t0 = time.perf_counter()
+            orc.lib(omp=True).orc_set_num_threads(os.cpu_count() or 1)
             orc.match_batch(d["frames"][:nf], d["templates"][:nf * M], d["h"][:nf * M], d["S"][:nf * M], sigma_size=3.0, omp=True)
             dt = time.perf_counter() - t0
             out["cpu_baseline"] = {"value": round(nf * M / dt, 1), "unit": UNIT_MATCH, "cores": orc.lib(omp=True).orc_num_threads(), "kind": "port",
@@ -605,6 +606,7 @@ def cpu_baseline(pkg, workload, budget_s=30.0):
     import orc
     orc.build()
     L = orc.lib(omp=True)
+    L.orc_set_num_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1; the baseline uses every host core
     cores = L.orc_num_threads()
     nfeat = WORKLOADS[workload][0]
     o, scene = _oracle_seeded(pkg, orc, workload, 4)
@@ -632,6 +634,7 @@ def run_reference(args):
     import orc
     orc.build()
     L = orc.lib(omp=True)
+    L.orc_set_num_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core
     cores = L.orc_num_threads()
     nfeat = WORKLOADS[args.workload][0]
     K, Wm = args.steps, args.warmup
@@ -667,6 +670,9 @@ def run_reference(args):
 
 
 def main():
+    # keep stdout to the single JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

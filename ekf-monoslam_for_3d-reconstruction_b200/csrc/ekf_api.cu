@@ -100,6 +100,7 @@ int ekf_destroy(ekf_handle* h) {
   cudaFree(h->Lb); cudaFree(h->Dinv); cudaFree(h->Dblk); cudaFree(h->yb); cudaFree(h->delta); cudaFree(h->mu_i); cudaFree(h->cand);
   cudaFree(h->map_dev); cudaFree(h->keep_dev); cudaFree(h->newpos_dev); cudaFree(h->ctl); cudaFree(h->frame);
   cudaFree(h->picks_dev); cudaFree(h->out_dev); cudaFree(h->gemm_counters);
+  cudaFree(h->xyz_flag); cudaFree(h->xyz_rmap); cudaFree(h->xyz_pos); cudaFree(h->xyz_coding); cudaFree(h->xyz_y); cudaFree(h->xyz_J);
   if (h->out_host) cudaFreeHost(h->out_host);
   free_feattab(h->ft); free_feattab(h->ftB);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -114,7 +115,6 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
   if (cfg->kernel_size < 100000) return EKF_ERR_UNSUPPORTED;   // motion-blur templates (libblur.cpp)
   if (cfg->scale != 1) return EKF_ERR_UNSUPPORTED;             // cv::resize in captureNewFrame
   if (cfg->forsePlane != 0) return EKF_ERR_UNSUPPORTED;        // plane pseudo-measurement (V:1250-1263)
-  if (cfg->xyz_conversion != 0) return EKF_ERR_UNSUPPORTED;    // convert2XYZ_ifLinear (V:741-780)
   if (cfg->window_size < 3 || cfg->window_size > 31) return EKF_ERR_UNSUPPORTED;
   if (cfg->search_clamp > 20 || cfg->search_clamp < 0) return EKF_ERR_UNSUPPORTED;
   int ndev = 0;
@@ -144,6 +144,8 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
   TRY(dalloc(&h->Dinv, EKF_UB * EKF_UB)) TRY(dalloc(&h->Dblk, EKF_UB * 32)) TRY(dalloc(&h->yb, EKF_UB)) TRY(dalloc(&h->delta, h->ld)) TRY(dalloc(&h->mu_i, h->ld))
   TRY(dalloc(&h->cand, h->Ncap)) TRY(dalloc(&h->map_dev, h->ncap)) TRY(dalloc(&h->keep_dev, h->Ncap))
   TRY(dalloc(&h->newpos_dev, h->Ncap)) TRY(dalloc(&h->ctl, 1)) TRY(dalloc(&h->gemm_counters, 2))
+  TRY(dalloc(&h->xyz_flag, h->Ncap)) TRY(dalloc(&h->xyz_rmap, 2 * (size_t)h->ncap)) TRY(dalloc(&h->xyz_pos, h->Ncap))
+  TRY(dalloc(&h->xyz_coding, h->Ncap)) TRY(dalloc(&h->xyz_y, 3 * (size_t)h->Ncap)) TRY(dalloc(&h->xyz_J, 18 * (size_t)h->Ncap))
   TRY(alloc_feattab(h->ft, h->Ncap, w2)) TRY(alloc_feattab(h->ftB, h->Ncap, w2))
   h->out_bytes = sizeof(double) * 210 + sizeof(int) * (16 + 3 * (size_t)h->Ncap);
   TRY(cudaMalloc((void**)&h->out_dev, h->out_bytes)) TRY(cudaMallocHost((void**)&h->out_host, h->out_bytes))
@@ -344,6 +346,47 @@ static int remove_features(ekf_handle* h, const std::vector<int>& victims) {
   return EKF_OK;
 }
 
+// convert2XYZ_ifLinear (only >= 0) / convert2XYZ_ifLinearAll (only < 0), V:741-780
+static int convert_xyz(ekf_handle* h, int only) {
+  if (h->N == 0) return EKF_OK;
+  cudaStream_t st = h->stream;
+  launch_xyz_decide(st, h->Sigma, h->ld, h->mu, h->ft, h->N, h->dcfg, only, h->xyz_flag, h->xyz_y, h->xyz_J, &h->launches);
+  EKF_CUDA_CHECK(cudaGetLastError());
+  std::vector<int> flag(h->N);
+  EKF_CUDA_CHECK(cudaMemcpyAsync(flag.data(), h->xyz_flag, sizeof(int) * h->N, cudaMemcpyDeviceToHost, st));
+  EKF_CUDA_CHECK(cudaStreamSynchronize(st));
+  int nconv = 0;
+  for (int f = 0; f < h->N; ++f) nconv += flag[f] ? 1 : 0;
+  if (nconv == 0) return EKF_OK;
+  std::vector<int> rmap, npos(h->N), ncod(h->N);
+  for (int i = 0; i < EKF_CAM; ++i) { rmap.push_back(i); rmap.push_back(-1); }
+  for (int f = 0; f < h->N; ++f) {
+    npos[f] = (int)rmap.size() / 2;
+    if (flag[f]) {
+      for (int x = 0; x < 3; ++x) { rmap.push_back(h->m_pos[f]); rmap.push_back(4 * f + x); }
+      ncod[f] = 1;
+    } else {
+      const int fs = h->m_coding[f] ? 3 : 6;
+      for (int c = 0; c < fs; ++c) { rmap.push_back(h->m_pos[f] + c); rmap.push_back(-1); }
+      ncod[f] = h->m_coding[f];
+    }
+  }
+  const int n2 = (int)rmap.size() / 2;
+  EKF_CUDA_CHECK(cudaMemcpyAsync(h->xyz_rmap, rmap.data(), sizeof(int) * rmap.size(), cudaMemcpyHostToDevice, st));
+  EKF_CUDA_CHECK(cudaMemcpyAsync(h->xyz_pos, npos.data(), sizeof(int) * h->N, cudaMemcpyHostToDevice, st));
+  EKF_CUDA_CHECK(cudaMemcpyAsync(h->xyz_coding, ncod.data(), sizeof(int) * h->N, cudaMemcpyHostToDevice, st));
+  launch_xyz_apply(st, h->Sigma, h->SigmaB, h->ld, h->mu, h->muB, n2, h->xyz_rmap, h->xyz_J, h->xyz_y, h->ft, h->N, h->xyz_pos,
+                   h->xyz_coding, &h->launches);
+  EKF_CUDA_CHECK(cudaGetLastError());
+  EKF_CUDA_CHECK(cudaStreamSynchronize(st));  // host vectors above go out of scope
+  std::swap(h->Sigma, h->SigmaB);
+  std::swap(h->mu, h->muB);
+  h->n = n2;
+  h->m_pos = npos; h->m_coding = ncod;
+  h->cache_ok = false;
+  return EKF_OK;
+}
+
 // One stacked update over `cnt` selected features (ft.sel), block by block (see ekf_update.cu).
 static int stacked_update(ekf_handle* h, int cnt) {
   if (cnt <= 0) return 0;
@@ -446,6 +489,10 @@ int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
     }
     h->stats.topup_request = h->cfg.min_features - nvis;  // findNewFeatures(...) is the caller's job
   }
+  if (h->cfg.xyz_conversion) {  // V:1317
+    rc = convert_xyz(h, -1);
+    if (rc) return rc;
+  }
   h->stats.kernel_launches = h->launches;
   h->predicted = false;
   return EKF_OK;
@@ -500,8 +547,17 @@ int ekf_remove_feature(ekf_handle* h, int index) {
   return remove_features(h, std::vector<int>{index});
 }
 
-int ekf_convert2xyz_if_linear(ekf_handle* h, int) { return ekf_fail(h, EKF_ERR_UNSUPPORTED, "convert2XYZ_ifLinear: SURVEY.md 8(f) next row"); }
-int ekf_convert2xyz_if_linear_all(ekf_handle* h) { return ekf_fail(h, EKF_ERR_UNSUPPORTED, "convert2XYZ_ifLinearAll: SURVEY.md 8(f) next row"); }
+int ekf_convert2xyz_if_linear(ekf_handle* h, int index) {
+  if (!h || index < 0 || index >= h->N) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  if (h->m_coding[index]) return EKF_OK;
+  return convert_xyz(h, index);
+}
+int ekf_convert2xyz_if_linear_all(ekf_handle* h) {
+  if (!h) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  return convert_xyz(h, -1);
+}
 
 int ekf_num_features(const ekf_handle* h) { return h ? h->N : EKF_ERR_ARG; }
 int ekf_state_dim(const ekf_handle* h) { return h ? h->n : EKF_ERR_ARG; }

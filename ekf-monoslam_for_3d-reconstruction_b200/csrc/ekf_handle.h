@@ -20,6 +20,8 @@ struct ekf_handle {
   int Ncap = 0, ncap = 0, ld = 0, N = 0, n = EKF_CAM;
   double *mu = nullptr, *muB = nullptr, *Sigma = nullptr, *SigmaB = nullptr;
   double *W = nullptr, *nu = nullptr, *Lb = nullptr, *Dinv = nullptr, *Dblk = nullptr, *yb = nullptr, *delta = nullptr, *mu_i = nullptr;
+  int *xyz_flag = nullptr, *xyz_rmap = nullptr, *xyz_pos = nullptr, *xyz_coding = nullptr;
+  double *xyz_y = nullptr, *xyz_J = nullptr;
   int *cand = nullptr, *map_dev = nullptr, *keep_dev = nullptr, *newpos_dev = nullptr, *gemm_counters = nullptr;
   DevCtl* ctl = nullptr;
   FeatTab ft{}, ftB{};

@@ -15,6 +15,11 @@ void launch_gather_state(cudaStream_t st, const double* Ssrc, double* Sdst, int 
                          int n2, const int* map, long long* launches);
 void launch_gather_features(cudaStream_t st, FeatTab src, FeatTab dst, int N2, const int* keep, const int* newpos, int w2,
                             long long* launches);
+void launch_xyz_decide(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, const DevCfg& cfg, int only,
+                       int* flag, double* y, double* J, long long* launches);
+void launch_xyz_apply(cudaStream_t st, const double* Ssrc, double* Sdst, int ld, const double* musrc, double* mudst, int n2,
+                      const int* rmap, const double* J, const double* y, FeatTab ft, int N, const int* pos, const int* coding,
+                      long long* launches);
 // ekf_match.cu
 void launch_match_filter(cudaStream_t st, FeatTab ft, int N, FrameView fr, const DevCfg& cfg, long long* launches);
 void launch_match_filter_batch(cudaStream_t st, FeatTab base, int Ncap, const int* Nper, int B, FrameView fr, const DevCfg& cfg,

@@ -10,10 +10,9 @@
 // by < 1e-13 (121 roundings of 1e-16 relative).  Rounding to float is monotonic, so only candidates
 // whose ncc* lies within two float ulps (+ that error bound) of the largest ncc* can be, or tie
 // with, the reference's float maximum.  Hence:
-//   fast pass : u8 search window (<= 72 x 72), its summed-area tables of p and p^2 (exact ints) and the
-//               template packed 4 bytes per word live in shared memory; each thread scores 4
-//               horizontally adjacent candidates at a time with DP4A (u8 x u8 dot products) on
-//               funnel-shifted window words -> Stp; P, Spp from the tables; ncc* in double.
+//   fast pass : the u8 search window (<= 72 x 72) and the template packed 4 bytes per word live in shared
+//               memory; each thread scores 4 horizontally adjacent candidates at a time with DP4A
+//               (u8 x u8 dot products) on funnel-shifted window words -> Stp, P, Spp; ncc* in double.
 //   exact pass: the handful of candidates inside the guard band (normally one) are re-scored with the
 //               reference's own operation sequence (__dadd_rn/__dmul_rn, row-major, never contracted)
 //               and compared as floats with the reference's first-wins tie-break.
@@ -45,7 +44,7 @@ struct MatchSmem {
   int wsb;       // window row stride in bytes (multiple of 4, >= side + 8)
   int tw;        // template words per row
   int ncmax;     // max candidates = (2 cl + 1)^2
-  size_t off_tpk, off_tb, off_win, off_sat1, off_sat2, off_score, off_list, off_red, total;
+  size_t off_tpk, off_tb, off_win, off_h1, off_h2, off_b1, off_b2, off_score, off_list, off_red, total;
 };
 __host__ __device__ inline MatchSmem match_smem_plan(int w, int cl) {
   MatchSmem p;
@@ -59,8 +58,11 @@ __host__ __device__ inline MatchSmem match_smem_plan(int w, int cl) {
   o = (o + 15) & ~(size_t)15;
   p.off_win = o; o += (size_t)(p.side + 1) * p.wsb;                           // u8 window (+1 spare row)
   o = (o + 15) & ~(size_t)15;
-  p.off_sat1 = o; o += (size_t)(p.side + 1) * (p.side + 1) * 4;               // box sums of p   (horizontal, then w x w)
-  p.off_sat2 = o; o += (size_t)(p.side + 1) * (p.side + 1) * 4;               // box sums of p^2
+  const size_t nh = (size_t)p.side * (2 * cl + 1);                            // horizontal sums: window rows x candidate columns
+  p.off_h1 = o; o += ((nh * 2 + 15) & ~(size_t)15);                           // u16: sum of w pixels
+  p.off_h2 = o; o += nh * 4;                                                  // u32: sum of w squares
+  p.off_b1 = o; o += (size_t)p.ncmax * 4;                                     // P  = sum p   over w x w, per candidate
+  p.off_b2 = o; o += (size_t)p.ncmax * 4;                                     // PP = sum p^2 over w x w, per candidate
   o = (o + 7) & ~(size_t)7;
   p.off_score = o; o += (size_t)p.ncmax * 8;                                  // ncc* per candidate
   p.off_list = o; o += (size_t)MATCH_LIST * 4;                                // guard-band candidate keys
@@ -70,12 +72,12 @@ __host__ __device__ inline MatchSmem match_smem_plan(int w, int cl) {
   return p;
 }
 
-// The reference's computeCorrelation for one candidate (window ROI at byte offset `roi`), exact
-// operation order; n1 = sum (t - m1)^2 is hoisted (identical for every candidate).
+// The reference's computeCorrelation for one candidate (window ROI at byte offset `roi`): exact
+// operation order, three independent accumulation chains (n1, n2, corr) as in Patch.cpp:316-326.
 __device__ __forceinline__ float match_exact_score(const uint8_t* tmpl, const uint8_t* win, int wsb, int roi, int w, double m1,
-                                                   double n1, int P) {
+                                                   int P) {
   const double m2 = __ddiv_rn((double)P, (double)(w * w));
-  double n2 = 0, corr = 0;
+  double n1 = 0, n2 = 0, corr = 0;
   for (int r = 0; r < w; ++r) {
     const uint8_t* wr = win + roi + r * wsb;
     const uint8_t* tr = tmpl + r * w;
@@ -83,6 +85,7 @@ __device__ __forceinline__ float match_exact_score(const uint8_t* tmpl, const ui
     for (int x = 0; x < w; ++x) {
       const double da = __dsub_rn((double)(float)tr[x], m1);
       const double db = __dsub_rn((double)(float)wr[x], m2);
+      n1 = __dadd_rn(n1, __dmul_rn(da, da));
       n2 = __dadd_rn(n2, __dmul_rn(db, db));
       corr = __dadd_rn(corr, __dmul_rn(da, db));
     }
@@ -155,8 +158,10 @@ __device__ MatchResult match_one(const MatchJob& jb, int w, float sigma_size, fl
   unsigned* tpk = reinterpret_cast<unsigned*>(smem_raw + pl.off_tpk);
   uint8_t* tb = smem_raw + pl.off_tb;
   uint8_t* win = smem_raw + pl.off_win;
-  unsigned* sat1 = reinterpret_cast<unsigned*>(smem_raw + pl.off_sat1);
-  unsigned* sat2 = reinterpret_cast<unsigned*>(smem_raw + pl.off_sat2);
+  unsigned short* Hh1 = reinterpret_cast<unsigned short*>(smem_raw + pl.off_h1);
+  unsigned* Hh2 = reinterpret_cast<unsigned*>(smem_raw + pl.off_h2);
+  unsigned* H1 = reinterpret_cast<unsigned*>(smem_raw + pl.off_b1);
+  unsigned* H2 = reinterpret_cast<unsigned*>(smem_raw + pl.off_b2);
   double* score = reinterpret_cast<double*>(smem_raw + pl.off_score);
   int* list = reinterpret_cast<int*>(smem_raw + pl.off_list);
   double* red_d = reinterpret_cast<double*>(smem_raw + pl.off_red);   // [0..7] warp maxima, [8] n1, [9] M*
@@ -186,104 +191,116 @@ __device__ MatchResult match_one(const MatchJob& jb, int w, float sigma_size, fl
   // --- stage the window as bytes; columns past ww and the spare row are zero ---
   if (any) {
     const int x0 = ilo - half, y0 = jlo - half;
-    for (int e = tid; e < (wh + 1) * wsb; e += MATCH_THREADS) {
-      const int yy = e / wsb, xx = e - yy * wsb;
-      win[e] = (yy < wh && xx < ww) ? jb.frame[(size_t)(y0 + yy) * jb.fstride + x0 + xx] : (uint8_t)0;
+    for (int yy = tid / 32; yy <= wh; yy += MATCH_THREADS / 32) {
+      const uint8_t* src = jb.frame + (size_t)(y0 + yy) * jb.fstride + x0;
+      for (int xx = tid & 31; xx < wsb; xx += 32) win[yy * wsb + xx] = (yy < wh && xx < ww) ? src[xx] : (uint8_t)0;
     }
   }
   __syncthreads();
   const int T = red_k[8], TT = red_k[9];
   const double dn = (double)w2;
   const double m1 = __ddiv_rn((double)T, dn);
-  // --- w x w box sums of p and p^2 for every candidate (exact unsigned ints), separable: horizontal
-  //     sums H[y][iu] over w pixels, then vertical sums over w rows, written to B[jv][iu] ---
-  unsigned* H1 = sat1; unsigned* H2 = sat2;                 // [wh][cw]
-  if (tid == MATCH_THREADS - 1) {
-    // n1 = sum (s1 - m1)^2 sequentially in the reference order; overlaps the horizontal pass
-    double n1 = 0;
-#pragma unroll 11
-    for (int e = 0; e < w2; ++e) {
-      const double d = __dsub_rn((double)(float)tb[e], m1);
-      n1 = __dadd_rn(n1, __dmul_rn(d, d));
-    }
-    red_d[8] = n1;
-  } else if (any) {
-    for (int e = tid; e < wh * cw; e += MATCH_THREADS - 1) {
-      const int yy = e / cw, iu = e - yy * cw;
-      const uint8_t* pr = win + yy * wsb + iu;
-      unsigned r1 = 0, r2 = 0;
-      for (int x = 0; x < w; ++x) { const unsigned v = pr[x]; r1 += v; r2 += v * v; }
-      H1[e] = r1; H2[e] = r2;
+  // --- w x w box sums of p and p^2 for every candidate (exact ints), separable with sliding sums:
+  //     a thread produces 4 adjacent outputs from one w-term sum plus three add/subtract slides ---
+  if (any) {
+    const int gx = (cw + 3) >> 2;
+    // linear item index (row, group) advanced without a division per item
+    const int dq = MATCH_THREADS % gx, dy = MATCH_THREADS / gx;
+    for (int yy = tid / gx, gq = tid - (tid / gx) * gx; yy < wh; ) {
+      {
+        const uint8_t* pr = win + yy * wsb + 4 * gq;
+        unsigned r1 = 0, r2 = 0;
+        for (int x = 0; x < w; ++x) { const unsigned v = pr[x]; r1 += v; r2 += v * v; }
+        unsigned short* o1 = Hh1 + yy * cw + 4 * gq;
+        unsigned* o2 = Hh2 + yy * cw + 4 * gq;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          if (4 * gq + s < cw) { o1[s] = (unsigned short)r1; o2[s] = r2; }
+          const unsigned vin = pr[w + s], vout = pr[s];     // bytes past ww are zero, inside the padded row
+          r1 += vin - vout; r2 += vin * vin - vout * vout;
+        }
+      }
+      gq += dq; yy += dy;
+      if (gq >= gx) { gq -= gx; ++yy; }
     }
   }
   __syncthreads();
-  // vertical pass into registers, then (after a barrier) back over the same arrays as B[jv][iu]
-  {
-    unsigned b1[8], b2[8];   // ncand <= 1681 -> at most 7 candidates per thread
-    int cnt = 0;
-    for (int c = tid; c < cw * ch && cnt < 8; c += MATCH_THREADS, ++cnt) {
-      const int jv = c / cw, iu = c - jv * cw;
-      unsigned r1 = 0, r2 = 0;
-      for (int r = 0; r < w; ++r) { r1 += H1[(jv + r) * cw + iu]; r2 += H2[(jv + r) * cw + iu]; }
-      b1[cnt] = r1; b2[cnt] = r2;
+  if (any) {
+    const int gv = (ch + 3) >> 2;
+    const int di = MATCH_THREADS % cw, dg = MATCH_THREADS / cw;
+    for (int gq = tid / cw, iu = tid - (tid / cw) * cw; gq < gv; ) {
+      {
+        const int jv0 = 4 * gq;
+        unsigned r1 = 0, r2 = 0;
+        for (int r = 0; r < w; ++r) { r1 += Hh1[(jv0 + r) * cw + iu]; r2 += Hh2[(jv0 + r) * cw + iu]; }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          if (jv0 + s >= ch) break;
+          H1[(jv0 + s) * cw + iu] = r1; H2[(jv0 + s) * cw + iu] = r2;
+          if (jv0 + s + 1 < ch) {
+            r1 += (unsigned)Hh1[(jv0 + s + w) * cw + iu] - (unsigned)Hh1[(jv0 + s) * cw + iu];
+            r2 += Hh2[(jv0 + s + w) * cw + iu] - Hh2[(jv0 + s) * cw + iu];
+          }
+        }
+      }
+      iu += di; gq += dg;
+      if (iu >= cw) { iu -= cw; ++gq; }
     }
-    __syncthreads();
-    cnt = 0;
-    for (int c = tid; c < cw * ch && cnt < 8; c += MATCH_THREADS, ++cnt) { H1[c] = b1[cnt]; H2[c] = b2[cnt]; }
   }
   __syncthreads();
-  const double n1 = red_d[8];
   const double d1 = dn * (double)TT - (double)T * (double)T;   // exact (< 2^53)
 
   // --- fast pass: ncc* of every in-ellipse candidate ---
   const double kNone = -1.0e300;
   double lmax = kNone;
   if (any) {
-    const int gx = (cw + 3) >> 2, ngroups = gx * ch;
-    for (int gq = tid; gq < ngroups; gq += MATCH_THREADS) {
-      const int jv = gq / gx, iu4 = (gq - jv * gx) * 4;
+    const int gx = (cw + 3) >> 2;
+    const double rd1 = (d1 > 0.0) ? rsqrt(d1) : 0.0;
+    // group = 4 horizontally adjacent candidates; warps stride over candidate rows, lanes over groups
+    const int dq = MATCH_THREADS % gx, dy = MATCH_THREADS / gx;
+    for (int jv = tid / gx, gq = tid - (tid / gx) * gx; jv < ch; gq += dq, jv += dy, jv += (gq >= gx) ? 1 : 0, gq -= (gq >= gx) ? gx : 0) {
       const int ja = jlo + jv;
-      // ellipse gate in float, same association as Patch.cpp:247
-      bool valid[4];
-      bool anyv = false;
       const float dj = (float)(ja - vc);
       const float ey = __fmul_rn(__fmul_rn(y_2_coeff, dj), dj);
+      {
+        const int iu4 = gq * 4;
+        // ellipse gate in float, same association as Patch.cpp:247
+        bool valid[4];
+        bool anyv = false;
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const int iu = iu4 + s;
-        const float fdi = (float)(ilo + iu - uc);
-        const float e = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(x_2_coeff, fdi), fdi), ey), __fmul_rn(__fmul_rn(yx_coeff, fdi), dj));
-        valid[s] = (iu < cw) && (e <= sigma_2);
-        anyv |= valid[s];
-      }
-      if (!anyv) {
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-          if (iu4 + s < cw) score[jv * cw + iu4 + s] = kNone;
-        continue;
-      }
-      unsigned acc[4] = {0u, 0u, 0u, 0u};
-      if (w == 11) match_dots4<11>(win + jv * wsb + iu4, wsb, tpk, w, acc);   // the benchmark / synthetic-scene template size
-      else if (w == 21) match_dots4<21>(win + jv * wsb + iu4, wsb, tpk, w, acc);  // reference default (ConfigVSLAM.cpp:31)
-      else match_dots4<0>(win + jv * wsb + iu4, wsb, tpk, w, acc);
-#pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const int iu = iu4 + s;
-        if (iu >= cw) continue;
-        double v = kNone;
-        if (valid[s]) {
-          const unsigned P = H1[jv * cw + iu];
-          const unsigned PP = H2[jv * cw + iu];
-          const double d2 = dn * (double)PP - (double)P * (double)P;
-          if (d1 > 0.0 && d2 > 0.0) {
-            const double num = dn * (double)acc[s] - (double)T * (double)P;
-            v = num / sqrt(d1 * d2);
-            if (v > lmax) lmax = v;
-          } else {
-            v = kNone;  // flat template or flat window: 0/0 in the reference, never selected
-          }
+        for (int s = 0; s < 4; ++s) {
+          const int iu = iu4 + s;
+          const float fdi = (float)(ilo + iu - uc);
+          const float e = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(x_2_coeff, fdi), fdi), ey), __fmul_rn(__fmul_rn(yx_coeff, fdi), dj));
+          valid[s] = (iu < cw) && (e <= sigma_2);
+          anyv |= valid[s];
         }
-        score[jv * cw + iu] = v;
+        if (!anyv) {
+#pragma unroll
+          for (int s = 0; s < 4; ++s)
+            if (iu4 + s < cw) score[jv * cw + iu4 + s] = kNone;
+          continue;
+        }
+        unsigned acc[4] = {0u, 0u, 0u, 0u};
+        if (w == 11) match_dots4<11>(win + jv * wsb + iu4, wsb, tpk, w, acc);       // the benchmark / synthetic-scene template size
+        else if (w == 21) match_dots4<21>(win + jv * wsb + iu4, wsb, tpk, w, acc);  // reference default (ConfigVSLAM.cpp:31)
+        else match_dots4<0>(win + jv * wsb + iu4, wsb, tpk, w, acc);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const int iu = iu4 + s;
+          if (iu >= cw) continue;
+          double v = kNone;
+          if (valid[s]) {
+            const unsigned P = H1[jv * cw + iu], PP = H2[jv * cw + iu];
+            const double d2 = dn * (double)PP - (double)P * (double)P;   // exact (< 2^53)
+            if (d1 > 0.0 && d2 > 0.0) {
+              const double num = dn * (double)acc[s] - (double)T * (double)P;
+              v = (num * rd1) * rsqrt(d2);
+              if (v > lmax) lmax = v;
+            }  // else: flat template or flat window, 0/0 in the reference, never selected
+          }
+          score[jv * cw + iu] = v;
+        }
       }
     }
   }
@@ -304,7 +321,7 @@ __device__ MatchResult match_one(const MatchJob& jb, int w, float sigma_size, fl
     // guard band: two float ulps at |M*| plus the bound on |reference - ncc*|
     const float fm = fabsf((float)Mstar);
     const double ulp = (double)(nextafterf(fm, 3.0e38f) - fm);
-    const double thr = Mstar - (2.0 * ulp + 4.0e-12);
+    const double thr = Mstar - (2.0 * ulp + 4.0e-12);   // ncc* itself carries ~4e-16 (two rsqrt), far inside the bound
     const int ncand = cw * ch;
     for (int c = tid; c < ncand; c += MATCH_THREADS) {
       if (score[c] >= thr) {
@@ -321,7 +338,7 @@ __device__ MatchResult match_one(const MatchJob& jb, int w, float sigma_size, fl
       if (overflow && !(score[c] > kNone)) continue;
       const int jv = c / cw, iu = c - jv * cw;
       const int P = (int)H1[c];
-      const float sc = match_exact_score(tb, win, wsb, jv * wsb + iu, w, m1, n1, P);
+      const float sc = match_exact_score(tb, win, wsb, jv * wsb + iu, w, m1, P);
       const int key = (ilo + iu - i0) * nv + (jlo + jv - j0);  // position in the reference's scan order (u outer, v inner)
       if (sc > best || (sc == best && key < bestkey)) { best = sc; bestkey = key; }
     }

@@ -86,6 +86,14 @@ class VSlamFilter:
     def removeFeature(self, i):
         self._ck(self.L.ekf_remove_feature(self.h, int(i)))
 
+    def convert2XYZ_ifLinear(self, i):
+        """vslamRansac.cpp:741-772."""
+        self._ck(self.L.ekf_convert2xyz_if_linear(self.h, int(i)))
+
+    def convert2XYZ_ifLinearAll(self):
+        """vslamRansac.cpp:775-780."""
+        self._ck(self.L.ekf_convert2xyz_if_linear_all(self.h))
+
     # ---- accessors ---------------------------------------------------------------------------
     def numOfFeatures(self):
         return self.L.ekf_num_features(self.h)

@@ -129,6 +129,36 @@ def test_remove_feature_and_controls(gpu_pkg, orc):
     assert_tables_equal(g, o, ctx="update after remove"); assert_state_close(g, o, ctx="update after remove")
 
 
+def test_xyz_conversion_and_mixed_update(gpu_pkg, orc):
+    """convert2XYZ_ifLinear(All) (vslamRansac.cpp:741-780) and steps with mixed inverse-depth / XYZ
+    features (XYZ measurement branch :552-578, RANSAC quirk :1016, removal archive :394-404)."""
+    sc = _scene(gpu_pkg, n_features=20, n_frames=6, seed=23)
+    g, o = make_pair(gpu_pkg, orc, sc, xyz_conversion=1)
+    seed_features(g, sc); seed_features(o, sc)
+    mu, S = o.get_full()
+    for i in (1, 4, 9, 10, 19):
+        pos = 14 + 6 * i
+        S[pos + 5, :] *= 1e-3; S[:, pos + 5] *= 1e-3
+    for f in (g, o):
+        f.set_full(mu, S)
+    g.convert2XYZ_ifLinear(4); o.convert2XYZ_ifLinear(4)          # one feature
+    g.convert2XYZ_ifLinear(0); o.convert2XYZ_ifLinear(0)          # not linear enough: no-op
+    assert g.state_dim() == o.state_dim() == 14 + 6 * 20 - 3
+    assert_tables_equal(g, o, ctx="single conversion"); assert_state_close(g, o, ctx="single conversion")
+    g.convert2XYZ_ifLinearAll(); o.convert2XYZ_ifLinearAll()      # the remaining four at once
+    assert g.state_dim() == o.state_dim() == 14 + 6 * 20 - 3 * 5
+    assert [g.feature(i).coding for i in range(20)] == [o.feature(i).coding for i in range(20)]
+    assert_tables_equal(g, o, ctx="convert all"); assert_state_close(g, o, ctx="convert all")
+    for t in range(1, sc.n_frames):
+        m, Sg = o.get_full(); g.set_full(m, Sg)
+        img = sc.frame(t)
+        for f in (g, o):
+            f.captureNewFrame(img, sc.stamps[t]); f.predict(); f.update(sc.picks(t, 20))
+        assert_tables_equal(g, o, ctx=f"mixed frame {t}"); assert_state_close(g, o, ctx=f"mixed frame {t}")
+    g.removeFeature(4); o.removeFeature(4)                        # an XYZ feature
+    assert_tables_equal(g, o, ctx="remove xyz"); assert_state_close(g, o, ctx="remove xyz")
+
+
 def test_unsupported_configs_fail_loudly(gpu_pkg):
     for over in (dict(kernel_size=3), dict(scale=2), dict(forsePlane=1)):
         cfg = gpu_pkg.default_config(xyz_conversion=0, **over)

@@ -13,18 +13,15 @@ pytestmark = pytest.mark.gpu
 CASES, run_case = load_cases()
 
 
-@pytest.mark.parametrize("name", sorted(n for n in CASES if not CASES[n].get("xyz")))
+@pytest.mark.parametrize("name", sorted(CASES))
 def test_cuda_path_reproduces_reference_fixture(gpu_pkg, name):
+    """Every fixture, including the XYZ-conversion case, with the reference's own configuration
+    (convert2XYZ_ifLinearAll at the end of every update, vslamRansac.cpp:1317)."""
     gold = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
 
     def make(over):
-        over = dict(over)
-        over["xyz_conversion"] = 0   # no feature of these cases reaches the linearity threshold (checked below)
         return gpu_pkg.VSlamFilter(gpu_pkg.default_config(**over), feature_capacity=CASES[name]["scene"]["n_features"] + 4)
 
-    for k in gold.files:
-        if k.endswith("_tab"):
-            assert not gold[k][:, 2].any(), "fixture converted a feature to XYZ"
     rec = run_case(gpu_pkg, name, CASES[name], make)
     worst = compare(rec, gold, TOL, name)
     print(f"{name}: CUDA path worst rel err vs reference fixture {worst:.2e}")
