@@ -55,7 +55,7 @@ class EkfStepStats(C.Structure):
 
 
 PROF_CLASSES = ("predict", "match", "ransac", "gather_W", "factor_S", "V_trsm", "downdate_gemm", "quat_normalise",
-                "hi_rescue", "bookkeeping", "add_remove", "spare")
+                "hi_rescue", "bookkeeping", "add_remove", "nccl_allgather")
 
 
 class EkfProfile(C.Structure):

@@ -65,6 +65,11 @@ SIGNATURES = {
     "ekf_batch_get_feature": (_i, [_vp, _i, _i, _P(_abi.EkfFeatureInfo)]),
     "ekf_batch_kernel_launches": (C.c_int64, [_vp]),
     "ekf_batch_last_step_ms": (_i, [_vp, _vp]),
+    "ekf_dist_load_nccl": (_i, [C.c_char_p]),
+    "ekf_dist_unique_id": (_i, [_vp]),
+    "ekf_dist_attach": (_i, [_vp, _vp, _i, _i]),
+    "ekf_dist_detach": (_i, [_vp]),
+    "ekf_dist_info": (_i, [_vp, _P(_i), _P(_i), _P(C.c_int64)]),
     "ekf_set_profiling": (_i, [_vp, _i]),
     "ekf_get_profile": (_i, [_vp, _P(_abi.EkfProfile), _i]),
     "ekf_set_symmetric_downdate": (_i, [_vp, _i]),

@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libekf_b200.so")
-SOURCES = ["ekf_api.cu", "ekf_predict.cu", "ekf_match.cu", "ekf_update.cu", "ekf_gemm.cu", "ekf_batch.cu"]
+SOURCES = ["ekf_api.cu", "ekf_predict.cu", "ekf_match.cu", "ekf_update.cu", "ekf_gemm.cu", "ekf_batch.cu", "ekf_dist.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-diag-suppress", "550"]
 
@@ -58,7 +58,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=6) as ex:
         objs = list(ex.map(one, srcs))
-    cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -94,6 +94,7 @@ int ekf_destroy(ekf_handle* h) {
   if (!h) return EKF_OK;
   cudaSetDevice(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  if (h->nccl_comm) ekf_dist_detach(h);
   for (auto& r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->prof_pool) cudaEventDestroy(e);
   cudaFree(h->mu); cudaFree(h->muB); cudaFree(h->Sigma); cudaFree(h->SigmaB); cudaFree(h->W); cudaFree(h->nu);
@@ -137,11 +138,11 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
   h->ncap = EKF_CAM + 6 * feature_capacity;
   h->ld = (h->ncap + 7) & ~7;
   const int w2 = (cfg->window_size * cfg->window_size + 15) & ~15;  // template record stride
-  const size_t ssz = (size_t)h->ncap * h->ld;
+  const size_t ssz = (size_t)(h->ncap + EKF_DIST_PAD_ROWS) * h->ld;
 #define TRY(x) if ((e = (x)) != cudaSuccess) return bail(e, #x);
   TRY(dalloc(&h->mu, h->ld)) TRY(dalloc(&h->muB, h->ld)) TRY(dalloc(&h->Sigma, ssz)) TRY(dalloc(&h->SigmaB, ssz))
-  TRY(dalloc(&h->W, (size_t)(h->ncap + 1) * EKF_UB)) TRY(dalloc(&h->nu, EKF_UB)) TRY(dalloc(&h->Lb, EKF_UB * EKF_UB))
-  TRY(dalloc(&h->Dinv, EKF_UB * EKF_UB)) TRY(dalloc(&h->Dblk, EKF_UB * 32)) TRY(dalloc(&h->yb, EKF_UB)) TRY(dalloc(&h->delta, h->ld)) TRY(dalloc(&h->mu_i, h->ld))
+  TRY(dalloc(&h->W, (size_t)(h->ncap + 1 + EKF_DIST_PAD_ROWS) * EKF_UB)) TRY(dalloc(&h->nu, EKF_UB)) TRY(dalloc(&h->Lb, EKF_UB * EKF_UB))
+  TRY(dalloc(&h->Dinv, EKF_UB * EKF_UB)) TRY(dalloc(&h->Dblk, EKF_UB * 32)) TRY(dalloc(&h->yb, EKF_UB)) TRY(dalloc(&h->delta, h->ld + EKF_DIST_PAD_ROWS)) TRY(dalloc(&h->mu_i, h->ld))
   TRY(dalloc(&h->cand, h->Ncap)) TRY(dalloc(&h->map_dev, h->ncap)) TRY(dalloc(&h->keep_dev, h->Ncap))
   TRY(dalloc(&h->newpos_dev, h->Ncap)) TRY(dalloc(&h->ctl, 1)) TRY(dalloc(&h->gemm_counters, 2))
   TRY(dalloc(&h->xyz_flag, h->Ncap)) TRY(dalloc(&h->xyz_rmap, 2 * (size_t)h->ncap)) TRY(dalloc(&h->xyz_pos, h->Ncap))
@@ -391,18 +392,37 @@ static int convert_xyz(ekf_handle* h, int only) {
 static int stacked_update(ekf_handle* h, int cnt) {
   if (cnt <= 0) return 0;
   cudaStream_t st = h->stream;
-  cudaMemsetAsync(h->delta, 0, sizeof(double) * (size_t)h->n, st);
+  // Row-block partition (BASELINE config 4): every rank holds a replica of Sigma, updates only its
+  // rows [r0, r1) and exchanges the small panels: W_b rows (S_b needs the camera / feature rows of W_b),
+  // V_b rows (the downdate of a row block needs all of V_b as its right factor) and delta; the updated
+  // row blocks of Sigma are all-gathered once at the end.  world == 1: r0 = 0, r1 = n, no exchange.
+  const bool dist = h->nccl_comm != nullptr && h->world > 1;
+  int rpr = h->n, r0 = 0, r1 = h->n;
+  if (dist) {
+    rpr = (((h->n + h->world - 1) / h->world) + 31) & ~31;
+    if ((long long)rpr * h->world > (long long)h->n + EKF_DIST_PAD_ROWS) return (int)cudaErrorInvalidValue;
+    r0 = std::min(h->n, h->rank * rpr);
+    r1 = std::min(h->n, r0 + rpr);
+  }
+  cudaMemsetAsync(h->delta, 0, sizeof(double) * (size_t)(h->n + (dist ? EKF_DIST_PAD_ROWS : 0)), st);
   for (int f0 = 0; f0 < cnt; f0 += EKF_UB / 2) {
-    { ProfScope ps(h, 3); launch_blk_gather(st, h->Sigma, h->ld, h->n, h->ft, f0, cnt, h->delta, h->W, h->nu, &h->launches); }
+    { ProfScope ps(h, 3); launch_blk_gather(st, h->Sigma, h->ld, r0, r1, h->ft, f0, cnt, h->delta, h->W, h->nu, &h->launches); }
+    if (dist) { ProfScope ps(h, 11); if (ekf_dist_allgather_rows(h, h->W, rpr, EKF_UB)) return (int)cudaErrorUnknown; }
     { ProfScope ps(h, 4); launch_blk_factor(st, h->W, h->ft, f0, cnt, h->nu, h->dcfg, h->Lb, h->Dinv, h->Dblk, h->yb, h->ctl, &h->launches);  /* Lb = S_b scratch, Dinv = L, Dblk = diagonal-block inverses */ }
-    { ProfScope ps(h, 5); launch_blk_V(st, h->W, h->n, h->Dinv, h->Dblk, h->yb, h->delta, &h->launches); }
+    { ProfScope ps(h, 5); launch_blk_V(st, h->W, r0, r1, h->Dinv, h->Dblk, h->yb, h->delta, &h->launches); }
+    if (dist) {
+      ProfScope ps(h, 11);
+      if (ekf_dist_allgather_rows(h, h->W, rpr, EKF_UB)) return (int)cudaErrorUnknown;
+      if (ekf_dist_allgather_rows(h, h->delta, rpr, 1)) return (int)cudaErrorUnknown;
+    }
     {
       ProfScope ps(h, 6);
-      const int rc = launch_gemm_nt_sub(st, h->Sigma, h->ld, h->W, EKF_UB, h->W, EKF_UB, h->n, h->n, EKF_UB, nullptr, h->lower_only,
-                                        h->gemm_counters, &h->launches);
+      const int rc = launch_gemm_nt_sub(st, h->Sigma + (size_t)r0 * h->ld, h->ld, h->W + (size_t)r0 * EKF_UB, EKF_UB, h->W, EKF_UB,
+                                        r1 - r0, h->n, EKF_UB, nullptr, dist ? 0 : h->lower_only, h->gemm_counters, &h->launches);
       if (rc) return rc;
     }
   }
+  if (dist) { ProfScope ps(h, 11); if (ekf_dist_allgather_rows(h, h->Sigma, rpr, (size_t)h->ld)) return (int)cudaErrorUnknown; }
   {
     ProfScope ps(h, 7);
     launch_apply_delta(st, h->mu, h->delta, h->n, &h->launches);

@@ -37,6 +37,10 @@ struct ekf_handle {
   int patchnumbre = 1, noise_cov_factor = 0;
   bool predicted = false, have_frame = false;
   int lower_only = 0;
+  // row-block partitioned update across ranks (ekf_dist.cu): NCCL communicator of this handle, or null
+  void* nccl_comm = nullptr;
+  int rank = 0, world = 1;
+  long long dist_bytes = 0;   // bytes this rank contributed to all-gathers so far
   ekf_step_stats stats{};
   long long launches = 0;
   std::string err;
@@ -57,3 +61,8 @@ struct ekf_handle {
   std::vector<int> m_pos, m_coding;
 };
 
+
+// ekf_dist.cu: in-place all-gather of a row-partitioned device buffer.  Rank r owns rows
+// [r * rows_per_rank, (r + 1) * rows_per_rank) of `buf` (row_elems doubles per row).
+int ekf_dist_allgather_rows(ekf_handle* h, double* buf, int rows_per_rank, size_t row_elems);
+#define EKF_DIST_PAD_ROWS 512   // extra rows allocated for W / delta / Sigma so that world * rows_per_rank fits

@@ -33,12 +33,12 @@ void launch_ransac(cudaStream_t st, const double* Sigma, int ld, int n, const do
                    const DevCfg& cfg, const uint32_t* picks, int n_picks, double* mu_i, int* cand, long long* launches);
 void launch_hi_rescue(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, DevCtl* ctl,
                       const DevCfg& cfg, long long* launches);
-void launch_blk_gather(cudaStream_t st, const double* Sigma, int ld, int n, FeatTab ft, int f0, int cnt, const double* delta,
-                       double* W, double* nu, long long* launches);
+void launch_blk_gather(cudaStream_t st, const double* Sigma, int ld, int row0, int row1, FeatTab ft, int f0, int cnt,
+                       const double* delta, double* W, double* nu, long long* launches);
 void launch_blk_factor(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const double* nu, const DevCfg& cfg,
                        double* Sb, double* Lb, double* Dblk, double* yb, DevCtl* ctl, long long* launches);
-void launch_blk_V(cudaStream_t st, double* W, int n, const double* Lb, const double* Dblk, const double* yb, double* delta,
-                  long long* launches);
+void launch_blk_V(cudaStream_t st, double* W, int row0, int row1, const double* Lb, const double* Dblk, const double* yb,
+                  double* delta, long long* launches);
 void launch_apply_delta(cudaStream_t st, double* mu, const double* delta, int n, long long* launches);
 void launch_bookkeeping(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, DevCtl* ctl,
                         const DevCfg& cfg, double* outd, int* outi, long long* launches);

@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(128) k_hi_rescue(const double* __restrict__ Si
 // (n x EKF_UB, row-major), and nu_b = (z - h) - H_b delta.  One pass over the needed columns of Sigma.
 // ------------------------------------------------------------------------------------------------
 #define GATHER_ROWS 8
-__global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ Sigma, int ld, int n, FeatTab ft, int f0, int cnt,
-                                                    const double* __restrict__ delta, double* __restrict__ W,
+__global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ Sigma, int ld, int row0, int n, FeatTab ft, int f0,
+                                                    int cnt, const double* __restrict__ delta, double* __restrict__ W,
                                                     double* __restrict__ nu) {
   __shared__ double Hs[EKF_UB / 2][27];
   __shared__ int poss[EKF_UB / 2], nds[EKF_UB / 2], fids[EKF_UB / 2];
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ S
   const int rows_per_cta = GATHER_ROWS, rstep = 256 / (EKF_UB / 2);
   const int pos = poss[a], nd = nds[a];
   for (int rq = rl; rq < rows_per_cta; rq += rstep) {
-    const int i = blockIdx.x * rows_per_cta + rq;
+    const int i = row0 + blockIdx.x * rows_per_cta + rq;   // rows [row0, n): the caller's row block
     if (i >= n) break;
     const double* row = Sigma + (size_t)i * ld;
     double w0 = 0, w1 = 0;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __res
 #define VT_THREADS 128
 #define VT_LD (EKF_UB + 4)
 #define VT_LDD 36
-__global__ void __launch_bounds__(VT_THREADS) k_blk_V(double* __restrict__ W, int n, const double* __restrict__ Lg,
+__global__ void __launch_bounds__(VT_THREADS) k_blk_V(double* __restrict__ W, int rbase, int n, const double* __restrict__ Lg,
                                                       const double* __restrict__ Dg, const double* __restrict__ yg,
                                                       double* __restrict__ delta) {
   extern __shared__ __align__(16) double vsm[];
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(VT_THREADS) k_blk_V(double* __restrict__ W, in
   double* Ws = Ds + (EKF_UB / 32) * 32 * VT_LDD;  // [VT_ROWS][VT_LD] W rows, then V rows
   double* ys = Ws + VT_ROWS * VT_LD;         // [EKF_UB]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int row0 = blockIdx.x * VT_ROWS;
+  const int row0 = rbase + blockIdx.x * VT_ROWS;   // rows [rbase, n): the caller's row block
   for (int e = tid; e < EKF_UB * EKF_UB / 2; e += VT_THREADS) {
     const int r = e >> 6, c = (e & 63) * 2;
     *reinterpret_cast<double2*>(Ls + r * VT_LD + c) = *reinterpret_cast<const double2*>(Lg + r * EKF_UB + c);
@@ -291,9 +291,10 @@ void launch_hi_rescue(cudaStream_t st, const double* Sigma, int ld, const double
   k_hi_rescue<<<fb, 128, 0, st>>>(Sigma, ld, mu, ft, N, ctl, cfg);
   *launches += 1;
 }
-void launch_blk_gather(cudaStream_t st, const double* Sigma, int ld, int n, FeatTab ft, int f0, int cnt, const double* delta,
-                       double* W, double* nu, long long* launches) {
-  k_blk_gather<<<(n + GATHER_ROWS - 1) / GATHER_ROWS, 256, 0, st>>>(Sigma, ld, n, ft, f0, cnt, delta, W, nu);
+void launch_blk_gather(cudaStream_t st, const double* Sigma, int ld, int row0, int row1, FeatTab ft, int f0, int cnt,
+                       const double* delta, double* W, double* nu, long long* launches) {
+  const int nr = row1 > row0 ? row1 - row0 : 1;   // at least one CTA: block 0 also forms nu
+  k_blk_gather<<<(nr + GATHER_ROWS - 1) / GATHER_ROWS, 256, 0, st>>>(Sigma, ld, row0, row1, ft, f0, cnt, delta, W, nu);
   *launches += 1;
 }
 void launch_blk_factor(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const double* nu, const DevCfg& cfg,
@@ -302,9 +303,10 @@ void launch_blk_factor(cudaStream_t st, const double* W, FeatTab ft, int f0, int
   k_blk_factor<<<1, FACT_THREADS, kFactSmem, st>>>(Sb, nu, Lb, Dblk, yb, ctl);
   *launches += 2;
 }
-void launch_blk_V(cudaStream_t st, double* W, int n, const double* Lb, const double* Dblk, const double* yb, double* delta,
-                  long long* launches) {
-  k_blk_V<<<(n + VT_ROWS - 1) / VT_ROWS, VT_THREADS, kVSmem, st>>>(W, n, Lb, Dblk, yb, delta);
+void launch_blk_V(cudaStream_t st, double* W, int row0, int row1, const double* Lb, const double* Dblk, const double* yb,
+                  double* delta, long long* launches) {
+  if (row1 <= row0) return;
+  k_blk_V<<<(row1 - row0 + VT_ROWS - 1) / VT_ROWS, VT_THREADS, kVSmem, st>>>(W, row0, row1, Lb, Dblk, yb, delta);
   *launches += 1;
 }
 void launch_apply_delta(cudaStream_t st, double* mu, const double* delta, int n, long long* launches) {

@@ -45,3 +45,25 @@ def gather_camera_states(mu14_local, dist=None, device=None):
     parts = [torch.empty_like(a) for _ in range(dist.get_world_size())]
     dist.all_gather(parts, a)
     return torch.cat(parts, dim=0).cpu().numpy()
+
+
+def attach_row_partition(filt, dist, device):
+    """Attaches a VSlamFilter replica to a fresh NCCL communicator spanning the torch.distributed
+    world: rank 0 creates the id, torch.distributed broadcasts its 128 bytes, every rank joins.
+    Afterwards the filter's stacked update is partitioned by covariance row blocks (BASELINE config 4)."""
+    import torch
+    from . import filter as _f
+    rank, world = dist.get_rank(), dist.get_world_size()
+    _f.load_nccl()
+    raw = _f.nccl_unique_id() if rank == 0 else bytes(128)
+    t = torch.tensor(list(raw), dtype=torch.uint8, device=device)
+    dist.broadcast(t, src=0)
+    filt.dist_attach(bytes(t.cpu().tolist()), rank, world)
+    return rank, world
+
+
+def row_block(rank: int, world: int, n: int):
+    """Rows [r0, r1) of an n x n covariance owned by `rank` (same rule as ekf_api.cu::stacked_update)."""
+    rpr = ((n + world - 1) // world + 31) & ~31
+    r0 = min(n, rank * rpr)
+    return r0, min(n, r0 + rpr), rpr

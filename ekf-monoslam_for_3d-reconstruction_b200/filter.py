@@ -176,6 +176,43 @@ class VSlamFilter:
     def sync(self):
         self._ck(self.L.ekf_sync(self.h))
 
+    # ---- large map split across GPUs (row-block partitioned update, ekf_dist_*) -------------------
+    def dist_attach(self, nccl_id: bytes, rank: int, world: int):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(nccl_id))
+        self._ck(self.L.ekf_dist_attach(self.h, C.cast(buf, C.c_void_p), int(rank), int(world)))
+
+    def dist_detach(self):
+        self._ck(self.L.ekf_dist_detach(self.h))
+
+    def dist_info(self):
+        r, w, b = C.c_int(0), C.c_int(0), C.c_int64(0)
+        self._ck(self.L.ekf_dist_info(self.h, C.byref(r), C.byref(w), C.byref(b)))
+        return dict(rank=r.value, world=w.value, allgather_bytes=b.value)
+
+
+def nccl_unique_id(libnccl_path=None) -> bytes:
+    """Loads libnccl (the copy torch uses unless a path is given) and returns a fresh 128-byte id."""
+    load_nccl(libnccl_path)
+    buf = (C.c_char * 128)()
+    rc = lib().ekf_dist_unique_id(C.cast(buf, C.c_void_p))
+    if rc != 0:
+        raise EkfError(f"ekf_dist_unique_id failed: {rc}")
+    return bytes(buf)
+
+
+def load_nccl(libnccl_path=None):
+    if libnccl_path is None:
+        try:
+            import os
+            import nvidia.nccl as _n
+            cand = os.path.join(os.path.dirname(_n.__file__), "lib", "libnccl.so.2")
+            libnccl_path = cand if os.path.exists(cand) else None
+        except Exception:
+            libnccl_path = None
+    rc = lib().ekf_dist_load_nccl(libnccl_path.encode() if libnccl_path else None)
+    if rc != 0:
+        raise EkfError(f"ekf_dist_load_nccl failed: {rc}")
+
 
 def match_batch(frames_dev, n_frames, width, height, stride, templates_dev, features_per_frame, window,
                 h_dev, S_dev, out_uv_dev, out_score_dev, sigma_size=3.0, ncc_threshold=0.8, search_clamp=20.0,

@@ -225,11 +225,27 @@ int64_t ekf_batch_kernel_launches(const ekf_batch* b);
 /* CUDA-event time (ms) of the three kernel classes of the last step: predict, match, update. */
 int ekf_batch_last_step_ms(ekf_batch* b, float out[3]);
 
+/* ---- large map split across GPUs (BASELINE config 4) ------------------------------------------- */
+/* One process per GPU, each with its own ekf_handle holding a replica of the same filter (same calls
+ * in the same order on every rank).  Once attached, the stacked EKF update — W = Sigma H^T, gain,
+ * Sigma -= V V^T, > 95 % of a large-map step — is partitioned by covariance ROW BLOCKS: rank r updates
+ * rows [r * rpr, (r + 1) * rpr) only, and NCCL (all-gather over NVLink / NVSwitch) carries the W_b /
+ * V_b panels (n x 128 fp64 per 64 features), the state correction and, once per update, the row
+ * blocks of Sigma.  Everything else (predict, match, RANSAC, book-keeping) is O(n) or O(N) work that
+ * every rank repeats on its replica.  libnccl is opened at run time: pass the path of the library the
+ * host already uses (NULL = "libnccl.so.2").  The 128-byte id comes from ekf_dist_unique_id on one
+ * rank and is distributed by the host (the Python host broadcasts it with torch.distributed). */
+int ekf_dist_load_nccl(const char* libnccl_path);
+int ekf_dist_unique_id(char out[128]);
+int ekf_dist_attach(ekf_handle* h, const char id[128], int rank, int world);
+int ekf_dist_detach(ekf_handle* h);
+int ekf_dist_info(const ekf_handle* h, int* rank, int* world, int64_t* allgather_bytes);
+
 /* ---- per-kernel timing (CUDA events on the handle's stream; off by default) ---------------------- */
 #define EKF_PROF_CLASSES 12
 typedef struct ekf_profile {
   /* classes: 0 predict_cov+features, 1 match, 2 ransac, 3 gather W, 4 factor S, 5 V=W L^-T,
-   * 6 downdate GEMM (DMMA), 7 quat normalise, 8 hi rescue, 9 bookkeeping, 10 add/remove, 11 spare */
+   * 6 downdate GEMM (DMMA), 7 quat normalise, 8 hi rescue, 9 bookkeeping, 10 add/remove, 11 NCCL all-gathers */
   double ms[EKF_PROF_CLASSES];
   int64_t launches[EKF_PROF_CLASSES];
 } ekf_profile;
