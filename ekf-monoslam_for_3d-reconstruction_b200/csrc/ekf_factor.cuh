@@ -2,11 +2,11 @@
 // memory, the inverses of its 32 x 32 diagonal blocks, and y = L^-1 nu.  Shared by the single-filter
 // update (NB = 128, ekf_update.cu) and the fused batched-filter kernel (NB = 64, ekf_batch.cu).
 //
-// Right-looking Cholesky in steps of TWO columns (the measurement rows come in pairs, one pair per
-// feature): every thread reads the 2 x 2 pivot block (a shared-memory broadcast) and factors it
-// redundantly — two rsqrt on the dependency chain per step, no data exchange — then all threads scale
-// the two panel columns and apply the rank-2 update to the trailing lower triangle.  Two block
-// barriers per step, NB / 2 steps.  nu rides along as row NB of the matrix: its panel entries come
+// Right-looking Cholesky in steps of FOUR columns (two features): every thread reads the 4 x 4 pivot
+// block (a shared-memory broadcast) and factors it redundantly — four rsqrt on the dependency chain
+// per step, no data exchange — then one thread per row solves the four panel columns and all warps
+// apply the rank-4 update to the trailing lower triangle with one DMMA.8x8x4 per 8 x 8 tile.  Two block
+// barriers per step, NB / 4 steps.  nu rides along as row NB of the matrix: its panel entries come
 // out as y = L^-1 nu (forward substitution is the same recurrence).  The previous version (one warp
 // factoring 32 x 32 blocks in registers + an explicit L^-1) spent most of its time with 15 warps
 // waiting on one; V = W L^-T is now a blocked triangular solve in the callers, which only needs the
@@ -23,9 +23,9 @@ __device__ __forceinline__ void dmma884f(double& d0, double& d1, double a, doubl
                : "d"(a), "d"(b));
 }
 
-// shared-memory doubles needed by cta_chol22<NB>: A[(NB + 1)][NB + 1] + pivot reciprocals[NB]
+// shared-memory doubles needed by cta_chol22<NB>: A[(NB + 8)][NB + 1] + pivot reciprocals[NB]
 template <int NB>
-__host__ __device__ constexpr int cta_chol22_smem_doubles() { return (NB + 1) * (NB + 1) + NB; }
+__host__ __device__ constexpr int cta_chol22_smem_doubles() { return (NB + 8) * (NB + 1) + NB; }
 
 // fsm: workspace (see above).  Sb: NB x NB symmetric positive definite (leading dimension lds; only
 // the lower triangle is read), nu: NB.  Outputs (shared or global memory):
@@ -33,44 +33,88 @@ __host__ __device__ constexpr int cta_chol22_smem_doubles() { return (NB + 1) * 
 //   Dout  (NB / 32) blocks of 32 rows x ldd: inverse of the J-th 32 x 32 diagonal block of L
 //   yout  NB: L^-1 nu
 // Lout may alias Sb.  blockDim.x must be FACT_THREADS.  Ends with a barrier.
+//
+// Steps of FOUR columns (two features): the 4 x 4 pivot block is factored redundantly by every thread
+// (four rsqrt on the chain), one thread per row solves the panel, and the rank-4 trailing update is one
+// DMMA.8x8x4 per 8 x 8 tile of the lower triangle (tiles on a fixed 8-aligned grid; fragment rows that
+// lie left of / above the trailing block are zeroed, so finished entries of L are never touched).
 template <int NB>
 __device__ void cta_chol22(double* fsm, const double* Sb, int lds, const double* nu, double* Lout, int ldl, double* Dout,
                            int ldd, double* yout, int* chol_fail) {
-  constexpr int NP = NB / 32, FLD = NB + 1;
-  double* A = fsm;                   // [(NB + 1)][FLD]
-  double* rinvs = A + (NB + 1) * FLD;  // [NB]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NP = NB / 32, FLD = NB + 1, T = NB / 8;
+  double* A = fsm;                      // [(NB + 8)][FLD]: rows 0..NB-1 S / L, row NB nu / y, rows NB+1.. padding
+  double* rinvs = A + (NB + 8) * FLD;   // [NB]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
   for (int e = tid; e < NB * NB; e += FACT_THREADS) {
     const int r = e / NB, c = e - r * NB;
-    if (c <= r) A[r * FLD + c] = Sb[(size_t)r * lds + c];
+    A[r * FLD + c] = (c <= r) ? Sb[(size_t)r * lds + c] : 0.0;
   }
-  for (int e = tid; e < NB; e += FACT_THREADS) A[NB * FLD + e] = nu[e];
+  for (int e = tid; e < 8 * FLD; e += FACT_THREADS) A[NB * FLD + e] = (e < NB) ? nu[e] : 0.0;
   __syncthreads();
-  for (int p = 0; p < NB; p += 2) {
-    // 2 x 2 pivot block, factored by every thread
-    const double a00 = A[p * FLD + p], a10 = A[(p + 1) * FLD + p], a11 = A[(p + 1) * FLD + p + 1];
-    const double r00 = rsqrt(a00);
-    const double c10 = a10 * r00;
-    const double t11 = a11 - c10 * c10;
-    const double r11 = rsqrt(t11);
-    // panel: rows p + 2 .. NB (row NB is nu)
-    for (int r = p + 2 + tid; r <= NB; r += FACT_THREADS) {
-      const double l0 = A[r * FLD + p] * r00;
-      const double l1 = (A[r * FLD + p + 1] - l0 * c10) * r11;
-      A[r * FLD + p] = l0;
-      A[r * FLD + p + 1] = l1;
+  for (int p = 0; p < NB; p += 4) {
+    // 4 x 4 pivot block (shared-memory broadcast), factored by every thread
+    const double* Pv = A + p * FLD + p;
+    const double a00 = Pv[0], a10 = Pv[FLD], a11 = Pv[FLD + 1], a20 = Pv[2 * FLD], a21 = Pv[2 * FLD + 1], a22 = Pv[2 * FLD + 2],
+                 a30 = Pv[3 * FLD], a31 = Pv[3 * FLD + 1], a32 = Pv[3 * FLD + 2], a33 = Pv[3 * FLD + 3];
+    const double r0 = rsqrt(a00);
+    const double l10 = a10 * r0, l20 = a20 * r0, l30 = a30 * r0;
+    const double t11 = a11 - l10 * l10;
+    const double r1 = rsqrt(t11);
+    const double l21 = (a21 - l20 * l10) * r1, l31 = (a31 - l30 * l10) * r1;
+    const double t22 = a22 - l20 * l20 - l21 * l21;
+    const double r2 = rsqrt(t22);
+    const double l32 = (a32 - l30 * l20 - l31 * l21) * r2;
+    const double t33 = a33 - l30 * l30 - l31 * l31 - l32 * l32;
+    const double r3 = rsqrt(t33);
+    // panel: rows p + 4 .. NB (row NB is nu), one thread per row
+    for (int r = p + 4 + tid; r <= NB; r += FACT_THREADS) {
+      double* row = A + r * FLD + p;
+      const double x0 = row[0] * r0;
+      const double x1 = (row[1] - x0 * l10) * r1;
+      const double x2 = (row[2] - x0 * l20 - x1 * l21) * r2;
+      const double x3 = (row[3] - x0 * l30 - x1 * l31 - x2 * l32) * r3;
+      row[0] = x0; row[1] = x1; row[2] = x2; row[3] = x3;
     }
     __syncthreads();
     if (tid == 0) {
-      if (!(a00 > 0.0) || !(t11 > 0.0)) *chol_fail = 1;
-      A[p * FLD + p] = a00 * r00; A[(p + 1) * FLD + p] = c10; A[(p + 1) * FLD + p + 1] = t11 * r11;
-      rinvs[p] = r00; rinvs[p + 1] = r11;
+      if (!(a00 > 0.0) || !(t11 > 0.0) || !(t22 > 0.0) || !(t33 > 0.0)) *chol_fail = 1;
+      double* Pw = A + p * FLD + p;
+      Pw[0] = a00 * r0;
+      Pw[FLD] = l10; Pw[FLD + 1] = t11 * r1;
+      Pw[2 * FLD] = l20; Pw[2 * FLD + 1] = l21; Pw[2 * FLD + 2] = t22 * r2;
+      Pw[3 * FLD] = l30; Pw[3 * FLD + 1] = l31; Pw[3 * FLD + 2] = l32; Pw[3 * FLD + 3] = t33 * r3;
+      rinvs[p] = r0; rinvs[p + 1] = r1; rinvs[p + 2] = r2; rinvs[p + 3] = r3;
     }
-    // trailing update of the lower triangle (and of row NB): warp per row, lanes over columns
-    for (int r = p + 2 + warp; r <= NB; r += FACT_WARPS) {
-      const double l0 = A[r * FLD + p], l1 = A[r * FLD + p + 1];
-      const int cmax = r < NB ? r : NB - 1;
-      for (int c = p + 2 + lane; c <= cmax; c += 32) A[r * FLD + c] -= l0 * A[c * FLD + p] + l1 * A[c * FLD + p + 1];
+    // rank-4 trailing update on the tensor pipe: lower 8 x 8 tiles (I >= J >= I0) plus the nu tile row
+    {
+      const int base = p + 4, I0 = base >> 3, nt = T - I0;
+      const int ntile = nt * (nt + 1) / 2 + nt;        // triangle, then tile row T (nu) with J = I0 .. T-1
+      for (int t = warp; t < ntile; t += FACT_WARPS) {
+        int I, J;
+        if (t < nt * (nt + 1) / 2) {
+          int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+          while (ti * (ti + 1) / 2 > t) --ti;
+          while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+          I = I0 + ti; J = I0 + (t - ti * (ti + 1) / 2);
+        } else {
+          I = T; J = I0 + (t - nt * (nt + 1) / 2);
+        }
+        const int ra = 8 * I + g, rb = 8 * J + g;
+        double a = A[ra * FLD + p + t4], b = A[rb * FLD + p + t4];
+        a = (ra >= base) ? -a : 0.0;          // rows above the trailing block (and the padding rows past nu) contribute nothing
+        b = (rb >= base) ? b : 0.0;
+        if (I == T && g > 0) a = 0.0;
+        double* cp = A + ra * FLD + 8 * J + 2 * t4;
+        double d0 = cp[0], d1 = cp[1];
+        dmma884f(d0, d1, a, b);
+        // finished entries (pivot rows / panel columns inside a boundary tile) are left alone: thread 0 is
+        // writing the pivot block's final values concurrently
+        if (ra >= base && !(I == T && g > 0)) {
+          const int col = 8 * J + 2 * t4;
+          if (col >= base) cp[0] = d0;
+          if (col + 1 >= base) cp[1] = d1;
+        }
+      }
     }
     __syncthreads();
   }

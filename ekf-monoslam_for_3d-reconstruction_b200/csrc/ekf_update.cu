@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __res
 // (warp_trsm_tile, ekf_factor.cuh), so there is no block barrier after the operands are staged.
 // ------------------------------------------------------------------------------------------------
 #define VT_ROWS 32
-#define VT_THREADS 128
+#define VT_THREADS 256   // 8 warps stage the operands; warps 0..3 each own one 8-row tile of the solve
 #define VT_LD (EKF_UB + 4)
 #define VT_LDD 36
 __global__ void __launch_bounds__(VT_THREADS) k_blk_V(double* __restrict__ W, int rbase, int n, const double* __restrict__ Lg,
@@ -220,11 +220,13 @@ __global__ void __launch_bounds__(VT_THREADS) k_blk_V(double* __restrict__ W, in
   }
   for (int e = tid; e < EKF_UB; e += VT_THREADS) ys[e] = yg[e];
   __syncthreads();
-  double part = warp_trsm_tile<EKF_UB>(Ws + (size_t)warp * 8 * VT_LD, VT_LD, Ls, VT_LD, Ds, VT_LDD, ys);
-  part += __shfl_xor_sync(0xffffffffu, part, 1);
-  part += __shfl_xor_sync(0xffffffffu, part, 2);
-  const int i = row0 + warp * 8 + (lane >> 2);
-  if ((lane & 3) == 0 && i < n) delta[i] += part;
+  if (warp < VT_ROWS / 8) {
+    double part = warp_trsm_tile<EKF_UB>(Ws + (size_t)warp * 8 * VT_LD, VT_LD, Ls, VT_LD, Ds, VT_LDD, ys);
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    const int i = row0 + warp * 8 + (lane >> 2);
+    if ((lane & 3) == 0 && i < n) delta[i] += part;
+  }
   __syncthreads();
   for (int e = tid; e < VT_ROWS * EKF_UB / 2; e += VT_THREADS) {
     const int r = e >> 6, c = (e & 63) * 2;
