@@ -23,9 +23,12 @@ __device__ __forceinline__ void dmma884f(double& d0, double& d1, double a, doubl
                : "d"(a), "d"(b));
 }
 
-// shared-memory doubles needed by cta_chol22<NB>: A[(NB + 8)][NB + 1] + pivot reciprocals[NB]
+// shared-memory doubles needed by cta_chol22<NB>
 template <int NB>
-__host__ __device__ constexpr int cta_chol22_smem_doubles() { return (NB + 8) * (NB + 1) + NB; }
+__host__ __device__ constexpr int cta_chol22_smem_doubles() {
+  // A[(NB + 8)][NB + 1] + pivot reciprocals[NB] + tile list (2 bytes per tile, T (T + 1) / 2 + T tiles)
+  return (NB + 8) * (NB + 1) + NB + (((NB / 8) * (NB / 8 + 1) / 2 + NB / 8) * 2 + 7) / 8;
+}
 
 // fsm: workspace (see above).  Sb: NB x NB symmetric positive definite (leading dimension lds; only
 // the lower triangle is read), nu: NB.  Outputs (shared or global memory):
@@ -44,7 +47,15 @@ __device__ void cta_chol22(double* fsm, const double* Sb, int lds, const double*
   constexpr int NP = NB / 32, FLD = NB + 1, T = NB / 8;
   double* A = fsm;                      // [(NB + 8)][FLD]: rows 0..NB-1 S / L, row NB nu / y, rows NB+1.. padding
   double* rinvs = A + (NB + 8) * FLD;   // [NB]
+  // tile list ordered by tile column J descending: the tiles of a trailing block that starts at tile
+  // index I0 (J >= I0) are always a prefix of it
+  unsigned char* tl = reinterpret_cast<unsigned char*>(rinvs + NB);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+  if (tid == 0) {
+    int k = 0;
+    for (int J = T - 1; J >= 0; --J)
+      for (int I = J; I <= T; ++I) { tl[2 * k] = (unsigned char)I; tl[2 * k + 1] = (unsigned char)J; ++k; }
+  }
   for (int e = tid; e < NB * NB; e += FACT_THREADS) {
     const int r = e / NB, c = e - r * NB;
     A[r * FLD + c] = (c <= r) ? Sb[(size_t)r * lds + c] : 0.0;
@@ -88,17 +99,9 @@ __device__ void cta_chol22(double* fsm, const double* Sb, int lds, const double*
     // rank-4 trailing update on the tensor pipe: lower 8 x 8 tiles (I >= J >= I0) plus the nu tile row
     {
       const int base = p + 4, I0 = base >> 3, nt = T - I0;
-      const int ntile = nt * (nt + 1) / 2 + nt;        // triangle, then tile row T (nu) with J = I0 .. T-1
+      const int ntile = nt * (nt + 1) / 2 + nt;        // tiles (I, J) with J >= I0, I = J .. T (tile row T holds nu)
       for (int t = warp; t < ntile; t += FACT_WARPS) {
-        int I, J;
-        if (t < nt * (nt + 1) / 2) {
-          int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-          while (ti * (ti + 1) / 2 > t) --ti;
-          while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-          I = I0 + ti; J = I0 + (t - ti * (ti + 1) / 2);
-        } else {
-          I = T; J = I0 + (t - nt * (nt + 1) / 2);
-        }
+        const int I = tl[2 * t], J = tl[2 * t + 1];
         const int ra = 8 * I + g, rb = 8 * J + g;
         double a = A[ra * FLD + p + t4], b = A[rb * FLD + p + t4];
         a = (ra >= base) ? -a : 0.0;          // rows above the trailing block (and the padding rows past nu) contribute nothing
