@@ -210,8 +210,13 @@ def run_ours(args):
     filt = new_filter()
     sampler = ClockSampler(local)
     sampler.start()
-    tA, wallA, launches, prof = timed_pass(step_resident, filt, profile=True)
+    tA, wallA, launches, _ = timed_pass(step_resident, filt)          # the reported value: no per-kernel events in the stream
     clocks = sampler.stop()
+    stA = filt.stats()
+    n_state = filt.state_dim()
+    del filt
+    filt = new_filter()                                                 # same sequence again on a fresh filter,
+    tP, _, _, prof = timed_pass(step_resident, filt, profile=True)      # with CUDA-event brackets per kernel class
     stA = filt.stats()
     n_state = filt.state_dim()
     del filt
@@ -263,7 +268,7 @@ def run_ours(args):
                 traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        step_ms = float(tA.mean())
+        step_ms = float(tP.mean())   # share_of_step is taken inside the profiled pass
         out = {
             "metric": metric_for(args.workload), "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": round(totA / K, 4), "higher_is_better": True, "scaling": "strong" if partitioned else "weak",

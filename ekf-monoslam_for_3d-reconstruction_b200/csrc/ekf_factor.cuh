@@ -16,6 +16,16 @@
 
 #define FACT_THREADS 512
 #define FACT_WARPS (FACT_THREADS / 32)
+#ifdef FACT_DEBUG   // tools/factor_probe.cu: cycles per phase, accumulated by thread 0
+__device__ long long g_fact_acc[16];
+#define FACC(i) do { if (threadIdx.x == 0) { const long long _t = clock64(); _facc[i] += _t - _fc; _fc = _t; } } while (0)
+#define FACC_INIT __shared__ long long _facc[16]; if (threadIdx.x < 16) _facc[threadIdx.x] = 0; __syncthreads(); long long _fc = clock64()
+#define FACC_DUMP do { if (threadIdx.x < 16) g_fact_acc[threadIdx.x] = _facc[threadIdx.x]; } while (0)
+#else
+#define FACC(i) do {} while (0)
+#define FACC_INIT do {} while (0)
+#define FACC_DUMP do {} while (0)
+#endif
 
 __device__ __forceinline__ void dmma884f(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -51,6 +61,7 @@ __device__ void cta_chol22(double* fsm, const double* Sb, int lds, const double*
   // index I0 (J >= I0) are always a prefix of it
   unsigned char* tl = reinterpret_cast<unsigned char*>(rinvs + NB);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+  FACC_INIT;
   if (tid == 0) {
     int k = 0;
     for (int J = T - 1; J >= 0; --J)
@@ -62,6 +73,7 @@ __device__ void cta_chol22(double* fsm, const double* Sb, int lds, const double*
   }
   for (int e = tid; e < 8 * FLD; e += FACT_THREADS) A[NB * FLD + e] = (e < NB) ? nu[e] : 0.0;
   __syncthreads();
+  FACC(0);
   for (int p = 0; p < NB; p += 4) {
     // 4 x 4 pivot block (shared-memory broadcast), factored by every thread
     const double* Pv = A + p * FLD + p;
@@ -77,6 +89,8 @@ __device__ void cta_chol22(double* fsm, const double* Sb, int lds, const double*
     const double l32 = (a32 - l30 * l20 - l31 * l21) * r2;
     const double t33 = a33 - l30 * l30 - l31 * l31 - l32 * l32;
     const double r3 = rsqrt(t33);
+    if (r3 == 123.456) *chol_fail = 2;   // keeps the chain from being sunk below the stamp in probe builds (never true)
+    FACC(1);
     // panel: rows p + 4 .. NB (row NB is nu), one thread per row
     for (int r = p + 4 + tid; r <= NB; r += FACT_THREADS) {
       double* row = A + r * FLD + p;
@@ -86,7 +100,9 @@ __device__ void cta_chol22(double* fsm, const double* Sb, int lds, const double*
       const double x3 = (row[3] - x0 * l30 - x1 * l31 - x2 * l32) * r3;
       row[0] = x0; row[1] = x1; row[2] = x2; row[3] = x3;
     }
+    FACC(2);
     __syncthreads();
+    FACC(3);
     if (tid == 0) {
       if (!(a00 > 0.0) || !(t11 > 0.0) || !(t22 > 0.0) || !(t33 > 0.0)) *chol_fail = 1;
       double* Pw = A + p * FLD + p;
@@ -100,26 +116,41 @@ __device__ void cta_chol22(double* fsm, const double* Sb, int lds, const double*
     {
       const int base = p + 4, I0 = base >> 3, nt = T - I0;
       const int ntile = nt * (nt + 1) / 2 + nt;        // tiles (I, J) with J >= I0, I = J .. T (tile row T holds nu)
-      for (int t = warp; t < ntile; t += FACT_WARPS) {
-        const int I = tl[2 * t], J = tl[2 * t + 1];
-        const int ra = 8 * I + g, rb = 8 * J + g;
-        double a = A[ra * FLD + p + t4], b = A[rb * FLD + p + t4];
-        a = (ra >= base) ? -a : 0.0;          // rows above the trailing block (and the padding rows past nu) contribute nothing
-        b = (rb >= base) ? b : 0.0;
-        if (I == T && g > 0) a = 0.0;
-        double* cp = A + ra * FLD + 8 * J + 2 * t4;
-        double d0 = cp[0], d1 = cp[1];
-        dmma884f(d0, d1, a, b);
-        // finished entries (pivot rows / panel columns inside a boundary tile) are left alone: thread 0 is
-        // writing the pivot block's final values concurrently
-        if (ra >= base && !(I == T && g > 0)) {
+      // four tiles of a warp in flight at a time: the DMMA accumulate latency, not its issue rate, is the cost here
+      for (int t0 = warp; t0 < ntile; t0 += 4 * FACT_WARPS) {
+        double a[4], b[4], d0[4], d1[4];
+        double* cp[4];
+        bool wr0[4], wr1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = t0 + u * FACT_WARPS;
+          const bool live = t < ntile;
+          const int I = live ? tl[2 * t] : T, J = live ? tl[2 * t + 1] : 0;
+          const int ra = 8 * I + g, rb = 8 * J + g;
+          const bool arow = live && ra >= base && !(I == T && g > 0);   // rows above the trailing block / padding rows past nu: nothing
+          a[u] = arow ? -A[ra * FLD + p + t4] : 0.0;
+          b[u] = (live && rb >= base) ? A[rb * FLD + p + t4] : 0.0;
+          cp[u] = A + ra * FLD + 8 * J + 2 * t4;
           const int col = 8 * J + 2 * t4;
-          if (col >= base) cp[0] = d0;
-          if (col + 1 >= base) cp[1] = d1;
+          // finished entries (pivot rows / panel columns inside a boundary tile) are left alone: thread 0 is
+          // writing the pivot block's final values concurrently
+          wr0[u] = arow && col >= base;
+          wr1[u] = arow && col + 1 >= base;
+          d0[u] = live ? cp[u][0] : 0.0;
+          d1[u] = live ? cp[u][1] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dmma884f(d0[u], d1[u], a[u], b[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (wr0[u]) cp[u][0] = d0[u];
+          if (wr1[u]) cp[u][1] = d1[u];
         }
       }
     }
+    FACC(4);
     __syncthreads();
+    FACC(5);
   }
   // inverses of the diagonal blocks: warp J solves X L_JJ^T = I by substitution, lane = row r of
   // X = L_JJ^-T, i.e. column r of L_JJ^-1
@@ -137,12 +168,15 @@ __device__ void cta_chol22(double* fsm, const double* Sb, int lds, const double*
 #pragma unroll
     for (int c = 0; c < 32; ++c) X[c * ldd + lane] = x[c];  // Dinv[c][r] = X[r][c]
   }
+  FACC(6);
   for (int e = tid; e < NB * NB; e += FACT_THREADS) {
     const int r = e / NB, c = e - r * NB;
     Lout[(size_t)r * ldl + c] = (c <= r) ? A[r * FLD + c] : 0.0;
   }
   for (int e = tid; e < NB; e += FACT_THREADS) yout[e] = A[NB * FLD + e];
   __syncthreads();
+  FACC(7);
+  FACC_DUMP;
 }
 
 // V = W L^-T for one 8-row tile owned by ONE warp, in place in shared memory (blocked triangular solve):

@@ -13,11 +13,9 @@
 
 #include "ekf_kernels.h"
 
-#define GT_M 128
 #define GT_N 64
 #define GT_K 16
 #define GT_LD 20
-#define GT_STAGES 3
 #define GT_THREADS 128
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
@@ -41,7 +39,8 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // Two CTAs per SM (128 threads, 92 KB smem each) overlap one tile's C traffic with the other's DMMAs.
 // lower_only: skip tiles entirely above the diagonal and mirror the strictly-lower elements into
 // the upper triangle (C symmetric on input => symmetric on output).
-__global__ void __launch_bounds__(GT_THREADS, 2)
+template <int GT_M, int GT_STAGES, int MINB>
+__global__ void __launch_bounds__(GT_THREADS, MINB)
 k_gemm_nt_sub(double* __restrict__ C, int ldc, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
               int M, int N, int kconst, const int* __restrict__ kdev, int lower_only, unsigned stagger_ns) {
   extern __shared__ __align__(16) double gsm[];
@@ -59,7 +58,8 @@ k_gemm_nt_sub(double* __restrict__ C, int ldc, const double* __restrict__ A, int
   double* As = gsm;                                   // [stages][GT_M][GT_LD]
   double* Bs = gsm + GT_STAGES * GT_M * GT_LD;        // [stages][GT_N][GT_LD]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 1, wn = warp & 1;            // 2 x 2 warps, each 64 x 32
+  const int wm = warp >> 1, wn = warp & 1;            // 2 x 2 warps, each (GT_M / 2) x 32
+  constexpr int WR = GT_M / 2, WI = GT_M / 16;        // warp tile rows, 8-row DMMA tiles per warp
   const int g = lane >> 2, t4 = lane & 3;
 
   const int ktiles = (K + GT_K - 1) / GT_K;
@@ -90,10 +90,10 @@ k_gemm_nt_sub(double* __restrict__ C, int ldc, const double* __restrict__ A, int
     cp_async_commit();
   }
   // accumulators <- C tile
-  double acc[8][4][2];
+  double acc[WI][4][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = m0 + wm * 64 + i * 8 + g;
+  for (int i = 0; i < WI; ++i) {
+    const int r = m0 + wm * WR + i * 8 + g;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = n0 + wn * 32 + j * 8 + 2 * t4;
@@ -106,25 +106,25 @@ k_gemm_nt_sub(double* __restrict__ C, int ldc, const double* __restrict__ A, int
   // warps whose 64 x 32 sub-tile lies outside the matrix, or (lower_only) entirely above the
   // diagonal, skip the tensor work (they still help with the loads): edge and diagonal tiles cost
   // half, which also removes most of the last partial wave.
-  const bool warp_active = (m0 + wm * 64 < M) && (n0 + wn * 32 < N) && !(lower_only && (n0 + wn * 32 > m0 + wm * 64 + 63));
+  const bool warp_active = (m0 + wm * WR < M) && (n0 + wn * 32 < N) && !(lower_only && (n0 + wn * 32 > m0 + wm * WR + WR - 1));
   for (int kt = 0; kt < ktiles; ++kt) {
     cp_async_wait<GT_STAGES - 2>();
     __syncthreads();
     const int nk = kt + GT_STAGES - 1;
     if (nk < ktiles) load_stage(nk, nk % GT_STAGES);
     cp_async_commit();
-    const double* as = As + (size_t)(kt % GT_STAGES) * GT_M * GT_LD + (size_t)(wm * 64 + g) * GT_LD + t4;
+    const double* as = As + (size_t)(kt % GT_STAGES) * GT_M * GT_LD + (size_t)(wm * WR + g) * GT_LD + t4;
     const double* bs = Bs + (size_t)(kt % GT_STAGES) * GT_N * GT_LD + (size_t)(wn * 32 + g) * GT_LD + t4;
     if (warp_active)
 #pragma unroll
     for (int k4 = 0; k4 < GT_K / 4; ++k4) {
-      double af[8], bf[4];
+      double af[WI], bf[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) af[i] = as[(size_t)i * 8 * GT_LD + k4 * 4];
+      for (int i = 0; i < WI; ++i) af[i] = as[(size_t)i * 8 * GT_LD + k4 * 4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) bf[j] = -bs[(size_t)j * 8 * GT_LD + k4 * 4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < WI; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
@@ -132,8 +132,8 @@ k_gemm_nt_sub(double* __restrict__ C, int ldc, const double* __restrict__ A, int
   cp_async_wait<0>();
   // epilogue: store.  Thread holds rows g (+8 i), column pairs 2*t4 (+8 j).
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = m0 + wm * 64 + i * 8 + g;
+  for (int i = 0; i < WI; ++i) {
+    const int r = m0 + wm * WR + i * 8 + g;
     if (r >= M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -158,22 +158,36 @@ k_gemm_nt_sub(double* __restrict__ C, int ldc, const double* __restrict__ A, int
   }
 }
 
-static const size_t kGemmSmem = (size_t)GT_STAGES * (GT_M + GT_N) * GT_LD * sizeof(double);
-
-int launch_gemm_nt_sub(cudaStream_t st, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M, int N,
-                       int kconst, const int* kdev, int lower_only, int* counters, long long* launches) {
-  (void)counters;
+template <int GT_M, int GT_STAGES, int MINB>
+static int launch_variant(cudaStream_t st, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M, int N,
+                          int kconst, const int* kdev, int lower_only, unsigned stagger) {
+  constexpr size_t smem = (size_t)GT_STAGES * (GT_M + GT_N) * GT_LD * sizeof(double);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_nt_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_nt_sub<GT_M, GT_STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  if (M <= 0 || N <= 0) return 0;
   dim3 grid((N + GT_N - 1) / GT_N, (M + GT_M - 1) / GT_M);
-  static int stagger = -1;
+  k_gemm_nt_sub<GT_M, GT_STAGES, MINB><<<grid, GT_THREADS, smem, st>>>(C, ldc, A, lda, B, ldb, M, N, kconst, kdev, lower_only, stagger);
+  return 0;
+}
+
+// Tile shape: 128 x 64 (2 CTAs / SM, 64 accumulators per thread) is the most efficient per tile and is
+// used for full-square / row-block launches; in lower-triangle mode the tile count decides — 64 x 64
+// tiles at 4 CTAs / SM split the triangle into about twice as many, twice as short tiles, which packs the
+// 148 x 4 slots with less than a few percent of the last wave idle (EKF_GEMM_TM=128 forces the large tile).
+int launch_gemm_nt_sub(cudaStream_t st, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M, int N,
+                       int kconst, const int* kdev, int lower_only, int* counters, long long* launches) {
+  (void)counters;
+  if (M <= 0 || N <= 0) return 0;
+  static int stagger = -1, force_tm = -1;
   if (stagger < 0) { const char* e = getenv("EKF_GEMM_STAGGER_NS"); stagger = e ? atoi(e) : 0; }
-  k_gemm_nt_sub<<<grid, GT_THREADS, kGemmSmem, st>>>(C, ldc, A, lda, B, ldb, M, N, kconst, kdev, lower_only, (unsigned)stagger);
+  if (force_tm < 0) { const char* e = getenv("EKF_GEMM_TM"); force_tm = e ? atoi(e) : 0; }
+  const bool small_tile = force_tm ? (force_tm == 64) : (lower_only != 0);
+  const int rc = small_tile ? launch_variant<64, 2, 4>(st, C, ldc, A, lda, B, ldb, M, N, kconst, kdev, lower_only, (unsigned)stagger)
+                            : launch_variant<128, 3, 2>(st, C, ldc, A, lda, B, ldb, M, N, kconst, kdev, lower_only, (unsigned)stagger);
+  if (rc) return rc;
   if (launches) *launches += 1;
   return 0;
 }
