@@ -36,8 +36,8 @@ __device__ __forceinline__ void dmma884f(double& d0, double& d1, double a, doubl
 // shared-memory doubles needed by cta_chol22<NB>
 template <int NB>
 __host__ __device__ constexpr int cta_chol22_smem_doubles() {
-  // A[(NB + 8)][NB + 1] + pivot reciprocals[NB] + tile list (2 bytes per tile, T (T + 1) / 2 + T tiles)
-  return (NB + 8) * (NB + 1) + NB + (((NB / 8) * (NB / 8 + 1) / 2 + NB / 8) * 2 + 7) / 8;
+  // A[(NB + 8)][NB + 8] + pivot reciprocals[NB] + tile list (2 bytes per tile, T (T + 1) / 2 + T tiles)
+  return (NB + 8) * (NB + 8) + NB + (((NB / 8) * (NB / 8 + 1) / 2 + NB / 8) * 2 + 7) / 8;
 }
 
 // fsm: workspace (see above).  Sb: NB x NB symmetric positive definite (leading dimension lds; only
@@ -54,7 +54,9 @@ __host__ __device__ constexpr int cta_chol22_smem_doubles() {
 template <int NB>
 __device__ void cta_chol22(double* fsm, const double* Sb, int lds, const double* nu, double* Lout, int ldl, double* Dout,
                            int ldd, double* yout, int* chol_fail) {
-  constexpr int NP = NB / 32, FLD = NB + 1, T = NB / 8;
+  // row stride = 8 (mod 16) doubles: the C-tile accesses of the rank-4 update are 16-byte vectors without bank
+  // conflicts and the A/B fragment loads 2-way; an odd stride made every access 4-way conflicted (smem-bound)
+  constexpr int NP = NB / 32, FLD = NB + 8, T = NB / 8;
   double* A = fsm;                      // [(NB + 8)][FLD]: rows 0..NB-1 S / L, row NB nu / y, rows NB+1.. padding
   double* rinvs = A + (NB + 8) * FLD;   // [NB]
   // tile list ordered by tile column J descending: the tiles of a trailing block that starts at tile
@@ -136,15 +138,16 @@ __device__ void cta_chol22(double* fsm, const double* Sb, int lds, const double*
           // writing the pivot block's final values concurrently
           wr0[u] = arow && col >= base;
           wr1[u] = arow && col + 1 >= base;
-          d0[u] = live ? cp[u][0] : 0.0;
-          d1[u] = live ? cp[u][1] : 0.0;
+          const double2 cv = live ? *reinterpret_cast<const double2*>(cp[u]) : make_double2(0.0, 0.0);
+          d0[u] = cv.x; d1[u] = cv.y;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) dmma884f(d0[u], d1[u], a[u], b[u]);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (wr0[u]) cp[u][0] = d0[u];
-          if (wr1[u]) cp[u][1] = d1[u];
+          if (wr0[u] && wr1[u]) *reinterpret_cast<double2*>(cp[u]) = make_double2(d0[u], d1[u]);
+          else if (wr0[u]) cp[u][0] = d0[u];
+          else if (wr1[u]) cp[u][1] = d1[u];
         }
       }
     }
