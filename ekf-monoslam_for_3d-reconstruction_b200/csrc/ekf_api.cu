@@ -3,6 +3,7 @@
 // CUDA device and fails with EKF_ERR_CUDA otherwise.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -28,14 +29,14 @@ static cudaEvent_t prof_event(ekf_handle* h) {
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 struct ProfScope {
-  ekf_handle* h; int cls; long long l0; cudaEvent_t a;
-  ProfScope(ekf_handle* hh, int c) : h(hh), cls(c), l0(hh->launches), a(nullptr) {
-    if (h->prof_on) { a = prof_event(h); cudaEventRecord(a, h->stream); }
+  ekf_handle* h; int cls; long long l0; cudaEvent_t a; cudaStream_t s;
+  ProfScope(ekf_handle* hh, int c, cudaStream_t st = nullptr) : h(hh), cls(c), l0(hh->launches), a(nullptr), s(st ? st : hh->stream) {
+    if (h->prof_on) { a = prof_event(h); cudaEventRecord(a, s); }
   }
   ~ProfScope() {
     if (h->prof_on) {
       cudaEvent_t b = prof_event(h);
-      cudaEventRecord(b, h->stream);
+      cudaEventRecord(b, s);
       h->prof_pending.push_back({cls, (int)(h->launches - l0), a, b});
     }
   }
@@ -101,6 +102,11 @@ int ekf_destroy(ekf_handle* h) {
   cudaFree(h->Lb); cudaFree(h->Dinv); cudaFree(h->Dblk); cudaFree(h->yb); cudaFree(h->delta); cudaFree(h->mu_i); cudaFree(h->cand);
   cudaFree(h->map_dev); cudaFree(h->keep_dev); cudaFree(h->newpos_dev); cudaFree(h->ctl); cudaFree(h->frame);
   cudaFree(h->picks_dev); cudaFree(h->out_dev); cudaFree(h->gemm_counters);
+  if (h->gemm_stream) { cudaStreamSynchronize(h->gemm_stream); cudaStreamDestroy(h->gemm_stream); }
+  cudaFree(h->Wbuf[1]); cudaFree(h->Wbuf[2]); cudaFree(h->Gbuf);
+  for (int i = 0; i < 3; ++i) { if (h->ev_gather[i]) cudaEventDestroy(h->ev_gather[i]); if (h->ev_V[i]) cudaEventDestroy(h->ev_V[i]); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   cudaFree(h->xyz_flag); cudaFree(h->xyz_rmap); cudaFree(h->xyz_pos); cudaFree(h->xyz_coding); cudaFree(h->xyz_y); cudaFree(h->xyz_J);
   if (h->out_host) cudaFreeHost(h->out_host);
   free_feattab(h->ft); free_feattab(h->ftB);
@@ -145,6 +151,23 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
   TRY(dalloc(&h->Dinv, EKF_UB * EKF_UB)) TRY(dalloc(&h->Dblk, EKF_UB * 32)) TRY(dalloc(&h->yb, EKF_UB)) TRY(dalloc(&h->delta, h->ld + EKF_DIST_PAD_ROWS)) TRY(dalloc(&h->mu_i, h->ld))
   TRY(dalloc(&h->cand, h->Ncap)) TRY(dalloc(&h->map_dev, h->ncap)) TRY(dalloc(&h->keep_dev, h->Ncap))
   TRY(dalloc(&h->newpos_dev, h->Ncap)) TRY(dalloc(&h->ctl, 1)) TRY(dalloc(&h->gemm_counters, 2))
+  h->Wbuf[0] = h->W;
+  TRY(dalloc(&h->Wbuf[1], (size_t)(h->ncap + 1) * EKF_UB)) TRY(dalloc(&h->Wbuf[2], (size_t)(h->ncap + 1) * EKF_UB))
+  TRY(dalloc(&h->Gbuf, EKF_UB * EKF_UB))
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = least priority
+    TRY(cudaStreamCreateWithPriority(&h->gemm_stream, cudaStreamNonBlocking, lo))
+    for (int i = 0; i < 3; ++i) {
+      TRY(cudaEventCreateWithFlags(&h->ev_gather[i], cudaEventDisableTiming)) TRY(cudaEventCreateWithFlags(&h->ev_V[i], cudaEventDisableTiming))
+    }
+    TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming))
+    // look-ahead pays off once the downdate of a block (n x n x 128) is long against the block's gain chain:
+    // measured +27 % at n = 11972, -7 % at n = 3014 (the chain kernels' large shared-memory CTAs cannot be
+    // co-scheduled with the downdate's while it is short); EKF_LOOKAHEAD_MIN_N overrides the threshold
+    const char* e = getenv("EKF_LOOKAHEAD_MIN_N");
+    h->lookahead = e ? atoi(e) : 6000;
+  }
   TRY(dalloc(&h->xyz_flag, h->Ncap)) TRY(dalloc(&h->xyz_rmap, 2 * (size_t)h->ncap)) TRY(dalloc(&h->xyz_pos, h->Ncap))
   TRY(dalloc(&h->xyz_coding, h->Ncap)) TRY(dalloc(&h->xyz_y, 3 * (size_t)h->Ncap)) TRY(dalloc(&h->xyz_J, 18 * (size_t)h->Ncap))
   TRY(alloc_feattab(h->ft, h->Ncap, w2)) TRY(alloc_feattab(h->ftB, h->Ncap, w2))
@@ -389,8 +412,66 @@ static int convert_xyz(ekf_handle* h, int only) {
 }
 
 // One stacked update over `cnt` selected features (ft.sel), block by block (see ekf_update.cu).
+// Stacked update with one block of look-ahead.  The chain of block b+1 (gain: S, Cholesky, V) does not
+// wait for the full covariance downdate of block b: W_{b+1} = Sigma_b H^T is formed as
+//     W'_{b+1} - V_b (H_{b+1} V_b)^T,   W'_{b+1} gathered from Sigma_{b-1}
+// (one n x 128 x 128 correction GEMM instead of the n x n x 128 downdate on the critical path), while the
+// downdate Sigma -= V_b V_b^T and the next gather run on a second, low-priority stream beside the
+// single-CTA Cholesky.  Same arithmetic per element up to the order of the two subtractions.
+static int stacked_update_lookahead(ekf_handle* h, int cnt) {
+  cudaStream_t sm = h->stream, sg = h->gemm_stream;
+  const int nblk = (cnt + EKF_UB / 2 - 1) / (EKF_UB / 2);
+  cudaMemsetAsync(h->delta, 0, sizeof(double) * (size_t)h->n, sm);
+  cudaEventRecord(h->ev_fork, sm);
+  cudaStreamWaitEvent(sg, h->ev_fork, 0);
+  for (int b = 0; b < nblk && b < 2; ++b) {
+    ProfScope ps(h, 3, sg);
+    launch_blk_gather(sg, h->Sigma, h->ld, 0, h->n, h->ft, b * (EKF_UB / 2), cnt, nullptr, h->Wbuf[b], nullptr, &h->launches);
+    cudaEventRecord(h->ev_gather[b], sg);
+  }
+  for (int b = 0; b < nblk; ++b) {
+    const int f0 = b * (EKF_UB / 2);
+    double* Wb = h->Wbuf[b % 3];
+    cudaStreamWaitEvent(sm, h->ev_gather[b % 3], 0);
+    if (b > 0) {
+      ProfScope ps(h, 3);
+      double* Vp = h->Wbuf[(b - 1) % 3];
+      launch_blk_G(sm, Vp, h->ft, f0, cnt, h->Gbuf, &h->launches);
+      const int rc = launch_gemm_nt_sub(sm, Wb, EKF_UB, Vp, EKF_UB, h->Gbuf, EKF_UB, h->n, EKF_UB, EKF_UB, nullptr, 0, h->gemm_counters, &h->launches);
+      if (rc) return rc;
+    }
+    {
+      ProfScope ps(h, 4);
+      launch_blk_S_nu(sm, Wb, h->ft, f0, cnt, h->dcfg, h->delta, h->Lb, h->nu, &h->launches);
+      launch_blk_factor_only(sm, h->Lb, h->nu, h->Dinv, h->Dblk, h->yb, h->ctl, &h->launches);
+    }
+    { ProfScope ps(h, 5); launch_blk_V(sm, Wb, 0, h->n, h->Dinv, h->Dblk, h->yb, h->delta, &h->launches); }
+    cudaEventRecord(h->ev_V[b % 3], sm);
+    cudaStreamWaitEvent(sg, h->ev_V[b % 3], 0);
+    {
+      ProfScope ps(h, 6, sg);
+      const int rc = launch_gemm_nt_sub(sg, h->Sigma, h->ld, Wb, EKF_UB, Wb, EKF_UB, h->n, h->n, EKF_UB, nullptr, h->lower_only, h->gemm_counters, &h->launches);
+      if (rc) return rc;
+    }
+    if (b + 2 < nblk) {
+      ProfScope ps(h, 3, sg);
+      launch_blk_gather(sg, h->Sigma, h->ld, 0, h->n, h->ft, (b + 2) * (EKF_UB / 2), cnt, nullptr, h->Wbuf[(b + 2) % 3], nullptr, &h->launches);
+      cudaEventRecord(h->ev_gather[(b + 2) % 3], sg);
+    }
+  }
+  cudaEventRecord(h->ev_join, sg);
+  cudaStreamWaitEvent(sm, h->ev_join, 0);
+  {
+    ProfScope ps(h, 7);
+    launch_apply_delta(sm, h->mu, h->delta, h->n, &h->launches);
+    launch_quat_normalize(sm, h->Sigma, h->ld, h->n, h->mu, h->ctl, &h->launches);
+  }
+  return 0;
+}
+
 static int stacked_update(ekf_handle* h, int cnt) {
   if (cnt <= 0) return 0;
+  if (h->lookahead > 0 && h->n >= h->lookahead && !(h->nccl_comm && h->world > 1) && cnt > EKF_UB / 2) return stacked_update_lookahead(h, cnt);
   cudaStream_t st = h->stream;
   // Row-block partition (BASELINE config 4): every rank holds a replica of Sigma, updates only its
   // rows [r0, r1) and exchanges the small panels: W_b rows (S_b needs the camera / feature rows of W_b),

@@ -37,6 +37,12 @@ struct ekf_handle {
   int patchnumbre = 1, noise_cov_factor = 0;
   bool predicted = false, have_frame = false;
   int lower_only = 0;
+  // look-ahead pipeline of the stacked update (ekf_api.cu::stacked_update_lookahead)
+  cudaStream_t gemm_stream = nullptr;
+  double* Wbuf[3] = {nullptr, nullptr, nullptr};   // Wbuf[0] == W
+  double* Gbuf = nullptr;
+  cudaEvent_t ev_gather[3] = {nullptr, nullptr, nullptr}, ev_V[3] = {nullptr, nullptr, nullptr}, ev_fork = nullptr, ev_join = nullptr;
+  int lookahead = 6000;   // minimum state dimension for the look-ahead pipeline (0 = never)
   // row-block partitioned update across ranks (ekf_dist.cu): NCCL communicator of this handle, or null
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;

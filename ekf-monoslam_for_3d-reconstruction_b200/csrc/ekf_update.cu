@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ S
     }
     reinterpret_cast<double2*>(W + (size_t)i * EKF_UB)[a] = make_double2(w0, w1);
   }
-  if (blockIdx.x == 0 && tid < EKF_UB / 2) {
+  if (nu && blockIdx.x == 0 && tid < EKF_UB / 2) {
     double v0 = 0, v1 = 0;
     if (tid < nb) {
       const int f = fids[tid];
@@ -156,27 +156,37 @@ __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ S
 // a partial block are identity so they contribute nothing downstream.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(EKF_UB) k_blk_S(const double* __restrict__ W, FeatTab ft, int f0, int cnt,
-                                                  double sigma_pixel_2, double* __restrict__ Sb) {
+                                                  double sigma_pixel_2, double* __restrict__ Sb, int plain,
+                                                  const double* __restrict__ delta, double* __restrict__ nu) {
+  // plain == 0: S_b = H_b W + sigma_px^2 I (identity past the block's rows).
+  // plain != 0: G = H_b W with zero padding — W then holds the PREVIOUS block's V (look-ahead correction).
+  // nu != null: CTA 0 also forms nu_b = (z - h) - H_b delta.
   const int r = blockIdx.x, s = threadIdx.x;
   const int nb = min(EKF_UB / 2, cnt - f0), kr = 2 * nb;
-  double v = (r == s) ? 1.0 : 0.0;
-  if (r < kr && s < kr) {
+  double v = (!plain && r == s) ? 1.0 : 0.0;
+  if (r < kr && (plain || s < kr)) {
     const int f = ft.sel[f0 + (r >> 1)];
     const int pos = ft.pos[f], nd = 7 + (ft.coding[f] ? 3 : 6);
     const double* hc = ft.Hc + 26 * f + 13 * (r & 1);
     double acc = 0;
     for (int c = 0; c < nd; ++c) acc += hc[c] * W[(size_t)ekf_idx13(c, pos) * EKF_UB + s];
-    v = acc + ((r == s) ? sigma_pixel_2 : 0.0);
+    v = acc + ((!plain && r == s) ? sigma_pixel_2 : 0.0);
   }
   Sb[r * EKF_UB + s] = v;
+  if (nu && r == 0) {
+    double out = 0.0;
+    if (s < kr) {
+      const int f = ft.sel[f0 + (s >> 1)];
+      const int pos = ft.pos[f], nd = 7 + (ft.coding[f] ? 3 : 6);
+      const double* hc = ft.Hc + 26 * f + 13 * (s & 1);
+      double hd = 0;
+      for (int c = 0; c < nd; ++c) hd += hc[c] * delta[ekf_idx13(c, pos)];
+      out = (ft.z[2 * f + (s & 1)] - ft.h[2 * f + (s & 1)]) - hd;
+    }
+    nu[s] = out;
+  }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K4b(2): Cholesky S_b = L L^T in shared memory (one CTA, right-looking, one barrier pair per
-// column), then Linv = L^-1 by 32x32 blocks (diagonal blocks by substitution, off-diagonal blocks
-// Linv[J][I] = -Dinv_J sum_P L[J][P] Linv[P][I], parked transposed in the unused upper triangle) and
-// y = Linv nu.  Outputs Linv (row-major, zero above the diagonal) and y.
-// ------------------------------------------------------------------------------------------------
 #include "ekf_factor.cuh"
 __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __restrict__ Sb, const double* __restrict__ nu,
                                                              double* __restrict__ Lout, double* __restrict__ Dblk,
@@ -301,9 +311,24 @@ void launch_blk_gather(cudaStream_t st, const double* Sigma, int ld, int row0, i
 }
 void launch_blk_factor(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const double* nu, const DevCfg& cfg,
                        double* Sb, double* Lb, double* Dblk, double* yb, DevCtl* ctl, long long* launches) {
-  k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(W, ft, f0, cnt, cfg.sigma_pixel_2, Sb);
+  k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(W, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, nullptr, nullptr);
   k_blk_factor<<<1, FACT_THREADS, kFactSmem, st>>>(Sb, nu, Lb, Dblk, yb, ctl);
   *launches += 2;
+}
+// look-ahead variants: S_b together with nu_b (delta is current only now), and G = H_b V_prev
+void launch_blk_S_nu(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const DevCfg& cfg, const double* delta,
+                     double* Sb, double* nu, long long* launches) {
+  k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(W, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, delta, nu);
+  *launches += 1;
+}
+void launch_blk_G(cudaStream_t st, const double* Vprev, FeatTab ft, int f0, int cnt, double* G, long long* launches) {
+  k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(Vprev, ft, f0, cnt, 0.0, G, 1, nullptr, nullptr);
+  *launches += 1;
+}
+void launch_blk_factor_only(cudaStream_t st, const double* Sb, const double* nu, double* Lb, double* Dblk, double* yb, DevCtl* ctl,
+                            long long* launches) {
+  k_blk_factor<<<1, FACT_THREADS, kFactSmem, st>>>(Sb, nu, Lb, Dblk, yb, ctl);
+  *launches += 1;
 }
 void launch_blk_V(cudaStream_t st, double* W, int row0, int row1, const double* Lb, const double* Dblk, const double* yb,
                   double* delta, long long* launches) {
