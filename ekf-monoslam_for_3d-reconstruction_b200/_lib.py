@@ -30,6 +30,8 @@ SIGNATURES = {
     "ekf_inject_match": (_i, [_vp, _i, _d, _d, _i]),
     "ekf_add_feature": (_i, [_vp, _f, _f]),
     "ekf_remove_feature": (_i, [_vp, _i]),
+    "ekf_find_new_features": (_i, [_vp, _i]),
+    "ekf_detect_corners": (_i, [_vp, _i, _vp, _P(_i)]),
     "ekf_convert2xyz_if_linear": (_i, [_vp, _i]),
     "ekf_convert2xyz_if_linear_all": (_i, [_vp]),
     "ekf_num_features": (_i, [_vp]),

@@ -107,6 +107,7 @@ int ekf_destroy(ekf_handle* h) {
   for (int i = 0; i < 3; ++i) { if (h->ev_gather[i]) cudaEventDestroy(h->ev_gather[i]); if (h->ev_V[i]) cudaEventDestroy(h->ev_V[i]); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  cudaFree(h->det_mask); cudaFree(h->det_eig); cudaFree(h->det_keys); cudaFree(h->det_counters); cudaFree(h->det_xy);
   cudaFree(h->xyz_flag); cudaFree(h->xyz_rmap); cudaFree(h->xyz_pos); cudaFree(h->xyz_coding); cudaFree(h->xyz_y); cudaFree(h->xyz_J);
   if (h->out_host) cudaFreeHost(h->out_host);
   free_feattab(h->ft); free_feattab(h->ftB);
@@ -588,7 +589,9 @@ int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
       if (rc) return rc;
       h->stats.n_removed += 1;
     }
-    h->stats.topup_request = h->cfg.min_features - nvis;  // findNewFeatures(...) is the caller's job
+    h->stats.topup_request = h->cfg.min_features - nvis;
+    rc = ekf_find_new_features(h, h->stats.topup_request);   // vslamRansac.cpp:1314
+    if (rc < 0) return rc;
   }
   if (h->cfg.xyz_conversion) {  // V:1317
     rc = convert_xyz(h, -1);
@@ -646,6 +649,71 @@ int ekf_remove_feature(ekf_handle* h, int index) {
   if (!h || index < 0 || index >= h->N) return EKF_ERR_ARG;
   EKF_CUDA_CHECK(cudaSetDevice(h->device));
   return remove_features(h, std::vector<int>{index});
+}
+
+#define EKF_DET_KEYS 65536
+#define EKF_DET_MAX 1024
+// goodFeaturesToTrack(frame, corners, num, 0.01, 12, mask) with the reference's mask (vslamRansac.cpp:788-831)
+static int detect_corners(ekf_handle* h, int num, std::vector<float>& xy) {
+  xy.clear();
+  if (!h->have_frame) return ekf_fail(h, EKF_ERR_STATE, "findNewFeatures before captureNewFrame");
+  if (num <= 0) num = h->cfg.nInitFeatures;   // vslamRansac.cpp:786
+  if (num > EKF_DET_MAX) num = EKF_DET_MAX;
+  const size_t px = (size_t)h->fv.w * h->fv.h;
+  cudaStream_t st = h->stream;
+  if (px > h->det_cap) {
+    EKF_CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(h->det_mask); cudaFree(h->det_eig);
+    h->det_mask = nullptr; h->det_eig = nullptr;
+    EKF_CUDA_CHECK(cudaMalloc((void**)&h->det_mask, px));
+    EKF_CUDA_CHECK(cudaMalloc((void**)&h->det_eig, px * sizeof(float)));
+    h->det_cap = px;
+  }
+  if (!h->det_keys) {
+    EKF_CUDA_CHECK(cudaMalloc((void**)&h->det_keys, sizeof(unsigned long long) * EKF_DET_KEYS));
+    EKF_CUDA_CHECK(cudaMalloc((void**)&h->det_counters, 4 * sizeof(int)));
+    EKF_CUDA_CHECK(cudaMalloc((void**)&h->det_xy, 2 * EKF_DET_MAX * sizeof(float)));
+  }
+  launch_detect_corners(st, h->fv, h->ft, h->N, h->cfg.window_size, h->det_mask, h->det_eig, h->det_keys, EKF_DET_KEYS, h->det_counters,
+                        num, h->det_xy, &h->launches);
+  EKF_CUDA_CHECK(cudaGetLastError());
+  int counters[4];
+  EKF_CUDA_CHECK(cudaMemcpyAsync(counters, h->det_counters, sizeof counters, cudaMemcpyDeviceToHost, st));
+  EKF_CUDA_CHECK(cudaStreamSynchronize(st));
+  const int n = counters[2];
+  xy.resize(2 * (size_t)n);
+  if (n > 0) {
+    EKF_CUDA_CHECK(cudaMemcpyAsync(xy.data(), h->det_xy, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, st));
+    EKF_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  return EKF_OK;
+}
+
+int ekf_detect_corners(ekf_handle* h, int num, float* out_xy, int* out_n) {
+  if (!h || !out_xy || !out_n) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  std::vector<float> xy;
+  const int rc = detect_corners(h, num, xy);
+  if (rc) return rc;
+  *out_n = (int)(xy.size() / 2);
+  for (size_t i = 0; i < xy.size(); ++i) out_xy[i] = xy[i];
+  return EKF_OK;
+}
+
+int ekf_find_new_features(ekf_handle* h, int num) {
+  if (!h) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  std::vector<float> xy;
+  int rc = detect_corners(h, num, xy);
+  if (rc) return rc;
+  int added = 0;
+  for (size_t i = 0; i + 1 < xy.size(); i += 2) {   // vslamRansac.cpp:832-835
+    if (h->N >= h->Ncap) break;
+    rc = ekf_add_feature(h, xy[i], xy[i + 1]);
+    if (rc < 0) return rc;
+    added += rc;
+  }
+  return added;
 }
 
 int ekf_convert2xyz_if_linear(ekf_handle* h, int index) {

@@ -37,6 +37,9 @@ struct ekf_handle {
   int patchnumbre = 1, noise_cov_factor = 0;
   bool predicted = false, have_frame = false;
   int lower_only = 0;
+  // corner detector scratch (ekf_detect.cu), sized to the frame on first use
+  uint8_t* det_mask = nullptr; float* det_eig = nullptr; unsigned long long* det_keys = nullptr; int* det_counters = nullptr;
+  float* det_xy = nullptr; size_t det_cap = 0;
   // look-ahead pipeline of the stacked update (ekf_api.cu::stacked_update_lookahead)
   cudaStream_t gemm_stream = nullptr;
   double* Wbuf[3] = {nullptr, nullptr, nullptr};   // Wbuf[0] == W

@@ -50,3 +50,6 @@ void launch_bookkeeping(cudaStream_t st, const double* Sigma, int ld, const doub
 // ekf_gemm.cu
 int launch_gemm_nt_sub(cudaStream_t st, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M, int N,
                        int kconst, const int* kdev, int lower_only, int* counters, long long* launches);
+// ekf_detect.cu
+int launch_detect_corners(cudaStream_t st, FrameView fr, FeatTab ft, int N, int window, uint8_t* mask, float* eig,
+                          unsigned long long* keys, int key_cap, int* counters, int max_corners, float* out_xy, long long* launches);

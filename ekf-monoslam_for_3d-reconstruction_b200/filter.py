@@ -86,6 +86,15 @@ class VSlamFilter:
     def removeFeature(self, i):
         self._ck(self.L.ekf_remove_feature(self.h, int(i)))
 
+    def findNewFeatures(self, num=-1):
+        """vslamRansac.cpp:783-839; returns the number of features added."""
+        return self._ck(self.L.ekf_find_new_features(self.h, int(num)))
+
+    def detect_corners(self, num):
+        out = np.zeros((1024, 2), dtype=np.float32); n = C.c_int(0)
+        self._ck(self.L.ekf_detect_corners(self.h, int(num), _ptr(out), C.byref(n)))
+        return out[:n.value].copy()
+
     def convert2XYZ_ifLinear(self, i):
         """vslamRansac.cpp:741-772."""
         self._ck(self.L.ekf_convert2xyz_if_linear(self.h, int(i)))

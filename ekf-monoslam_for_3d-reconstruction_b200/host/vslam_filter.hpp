@@ -56,8 +56,8 @@ class VSlamFilter {
   float Covariance_Parameter() { double p = 0; ck(ekf_covariance_parameter(h_, &p)); return (float)p; }          // :841
   Point2f returnCentrPatchIndx(int i) { float c[2]; ck(ekf_get_center(h_, i, c)); return Point2f{c[0], c[1]}; }  // vslamRansac.hpp:136
   double getDt() { return ekf_get_dt(h_); }                                                                      // :247
-  // findNewFeatures(num) (:783) relies on OpenCV goodFeaturesToTrack: the caller detects corners and
-  // calls addFeature; topupRequest() is the `num` the reference would have asked for (:1314).
+  int findNewFeatures(int num = -1) { return ck(ekf_find_new_features(h_, num)); }                              // :783
+  // the `num` update() passed to findNewFeatures in its last call (:1314), 0 if it did not top up
   int topupRequest() { ekf_step_stats s; ck(ekf_get_step_stats(h_, &s)); return s.topup_request; }
 
   // what RosVSLAM reads from the protected members (RosVSLAMRansac.cpp:19-21,68,114,177-183)

@@ -87,7 +87,7 @@ typedef struct ekf_step_stats {
   int32_t n_li, n_hi;              /* rows/2 of the two updates */
   int32_t ransac_hypotheses;       /* loop trips of vslamRansac.cpp:986 */
   int32_t n_removed;               /* features dropped by vslamRansac.cpp:1296-1299 */
-  int32_t topup_request;           /* argument vslamRansac.cpp:1314 would pass to findNewFeatures */
+  int32_t topup_request;           /* argument passed to findNewFeatures at vslamRansac.cpp:1314 (0 = no top-up this step) */
   int32_t blur_requests;           /* always 0: blur is rejected at create time */
   int64_t kernel_launches;         /* kernels of this library launched on the handle so far */
 } ekf_step_stats;
@@ -134,6 +134,14 @@ int ekf_inject_match(ekf_handle* h, int idx, double zu, double zv, int accepted)
 int ekf_add_feature(ekf_handle* h, float u, float v);
 /* VSlamFilter::removeFeature (vslamRansac.cpp:373-421). */
 int ekf_remove_feature(ekf_handle* h, int index);
+/* VSlamFilter::findNewFeatures(num) (vslamRansac.cpp:783-839): builds the reference's mask around the
+ * existing patches, detects up to `num` (<= 0: nInitFeatures; capped at 1024) Shi-Tomasi corners with
+ * the parameters the reference passes to OpenCV goodFeaturesToTrack (quality 0.01, min distance 12,
+ * 3x3 block) and calls addFeature on each.  Returns the number added (>= 0) or an error.  The
+ * detector restates OpenCV's published algorithm; see csrc/ekf_detect.cu for the parity statement. */
+int ekf_find_new_features(ekf_handle* h, int num);
+/* The detection alone: up to `num` corners as (x, y) pairs into out_xy (capacity 2 * 1024 floats). */
+int ekf_detect_corners(ekf_handle* h, int num, float* out_xy, int* out_n);
 /* VSlamFilter::convert2XYZ_ifLinear / convert2XYZ_ifLinearAll (vslamRansac.cpp:741-780). */
 int ekf_convert2xyz_if_linear(ekf_handle* h, int index);
 int ekf_convert2xyz_if_linear_all(ekf_handle* h);
