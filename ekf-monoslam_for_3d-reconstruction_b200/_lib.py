@@ -22,6 +22,8 @@ SIGNATURES = {
     "ekf_sync": (_i, [_vp]),
     "ekf_last_error": (C.c_char_p, [_vp]),
     "ekf_capture_frame": (_i, [_vp, _vp, _i, _i, _i, _d]),
+    "ekf_capture_frame_bgr": (_i, [_vp, _vp, _i, _i, _i, _d]),
+    "ekf_get_frame": (_i, [_vp, _vp, _P(_i), _P(_i)]),
     "ekf_capture_frame_device": (_i, [_vp, _vp, _i, _i, _i, _d]),
     "ekf_predict": (_i, [_vp, _vp, _vp, _i]),
     "ekf_match": (_i, [_vp, _P(_i)]),

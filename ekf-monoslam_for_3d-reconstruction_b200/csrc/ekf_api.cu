@@ -100,7 +100,7 @@ int ekf_destroy(ekf_handle* h) {
   for (auto e : h->prof_pool) cudaEventDestroy(e);
   cudaFree(h->mu); cudaFree(h->muB); cudaFree(h->Sigma); cudaFree(h->SigmaB); cudaFree(h->W); cudaFree(h->nu);
   cudaFree(h->Lb); cudaFree(h->Dinv); cudaFree(h->Dblk); cudaFree(h->yb); cudaFree(h->delta); cudaFree(h->mu_i); cudaFree(h->cand);
-  cudaFree(h->map_dev); cudaFree(h->keep_dev); cudaFree(h->newpos_dev); cudaFree(h->ctl); cudaFree(h->frame);
+  cudaFree(h->map_dev); cudaFree(h->keep_dev); cudaFree(h->newpos_dev); cudaFree(h->ctl); cudaFree(h->frame); cudaFree(h->raw);
   cudaFree(h->picks_dev); cudaFree(h->out_dev); cudaFree(h->gemm_counters);
   if (h->gemm_stream) { cudaStreamSynchronize(h->gemm_stream); cudaStreamDestroy(h->gemm_stream); }
   cudaFree(h->Wbuf[1]); cudaFree(h->Wbuf[2]); cudaFree(h->Gbuf);
@@ -121,7 +121,7 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
   *out = nullptr;
   // parts of the reference outside this path are rejected, never emulated on the CPU
   if (cfg->kernel_size < 100000) return EKF_ERR_UNSUPPORTED;   // motion-blur templates (libblur.cpp)
-  if (cfg->scale != 1) return EKF_ERR_UNSUPPORTED;             // cv::resize in captureNewFrame
+  if (cfg->scale < 1 || cfg->scale > 64) return EKF_ERR_ARG;
   if (cfg->forsePlane != 0) return EKF_ERR_UNSUPPORTED;        // plane pseudo-measurement (V:1250-1263)
   if (cfg->window_size < 3 || cfg->window_size > 31) return EKF_ERR_UNSUPPORTED;
   if (cfg->search_clamp > 20 || cfg->search_clamp < 0) return EKF_ERR_UNSUPPORTED;
@@ -227,15 +227,20 @@ int ekf_sync(ekf_handle* h) {
   return EKF_OK;
 }
 
-static int capture_common(ekf_handle* h, const uint8_t* gray, int width, int height, int stride, double stamp, bool device_src) {
-  if (!h || !gray || width < 8 || height < 8 || stride < width) return EKF_ERR_ARG;
+// captureNewFrame(Mat[, double]) (vslamRansac.cpp:226-245): time stamp, resize by 1 / scale, BGR -> gray
+static int capture_common(ekf_handle* h, const uint8_t* img, int width, int height, int stride, int channels, double stamp,
+                          bool device_src) {
+  if (!h || !img || width < 8 || height < 8 || (channels != 1 && channels != 3) || stride < width * channels) return EKF_ERR_ARG;
   EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  const int scale = h->cfg.scale;
+  const int dw = width / scale, dh = height / scale;   // cv::Size(width / scale, height / scale), integer division
+  if (dw < 8 || dh < 8) return EKF_ERR_ARG;
   if (stamp >= 0) {  // captureNewFrame(Mat, double), vslamRansac.cpp:226-233
     if (h->old_ts > 0) h->dT = (stamp - h->old_ts);
     h->old_ts = stamp;
   }
-  const int dstride = (width + 15) & ~15;
-  const size_t need = (size_t)dstride * height;
+  const int dstride = (dw + 15) & ~15;
+  const size_t need = (size_t)dstride * dh;
   if (need > h->frame_cap) {
     EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     cudaFree(h->frame);
@@ -243,17 +248,51 @@ static int capture_common(ekf_handle* h, const uint8_t* gray, int width, int hei
     EKF_CUDA_CHECK(cudaMalloc((void**)&h->frame, need));
     h->frame_cap = need;
   }
-  EKF_CUDA_CHECK(cudaMemcpy2DAsync(h->frame, dstride, gray, stride, width, height,
-                                   device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
-  h->fv = FrameView{h->frame, width, height, dstride};
+  if (scale == 1 && channels == 1) {
+    EKF_CUDA_CHECK(cudaMemcpy2DAsync(h->frame, dstride, img, stride, width, height,
+                                     device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  } else {
+    const uint8_t* src = img;
+    int sstride = stride;
+    if (!device_src) {
+      const size_t rawneed = (size_t)width * channels * height;
+      if (rawneed > h->raw_cap) {
+        EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        cudaFree(h->raw);
+        h->raw = nullptr;
+        EKF_CUDA_CHECK(cudaMalloc((void**)&h->raw, rawneed));
+        h->raw_cap = rawneed;
+      }
+      EKF_CUDA_CHECK(cudaMemcpy2DAsync(h->raw, (size_t)width * channels, img, stride, (size_t)width * channels, height,
+                                       cudaMemcpyHostToDevice, h->stream));
+      src = h->raw; sstride = width * channels;
+    }
+    launch_capture_resize_gray(h->stream, src, width, height, sstride, channels, h->frame, dw, dh, dstride, &h->launches);
+    EKF_CUDA_CHECK(cudaGetLastError());
+  }
+  h->fv = FrameView{h->frame, dw, dh, dstride};
   h->have_frame = true;
   return EKF_OK;
 }
 int ekf_capture_frame(ekf_handle* h, const uint8_t* gray, int width, int height, int stride, double stamp) {
-  return capture_common(h, gray, width, height, stride, stamp, false);
+  return capture_common(h, gray, width, height, stride, 1, stamp, false);
 }
 int ekf_capture_frame_device(ekf_handle* h, const uint8_t* gray, int width, int height, int stride, double stamp) {
-  return capture_common(h, gray, width, height, stride, stamp, true);
+  return capture_common(h, gray, width, height, stride, 1, stamp, true);
+}
+int ekf_capture_frame_bgr(ekf_handle* h, const uint8_t* bgr, int width, int height, int stride, double stamp) {
+  return capture_common(h, bgr, width, height, stride, 3, stamp, false);
+}
+int ekf_get_frame(ekf_handle* h, uint8_t* out, int* width, int* height) {   // returnGrayImg (vslamRansac.cpp:1364)
+  if (!h || !width || !height) return EKF_ERR_ARG;
+  if (!h->have_frame) return ekf_fail(h, EKF_ERR_STATE, "no frame captured");
+  *width = h->fv.w; *height = h->fv.h;
+  if (out) {
+    EKF_CUDA_CHECK(cudaSetDevice(h->device));
+    EKF_CUDA_CHECK(cudaMemcpy2DAsync(out, h->fv.w, h->frame, h->fv.stride, h->fv.w, h->fv.h, cudaMemcpyDeviceToHost, h->stream));
+    EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  }
+  return EKF_OK;
 }
 
 int ekf_predict(ekf_handle* h, const double dv[3], const double dw[3], int vcontrol) {

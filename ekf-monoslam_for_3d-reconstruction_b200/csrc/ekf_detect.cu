@@ -178,3 +178,61 @@ int launch_detect_corners(cudaStream_t st, FrameView fr, FeatTab ft, int N, int 
   *launches += N > 0 ? 6 : 5;
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// captureNewFrame (vslamRansac.cpp:234-245): cv::resize(frame, Size(w / scale, h / scale)) followed by
+// cvtColor(BGR2GRAY) when the frame has three channels.  Restates OpenCV's 8-bit paths:
+//   INTER_LINEAR: 11-bit fixed-point coefficients, horizontal pass in int, vertical pass
+//                 ((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2 >> 2;
+//   exact 2x decimation: OpenCV switches to INTER_AREA, (s00 + s01 + s10 + s11 + 2) >> 2;
+//   BGR2GRAY: (3735 B + 19235 G + 9798 R + 16384) >> 15 (OpenCV 4 coefficients).
+// PARITY: unpinned (OpenCV is an un-vendored, unpinned dependency of the reference); bit-exact against
+// the cv2 4.13 wheel of this image (tests/test_gpu_detect.py).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void resize_coeff(int d, double scale, int ssize, int* s0, short* a0, short* a1) {
+  float f = (float)((d + 0.5) * scale - 0.5);
+  int s = (int)floorf(f);
+  f -= s;
+  if (s < 0) { f = 0; s = 0; }
+  if (s >= ssize - 1) { f = 0; s = ssize - 1; }
+  *s0 = s;
+  // saturate_cast<short>(float): round to nearest even
+  *a0 = (short)__float2int_rn((1.f - f) * 2048.f);
+  *a1 = (short)__float2int_rn(f * 2048.f);
+}
+__global__ void k_capture_resize_gray(const uint8_t* __restrict__ src, int sw, int sh, int sstride, int cn, uint8_t* __restrict__ dst,
+                                      int dw, int dh, int dstride) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= dw || y >= dh) return;
+  int ch[3] = {0, 0, 0};
+  if (sw == dw && sh == dh) {
+    for (int c = 0; c < cn; ++c) ch[c] = src[(size_t)y * sstride + x * cn + c];
+  } else {
+    const double scale_x = (double)sw / dw, scale_y = (double)sh / dh;
+    const bool area2 = (sw == 2 * dw) && (sh == 2 * dh);
+    if (area2) {
+      for (int c = 0; c < cn; ++c) {
+        const uint8_t* p = src + (size_t)(2 * y) * sstride + (2 * x) * cn + c;
+        ch[c] = (p[0] + p[cn] + p[sstride] + p[sstride + cn] + 2) >> 2;
+      }
+    } else {
+      int sx, sy; short ax0, ax1, by0, by1;
+      resize_coeff(x, scale_x, sw, &sx, &ax0, &ax1);
+      resize_coeff(y, scale_y, sh, &sy, &by0, &by1);
+      const int sx1 = min(sx + 1, sw - 1), sy1 = min(sy + 1, sh - 1);
+      for (int c = 0; c < cn; ++c) {
+        const int r0 = src[(size_t)sy * sstride + sx * cn + c] * ax0 + src[(size_t)sy * sstride + sx1 * cn + c] * ax1;
+        const int r1 = src[(size_t)sy1 * sstride + sx * cn + c] * ax0 + src[(size_t)sy1 * sstride + sx1 * cn + c] * ax1;
+        ch[c] = (((by0 * (r0 >> 4)) >> 16) + ((by1 * (r1 >> 4)) >> 16) + 2) >> 2;
+      }
+    }
+  }
+  int g = ch[0];
+  if (cn == 3) g = (ch[0] * 3735 + ch[1] * 19235 + ch[2] * 9798 + 16384) >> 15;
+  dst[(size_t)y * dstride + x] = (uint8_t)min(max(g, 0), 255);
+}
+void launch_capture_resize_gray(cudaStream_t st, const uint8_t* src, int sw, int sh, int sstride, int cn, uint8_t* dst, int dw, int dh,
+                                int dstride, long long* launches) {
+  k_capture_resize_gray<<<dim3((dw + 255) / 256, dh), 256, 0, st>>>(src, sw, sh, sstride, cn, dst, dw, dh, dstride);
+  *launches += 1;
+}

@@ -27,6 +27,8 @@ struct ekf_handle {
   FeatTab ft{}, ftB{};
   uint8_t* frame = nullptr;
   size_t frame_cap = 0;
+  uint8_t* raw = nullptr;   // full-resolution / colour staging for captureNewFrame's resize + BGR2GRAY
+  size_t raw_cap = 0;
   FrameView fv{nullptr, 0, 0, 0};
   uint32_t* picks_dev = nullptr;
   int picks_cap = 0;

@@ -53,3 +53,5 @@ int launch_gemm_nt_sub(cudaStream_t st, double* C, int ldc, const double* A, int
 // ekf_detect.cu
 int launch_detect_corners(cudaStream_t st, FrameView fr, FeatTab ft, int N, int window, uint8_t* mask, float* eig,
                           unsigned long long* keys, int key_cap, int* counters, int max_corners, float* out_xy, long long* launches);
+void launch_capture_resize_gray(cudaStream_t st, const uint8_t* src, int sw, int sh, int sstride, int cn, uint8_t* dst, int dw, int dh,
+                                int dstride, long long* launches);

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128) k_hi_rescue(const double* __restrict__ Si
 // K4a: W_b = Sigma H_b^T for the block of <= 64 selected features starting at sel[f0]
 // (n x EKF_UB, row-major), and nu_b = (z - h) - H_b delta.  One pass over the needed columns of Sigma.
 // ------------------------------------------------------------------------------------------------
-#define GATHER_ROWS 8
+#define GATHER_ROWS 4
 __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ Sigma, int ld, int row0, int n, FeatTab ft, int f0,
                                                     int cnt, const double* __restrict__ delta, double* __restrict__ W,
                                                     double* __restrict__ nu) {
@@ -128,11 +128,13 @@ __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ S
     const int i = row0 + blockIdx.x * rows_per_cta + rq;   // rows [row0, n): the caller's row block
     if (i >= n) break;
     const double* row = Sigma + (size_t)i * ld;
+    double sg[13];
+#pragma unroll
+    for (int c = 0; c < 13; ++c) sg[c] = (c < nd) ? row[ekf_idx13(c, pos)] : 0.0;   // 13 independent loads in flight
     double w0 = 0, w1 = 0;
-    for (int c = 0; c < nd; ++c) {
-      const double s = row[ekf_idx13(c, pos)];
-      w0 += s * Hs[a][c]; w1 += s * Hs[a][13 + c];
-    }
+#pragma unroll
+    for (int c = 0; c < 13; ++c)
+      if (c < nd) { w0 += sg[c] * Hs[a][c]; w1 += sg[c] * Hs[a][13 + c]; }
     reinterpret_cast<double2*>(W + (size_t)i * EKF_UB)[a] = make_double2(w0, w1);
   }
   if (nu && blockIdx.x == 0 && tid < EKF_UB / 2) {

@@ -50,9 +50,21 @@ class VSlamFilter:
 
     # ---- the per-frame path ------------------------------------------------------------------
     def captureNewFrame(self, img, stamp=-1.0):
-        """vslamRansac.cpp:226-245; img is an HxW uint8 numpy array (host) — copied inside the call."""
+        """vslamRansac.cpp:226-245; img is an HxW (gray) or HxWx3 (BGR) uint8 numpy array (host) — copied,
+        resized by 1 / cfg.scale and converted to gray inside the call."""
         img = np.ascontiguousarray(img, dtype=np.uint8)
-        self._ck(self.L.ekf_capture_frame(self.h, _ptr(img), img.shape[1], img.shape[0], img.strides[0], float(stamp)))
+        if img.ndim == 3:
+            self._ck(self.L.ekf_capture_frame_bgr(self.h, _ptr(img), img.shape[1], img.shape[0], img.strides[0], float(stamp)))
+        else:
+            self._ck(self.L.ekf_capture_frame(self.h, _ptr(img), img.shape[1], img.shape[0], img.strides[0], float(stamp)))
+
+    def returnGrayImg(self):
+        """vslamRansac.cpp:1364."""
+        w, h = C.c_int(0), C.c_int(0)
+        self._ck(self.L.ekf_get_frame(self.h, None, C.byref(w), C.byref(h)))
+        out = np.zeros((h.value, w.value), dtype=np.uint8)
+        self._ck(self.L.ekf_get_frame(self.h, _ptr(out), C.byref(w), C.byref(h)))
+        return out
 
     def captureNewFrame_device(self, dev_ptr, width, height, stride, stamp=-1.0):
         """Same for a frame already in device memory (raw pointer, e.g. tensor.data_ptr())."""

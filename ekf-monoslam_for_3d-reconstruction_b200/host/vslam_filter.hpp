@@ -18,7 +18,7 @@
 namespace ekf_b200 {
 
 struct Point2f { float x, y; };
-struct GrayImage { const uint8_t* data; int width, height, stride; };  // stands in for cv::Mat (8-bit gray)
+struct GrayImage { const uint8_t* data; int width, height, stride; int channels = 1; };  // stands in for cv::Mat (8-bit gray or BGR)
 
 class VSlamFilter {
  public:
@@ -46,8 +46,11 @@ class VSlamFilter {
   }
   // update(float v_x, float w_z) (:868; both arguments are unused by the reference).  `picks` replaces rand().
   void update(const std::vector<uint32_t>& picks = {}) { ck(ekf_update(h_, picks.empty() ? nullptr : picks.data(), (int)picks.size())); }
-  void captureNewFrame(const GrayImage& f) { ck(ekf_capture_frame(h_, f.data, f.width, f.height, f.stride, -1.0)); }            // :234
-  void captureNewFrame(const GrayImage& f, double time_stamp) { ck(ekf_capture_frame(h_, f.data, f.width, f.height, f.stride, time_stamp)); }  // :226
+  void captureNewFrame(const GrayImage& f) { captureNewFrame(f, -1.0); }                                          // :234
+  void captureNewFrame(const GrayImage& f, double time_stamp) {                                                  // :226
+    ck(f.channels == 3 ? ekf_capture_frame_bgr(h_, f.data, f.width, f.height, f.stride, time_stamp)
+                       : ekf_capture_frame(h_, f.data, f.width, f.height, f.stride, time_stamp));
+  }
   std::vector<double> getState() { std::vector<double> v(EKF_STATE_DIM); ck(ekf_get_state(h_, v.data())); return v; }          // :135
   std::vector<double> getSigma() { std::vector<double> v(EKF_STATE_DIM * EKF_STATE_DIM); ck(ekf_get_sigma(h_, v.data())); return v; }  // :131
   void convert2XYZ_ifLinear(int index) { ck(ekf_convert2xyz_if_linear(h_, index)); }                             // :741

@@ -99,8 +99,8 @@ typedef struct ekf_handle ekf_handle;
 void ekf_config_default(ekf_config* cfg);
 /* VSlamFilter::VSlamFilter (vslamRansac.cpp:142-223).  `feature_capacity` bounds the number of
  * simultaneously tracked features (device buffers are sized for n = 14 + 6*capacity). `device` is
- * a CUDA ordinal.  Configs that need blur (kernel_size < 100000), scale != 1 or an even
- * window_size > 64 return EKF_ERR_UNSUPPORTED. */
+ * a CUDA ordinal.  Configs that need motion-blur templates (kernel_size < 100000), forsePlane or a
+ * window_size outside [3, 31] return EKF_ERR_UNSUPPORTED. */
 int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_handle** out);
 int ekf_destroy(ekf_handle* h);
 /* Use `cuda_stream` (a cudaStream_t) for all work of this handle; NULL = the handle's own stream. */
@@ -113,6 +113,14 @@ const char* ekf_last_error(const ekf_handle* h);
 /* VSlamFilter::captureNewFrame(cv::Mat, double) (vslamRansac.cpp:226-245): 8-bit gray, HOST
  * memory, copied to the device inside the call.  stamp < 0 = the no-stamp overload. */
 int ekf_capture_frame(ekf_handle* h, const uint8_t* gray, int width, int height, int stride, double stamp);
+/* The 3-channel case of captureNewFrame (vslamRansac.cpp:238-241): 8-bit BGR, HOST memory.  With
+ * cfg.scale > 1 every capture call first resizes to (width / scale) x (height / scale) like cv::resize
+ * (INTER_LINEAR) and then converts BGR to gray, on the GPU; the intrinsics of ekf_config are those of the
+ * resized image, as ConfigVSLAM.cpp:89-120 produces them. */
+int ekf_capture_frame_bgr(ekf_handle* h, const uint8_t* bgr, int width, int height, int stride, double stamp);
+/* VSlamFilter::returnGrayImg (vslamRansac.cpp:1364): the gray frame the filter works on (after resize);
+ * out may be NULL to query the size only. */
+int ekf_get_frame(ekf_handle* h, uint8_t* out, int* width, int* height);
 /* Same, for a frame already resident in DEVICE memory (copied device-to-device). */
 int ekf_capture_frame_device(ekf_handle* h, const uint8_t* gray_dev, int width, int height, int stride, double stamp);
 /* VSlamFilter::predict (vslamRansac.cpp:451-603). */

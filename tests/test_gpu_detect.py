@@ -89,3 +89,24 @@ def test_update_tops_up_when_too_few_features_are_visible(gpu_pkg):
     assert f.numOfFeatures() == 15 and f.state_dim() == 14 + 6 * 15
     mu, S = f.get_full()
     assert np.isfinite(mu).all() and np.isfinite(S).all() and np.all(np.diag(S) > 0)
+
+
+@pytest.mark.parametrize("scale,shape,color", [(2, (480, 640), False), (2, (480, 640), True), (10, (1080, 1920), True),
+                                               (3, (481, 643), False), (1, (240, 320), True)])
+def test_capture_resize_and_gray_match_cv2(gpu_pkg, scale, shape, color):
+    """captureNewFrame (vslamRansac.cpp:234-245): cv::resize by 1 / scale, then BGR2GRAY — bit-exact against cv2."""
+    rng = np.random.default_rng(scale * 7 + int(color))
+    H, W = shape
+    img = rng.integers(0, 256, (H, W, 3) if color else (H, W), dtype=np.uint8)
+    cfg = gpu_pkg.default_config(window_size=11, xyz_conversion=0, min_features=0, scale=scale)
+    f = gpu_pkg.VSlamFilter(cfg, feature_capacity=8)
+    f.captureNewFrame(img, 1.0)
+    want = cv2.resize(img, (W // scale, H // scale))
+    if color:
+        want = cv2.cvtColor(want, cv2.COLOR_BGR2GRAY)
+    got = f.returnGrayImg()
+    assert got.shape == want.shape
+    assert np.array_equal(got, want), f"{(got != want).sum()} of {want.size} pixels differ (max {np.abs(got.astype(int) - want).max()})"
+    # the filter works on the resized frame: the in-image gate of addFeature uses its size
+    assert f.addFeature(W // scale - 20.0, H // scale - 20.0) == 1
+    assert f.addFeature(W // scale + 5.0, 30.0) == 0

@@ -177,7 +177,7 @@ def test_xyz_conversion_and_mixed_update(gpu_pkg, orc):
 
 
 def test_unsupported_configs_fail_loudly(gpu_pkg):
-    for over in (dict(kernel_size=3), dict(scale=2), dict(forsePlane=1)):
+    for over in (dict(kernel_size=3), dict(forsePlane=1), dict(window_size=33)):
         cfg = gpu_pkg.default_config(xyz_conversion=0, **over)
         with pytest.raises(gpu_pkg.EkfError):
             gpu_pkg.VSlamFilter(cfg)
