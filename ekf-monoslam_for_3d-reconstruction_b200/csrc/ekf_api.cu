@@ -120,7 +120,6 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
   if (!cfg || !out || feature_capacity < 1 || feature_capacity > 8192) return EKF_ERR_ARG;
   *out = nullptr;
   // parts of the reference outside this path are rejected, never emulated on the CPU
-  if (cfg->kernel_size < 100000) return EKF_ERR_UNSUPPORTED;   // motion-blur templates (libblur.cpp)
   if (cfg->scale < 1 || cfg->scale > 64) return EKF_ERR_ARG;
   if (cfg->forsePlane != 0) return EKF_ERR_UNSUPPORTED;        // plane pseudo-measurement (V:1250-1263)
   if (cfg->window_size < 3 || cfg->window_size > 31) return EKF_ERR_UNSUPPORTED;
@@ -190,6 +189,7 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
   d.ransac_p = cfg->ransac_p;
   d.linearity_threshold = cfg->linearity_threshold;
   d.rho_0 = cfg->rho_0; d.sigma_rho_0 = cfg->sigma_rho_0;
+  d.T_camera = cfg->T_camera; d.kernel_min_size = cfg->kernel_size;
   d.ncc_threshold = (float)cfg->ncc_threshold; d.search_clamp = (float)cfg->search_clamp;
   d.sigma_size_f = (float)cfg->sigma_size; d.quality_ratio = (float)cfg->quality_ratio;
   d.window = cfg->window_size; d.sigma_pixel = cfg->sigma_pixel; d.nhyp0 = cfg->ransac_nhyp0;
@@ -607,8 +607,9 @@ int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
   h->stats.n_li = n_li;
   h->stats.n_hi = n_hi;
   h->stats.ransac_hypotheses = outi[4];
-  h->stats.blur_requests = 0;
+  h->stats.blur_requests = outi[6];
   if (outi[5]) return ekf_fail(h, EKF_ERR_STATE, "innovation covariance not positive definite");
+  if (outi[7]) return ekf_fail(h, EKF_ERR_UNSUPPORTED, "a motion-blur kernel exceeded 256 x 256 pixels");
   h->cache_ok = false;
   // delete flagged features (V:1296-1299), then the visibility top-up hook (V:1301-1315)
   std::vector<int> victims;

@@ -738,6 +738,7 @@ int ekf_batch_create(const ekf_config* cfg, int n_filters, int feature_capacity,
   d.ransac_p = cfg->ransac_p;
   d.linearity_threshold = cfg->linearity_threshold;
   d.rho_0 = cfg->rho_0; d.sigma_rho_0 = cfg->sigma_rho_0;
+  d.T_camera = cfg->T_camera; d.kernel_min_size = cfg->kernel_size;
   d.ncc_threshold = (float)cfg->ncc_threshold; d.search_clamp = (float)cfg->search_clamp;
   d.sigma_size_f = (float)cfg->sigma_size; d.quality_ratio = (float)cfg->quality_ratio;
   d.window = cfg->window_size; d.sigma_pixel = cfg->sigma_pixel; d.nhyp0 = cfg->ransac_nhyp0;

@@ -31,9 +31,11 @@ struct DevCfg {
   double ransac_p;
   double linearity_threshold;
   double rho_0, sigma_rho_0;
+  double T_camera;      // fraction of dT used for the blur pose (ConfigVSLAM.cpp:39)
   float ncc_threshold, search_clamp, sigma_size_f, quality_ratio;
   int window, sigma_pixel, nhyp0, forsePlane, abs_int_quirk;
   int tstride;  // bytes per template record (window^2 rounded up to 16)
+  int kernel_min_size;  // Patch::blur threshold (vslamRansac.cpp:148); >= 100000: motion blur off
 };
 
 // Device-resident control block.
@@ -49,7 +51,8 @@ struct DevCtl {
   int n_remove;           // features flagged by update_quality_index / rho <= 0
   unsigned int ticket;    // last-block-done counter (self-resetting)
   int chol_fail;          // non-positive pivot seen
-  int pad[2];
+  int blur_count;         // templates blurred by the last predict
+  int blur_too_large;     // a blur kernel exceeded the supported 256 x 256
 };
 
 // Feature table (structure of arrays, device pointers).

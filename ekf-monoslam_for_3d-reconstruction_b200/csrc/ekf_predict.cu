@@ -137,6 +137,94 @@ __global__ void __launch_bounds__(128) k_predict_features(const double* __restri
   if (threadIdx.x == 0) {
     ctl->m_innov = m;
     ctl->ticket = 0;
+    ctl->blur_count = 0;
+    ctl->blur_too_large = 0;
+  }
+}
+
+// Motion-blur template prediction (V:498-500, 546-548, 575-576; Patch::blur Patch.cpp:50-57; evaluateKernel /
+// blurPatch libblur.cpp:17-81).  One CTA per gated-in feature: project the feature from the pose the camera
+// will have T_camera * dT later; if that moves the prediction by more than kernel_min_size pixels the
+// template is correlated with a normalised line kernel of that displacement (double arithmetic,
+// BORDER_REFLECT_101, round-half-even to u8) into matching_patch.  The kernel lives as a bit mask
+// (<= 256 x 256); its set coefficients are visited in row-major order like OpenCV's direct filter engine.
+#define BLUR_MAXK 256
+__global__ void __launch_bounds__(128) k_predict_blur(const double* __restrict__ mu, FeatTab ft, int N, DevCtl* ctl, DevCfg cfg,
+                                                      double dT) {
+  __shared__ unsigned kbits[BLUR_MAXK * BLUR_MAXK / 32];
+  __shared__ int s_rows, s_cols, s_do;
+  __shared__ double s_kf, s_dx, s_dy;
+  const int f = blockIdx.x, tid = threadIdx.x;
+  if (f >= N || !ft.innov[f]) return;
+  const int w = cfg.window;
+  if (tid == 0) {
+    s_do = 0;
+    double cam[13];
+    for (int c = 0; c < 13; ++c) cam[c] = mu[c];   // predicted camera state, committed by k_predict_features
+    const double q[4] = {cam[3], cam[4], cam[5], cam[6]};
+    double wb[3], hb[4], qb[4], rb[3], Rb[9];
+    for (int c = 0; c < 3; ++c) wb[c] = (cam[10 + c] * cfg.T_camera) * dT;
+    d_vec2quat(wb, hb);
+    d_quat_mul(q, hb, qb);
+    const double qbc[4] = {qb[0], -qb[1], -qb[2], -qb[3]};
+    d_quat2rot(qbc, Rb);
+    for (int c = 0; c < 3; ++c) rb[c] = cam[c] + (cam[7 + c] * cfg.T_camera) * dT;
+    const int pos = ft.pos[f], coding = ft.coding[f];
+    double fs[6], hib[2];
+    for (int c = 0; c < (coding ? 3 : 6); ++c) fs[c] = mu[pos + c];
+    d_feature_h(cfg.cam, fs, coding, rb, Rb, hib);
+    const double ddx = ft.h[2 * f] - hib[0], ddy = ft.h[2 * f + 1] - hib[1];
+    const double dn = sqrt(ddx * ddx + ddy * ddy);
+    if (dn > cfg.kernel_min_size) {
+      const int kcols = (int)(fabs(ddx) + 1), krows = (int)(fabs(ddy) + 1);   // cv::Mat::zeros(width, height), libblur.cpp:20-23
+      if (krows > BLUR_MAXK || kcols > BLUR_MAXK) { ctl->blur_too_large = 1; }
+      else { s_do = 1; s_rows = krows; s_cols = kcols; s_dx = ddx; s_dy = ddy; }
+    }
+  }
+  __syncthreads();
+  if (!s_do) return;   // matching_patch already holds the unblurred template (k_predict_features)
+  const int krows = s_rows, kcols = s_cols;
+  for (int e = tid; e < (krows * kcols + 31) / 32; e += 128) kbits[e] = 0u;
+  __syncthreads();
+  if (tid == 0) {
+    // rasterise the line, libblur.cpp:25-43
+    const double dx = s_dx, dy = s_dy;
+    const double theta = atan2(dy, dx);
+    const double length = sqrt(dx * dx + dy * dy);
+    const double c = cos(theta), s = sin(theta);
+    const int x0 = (int)(s < 0 ? -s * length : 0.0), y0 = (int)(c < 0 ? -c * length : 0.0);
+    int count = 0;
+    for (int i = 0; i < length; ++i) {
+      const int x = (int)(i * s + x0), y = (int)(i * c + y0);
+      if (x >= 0 && y >= 0 && x < krows && y < kcols) {   // one past the kernel: undefined behaviour in the reference, skipped
+        const int bit = x * kcols + y;
+        if (!(kbits[bit >> 5] & (1u << (bit & 31)))) { kbits[bit >> 5] |= 1u << (bit & 31); ++count; }
+      }
+    }
+    s_kf = 1.0 / (double)count;   // kernel / sum(kernel): every set coefficient is 1 / count
+    atomicAdd(&ctl->blur_count, 1);
+  }
+  __syncthreads();
+  const double kf = s_kf;
+  const int ax = kcols / 2, ay = krows / 2;
+  const uint8_t* src = ft.patch + (size_t)f * cfg.tstride;
+  uint8_t* dst = ft.mpatch + (size_t)f * cfg.tstride;
+  for (int e = tid; e < w * w; e += 128) {
+    const int y = e / w, x = e - y * w;
+    double acc = 0.0;
+    for (int ky = 0; ky < krows; ++ky) {
+      int yy = y + ky - ay;
+      while (yy < 0 || yy >= w) yy = yy < 0 ? -yy : 2 * w - 2 - yy;   // BORDER_REFLECT_101
+      for (int kx = 0; kx < kcols; ++kx) {
+        const int bit = ky * kcols + kx;
+        if (!(kbits[bit >> 5] & (1u << (bit & 31)))) continue;
+        int xx = x + kx - ax;
+        while (xx < 0 || xx >= w) xx = xx < 0 ? -xx : 2 * w - 2 - xx;
+        acc = __dadd_rn(acc, __dmul_rn(kf, (double)src[yy * w + xx]));
+      }
+    }
+    const int iv = __double2int_rn(acc);   // saturate_cast<uchar>(cvRound(v)): round half to even
+    dst[e] = (uint8_t)min(max(iv, 0), 255);
   }
 }
 
@@ -490,6 +578,10 @@ void launch_predict(cudaStream_t st, double* Sigma, int ld, int n, double* mu, F
   const int fb = N > 0 ? (N + 127) / 128 : 1;
   k_predict_features<<<fb, 128, 0, st>>>(Sigma, ld, mu, ft, N, fr, ctl, cfg);
   *launches += 2;
+  if (N > 0 && cfg.kernel_min_size < 100000) {   // motion-blur templates enabled
+    k_predict_blur<<<N, 128, 0, st>>>(mu, ft, N, ctl, cfg, dT);
+    *launches += 1;
+  }
   if (N > 0) {
     k_predict_S2<<<(N + 3) / 4, 128, 0, st>>>(Sigma, ld, ft, N, cfg);
     *launches += 1;

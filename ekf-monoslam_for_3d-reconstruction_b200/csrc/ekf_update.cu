@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256) k_bookkeeping(const double* __restrict__ 
     for (int e = threadIdx.x; e < 196; e += blockDim.x) outd[14 + e] = Sigma[(size_t)(e / 14) * ld + (e % 14)];
     if (threadIdx.x == 0) {
       outi[0] = ctl->m_innov; outi[1] = ctl->n_matched; outi[2] = ctl->n_li; outi[3] = ctl->n_hi;
-      outi[4] = ctl->ransac_hyps; outi[5] = ctl->chol_fail;
+      outi[4] = ctl->ransac_hyps; outi[5] = ctl->chol_fail; outi[6] = ctl->blur_count; outi[7] = ctl->blur_too_large;
     }
   }
 }

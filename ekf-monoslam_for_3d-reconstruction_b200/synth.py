@@ -94,6 +94,7 @@ class Scene:
     outlier_frac: float = 0.02
     outlier_shift: int = 8
     noise_sigma: float = 20.0
+    template_smooth: float = 0.0  # > 0: low-pass templates (Gaussian sigma in px) that survive motion-blur prediction
 
     def __post_init__(self):
         rng = np.random.default_rng(self.seed)
@@ -134,6 +135,14 @@ class Scene:
         pc = rays * depth[:, None]
         self.points = r[0][None, :] + pc @ quat2rot(q[0]).T
         self.templates = rng.integers(0, 256, size=(N, self.window, self.window), dtype=np.uint8)
+        if self.template_smooth > 0:
+            k = int(3 * self.template_smooth) + 1
+            g = np.exp(-0.5 * (np.arange(-k, k + 1) / self.template_smooth) ** 2); g /= g.sum()
+            big = rng.normal(size=(N, self.window + 2 * k, self.window + 2 * k))
+            sm = np.apply_along_axis(lambda v: np.convolve(v, g, mode="valid"), 1, big)
+            sm = np.apply_along_axis(lambda v: np.convolve(v, g, mode="valid"), 2, sm)
+            lo = sm.min(axis=(1, 2), keepdims=True); hi = sm.max(axis=(1, 2), keepdims=True)
+            self.templates = np.round((sm - lo) / (hi - lo) * 255).astype(np.uint8)
         self.outliers = np.zeros(N, dtype=bool)
         if self.hard:
             k = max(1, int(round(self.outlier_frac * N)))

@@ -57,7 +57,7 @@ typedef struct ekf_config {
   double linearity_threshold;  /* vslamRansac.cpp:701   0.01  */
   int32_t window_size;         /* ConfigVSLAM.cpp:31    21    */
   int32_t sigma_pixel;         /* ConfigVSLAM.cpp:32    2     */
-  int32_t kernel_size;         /* no default in the reference (ConfigVSLAM.cpp:76); here 1e9 = blur off */
+  int32_t kernel_size;         /* Patch::blur threshold in px; no default in the reference (ConfigVSLAM.cpp:76); here 1e9 = blur off */
   int32_t sigma_size;          /* ConfigVSLAM.cpp:41    2     */
   int32_t scale;               /* ConfigVSLAM.cpp:37    1     */
   int32_t nInitFeatures, min_features, max_features, forsePlane; /* ConfigVSLAM.cpp:43-48 */
@@ -88,7 +88,7 @@ typedef struct ekf_step_stats {
   int32_t ransac_hypotheses;       /* loop trips of vslamRansac.cpp:986 */
   int32_t n_removed;               /* features dropped by vslamRansac.cpp:1296-1299 */
   int32_t topup_request;           /* argument passed to findNewFeatures at vslamRansac.cpp:1314 (0 = no top-up this step) */
-  int32_t blur_requests;           /* always 0: blur is rejected at create time */
+  int32_t blur_requests;           /* templates blurred by the last predict (Patch::blur, Patch.cpp:52) */
   int64_t kernel_launches;         /* kernels of this library launched on the handle so far */
 } ekf_step_stats;
 
@@ -99,8 +99,8 @@ typedef struct ekf_handle ekf_handle;
 void ekf_config_default(ekf_config* cfg);
 /* VSlamFilter::VSlamFilter (vslamRansac.cpp:142-223).  `feature_capacity` bounds the number of
  * simultaneously tracked features (device buffers are sized for n = 14 + 6*capacity). `device` is
- * a CUDA ordinal.  Configs that need motion-blur templates (kernel_size < 100000), forsePlane or a
- * window_size outside [3, 31] return EKF_ERR_UNSUPPORTED. */
+ * a CUDA ordinal.  forsePlane, a window_size outside [3, 31] or a search_clamp above 20 px return
+ * EKF_ERR_UNSUPPORTED. */
 int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_handle** out);
 int ekf_destroy(ekf_handle* h);
 /* Use `cuda_stream` (a cudaStream_t) for all work of this handle; NULL = the handle's own stream. */

@@ -34,6 +34,9 @@ CASES = {
     "seq_n40_hard": dict(scene=dict(n_features=40, n_frames=7, seed=9, hard=True), controls=False),
     "seq_n16_controls": dict(scene=dict(n_features=16, n_frames=5, seed=17), controls=True),
     "seq_n10_xyz": dict(scene=dict(n_features=10, n_frames=4, seed=23), controls=False, xyz=(1, 4, 9)),
+    # motion-blur templates (kernel_size = 3, T_camera = 0.5 as conf_sim.cfg) with a fast camera
+    "seq_n16_blur": dict(scene=dict(n_features=16, n_frames=5, seed=29, speed=0.9, omega=0.5, template_smooth=2.5), controls=False,
+                         cfg=dict(kernel_size=3, T_camera=0.5)),
 }
 
 
@@ -48,6 +51,7 @@ def run_case(pkg, name, spec, make_filter):
     sc = pkg.synth.Scene(**spec["scene"])
     over = sc.config_overrides()
     over["xyz_conversion"] = 1  # the reference always converts at the end of update (vslamRansac.cpp:1317)
+    over.update(spec.get("cfg", {}))
     f = make_filter(over)
     N = sc.n_features
     f.captureNewFrame(sc.frame(0), sc.stamps[0])

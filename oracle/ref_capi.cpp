@@ -1,7 +1,7 @@
 // oracle/ref_capi.cpp — TEST INFRASTRUCTURE ONLY.
 //
 // C harness around the REFERENCE'S OWN `class VSlamFilter`, compiled from the unmodified sources
-// under /root/reference/mono-slam/src (vslamRansac.cpp, Patch.cpp, camModel.cpp, utils.cpp) against
+// under /root/reference/mono-slam/src (vslamRansac.cpp, Patch.cpp, camModel.cpp, utils.cpp, libblur.cpp) against
 // the API stand-ins in oracle/shim/ (Eigen3, OpenCV, ROS and libconfig++ are not installed here).
 // oracle/build_ref.py builds two variants into oracle/_ref/:
 //   libref_f32.so  the sources as written (fp32 state, what the reference really runs)
@@ -9,7 +9,7 @@
 //                  parity target BASELINE.json names; compared with the oracle's all-double kind
 // tests/test_oracle_vs_ref.py and oracle/gen_golden.py drive it; nothing in the product does.
 // Replaced pieces, all outside the EKF arithmetic: ConfigVSLAM's libconfig reader (values come from
-// the ekf_config struct), rand()/srand() (injected picks), blurPatch/deblurPatch (blur disabled).
+// the ekf_config struct) and rand()/srand() (injected picks).
 #include "../include/ekf_b200.h"  // before the shims: keeps `float` fields of the ABI structs float
 
 #include <stdarg.h>
@@ -50,8 +50,6 @@ ConfigVSLAM::ConfigVSLAM(char*) {  // stands in for ConfigVSLAM.cpp:26-151 (libc
   camParams.k3 = (shim_real)g_cfg.k3; camParams.p1 = (shim_real)g_cfg.p1; camParams.p2 = (shim_real)g_cfg.p2;
 }
 
-cv::Mat blurPatch(const cv::Mat&, cv::Point2f, cv::Point2f) { cv::shim_unsupported("blurPatch (libblur.cpp; kernel_size must disable blur)"); }
-cv::Mat deblurPatch(const cv::Mat&, cv::Point2f, cv::Point2f) { cv::shim_unsupported("deblurPatch"); }
 
 static std::vector<uint32_t> g_picks;
 static size_t g_pick_pos = 0;
@@ -196,6 +194,14 @@ void ref_get_S_blocks(void* hh, double* out) {
 }
 
 // computeCorrelation / Patch::findMatch stand-alone (Patch.cpp:215-329): one feature
+// blurPatch of the reference (libblur.cpp:57-81) stand-alone: w x w u8 patch, segment one -> two
+void ref_blur_patch(const uint8_t* patch, int w, double x1, double y1, double x2, double y2, uint8_t* out) {
+  cv::Mat pv(w, w, CV_8UC1, (void*)patch, (size_t)w);
+  cv::Mat res = blurPatch(pv.clone(), cv::Point2f((shim_real)x1, (shim_real)y1), cv::Point2f((shim_real)x2, (shim_real)y2));
+  for (int r = 0; r < w; ++r)
+    for (int c = 0; c < w; ++c) out[r * w + c] = res.at<uchar>(r, c);
+}
+
 int ref_find_match(const uint8_t* frame, int w, int hgt, int stride, const uint8_t* tmpl, int win, const double* h2,
                    const double* S4, float sigma_size, int32_t* out_uv) {
   cv::Mat view(hgt, w, CV_8UC1, (void*)frame, (size_t)stride);

@@ -4,8 +4,9 @@
 // image with ROI views, clone(), at<uchar>(); Point/Size/Rect/Scalar), so that those sources compile
 // unmodified into oracle/_ref (OpenCV's C++ headers are not installed in this image).  On the path
 // itself the reference uses OpenCV only for exact byte copies and pixel reads.
-// Everything the path does not reach either does nothing (drawing, imshow) or aborts loudly
-// (resize to another size, colour conversion, optical flow, filter2D): the harness never enables them.
+// Also the double-matrix subset libblur.cpp needs (zeros, convertTo, at<double>, Mat / scalar, sum, norm,
+// filter2D in its direct form).  Everything the path does not reach either does nothing (drawing,
+// imshow) or aborts loudly (resize to another size, colour conversion, optical flow).
 #ifndef EKF_SHIM_OPENCV_HPP_
 #define EKF_SHIM_OPENCV_HPP_
 #include "../shim_prelude.h"
@@ -13,7 +14,9 @@
 typedef unsigned char uchar;
 
 #define CV_8UC1 0
+#define CV_8U 0
 #define CV_8UC3 16
+#define CV_64F 6
 #define CV_BGR2GRAY 6
 #define CV_RGB(r, g, b) cv::Scalar((b), (g), (r), 0)
 
@@ -62,7 +65,12 @@ struct NoArray {};
 inline NoArray noArray() { return NoArray(); }
 enum { FONT_HERSHEY_SIMPLEX = 0, FONT_HERSHEY_SCRIPT_SIMPLEX = 6 };
 
-// 8-bit image, 1 or 3 channels, reference-counted buffer, ROI views share the buffer.
+enum { BORDER_REFLECT_101 = 4, BORDER_DEFAULT = 4 };
+template <class T> struct DataType;
+template <> struct DataType<double> { enum { type = CV_64F }; };
+template <> struct DataType<uchar> { enum { type = CV_8U }; };
+
+// 8-bit image (1 or 3 channels) or double matrix, reference-counted buffer, ROI views share the buffer.
 class Mat {
   std::shared_ptr<std::vector<uchar>> buf_;
 
@@ -84,29 +92,99 @@ class Mat {
     data = m.data + (size_t)roi.y * m.step + (size_t)roi.x * m.channels();
   }
   void create(int r, int c, int type) {
-    type_ = type; rows = r; cols = c; step = (size_t)c * channels();
-    buf_ = std::make_shared<std::vector<uchar>>((size_t)r * step, 0);
+    type_ = type; rows = r; cols = c; step = (size_t)c * channels() * elemSize1();
+    buf_ = std::make_shared<std::vector<uchar>>((size_t)r * step + 8, 0);
     data = buf_->data();
   }
   int channels() const { return type_ == CV_8UC3 ? 3 : 1; }
+  size_t elemSize1() const { return type_ == CV_64F ? 8 : 1; }
+  int type() const { return type_; }
+  int depth() const { return type_ == CV_64F ? CV_64F : CV_8U; }
+  static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
   Size size() const { return Size(cols, rows); }
   bool empty() const { return rows == 0 || cols == 0; }
   Mat clone() const {
     Mat m;
     if (empty()) return m;
     m.create(rows, cols, type_);
-    for (int r = 0; r < rows; ++r) memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * channels());
+    for (int r = 0; r < rows; ++r) memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * channels() * elemSize1());
     return m;
   }
+  // convertTo between 8-bit and double (scale 1): u8 -> double exact; double -> u8 = saturate_cast<uchar>(cvRound(v)),
+  // cvRound rounding half to even
+  void convertTo(Mat& dst, int rtype) const {
+    Mat out(rows, cols, rtype);
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < cols; ++c) {
+        const double v = type_ == CV_64F ? *reinterpret_cast<const double*>(data + (size_t)r * step + (size_t)c * 8)
+                                          : (double)data[(size_t)r * step + c];
+        if (rtype == CV_64F) *reinterpret_cast<double*>(out.data + (size_t)r * out.step + (size_t)c * 8) = v;
+        else {
+          const long iv = lrint(v);
+          out.data[(size_t)r * out.step + c] = (uchar)(iv < 0 ? 0 : (iv > 255 ? 255 : iv));
+        }
+      }
+    dst = out;
+  }
   void copyTo(Mat& dst) const { dst = clone(); }
-  template <class T> T& at(int r, int c) { return *reinterpret_cast<T*>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
-  template <class T> const T& at(int r, int c) const { return *reinterpret_cast<const T*>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
+  // out-of-range accesses (evaluateKernel can index one past its kernel, libblur.cpp:39-43: undefined behaviour in the
+  // reference) go to a sink instead of corrupting the heap
+  template <class T> T& at(int r, int c) {
+    static T sink; if (r < 0 || c < 0 || r >= rows || c >= cols) { sink = T(); return sink; }
+    return *reinterpret_cast<T*>(data + (size_t)r * step + (size_t)c * sizeof(T));
+  }
+  template <class T> const T& at(int r, int c) const {
+    static T sink = T(); if (r < 0 || c < 0 || r >= rows || c >= cols) return sink;
+    return *reinterpret_cast<const T*>(data + (size_t)r * step + (size_t)c * sizeof(T));
+  }
   Mat& setTo(const Scalar& s) {
     for (int r = 0; r < rows; ++r) memset(data + (size_t)r * step, (int)s.val[0], (size_t)cols * channels());
     return *this;
   }
 };
 
+inline Mat operator/(const Mat& a, double s) {
+  Mat out = a.clone();
+  if (a.type() != CV_64F) shim_unsupported("Mat / scalar on a non-double matrix");
+  for (int r = 0; r < a.rows; ++r)
+    for (int c = 0; c < a.cols; ++c) out.at<double>(r, c) = a.at<double>(r, c) / s;
+  return out;
+}
+inline Scalar sum(const Mat& a) {
+  if (a.type() != CV_64F) shim_unsupported("sum on a non-double matrix");
+  double s = 0;
+  for (int r = 0; r < a.rows; ++r)
+    for (int c = 0; c < a.cols; ++c) s += a.at<double>(r, c);
+  return Scalar(s);
+}
+template <class T> Point_<T> operator-(const Point_<T>& a, const Point_<T>& b) { return Point_<T>(a.x - b.x, a.y - b.y); }
+template <class T> double norm(const Point_<T>& p) { return std::sqrt((double)p.x * p.x + (double)p.y * p.y); }
+inline int shim_reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+  return i;
+}
+// filter2D, direct form (correlation, anchor at the kernel centre by default, BORDER_REFLECT_101), double only.
+// Coefficients are visited in row-major order, zeros skipped, as OpenCV's non-DFT engine does.
+inline void filter2D(const Mat& src, Mat& dst, int /*ddepth*/, const Mat& kernel, Point anchor = Point(-1, -1), double delta = 0,
+                     int /*borderType*/ = BORDER_DEFAULT) {
+  if (src.type() != CV_64F || kernel.type() != CV_64F) shim_unsupported("filter2D on non-double matrices");
+  const int ax = anchor.x < 0 ? kernel.cols / 2 : anchor.x, ay = anchor.y < 0 ? kernel.rows / 2 : anchor.y;
+  Mat in = src.clone();   // src and dst may be the same object (libblur.cpp:70)
+  Mat out(src.rows, src.cols, CV_64F);
+  for (int y = 0; y < src.rows; ++y)
+    for (int x = 0; x < src.cols; ++x) {
+      double s = delta;
+      for (int ky = 0; ky < kernel.rows; ++ky)
+        for (int kx = 0; kx < kernel.cols; ++kx) {
+          const double kf = kernel.at<double>(ky, kx);
+          if (kf == 0) continue;
+          s += kf * in.at<double>(shim_reflect101(y + ky - ay, src.rows), shim_reflect101(x + kx - ax, src.cols));
+        }
+      out.at<double>(y, x) = s;
+    }
+  dst = out;
+}
 inline void resize(const Mat& src, Mat& dst, Size sz) {
   if (sz.width != src.cols || sz.height != src.rows) shim_unsupported("resize to a different size (config.scale != 1)");
   Mat keep = src;  // src and dst may be the same object (vslamRansac.cpp:236)

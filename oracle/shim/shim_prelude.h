@@ -6,6 +6,7 @@
 // (vslamRansac.cpp:970,989) to an injectable sequence so that runs are reproducible.
 #ifndef EKF_SHIM_PRELUDE_H_
 #define EKF_SHIM_PRELUDE_H_
+#include <float.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>

@@ -176,8 +176,35 @@ def test_xyz_conversion_and_mixed_update(gpu_pkg, orc):
     assert_tables_equal(g, o, ctx="remove xyz"); assert_state_close(g, o, ctx="remove xyz")
 
 
+def test_motion_blur_templates(gpu_pkg, orc):
+    """Patch::blur (Patch.cpp:50-57) + blurPatch / evaluateKernel (libblur.cpp:17-81), kernel_size = 3 and
+    T_camera = 0.5 as conf_sim.cfg, fast camera: blurred templates, matches and the step bit-exact / 1e-9."""
+    sc = _scene(gpu_pkg, n_features=24, n_frames=6, seed=29, speed=0.9, omega=0.5, template_smooth=2.5)
+    g, o = make_pair(gpu_pkg, orc, sc, kernel_size=3, T_camera=0.5)
+    seed_features(g, sc); seed_features(o, sc)
+    blurred = 0
+    for t in range(1, sc.n_frames):
+        mu, S = o.get_full(); g.set_full(mu, S)
+        img = sc.frame(t)
+        for f in (g, o):
+            f.captureNewFrame(img, sc.stamps[t]); f.predict()
+        for i in range(g.numOfFeatures()):
+            if o.feature(i).is_in_innovation:
+                a, b = g.template(i, 1), o.template(i, 1)
+                assert np.array_equal(a, b), f"frame {t} feature {i}: blurred template differs in {(a != b).sum()} pixels"
+                blurred += int(not np.array_equal(b, o.template(i, 0)))
+        picks = sc.picks(t, 24)
+        g.update(picks); o.update(picks)
+        assert g.stats().n_matched == o.stats().n_matched
+        assert_tables_equal(g, o, ctx=f"blur frame {t}")
+        for i in range(g.numOfFeatures()):
+            assert g.feature(i).last_ncc == o.feature(i).last_ncc
+        assert_state_close(g, o, ctx=f"blur frame {t}")
+    assert blurred >= 10 and g.stats().blur_requests > 0
+
+
 def test_unsupported_configs_fail_loudly(gpu_pkg):
-    for over in (dict(kernel_size=3), dict(forsePlane=1), dict(window_size=33)):
+    for over in (dict(forsePlane=1), dict(window_size=33), dict(search_clamp=25.0)):
         cfg = gpu_pkg.default_config(xyz_conversion=0, **over)
         with pytest.raises(gpu_pkg.EkfError):
             gpu_pkg.VSlamFilter(cfg)

@@ -140,3 +140,30 @@ def test_find_match_standalone(pkg, orc, ref):
     for k in range(24):
         got = ref.find_match(d["frames"][0], tm[k], h[k], S[k], sigma_size=3.0, fp64=False)
         assert got == (uv[k, 0], uv[k, 1]), k
+
+
+@pytest.mark.parametrize("fp64,kind,tol", VARIANTS)
+def test_motion_blur_templates(pkg, orc, ref, fp64, kind, tol):
+    """Patch::blur / blurPatch / evaluateKernel (Patch.cpp:50-57, libblur.cpp:17-81) with the reference's own
+    libblur.cpp compiled in: kernel_size = 3 as conf_sim.cfg, T_camera = 0.5, a fast camera so that the
+    predicted displacement over the exposure exceeds the threshold for most features."""
+    sc = pkg.synth.Scene(n_features=16, n_frames=6, seed=29, speed=0.9, omega=0.5, template_smooth=2.5)
+    r, o = _pair(pkg, orc, ref, sc, fp64, kind, kernel_size=3, T_camera=0.5)
+    for f in (r, o):
+        f.captureNewFrame(sc.frame(0), sc.stamps[0])
+        for p in sc.feature_pixels:
+            f.addFeature(*p)
+    blurred = 0
+    for t in range(1, sc.n_frames):
+        for f in (r, o):
+            f.captureNewFrame(sc.frame(t), sc.stamps[t]); f.predict()
+        for i in range(r.numOfFeatures()):
+            if o.feature(i).is_in_innovation:
+                a, b = r.template(i, 1), o.template(i, 1)       # matching_patch after Patch::blur
+                assert np.array_equal(a, b), f"frame {t} feature {i}: blurred template differs in {(a != b).sum()} pixels"
+                blurred += int(not np.array_equal(b, o.template(i, 0)))
+        picks = sc.picks(t, 16)
+        r.update(picks); o.update(picks)
+        _same_tables(r, o, f"frame {t} update"); _same_state(r, o, tol, f"frame {t} update")
+    assert blurred >= 10, f"only {blurred} templates were blurred: the scene does not exercise the path"
+    assert o.stats().blur_requests > 0
