@@ -121,7 +121,6 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
   *out = nullptr;
   // parts of the reference outside this path are rejected, never emulated on the CPU
   if (cfg->scale < 1 || cfg->scale > 64) return EKF_ERR_ARG;
-  if (cfg->forsePlane != 0) return EKF_ERR_UNSUPPORTED;        // plane pseudo-measurement (V:1250-1263)
   if (cfg->window_size < 3 || cfg->window_size > 31) return EKF_ERR_UNSUPPORTED;
   if (cfg->search_clamp > 20 || cfg->search_clamp < 0) return EKF_ERR_UNSUPPORTED;
   int ndev = 0;
@@ -509,9 +508,11 @@ static int stacked_update_lookahead(ekf_handle* h, int cnt) {
   return 0;
 }
 
-static int stacked_update(ekf_handle* h, int cnt) {
-  if (cnt <= 0) return 0;
-  if (h->lookahead > 0 && h->n >= h->lookahead && !(h->nccl_comm && h->world > 1) && cnt > EKF_UB / 2) return stacked_update_lookahead(h, cnt);
+static int stacked_update(ekf_handle* h, int cnt, bool plane = false) {
+  if (cnt <= 0 && !plane) return 0;
+  if (cnt < 0) cnt = 0;
+  if (!plane && h->lookahead > 0 && h->n >= h->lookahead && !(h->nccl_comm && h->world > 1) && cnt > EKF_UB / 2)
+    return stacked_update_lookahead(h, cnt);
   cudaStream_t st = h->stream;
   // Row-block partition (BASELINE config 4): every rank holds a replica of Sigma, updates only its
   // rows [r0, r1) and exchanges the small panels: W_b rows (S_b needs the camera / feature rows of W_b),
@@ -530,6 +531,27 @@ static int stacked_update(ekf_handle* h, int cnt) {
     { ProfScope ps(h, 3); launch_blk_gather(st, h->Sigma, h->ld, r0, r1, h->ft, f0, cnt, h->delta, h->W, h->nu, &h->launches); }
     if (dist) { ProfScope ps(h, 11); if (ekf_dist_allgather_rows(h, h->W, rpr, EKF_UB)) return (int)cudaErrorUnknown; }
     { ProfScope ps(h, 4); launch_blk_factor(st, h->W, h->ft, f0, cnt, h->nu, h->dcfg, h->Lb, h->Dinv, h->Dblk, h->yb, h->ctl, &h->launches);  /* Lb = S_b scratch, Dinv = L, Dblk = diagonal-block inverses */ }
+    { ProfScope ps(h, 5); launch_blk_V(st, h->W, r0, r1, h->Dinv, h->Dblk, h->yb, h->delta, &h->launches); }
+    if (dist) {
+      ProfScope ps(h, 11);
+      if (ekf_dist_allgather_rows(h, h->W, rpr, EKF_UB)) return (int)cudaErrorUnknown;
+      if (ekf_dist_allgather_rows(h, h->delta, rpr, 1)) return (int)cudaErrorUnknown;
+    }
+    {
+      ProfScope ps(h, 6);
+      const int rc = launch_gemm_nt_sub(st, h->Sigma + (size_t)r0 * h->ld, h->ld, h->W + (size_t)r0 * EKF_UB, EKF_UB, h->W, EKF_UB,
+                                        r1 - r0, h->n, EKF_UB, nullptr, dist ? 0 : h->lower_only, h->gemm_counters, &h->launches);
+      if (rc) return rc;
+    }
+  }
+  if (plane) {   // forsePlane rows as one more block (V:1250-1263)
+    { ProfScope ps(h, 3); launch_plane_gather(st, h->Sigma, h->ld, r0, r1, h->mu, h->delta, h->W, h->nu, h->ctl, &h->launches); }
+    if (dist) { ProfScope ps(h, 11); if (ekf_dist_allgather_rows(h, h->W, rpr, EKF_UB)) return (int)cudaErrorUnknown; }
+    {
+      ProfScope ps(h, 4);
+      launch_plane_S(st, h->W, h->Lb, &h->launches);
+      launch_blk_factor_only(st, h->Lb, h->nu, h->Dinv, h->Dblk, h->yb, h->ctl, &h->launches);
+    }
     { ProfScope ps(h, 5); launch_blk_V(st, h->W, r0, r1, h->Dinv, h->Dblk, h->yb, h->delta, &h->launches); }
     if (dist) {
       ProfScope ps(h, 11);
@@ -586,8 +608,9 @@ int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
   EKF_CUDA_CHECK(cudaMemcpyAsync(&hc, h->ctl, sizeof hc, cudaMemcpyDeviceToHost, st));
   EKF_CUDA_CHECK(cudaStreamSynchronize(st));
   const int n_hi = hc.n_hi;
-  if (n_hi > 0) {
-    int rc = stacked_update(h, n_hi);
+  const bool plane = h->cfg.forsePlane != 0;
+  if (n_hi > 0 || plane) {
+    int rc = stacked_update(h, n_hi, plane);
     if (rc) return ekf_fail_cuda(h, (cudaError_t)rc, "stacked update (hi)", __FILE__, __LINE__);
   }
   // book-keeping + packed result record

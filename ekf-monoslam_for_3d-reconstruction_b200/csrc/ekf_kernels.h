@@ -42,6 +42,9 @@ void launch_blk_S_nu(cudaStream_t st, const double* W, FeatTab ft, int f0, int c
 void launch_blk_G(cudaStream_t st, const double* Vprev, FeatTab ft, int f0, int cnt, double* G, long long* launches);
 void launch_blk_factor_only(cudaStream_t st, const double* Sb, const double* nu, double* Lb, double* Dblk, double* yb, DevCtl* ctl,
                             long long* launches);
+void launch_plane_gather(cudaStream_t st, const double* Sigma, int ld, int row0, int row1, const double* mu, const double* delta,
+                         double* W, double* nu, DevCtl* ctl, long long* launches);
+void launch_plane_S(cudaStream_t st, const double* W, double* Sb, long long* launches);
 void launch_blk_V(cudaStream_t st, double* W, int row0, int row1, const double* Lb, const double* Dblk, const double* yb,
                   double* delta, long long* launches);
 void launch_apply_delta(cudaStream_t st, double* mu, const double* delta, int n, long long* launches);

@@ -189,6 +189,41 @@ __global__ void __launch_bounds__(EKF_UB) k_blk_S(const double* __restrict__ W, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// forsePlane (V:1245-1263, 1272): three pseudo-measurements mu[1] = mu[4] = mu[6] = 0 with R = 1e-5 I3,
+// appended to the second stacked update.  Handled as one more 128-row block whose first three rows are
+// the unit rows e1, e4, e6: W[:, j] = Sigma[:, k_j], nu_j = -(mu[k_j] + delta[k_j]), S = that 3x3 block of
+// W + 1e-5 I (identity elsewhere).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_plane_gather(const double* __restrict__ Sigma, int ld, int row0, int n,
+                                                      const double* __restrict__ mu, const double* __restrict__ delta,
+                                                      double* __restrict__ W, double* __restrict__ nu, DevCtl* ctl) {
+  const int kidx[3] = {1, 4, 6};
+  const int i = row0 + blockIdx.x, s = threadIdx.x;
+  if (i < n) W[(size_t)i * EKF_UB + s] = (s < 3) ? Sigma[(size_t)i * ld + kidx[s]] : 0.0;
+  if (blockIdx.x == 0) {
+    nu[s] = (s < 3) ? (0.0 - mu[kidx[s]]) - delta[kidx[s]] : 0.0;
+    if (s == 0) ctl->k_rows += 3;
+  }
+}
+__global__ void __launch_bounds__(EKF_UB) k_plane_S(const double* __restrict__ W, double* __restrict__ Sb) {
+  const int kidx[3] = {1, 4, 6};
+  const int r = blockIdx.x, s = threadIdx.x;
+  double v = (r == s) ? 1.0 : 0.0;
+  if (r < 3 && s < 3) v = W[(size_t)kidx[r] * EKF_UB + s] + ((r == s) ? 0.00001 : 0.0);
+  Sb[r * EKF_UB + s] = v;
+}
+void launch_plane_gather(cudaStream_t st, const double* Sigma, int ld, int row0, int row1, const double* mu, const double* delta,
+                         double* W, double* nu, DevCtl* ctl, long long* launches) {
+  const int nr = row1 > row0 ? row1 - row0 : 1;
+  k_plane_gather<<<nr, 128, 0, st>>>(Sigma, ld, row0, row1, mu, delta, W, nu, ctl);
+  *launches += 1;
+}
+void launch_plane_S(cudaStream_t st, const double* W, double* Sb, long long* launches) {
+  k_plane_S<<<EKF_UB, EKF_UB, 0, st>>>(W, Sb);
+  *launches += 1;
+}
+
 #include "ekf_factor.cuh"
 __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __restrict__ Sb, const double* __restrict__ nu,
                                                              double* __restrict__ Lout, double* __restrict__ Dblk,

@@ -99,7 +99,7 @@ typedef struct ekf_handle ekf_handle;
 void ekf_config_default(ekf_config* cfg);
 /* VSlamFilter::VSlamFilter (vslamRansac.cpp:142-223).  `feature_capacity` bounds the number of
  * simultaneously tracked features (device buffers are sized for n = 14 + 6*capacity). `device` is
- * a CUDA ordinal.  forsePlane, a window_size outside [3, 31] or a search_clamp above 20 px return
+ * a CUDA ordinal.  A window_size outside [3, 31] or a search_clamp above 20 px return
  * EKF_ERR_UNSUPPORTED. */
 int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_handle** out);
 int ekf_destroy(ekf_handle* h);

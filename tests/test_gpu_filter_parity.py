@@ -203,8 +203,27 @@ def test_motion_blur_templates(gpu_pkg, orc):
     assert blurred >= 10 and g.stats().blur_requests > 0
 
 
+@pytest.mark.parametrize("hard", [False, True])
+def test_forse_plane_pseudo_measurement(gpu_pkg, orc, hard):
+    """forsePlane (vslamRansac.cpp:1245-1263): mu[1] = mu[4] = mu[6] = 0 with R = 1e-5 I appended to the second
+    update — with and without high-innovation rows beside it."""
+    sc = _scene(gpu_pkg, n_features=30, n_frames=5, seed=61, hard=hard)
+    g, o = make_pair(gpu_pkg, orc, sc, forsePlane=1)
+    seed_features(g, sc); seed_features(o, sc)
+    for t in range(1, sc.n_frames):
+        mu, S = o.get_full(); g.set_full(mu, S)
+        img = sc.frame(t)
+        for f in (g, o):
+            f.captureNewFrame(img, sc.stamps[t]); f.predict(); f.update(sc.picks(t, 30))
+        assert (g.stats().n_li, g.stats().n_hi) == (o.stats().n_li, o.stats().n_hi)
+        assert_tables_equal(g, o, ctx=f"plane frame {t}")
+        assert_state_close(g, o, ctx=f"plane frame {t}")
+    mu, _ = g.get_full()
+    assert abs(mu[1]) < 1e-2 and abs(mu[4]) < 1e-2     # the pseudo-measurement holds y and q_x near zero
+
+
 def test_unsupported_configs_fail_loudly(gpu_pkg):
-    for over in (dict(forsePlane=1), dict(window_size=33), dict(search_clamp=25.0)):
+    for over in (dict(window_size=33), dict(search_clamp=25.0), dict(scale=0)):
         cfg = gpu_pkg.default_config(xyz_conversion=0, **over)
         with pytest.raises(gpu_pkg.EkfError):
             gpu_pkg.VSlamFilter(cfg)

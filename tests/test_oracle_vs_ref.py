@@ -167,3 +167,18 @@ def test_motion_blur_templates(pkg, orc, ref, fp64, kind, tol):
         _same_tables(r, o, f"frame {t} update"); _same_state(r, o, tol, f"frame {t} update")
     assert blurred >= 10, f"only {blurred} templates were blurred: the scene does not exercise the path"
     assert o.stats().blur_requests > 0
+
+
+@pytest.mark.parametrize("fp64,kind,tol", VARIANTS)
+def test_forse_plane(pkg, orc, ref, fp64, kind, tol):
+    """forsePlane pseudo-measurement (vslamRansac.cpp:1245-1263, 1272)."""
+    sc = pkg.synth.Scene(n_features=14, n_frames=5, seed=61, hard=True)
+    r, o = _pair(pkg, orc, ref, sc, fp64, kind, forsePlane=1)
+    for f in (r, o):
+        f.captureNewFrame(sc.frame(0), sc.stamps[0])
+        for p in sc.feature_pixels:
+            f.addFeature(*p)
+    for t in range(1, sc.n_frames):
+        for f in (r, o):
+            f.captureNewFrame(sc.frame(t), sc.stamps[t]); f.predict(); f.update(sc.picks(t, 14))
+        _same_tables(r, o, f"frame {t}"); _same_state(r, o, tol, f"frame {t}")
