@@ -44,8 +44,8 @@ struct BatchView {
 // ------------------------------------------------------------------------------------------------
 // predict for one filter per CTA: same arithmetic as k_predict_cov / k_predict_features / k_predict_S2
 // ------------------------------------------------------------------------------------------------
-#define BPRED_THREADS 256
-__global__ void __launch_bounds__(BPRED_THREADS) k_batch_predict(BatchView bv, FrameView fr, DevCfg cfg, double dT, double3 dv,
+#define BPRED_THREADS 128
+__global__ void __launch_bounds__(BPRED_THREADS, 4) k_batch_predict(BatchView bv, FrameView fr, DevCfg cfg, double dT, double3 dv,
                                                                  double3 dw, int vcontrol) {
   __shared__ double F[169], C[169], T[169], Q[169], cam[13];
   const int b = blockIdx.x, tid = threadIdx.x;
