@@ -136,7 +136,13 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
     return EKF_ERR_CUDA;
   };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
-  if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+  {
+    // the filter's own stream carries the serial gain chain: highest priority, so that its CTAs are placed before
+    // those of the downdate running on the second (lowest-priority) stream
+    int plo = 0, phi = 0;
+    cudaDeviceGetStreamPriorityRange(&plo, &phi);
+    if ((e = cudaStreamCreateWithPriority(&h->own_stream, cudaStreamNonBlocking, phi)) != cudaSuccess) return bail(e, "stream");
+  }
   h->stream = h->own_stream;
   if (update_kernels_init() != 0) return bail(cudaGetLastError(), "kernel attributes");
   h->Ncap = feature_capacity;
@@ -160,12 +166,16 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
     for (int i = 0; i < 3; ++i) {
       TRY(cudaEventCreateWithFlags(&h->ev_gather[i], cudaEventDisableTiming)) TRY(cudaEventCreateWithFlags(&h->ev_V[i], cudaEventDisableTiming))
     }
-    TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming))
+    TRY(cudaEventCreateWithFlags(&h->ev_S, cudaEventDisableTiming)) TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming))
     // look-ahead pays off once the downdate of a block (n x n x 128) is long against the block's gain chain:
     // measured +27 % at n = 11972, -7 % at n = 3014 (the chain kernels' large shared-memory CTAs cannot be
     // co-scheduled with the downdate's while it is short); EKF_LOOKAHEAD_MIN_N overrides the threshold
     const char* e = getenv("EKF_LOOKAHEAD_MIN_N");
     h->lookahead = e ? atoi(e) : 6000;
+    // below that threshold: the schedule that starts the downdate of a block beside the NEXT block's Cholesky
+    // (stacked_update_factor_beside_downdate); EKF_PIPE_MIN_N overrides (0 = never)
+    e = getenv("EKF_PIPE_MIN_N");
+    h->pipe_small = e ? atoi(e) : 1000;
   }
   TRY(dalloc(&h->xyz_flag, h->Ncap)) TRY(dalloc(&h->xyz_rmap, 2 * (size_t)h->ncap)) TRY(dalloc(&h->xyz_pos, h->Ncap))
   TRY(dalloc(&h->xyz_coding, h->Ncap)) TRY(dalloc(&h->xyz_y, 3 * (size_t)h->Ncap)) TRY(dalloc(&h->xyz_J, 18 * (size_t)h->Ncap))
@@ -508,11 +518,81 @@ static int stacked_update_lookahead(ekf_handle* h, int cnt) {
   return 0;
 }
 
+// Second schedule of the same look-ahead algebra, for maps whose downdate is SHORT (one or two waves of tiles):
+// there the low-priority downdate, once resident, keeps every SM busy for its whole duration and the single-CTA
+// Cholesky of the next block (140 KB of shared memory: needs a drained SM) queues behind it.  Here the downdate
+// of block b-1 is held back until S_b is ready and is launched right AFTER the Cholesky of block b, so the
+// Cholesky takes its SM first and the downdate fills the other 147: the longest serial kernel of the chain is
+// hidden behind the widest one.  The gather of W'_{b+1} follows the downdate on the second stream and runs beside V_b.
+//   main:  [G_b, corr_b, S_b] -> factor_b -> V_b            second:  downdate_{b-1} -> gather_{b+1}
+static int stacked_update_factor_beside_downdate(ekf_handle* h, int cnt) {
+  cudaStream_t sm = h->stream, sg = h->gemm_stream;
+  const int nblk = (cnt + EKF_UB / 2 - 1) / (EKF_UB / 2);
+  cudaMemsetAsync(h->delta, 0, sizeof(double) * (size_t)h->n, sm);
+  cudaEventRecord(h->ev_fork, sm);
+  cudaStreamWaitEvent(sg, h->ev_fork, 0);
+  for (int b = 0; b < nblk && b < 2; ++b) {   // W'_0 = W_0 and W'_1, both from the prior covariance
+    ProfScope ps(h, 3, sg);
+    launch_blk_gather(sg, h->Sigma, h->ld, 0, h->n, h->ft, b * (EKF_UB / 2), cnt, nullptr, h->Wbuf[b], nullptr, &h->launches);
+    cudaEventRecord(h->ev_gather[b], sg);
+  }
+  for (int b = 0; b < nblk; ++b) {
+    const int f0 = b * (EKF_UB / 2);
+    double* Wb = h->Wbuf[b % 3];
+    cudaStreamWaitEvent(sm, h->ev_gather[b % 3], 0);
+    if (b > 0) {
+      ProfScope ps(h, 3);
+      double* Vp = h->Wbuf[(b - 1) % 3];
+      launch_blk_G(sm, Vp, h->ft, f0, cnt, h->Gbuf, &h->launches);
+      const int rc = launch_gemm_nt_sub(sm, Wb, EKF_UB, Vp, EKF_UB, h->Gbuf, EKF_UB, h->n, EKF_UB, EKF_UB, nullptr, 0, h->gemm_counters, &h->launches);
+      if (rc) return rc;
+    }
+    { ProfScope ps(h, 4); launch_blk_S_nu(sm, Wb, h->ft, f0, cnt, h->dcfg, h->delta, h->Lb, h->nu, &h->launches); }
+    if (b > 0) {   // release the downdate of block b-1 (it already waits for V_{b-1})
+      cudaEventRecord(h->ev_S, sm);
+      cudaStreamWaitEvent(sg, h->ev_S, 0);
+    }
+    { ProfScope ps(h, 4); launch_blk_factor_only(sm, h->Lb, h->nu, h->Dinv, h->Dblk, h->yb, h->ctl, &h->launches); }
+    if (b > 0) {
+      double* Vp = h->Wbuf[(b - 1) % 3];
+      {
+        ProfScope ps(h, 6, sg);
+        const int rc = launch_gemm_nt_sub(sg, h->Sigma, h->ld, Vp, EKF_UB, Vp, EKF_UB, h->n, h->n, EKF_UB, nullptr, h->lower_only, h->gemm_counters, &h->launches);
+        if (rc) return rc;
+      }
+      if (b + 1 < nblk) {
+        ProfScope ps(h, 3, sg);
+        launch_blk_gather(sg, h->Sigma, h->ld, 0, h->n, h->ft, (b + 1) * (EKF_UB / 2), cnt, nullptr, h->Wbuf[(b + 1) % 3], nullptr, &h->launches);
+        cudaEventRecord(h->ev_gather[(b + 1) % 3], sg);
+      }
+    }
+    { ProfScope ps(h, 5); launch_blk_V(sm, Wb, 0, h->n, h->Dinv, h->Dblk, h->yb, h->delta, &h->launches); }
+    cudaEventRecord(h->ev_V[b % 3], sm);
+    cudaStreamWaitEvent(sg, h->ev_V[b % 3], 0);
+  }
+  {
+    double* Vl = h->Wbuf[(nblk - 1) % 3];
+    ProfScope ps(h, 6, sg);
+    const int rc = launch_gemm_nt_sub(sg, h->Sigma, h->ld, Vl, EKF_UB, Vl, EKF_UB, h->n, h->n, EKF_UB, nullptr, h->lower_only, h->gemm_counters, &h->launches);
+    if (rc) return rc;
+  }
+  cudaEventRecord(h->ev_join, sg);
+  cudaStreamWaitEvent(sm, h->ev_join, 0);
+  {
+    ProfScope ps(h, 7);
+    launch_apply_delta(sm, h->mu, h->delta, h->n, &h->launches);
+    launch_quat_normalize(sm, h->Sigma, h->ld, h->n, h->mu, h->ctl, &h->launches);
+  }
+  return 0;
+}
+
 static int stacked_update(ekf_handle* h, int cnt, bool plane = false) {
   if (cnt <= 0 && !plane) return 0;
   if (cnt < 0) cnt = 0;
-  if (!plane && h->lookahead > 0 && h->n >= h->lookahead && !(h->nccl_comm && h->world > 1) && cnt > EKF_UB / 2)
-    return stacked_update_lookahead(h, cnt);
+  if (!plane && !(h->nccl_comm && h->world > 1) && cnt > EKF_UB / 2) {
+    if (h->lookahead > 0 && h->n >= h->lookahead) return stacked_update_lookahead(h, cnt);
+    if (h->pipe_small > 0 && h->n >= h->pipe_small) return stacked_update_factor_beside_downdate(h, cnt);
+  }
   cudaStream_t st = h->stream;
   // Row-block partition (BASELINE config 4): every rank holds a replica of Sigma, updates only its
   // rows [r0, r1) and exchanges the small panels: W_b rows (S_b needs the camera / feature rows of W_b),

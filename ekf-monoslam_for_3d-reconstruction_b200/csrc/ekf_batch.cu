@@ -184,7 +184,7 @@ struct UpdSmem {
   int* ibuf;      // cand[BNCAP], fids[BNCAP], poss[BNCAP], nds[BNCAP]
 };
 #define BLDD 36
-static constexpr size_t kFactDoubles = 2 * 16 * BNMAX > cta_chol22_smem_doubles<BK>() ? 2 * 16 * BNMAX : cta_chol22_smem_doubles<BK>();
+static constexpr size_t kFactDoubles = 2 * 16 * BNMAX > cta_chol_panel_smem_doubles<BK>() ? 2 * 16 * BNMAX : cta_chol_panel_smem_doubles<BK>();
 static constexpr size_t kUpdSmemDoubles =
     (size_t)BNMAX * BLDW + kFactDoubles + (BK / 32) * 32 * BLDD + (size_t)BK * BLDW + BK + BK + BNMAX + BNCAP * 27 + 48 + (4 * BNCAP) / 2;
 static constexpr size_t kUpdSmemBytes = kUpdSmemDoubles * sizeof(double);
@@ -273,7 +273,7 @@ __device__ void cta_stacked_update(const UpdSmem& sm, double* __restrict__ Sigma
     sm.Sb[r * BLDW + s] = v;
   }
   __syncthreads();
-  cta_chol22<BK>(sm.fact, sm.Sb, BLDW, sm.nu, sm.Sb, BLDW, sm.Dv, BLDD, sm.y, &ctl->chol_fail);
+  cta_chol_panel<BK>(sm.fact, sm.Sb, BLDW, sm.nu, sm.Sb, BLDW, sm.Dv, BLDD, sm.y, &ctl->chol_fail);
   // V = W L^-T in place: every warp owns 8-row tiles for the whole blocked triangular solve
   for (int rt = warp; rt < BNMAX / 8; rt += BUPD_THREADS / 32) {
     double part = warp_trsm_tile<BK>(sm.W + (size_t)rt * 8 * BLDW, BLDW, sm.Sb, BLDW, sm.Dv, BLDD, sm.y);

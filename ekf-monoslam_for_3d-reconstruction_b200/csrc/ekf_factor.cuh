@@ -33,11 +33,42 @@ __device__ __forceinline__ void dmma884f(double& d0, double& d1, double a, doubl
                : "d"(a), "d"(b));
 }
 
-// shared-memory doubles needed by cta_chol22<NB>
+// shared-memory doubles needed by cta_chol_panel<NB>
 template <int NB>
-__host__ __device__ constexpr int cta_chol22_smem_doubles() {
-  // A[(NB + 8)][NB + 8] + pivot reciprocals[NB] + tile list (2 bytes per tile, T (T + 1) / 2 + T tiles)
-  return (NB + 8) * (NB + 8) + NB + (((NB / 8) * (NB / 8 + 1) / 2 + NB / 8) * 2 + 7) / 8;
+__host__ __device__ constexpr int cta_chol_panel_smem_doubles() {
+  // A[(NB + 8)][NB + 8] + pivot reciprocals[NB] + pivot parameters[16] + tile list (2 bytes per tile)
+  return (NB + 8) * (NB + 8) + NB + 16 + (((NB / 8) * (NB / 8 + 1) / 2 + NB / 8) * 2 + 7) / 8;
+}
+
+// 4 x 4 pivot block at (p, p): factored by every lane of the calling warp (four rsqrt on the chain);
+// lane 0 publishes the parameters the panel solve needs and writes the block's final values.
+template <bool SKIP = false>
+__device__ __forceinline__ void chol_pivot4(double* A, int FLD, int p, double* piv, double* rinvs, int* chol_fail, int lane) {
+  double* Pv = A + p * FLD + p;
+  if (SKIP) { if (lane < 16) { piv[lane] = 0.5; rinvs[p + (lane & 3)] = 0.5; } return; }
+  const double a00 = Pv[0], a10 = Pv[FLD], a11 = Pv[FLD + 1], a20 = Pv[2 * FLD], a21 = Pv[2 * FLD + 1], a22 = Pv[2 * FLD + 2],
+               a30 = Pv[3 * FLD], a31 = Pv[3 * FLD + 1], a32 = Pv[3 * FLD + 2], a33 = Pv[3 * FLD + 3];
+  const double r0 = rsqrt(a00);
+  const double l10 = a10 * r0, l20 = a20 * r0, l30 = a30 * r0;
+  const double t11 = a11 - l10 * l10;
+  const double r1 = rsqrt(t11);
+  const double l21 = (a21 - l20 * l10) * r1, l31 = (a31 - l30 * l10) * r1;
+  const double t22 = a22 - l20 * l20 - l21 * l21;
+  const double r2 = rsqrt(t22);
+  const double l32 = (a32 - l30 * l20 - l31 * l21) * r2;
+  const double t33 = a33 - l30 * l30 - l31 * l31 - l32 * l32;
+  const double r3 = rsqrt(t33);
+  __syncwarp();
+  if (lane == 0) {
+    if (!(a00 > 0.0) || !(t11 > 0.0) || !(t22 > 0.0) || !(t33 > 0.0)) *chol_fail = 1;
+    Pv[0] = a00 * r0;
+    Pv[FLD] = l10; Pv[FLD + 1] = t11 * r1;
+    Pv[2 * FLD] = l20; Pv[2 * FLD + 1] = l21; Pv[2 * FLD + 2] = t22 * r2;
+    Pv[3 * FLD] = l30; Pv[3 * FLD + 1] = l31; Pv[3 * FLD + 2] = l32; Pv[3 * FLD + 3] = t33 * r3;
+    rinvs[p] = r0; rinvs[p + 1] = r1; rinvs[p + 2] = r2; rinvs[p + 3] = r3;
+    piv[0] = r0; piv[1] = r1; piv[2] = r2; piv[3] = r3;
+    piv[4] = l10; piv[5] = l20; piv[6] = l30; piv[7] = l21; piv[8] = l31; piv[9] = l32;
+  }
 }
 
 // fsm: workspace (see above).  Sb: NB x NB symmetric positive definite (leading dimension lds; only
@@ -47,27 +78,45 @@ __host__ __device__ constexpr int cta_chol22_smem_doubles() {
 //   yout  NB: L^-1 nu
 // Lout may alias Sb.  blockDim.x must be FACT_THREADS.  Ends with a barrier.
 //
-// Steps of FOUR columns (two features): the 4 x 4 pivot block is factored redundantly by every thread
-// (four rsqrt on the chain), one thread per row solves the panel, and the rank-4 trailing update is one
-// DMMA.8x8x4 per 8 x 8 tile of the lower triangle (tiles on a fixed 8-aligned grid; fragment rows that
-// lie left of / above the trailing block are zeroed, so finished entries of L are never touched).
-template <int NB>
-__device__ void cta_chol22(double* fsm, const double* Sb, int lds, const double* nu, double* Lout, int ldl, double* Dout,
-                           int ldd, double* yout, int* chol_fail) {
-  // row stride = 8 (mod 16) doubles: the C-tile accesses of the rank-4 update are 16-byte vectors without bank
+// Panel-blocked right-looking Cholesky with a pivot look-ahead.  Columns are processed in panels of 32;
+// inside a panel, steps of FOUR columns (two features):
+//   * every thread reads the ten parameters of the step's factored 4 x 4 pivot block (broadcast) and one
+//     thread per row solves the four panel columns;
+//   * the rank-4 update is applied only to the remaining columns of the PANEL (at most 62 8 x 8 tiles, one
+//     DMMA.8x8x4 each, one round of <= 5 tiles per warp), and while warps 1.. do that, warp 0 updates the tile
+//     holding the NEXT pivot block first and factors it (four rsqrt on the chain) — the pivot chain is off
+//     the other warps' critical path;
+//   * after the panel's last step the columns right of the panel receive one rank-32 update (8 DMMAs per
+//     tile, C tile read and written once), again with warp 0 running ahead to the next pivot.
+// Tiles lie on a fixed 8-aligned grid; fragment rows left of / above the trailing block are zeroed, so
+// finished entries of L are never touched.  nu rides along as row NB (tile row T): its panel entries come
+// out as y = L^-1 nu.  The earlier version applied every rank-4 update to the whole trailing matrix and
+// factored the pivot between two barriers: 57 us per 128 x 128 block against ~?? us now (tools/factor_probe.cu).
+// KO: timing knock-outs for tools/factor_probe.cu only (1 pivot chain, 2 panel solve, 4 rank-4 update, 8 rank-32 update,
+// 16 diagonal-block inverses, 32 barriers); production code instantiates KO = 0.
+template <int NB, int KO = 0>
+__device__ void cta_chol_panel(double* fsm, const double* Sb, int lds, const double* nu, double* Lout, int ldl, double* Dout,
+                               int ldd, double* yout, int* chol_fail) {
+  // row stride = 8 (mod 16) doubles: the C-tile accesses of the updates are 16-byte vectors without bank
   // conflicts and the A/B fragment loads 2-way; an odd stride made every access 4-way conflicted (smem-bound)
-  constexpr int NP = NB / 32, FLD = NB + 8, T = NB / 8;
-  double* A = fsm;                      // [(NB + 8)][FLD]: rows 0..NB-1 S / L, row NB nu / y, rows NB+1.. padding
+  constexpr int NP = NB / 32, FLD = NB + 8, T = NB / 8, NTILES = T * (T + 1) / 2 + T;
+  constexpr int UW = FACT_WARPS - 1;    // warps 1.. carry the updates, warp 0 the pivot look-ahead
+  double* A = fsm;                      // [(NB + 8)][FLD]: rows 0..NB-1 S / L, row NB nu / y, rows NB+1.. zero padding
   double* rinvs = A + (NB + 8) * FLD;   // [NB]
-  // tile list ordered by tile column J descending: the tiles of a trailing block that starts at tile
-  // index I0 (J >= I0) are always a prefix of it
-  unsigned char* tl = reinterpret_cast<unsigned char*>(rinvs + NB);
+  double* piv = rinvs + NB;             // [16] r0..r3, l10 l20 l30 l21 l31 l32 of the current step
+  // tile list: panels ascending; inside a panel tile columns J descending, rows I = J .. T.  The tiles a
+  // step needs (J >= I0 inside its panel) are a prefix of the panel's segment, the tiles right of a panel
+  // are the rest of the list.
+  unsigned char* tl = reinterpret_cast<unsigned char*>(piv + 16);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+  auto seg = [](int P) { const int j = 4 * P; return j * (T + 1) - j * (j - 1) / 2; };   // tiles with J < 4 P
   FACC_INIT;
-  if (tid == 0) {
-    int k = 0;
-    for (int J = T - 1; J >= 0; --J)
-      for (int I = J; I <= T; ++I) { tl[2 * k] = (unsigned char)I; tl[2 * k + 1] = (unsigned char)J; ++k; }
+  if (tid < NTILES) {
+    int P = 0;
+    while (P + 1 < NP && seg(P + 1) <= tid) ++P;
+    int rem = tid - seg(P), J = 4 * P + 3;
+    while (rem >= T - J + 1) { rem -= T - J + 1; --J; }
+    tl[2 * tid] = (unsigned char)(J + rem); tl[2 * tid + 1] = (unsigned char)J;
   }
   for (int e = tid; e < NB * NB; e += FACT_THREADS) {
     const int r = e / NB, c = e - r * NB;
@@ -75,110 +124,151 @@ __device__ void cta_chol22(double* fsm, const double* Sb, int lds, const double*
   }
   for (int e = tid; e < 8 * FLD; e += FACT_THREADS) A[NB * FLD + e] = (e < NB) ? nu[e] : 0.0;
   __syncthreads();
+  if (warp == 0) chol_pivot4<(KO & 1) != 0>(A, FLD, 0, piv, rinvs, chol_fail, lane);
+  __syncthreads();
   FACC(0);
   for (int p = 0; p < NB; p += 4) {
-    // 4 x 4 pivot block (shared-memory broadcast), factored by every thread
-    const double* Pv = A + p * FLD + p;
-    const double a00 = Pv[0], a10 = Pv[FLD], a11 = Pv[FLD + 1], a20 = Pv[2 * FLD], a21 = Pv[2 * FLD + 1], a22 = Pv[2 * FLD + 2],
-                 a30 = Pv[3 * FLD], a31 = Pv[3 * FLD + 1], a32 = Pv[3 * FLD + 2], a33 = Pv[3 * FLD + 3];
-    const double r0 = rsqrt(a00);
-    const double l10 = a10 * r0, l20 = a20 * r0, l30 = a30 * r0;
-    const double t11 = a11 - l10 * l10;
-    const double r1 = rsqrt(t11);
-    const double l21 = (a21 - l20 * l10) * r1, l31 = (a31 - l30 * l10) * r1;
-    const double t22 = a22 - l20 * l20 - l21 * l21;
-    const double r2 = rsqrt(t22);
-    const double l32 = (a32 - l30 * l20 - l31 * l21) * r2;
-    const double t33 = a33 - l30 * l30 - l31 * l31 - l32 * l32;
-    const double r3 = rsqrt(t33);
-    if (r3 == 123.456) *chol_fail = 2;   // keeps the chain from being sunk below the stamp in probe builds (never true)
-    FACC(1);
-    // panel: rows p + 4 .. NB (row NB is nu), one thread per row
-    for (int r = p + 4 + tid; r <= NB; r += FACT_THREADS) {
-      double* row = A + r * FLD + p;
-      const double x0 = row[0] * r0;
-      const double x1 = (row[1] - x0 * l10) * r1;
-      const double x2 = (row[2] - x0 * l20 - x1 * l21) * r2;
-      const double x3 = (row[3] - x0 * l30 - x1 * l31 - x2 * l32) * r3;
-      row[0] = x0; row[1] = x1; row[2] = x2; row[3] = x3;
-    }
-    FACC(2);
-    __syncthreads();
-    FACC(3);
-    if (tid == 0) {
-      if (!(a00 > 0.0) || !(t11 > 0.0) || !(t22 > 0.0) || !(t33 > 0.0)) *chol_fail = 1;
-      double* Pw = A + p * FLD + p;
-      Pw[0] = a00 * r0;
-      Pw[FLD] = l10; Pw[FLD + 1] = t11 * r1;
-      Pw[2 * FLD] = l20; Pw[2 * FLD + 1] = l21; Pw[2 * FLD + 2] = t22 * r2;
-      Pw[3 * FLD] = l30; Pw[3 * FLD + 1] = l31; Pw[3 * FLD + 2] = l32; Pw[3 * FLD + 3] = t33 * r3;
-      rinvs[p] = r0; rinvs[p + 1] = r1; rinvs[p + 2] = r2; rinvs[p + 3] = r3;
-    }
-    // rank-4 trailing update on the tensor pipe: lower 8 x 8 tiles (I >= J >= I0) plus the nu tile row
+    const int P = p >> 5, pend = 32 * P + 32, base = p + 4;
     {
-      const int base = p + 4, I0 = base >> 3, nt = T - I0;
-      const int ntile = nt * (nt + 1) / 2 + nt;        // tiles (I, J) with J >= I0, I = J .. T (tile row T holds nu)
-      // four tiles of a warp in flight at a time: the DMMA accumulate latency, not its issue rate, is the cost here
-      for (int t0 = warp; t0 < ntile; t0 += 4 * FACT_WARPS) {
-        double a[4], b[4], d0[4], d1[4];
-        double* cp[4];
-        bool wr0[4], wr1[4];
+      const double r0 = piv[0], r1 = piv[1], r2 = piv[2], r3 = piv[3], l10 = piv[4], l20 = piv[5], l30 = piv[6], l21 = piv[7],
+                   l31 = piv[8], l32 = piv[9];
+      // panel: rows p + 4 .. NB (row NB is nu), one thread per row
+      for (int r = base + tid; r <= NB && !(KO & 2); r += FACT_THREADS) {
+        double* row = A + r * FLD + p;
+        const double x0 = row[0] * r0;
+        const double x1 = (row[1] - x0 * l10) * r1;
+        const double x2 = (row[2] - x0 * l20 - x1 * l21) * r2;
+        const double x3 = (row[3] - x0 * l30 - x1 * l31 - x2 * l32) * r3;
+        row[0] = x0; row[1] = x1; row[2] = x2; row[3] = x3;
+      }
+    }
+    FACC(1);
+    if (!(KO & 32)) __syncthreads();
+    FACC(2);
+    if (base < pend) {
+      // rank-4 update of the panel's remaining columns [base, pend): tiles (I, J), I0 <= J < 4 P + 4, I = J .. T
+      const int I0 = base >> 3, nJ = 4 * P + 4 - I0;
+      const int ntile = nJ * (T + 1) - (I0 + 4 * P + 3) * nJ / 2;
+      const int pidx = ntile - (T - I0 + 1);          // tile (I0, I0): holds the next pivot block
+      const unsigned char* tp = tl + 2 * seg(P);
+      if (warp == 0) {
+        const int ra = 8 * I0 + g;
+        const bool arow = ra >= base;
+        const double a = arow ? -A[ra * FLD + p + t4] : 0.0;
+        const double b = arow ? A[ra * FLD + p + t4] : 0.0;
+        double* cp = A + ra * FLD + 8 * I0 + 2 * t4;
+        const int col = 8 * I0 + 2 * t4;
+        double2 cv = *reinterpret_cast<const double2*>(cp);
+        dmma884f(cv.x, cv.y, a, b);
+        if (arow && col >= base) *reinterpret_cast<double2*>(cp) = cv;   // base is a multiple of 4: col, col + 1 on the same side
+        __syncwarp();
+        chol_pivot4<(KO & 1) != 0>(A, FLD, base, piv, rinvs, chol_fail, lane);
+      } else if (!(KO & 4)) {
+        for (int t0 = warp - 1; t0 < ntile; t0 += 5 * UW) {
+          double a[5], b[5], d0[5], d1[5];
+          double* cp[5];
+          bool wr[5];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int t = t0 + u * FACT_WARPS;
-          const bool live = t < ntile;
-          const int I = live ? tl[2 * t] : T, J = live ? tl[2 * t + 1] : 0;
-          const int ra = 8 * I + g, rb = 8 * J + g;
-          const bool arow = live && ra >= base && !(I == T && g > 0);   // rows above the trailing block / padding rows past nu: nothing
-          a[u] = arow ? -A[ra * FLD + p + t4] : 0.0;
-          b[u] = (live && rb >= base) ? A[rb * FLD + p + t4] : 0.0;
-          cp[u] = A + ra * FLD + 8 * J + 2 * t4;
-          const int col = 8 * J + 2 * t4;
-          // finished entries (pivot rows / panel columns inside a boundary tile) are left alone: thread 0 is
-          // writing the pivot block's final values concurrently
-          wr0[u] = arow && col >= base;
-          wr1[u] = arow && col + 1 >= base;
-          const double2 cv = live ? *reinterpret_cast<const double2*>(cp[u]) : make_double2(0.0, 0.0);
-          d0[u] = cv.x; d1[u] = cv.y;
+          for (int u = 0; u < 5; ++u) {
+            const int t = t0 + u * UW;
+            const bool live = t < ntile && t != pidx;
+            const int I = live ? tp[2 * t] : T, J = live ? tp[2 * t + 1] : 0;
+            const int ra = 8 * I + g, rb = 8 * J + g;
+            const bool arow = live && ra >= base && !(I == T && g > 0);   // rows above the trailing block / padding rows past nu: nothing
+            a[u] = arow ? -A[ra * FLD + p + t4] : 0.0;
+            b[u] = (live && rb >= base) ? A[rb * FLD + p + t4] : 0.0;
+            cp[u] = A + ra * FLD + 8 * J + 2 * t4;
+            wr[u] = arow && 8 * J + 2 * t4 >= base;    // finished columns inside a boundary tile are left alone
+            const double2 cv = live ? *reinterpret_cast<const double2*>(cp[u]) : make_double2(0.0, 0.0);
+            d0[u] = cv.x; d1[u] = cv.y;
+          }
+#pragma unroll
+          for (int u = 0; u < 5; ++u) dmma884f(d0[u], d1[u], a[u], b[u]);
+#pragma unroll
+          for (int u = 0; u < 5; ++u)
+            if (wr[u]) *reinterpret_cast<double2*>(cp[u]) = make_double2(d0[u], d1[u]);
         }
+      }
+    } else if (pend < NB) {
+      // rank-32 update of everything right of the finished panel: tiles seg(P + 1) .. NTILES, K = columns [32 P, pend)
+      const int first = seg(P + 1), ntile = NTILES - first;
+      const int I0 = 4 * P + 4, pidx = seg(P + 2) - first - (T - I0 + 1);   // tile (I0, I0) in the list
+      const unsigned char* tp = tl + 2 * first;
+      const int k0 = 32 * P;
+      if (warp == 0) {
+        const int ra = 8 * I0 + g;
+        double* cp = A + ra * FLD + 8 * I0 + 2 * t4;
+        double2 cv = *reinterpret_cast<const double2*>(cp);
+        double c1x = 0.0, c1y = 0.0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) dmma884f(d0[u], d1[u], a[u], b[u]);
+        for (int kq = 0; kq < 8; kq += 2) {
+          const double f0 = A[ra * FLD + k0 + 4 * kq + t4], f1 = A[ra * FLD + k0 + 4 * kq + 4 + t4];
+          dmma884f(cv.x, cv.y, -f0, f0);
+          dmma884f(c1x, c1y, -f1, f1);
+        }
+        *reinterpret_cast<double2*>(cp) = make_double2(cv.x + c1x, cv.y + c1y);
+        __syncwarp();
+        chol_pivot4<(KO & 1) != 0>(A, FLD, base, piv, rinvs, chol_fail, lane);
+      } else if (!(KO & 8)) {
+        for (int t0 = warp - 1; t0 < ntile; t0 += 3 * UW) {
+          double d0[3], d1[3];
+          double* cp[3];
+          const double *ap[3], *bp[3];
+          bool live[3];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (wr0[u] && wr1[u]) *reinterpret_cast<double2*>(cp[u]) = make_double2(d0[u], d1[u]);
-          else if (wr0[u]) cp[u][0] = d0[u];
-          else if (wr1[u]) cp[u][1] = d1[u];
+          for (int u = 0; u < 3; ++u) {
+            const int t = t0 + u * UW;
+            live[u] = t < ntile && t != pidx;
+            const int I = live[u] ? tp[2 * t] : T, J = live[u] ? tp[2 * t + 1] : 0;
+            ap[u] = A + (8 * I + g) * FLD + k0 + t4;
+            bp[u] = A + (8 * J + g) * FLD + k0 + t4;
+            cp[u] = A + (8 * I + g) * FLD + 8 * J + 2 * t4;
+            const double2 cv = *reinterpret_cast<const double2*>(cp[u]);
+            d0[u] = cv.x; d1[u] = cv.y;
+          }
+#pragma unroll
+          for (int kq = 0; kq < 8; ++kq) {
+#pragma unroll
+            for (int u = 0; u < 3; ++u) dmma884f(d0[u], d1[u], -ap[u][4 * kq], bp[u][4 * kq]);
+          }
+          // padding rows past nu (tile row T, g > 0) are zero in every column: their update is zero
+#pragma unroll
+          for (int u = 0; u < 3; ++u)
+            if (live[u]) *reinterpret_cast<double2*>(cp[u]) = make_double2(d0[u], d1[u]);
         }
       }
     }
+    FACC(3);
+    if (!(KO & 32)) __syncthreads();
     FACC(4);
-    __syncthreads();
-    FACC(5);
   }
   // inverses of the diagonal blocks: warp J solves X L_JJ^T = I by substitution, lane = row r of
   // X = L_JJ^-T, i.e. column r of L_JJ^-1
-  if (warp < NP) {
+  if (warp < NP && !(KO & 16)) {
     const int o = 32 * warp;
     double x[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
-      double sx = (c == lane) ? 1.0 : 0.0;
+      double s0 = (c == lane) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;   // four chains: the sum is latency-bound
 #pragma unroll
-      for (int dd = 0; dd < c; ++dd) sx -= x[dd] * A[(o + c) * FLD + o + dd];
-      x[c] = sx * rinvs[o + c];
+      for (int dd = 0; dd < c; ++dd) {
+        const double pr = x[dd] * A[(o + c) * FLD + o + dd];
+        if ((dd & 3) == 0) s0 -= pr; else if ((dd & 3) == 1) s1 -= pr; else if ((dd & 3) == 2) s2 -= pr; else s3 -= pr;
+      }
+      x[c] = ((s0 + s1) + (s2 + s3)) * rinvs[o + c];
     }
     double* X = Dout + (size_t)warp * 32 * ldd;
 #pragma unroll
     for (int c = 0; c < 32; ++c) X[c * ldd + lane] = x[c];  // Dinv[c][r] = X[r][c]
   }
-  FACC(6);
+  FACC(5);
   for (int e = tid; e < NB * NB; e += FACT_THREADS) {
     const int r = e / NB, c = e - r * NB;
     Lout[(size_t)r * ldl + c] = (c <= r) ? A[r * FLD + c] : 0.0;
   }
   for (int e = tid; e < NB; e += FACT_THREADS) yout[e] = A[NB * FLD + e];
   __syncthreads();
-  FACC(7);
+  FACC(6);
   FACC_DUMP;
 }
 

@@ -46,7 +46,8 @@ struct ekf_handle {
   cudaStream_t gemm_stream = nullptr;
   double* Wbuf[3] = {nullptr, nullptr, nullptr};   // Wbuf[0] == W
   double* Gbuf = nullptr;
-  cudaEvent_t ev_gather[3] = {nullptr, nullptr, nullptr}, ev_V[3] = {nullptr, nullptr, nullptr}, ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_gather[3] = {nullptr, nullptr, nullptr}, ev_V[3] = {nullptr, nullptr, nullptr}, ev_fork = nullptr, ev_join = nullptr, ev_S = nullptr;
+  int pipe_small = 1000;  // minimum state dimension for the factor-beside-downdate schedule (0 = never)
   int lookahead = 6000;   // minimum state dimension for the look-ahead pipeline (0 = never)
   // row-block partitioned update across ranks (ekf_dist.cu): NCCL communicator of this handle, or null
   void* nccl_comm = nullptr;

@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __res
                                                              double* __restrict__ Lout, double* __restrict__ Dblk,
                                                              double* __restrict__ yout, DevCtl* ctl) {
   extern __shared__ __align__(16) double fsm[];
-  cta_chol22<EKF_UB>(fsm, Sb, EKF_UB, nu, Lout, EKF_UB, Dblk, 32, yout, &ctl->chol_fail);
+  cta_chol_panel<EKF_UB>(fsm, Sb, EKF_UB, nu, Lout, EKF_UB, Dblk, 32, yout, &ctl->chol_fail);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(256) k_bookkeeping(const double* __restrict__ 
 }
 
 // ---- launch wrappers ---------------------------------------------------------------------------
-static const size_t kFactSmem = (size_t)cta_chol22_smem_doubles<EKF_UB>() * sizeof(double);
+static const size_t kFactSmem = (size_t)cta_chol_panel_smem_doubles<EKF_UB>() * sizeof(double);
 static const size_t kVSmem = (size_t)(EKF_UB * VT_LD + (EKF_UB / 32) * 32 * VT_LDD + VT_ROWS * VT_LD + EKF_UB) * sizeof(double);
 
 int update_kernels_init() {

@@ -17,7 +17,7 @@ int main() {
   cudaMemcpy(dS, S.data(), n * n * 8, cudaMemcpyHostToDevice); cudaMemcpy(dnu, nu.data(), n * 8, cudaMemcpyHostToDevice);
   update_kernels_init();
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  const char* names[8] = {"load", "pivot4x4", "panel", "barrier1", "trailing", "barrier2", "dinv", "out"};
+  const char* names[8] = {"load+piv0", "panel", "barrier1", "update/LA", "barrier2", "dinv", "out", "-"};
   for (int rep = 0; rep < 3; ++rep) {
     long long zero[16] = {0}; cudaMemcpyToSymbol(g_fact_acc, zero, sizeof zero);
     cudaEventRecord(e0);
