@@ -118,11 +118,25 @@ __device__ void cta_chol_panel(double* fsm, const double* Sb, int lds, const dou
     while (rem >= T - J + 1) { rem -= T - J + 1; --J; }
     tl[2 * tid] = (unsigned char)(J + rem); tl[2 * tid + 1] = (unsigned char)J;
   }
-  for (int e = tid; e < NB * NB; e += FACT_THREADS) {
-    const int r = e / NB, c = e - r * NB;
-    A[r * FLD + c] = (c <= r) ? Sb[(size_t)r * lds + c] : 0.0;
+  {
+    // lower triangle of S as 16-byte vectors, every load of a thread in flight before the first store (one latency,
+    // not NB * NB / FACT_THREADS of them); Sb rows must be 16-byte aligned (lds even)
+    constexpr int NV = NB * NB / 2 / FACT_THREADS;
+    double2 v[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      const int e = tid + q * FACT_THREADS, r = e / (NB / 2), c = (e % (NB / 2)) * 2;
+      v[q] = (c <= r) ? *reinterpret_cast<const double2*>(Sb + (size_t)r * lds + c) : make_double2(0.0, 0.0);
+    }
+    const double nuv = (tid < NB) ? nu[tid] : 0.0;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      const int e = tid + q * FACT_THREADS, r = e / (NB / 2), c = (e % (NB / 2)) * 2;
+      if (c + 1 > r) v[q].y = 0.0;
+      *reinterpret_cast<double2*>(A + r * FLD + c) = v[q];
+    }
+    for (int e = tid; e < 8 * FLD; e += FACT_THREADS) A[NB * FLD + e] = (e == tid && e < NB) ? nuv : 0.0;
   }
-  for (int e = tid; e < 8 * FLD; e += FACT_THREADS) A[NB * FLD + e] = (e < NB) ? nu[e] : 0.0;
   __syncthreads();
   if (warp == 0) chol_pivot4<(KO & 1) != 0>(A, FLD, 0, piv, rinvs, chol_fail, lane);
   __syncthreads();
@@ -262,9 +276,12 @@ __device__ void cta_chol_panel(double* fsm, const double* Sb, int lds, const dou
     for (int c = 0; c < 32; ++c) X[c * ldd + lane] = x[c];  // Dinv[c][r] = X[r][c]
   }
   FACC(5);
-  for (int e = tid; e < NB * NB; e += FACT_THREADS) {
-    const int r = e / NB, c = e - r * NB;
-    Lout[(size_t)r * ldl + c] = (c <= r) ? A[r * FLD + c] : 0.0;
+  for (int e = tid; e < NB * NB / 2; e += FACT_THREADS) {   // diagonal tiles carry update residue above the diagonal: masked
+    const int r = e / (NB / 2), c = (e % (NB / 2)) * 2;
+    double2 v = *reinterpret_cast<const double2*>(A + r * FLD + c);
+    if (c > r) v.x = 0.0;
+    if (c + 1 > r) v.y = 0.0;
+    *reinterpret_cast<double2*>(Lout + (size_t)r * ldl + c) = v;
   }
   for (int e = tid; e < NB; e += FACT_THREADS) yout[e] = A[NB * FLD + e];
   __syncthreads();

@@ -251,21 +251,29 @@ __global__ void __launch_bounds__(VT_THREADS) k_blk_V(double* __restrict__ W, in
   double* ys = Ws + VT_ROWS * VT_LD;         // [EKF_UB]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row0 = rbase + blockIdx.x * VT_ROWS;   // rows [rbase, n): the caller's row block
-  for (int e = tid; e < EKF_UB * EKF_UB / 2; e += VT_THREADS) {
+  // everything is staged with cp.async, all copies in flight at once (the kernel is latency-bound: 95 CTAs, one wave).
+  // Of L only the 32 x 32 blocks strictly below the diagonal are read by the solve — the diagonal blocks enter
+  // through their inverses D — so 48 KB instead of 128 KB per CTA.
+  auto cp16 = [](double* sdst, const double* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc));
+  };
+  for (int e = tid; e < VT_ROWS * EKF_UB / 2; e += VT_THREADS) {
     const int r = e >> 6, c = (e & 63) * 2;
-    *reinterpret_cast<double2*>(Ls + r * VT_LD + c) = *reinterpret_cast<const double2*>(Lg + r * EKF_UB + c);
+    if (row0 + r < n) cp16(Ws + r * VT_LD + c, W + (size_t)(row0 + r) * EKF_UB + c);
+    else *reinterpret_cast<double2*>(Ws + r * VT_LD + c) = make_double2(0.0, 0.0);
   }
   for (int e = tid; e < (EKF_UB / 32) * 32 * 16; e += VT_THREADS) {
     const int r = e >> 4, c = (e & 15) * 2;   // r = block * 32 + row
-    *reinterpret_cast<double2*>(Ds + r * VT_LDD + c) = *reinterpret_cast<const double2*>(Dg + r * 32 + c);
+    cp16(Ds + r * VT_LDD + c, Dg + r * 32 + c);
   }
-  for (int e = tid; e < VT_ROWS * EKF_UB / 2; e += VT_THREADS) {
-    const int r = e >> 6, c = (e & 63) * 2;
-    double2 v = make_double2(0.0, 0.0);
-    if (row0 + r < n) v = *reinterpret_cast<const double2*>(W + (size_t)(row0 + r) * EKF_UB + c);
-    *reinterpret_cast<double2*>(Ws + r * VT_LD + c) = v;
+  for (int e = tid; e < (EKF_UB - 32) * (EKF_UB - 32) / 2; e += VT_THREADS) {
+    const int r = 32 + e / ((EKF_UB - 32) / 2), c = (e % ((EKF_UB - 32) / 2)) * 2;
+    if (c < (r & ~31)) cp16(Ls + r * VT_LD + c, Lg + r * EKF_UB + c);
   }
+  asm volatile("cp.async.commit_group;\n" ::);
   for (int e = tid; e < EKF_UB; e += VT_THREADS) ys[e] = yg[e];
+  asm volatile("cp.async.wait_group 0;\n" ::);
   __syncthreads();
   if (warp < VT_ROWS / 8) {
     double part = warp_trsm_tile<EKF_UB>(Ws + (size_t)warp * 8 * VT_LD, VT_LD, Ls, VT_LD, Ds, VT_LDD, ys);
