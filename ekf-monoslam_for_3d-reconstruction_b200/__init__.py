@@ -5,7 +5,7 @@ include/ekf_b200.h); this package is the thin Python host mirror used by tests a
 The directory name is not a valid Python identifier; import it with `load_package()` from the
 repository root's `ekfb200.py` shim, which registers it as module `ekf_b200`.
 """
-from . import _abi, dist, synth  # noqa: F401
+from . import _abi, dist, keyframes, synth  # noqa: F401
 from ._abi import EkfBatchDesc, EkfConfig, EkfFeatureInfo, EkfStepStats, default_config  # noqa: F401
 from .build import build  # noqa: F401
 

@@ -48,6 +48,10 @@ class EkfFeatureInfo(C.Structure):
         ("state", C.c_double * 6), ("cov", C.c_double * 36)]
 
 
+class EkfDeletedInfo(C.Structure):
+    _fields_ = [("real_index", C.c_int32), ("_pad", C.c_int32), ("xyz_pos", C.c_double * 3), ("cov_4_delete", C.c_double * 9)]
+
+
 class EkfStepStats(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "n_in_innovation_predict", "n_matched", "n_li", "n_hi", "ransac_hypotheses", "n_removed",

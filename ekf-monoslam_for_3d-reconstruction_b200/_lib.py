@@ -43,6 +43,10 @@ SIGNATURES = {
     "ekf_covariance_parameter": (_i, [_vp, _P(_d)]),
     "ekf_get_dt": (_d, [_vp]),
     "ekf_get_center": (_i, [_vp, _i, _vp]),
+    "ekf_num_deleted": (_i, [_vp]),
+    "ekf_get_deleted": (_i, [_vp, _i, _vp]),
+    "ekf_get_points_features": (_i, [_vp, _vp, _i, _vp]),
+    "ekf_rts_epoch": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d]),
     "ekf_get_feature": (_i, [_vp, _i, _P(_abi.EkfFeatureInfo)]),
     "ekf_get_template": (_i, [_vp, _i, _i, _vp]),
     "ekf_get_step_stats": (_i, [_vp, _P(_abi.EkfStepStats)]),

@@ -901,6 +901,68 @@ int ekf_covariance_parameter(ekf_handle* h, double* out) {
   *out = P;
   return EKF_OK;
 }
+int ekf_num_deleted(const ekf_handle* h) { return h ? (int)h->deleted.size() : EKF_ERR_ARG; }
+int ekf_get_deleted(ekf_handle* h, int i, ekf_deleted_info* out) {
+  if (!h || !out || i < 0 || i >= (int)h->deleted.size()) return EKF_ERR_ARG;
+  const DeletedPatch& dp = h->deleted[i];
+  out->real_index = dp.real_index; out->_pad = 0;
+  for (int c = 0; c < 3; ++c) out->xyz_pos[c] = dp.XYZ_pos[c];
+  for (int c = 0; c < 9; ++c) out->cov_4_delete[c] = dp.cov_4_delete[c];
+  return EKF_OK;
+}
+int ekf_get_points_features(ekf_handle* h, double* out, int rows_cap, int* rows) {
+  if (!h || !rows) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  int rc = refresh_cache(h);
+  if (rc) return rc;
+  const int psize = h->N > 0 ? h->c_real[h->N - 1] : 0;   // R:349 (the reference reads patches[size-1] unguarded)
+  *rows = psize + 1;
+  if (!out) return EKF_OK;
+  if (rows_cap < psize + 1) return EKF_ERR_ARG;
+  const size_t bytes = sizeof(double) * 12 * (size_t)(psize + 1);
+  double* dev = nullptr;
+  EKF_CUDA_CHECK(cudaMallocAsync((void**)&dev, bytes, h->stream));
+  EKF_CUDA_CHECK(cudaMemsetAsync(dev, 0, bytes, h->stream));
+  launch_points_features(h->stream, h->Sigma, h->ld, h->mu, h->ft, h->N, dev, psize + 1, &h->launches);
+  EKF_CUDA_CHECK(cudaGetLastError());
+  EKF_CUDA_CHECK(cudaMemcpyAsync(out, dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+  double map_scale = 1.0;
+  EKF_CUDA_CHECK(cudaMemcpyAsync(&map_scale, h->mu + 13, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  EKF_CUDA_CHECK(cudaFreeAsync(dev, h->stream));
+  EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  for (const DeletedPatch& dp : h->deleted) {             // R:397-416, host-resident archive
+    if (dp.real_index < 0 || dp.real_index > psize) continue;
+    double* o = out + (size_t)dp.real_index * 12;
+    for (int c = 0; c < 9; ++c) o[3 + c] = dp.cov_4_delete[c];
+    for (int c = 0; c < 3; ++c) o[c] = dp.XYZ_pos[c] * map_scale;
+  }
+  if (h->deleted.size() > 7000) h->deleted.clear();
+  return EKF_OK;
+}
+int ekf_rts_epoch(ekf_handle* h, double mu[13], double sigma[169], const double mu_s[13], const double sigma_s[169],
+                  const double dTspeed[3], const double dRspeed[3], double deltaT) {
+  if (!h || !mu || !sigma || !mu_s || !sigma_s || !dTspeed || !dRspeed || !(deltaT > 0)) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  double io[370];
+  memcpy(io, mu, 13 * sizeof(double)); memcpy(io + 13, sigma, 169 * sizeof(double));
+  memcpy(io + 182, mu_s, 13 * sizeof(double)); memcpy(io + 195, sigma_s, 169 * sizeof(double));
+  memcpy(io + 364, dTspeed, 3 * sizeof(double)); memcpy(io + 367, dRspeed, 3 * sizeof(double));
+  double* dev = nullptr;
+  EKF_CUDA_CHECK(cudaMallocAsync((void**)&dev, sizeof(io) + 16, h->stream));
+  int* flag = reinterpret_cast<int*>(dev + 370);
+  EKF_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
+  EKF_CUDA_CHECK(cudaMemcpyAsync(dev, io, sizeof(io), cudaMemcpyHostToDevice, h->stream));
+  launch_rts_epoch(h->stream, dev, h->dcfg, deltaT, flag, &h->launches);
+  EKF_CUDA_CHECK(cudaGetLastError());
+  int singular = 0;
+  EKF_CUDA_CHECK(cudaMemcpyAsync(io, dev, 182 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  EKF_CUDA_CHECK(cudaMemcpyAsync(&singular, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  EKF_CUDA_CHECK(cudaFreeAsync(dev, h->stream));
+  EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (singular) return ekf_fail(h, EKF_ERR_STATE, "rts_epoch: predicted covariance is singular");
+  memcpy(mu, io, 13 * sizeof(double)); memcpy(sigma, io + 13, 169 * sizeof(double));
+  return EKF_OK;
+}
 int ekf_get_center(ekf_handle* h, int idx, float out[2]) {
   if (!h || !out || idx < 0 || idx >= h->N) return EKF_ERR_ARG;
   EKF_CUDA_CHECK(cudaSetDevice(h->device));

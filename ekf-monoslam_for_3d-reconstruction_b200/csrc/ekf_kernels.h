@@ -50,6 +50,10 @@ void launch_blk_V(cudaStream_t st, double* W, int row0, int row1, const double* 
 void launch_apply_delta(cudaStream_t st, double* mu, const double* delta, int n, long long* launches);
 void launch_bookkeeping(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, DevCtl* ctl,
                         const DevCfg& cfg, double* outd, int* outi, long long* launches);
+// ekf_export.cu
+void launch_points_features(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, double* out, int rows,
+                            long long* launches);
+void launch_rts_epoch(cudaStream_t st, double* io, const DevCfg& cfg, double dT, int* singular, long long* launches);
 // ekf_gemm.cu
 int launch_gemm_nt_sub(cudaStream_t st, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M, int N,
                        int kconst, const int* kdev, int lower_only, int* counters, long long* launches);

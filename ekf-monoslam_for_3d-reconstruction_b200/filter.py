@@ -150,6 +150,32 @@ class VSlamFilter:
         self._ck(self.L.ekf_get_feature(self.h, int(i), C.byref(o)))
         return o
 
+    def deleted(self):
+        """VSlamFilter::deleted_patches (vslamRansac.cpp:394-404): list of (real_index, XYZ_pos[3], cov_4_delete[9])."""
+        out = []
+        for i in range(self.L.ekf_num_deleted(self.h)):
+            o = _abi.EkfDeletedInfo()
+            self._ck(self.L.ekf_get_deleted(self.h, i, C.byref(o)))
+            out.append((o.real_index, np.array(o.xyz_pos), np.array(o.cov_4_delete)))
+        return out
+
+    def getPointsFeatures(self):
+        """RosVSLAM::getPointsFeatures (RosVSLAMRansac.cpp:340-418): (last real_index + 1) x 12."""
+        rows = C.c_int(0)
+        self._ck(self.L.ekf_get_points_features(self.h, None, 0, C.byref(rows)))
+        out = np.zeros((rows.value, 12))
+        self._ck(self.L.ekf_get_points_features(self.h, _ptr(out), rows.value, C.byref(rows)))
+        return out
+
+    def rts_epoch(self, MU, SIGMA, MU_S, SIGMA_S, dTspeed, dRspeed, deltaT):
+        """VSlamFilter::rts_epoch (vslamRansac.cpp:423-449) on 13-dimensional camera states; returns (MU, SIGMA)."""
+        mu = np.array(MU, dtype=np.float64).copy(); sg = np.array(SIGMA, dtype=np.float64).reshape(13, 13).copy()
+        mus = np.ascontiguousarray(MU_S, dtype=np.float64); sgs = np.ascontiguousarray(SIGMA_S, dtype=np.float64)
+        a = np.ascontiguousarray(dTspeed, dtype=np.float64); b = np.ascontiguousarray(dRspeed, dtype=np.float64)
+        assert mu.size == 13 and mus.size == 13 and sgs.size == 169
+        self._ck(self.L.ekf_rts_epoch(self.h, _ptr(mu), _ptr(sg), _ptr(mus), _ptr(sgs), _ptr(a), _ptr(b), float(deltaT)))
+        return mu, sg
+
     def template(self, i, which=0):
         w = self.cfg.window_size
         out = np.zeros((w, w), dtype=np.uint8)

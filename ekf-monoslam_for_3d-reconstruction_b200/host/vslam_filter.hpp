@@ -37,6 +37,9 @@ class VSlamFilter {
 
   int patchnumbre;       // vslamRansac.hpp:103
   int noise_cov_factor;  // vslamRansac.hpp:140
+  // MatrixX3i Point4sba (vslamRansac.hpp:98), rows of (real_index, u, v): Zero(1,3) at construction
+  // (vslamRansac.cpp:219); the loop that would fill it in update() is commented out in the reference (:1318-1340)
+  std::vector<int> Point4sba = std::vector<int>(3, 0);
 
   int addFeature(Point2f pf) { int rc = ck(ekf_add_feature(h_, pf.x, pf.y)); patchnumbre += rc; return rc; }  // :309
   void removeFeature(int index) { ck(ekf_remove_feature(h_, index)); }                                           // :373
@@ -70,6 +73,26 @@ class VSlamFilter {
     const int n = stateDim();
     mu.resize(n); Sigma.resize((size_t)n * n);
     ck(ekf_get_full(h_, mu.data(), Sigma.data(), n));
+  }
+  // RosVSLAM::getPointsFeatures (RosVSLAMRansac.cpp:340-418): rows x 12, row-major
+  std::vector<double> getPointsFeatures(int* rows_out = nullptr) {
+    int rows = 0;
+    ck(ekf_get_points_features(h_, nullptr, 0, &rows));
+    std::vector<double> pts((size_t)rows * 12);
+    ck(ekf_get_points_features(h_, pts.data(), rows, &rows));
+    if (rows_out) *rows_out = rows;
+    return pts;
+  }
+  // VSlamFilter::deleted_patches (vslamRansac.cpp:394-404)
+  std::vector<ekf_deleted_info> deletedPatches() {
+    std::vector<ekf_deleted_info> v(ekf_num_deleted(h_));
+    for (size_t i = 0; i < v.size(); ++i) ck(ekf_get_deleted(h_, (int)i, &v[i]));
+    return v;
+  }
+  // rts_epoch(MU, SIGMA, MU_S, SIGMA_S, dTspeed, dRspeed, deltaT) (:423): 13-dimensional camera states, in place
+  void rts_epoch(double MU[13], double SIGMA[169], const double MU_S[13], const double SIGMA_S[169], const double dTspeed[3],
+                 const double dRspeed[3], double deltaT) {
+    ck(ekf_rts_epoch(h_, MU, SIGMA, MU_S, SIGMA_S, dTspeed, dRspeed, deltaT));
   }
   ekf_handle* handle() { return h_; }
 

@@ -167,6 +167,30 @@ int ekf_get_feature(ekf_handle* h, int idx, ekf_feature_info* out);
 int ekf_get_template(ekf_handle* h, int idx, int which, uint8_t* out);
 int ekf_get_step_stats(ekf_handle* h, ekf_step_stats* out);
 
+/* ---- caller-side rows ------------------------------------------ */
+/* Patch archived by removeFeature (Patch::XYZ_pos / cov_4_delete, vslamRansac.cpp:394-404): XYZ features seen
+ * more than five times keep their last position and 3x3 covariance (column-major copy of block^T = the block
+ * row by row) in VSlamFilter::deleted_patches, which RosVSLAM reads (RosVSLAMRansac.cpp:312-332, 397-416). */
+typedef struct ekf_deleted_info {
+  int32_t real_index;
+  int32_t _pad;
+  double xyz_pos[3];
+  double cov_4_delete[9];
+} ekf_deleted_info;
+int ekf_num_deleted(const ekf_handle* h);                      /* deleted_patches.size() */
+int ekf_get_deleted(ekf_handle* h, int i, ekf_deleted_info* out);
+/* RosVSLAM::getPointsFeatures (RosVSLAMRansac.cpp:340-418), the matrix points.txt is written from
+ * (monoslam_ransac.cpp:273-275): (real_index of the last patch + 1) rows x 12, row r = feature with
+ * real_index r: XYZ position * map_scale and its 3x3 covariance; rows of inverse-depth or unknown features
+ * stay zero; archived features fill theirs.  *rows receives the row count; out may be NULL to query it.
+ * As in the reference, more than 7000 archived patches are cleared by the call. */
+int ekf_get_points_features(ekf_handle* h, double* out, int rows_cap, int* rows);
+/* VSlamFilter::rts_epoch (vslamRansac.cpp:423-449): one backward Rauch-Tung-Striebel step on the 13 camera
+ * states (System_model_jacobian is 13 x 13).  mu / sigma (13, 13 x 13 row-major) are updated in place from the
+ * smoothed successor (mu_s, sigma_s) and the controls that were applied between the two epochs. */
+int ekf_rts_epoch(ekf_handle* h, double mu[13], double sigma[169], const double mu_s[13], const double sigma_s[169],
+                  const double dTspeed[3], const double dRspeed[3], double deltaT);
+
 /* ---- whole-state get / set (checkpoint-resume and per-step parity with identical inputs) ------- */
 /* mu: n doubles; sigma: n x n row-major with leading dimension ld >= n. */
 int ekf_get_full(ekf_handle* h, double* mu, double* sigma, int ld);

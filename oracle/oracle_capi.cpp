@@ -59,6 +59,11 @@ struct Base {
   virtual double min_margin() = 0;
   virtual void import_state(int, int, const double*, const double*, const int*, const int*, const int*, const int*,
                             const int*, const float*, const uint8_t*, int) = 0;
+  virtual int num_deleted() = 0;
+  virtual void get_deleted(int i, int* real_index, double* xyz, double* cov9) = 0;
+  virtual int points_features(double* out, int cap_rows) = 0;
+  virtual void rts_epoch(double* mu13, double* sg13, const double* mus13, const double* sgs13, const double* dts,
+                         const double* drs, double dT) = 0;
 };
 
 template <class S, class MF>
@@ -164,6 +169,29 @@ struct Impl : Base {
     s->topup_request = f.topup_request; s->blur_requests = f.blur_requests;
   }
   double cov_param() override { return double(f.Covariance_Parameter()); }
+  int num_deleted() override { return (int)f.deleted_patches.size(); }
+  void get_deleted(int i, int* real_index, double* xyz, double* cov9) override {
+    const auto& p = f.deleted_patches[i];
+    *real_index = p.real_index;
+    for (int c = 0; c < 3; ++c) xyz[c] = double(p.XYZ_pos[c]);
+    for (int c = 0; c < 9; ++c) cov9[c] = double(p.cov_4_delete[c]);
+  }
+  int points_features(double* out, int cap_rows) override {
+    Mat<S> pts = f.getPointsFeatures();
+    if (out && cap_rows >= pts.r)
+      for (int i = 0; i < pts.r * 12; ++i) out[i] = double(pts.d[i]);
+    return pts.r;
+  }
+  void rts_epoch(double* mu13, double* sg13, const double* mus13, const double* sgs13, const double* dts, const double* drs,
+                 double dT) override {
+    Mat<S> MU(13, 1), SG(13, 13), MUS(13, 1), SGS(13, 13);
+    for (int i = 0; i < 13; ++i) { MU[i] = S(mu13[i]); MUS[i] = S(mus13[i]); }
+    for (int i = 0; i < 169; ++i) { SG.d[i] = S(sg13[i]); SGS.d[i] = S(sgs13[i]); }
+    const S a[3] = {S(dts[0]), S(dts[1]), S(dts[2])}, b[3] = {S(drs[0]), S(drs[1]), S(drs[2])};
+    f.rts_epoch(MU, SG, MUS, SGS, a, b, dT);
+    for (int i = 0; i < 13; ++i) mu13[i] = double(MU[i]);
+    for (int i = 0; i < 169; ++i) sg13[i] = double(SG.d[i]);
+  }
   double dt() override { return f.dT; }
   double min_margin() override { return f.min_margin; }
   // Replace mu / Sigma / the patch list wholesale (tests and the bench baseline seed large maps this
@@ -220,6 +248,11 @@ void orc_get_step_stats(void* h, ekf_step_stats* s) { static_cast<Base*>(h)->sta
 double orc_covariance_parameter(void* h) { return static_cast<Base*>(h)->cov_param(); }
 double orc_get_dt(void* h) { return static_cast<Base*>(h)->dt(); }
 double orc_min_margin(void* h) { return static_cast<Base*>(h)->min_margin(); }
+int orc_num_deleted(void* h) { return static_cast<Base*>(h)->num_deleted(); }
+void orc_get_deleted(void* h, int i, int* real_index, double* xyz, double* cov9) { static_cast<Base*>(h)->get_deleted(i, real_index, xyz, cov9); }
+int orc_points_features(void* h, double* out, int cap_rows) { return static_cast<Base*>(h)->points_features(out, cap_rows); }
+void orc_rts_epoch(void* h, double* mu13, double* sg13, const double* mus13, const double* sgs13, const double* dts,
+                   const double* drs, double dT) { static_cast<Base*>(h)->rts_epoch(mu13, sg13, mus13, sgs13, dts, drs, dT); }
 
 // Patch::findMatch for a batch (BASELINE config 5), host buffers.  Same argument meaning as
 // ekf_match_batch of include/ekf_b200.h.  kind_mf: 0 float matcher, 1 double matcher.

@@ -64,6 +64,10 @@ def lib(omp=False):
         "orc_min_margin": (f64, [vp]),
         "orc_match_batch": (None, [vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, f32, f32, f32, vp, vp, i32]),
         "orc_import_state": (None, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]),
+        "orc_num_deleted": (i32, [vp]),
+        "orc_get_deleted": (None, [vp, i32, vp, vp, vp]),
+        "orc_points_features": (i32, [vp, vp, i32]),
+        "orc_rts_epoch": (None, [vp, vp, vp, vp, vp, vp, vp, f64]),
         "orc_num_threads": (i32, []),
         "orc_set_num_threads": (None, [i32]),
     }
@@ -185,6 +189,29 @@ class OracleFilter:
 
     def min_margin(self):
         return self.L.orc_min_margin(self.h)
+
+    def deleted(self):
+        """Archive of removed XYZ features (vslamRansac.cpp:394-404): list of (real_index, XYZ_pos[3], cov_4_delete[9])."""
+        out = []
+        for i in range(self.L.orc_num_deleted(self.h)):
+            ri = np.zeros(1, dtype=np.int32); xyz = np.zeros(3); cov = np.zeros(9)
+            self.L.orc_get_deleted(self.h, i, _ptr(ri), _ptr(xyz), _ptr(cov))
+            out.append((int(ri[0]), xyz, cov))
+        return out
+
+    def getPointsFeatures(self):
+        rows = self.L.orc_points_features(self.h, None, 0)
+        out = np.zeros((rows, 12))
+        self.L.orc_points_features(self.h, _ptr(out), rows)
+        return out
+
+    def rts_epoch(self, MU, SIGMA, MU_S, SIGMA_S, dTspeed, dRspeed, deltaT):
+        """VSlamFilter::rts_epoch on 13-dimensional camera states; returns the smoothed (MU, SIGMA)."""
+        mu = np.array(MU, dtype=np.float64).copy(); sg = np.array(SIGMA, dtype=np.float64).reshape(13, 13).copy()
+        mus = np.ascontiguousarray(MU_S, dtype=np.float64); sgs = np.ascontiguousarray(SIGMA_S, dtype=np.float64)
+        a = np.ascontiguousarray(dTspeed, dtype=np.float64); b = np.ascontiguousarray(dRspeed, dtype=np.float64)
+        self.L.orc_rts_epoch(self.h, _ptr(mu), _ptr(sg), _ptr(mus), _ptr(sgs), _ptr(a), _ptr(b), float(deltaT))
+        return mu, sg
 
     def import_from(self, other):
         """Copy mu, Sigma and the feature table of another filter object (product or oracle) that

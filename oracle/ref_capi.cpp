@@ -179,6 +179,29 @@ void ref_get_template(void* hh, int i, int which, uint8_t* out) {
     for (int c = 0; c < m.cols; ++c) out[r * m.cols + c] = m.at<uchar>(r, c);
 }
 // 2x2 diagonal blocks of St after predict (vslamRansac.cpp:598), zeros for features not in innovation
+// archive of removed features (vslamRansac.cpp:394-404) and the RTS epoch (vslamRansac.cpp:423-449)
+int ref_num_deleted(void* hh) { return (int)static_cast<RefHandle*>(hh)->f->deleted_patches.size(); }
+void ref_get_deleted(void* hh, int i, int* real_index, double* xyz, double* cov9) {
+  Patch& p = static_cast<RefHandle*>(hh)->f->deleted_patches[i];
+  *real_index = p.real_index;
+  for (int c = 0; c < 3; ++c) xyz[c] = (double)p.XYZ_pos(c);
+  for (int c = 0; c < 9; ++c) cov9[c] = (double)p.cov_4_delete(c);
+}
+void ref_rts_epoch(void* hh, double* mu13, double* sg13, const double* mus13, const double* sgs13, const double* dts,
+                   const double* drs, double dT) {
+  VSlamFilter* f = static_cast<RefHandle*>(hh)->f;
+  VectorXf MU(13), MUS(13);
+  MatrixXf SG(13, 13), SGS(13, 13);
+  for (int i = 0; i < 13; ++i) { MU(i) = (shim_real)mu13[i]; MUS(i) = (shim_real)mus13[i]; }
+  for (int i = 0; i < 13; ++i)
+    for (int j = 0; j < 13; ++j) { SG(i, j) = (shim_real)sg13[i * 13 + j]; SGS(i, j) = (shim_real)sgs13[i * 13 + j]; }
+  Vector3f a, b;
+  for (int i = 0; i < 3; ++i) { a(i) = (shim_real)dts[i]; b(i) = (shim_real)drs[i]; }
+  f->rts_epoch(MU, SG, MUS, SGS, a, b, dT);
+  for (int i = 0; i < 13; ++i) mu13[i] = (double)MU(i);
+  for (int i = 0; i < 13; ++i)
+    for (int j = 0; j < 13; ++j) sg13[i * 13 + j] = (double)SG(i, j);
+}
 void ref_get_S_blocks(void* hh, double* out) {
   VSlamFilter* f = static_cast<RefHandle*>(hh)->f;
   const int N = (int)f->patches.size();

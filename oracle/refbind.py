@@ -52,6 +52,8 @@ def lib(fp64=True):
         "ref_get_feature": (None, [vp, i32, C.POINTER(abi.EkfFeatureInfo)]),
         "ref_get_template": (None, [vp, i32, i32, vp]), "ref_get_S_blocks": (None, [vp, vp]),
         "ref_find_match": (i32, [vp, i32, i32, i32, vp, i32, vp, vp, f32, vp]),
+        "ref_num_deleted": (i32, [vp]), "ref_get_deleted": (None, [vp, i32, vp, vp, vp]),
+        "ref_rts_epoch": (None, [vp, vp, vp, vp, vp, vp, vp, f64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -154,6 +156,21 @@ class ReferenceFilter:
         out = np.zeros((self.numOfFeatures(), 2, 2))
         self.L.ref_get_S_blocks(self.h, _ptr(out))
         return out
+
+    def deleted(self):
+        out = []
+        for i in range(self.L.ref_num_deleted(self.h)):
+            ri = np.zeros(1, dtype=np.int32); xyz = np.zeros(3); cov = np.zeros(9)
+            self.L.ref_get_deleted(self.h, i, _ptr(ri), _ptr(xyz), _ptr(cov))
+            out.append((int(ri[0]), xyz, cov))
+        return out
+
+    def rts_epoch(self, MU, SIGMA, MU_S, SIGMA_S, dTspeed, dRspeed, deltaT):
+        mu = np.array(MU, dtype=np.float64).copy(); sg = np.array(SIGMA, dtype=np.float64).reshape(13, 13).copy()
+        mus = np.ascontiguousarray(MU_S, dtype=np.float64); sgs = np.ascontiguousarray(SIGMA_S, dtype=np.float64)
+        a = np.ascontiguousarray(dTspeed, dtype=np.float64); b = np.ascontiguousarray(dRspeed, dtype=np.float64)
+        self.L.ref_rts_epoch(self.h, _ptr(mu), _ptr(sg), _ptr(mus), _ptr(sgs), _ptr(a), _ptr(b), float(deltaT))
+        return mu, sg
 
 
 def find_match(frame, tmpl, h, S, sigma_size=3.0, fp64=False):

@@ -182,3 +182,60 @@ def test_forse_plane(pkg, orc, ref, fp64, kind, tol):
         for f in (r, o):
             f.captureNewFrame(sc.frame(t), sc.stamps[t]); f.predict(); f.update(sc.picks(t, 14))
         _same_tables(r, o, f"frame {t}"); _same_state(r, o, tol, f"frame {t}")
+
+
+def _rts_inputs(seed):
+    rng = np.random.default_rng(seed)
+    def state():
+        mu = np.zeros(13)
+        mu[:3] = rng.normal(0, 0.5, 3)
+        q = rng.normal(0, 1, 4); mu[3:7] = q / np.linalg.norm(q)
+        mu[7:10] = rng.normal(0, 0.2, 3); mu[10:13] = rng.normal(0, 0.1, 3)
+        A = rng.normal(0, 1, (13, 13))
+        return mu, A @ A.T * 1e-3 + np.eye(13) * 1e-4
+    return state(), state(), rng.normal(0, 0.01, 3), rng.normal(0, 0.01, 3)
+
+
+@pytest.mark.parametrize("fp64,kind,tol", VARIANTS)
+@pytest.mark.parametrize("seed,zero_w", [(1, False), (2, False), (3, True)])
+def test_rts_epoch(pkg, orc, ref, fp64, kind, tol, seed, zero_w):
+    """VSlamFilter::rts_epoch (vslamRansac.cpp:423-449) on 13-dimensional camera states."""
+    cfg = pkg.default_config()
+    r, o = ref.ReferenceFilter(cfg, fp64=fp64), orc.OracleFilter(cfg, kind=kind)
+    (mu, sg), (mus, sgs), dts, drs = _rts_inputs(seed)
+    if zero_w:
+        mu[10:13] = 0; drs[:] = 0   # |w| = 0 branch of Jacobian_qt_w (Sinc = 1, n_w = 0)
+    mr, Sr = r.rts_epoch(mu, sg, mus, sgs, dts, drs, 1 / 30)
+    mo, So = o.rts_epoch(mu, sg, mus, sgs, dts, drs, 1 / 30)
+    assert relerr(mo, mr) <= tol and relerr(So, Sr) <= tol, f"mu {relerr(mo, mr):.2e} Sigma {relerr(So, Sr):.2e}"
+    assert relerr(mo, mu) > 1e-6   # the epoch did something
+
+
+@pytest.mark.parametrize("fp64,kind,tol", VARIANTS)
+def test_deleted_archive(pkg, orc, ref, fp64, kind, tol):
+    """removeFeature archives XYZ features seen more than five times (vslamRansac.cpp:394-404)."""
+    sc = pkg.synth.Scene(n_features=10, n_frames=9, seed=77)
+    r, o = _pair(pkg, orc, ref, sc, fp64, kind)
+    for f in (r, o):
+        f.captureNewFrame(sc.frame(0), sc.stamps[0])
+        for p in sc.feature_pixels:
+            f.addFeature(*p)
+    for t in range(1, 9):
+        for f in (r, o):
+            f.captureNewFrame(sc.frame(t), sc.stamps[t]); f.predict(); f.update(sc.picks(t, 10))
+    for f in (r, o):   # shrink rho's variance until the linearity index passes (as test_xyz_conversion)
+        mu, S = f.get_full()
+        for i in (1, 4, 9):
+            pos = 14 + 6 * i
+            S[pos + 5, :] *= 1e-4; S[:, pos + 5] *= 1e-4
+        f.set_full(mu, S)
+        f.convert2XYZ_ifLinearAll()
+    xyz = [i for i in range(r.numOfFeatures()) if r.feature(i).coding]
+    assert len(xyz) >= 2 and xyz == [i for i in range(o.numOfFeatures()) if o.feature(i).coding]
+    for i in sorted(xyz[:3] + [0], reverse=True):   # feature 0 is inverse-depth: removed, not archived
+        r.removeFeature(i); o.removeFeature(i)
+    dr, do = r.deleted(), o.deleted()
+    assert len(dr) == len(do) == len(xyz[:3])
+    for (ia, xa, ca), (ib, xb, cb) in zip(dr, do):
+        assert ia == ib
+        assert relerr(xb, xa) <= tol and relerr(cb, ca) <= tol
