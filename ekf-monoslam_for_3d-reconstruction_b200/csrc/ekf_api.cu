@@ -103,7 +103,11 @@ int ekf_destroy(ekf_handle* h) {
   cudaFree(h->map_dev); cudaFree(h->keep_dev); cudaFree(h->newpos_dev); cudaFree(h->ctl); cudaFree(h->frame); cudaFree(h->raw);
   cudaFree(h->picks_dev); cudaFree(h->out_dev); cudaFree(h->gemm_counters);
   if (h->gemm_stream) { cudaStreamSynchronize(h->gemm_stream); cudaStreamDestroy(h->gemm_stream); }
-  cudaFree(h->Wbuf[1]); cudaFree(h->Wbuf[2]); cudaFree(h->Gbuf);
+  cudaFree(h->Wbuf[1]); cudaFree(h->Wbuf[2]); cudaFree(h->Wbuf[3]); cudaFree(h->Gbuf);
+  if (h->corr_stream) { cudaStreamSynchronize(h->corr_stream); cudaStreamDestroy(h->corr_stream); }
+  if (h->ev_S) cudaEventDestroy(h->ev_S);
+  if (h->ev_G) cudaEventDestroy(h->ev_G);
+  if (h->ev_corr) cudaEventDestroy(h->ev_corr);
   for (int i = 0; i < 3; ++i) { if (h->ev_gather[i]) cudaEventDestroy(h->ev_gather[i]); if (h->ev_V[i]) cudaEventDestroy(h->ev_V[i]); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -157,12 +161,14 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
   TRY(dalloc(&h->cand, h->Ncap)) TRY(dalloc(&h->map_dev, h->ncap)) TRY(dalloc(&h->keep_dev, h->Ncap))
   TRY(dalloc(&h->newpos_dev, h->Ncap)) TRY(dalloc(&h->ctl, 1)) TRY(dalloc(&h->gemm_counters, 2))
   h->Wbuf[0] = h->W;
-  TRY(dalloc(&h->Wbuf[1], (size_t)(h->ncap + 1) * EKF_UB)) TRY(dalloc(&h->Wbuf[2], (size_t)(h->ncap + 1) * EKF_UB))
+  TRY(dalloc(&h->Wbuf[1], (size_t)(h->ncap + 1) * EKF_UB)) TRY(dalloc(&h->Wbuf[2], (size_t)(h->ncap + 1) * EKF_UB)) TRY(dalloc(&h->Wbuf[3], (size_t)(h->ncap + 1) * EKF_UB))
   TRY(dalloc(&h->Gbuf, EKF_UB * EKF_UB))
   {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = least priority
     TRY(cudaStreamCreateWithPriority(&h->gemm_stream, cudaStreamNonBlocking, lo))
+    TRY(cudaStreamCreateWithPriority(&h->corr_stream, cudaStreamNonBlocking, hi))
+    TRY(cudaEventCreateWithFlags(&h->ev_G, cudaEventDisableTiming)) TRY(cudaEventCreateWithFlags(&h->ev_corr, cudaEventDisableTiming))
     for (int i = 0; i < 3; ++i) {
       TRY(cudaEventCreateWithFlags(&h->ev_gather[i], cudaEventDisableTiming)) TRY(cudaEventCreateWithFlags(&h->ev_V[i], cudaEventDisableTiming))
     }
@@ -526,52 +532,58 @@ static int stacked_update_lookahead(ekf_handle* h, int cnt) {
 // hidden behind the widest one.  The gather of W'_{b+1} follows the downdate on the second stream and runs beside V_b.
 //   main:  [G_b, corr_b, S_b] -> factor_b -> V_b            second:  downdate_{b-1} -> gather_{b+1}
 static int stacked_update_factor_beside_downdate(ekf_handle* h, int cnt) {
-  cudaStream_t sm = h->stream, sg = h->gemm_stream;
+  cudaStream_t sm = h->stream, sg = h->gemm_stream, sc = h->corr_stream;
   const int nblk = (cnt + EKF_UB / 2 - 1) / (EKF_UB / 2);
+  // raw[b & 1]: W'_b as gathered (read by S_b); cor[b & 1]: second copy, corrected in place to W_b, then V_b
+  double* raw[2] = {h->Wbuf[1], h->Wbuf[2]};
+  double* cor[2] = {h->Wbuf[0], h->Wbuf[3]};
   cudaMemsetAsync(h->delta, 0, sizeof(double) * (size_t)h->n, sm);
   cudaEventRecord(h->ev_fork, sm);
   cudaStreamWaitEvent(sg, h->ev_fork, 0);
   for (int b = 0; b < nblk && b < 2; ++b) {   // W'_0 = W_0 and W'_1, both from the prior covariance
     ProfScope ps(h, 3, sg);
-    launch_blk_gather(sg, h->Sigma, h->ld, 0, h->n, h->ft, b * (EKF_UB / 2), cnt, nullptr, h->Wbuf[b], nullptr, &h->launches);
+    launch_blk_gather2(sg, h->Sigma, h->ld, h->n, h->ft, b * (EKF_UB / 2), cnt, raw[b], cor[b], &h->launches);
     cudaEventRecord(h->ev_gather[b], sg);
   }
   for (int b = 0; b < nblk; ++b) {
     const int f0 = b * (EKF_UB / 2);
-    double* Wb = h->Wbuf[b % 3];
-    cudaStreamWaitEvent(sm, h->ev_gather[b % 3], 0);
+    double* Vp = cor[(b - 1) & 1];
+    cudaStreamWaitEvent(sm, h->ev_gather[b & 1], 0);
     if (b > 0) {
-      ProfScope ps(h, 3);
-      double* Vp = h->Wbuf[(b - 1) % 3];
-      launch_blk_G(sm, Vp, h->ft, f0, cnt, h->Gbuf, &h->launches);
-      const int rc = launch_gemm_nt_sub(sm, Wb, EKF_UB, Vp, EKF_UB, h->Gbuf, EKF_UB, h->n, EKF_UB, EKF_UB, nullptr, 0, h->gemm_counters, &h->launches);
+      { ProfScope ps(h, 3); launch_blk_G(sm, Vp, h->ft, f0, cnt, h->Gbuf, &h->launches); }
+      cudaEventRecord(h->ev_G, sm);
+      cudaStreamWaitEvent(sc, h->ev_G, 0);
+      // W_b = W'_b - V_{b-1} G^T on the third stream, beside S_b and the Cholesky: only V_b needs it
+      const int rc = launch_gemm_nt_sub(sc, cor[b & 1], EKF_UB, Vp, EKF_UB, h->Gbuf, EKF_UB, h->n, EKF_UB, EKF_UB, nullptr, 0, h->gemm_counters, &h->launches);
       if (rc) return rc;
+      cudaEventRecord(h->ev_corr, sc);
     }
-    { ProfScope ps(h, 4); launch_blk_S_nu(sm, Wb, h->ft, f0, cnt, h->dcfg, h->delta, h->Lb, h->nu, &h->launches); }
+    { ProfScope ps(h, 4); launch_blk_S_nu_G(sm, raw[b & 1], h->ft, f0, cnt, h->dcfg, h->delta, b > 0 ? h->Gbuf : nullptr, h->Lb, h->nu, &h->launches); }
     if (b > 0) {   // release the downdate of block b-1 (it already waits for V_{b-1})
       cudaEventRecord(h->ev_S, sm);
       cudaStreamWaitEvent(sg, h->ev_S, 0);
     }
     { ProfScope ps(h, 4); launch_blk_factor_only(sm, h->Lb, h->nu, h->Dinv, h->Dblk, h->yb, h->ctl, &h->launches); }
     if (b > 0) {
-      double* Vp = h->Wbuf[(b - 1) % 3];
       {
         ProfScope ps(h, 6, sg);
         const int rc = launch_gemm_nt_sub(sg, h->Sigma, h->ld, Vp, EKF_UB, Vp, EKF_UB, h->n, h->n, EKF_UB, nullptr, h->lower_only, h->gemm_counters, &h->launches);
         if (rc) return rc;
       }
       if (b + 1 < nblk) {
+        cudaStreamWaitEvent(sg, h->ev_corr, 0);   // the next gather overwrites V_{b-1}, which the correction of W_b reads
         ProfScope ps(h, 3, sg);
-        launch_blk_gather(sg, h->Sigma, h->ld, 0, h->n, h->ft, (b + 1) * (EKF_UB / 2), cnt, nullptr, h->Wbuf[(b + 1) % 3], nullptr, &h->launches);
-        cudaEventRecord(h->ev_gather[(b + 1) % 3], sg);
+        launch_blk_gather2(sg, h->Sigma, h->ld, h->n, h->ft, (b + 1) * (EKF_UB / 2), cnt, raw[(b + 1) & 1], cor[(b + 1) & 1], &h->launches);
+        cudaEventRecord(h->ev_gather[(b + 1) & 1], sg);
       }
+      cudaStreamWaitEvent(sm, h->ev_corr, 0);
     }
-    { ProfScope ps(h, 5); launch_blk_V(sm, Wb, 0, h->n, h->Dinv, h->Dblk, h->yb, h->delta, &h->launches); }
+    { ProfScope ps(h, 5); launch_blk_V(sm, cor[b & 1], 0, h->n, h->Dinv, h->Dblk, h->yb, h->delta, &h->launches); }
     cudaEventRecord(h->ev_V[b % 3], sm);
     cudaStreamWaitEvent(sg, h->ev_V[b % 3], 0);
   }
   {
-    double* Vl = h->Wbuf[(nblk - 1) % 3];
+    double* Vl = cor[(nblk - 1) & 1];
     ProfScope ps(h, 6, sg);
     const int rc = launch_gemm_nt_sub(sg, h->Sigma, h->ld, Vl, EKF_UB, Vl, EKF_UB, h->n, h->n, EKF_UB, nullptr, h->lower_only, h->gemm_counters, &h->launches);
     if (rc) return rc;

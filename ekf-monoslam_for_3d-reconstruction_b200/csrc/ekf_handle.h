@@ -43,10 +43,10 @@ struct ekf_handle {
   uint8_t* det_mask = nullptr; float* det_eig = nullptr; unsigned long long* det_keys = nullptr; int* det_counters = nullptr;
   float* det_xy = nullptr; size_t det_cap = 0;
   // look-ahead pipeline of the stacked update (ekf_api.cu::stacked_update_lookahead)
-  cudaStream_t gemm_stream = nullptr;
-  double* Wbuf[3] = {nullptr, nullptr, nullptr};   // Wbuf[0] == W
+  cudaStream_t gemm_stream = nullptr, corr_stream = nullptr;
+  double* Wbuf[4] = {nullptr, nullptr, nullptr, nullptr};   // Wbuf[0] == W
   double* Gbuf = nullptr;
-  cudaEvent_t ev_gather[3] = {nullptr, nullptr, nullptr}, ev_V[3] = {nullptr, nullptr, nullptr}, ev_fork = nullptr, ev_join = nullptr, ev_S = nullptr;
+  cudaEvent_t ev_gather[3] = {nullptr, nullptr, nullptr}, ev_V[3] = {nullptr, nullptr, nullptr}, ev_fork = nullptr, ev_join = nullptr, ev_S = nullptr, ev_G = nullptr, ev_corr = nullptr;
   int pipe_small = 1000;  // minimum state dimension for the factor-beside-downdate schedule (0 = never)
   int lookahead = 6000;   // minimum state dimension for the look-ahead pipeline (0 = never)
   // row-block partitioned update across ranks (ekf_dist.cu): NCCL communicator of this handle, or null

@@ -39,6 +39,10 @@ void launch_blk_factor(cudaStream_t st, const double* W, FeatTab ft, int f0, int
                        double* Sb, double* Lb, double* Dblk, double* yb, DevCtl* ctl, long long* launches);
 void launch_blk_S_nu(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const DevCfg& cfg, const double* delta,
                      double* Sb, double* nu, long long* launches);
+void launch_blk_S_nu_G(cudaStream_t st, const double* Wraw, FeatTab ft, int f0, int cnt, const DevCfg& cfg, const double* delta,
+                       const double* G, double* Sb, double* nu, long long* launches);
+void launch_blk_gather2(cudaStream_t st, const double* Sigma, int ld, int n, FeatTab ft, int f0, int cnt, double* W, double* W2,
+                        long long* launches);
 void launch_blk_G(cudaStream_t st, const double* Vprev, FeatTab ft, int f0, int cnt, double* G, long long* launches);
 void launch_blk_factor_only(cudaStream_t st, const double* Sb, const double* nu, double* Lb, double* Dblk, double* yb, DevCtl* ctl,
                             long long* launches);

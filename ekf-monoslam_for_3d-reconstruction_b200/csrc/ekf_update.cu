@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128) k_hi_rescue(const double* __restrict__ Si
 #define GATHER_ROWS 4
 __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ Sigma, int ld, int row0, int n, FeatTab ft, int f0,
                                                     int cnt, const double* __restrict__ delta, double* __restrict__ W,
-                                                    double* __restrict__ nu) {
+                                                    double* __restrict__ nu, double* __restrict__ W2) {
   __shared__ double Hs[EKF_UB / 2][27];
   __shared__ int poss[EKF_UB / 2], nds[EKF_UB / 2], fids[EKF_UB / 2];
   const int nb = min(EKF_UB / 2, cnt - f0);
@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ S
     for (int c = 0; c < 13; ++c)
       if (c < nd) { w0 += sg[c] * Hs[a][c]; w1 += sg[c] * Hs[a][13 + c]; }
     reinterpret_cast<double2*>(W + (size_t)i * EKF_UB)[a] = make_double2(w0, w1);
+    if (W2) reinterpret_cast<double2*>(W2 + (size_t)i * EKF_UB)[a] = make_double2(w0, w1);   // second copy: see launch_blk_gather2
   }
   if (nu && blockIdx.x == 0 && tid < EKF_UB / 2) {
     double v0 = 0, v1 = 0;
@@ -159,11 +160,16 @@ __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ S
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(EKF_UB) k_blk_S(const double* __restrict__ W, FeatTab ft, int f0, int cnt,
                                                   double sigma_pixel_2, double* __restrict__ Sb, int plain,
-                                                  const double* __restrict__ delta, double* __restrict__ nu) {
+                                                  const double* __restrict__ delta, double* __restrict__ nu,
+                                                  const double* __restrict__ Gsub) {
   // plain == 0: S_b = H_b W + sigma_px^2 I (identity past the block's rows).
   // plain != 0: G = H_b W with zero padding — W then holds the PREVIOUS block's V (look-ahead correction).
   // nu != null: CTA 0 also forms nu_b = (z - h) - H_b delta.
+  // Gsub != null: W is the UNCORRECTED gather W' of the look-ahead pipeline and S_b = H_b W' + R - G G^T with
+  // G = H_b V_prev (H_b (W' - V_prev G^T) = H_b W' - G G^T), so that S_b does not wait for the correction of W.
+  __shared__ double Gr[EKF_UB];
   const int r = blockIdx.x, s = threadIdx.x;
+  if (Gsub) { Gr[s] = Gsub[r * EKF_UB + s]; __syncthreads(); }
   const int nb = min(EKF_UB / 2, cnt - f0), kr = 2 * nb;
   double v = (!plain && r == s) ? 1.0 : 0.0;
   if (r < kr && (plain || s < kr)) {
@@ -173,6 +179,16 @@ __global__ void __launch_bounds__(EKF_UB) k_blk_S(const double* __restrict__ W, 
     double acc = 0;
     for (int c = 0; c < nd; ++c) acc += hc[c] * W[(size_t)ekf_idx13(c, pos) * EKF_UB + s];
     v = acc + ((!plain && r == s) ? sigma_pixel_2 : 0.0);
+    if (Gsub) {
+      const double2* gs = reinterpret_cast<const double2*>(Gsub + (size_t)s * EKF_UB);
+      double g0 = 0, g1 = 0;
+#pragma unroll 8
+      for (int k = 0; k < EKF_UB / 2; ++k) {
+        const double2 t = gs[k];
+        g0 += Gr[2 * k] * t.x; g1 += Gr[2 * k + 1] * t.y;
+      }
+      v -= g0 + g1;
+    }
   }
   Sb[r * EKF_UB + s] = v;
   if (nu && r == 0) {
@@ -351,23 +367,35 @@ void launch_hi_rescue(cudaStream_t st, const double* Sigma, int ld, const double
 void launch_blk_gather(cudaStream_t st, const double* Sigma, int ld, int row0, int row1, FeatTab ft, int f0, int cnt,
                        const double* delta, double* W, double* nu, long long* launches) {
   const int nr = row1 > row0 ? row1 - row0 : 1;   // at least one CTA: block 0 also forms nu
-  k_blk_gather<<<(nr + GATHER_ROWS - 1) / GATHER_ROWS, 256, 0, st>>>(Sigma, ld, row0, row1, ft, f0, cnt, delta, W, nu);
+  k_blk_gather<<<(nr + GATHER_ROWS - 1) / GATHER_ROWS, 256, 0, st>>>(Sigma, ld, row0, row1, ft, f0, cnt, delta, W, nu, nullptr);
   *launches += 1;
 }
 void launch_blk_factor(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const double* nu, const DevCfg& cfg,
                        double* Sb, double* Lb, double* Dblk, double* yb, DevCtl* ctl, long long* launches) {
-  k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(W, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, nullptr, nullptr);
+  k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(W, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, nullptr, nullptr, nullptr);
   k_blk_factor<<<1, FACT_THREADS, kFactSmem, st>>>(Sb, nu, Lb, Dblk, yb, ctl);
   *launches += 2;
 }
 // look-ahead variants: S_b together with nu_b (delta is current only now), and G = H_b V_prev
 void launch_blk_S_nu(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const DevCfg& cfg, const double* delta,
                      double* Sb, double* nu, long long* launches) {
-  k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(W, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, delta, nu);
+  k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(W, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, delta, nu, nullptr);
+  *launches += 1;
+}
+// S_b from the uncorrected gather and G (see k_blk_S), and the gather with a second copy of W'
+void launch_blk_S_nu_G(cudaStream_t st, const double* Wraw, FeatTab ft, int f0, int cnt, const DevCfg& cfg, const double* delta,
+                       const double* G, double* Sb, double* nu, long long* launches) {
+  k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(Wraw, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, delta, nu, G);
+  *launches += 1;
+}
+void launch_blk_gather2(cudaStream_t st, const double* Sigma, int ld, int n, FeatTab ft, int f0, int cnt, double* W, double* W2,
+                        long long* launches) {
+  const int nr = n > 0 ? n : 1;
+  k_blk_gather<<<(nr + GATHER_ROWS - 1) / GATHER_ROWS, 256, 0, st>>>(Sigma, ld, 0, n, ft, f0, cnt, nullptr, W, nullptr, W2);
   *launches += 1;
 }
 void launch_blk_G(cudaStream_t st, const double* Vprev, FeatTab ft, int f0, int cnt, double* G, long long* launches) {
-  k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(Vprev, ft, f0, cnt, 0.0, G, 1, nullptr, nullptr);
+  k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(Vprev, ft, f0, cnt, 0.0, G, 1, nullptr, nullptr, nullptr);
   *launches += 1;
 }
 void launch_blk_factor_only(cudaStream_t st, const double* Sb, const double* nu, double* Lb, double* Dblk, double* yb, DevCtl* ctl,

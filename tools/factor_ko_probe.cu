@@ -12,6 +12,12 @@ __global__ void __launch_bounds__(FACT_THREADS) k_probe(const double* Sb, const 
   extern __shared__ __align__(16) double fsm[];
   cta_chol_panel<NBK, KO>(fsm, Sb, NBK, nu, L, NBK, D, 32, y, fail);
 }
+// the same factorisation repeated inside one launch: enough PC samples for ncu's source view (one launch of the real
+// kernel is 45 us on one SM, a handful of samples)
+__global__ void __launch_bounds__(FACT_THREADS) k_probe_loop(const double* Sb, const double* nu, double* L, double* D, double* y, int* fail, int reps) {
+  extern __shared__ __align__(16) double fsm[];
+  for (int r = 0; r < reps; ++r) cta_chol_panel<NBK, 0>(fsm, Sb, NBK, nu, L, NBK, D, 32, y, fail);
+}
 template <int KO>
 float run(const double* dS, const double* dnu, double* dL, double* dD, double* dy, int* df) {
   const size_t sm = (size_t)cta_chol_panel_smem_doubles<NBK>() * 8;
@@ -55,5 +61,11 @@ int main() {
   run<31>(dS, dnu, dL, dD, dy, df);
   run<63>(dS, dnu, dL, dD, dy, df);
   run<32>(dS, dnu, dL, dD, dy, df);
+  {
+    const size_t sm = (size_t)cta_chol_panel_smem_doubles<NBK>() * 8;
+    cudaFuncSetAttribute(k_probe_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    k_probe_loop<<<1, FACT_THREADS, sm>>>(dS, dnu, dL, dD, dy, df, 200);
+    printf("loop: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+  }
   return 0;
 }
