@@ -621,13 +621,21 @@ static int stacked_update(ekf_handle* h, int cnt, bool plane = false) {
   cudaMemsetAsync(h->delta, 0, sizeof(double) * (size_t)(h->n + (dist ? EKF_DIST_PAD_ROWS : 0)), st);
   for (int f0 = 0; f0 < cnt; f0 += EKF_UB / 2) {
     { ProfScope ps(h, 3); launch_blk_gather(st, h->Sigma, h->ld, r0, r1, h->ft, f0, cnt, h->delta, h->W, h->nu, &h->launches); }
-    if (dist) { ProfScope ps(h, 11); if (ekf_dist_allgather_rows(h, h->W, rpr, EKF_UB)) return (int)cudaErrorUnknown; }
-    { ProfScope ps(h, 4); launch_blk_factor(st, h->W, h->ft, f0, cnt, h->nu, h->dcfg, h->Lb, h->Dinv, h->Dblk, h->yb, h->ctl, &h->launches);  /* Lb = S_b scratch, Dinv = L, Dblk = diagonal-block inverses */ }
-    { ProfScope ps(h, 5); launch_blk_V(st, h->W, r0, r1, h->Dinv, h->Dblk, h->yb, h->delta, &h->launches); }
     if (dist) {
-      ProfScope ps(h, 11);
-      if (ekf_dist_allgather_rows(h, h->W, rpr, EKF_UB)) return (int)cudaErrorUnknown;
-      if (ekf_dist_allgather_rows(h, h->delta, rpr, 1)) return (int)cudaErrorUnknown;
+      // S_b = H_b W_b + R needs the camera / feature rows of W_b, which live on several ranks: every rank sums the terms of
+      // the rows it owns and the 128 x 128 partial blocks are all-reduced (128 KB instead of all-gathering the 12 MB panel)
+      { ProfScope ps(h, 4); launch_blk_S_part(st, h->W, h->ft, f0, cnt, h->dcfg, r0, r1, h->rank == 0 ? 1 : 0, h->Lb, &h->launches); }
+      { ProfScope ps(h, 11); if (ekf_dist_allreduce_sum(h, h->Lb, (size_t)EKF_UB * EKF_UB)) return (int)cudaErrorUnknown; }
+      { ProfScope ps(h, 4); launch_blk_factor_only(st, h->Lb, h->nu, h->Dinv, h->Dblk, h->yb, h->ctl, &h->launches); }
+    } else {
+      ProfScope ps(h, 4);
+      launch_blk_factor(st, h->W, h->ft, f0, cnt, h->nu, h->dcfg, h->Lb, h->Dinv, h->Dblk, h->yb, h->ctl, &h->launches);  /* Lb = S_b scratch, Dinv = L, Dblk = diagonal-block inverses */
+    }
+    { ProfScope ps(h, 5); launch_blk_V(st, h->W, r0, r1, h->Dinv, h->Dblk, h->yb, dist ? nullptr : h->delta, &h->launches); }
+    if (dist) {
+      { ProfScope ps(h, 11); if (ekf_dist_allgather_rows(h, h->W, rpr, EKF_UB)) return (int)cudaErrorUnknown; }
+      // delta += V_b y_b for all rows from the gathered panel, the same kernel on every rank: replicas stay bit-identical
+      { ProfScope ps(h, 5); launch_delta_rows(st, h->W, h->yb, h->delta, h->n, &h->launches); }
     }
     {
       ProfScope ps(h, 6);

@@ -25,6 +25,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;   // op 0 = ncclSum
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
@@ -46,8 +47,9 @@ int ekf_dist_load_nccl(const char* path) {
   g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
   g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
   g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(lib, "ncclAllGather");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(lib, "ncclAllReduce");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(lib, "ncclGetErrorString");
-  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather) return EKF_ERR_UNSUPPORTED;
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather || !g_nccl.AllReduce) return EKF_ERR_UNSUPPORTED;
   g_nccl.lib = lib;
   return EKF_OK;
 }
@@ -100,6 +102,14 @@ int ekf_dist_allgather_rows(ekf_handle* h, double* buf, int rows_per_rank, size_
   const size_t count = (size_t)rows_per_rank * row_elems;
   const ncclResult_t r = g_nccl.AllGather(buf + (size_t)h->rank * count, buf, count, kNcclDouble, (ncclComm_t)h->nccl_comm, h->stream);
   if (r != 0) return nccl_fail(h, r, "ncclAllGather");
+  h->dist_bytes += (long long)(count * sizeof(double));
+  return 0;
+}
+
+// In-place sum over the ranks (the 128 x 128 partial innovation blocks of the row-block partition).
+int ekf_dist_allreduce_sum(ekf_handle* h, double* buf, size_t count) {
+  const ncclResult_t r = g_nccl.AllReduce(buf, buf, count, kNcclDouble, /*ncclSum*/ 0, (ncclComm_t)h->nccl_comm, h->stream);
+  if (r != 0) return nccl_fail(h, r, "ncclAllReduce");
   h->dist_bytes += (long long)(count * sizeof(double));
   return 0;
 }

@@ -77,4 +77,5 @@ struct ekf_handle {
 // ekf_dist.cu: in-place all-gather of a row-partitioned device buffer.  Rank r owns rows
 // [r * rows_per_rank, (r + 1) * rows_per_rank) of `buf` (row_elems doubles per row).
 int ekf_dist_allgather_rows(ekf_handle* h, double* buf, int rows_per_rank, size_t row_elems);
+int ekf_dist_allreduce_sum(ekf_handle* h, double* buf, size_t count);
 #define EKF_DIST_PAD_ROWS 512   // extra rows allocated for W / delta / Sigma so that world * rows_per_rank fits

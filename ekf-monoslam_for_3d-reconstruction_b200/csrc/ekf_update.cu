@@ -161,24 +161,30 @@ __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ S
 __global__ void __launch_bounds__(EKF_UB) k_blk_S(const double* __restrict__ W, FeatTab ft, int f0, int cnt,
                                                   double sigma_pixel_2, double* __restrict__ Sb, int plain,
                                                   const double* __restrict__ delta, double* __restrict__ nu,
-                                                  const double* __restrict__ Gsub) {
+                                                  const double* __restrict__ Gsub, int row0 = 0, int row1 = 0x7fffffff,
+                                                  int add_diag = 1) {
   // plain == 0: S_b = H_b W + sigma_px^2 I (identity past the block's rows).
   // plain != 0: G = H_b W with zero padding — W then holds the PREVIOUS block's V (look-ahead correction).
   // nu != null: CTA 0 also forms nu_b = (z - h) - H_b delta.
+  // [row0, row1), add_diag: row-block partition (ekf_dist) — only the rows of W this rank owns contribute (the partial
+  // S blocks are summed by an all-reduce) and one rank adds the diagonal term.
   // Gsub != null: W is the UNCORRECTED gather W' of the look-ahead pipeline and S_b = H_b W' + R - G G^T with
   // G = H_b V_prev (H_b (W' - V_prev G^T) = H_b W' - G G^T), so that S_b does not wait for the correction of W.
   __shared__ double Gr[EKF_UB];
   const int r = blockIdx.x, s = threadIdx.x;
   if (Gsub) { Gr[s] = Gsub[r * EKF_UB + s]; __syncthreads(); }
   const int nb = min(EKF_UB / 2, cnt - f0), kr = 2 * nb;
-  double v = (!plain && r == s) ? 1.0 : 0.0;
+  double v = (!plain && r == s && add_diag) ? 1.0 : 0.0;
   if (r < kr && (plain || s < kr)) {
     const int f = ft.sel[f0 + (r >> 1)];
     const int pos = ft.pos[f], nd = 7 + (ft.coding[f] ? 3 : 6);
     const double* hc = ft.Hc + 26 * f + 13 * (r & 1);
     double acc = 0;
-    for (int c = 0; c < nd; ++c) acc += hc[c] * W[(size_t)ekf_idx13(c, pos) * EKF_UB + s];
-    v = acc + ((!plain && r == s) ? sigma_pixel_2 : 0.0);
+    for (int c = 0; c < nd; ++c) {
+      const int idx = ekf_idx13(c, pos);
+      if (idx >= row0 && idx < row1) acc += hc[c] * W[(size_t)idx * EKF_UB + s];
+    }
+    v = acc + ((!plain && r == s && add_diag) ? sigma_pixel_2 : 0.0);
     if (Gsub) {
       // G^T follows G in the buffer (written by the plain pass): Gt[k][s] is coalesced over s and every load is independent
       const double* gt = Gsub + EKF_UB * EKF_UB + s;
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(VT_THREADS) k_blk_V(double* __restrict__ W, in
     part += __shfl_xor_sync(0xffffffffu, part, 1);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
     const int i = row0 + warp * 8 + (lane >> 2);
-    if ((lane & 3) == 0 && i < n) delta[i] += part;
+    if ((lane & 3) == 0 && i < n && delta) delta[i] += part;
   }
   __syncthreads();
   for (int e = tid; e < VT_ROWS * EKF_UB / 2; e += VT_THREADS) {
@@ -306,6 +312,25 @@ __global__ void __launch_bounds__(VT_THREADS) k_blk_V(double* __restrict__ W, in
     if (row0 + r < n)
       *reinterpret_cast<double2*>(W + (size_t)(row0 + r) * EKF_UB + c) = *reinterpret_cast<const double2*>(Ws + r * VT_LD + c);
   }
+}
+
+// delta += V y for ALL rows, one warp per row (row-block partition: every rank runs this on the all-gathered V so that
+// the replicas of delta stay bit-identical; the owner-only accumulation inside k_blk_V is switched off there)
+__global__ void __launch_bounds__(256) k_delta_rows(const double* __restrict__ V, const double* __restrict__ y, double* __restrict__ delta,
+                                                    int n) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const double2* v = reinterpret_cast<const double2*>(V + (size_t)row * EKF_UB);
+  const double2* yy = reinterpret_cast<const double2*>(y);
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < EKF_UB / 64; ++k) {
+    const double2 a = v[lane + 32 * k], b = yy[lane + 32 * k];
+    s += a.x * b.x + a.y * b.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) delta[row] += s;
 }
 
 __global__ void k_apply_delta(double* __restrict__ mu, const double* __restrict__ delta, int n) {
@@ -409,6 +434,15 @@ void launch_blk_V(cudaStream_t st, double* W, int row0, int row1, const double* 
                   double* delta, long long* launches) {
   if (row1 <= row0) return;
   k_blk_V<<<(row1 - row0 + VT_ROWS - 1) / VT_ROWS, VT_THREADS, kVSmem, st>>>(W, row0, row1, Lb, Dblk, yb, delta);
+  *launches += 1;
+}
+void launch_blk_S_part(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const DevCfg& cfg, int row0, int row1, int add_diag,
+                       double* Sb, long long* launches) {
+  k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(W, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, nullptr, nullptr, nullptr, row0, row1, add_diag);
+  *launches += 1;
+}
+void launch_delta_rows(cudaStream_t st, const double* V, const double* y, double* delta, int n, long long* launches) {
+  k_delta_rows<<<(n + 7) / 8, 256, 0, st>>>(V, y, delta, n);
   *launches += 1;
 }
 void launch_apply_delta(cudaStream_t st, double* mu, const double* delta, int n, long long* launches) {
