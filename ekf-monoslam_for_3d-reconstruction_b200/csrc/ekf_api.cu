@@ -161,7 +161,7 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
   TRY(dalloc(&h->cand, h->Ncap)) TRY(dalloc(&h->map_dev, h->ncap)) TRY(dalloc(&h->keep_dev, h->Ncap))
   TRY(dalloc(&h->newpos_dev, h->Ncap)) TRY(dalloc(&h->ctl, 1)) TRY(dalloc(&h->gemm_counters, 2))
   h->Wbuf[0] = h->W;
-  TRY(dalloc(&h->Wbuf[1], (size_t)(h->ncap + 1) * EKF_UB)) TRY(dalloc(&h->Wbuf[2], (size_t)(h->ncap + 1) * EKF_UB)) TRY(dalloc(&h->Wbuf[3], (size_t)(h->ncap + 1) * EKF_UB))
+  TRY(dalloc(&h->Wbuf[1], (size_t)(h->ncap + 1 + EKF_DIST_PAD_ROWS) * EKF_UB)) TRY(dalloc(&h->Wbuf[2], (size_t)(h->ncap + 1 + EKF_DIST_PAD_ROWS) * EKF_UB)) TRY(dalloc(&h->Wbuf[3], (size_t)(h->ncap + 1) * EKF_UB))
   TRY(dalloc(&h->Gbuf, 2 * EKF_UB * EKF_UB))   // G and G^T
   {
     int lo = 0, hi = 0;
@@ -476,46 +476,67 @@ static int convert_xyz(ekf_handle* h, int only) {
 static int stacked_update_lookahead(ekf_handle* h, int cnt) {
   cudaStream_t sm = h->stream, sg = h->gemm_stream;
   const int nblk = (cnt + EKF_UB / 2 - 1) / (EKF_UB / 2);
-  cudaMemsetAsync(h->delta, 0, sizeof(double) * (size_t)h->n, sm);
+  // Row-block partition (ekf_dist): this rank gathers, corrects, solves and downdates rows [r0, r1) only; the partial
+  // S blocks are all-reduced and V_b is all-gathered on the main stream, beside the downdate of block b-1 on the second.
+  const bool dist = h->nccl_comm != nullptr && h->world > 1;
+  int rpr = h->n, r0 = 0, r1 = h->n;
+  if (dist) {
+    rpr = (((h->n + h->world - 1) / h->world) + 31) & ~31;
+    if ((long long)rpr * h->world > (long long)h->n + EKF_DIST_PAD_ROWS) return (int)cudaErrorInvalidValue;
+    r0 = std::min(h->n, h->rank * rpr);
+    r1 = std::min(h->n, r0 + rpr);
+  }
+  cudaMemsetAsync(h->delta, 0, sizeof(double) * (size_t)(h->n + (dist ? EKF_DIST_PAD_ROWS : 0)), sm);
   cudaEventRecord(h->ev_fork, sm);
   cudaStreamWaitEvent(sg, h->ev_fork, 0);
   for (int b = 0; b < nblk && b < 2; ++b) {
     ProfScope ps(h, 3, sg);
-    launch_blk_gather(sg, h->Sigma, h->ld, 0, h->n, h->ft, b * (EKF_UB / 2), cnt, nullptr, h->Wbuf[b], nullptr, &h->launches);
+    launch_blk_gather(sg, h->Sigma, h->ld, r0, r1, h->ft, b * (EKF_UB / 2), cnt, nullptr, h->Wbuf[b], nullptr, &h->launches);
     cudaEventRecord(h->ev_gather[b], sg);
   }
   for (int b = 0; b < nblk; ++b) {
     const int f0 = b * (EKF_UB / 2);
     double* Wb = h->Wbuf[b % 3];
     cudaStreamWaitEvent(sm, h->ev_gather[b % 3], 0);
-    if (b > 0) {
+    if (b > 0 && r1 > r0) {
       ProfScope ps(h, 3);
       double* Vp = h->Wbuf[(b - 1) % 3];
       launch_blk_G(sm, Vp, h->ft, f0, cnt, h->Gbuf, &h->launches);
-      const int rc = launch_gemm_nt_sub(sm, Wb, EKF_UB, Vp, EKF_UB, h->Gbuf, EKF_UB, h->n, EKF_UB, EKF_UB, nullptr, 0, h->gemm_counters, &h->launches);
+      const int rc = launch_gemm_nt_sub(sm, Wb + (size_t)r0 * EKF_UB, EKF_UB, Vp + (size_t)r0 * EKF_UB, EKF_UB, h->Gbuf, EKF_UB, r1 - r0, EKF_UB,
+                                        EKF_UB, nullptr, 0, h->gemm_counters, &h->launches);
       if (rc) return rc;
     }
-    {
+    if (dist) {
+      { ProfScope ps(h, 4); launch_blk_S_part(sm, Wb, h->ft, f0, cnt, h->dcfg, r0, r1, h->rank == 0 ? 1 : 0, h->delta, h->nu, h->Lb, &h->launches); }
+      { ProfScope ps(h, 11); if (ekf_dist_allreduce_sum(h, h->Lb, (size_t)EKF_UB * EKF_UB)) return (int)cudaErrorUnknown; }
+      { ProfScope ps(h, 4); launch_blk_factor_only(sm, h->Lb, h->nu, h->Dinv, h->Dblk, h->yb, h->ctl, &h->launches); }
+    } else {
       ProfScope ps(h, 4);
       launch_blk_S_nu(sm, Wb, h->ft, f0, cnt, h->dcfg, h->delta, h->Lb, h->nu, &h->launches);
       launch_blk_factor_only(sm, h->Lb, h->nu, h->Dinv, h->Dblk, h->yb, h->ctl, &h->launches);
     }
-    { ProfScope ps(h, 5); launch_blk_V(sm, Wb, 0, h->n, h->Dinv, h->Dblk, h->yb, h->delta, &h->launches); }
+    { ProfScope ps(h, 5); launch_blk_V(sm, Wb, r0, r1, h->Dinv, h->Dblk, h->yb, dist ? nullptr : h->delta, &h->launches); }
+    if (dist) {
+      { ProfScope ps(h, 11); if (ekf_dist_allgather_rows(h, Wb, rpr, EKF_UB)) return (int)cudaErrorUnknown; }
+      { ProfScope ps(h, 5); launch_delta_rows(sm, Wb, h->yb, h->delta, h->n, &h->launches); }
+    }
     cudaEventRecord(h->ev_V[b % 3], sm);
     cudaStreamWaitEvent(sg, h->ev_V[b % 3], 0);
-    {
+    if (r1 > r0) {
       ProfScope ps(h, 6, sg);
-      const int rc = launch_gemm_nt_sub(sg, h->Sigma, h->ld, Wb, EKF_UB, Wb, EKF_UB, h->n, h->n, EKF_UB, nullptr, h->lower_only, h->gemm_counters, &h->launches);
+      const int rc = launch_gemm_nt_sub(sg, h->Sigma + (size_t)r0 * h->ld, h->ld, Wb + (size_t)r0 * EKF_UB, EKF_UB, Wb, EKF_UB, r1 - r0, h->n, EKF_UB,
+                                        nullptr, dist ? 0 : h->lower_only, h->gemm_counters, &h->launches);
       if (rc) return rc;
     }
     if (b + 2 < nblk) {
       ProfScope ps(h, 3, sg);
-      launch_blk_gather(sg, h->Sigma, h->ld, 0, h->n, h->ft, (b + 2) * (EKF_UB / 2), cnt, nullptr, h->Wbuf[(b + 2) % 3], nullptr, &h->launches);
+      launch_blk_gather(sg, h->Sigma, h->ld, r0, r1, h->ft, (b + 2) * (EKF_UB / 2), cnt, nullptr, h->Wbuf[(b + 2) % 3], nullptr, &h->launches);
       cudaEventRecord(h->ev_gather[(b + 2) % 3], sg);
     }
   }
   cudaEventRecord(h->ev_join, sg);
   cudaStreamWaitEvent(sm, h->ev_join, 0);
+  if (dist) { ProfScope ps(h, 11); if (ekf_dist_allgather_rows(h, h->Sigma, rpr, (size_t)h->ld)) return (int)cudaErrorUnknown; }
   {
     ProfScope ps(h, 7);
     launch_apply_delta(sm, h->mu, h->delta, h->n, &h->launches);
@@ -601,9 +622,10 @@ static int stacked_update_factor_beside_downdate(ekf_handle* h, int cnt) {
 static int stacked_update(ekf_handle* h, int cnt, bool plane = false) {
   if (cnt <= 0 && !plane) return 0;
   if (cnt < 0) cnt = 0;
-  if (!plane && !(h->nccl_comm && h->world > 1) && cnt > EKF_UB / 2) {
-    if (h->lookahead > 0 && h->n >= h->lookahead) return stacked_update_lookahead(h, cnt);
-    if (h->pipe_small > 0 && h->n >= h->pipe_small) return stacked_update_factor_beside_downdate(h, cnt);
+  if (!plane && cnt > EKF_UB / 2) {
+    const bool partitioned = h->nccl_comm && h->world > 1;
+    if (h->lookahead > 0 && h->n >= h->lookahead) return stacked_update_lookahead(h, cnt);   // also row-block partitioned
+    if (!partitioned && h->pipe_small > 0 && h->n >= h->pipe_small) return stacked_update_factor_beside_downdate(h, cnt);
   }
   cudaStream_t st = h->stream;
   // Row-block partition (BASELINE config 4): every rank holds a replica of Sigma, updates only its
@@ -624,7 +646,7 @@ static int stacked_update(ekf_handle* h, int cnt, bool plane = false) {
     if (dist) {
       // S_b = H_b W_b + R needs the camera / feature rows of W_b, which live on several ranks: every rank sums the terms of
       // the rows it owns and the 128 x 128 partial blocks are all-reduced (128 KB instead of all-gathering the 12 MB panel)
-      { ProfScope ps(h, 4); launch_blk_S_part(st, h->W, h->ft, f0, cnt, h->dcfg, r0, r1, h->rank == 0 ? 1 : 0, h->Lb, &h->launches); }
+      { ProfScope ps(h, 4); launch_blk_S_part(st, h->W, h->ft, f0, cnt, h->dcfg, r0, r1, h->rank == 0 ? 1 : 0, nullptr, nullptr, h->Lb, &h->launches); }
       { ProfScope ps(h, 11); if (ekf_dist_allreduce_sum(h, h->Lb, (size_t)EKF_UB * EKF_UB)) return (int)cudaErrorUnknown; }
       { ProfScope ps(h, 4); launch_blk_factor_only(st, h->Lb, h->nu, h->Dinv, h->Dblk, h->yb, h->ctl, &h->launches); }
     } else {

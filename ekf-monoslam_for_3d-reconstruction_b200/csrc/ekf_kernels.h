@@ -52,7 +52,7 @@ void launch_plane_S(cudaStream_t st, const double* W, double* Sb, long long* lau
 void launch_blk_V(cudaStream_t st, double* W, int row0, int row1, const double* Lb, const double* Dblk, const double* yb,
                   double* delta, long long* launches);
 void launch_blk_S_part(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const DevCfg& cfg, int row0, int row1, int add_diag,
-                       double* Sb, long long* launches);
+                       const double* delta, double* nu, double* Sb, long long* launches);
 void launch_delta_rows(cudaStream_t st, const double* V, const double* y, double* delta, int n, long long* launches);
 void launch_apply_delta(cudaStream_t st, double* mu, const double* delta, int n, long long* launches);
 void launch_bookkeeping(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, DevCtl* ctl,

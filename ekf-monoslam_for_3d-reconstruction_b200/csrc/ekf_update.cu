@@ -437,8 +437,8 @@ void launch_blk_V(cudaStream_t st, double* W, int row0, int row1, const double* 
   *launches += 1;
 }
 void launch_blk_S_part(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const DevCfg& cfg, int row0, int row1, int add_diag,
-                       double* Sb, long long* launches) {
-  k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(W, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, nullptr, nullptr, nullptr, row0, row1, add_diag);
+                       const double* delta, double* nu, double* Sb, long long* launches) {
+  k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(W, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, delta, nu, nullptr, row0, row1, add_diag);
   *launches += 1;
 }
 void launch_delta_rows(cudaStream_t st, const double* V, const double* y, double* delta, int n, long long* launches) {
