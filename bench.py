@@ -235,6 +235,7 @@ def run_ours(args):
     tB, wallB, _, _ = timed_pass(step_e2e, filt)
     h2d = width * height + 4 * nfeat
     d2h = 210 * 8 + (16 + 3 * nfeat) * 4 + 2 * 88 + 14 * 8 + 196 * 8
+    peer_memory = bool(filt.dist_info()["peer_memory"]) if partitioned else False
     del filt
 
     def agg(times):
@@ -277,8 +278,10 @@ def run_ours(args):
                                    f"{width}x{height} u8 frames, predict+match+update per frame, all features matched "
                                    f"(n_li={stA.n_li})",
                        "l2": "flushed between timed steps (256 MiB write outside the event pairs)",
-                       "multi_gpu": ("one filter, stacked update partitioned by covariance row blocks, NCCL all-gather of the W/V "
-                                     "panels and of the row blocks (strong scaling)") if partitioned else
+                       "multi_gpu": ("one filter, stacked update partitioned by covariance row blocks, look-ahead pipeline; partial S blocks "
+                                     "and V panels exchanged " + ("by peer-memory stores from inside the producing kernels (NVLink)"
+                                                                  if peer_memory else "by NCCL all-reduce / all-gather")
+                                     + ", row blocks of Sigma all-gathered by NCCL once per update (strong scaling)") if partitioned else
                                     ("replicas only (one independent filter per rank)" if world > 1 else "n/a")},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),

@@ -78,6 +78,7 @@ SIGNATURES = {
     "ekf_dist_attach": (_i, [_vp, _vp, _i, _i]),
     "ekf_dist_detach": (_i, [_vp]),
     "ekf_dist_info": (_i, [_vp, _P(_i), _P(_i), _P(C.c_int64)]),
+    "ekf_dist_peer_memory": (_i, [_vp]),
     "ekf_set_profiling": (_i, [_vp, _i]),
     "ekf_get_profile": (_i, [_vp, _P(_abi.EkfProfile), _i]),
     "ekf_set_symmetric_downdate": (_i, [_vp, _i]),

@@ -506,19 +506,31 @@ static int stacked_update_lookahead(ekf_handle* h, int cnt) {
                                         EKF_UB, nullptr, 0, h->gemm_counters, &h->launches);
       if (rc) return rc;
     }
-    if (dist) {
+    if (dist && h->p2p.on) {
+      // peer-memory exchange: the S kernel stores its partial block into every rank's slot, the factor kernel waits for
+      // the peers' epochs and sums the slots, the V kernel stores its finished rows into every rank's panel — no NCCL call
+      P2PView pv;
+      for (int q = 0; q < 8; ++q) { pv.w[q] = h->p2p.peerW[b % 3][q]; pv.spart[q] = h->p2p.peerSpart[q]; pv.flags[q] = h->p2p.peerFlags[q]; }
+      pv.rank = h->rank; pv.world = h->world; pv.epoch = ++h->p2p.epoch;
+      const unsigned long long* lflags = h->p2p.peerFlags[h->rank];
+      unsigned int* tickets = (unsigned int*)(h->p2p.peerFlags[h->rank] + 16);
+      { ProfScope ps(h, 4); launch_blk_S_part_p2p(sm, Wb, h->ft, f0, cnt, h->dcfg, r0, r1, h->rank == 0 ? 1 : 0, h->delta, h->nu, h->Lb, pv, tickets, &h->launches); }
+      { ProfScope ps(h, 4); launch_blk_factor_p2p(sm, h->p2p.peerSpart[h->rank], lflags, h->world, pv.epoch, h->Lb, h->nu, h->Dinv, h->Dblk, h->yb, h->ctl, &h->launches); }
+      { ProfScope ps(h, 5); launch_blk_V_p2p(sm, Wb, r0, r1, h->Dinv, h->Dblk, h->yb, pv, tickets + 1, lflags, h->world, pv.epoch, h->ctl, &h->launches); }
+      h->dist_bytes += (long long)sizeof(double) * ((size_t)EKF_UB * EKF_UB + (size_t)(r1 - r0) * EKF_UB) * (h->world - 1);
+      { ProfScope ps(h, 5); launch_delta_rows(sm, Wb, h->yb, h->delta, h->n, &h->launches); }
+    } else if (dist) {
       { ProfScope ps(h, 4); launch_blk_S_part(sm, Wb, h->ft, f0, cnt, h->dcfg, r0, r1, h->rank == 0 ? 1 : 0, h->delta, h->nu, h->Lb, &h->launches); }
       { ProfScope ps(h, 11); if (ekf_dist_allreduce_sum(h, h->Lb, (size_t)EKF_UB * EKF_UB)) return (int)cudaErrorUnknown; }
       { ProfScope ps(h, 4); launch_blk_factor_only(sm, h->Lb, h->nu, h->Dinv, h->Dblk, h->yb, h->ctl, &h->launches); }
-    } else {
-      ProfScope ps(h, 4);
-      launch_blk_S_nu(sm, Wb, h->ft, f0, cnt, h->dcfg, h->delta, h->Lb, h->nu, &h->launches);
-      launch_blk_factor_only(sm, h->Lb, h->nu, h->Dinv, h->Dblk, h->yb, h->ctl, &h->launches);
-    }
-    { ProfScope ps(h, 5); launch_blk_V(sm, Wb, r0, r1, h->Dinv, h->Dblk, h->yb, dist ? nullptr : h->delta, &h->launches); }
-    if (dist) {
+      { ProfScope ps(h, 5); launch_blk_V(sm, Wb, r0, r1, h->Dinv, h->Dblk, h->yb, nullptr, &h->launches); }
       { ProfScope ps(h, 11); if (ekf_dist_allgather_rows(h, Wb, rpr, EKF_UB)) return (int)cudaErrorUnknown; }
       { ProfScope ps(h, 5); launch_delta_rows(sm, Wb, h->yb, h->delta, h->n, &h->launches); }
+    } else {
+      { ProfScope ps(h, 4);
+        launch_blk_S_nu(sm, Wb, h->ft, f0, cnt, h->dcfg, h->delta, h->Lb, h->nu, &h->launches);
+        launch_blk_factor_only(sm, h->Lb, h->nu, h->Dinv, h->Dblk, h->yb, h->ctl, &h->launches); }
+      { ProfScope ps(h, 5); launch_blk_V(sm, Wb, r0, r1, h->Dinv, h->Dblk, h->yb, h->delta, &h->launches); }
     }
     cudaEventRecord(h->ev_V[b % 3], sm);
     cudaStreamWaitEvent(sg, h->ev_V[b % 3], 0);

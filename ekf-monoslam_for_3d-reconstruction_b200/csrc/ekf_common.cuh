@@ -91,6 +91,15 @@ __host__ __device__ __forceinline__ FeatTab feattab_slice(const FeatTab& t, int 
   return o;
 }
 
+// device-side view of the peer mappings, passed by value to the kernels that push panels to the peers
+struct P2PView {
+  double* w[8];                 // destination panel (Wbuf[b % 3]) on every rank
+  double* spart[8];             // partial-S slots on every rank
+  unsigned long long* flags[8]; // flag words on every rank
+  int rank, world;
+  unsigned long long epoch;
+};
+
 struct FrameView {
   const uint8_t* px;
   int w, h, stride;

@@ -9,7 +9,9 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "../../include/ekf_b200.h"
 #include "ekf_handle.h"
@@ -38,6 +40,8 @@ static int nccl_fail(ekf_handle* h, ncclResult_t r, const char* what) {
 }
 
 extern "C" {
+
+static int p2p_setup(ekf_handle* h);
 
 int ekf_dist_load_nccl(const char* path) {
   if (g_nccl.lib) return EKF_OK;
@@ -74,7 +78,73 @@ int ekf_dist_attach(ekf_handle* h, const char id_bytes[128], int rank, int world
   const ncclResult_t r = g_nccl.CommInitRank(&comm, world, id, rank);
   if (r != 0) return nccl_fail(h, r, "ncclCommInitRank");
   h->nccl_comm = comm; h->rank = rank; h->world = world;
+  return p2p_setup(h);
+}
+
+// ---- peer-memory exchange ------------------------------------------------------------------------
+// Every rank exports its three W / V panel buffers and one small allocation (partial-S slots + flag words) with CUDA IPC;
+// the handles travel once over the fresh communicator; afterwards the producing kernels store straight into the peers
+// (ekf_update.cu: k_blk_S / k_blk_V with a P2PView) and no NCCL call remains inside a block of the partitioned
+// look-ahead update.  EKF_DIST_P2P=0 keeps the NCCL collectives.
+typedef int (*cuMemGetAddressRange_t)(unsigned long long*, size_t*, unsigned long long);
+struct P2PExport { cudaIpcMemHandle_t hnd; unsigned long long off; };   // 72 bytes
+
+static int p2p_setup(ekf_handle* h) {
+  const char* e = getenv("EKF_DIST_P2P");
+  if ((e && atoi(e) == 0) || h->world > 8 || h->world < 2) return EKF_OK;
+  void* cu = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+  cuMemGetAddressRange_t range = cu ? (cuMemGetAddressRange_t)dlsym(cu, "cuMemGetAddressRange_v2") : nullptr;
+  if (!range) return EKF_OK;   // stay on NCCL
+  const size_t spart_doubles = (size_t)h->world * EKF_UB * EKF_UB;
+  const size_t xs_bytes = spart_doubles * sizeof(double) + 16 * sizeof(unsigned long long) + 64;
+  if (cudaMalloc((void**)&h->p2p.xs, xs_bytes) != cudaSuccess) return EKF_ERR_CUDA;
+  cudaMemset(h->p2p.xs, 0, xs_bytes);
+  cudaDeviceSynchronize();
+  void* local[4] = {h->Wbuf[0], h->Wbuf[1], h->Wbuf[2], h->p2p.xs};
+  P2PExport mine[4];
+  for (int k = 0; k < 4; ++k) {
+    unsigned long long base = 0; size_t sz = 0;
+    if (range(&base, &sz, (unsigned long long)local[k]) != 0) return EKF_OK;
+    if (cudaIpcGetMemHandle(&mine[k].hnd, (void*)base) != cudaSuccess) { cudaGetLastError(); return EKF_OK; }
+    mine[k].off = (unsigned long long)local[k] - base;
+  }
+  const size_t rec = sizeof(mine);
+  char *dsend = nullptr, *drecv = nullptr;
+  if (cudaMalloc((void**)&dsend, rec) != cudaSuccess || cudaMalloc((void**)&drecv, rec * h->world) != cudaSuccess) return EKF_ERR_CUDA;
+  cudaMemcpy(dsend, mine, rec, cudaMemcpyHostToDevice);
+  const ncclResult_t r = g_nccl.AllGather(dsend, drecv, rec, /*ncclInt8*/ 0, (ncclComm_t)h->nccl_comm, h->stream);
+  if (r != 0) return nccl_fail(h, r, "ncclAllGather (IPC handles)");
+  cudaStreamSynchronize(h->stream);
+  std::vector<P2PExport> all((size_t)4 * h->world);
+  cudaMemcpy(all.data(), drecv, rec * h->world, cudaMemcpyDeviceToHost);
+  cudaFree(dsend); cudaFree(drecv);
+  for (int q = 0; q < h->world; ++q) {
+    void* ptr[4];
+    for (int k = 0; k < 4; ++k) {
+      if (q == h->rank) { ptr[k] = local[k]; continue; }
+      void* base = nullptr;
+      if (cudaIpcOpenMemHandle(&base, all[(size_t)q * 4 + k].hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        fprintf(stderr, "ekf_dist: cudaIpcOpenMemHandle failed (rank %d <- %d): staying on NCCL\n", h->rank, q);
+        return EKF_OK;   // mappings opened so far are closed by detach
+      }
+      h->p2p.mapped[q][k] = base;
+      ptr[k] = (char*)base + all[(size_t)q * 4 + k].off;
+    }
+    for (int k = 0; k < 3; ++k) h->p2p.peerW[k][q] = (double*)ptr[k];
+    h->p2p.peerSpart[q] = (double*)ptr[3];
+    h->p2p.peerFlags[q] = (unsigned long long*)((double*)ptr[3] + spart_doubles);
+  }
+  h->p2p.on = true;
   return EKF_OK;
+}
+
+static void p2p_teardown(ekf_handle* h) {
+  for (int q = 0; q < 8; ++q)
+    for (int k = 0; k < 4; ++k)
+      if (h->p2p.mapped[q][k]) { cudaIpcCloseMemHandle(h->p2p.mapped[q][k]); h->p2p.mapped[q][k] = nullptr; }
+  if (h->p2p.xs) { cudaFree(h->p2p.xs); h->p2p.xs = nullptr; }
+  h->p2p.on = false;
 }
 
 int ekf_dist_detach(ekf_handle* h) {
@@ -82,11 +152,18 @@ int ekf_dist_detach(ekf_handle* h) {
   if (h->nccl_comm) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->p2p.xs) {   // no peer may still be storing into this rank when its buffers go away
+      g_nccl.AllReduce(h->p2p.xs, h->p2p.xs, 1, kNcclDouble, 0, (ncclComm_t)h->nccl_comm, h->stream);
+      cudaStreamSynchronize(h->stream);
+      p2p_teardown(h);
+    }
     g_nccl.CommDestroy((ncclComm_t)h->nccl_comm);
     h->nccl_comm = nullptr; h->rank = 0; h->world = 1;
   }
   return EKF_OK;
 }
+
+int ekf_dist_peer_memory(const ekf_handle* h) { return h && h->p2p.on ? 1 : 0; }
 
 int ekf_dist_info(const ekf_handle* h, int* rank, int* world, int64_t* allgather_bytes) {
   if (!h) return EKF_ERR_ARG;

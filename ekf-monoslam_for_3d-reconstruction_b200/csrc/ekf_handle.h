@@ -53,6 +53,17 @@ struct ekf_handle {
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
   long long dist_bytes = 0;   // bytes this rank contributed to all-gathers so far
+  // Peer-memory exchange of the partitioned look-ahead update (ekf_dist.cu::p2p_setup): the panels go to the peers
+  // by NVLink stores from inside the producing kernels instead of NCCL calls.
+  struct P2P {
+    bool on = false;
+    void* mapped[8][4] = {};              // cudaIpcOpenMemHandle results per peer (to close on detach)
+    double* peerW[3][8] = {};             // peers' Wbuf[0..2] (own entry = local pointer)
+    double* peerSpart[8] = {};            // peers' partial-S slots [world][EKF_UB * EKF_UB]
+    unsigned long long* peerFlags[8] = {};  // peers' flag words: [0, 8) S epochs by writer rank, [8, 16) V epochs
+    double* xs = nullptr;                 // local allocation: partial-S slots, then the flag words
+    unsigned long long epoch = 0;         // one per update block, the same sequence on every rank
+  } p2p;
   ekf_step_stats stats{};
   long long launches = 0;
   std::string err;

@@ -53,6 +53,13 @@ void launch_blk_V(cudaStream_t st, double* W, int row0, int row1, const double* 
                   double* delta, long long* launches);
 void launch_blk_S_part(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const DevCfg& cfg, int row0, int row1, int add_diag,
                        const double* delta, double* nu, double* Sb, long long* launches);
+void launch_blk_S_part_p2p(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const DevCfg& cfg, int row0, int row1, int add_diag,
+                           const double* delta, double* nu, double* Sb, const P2PView& pv, unsigned int* ticket, long long* launches);
+void launch_blk_factor_p2p(cudaStream_t st, const double* spart, const unsigned long long* flags, int world, unsigned long long epoch,
+                           double* Ssum, const double* nu, double* Lb, double* Dblk, double* yb, DevCtl* ctl, long long* launches);
+void launch_blk_V_p2p(cudaStream_t st, double* W, int row0, int row1, const double* Lb, const double* Dblk, const double* yb,
+                      const P2PView& pv, unsigned int* ticket, const unsigned long long* flags, int world, unsigned long long epoch,
+                      DevCtl* ctl, long long* launches);
 void launch_delta_rows(cudaStream_t st, const double* V, const double* y, double* delta, int n, long long* launches);
 void launch_apply_delta(cudaStream_t st, double* mu, const double* delta, int n, long long* launches);
 void launch_bookkeeping(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, DevCtl* ctl,

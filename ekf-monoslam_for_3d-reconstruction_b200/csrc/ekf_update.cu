@@ -98,6 +98,56 @@ __global__ void __launch_bounds__(128) k_hi_rescue(const double* __restrict__ Si
 }
 
 // ------------------------------------------------------------------------------------------------
+// Peer-memory exchange (row-block partition, look-ahead pipeline).  A producing kernel stores its panel into
+// every peer's buffer over NVLink, its last CTA publishes the block's epoch in every peer's flag word, and the
+// consumer spins on its OWN flag words (bounded: a timeout sets ctl->chol_fail |= 16 instead of hanging).
+// ------------------------------------------------------------------------------------------------
+#define P2P_TIMEOUT_CYCLES (1ll << 32)   // ~2 s at 1.965 GHz
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+// called by every thread of a kernel after its peer stores; the last CTA to arrive publishes `epoch` in slot
+// `slot0 + rank` of every rank's flag words.  ticket: device counter, self-resetting.
+__device__ __forceinline__ void p2p_publish(const P2PView& pv, int slot0, unsigned int* ticket) {
+  __shared__ int last_cta;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(ticket, 1u);
+    last_cta = (t == gridDim.x * gridDim.y - 1);
+  }
+  __syncthreads();
+  if (!last_cta) return;
+  __threadfence_system();
+  if (threadIdx.x < pv.world) st_release_sys(pv.flags[threadIdx.x] + slot0 + pv.rank, pv.epoch);
+  if (threadIdx.x == 0) *ticket = 0;
+}
+// lanes 0 .. world-1 of the calling warp wait until slot0 + r of the LOCAL flag words reached `epoch`
+__device__ __forceinline__ void p2p_wait(const unsigned long long* local_flags, int slot0, int world, unsigned long long epoch, DevCtl* ctl) {
+  const int lane = threadIdx.x & 31;
+  if (lane < world) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(local_flags + slot0 + lane) < epoch) {
+      if (clock64() - t0 > P2P_TIMEOUT_CYCLES) { atomicOr(&ctl->chol_fail, 16); break; }
+      __nanosleep(100);
+    }
+  }
+  __syncwarp();
+}
+__global__ void k_p2p_publish_only(P2PView pv, int slot0) {   // a rank without rows still has to report
+  __threadfence_system();
+  if (threadIdx.x < pv.world) st_release_sys(pv.flags[threadIdx.x] + slot0 + pv.rank, pv.epoch);
+}
+__global__ void k_p2p_wait(const unsigned long long* local_flags, int slot0, int world, unsigned long long epoch, DevCtl* ctl) {
+  p2p_wait(local_flags, slot0, world, epoch, ctl);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4a: W_b = Sigma H_b^T for the block of <= 64 selected features starting at sel[f0]
 // (n x EKF_UB, row-major), and nu_b = (z - h) - H_b delta.  One pass over the needed columns of Sigma.
 // ------------------------------------------------------------------------------------------------
@@ -162,7 +212,7 @@ __global__ void __launch_bounds__(EKF_UB) k_blk_S(const double* __restrict__ W, 
                                                   double sigma_pixel_2, double* __restrict__ Sb, int plain,
                                                   const double* __restrict__ delta, double* __restrict__ nu,
                                                   const double* __restrict__ Gsub, int row0 = 0, int row1 = 0x7fffffff,
-                                                  int add_diag = 1) {
+                                                  int add_diag = 1, P2PView pv = P2PView{}, unsigned int* ticket = nullptr) {
   // plain == 0: S_b = H_b W + sigma_px^2 I (identity past the block's rows).
   // plain != 0: G = H_b W with zero padding — W then holds the PREVIOUS block's V (look-ahead correction).
   // nu != null: CTA 0 also forms nu_b = (z - h) - H_b delta.
@@ -198,6 +248,9 @@ __global__ void __launch_bounds__(EKF_UB) k_blk_S(const double* __restrict__ W, 
     }
   }
   Sb[r * EKF_UB + s] = v;
+  if (ticket) {   // the partial block goes into slot `rank` of every rank's partial-S buffer
+    for (int q = 0; q < pv.world; ++q) pv.spart[q][(size_t)pv.rank * EKF_UB * EKF_UB + r * EKF_UB + s] = v;
+  }
   if (plain == 2) Sb[EKF_UB * EKF_UB + s * EKF_UB + r] = v;   // G^T for the S pass of the look-ahead pipeline
   if (nu && r == 0) {
     double out = 0.0;
@@ -211,6 +264,7 @@ __global__ void __launch_bounds__(EKF_UB) k_blk_S(const double* __restrict__ W, 
     }
     nu[s] = out;
   }
+  if (ticket) p2p_publish(pv, 0, ticket);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -256,6 +310,24 @@ __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __res
   cta_chol_panel<EKF_UB>(fsm, Sb, EKF_UB, nu, Lout, EKF_UB, Dblk, 32, yout, &ctl->chol_fail);
 }
 
+// Row-block partition: S_b = sum over ranks of the partial blocks the peers stored into this rank's slots (fixed
+// order: every rank forms the same bits), once every peer's epoch has arrived; then the same factorisation.
+__global__ void __launch_bounds__(FACT_THREADS) k_blk_factor_p2p(const double* __restrict__ spart, const unsigned long long* __restrict__ flags,
+                                                                 int world, unsigned long long epoch, double* __restrict__ Ssum,
+                                                                 const double* __restrict__ nu, double* __restrict__ Lout,
+                                                                 double* __restrict__ Dblk, double* __restrict__ yout, DevCtl* ctl) {
+  extern __shared__ __align__(16) double fsm[];
+  if (threadIdx.x < 32) p2p_wait(flags, 0, world, epoch, ctl);
+  __syncthreads();
+  for (int e = threadIdx.x; e < EKF_UB * EKF_UB; e += FACT_THREADS) {
+    double s = 0;
+    for (int q = 0; q < world; ++q) s += __ldcg(spart + (size_t)q * EKF_UB * EKF_UB + e);
+    Ssum[e] = s;
+  }
+  __syncthreads();
+  cta_chol_panel<EKF_UB>(fsm, Ssum, EKF_UB, nu, Lout, EKF_UB, Dblk, 32, yout, &ctl->chol_fail);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K4c: V_b = W_b L^-T in place (blocked triangular solve on the fp64 tensor pipe, DMMA.8x8x4) and
 // delta += V_b y.  One CTA = 32 rows; each of its 4 warps owns one 8-row tile for the whole solve
@@ -267,7 +339,7 @@ __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __res
 #define VT_LDD 36
 __global__ void __launch_bounds__(VT_THREADS) k_blk_V(double* __restrict__ W, int rbase, int n, const double* __restrict__ Lg,
                                                       const double* __restrict__ Dg, const double* __restrict__ yg,
-                                                      double* __restrict__ delta) {
+                                                      double* __restrict__ delta, P2PView pv = P2PView{}, unsigned int* ticket = nullptr) {
   extern __shared__ __align__(16) double vsm[];
   double* Ls = vsm;                          // [EKF_UB][VT_LD]  L (lower)
   double* Ds = Ls + EKF_UB * VT_LD;          // [EKF_UB / 32][32][VT_LDD] inverses of the diagonal blocks
@@ -309,9 +381,16 @@ __global__ void __launch_bounds__(VT_THREADS) k_blk_V(double* __restrict__ W, in
   __syncthreads();
   for (int e = tid; e < VT_ROWS * EKF_UB / 2; e += VT_THREADS) {
     const int r = e >> 6, c = (e & 63) * 2;
-    if (row0 + r < n)
-      *reinterpret_cast<double2*>(W + (size_t)(row0 + r) * EKF_UB + c) = *reinterpret_cast<const double2*>(Ws + r * VT_LD + c);
+    if (row0 + r < n) {
+      const double2 v = *reinterpret_cast<const double2*>(Ws + r * VT_LD + c);
+      *reinterpret_cast<double2*>(W + (size_t)(row0 + r) * EKF_UB + c) = v;
+      if (ticket) {   // all-gather fused into the solve: the finished rows go straight into every peer's panel over NVLink
+        for (int q = 0; q < pv.world; ++q)
+          if (q != pv.rank) *reinterpret_cast<double2*>(pv.w[q] + (size_t)(row0 + r) * EKF_UB + c) = v;
+      }
+    }
   }
+  if (ticket) p2p_publish(pv, 8, ticket);
 }
 
 // delta += V y for ALL rows, one warp per row (row-block partition: every rank runs this on the all-gathered V so that
@@ -376,6 +455,8 @@ static const size_t kVSmem = (size_t)(EKF_UB * VT_LD + (EKF_UB / 32) * 32 * VT_L
 int update_kernels_init() {
   cudaError_t e = cudaFuncSetAttribute(k_blk_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFactSmem);
   if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_blk_factor_p2p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFactSmem);
+  if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_blk_V, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVSmem);
   return (int)e;
 }
@@ -439,6 +520,29 @@ void launch_blk_V(cudaStream_t st, double* W, int row0, int row1, const double* 
 void launch_blk_S_part(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const DevCfg& cfg, int row0, int row1, int add_diag,
                        const double* delta, double* nu, double* Sb, long long* launches) {
   k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(W, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, delta, nu, nullptr, row0, row1, add_diag);
+  *launches += 1;
+}
+// peer-memory variants of the partitioned look-ahead update (pv: the peer mappings of this block, passed by value)
+void launch_blk_S_part_p2p(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const DevCfg& cfg, int row0, int row1, int add_diag,
+                           const double* delta, double* nu, double* Sb, const P2PView& pv, unsigned int* ticket, long long* launches) {
+  k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(W, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, delta, nu, nullptr, row0, row1, add_diag, pv, ticket);
+  *launches += 1;
+}
+void launch_blk_factor_p2p(cudaStream_t st, const double* spart, const unsigned long long* flags, int world, unsigned long long epoch,
+                           double* Ssum, const double* nu, double* Lb, double* Dblk, double* yb, DevCtl* ctl, long long* launches) {
+  k_blk_factor_p2p<<<1, FACT_THREADS, kFactSmem, st>>>(spart, flags, world, epoch, Ssum, nu, Lb, Dblk, yb, ctl);
+  *launches += 1;
+}
+void launch_blk_V_p2p(cudaStream_t st, double* W, int row0, int row1, const double* Lb, const double* Dblk, const double* yb,
+                      const P2PView& pv, unsigned int* ticket, const unsigned long long* flags, int world, unsigned long long epoch,
+                      DevCtl* ctl, long long* launches) {
+  if (row1 > row0) {
+    k_blk_V<<<(row1 - row0 + VT_ROWS - 1) / VT_ROWS, VT_THREADS, kVSmem, st>>>(W, row0, row1, Lb, Dblk, yb, nullptr, pv, ticket);
+  } else {
+    k_p2p_publish_only<<<1, 32, 0, st>>>(pv, 8);
+  }
+  *launches += 1;
+  k_p2p_wait<<<1, 32, 0, st>>>(flags, 8, world, epoch, ctl);   // every rank's rows of V_b have landed in the local panel
   *launches += 1;
 }
 void launch_delta_rows(cudaStream_t st, const double* V, const double* y, double* delta, int n, long long* launches) {

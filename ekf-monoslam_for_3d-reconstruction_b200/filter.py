@@ -234,7 +234,7 @@ class VSlamFilter:
     def dist_info(self):
         r, w, b = C.c_int(0), C.c_int(0), C.c_int64(0)
         self._ck(self.L.ekf_dist_info(self.h, C.byref(r), C.byref(w), C.byref(b)))
-        return dict(rank=r.value, world=w.value, allgather_bytes=b.value)
+        return dict(rank=r.value, world=w.value, allgather_bytes=b.value, peer_memory=bool(self.L.ekf_dist_peer_memory(self.h)))
 
 
 def nccl_unique_id(libnccl_path=None) -> bytes:

@@ -280,6 +280,9 @@ int ekf_dist_unique_id(char out[128]);
 int ekf_dist_attach(ekf_handle* h, const char id[128], int rank, int world);
 int ekf_dist_detach(ekf_handle* h);
 int ekf_dist_info(const ekf_handle* h, int* rank, int* world, int64_t* allgather_bytes);
+/* 1 when the panels of the partitioned look-ahead update travel by peer-memory stores from inside the producing kernels
+ * (CUDA IPC mappings set up by ekf_dist_attach; EKF_DIST_P2P=0 or a failed mapping keeps the NCCL collectives), else 0. */
+int ekf_dist_peer_memory(const ekf_handle* h);
 
 /* ---- per-kernel timing (CUDA events on the handle's stream; off by default) ---------------------- */
 #define EKF_PROF_CLASSES 12

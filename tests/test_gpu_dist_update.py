@@ -42,7 +42,7 @@ def _worker(rank, world, port, out_dir, n_features, n_frames, lookahead_min_n):
         s = f.stats(); stats.append((s.n_matched, s.n_li, s.n_hi))
     mu, S = f.get_full()
     info = f.dist_info()
-    np.savez(os.path.join(out_dir, f"r{rank}.npz"), mu=mu, S=S, stats=np.array(stats), bytes=info["allgather_bytes"], world=info["world"])
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), mu=mu, S=S, stats=np.array(stats), bytes=info["allgather_bytes"], world=info["world"], peer=int(info["peer_memory"]))
     f.dist_detach()
     dist.barrier()
     dist.destroy_process_group()
@@ -59,6 +59,8 @@ def test_row_partitioned_update_matches_single_gpu_and_oracle(gpu_pkg, orc, tmp_
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), n_features, n_frames, lookahead_min_n), nprocs=world, join=True)
     r = [np.load(tmp_path / f"r{k}.npz") for k in range(world)]
     assert int(r[0]["world"]) == 2 and int(r[0]["bytes"]) > 0
+    # the panels travel by peer-memory stores unless EKF_DIST_P2P=0 (then by NCCL collectives)
+    assert int(r[0]["peer"]) == (0 if os.environ.get("EKF_DIST_P2P") == "0" else 1)
     # replicas stay identical across ranks (same arithmetic on the same data)
     assert np.array_equal(r[0]["mu"], r[1]["mu"]) and np.array_equal(r[0]["S"], r[1]["S"])
     sc = gpu_pkg.synth.Scene(n_features=n_features, n_frames=n_frames, seed=55)
