@@ -162,7 +162,7 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
   TRY(dalloc(&h->newpos_dev, h->Ncap)) TRY(dalloc(&h->ctl, 1)) TRY(dalloc(&h->gemm_counters, 2))
   h->Wbuf[0] = h->W;
   TRY(dalloc(&h->Wbuf[1], (size_t)(h->ncap + 1 + EKF_DIST_PAD_ROWS) * EKF_UB)) TRY(dalloc(&h->Wbuf[2], (size_t)(h->ncap + 1 + EKF_DIST_PAD_ROWS) * EKF_UB)) TRY(dalloc(&h->Wbuf[3], (size_t)(h->ncap + 1) * EKF_UB))
-  TRY(dalloc(&h->Gbuf, 2 * EKF_UB * EKF_UB))   // G and G^T
+  TRY(dalloc(&h->Gbuf, EKF_UB * EKF_UB))
   {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = least priority

@@ -236,13 +236,15 @@ __global__ void __launch_bounds__(EKF_UB) k_blk_S(const double* __restrict__ W, 
     }
     v = acc + ((!plain && r == s && add_diag) ? sigma_pixel_2 : 0.0);
     if (Gsub) {
-      // G^T follows G in the buffer (written by the plain pass): Gt[k][s] is coalesced over s and every load is independent
-      const double* gt = Gsub + EKF_UB * EKF_UB + s;
+      // thread s streams row s of G (16-byte loads, 16 in flight) against row r in shared memory; a transposed copy of G
+      // read coalesced over s was measured SLOWER (25 vs 15 us: twice the load instructions in this latency-bound kernel)
+      const double2* gs = reinterpret_cast<const double2*>(Gsub + (size_t)s * EKF_UB);
       double g0 = 0, g1 = 0, g2 = 0, g3 = 0;
 #pragma unroll 8
-      for (int k = 0; k < EKF_UB; k += 4) {
-        g0 += Gr[k] * gt[(size_t)k * EKF_UB]; g1 += Gr[k + 1] * gt[(size_t)(k + 1) * EKF_UB];
-        g2 += Gr[k + 2] * gt[(size_t)(k + 2) * EKF_UB]; g3 += Gr[k + 3] * gt[(size_t)(k + 3) * EKF_UB];
+      for (int k = 0; k < EKF_UB / 2; k += 2) {
+        const double2 t = gs[k], u = gs[k + 1];
+        g0 += Gr[2 * k] * t.x; g1 += Gr[2 * k + 1] * t.y;
+        g2 += Gr[2 * k + 2] * u.x; g3 += Gr[2 * k + 3] * u.y;
       }
       v -= (g0 + g1) + (g2 + g3);
     }
@@ -251,7 +253,6 @@ __global__ void __launch_bounds__(EKF_UB) k_blk_S(const double* __restrict__ W, 
   if (ticket) {   // the partial block goes into slot `rank` of every rank's partial-S buffer
     for (int q = 0; q < pv.world; ++q) pv.spart[q][(size_t)pv.rank * EKF_UB * EKF_UB + r * EKF_UB + s] = v;
   }
-  if (plain == 2) Sb[EKF_UB * EKF_UB + s * EKF_UB + r] = v;   // G^T for the S pass of the look-ahead pipeline
   if (nu && r == 0) {
     double out = 0.0;
     if (s < kr) {
@@ -503,7 +504,7 @@ void launch_blk_gather2(cudaStream_t st, const double* Sigma, int ld, int n, Fea
   *launches += 1;
 }
 void launch_blk_G(cudaStream_t st, const double* Vprev, FeatTab ft, int f0, int cnt, double* G, long long* launches) {
-  k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(Vprev, ft, f0, cnt, 0.0, G, 2, nullptr, nullptr, nullptr);   // G and G^T (2 x EKF_UB^2 doubles)
+  k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(Vprev, ft, f0, cnt, 0.0, G, 1, nullptr, nullptr, nullptr);
   *launches += 1;
 }
 void launch_blk_factor_only(cudaStream_t st, const double* Sb, const double* nu, double* Lb, double* Dblk, double* yb, DevCtl* ctl,

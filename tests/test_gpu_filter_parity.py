@@ -112,21 +112,24 @@ def test_multi_block_update(gpu_pkg, orc, symmetric):
         assert_state_close(g, o, ctx=f"frame {t} multi-block")
 
 
-def test_lookahead_pipeline_parity(gpu_pkg, orc, monkeypatch):
-    """The look-ahead stacked update (second stream, W correction GEMM; default only for n >= 6000) forced on at
-    n = 914 / three update blocks: same tolerance as the plain path."""
-    monkeypatch.setenv("EKF_LOOKAHEAD_MIN_N", "1")
-    sc = _scene(gpu_pkg, n_features=150, n_frames=4, seed=6)
+@pytest.mark.parametrize("env,n_features", [("EKF_LOOKAHEAD_MIN_N", 150), ("EKF_PIPE_MIN_N", 150), ("EKF_PIPE_MIN_N", 210)])
+def test_lookahead_pipeline_parity(gpu_pkg, orc, monkeypatch, env, n_features):
+    """The two pipelined stacked updates forced on at n = 914 (three update blocks) and n = 1274 (four): the look-ahead
+    schedule (second stream, W correction GEMM; default for n >= 6000) and the factor-beside-downdate schedule (S_b from the raw
+    gather minus G G^T, correction on a third stream; default for 1000 <= n < 6000).  Same tolerance as the plain path."""
+    monkeypatch.setenv("EKF_LOOKAHEAD_MIN_N", "1000000")
+    monkeypatch.setenv(env, "1")
+    sc = _scene(gpu_pkg, n_features=n_features, n_frames=4, seed=6)
     g, o = make_pair(gpu_pkg, orc, sc)
     seed_features(g, sc); seed_features(o, sc)
     for t in range(1, 4):
         mu, S = o.get_full(); g.set_full(mu, S)
         img = sc.frame(t)
         for f in (g, o):
-            f.captureNewFrame(img, sc.stamps[t]); f.predict(); f.update(sc.picks(t, 150))
+            f.captureNewFrame(img, sc.stamps[t]); f.predict(); f.update(sc.picks(t, n_features))
         assert g.stats().n_li == o.stats().n_li and g.stats().n_li > 128
         assert_tables_equal(g, o, ctx=f"frame {t}")
-        assert_state_close(g, o, ctx=f"frame {t} look-ahead")
+        assert_state_close(g, o, ctx=f"frame {t} {env}")
 
 
 def test_remove_feature_and_controls(gpu_pkg, orc):
