@@ -765,6 +765,7 @@ int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
   h->stats.n_hi = n_hi;
   h->stats.ransac_hypotheses = outi[4];
   h->stats.blur_requests = outi[6];
+  if (outi[5] & 16) return ekf_fail(h, EKF_ERR_CUDA, "row-block partition: a peer's panel did not arrive within the wait limit (peer-memory exchange)");
   if (outi[5]) return ekf_fail(h, EKF_ERR_STATE, "innovation covariance not positive definite");
   if (outi[7]) return ekf_fail(h, EKF_ERR_UNSUPPORTED, "a motion-blur kernel exceeded 256 x 256 pixels");
   h->cache_ok = false;
