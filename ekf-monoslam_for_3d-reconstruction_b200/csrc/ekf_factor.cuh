@@ -209,46 +209,54 @@ __device__ void cta_chol_panel(double* fsm, const double* Sb, int lds, const dou
       const int I0 = 4 * P + 4, pidx = seg(P + 2) - first - (T - I0 + 1);   // tile (I0, I0) in the list
       const unsigned char* tp = tl + 2 * first;
       const int k0 = 32 * P;
+      // Fragments come as 16-byte loads: lane (g, t4) takes columns 8 q + 2 t4 and 8 q + 2 t4 + 1 of its row, the first feeds a
+      // DMMA over the even columns of the 8-chunk, the second one over the odd columns (a and b use the same column
+      // assignment, so the two sums cover the chunk) — half the load instructions of 8-byte fragments and, at this row
+      // stride, no bank conflicts (the updates are shared-memory-bandwidth bound); two accumulators per tile.
       if (warp == 0) {
         const int ra = 8 * I0 + g;
         double* cp = A + ra * FLD + 8 * I0 + 2 * t4;
         double2 cv = *reinterpret_cast<const double2*>(cp);
         double c1x = 0.0, c1y = 0.0;
 #pragma unroll
-        for (int kq = 0; kq < 8; kq += 2) {
-          const double f0 = A[ra * FLD + k0 + 4 * kq + t4], f1 = A[ra * FLD + k0 + 4 * kq + 4 + t4];
-          dmma884f(cv.x, cv.y, -f0, f0);
-          dmma884f(c1x, c1y, -f1, f1);
+        for (int q = 0; q < 4; ++q) {
+          const double2 f = *reinterpret_cast<const double2*>(A + ra * FLD + k0 + 8 * q + 2 * t4);
+          dmma884f(cv.x, cv.y, -f.x, f.x);
+          dmma884f(c1x, c1y, -f.y, f.y);
         }
         *reinterpret_cast<double2*>(cp) = make_double2(cv.x + c1x, cv.y + c1y);
         __syncwarp();
         chol_pivot4<(KO & 1) != 0>(A, FLD, base, piv, rinvs, chol_fail, lane);
       } else if (!(KO & 8)) {
-        for (int t0 = warp - 1; t0 < ntile; t0 += 3 * UW) {
-          double d0[3], d1[3];
-          double* cp[3];
-          const double *ap[3], *bp[3];
-          bool live[3];
+        for (int t0 = warp - 1; t0 < ntile; t0 += 4 * UW) {
+          double d0[4], d1[4], e0[4], e1[4];
+          double* cp[4];
+          const double *ap[4], *bp[4];
+          bool live[4];
 #pragma unroll
-          for (int u = 0; u < 3; ++u) {
+          for (int u = 0; u < 4; ++u) {
             const int t = t0 + u * UW;
             live[u] = t < ntile && t != pidx;
             const int I = live[u] ? tp[2 * t] : T, J = live[u] ? tp[2 * t + 1] : 0;
-            ap[u] = A + (8 * I + g) * FLD + k0 + t4;
-            bp[u] = A + (8 * J + g) * FLD + k0 + t4;
+            ap[u] = A + (8 * I + g) * FLD + k0 + 2 * t4;
+            bp[u] = A + (8 * J + g) * FLD + k0 + 2 * t4;
             cp[u] = A + (8 * I + g) * FLD + 8 * J + 2 * t4;
             const double2 cv = *reinterpret_cast<const double2*>(cp[u]);
-            d0[u] = cv.x; d1[u] = cv.y;
+            d0[u] = cv.x; d1[u] = cv.y; e0[u] = 0.0; e1[u] = 0.0;
           }
 #pragma unroll
-          for (int kq = 0; kq < 8; ++kq) {
+          for (int q = 0; q < 4; ++q) {
 #pragma unroll
-            for (int u = 0; u < 3; ++u) dmma884f(d0[u], d1[u], -ap[u][4 * kq], bp[u][4 * kq]);
+            for (int u = 0; u < 4; ++u) {
+              const double2 av = *reinterpret_cast<const double2*>(ap[u] + 8 * q), bv = *reinterpret_cast<const double2*>(bp[u] + 8 * q);
+              dmma884f(d0[u], d1[u], -av.x, bv.x);
+              dmma884f(e0[u], e1[u], -av.y, bv.y);
+            }
           }
           // padding rows past nu (tile row T, g > 0) are zero in every column: their update is zero
 #pragma unroll
-          for (int u = 0; u < 3; ++u)
-            if (live[u]) *reinterpret_cast<double2*>(cp[u]) = make_double2(d0[u], d1[u]);
+          for (int u = 0; u < 4; ++u)
+            if (live[u]) *reinterpret_cast<double2*>(cp[u]) = make_double2(d0[u] + e0[u], d1[u] + e1[u]);
         }
       }
     }
