@@ -102,3 +102,20 @@ def test_keyframe_recorder_on_gpu_filter_matches_oracle(gpu_pkg, orc, tmp_path):
     assert np.allclose(Pg, Po, rtol=1e-5, atol=1e-12) and np.allclose(Cg, Co, rtol=1e-5, atol=1e-15)
     for (ca, pa, ja), (cb, pb, jb) in zip(Ng, No):
         assert ca == cb and ja == jb and np.allclose(pa, pb, rtol=1e-5, atol=1e-9)
+
+
+def test_points_features_empty_and_inverse_depth_only(gpu_pkg, orc):
+    """No feature: one zero row (psize = 0, RosVSLAMRansac.cpp:349 guarded); inverse-depth features only: all rows zero."""
+    sc = gpu_pkg.synth.Scene(n_features=6, n_frames=2, seed=3)
+    g, o = make_pair(gpu_pkg, orc, sc)
+    for f in (g, o):
+        f.captureNewFrame(sc.frame(0), sc.stamps[0])
+    Pg, Po = g.getPointsFeatures(), o.getPointsFeatures()
+    assert Pg.shape == Po.shape == (1, 12) and not Pg.any() and not Po.any()
+    assert g.deleted() == [] and o.deleted() == []
+    for f in (g, o):
+        for p in sc.feature_pixels:
+            f.addFeature(*p)
+    Pg, Po = g.getPointsFeatures(), o.getPointsFeatures()
+    assert Pg.shape == Po.shape == (g.feature(5).real_index + 1, 12) and not Pg.any() and not Po.any()
+    assert g.L.ekf_get_points_features(g.h, None, 0, None) < 0      # rows pointer is mandatory
