@@ -44,7 +44,7 @@ struct MatchSmem {
   int wsb;       // window row stride in bytes (multiple of 4, >= side + 8)
   int tw;        // template words per row
   int ncmax;     // max candidates = (2 cl + 1)^2
-  size_t off_tpk, off_tb, off_win, off_h1, off_h2, off_b1, off_b2, off_score, off_list, off_red, total;
+  size_t off_tpk, off_tb, off_win, off_h1, off_h2, off_b1, off_b2, off_score, off_list, off_red, off_da, total;
 };
 __host__ __device__ inline MatchSmem match_smem_plan(int w, int cl) {
   MatchSmem p;
@@ -68,28 +68,34 @@ __host__ __device__ inline MatchSmem match_smem_plan(int w, int cl) {
   p.off_list = o; o += (size_t)MATCH_LIST * 4;                                // guard-band candidate keys
   o = (o + 7) & ~(size_t)7;
   p.off_red = o; o += 16 * sizeof(double) + 16 * sizeof(float) + 16 * sizeof(int);
+  o = (o + 7) & ~(size_t)7;
+  p.off_da = o; o += (size_t)w * w * sizeof(double);                          // (double)(float)t - m1 per template pixel (exact pass)
   p.total = o;
   return p;
 }
 
-// The reference's computeCorrelation for one candidate (window ROI at byte offset `roi`): exact
-// operation order, three independent accumulation chains (n1, n2, corr) as in Patch.cpp:316-326.
-__device__ __forceinline__ float match_exact_score(const uint8_t* tmpl, const uint8_t* win, int wsb, int roi, int w, double m1,
-                                                   int P) {
+// The reference's computeCorrelation for one candidate (window ROI at byte offset `roi`) in its exact operation order.  The
+// three accumulation chains of Patch.cpp:316-326 — n1 = sum da da, n2 = sum db db, corr = sum da db, each a sequential sum
+// over the pixels in row-major order — are independent, so three lanes of a 4-lane group run one chain each on the SAME
+// instruction stream (role 0: n1, 1: n2, 2: corr): a third of the fp64 instructions of one thread running all three, and
+// the chain (one DADD of 8.7 cycles per pixel) stays the only serial dependency.  da = (double)(float)t - m1 comes from shared
+// memory (formed once per feature with the same expression).  Every lane of the group returns the score.
+__device__ __forceinline__ float match_exact_score4(const double* da, const uint8_t* win, int wsb, int roi, int w, int P, int role,
+                                                    unsigned gmask, int gbase) {
   const double m2 = __ddiv_rn((double)P, (double)(w * w));
-  double n1 = 0, n2 = 0, corr = 0;
+  double acc = 0;
   for (int r = 0; r < w; ++r) {
     const uint8_t* wr = win + roi + r * wsb;
-    const uint8_t* tr = tmpl + r * w;
+    const double* dr = da + r * w;
 #pragma unroll 11
     for (int x = 0; x < w; ++x) {
-      const double da = __dsub_rn((double)(float)tr[x], m1);
-      const double db = __dsub_rn((double)(float)wr[x], m2);
-      n1 = __dadd_rn(n1, __dmul_rn(da, da));
-      n2 = __dadd_rn(n2, __dmul_rn(db, db));
-      corr = __dadd_rn(corr, __dmul_rn(da, db));
+      const double a = dr[x];
+      const double b = __dsub_rn((double)(float)wr[x], m2);
+      const double fa = role == 1 ? b : a, fb = role == 0 ? a : b;
+      acc = __dadd_rn(acc, __dmul_rn(fa, fb));
     }
   }
+  const double n1 = __shfl_sync(gmask, acc, gbase), n2 = __shfl_sync(gmask, acc, gbase + 1), corr = __shfl_sync(gmask, acc, gbase + 2);
   return (float)__ddiv_rn(corr, __dsqrt_rn(__dmul_rn(n2, n1)));
 }
 
@@ -164,6 +170,7 @@ __device__ MatchResult match_one(const MatchJob& jb, int w, float sigma_size, fl
   unsigned* H2 = reinterpret_cast<unsigned*>(smem_raw + pl.off_b2);
   double* score = reinterpret_cast<double*>(smem_raw + pl.off_score);
   int* list = reinterpret_cast<int*>(smem_raw + pl.off_list);
+  double* da = reinterpret_cast<double*>(smem_raw + pl.off_da);
   double* red_d = reinterpret_cast<double*>(smem_raw + pl.off_red);   // [0..7] warp maxima, [8] n1, [9] M*
   float* red_s = reinterpret_cast<float*>(red_d + 16);
   int* red_k = reinterpret_cast<int*>(red_s + 16);                     // [0..7] keys, [8] T, [9] TT, [10] list count
@@ -191,15 +198,38 @@ __device__ MatchResult match_one(const MatchJob& jb, int w, float sigma_size, fl
   // --- stage the window as bytes; columns past ww and the spare row are zero ---
   if (any) {
     const int x0 = ilo - half, y0 = jlo - half;
-    for (int yy = tid / 32; yy <= wh; yy += MATCH_THREADS / 32) {
-      const uint8_t* src = jb.frame + (size_t)(y0 + yy) * jb.fstride + x0;
-      for (int xx = tid & 31; xx < wsb; xx += 32) win[yy * wsb + xx] = (yy < wh && xx < ww) ? src[xx] : (uint8_t)0;
+    if ((((size_t)jb.frame | (size_t)jb.fstride) & 3) == 0) {
+      // aligned 4-byte loads, funnel-shifted to the window's own alignment (a quarter of the load instructions of the
+      // byte loop, which took a fifth of the kernel); the word past the last needed byte is never touched
+      const int sh = x0 & 3, xa = x0 - sh, nwords = wsb >> 2;
+      for (int yy = tid / 32; yy <= wh; yy += MATCH_THREADS / 32) {
+        const unsigned* srcw = reinterpret_cast<const unsigned*>(jb.frame + (size_t)(y0 + yy) * jb.fstride + xa);
+        unsigned* dstw = reinterpret_cast<unsigned*>(win + yy * wsb);
+        for (int k = tid & 31; k < nwords; k += 32) {
+          unsigned v = 0;
+          if (yy < wh && 4 * k < ww) {
+            const int last = min(4 * k + 3, ww - 1);          // last window column this word needs
+            const unsigned lo = srcw[k];
+            const unsigned hi = (sh > 0 && last + sh >= 4 * k + 4) ? srcw[k + 1] : 0u;
+            v = __funnelshift_r(lo, hi, 8 * sh);
+            const int rem = ww - 4 * k;
+            if (rem < 4) v &= (1u << (8 * rem)) - 1u;
+          }
+          dstw[k] = v;
+        }
+      }
+    } else {
+      for (int yy = tid / 32; yy <= wh; yy += MATCH_THREADS / 32) {
+        const uint8_t* src = jb.frame + (size_t)(y0 + yy) * jb.fstride + x0;
+        for (int xx = tid & 31; xx < wsb; xx += 32) win[yy * wsb + xx] = (yy < wh && xx < ww) ? src[xx] : (uint8_t)0;
+      }
     }
   }
   __syncthreads();
   const int T = red_k[8], TT = red_k[9];
   const double dn = (double)w2;
   const double m1 = __ddiv_rn((double)T, dn);
+  for (int e = tid; e < w2; e += MATCH_THREADS) da[e] = __dsub_rn((double)(float)tb[e], m1);   // read after later barriers
   // --- w x w box sums of p and p^2 for every candidate (exact ints), separable with sliding sums:
   //     a thread produces 4 adjacent outputs from one w-term sum plus three add/subtract slides ---
   if (any) {
@@ -333,14 +363,19 @@ __device__ MatchResult match_one(const MatchJob& jb, int w, float sigma_size, fl
     const int nlist = red_k[10];
     const bool overflow = nlist > MATCH_LIST;
     const int nwork = overflow ? ncand : nlist;
-    for (int q = tid; q < nwork; q += MATCH_THREADS) {
+    // one 4-lane group per guard-band candidate (see match_exact_score4); whole warps iterate together
+    const int lane = tid & 31, role = tid & 3, gbase = lane & ~3;
+    const unsigned gmask = 0xfu << gbase;
+    for (int q0 = (tid >> 5) * 8; q0 < nwork; q0 += (MATCH_THREADS / 32) * 8) {
+      const int q = q0 + (lane >> 2);
+      if (q >= nwork) continue;                          // uniform inside a 4-lane group
       const int c = overflow ? q : list[q];
       if (overflow && !(score[c] > kNone)) continue;
       const int jv = c / cw, iu = c - jv * cw;
       const int P = (int)H1[c];
-      const float sc = match_exact_score(tb, win, wsb, jv * wsb + iu, w, m1, P);
+      const float sc = match_exact_score4(da, win, wsb, jv * wsb + iu, w, P, role, gmask, gbase);
       const int key = (ilo + iu - i0) * nv + (jlo + jv - j0);  // position in the reference's scan order (u outer, v inner)
-      if (sc > best || (sc == best && key < bestkey)) { best = sc; bestkey = key; }
+      if (role == 0 && (sc > best || (sc == best && key < bestkey))) { best = sc; bestkey = key; }
     }
   }
   // --- arg-max: higher score wins, ties go to the earlier key (strict '>' in a sequential scan) ---
