@@ -91,7 +91,8 @@ __device__ __forceinline__ void chol_pivot4(double* A, int FLD, int p, double* p
 // Tiles lie on a fixed 8-aligned grid; fragment rows left of / above the trailing block are zeroed, so
 // finished entries of L are never touched.  nu rides along as row NB (tile row T): its panel entries come
 // out as y = L^-1 nu.  The earlier version applied every rank-4 update to the whole trailing matrix and
-// factored the pivot between two barriers: 57 us per 128 x 128 block against ~?? us now (tools/factor_probe.cu).
+// factored the pivot between two barriers: 57 us per 128 x 128 block against 40 us now (tools/factor_ko_probe.cu; the
+// per-phase accounting is in DESIGN.md section 4: the updates are bound by shared-memory bandwidth).
 // KO: timing knock-outs for tools/factor_probe.cu only (1 pivot chain, 2 panel solve, 4 rank-4 update, 8 rank-32 update,
 // 16 diagonal-block inverses, 32 barriers); production code instantiates KO = 0.
 template <int NB, int KO = 0>
