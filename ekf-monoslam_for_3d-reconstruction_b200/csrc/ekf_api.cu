@@ -174,8 +174,8 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
     }
     TRY(cudaEventCreateWithFlags(&h->ev_S, cudaEventDisableTiming)) TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming))
     // look-ahead pays off once the downdate of a block (n x n x 128) is long against the block's gain chain:
-    // measured +27 % at n = 11972, -7 % at n = 3014 (the chain kernels' large shared-memory CTAs cannot be
-    // co-scheduled with the downdate's while it is short); EKF_LOOKAHEAD_MIN_N overrides the threshold
+    // measured +27 % at n = 11972; at n = 3014 only +6 % (the chain kernels' large shared-memory CTAs queue behind the
+    // short, resident downdate) against +33 % for the schedule below; EKF_LOOKAHEAD_MIN_N overrides the threshold
     const char* e = getenv("EKF_LOOKAHEAD_MIN_N");
     h->lookahead = e ? atoi(e) : 6000;
     // below that threshold: the schedule that starts the downdate of a block beside the NEXT block's Cholesky
