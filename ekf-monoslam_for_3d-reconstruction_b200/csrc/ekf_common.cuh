@@ -53,6 +53,7 @@ struct DevCtl {
   int chol_fail;          // non-positive pivot seen
   int blur_count;         // templates blurred by the last predict
   int blur_too_large;     // a blur kernel exceeded the supported 256 x 256
+  int rs_sel, rs_count;   // cluster RANSAC (k_ransac_cluster): feature picked by CTA 0, inlier count summed over the CTAs
 };
 
 // Feature table (structure of arrays, device pointers).

@@ -13,6 +13,8 @@
 // complement of the preceding blocks, so the sequence is exactly a right-looking blocked Cholesky
 // of the full St whose trailing updates are carried by the covariance downdate; in exact arithmetic
 // it equals the reference's one-shot update (R is diagonal, H is evaluated once at the prior mean).
+#include <cstdlib>
+
 #include "ekf_kernels.h"
 #include "ekf_math.cuh"
 #include "ekf_cta.cuh"
@@ -29,6 +31,142 @@ __global__ void __launch_bounds__(RANSAC_THREADS) k_ransac(const double* __restr
                                                            DevCfg cfg, const uint32_t* __restrict__ picks, int n_picks,
                                                            double* __restrict__ mu_i, int* __restrict__ cand) {
   cta_ransac(Sigma, ld, n, mu, ft, N, ctl, cfg, picks, n_picks, mu_i, cand);
+}
+
+// The same loop by a thread-block CLUSTER of RANSAC_CL CTAs (single filter, n >= RANSAC_CLUSTER_MIN_N): the two O(n) / O(N)
+// phases of a hypothesis — mu_i = mu + (Sigma H_i^T) S_i^-1 (z_i - h_i), 13 scattered columns of Sigma for every row, and the
+// re-projection of every feature — are split over the CTAs (one SM pulls ~1.25 MB of 32-byte sectors per hypothesis at
+// n = 3014, which bounded the one-CTA version: 43 us); the candidate list stays with CTA 0, the pick and the inlier count
+// travel through DevCtl, and cluster barriers (release / acquire at cluster scope) order the global-memory hand-overs.
+// Every CTA keeps its own copy of the loop state (cnt, nhyp, best count), computed from the same inputs, so all of them
+// leave the loop in the same iteration.  Arithmetic per row / per feature is that of cta_ransac: identical flags and counts.
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+#define RANSAC_CL 8
+#define RANSAC_CL_THREADS 512
+#define RANSAC_CLUSTER_MIN_N 1000
+__global__ void __launch_bounds__(RANSAC_CL_THREADS) k_ransac_cluster(const double* __restrict__ Sigma, int ld, int n,
+                                                                      const double* __restrict__ mu, FeatTab ft, int N, DevCtl* ctl,
+                                                                      DevCfg cfg, const uint32_t* __restrict__ picks, int n_picks,
+                                                                      double* __restrict__ mu_i, int* __restrict__ cand) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank(), ncta = (int)cluster.num_blocks();
+  const int nthr = blockDim.x, tid = threadIdx.x;
+  __shared__ double Hs[26], Sinv[4], inn[2], rr[3], Rcw[9];
+  __shared__ int s_pos, s_nd, s_nhyp, s_numzli, s_cnt;
+  if (rank == 0) {
+    const int c0 = block_compact(ft.innov, N, cand, nullptr);
+    if (tid == 0) {
+      ctl->n_matched = c0;
+      for (int i = 0; i < 7; ++i) ctl->cam_old[i] = mu[i];
+      ctl->rs_count = 0;
+    }
+  }
+  cluster.sync();
+  if (tid == 0) { s_cnt = ctl->n_matched; s_nhyp = cfg.nhyp0; s_numzli = 0; }
+  __syncthreads();
+  const int matched = s_cnt;
+  int cnt = matched, it = 0;
+  while (it < s_nhyp && cnt > 0) {
+    if (rank == 0) {   // pick without replacement (V:989-991); the list is private to CTA 0
+      __shared__ int s_p;
+      if (tid == 0) {
+        const uint32_t rv = n_picks > 0 ? picks[it % n_picks] : 0u;
+        s_p = (int)(rv % (uint32_t)cnt);
+        ctl->rs_sel = cand[s_p];
+        ctl->rs_count = 0;
+      }
+      __syncthreads();
+      const int p = s_p;
+      int tmp[8];
+      int c = 0;
+      for (int idx = p + tid; idx < cnt - 1 && c < 8; idx += nthr) tmp[c++] = cand[idx + 1];
+      __syncthreads();
+      c = 0;
+      for (int idx = p + tid; idx < cnt - 1 && c < 8; idx += nthr) cand[idx] = tmp[c++];
+    }
+    cnt -= 1;
+    cluster.sync();                                   // the pick is visible
+    const int sel = ctl->rs_sel;
+    if (tid < 26) Hs[tid] = ft.Hc[26 * sel + tid];
+    if (tid == 32) {
+      double S[4];
+      for (int c = 0; c < 4; ++c) S[c] = ft.S2[4 * sel + c];
+      double X[4];
+      d_inv2_pplu(S, X);
+      for (int c = 0; c < 4; ++c) Sinv[c] = X[c];
+      inn[0] = ft.z[2 * sel] - ft.h[2 * sel];
+      inn[1] = ft.z[2 * sel + 1] - ft.h[2 * sel + 1];
+      s_pos = ft.pos[sel];
+      s_nd = 7 + (ft.coding[sel] ? 3 : 6);
+    }
+    __syncthreads();
+    {  // mu_i = mu + (Sigma H^T) S^-1 (z - h)   (V:995-996), rows interleaved over the cluster
+      const int pos = s_pos, nd = s_nd;
+      for (int i = rank * nthr + tid; i < n; i += ncta * nthr) {
+        const double* row = Sigma + (size_t)i * ld;
+        double sg[13];
+#pragma unroll
+        for (int c = 0; c < 13; ++c) sg[c] = (c < nd) ? row[ekf_idx13(c, pos)] : 0.0;
+        double w0 = 0, w1 = 0;
+#pragma unroll
+        for (int c = 0; c < 13; ++c)
+          if (c < nd) { w0 += sg[c] * Hs[c]; w1 += sg[c] * Hs[13 + c]; }
+        const double k0 = w0 * Sinv[0] + w1 * Sinv[2];
+        const double k1 = w0 * Sinv[1] + w1 * Sinv[3];
+        mu_i[i] = mu[i] + (k0 * inn[0] + k1 * inn[1]);
+      }
+    }
+    cluster.sync();                                   // mu_i complete
+    if (tid == 0) {
+      for (int c = 0; c < 3; ++c) rr[c] = mu_i[c];
+      double q[4] = {mu_i[3], mu_i[4], mu_i[5], mu_i[6]};
+      const double qn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+      double qc[4];
+      qc[0] = q[0] / qn; qc[1] = -(q[1] / qn); qc[2] = -(q[2] / qn); qc[3] = -(q[3] / qn);
+      double R[9];
+      d_quat2rot(qc, R);
+      for (int c = 0; c < 9; ++c) Rcw[c] = R[c];
+    }
+    __syncthreads();
+    int local = 0;
+    for (int start = rank * nthr; start < N; start += ncta * nthr) {
+      const int i = start + tid;
+      int flag = 0;
+      if (i < N && ft.innov[i]) {
+        const int pos = ft.pos[i], coding = ft.coding[i];
+        double fs[6], hi[2], r3[3] = {rr[0], rr[1], rr[2]}, R[9];
+        for (int c = 0; c < 9; ++c) R[c] = Rcw[c];
+        if (!coding) for (int c = 0; c < 6; ++c) fs[c] = mu_i[pos + c];
+        else for (int c = 0; c < 3; ++c) fs[c] = mu[pos + c];  // quirk V:1016: mu, not mu_i
+        d_feature_h(cfg.cam, fs, coding, r3, R, hi);
+        const double e0 = ft.z[2 * i] - hi[0], e1 = ft.z[2 * i + 1] - hi[1];
+        flag = (sqrt(e0 * e0 + e1 * e1) <= cfg.th_low) ? 1 : 0;
+        ft.li[i] = flag;
+      }
+      local += __syncthreads_count(flag);
+    }
+    if (tid == 0 && local > 0) atomicAdd(&ctl->rs_count, local);
+    cluster.sync();                                   // the count is complete
+    if (tid == 0) {
+      const int actual = ctl->rs_count;
+      if (actual > s_numzli) {
+        s_numzli = actual;
+        s_nhyp = (int)(log(1 - cfg.ransac_p) / (log(1 - (actual / (matched + 0.0)))));  // V:1030
+      }
+    }
+    ++it;
+    cluster.sync();                                   // everybody has read the count before CTA 0 clears it for the next pick
+  }
+  cluster.sync();
+  if (rank == 0) {
+    const int nli = block_compact(ft.li, N, ft.sel, ft.pos_in_z);  // V:1040-1048
+    if (tid == 0) {
+      ctl->ransac_hyps = it;
+      ctl->n_li = nli;
+      ctl->k_rows = 2 * nli;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -464,6 +602,21 @@ int update_kernels_init() {
 
 void launch_ransac(cudaStream_t st, const double* Sigma, int ld, int n, const double* mu, FeatTab ft, int N, DevCtl* ctl,
                    const DevCfg& cfg, const uint32_t* picks, int n_picks, double* mu_i, int* cand, long long* launches) {
+  static int use_cluster = -1;
+  if (use_cluster < 0) { const char* e = getenv("EKF_RANSAC_CLUSTER"); use_cluster = e ? atoi(e) : 1; }
+  if (use_cluster && n >= RANSAC_CLUSTER_MIN_N) {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(RANSAC_CL); lc.blockDim = dim3(RANSAC_CL_THREADS); lc.dynamicSmemBytes = 0; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = RANSAC_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    if (cudaLaunchKernelEx(&lc, k_ransac_cluster, Sigma, ld, n, mu, ft, N, ctl, cfg, picks, n_picks, mu_i, cand) == cudaSuccess) {
+      *launches += 1;
+      return;
+    }
+    cudaGetLastError();   // fall through to the one-CTA kernel
+  }
   k_ransac<<<1, RANSAC_THREADS, 0, st>>>(Sigma, ld, n, mu, ft, N, ctl, cfg, picks, n_picks, mu_i, cand);
   *launches += 1;
 }
