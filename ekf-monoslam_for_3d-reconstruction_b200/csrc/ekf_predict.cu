@@ -11,9 +11,8 @@
 //   blocks 1..         : thread j (>= 13): column j of rows 0:13  <- F * Sigma[0:13, j]
 //                                          row j of cols 0:13     <- Sigma[j, 0:13] * F^T
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_predict_cov(double* __restrict__ Sigma, int ld, int n,
-                                                     const double* __restrict__ mu, DevCtl* ctl, DevCfg cfg,
-                                                     double dT, double3 dv, double3 dw, int vcontrol) {
+__device__ __forceinline__ void predict_cov_body(int bid, double* __restrict__ Sigma, int ld, int n, const double* __restrict__ mu,
+                                                 DevCtl* ctl, const DevCfg& cfg, double dT, double3 dv, double3 dw, int vcontrol) {
   __shared__ double F[169];
   __shared__ double C[169], T[169], Q[169];
   if (threadIdx.x == 0) {
@@ -23,7 +22,7 @@ __global__ void __launch_bounds__(256) k_predict_cov(double* __restrict__ Sigma,
     d_system_jacobian(mu13, dT, ctrl, F);
   }
   __syncthreads();
-  if (blockIdx.x == 0) {
+  if (bid == 0) {
     for (int e = threadIdx.x; e < 169; e += blockDim.x) C[e] = Sigma[(size_t)(e / 13) * ld + (e % 13)];
     __syncthreads();
     // Q = (F6 * Vs) * F6^T, Vs = (V/dT)/dT diagonal, F6 = F[:, 7:13] (V:463-473)
@@ -57,7 +56,7 @@ __global__ void __launch_bounds__(256) k_predict_cov(double* __restrict__ Sigma,
     }
     return;
   }
-  const int j = 13 + (blockIdx.x - 1) * blockDim.x + threadIdx.x;
+  const int j = 13 + (bid - 1) * blockDim.x + threadIdx.x;
   if (j >= n) return;
   double x[13], y[13];
   // column j of the camera rows (coalesced across threads)
@@ -85,12 +84,8 @@ __global__ void __launch_bounds__(256) k_predict_cov(double* __restrict__ Sigma,
 // St = H Sigma H^T + sigma_px^2 I (the only part of St the reference consumes, V:875), and — by the
 // last block to finish — the ordered compaction that assigns position_in_z (V:584-592).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_predict_features(const double* __restrict__ Sigma, int ld, double* __restrict__ mu,
-                                                          FeatTab ft, int N, FrameView fr, DevCtl* ctl, DevCfg cfg) {
-  __shared__ int is_last;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double cam[13];
-  for (int c = 0; c < 13; ++c) cam[c] = ctl->mu_cam_new[c];
+__device__ __forceinline__ int predict_features_body(int i, const double* cam, const double* __restrict__ mu, FeatTab ft, int N, FrameView fr,
+                                                     const DevCfg& cfg) {
   int ok = 0;
   if (i < N) {
     const int pos = ft.pos[i], coding = ft.coding[i];
@@ -122,7 +117,35 @@ __global__ void __launch_bounds__(128) k_predict_features(const double* __restri
     uint4* dst = reinterpret_cast<uint4*>(ft.mpatch + (size_t)i * cfg.tstride);
     for (int c = 0; c < chunks; ++c) dst[c] = src[c];
   }
-  // last block: commit the predicted camera state and compact
+  return ok;
+}
+
+// K1 and K2 in ONE launch: CTAs [0, nb_cov) propagate the covariance, CTAs [nb_cov, ..) predict the features.  The two
+// are independent once every feature CTA forms the predicted camera state itself (Predict_State on the thirteen old camera
+// entries: the bits CTA 0 writes to ctl->mu_cam_new); mu is committed — and the in-innovation list compacted — by the last
+// CTA of the grid to finish, after every CTA has read the old mu (one launch and one dependent-launch gap less than the
+// two kernels this replaces).
+__global__ void __launch_bounds__(256) k_predict_fused(double* __restrict__ Sigma, int ld, int n, double* __restrict__ mu, FeatTab ft,
+                                                       int N, FrameView fr, DevCtl* ctl, DevCfg cfg, double dT, double3 dv, double3 dw,
+                                                       int vcontrol, int nb_cov) {
+  __shared__ int is_last;
+  __shared__ double camS[13];
+  if ((int)blockIdx.x < nb_cov) {
+    predict_cov_body((int)blockIdx.x, Sigma, ld, n, mu, ctl, cfg, dT, dv, dw, vcontrol);
+  } else {
+    if (threadIdx.x == 0) {
+      double X[13];
+      for (int i = 0; i < 13; ++i) X[i] = mu[i];
+      const double a[3] = {dv.x, dv.y, dv.z}, b[3] = {dw.x, dw.y, dw.z};
+      d_predict_state(X, a, b, dT);
+      for (int i = 0; i < 13; ++i) camS[i] = X[i];
+    }
+    __syncthreads();
+    double cam[13];
+    for (int c = 0; c < 13; ++c) cam[c] = camS[c];
+    predict_features_body(((int)blockIdx.x - nb_cov) * blockDim.x + threadIdx.x, cam, mu, ft, N, fr, cfg);
+  }
+  // last CTA of the grid: commit the predicted camera state and compact
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -132,7 +155,7 @@ __global__ void __launch_bounds__(128) k_predict_features(const double* __restri
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  if (threadIdx.x < 13) mu[threadIdx.x] = cam[threadIdx.x];
+  if (threadIdx.x < 13) mu[threadIdx.x] = ctl->mu_cam_new[threadIdx.x];
   const int m = block_compact(ft.innov, N, ft.sel, ft.pos_in_z);
   if (threadIdx.x == 0) {
     ctl->m_innov = m;
@@ -573,11 +596,10 @@ void launch_predict(cudaStream_t st, double* Sigma, int ld, int n, double* mu, F
                     DevCtl* ctl, const DevCfg& cfg, double dT, const double dv[3], const double dw[3], int vcontrol,
                     long long* launches) {
   const int nb = 1 + (n - 13 + 255) / 256;
-  k_predict_cov<<<nb, 256, 0, st>>>(Sigma, ld, n, mu, ctl, cfg, dT, make_double3(dv[0], dv[1], dv[2]),
-                                   make_double3(dw[0], dw[1], dw[2]), vcontrol);
-  const int fb = N > 0 ? (N + 127) / 128 : 1;
-  k_predict_features<<<fb, 128, 0, st>>>(Sigma, ld, mu, ft, N, fr, ctl, cfg);
-  *launches += 2;
+  const int fb = N > 0 ? (N + 255) / 256 : 1;
+  k_predict_fused<<<nb + fb, 256, 0, st>>>(Sigma, ld, n, mu, ft, N, fr, ctl, cfg, dT, make_double3(dv[0], dv[1], dv[2]),
+                                          make_double3(dw[0], dw[1], dw[2]), vcontrol, nb);
+  *launches += 1;
   if (N > 0 && cfg.kernel_min_size < 100000) {   // motion-blur templates enabled
     k_predict_blur<<<N, 128, 0, st>>>(mu, ft, N, ctl, cfg, dT);
     *launches += 1;
