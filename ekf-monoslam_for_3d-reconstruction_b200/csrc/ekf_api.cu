@@ -114,6 +114,7 @@ int ekf_destroy(ekf_handle* h) {
   cudaFree(h->det_mask); cudaFree(h->det_eig); cudaFree(h->det_keys); cudaFree(h->det_counters); cudaFree(h->det_xy);
   cudaFree(h->xyz_flag); cudaFree(h->xyz_rmap); cudaFree(h->xyz_pos); cudaFree(h->xyz_coding); cudaFree(h->xyz_y); cudaFree(h->xyz_J);
   if (h->out_host) cudaFreeHost(h->out_host);
+  if (h->ctl_host) cudaFreeHost(h->ctl_host);
   free_feattab(h->ft); free_feattab(h->ftB);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -187,7 +188,7 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
   TRY(dalloc(&h->xyz_coding, h->Ncap)) TRY(dalloc(&h->xyz_y, 3 * (size_t)h->Ncap)) TRY(dalloc(&h->xyz_J, 18 * (size_t)h->Ncap))
   TRY(alloc_feattab(h->ft, h->Ncap, w2)) TRY(alloc_feattab(h->ftB, h->Ncap, w2))
   h->out_bytes = sizeof(double) * 210 + sizeof(int) * (16 + 3 * (size_t)h->Ncap);
-  TRY(cudaMalloc((void**)&h->out_dev, h->out_bytes)) TRY(cudaMallocHost((void**)&h->out_host, h->out_bytes))
+  TRY(cudaMalloc((void**)&h->out_dev, h->out_bytes)) TRY(cudaMallocHost((void**)&h->out_host, h->out_bytes)) TRY(cudaMallocHost((void**)&h->ctl_host, sizeof(DevCtl)))
   TRY(cudaMemsetAsync(h->ctl, 0, sizeof(DevCtl), h->stream))
   TRY(cudaMemsetAsync(h->gemm_counters, 0, 2 * sizeof(int), h->stream))
   TRY(cudaMemsetAsync(h->Sigma, 0, sizeof(double) * ssz, h->stream))
@@ -551,8 +552,7 @@ static int stacked_update_lookahead(ekf_handle* h, int cnt) {
   if (dist) { ProfScope ps(h, 11); if (ekf_dist_allgather_rows(h, h->Sigma, rpr, (size_t)h->ld)) return (int)cudaErrorUnknown; }
   {
     ProfScope ps(h, 7);
-    launch_apply_delta(sm, h->mu, h->delta, h->n, &h->launches);
-    launch_quat_normalize(sm, h->Sigma, h->ld, h->n, h->mu, h->ctl, &h->launches);
+    launch_finish_update(sm, h->Sigma, h->ld, h->n, h->mu, h->delta, h->ctl, &h->launches);
   }
   return 0;
 }
@@ -625,8 +625,7 @@ static int stacked_update_factor_beside_downdate(ekf_handle* h, int cnt) {
   cudaStreamWaitEvent(sm, h->ev_join, 0);
   {
     ProfScope ps(h, 7);
-    launch_apply_delta(sm, h->mu, h->delta, h->n, &h->launches);
-    launch_quat_normalize(sm, h->Sigma, h->ld, h->n, h->mu, h->ctl, &h->launches);
+    launch_finish_update(sm, h->Sigma, h->ld, h->n, h->mu, h->delta, h->ctl, &h->launches);
   }
   return 0;
 }
@@ -702,8 +701,7 @@ static int stacked_update(ekf_handle* h, int cnt, bool plane = false) {
   if (dist) { ProfScope ps(h, 11); if (ekf_dist_allgather_rows(h, h->Sigma, rpr, (size_t)h->ld)) return (int)cudaErrorUnknown; }
   {
     ProfScope ps(h, 7);
-    launch_apply_delta(st, h->mu, h->delta, h->n, &h->launches);
-    launch_quat_normalize(st, h->Sigma, h->ld, h->n, h->mu, h->ctl, &h->launches);
+    launch_finish_update(st, h->Sigma, h->ld, h->n, h->mu, h->delta, h->ctl, &h->launches);
   }
   return 0;
 }
@@ -721,13 +719,13 @@ int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
     h->picks_cap = n_picks;
   }
   if (n_picks > 0) EKF_CUDA_CHECK(cudaMemcpyAsync(h->picks_dev, picks, sizeof(uint32_t) * n_picks, cudaMemcpyHostToDevice, st));
-  DevCtl hc;
+  DevCtl& hc = *h->ctl_host;   // pinned: the read-backs below are true asynchronous copies followed by one stream wait
   // 1-point RANSAC, then the low-innovation update
   {
     ProfScope ps(h, 2);
     launch_ransac(st, h->Sigma, h->ld, h->n, h->mu, h->ft, h->N, h->ctl, h->dcfg, h->picks_dev, n_picks, h->mu_i, h->cand, &h->launches);
   }
-  EKF_CUDA_CHECK(cudaMemcpyAsync(&hc, h->ctl, sizeof hc, cudaMemcpyDeviceToHost, st));
+  EKF_CUDA_CHECK(cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost, st));
   EKF_CUDA_CHECK(cudaStreamSynchronize(st));
   const int n_li = hc.n_li;
   if (n_li > 0) {
@@ -739,7 +737,7 @@ int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
     ProfScope ps(h, 8);
     launch_hi_rescue(st, h->Sigma, h->ld, h->mu, h->ft, h->N, h->ctl, h->dcfg, &h->launches);
   }
-  EKF_CUDA_CHECK(cudaMemcpyAsync(&hc, h->ctl, sizeof hc, cudaMemcpyDeviceToHost, st));
+  EKF_CUDA_CHECK(cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost, st));
   EKF_CUDA_CHECK(cudaStreamSynchronize(st));
   const int n_hi = hc.n_hi;
   const bool plane = h->cfg.forsePlane != 0;

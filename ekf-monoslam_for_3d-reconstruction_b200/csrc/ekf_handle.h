@@ -24,6 +24,7 @@ struct ekf_handle {
   double *xyz_y = nullptr, *xyz_J = nullptr;
   int *cand = nullptr, *map_dev = nullptr, *keep_dev = nullptr, *newpos_dev = nullptr, *gemm_counters = nullptr;
   DevCtl* ctl = nullptr;
+  DevCtl* ctl_host = nullptr;   // pinned mirror for the two mid-step read-backs (n_li, n_hi)
   FeatTab ft{}, ftB{};
   uint8_t* frame = nullptr;
   size_t frame_cap = 0;

@@ -8,7 +8,8 @@
 void launch_predict(cudaStream_t st, double* Sigma, int ld, int n, double* mu, FeatTab ft, int N, FrameView fr,
                     DevCtl* ctl, const DevCfg& cfg, double dT, const double dv[3], const double dw[3], int vcontrol,
                     long long* launches);
-void launch_quat_normalize(cudaStream_t st, double* Sigma, int ld, int n, double* mu, const DevCtl* ctl, long long* launches);
+void launch_finish_update(cudaStream_t st, double* Sigma, int ld, int n, double* mu, const double* delta, DevCtl* ctl,
+                          long long* launches);
 void launch_add_feature(cudaStream_t st, double* Sigma, int ld, int n, double* mu, FeatTab ft, int fidx, FrameView fr,
                         const DevCfg& cfg, float pfx, float pfy, int real_index, long long* launches);
 void launch_gather_state(cudaStream_t st, const double* Ssrc, double* Sdst, int ld, const double* musrc, double* mudst,

@@ -284,71 +284,79 @@ __global__ void __launch_bounds__(128) k_predict_S2(const double* __restrict__ S
 // 4x4 block J = (|q|^2 I - q q^T)/|q|^3 on rows/cols 3:7.  Structured: 4 rows + 4 columns.
 // Runs only when the preceding stacked update had rows (ctl->k_rows > 0), as in the reference.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_quat_normalize(double* __restrict__ Sigma, int ld, int n, double* __restrict__ mu,
-                                                        const DevCtl* ctl) {
-  if (ctl->k_rows <= 0) return;
+// mu += delta fused in: every CTA forms the updated, not yet normalised quaternion q = mu[3:7] + delta[3:7] itself; thread j
+// of the row / column CTAs also commits mu[j] += delta[j] for the entries outside the quaternion; the last CTA of the grid
+// (device ticket) writes the quaternion — normalised if the update had rows — after every CTA has read the old one.
+// One launch instead of three (apply_delta, normalise, commit).
+__global__ void __launch_bounds__(256) k_finish_update(double* __restrict__ Sigma, int ld, int n, double* __restrict__ mu,
+                                                       const double* __restrict__ delta, DevCtl* ctl) {
   __shared__ double J[16];
   __shared__ double C[16], T[16];
-  __shared__ double qn[4];
+  __shared__ double qs[4], qn[4];
+  __shared__ int is_last;
+  const bool rows = ctl->k_rows > 0;
   if (threadIdx.x == 0) {
-    // every block recomputes J from the pre-normalisation q; block 0 writes the normalised q at the end
     double q[4];
-    for (int i = 0; i < 4; ++i) q[i] = mu[3 + i];
+    for (int i = 0; i < 4; ++i) q[i] = mu[3 + i] + delta[3 + i];
     const double norma = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-    for (int i = 0; i < 4; ++i) qn[i] = q[i] / norma;
+    for (int i = 0; i < 4; ++i) { qs[i] = q[i]; qn[i] = q[i] / norma; }
     const double sc = 1 / (norma * norma * norma);
     for (int i = 0; i < 4; ++i)
       for (int j = 0; j < 4; ++j) J[i * 4 + j] = ((norma * norma) * (i == j ? 1.0 : 0.0) - q[i] * q[j]) * sc;
   }
   __syncthreads();
   if (blockIdx.x == 0) {
-    if (threadIdx.x < 16) C[threadIdx.x] = Sigma[(size_t)(3 + threadIdx.x / 4) * ld + 3 + (threadIdx.x % 4)];
-    __syncthreads();
-    if (threadIdx.x < 16) {
-      const int a = threadIdx.x / 4, b = threadIdx.x % 4;
-      double t = 0;
-      for (int k = 0; k < 4; ++k) t += J[a * 4 + k] * C[k * 4 + b];
-      T[threadIdx.x] = t;
+    if (rows) {
+      if (threadIdx.x < 16) C[threadIdx.x] = Sigma[(size_t)(3 + threadIdx.x / 4) * ld + 3 + (threadIdx.x % 4)];
+      __syncthreads();
+      if (threadIdx.x < 16) {
+        const int a = threadIdx.x / 4, b = threadIdx.x % 4;
+        double t = 0;
+        for (int k = 0; k < 4; ++k) t += J[a * 4 + k] * C[k * 4 + b];
+        T[threadIdx.x] = t;
+      }
+      __syncthreads();
+      if (threadIdx.x < 16) {
+        const int a = threadIdx.x / 4, b = threadIdx.x % 4;
+        double s = 0;
+        for (int k = 0; k < 4; ++k) s += T[a * 4 + k] * J[b * 4 + k];
+        Sigma[(size_t)(3 + a) * ld + 3 + b] = s;
+      }
     }
-    __syncthreads();
-    if (threadIdx.x < 16) {
-      const int a = threadIdx.x / 4, b = threadIdx.x % 4;
-      double s = 0;
-      for (int k = 0; k < 4; ++k) s += T[a * 4 + k] * J[b * 4 + k];
-      Sigma[(size_t)(3 + a) * ld + 3 + b] = s;
+  } else {
+    int j = (blockIdx.x - 1) * blockDim.x + threadIdx.x;  // index over states outside 3..6
+    if (j >= 3) j += 4;
+    if (j < n) {
+      mu[j] += delta[j];
+      if (rows) {
+        double x[4], y[4];
+        for (int c = 0; c < 4; ++c) x[c] = Sigma[(size_t)(3 + c) * ld + j];
+        for (int a = 0; a < 4; ++a) {
+          double s = 0;
+          for (int c = 0; c < 4; ++c) s += J[a * 4 + c] * x[c];
+          y[a] = s;
+        }
+        for (int a = 0; a < 4; ++a) Sigma[(size_t)(3 + a) * ld + j] = y[a];
+        double* row = Sigma + (size_t)j * ld + 3;
+        for (int c = 0; c < 4; ++c) x[c] = row[c];
+        for (int a = 0; a < 4; ++a) {
+          double s = 0;
+          for (int c = 0; c < 4; ++c) s += x[c] * J[a * 4 + c];
+          y[a] = s;
+        }
+        for (int a = 0; a < 4; ++a) row[a] = y[a];
+      }
     }
-    return;
   }
-  // all blocks > 0 read mu[3:7] before block-last writes it: the write happens in a separate tiny
-  // kernel (k_quat_commit) to avoid the race.
-  int j = (blockIdx.x - 1) * blockDim.x + threadIdx.x;  // index over states outside 3..6
-  if (j >= 3) j += 4;
-  if (j >= n) return;
-  double x[4], y[4];
-  for (int c = 0; c < 4; ++c) x[c] = Sigma[(size_t)(3 + c) * ld + j];
-  for (int a = 0; a < 4; ++a) {
-    double s = 0;
-    for (int c = 0; c < 4; ++c) s += J[a * 4 + c] * x[c];
-    y[a] = s;
-  }
-  for (int a = 0; a < 4; ++a) Sigma[(size_t)(3 + a) * ld + j] = y[a];
-  double* row = Sigma + (size_t)j * ld + 3;
-  for (int c = 0; c < 4; ++c) x[c] = row[c];
-  for (int a = 0; a < 4; ++a) {
-    double s = 0;
-    for (int c = 0; c < 4; ++c) s += x[c] * J[a * 4 + c];
-    y[a] = s;
-  }
-  for (int a = 0; a < 4; ++a) row[a] = y[a];
-}
-__global__ void k_quat_commit(double* __restrict__ mu, const DevCtl* ctl) {
-  if (ctl->k_rows <= 0) return;
+  __threadfence();
+  __syncthreads();
   if (threadIdx.x == 0) {
-    double q[4];
-    for (int i = 0; i < 4; ++i) q[i] = mu[3 + i];
-    const double norma = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-    for (int i = 0; i < 4; ++i) mu[3 + i] = q[i] / norma;
+    const unsigned t = atomicAdd(&ctl->ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+    if (is_last) ctl->ticket = 0;
   }
+  __syncthreads();
+  if (is_last && threadIdx.x < 4) mu[3 + threadIdx.x] = rows ? qn[threadIdx.x] : qs[threadIdx.x];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -609,11 +617,12 @@ void launch_predict(cudaStream_t st, double* Sigma, int ld, int n, double* mu, F
     *launches += 1;
   }
 }
-void launch_quat_normalize(cudaStream_t st, double* Sigma, int ld, int n, double* mu, const DevCtl* ctl, long long* launches) {
+// mu += delta and, when the update had rows, the quaternion renormalisation with its Jacobian on Sigma (V:1625-1642)
+void launch_finish_update(cudaStream_t st, double* Sigma, int ld, int n, double* mu, const double* delta, DevCtl* ctl,
+                          long long* launches) {
   const int nb = 1 + (n - 4 + 255) / 256;
-  k_quat_normalize<<<nb, 256, 0, st>>>(Sigma, ld, n, mu, ctl);
-  k_quat_commit<<<1, 32, 0, st>>>(mu, ctl);
-  *launches += 2;
+  k_finish_update<<<nb, 256, 0, st>>>(Sigma, ld, n, mu, delta, ctl);
+  *launches += 1;
 }
 void launch_add_feature(cudaStream_t st, double* Sigma, int ld, int n, double* mu, FeatTab ft, int fidx, FrameView fr,
                         const DevCfg& cfg, float pfx, float pfy, int real_index, long long* launches) {
