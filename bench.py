@@ -106,11 +106,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_scene(pkg, workload, n_frames, seed=1235):
+def make_scene(pkg, workload, n_frames, seed=1235, visible_every=1):
     nfeat, W, H = WORKLOADS[workload]
     # slow motion so that all seeded features stay inside the image for the whole run (fixed N)
     return pkg.synth.Scene(n_features=nfeat, width=W, height=H, n_frames=n_frames, seed=seed, speed=0.1, omega=0.02,
-                           accel_sigma=0.002, border=44)
+                           accel_sigma=0.002, border=44, visible_every=visible_every)
 
 
 def seed_filter(filt, scene):
@@ -147,9 +147,13 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K, Wm = args.steps, max(args.warmup, 3)
     nfeat, width, height = WORKLOADS[args.workload]
-    scene = make_scene(pkg, args.workload, 1 + Wm + K, seed=1235 + (0 if (world > 1 and args.workload.startswith("cfg4")) else rank))
+    scene = make_scene(pkg, args.workload, 1 + Wm + K, seed=1235 + (0 if (world > 1 and args.workload.startswith("cfg4")) else rank),
+                       visible_every=max(1, args.match_every))
     frames = [scene.frame(t) for t in range(scene.n_frames)]
-    cfg = pkg.default_config(**scene.config_overrides())
+    over = scene.config_overrides()
+    if args.match_every > 1:   # SURVEY.md 8(d) "also report m = N/4": unmatched features must stay in the map (fixed n)
+        over["quality_ratio"] = 1.0e9
+    cfg = pkg.default_config(**over)
     stream = torch.cuda.current_stream()
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
@@ -275,8 +279,9 @@ def run_ours(args):
             "ms_per_step": round(totA / K, 4), "higher_is_better": True, "scaling": "strong" if partitioned else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload}: single filter, {nfeat} inverse-depth features (n={n_state}), "
-                                   f"{width}x{height} u8 frames, predict+match+update per frame, all features matched "
-                                   f"(n_li={stA.n_li})",
+                                   f"{width}x{height} u8 frames, predict+match+update per frame, "
+                                   + ("all features matched" if args.match_every <= 1 else f"every {args.match_every}th feature visible")
+                                   + f" (n_li={stA.n_li})",
                        "l2": "flushed between timed steps (256 MiB write outside the event pairs)",
                        "multi_gpu": ("one filter, stacked update partitioned by covariance row blocks, look-ahead pipeline; partial S blocks "
                                      "and V panels exchanged " + ("by peer-memory stores from inside the producing kernels (NVLink)"
@@ -703,6 +708,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2_n500", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--match-every", type=int, default=1,
+                    help="single-filter workloads: only every k-th feature is visible after frame 0 (m = N / k matches per frame; "
+                         "the headline uses k = 1, all features matched, the stated worst case)")
     ap.add_argument("--full-square", action="store_true", help="downdate all n x n tiles instead of lower triangle + mirror")
     ap.add_argument("--frames", type=int, default=MATCH_FRAMES, help="frames per GPU of the matcher workload")
     ap.add_argument("--filters", type=int, default=BATCH_FILTERS, help="filters per GPU of the batched workload")

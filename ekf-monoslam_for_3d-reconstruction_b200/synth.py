@@ -94,6 +94,7 @@ class Scene:
     outlier_frac: float = 0.02
     outlier_shift: int = 8
     noise_sigma: float = 20.0
+    visible_every: int = 1    # > 1: after frame 0 only every visible_every-th feature's template is in the image (m = N / visible_every matches)
     template_smooth: float = 0.0  # > 0: low-pass templates (Gaussian sigma in px) that survive motion-blur prediction
 
     def __post_init__(self):
@@ -167,6 +168,8 @@ class Scene:
             if not (z[i] > 0 and np.isfinite(uv[i]).all()):
                 continue
             u = int(np.round(uv[i, 0])); v = int(np.round(uv[i, 1]))
+            if t > 0 and self.visible_every > 1 and i % self.visible_every:
+                continue
             if self.outliers[i] and t > 0:
                 u += self.outlier_shift
             x0, y0 = u - half, v - half
