@@ -62,7 +62,6 @@ void launch_blk_V_p2p(cudaStream_t st, double* W, int row0, int row1, const doub
                       const P2PView& pv, unsigned int* ticket, const unsigned long long* flags, int world, unsigned long long epoch,
                       DevCtl* ctl, long long* launches);
 void launch_delta_rows(cudaStream_t st, const double* V, const double* y, double* delta, int n, long long* launches);
-void launch_apply_delta(cudaStream_t st, double* mu, const double* delta, int n, long long* launches);
 void launch_bookkeeping(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, DevCtl* ctl,
                         const DevCfg& cfg, double* outd, int* outi, long long* launches);
 // ekf_export.cu

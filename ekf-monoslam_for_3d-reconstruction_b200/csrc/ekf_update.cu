@@ -551,10 +551,6 @@ __global__ void __launch_bounds__(256) k_delta_rows(const double* __restrict__ V
   if (lane == 0) delta[row] += s;
 }
 
-__global__ void k_apply_delta(double* __restrict__ mu, const double* __restrict__ delta, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) mu[i] += delta[i];
-}
 
 // ------------------------------------------------------------------------------------------------
 // Book-keeping (V:1296-1303, Patch.cpp:143-150) and the packed per-step output record.
@@ -701,10 +697,6 @@ void launch_blk_V_p2p(cudaStream_t st, double* W, int row0, int row1, const doub
 }
 void launch_delta_rows(cudaStream_t st, const double* V, const double* y, double* delta, int n, long long* launches) {
   k_delta_rows<<<(n + 7) / 8, 256, 0, st>>>(V, y, delta, n);
-  *launches += 1;
-}
-void launch_apply_delta(cudaStream_t st, double* mu, const double* delta, int n, long long* launches) {
-  k_apply_delta<<<(n + 255) / 256, 256, 0, st>>>(mu, delta, n);
   *launches += 1;
 }
 void launch_bookkeeping(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, DevCtl* ctl,
