@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("EKF_REFERENCE_ROOT", "/root/reference")
 SRC = os.path.join(REF, "mono-slam", "src")
 OUT = os.path.join(HERE, "_ref")
-FILES = ["vslamRansac.cpp", "Patch.cpp", "camModel.cpp", "utils.cpp", "libblur.cpp"]
+FILES = ["vslamRansac.cpp", "Patch.cpp", "camModel.cpp", "utils.cpp", "libblur.cpp", "RosVSLAMRansac.cpp"]
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 # -O2 -msse4 as mono-slam/CMakeLists.txt:3; asserts of the shim stay on (no -DNDEBUG); no FMA contraction
 COMMON = ["-std=c++17", "-O2", "-msse4", "-fPIC", "-shared", "-ffp-contract=off", "-w",

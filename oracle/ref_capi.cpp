@@ -1,7 +1,7 @@
 // oracle/ref_capi.cpp — TEST INFRASTRUCTURE ONLY.
 //
 // C harness around the REFERENCE'S OWN `class VSlamFilter`, compiled from the unmodified sources
-// under /root/reference/mono-slam/src (vslamRansac.cpp, Patch.cpp, camModel.cpp, utils.cpp, libblur.cpp) against
+// under /root/reference/mono-slam/src (vslamRansac.cpp, Patch.cpp, camModel.cpp, utils.cpp, libblur.cpp, RosVSLAMRansac.cpp) against
 // the API stand-ins in oracle/shim/ (Eigen3, OpenCV, ROS and libconfig++ are not installed here).
 // oracle/build_ref.py builds two variants into oracle/_ref/:
 //   libref_f32.so  the sources as written (fp32 state, what the reference really runs)
@@ -23,7 +23,7 @@
 #define private public
 #define protected public
 #define class struct
-#include "vslamRansac.hpp"
+#include "RosVSLAMRansac.hpp"   // includes vslamRansac.hpp; RosVSLAM::getPointsFeatures (RosVSLAMRansac.cpp:340-418)
 #include "libblur.h"
 #undef class
 #undef private
@@ -71,7 +71,8 @@ extern "C" void ekf_shim_log(int level, const char* fmt, ...) {
 }
 
 struct RefHandle {
-  VSlamFilter* f;
+  VSlamFilter* f;       // the RosVSLAM object seen through its base: predict / update resolve to VSlamFilter's (non-virtual)
+  RosVSLAM* ros = nullptr;
   int n_hyp_last = 0;
 };
 
@@ -83,12 +84,13 @@ void ref_set_log_level(int l) { g_log_level = l; }
 void* ref_create(const ekf_config* cfg) {
   g_cfg = *cfg;
   RefHandle* h = new RefHandle;
-  h->f = new VSlamFilter(nullptr);
+  h->ros = new RosVSLAM(nullptr);
+  h->f = h->ros;
   return h;
 }
 void ref_destroy(void* hh) {
   RefHandle* h = static_cast<RefHandle*>(hh);
-  delete h->f;
+  delete h->ros;
   delete h;
 }
 void ref_capture(void* hh, const uint8_t* gray, int w, int hgt, int stride, double stamp) {
@@ -186,6 +188,17 @@ void ref_get_deleted(void* hh, int i, int* real_index, double* xyz, double* cov9
   *real_index = p.real_index;
   for (int c = 0; c < 3; ++c) xyz[c] = (double)p.XYZ_pos(c);
   for (int c = 0; c < 9; ++c) cov9[c] = (double)p.cov_4_delete(c);
+}
+// RosVSLAM::getPointsFeatures, compiled from the reference's own RosVSLAMRansac.cpp (ROS message types are stand-ins)
+int ref_points_features(void* hh, double* out, int cap_rows) {
+  RosVSLAM* r = static_cast<RefHandle*>(hh)->ros;
+  if (r->patches.empty()) return 0;   // the reference reads patches[size-1] unguarded (RosVSLAMRansac.cpp:349)
+  MatrixXf pts = r->getPointsFeatures();
+  const int rows = (int)pts.rows();
+  if (out && cap_rows >= rows)
+    for (int i = 0; i < rows; ++i)
+      for (int j = 0; j < 12; ++j) out[i * 12 + j] = (double)pts(i, j);
+  return rows;
 }
 void ref_rts_epoch(void* hh, double* mu13, double* sg13, const double* mus13, const double* sgs13, const double* dts,
                    const double* drs, double dT) {

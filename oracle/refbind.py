@@ -54,6 +54,7 @@ def lib(fp64=True):
         "ref_find_match": (i32, [vp, i32, i32, i32, vp, i32, vp, vp, f32, vp]),
         "ref_num_deleted": (i32, [vp]), "ref_get_deleted": (None, [vp, i32, vp, vp, vp]),
         "ref_rts_epoch": (None, [vp, vp, vp, vp, vp, vp, vp, f64]),
+        "ref_points_features": (i32, [vp, vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -163,6 +164,14 @@ class ReferenceFilter:
             ri = np.zeros(1, dtype=np.int32); xyz = np.zeros(3); cov = np.zeros(9)
             self.L.ref_get_deleted(self.h, i, _ptr(ri), _ptr(xyz), _ptr(cov))
             out.append((int(ri[0]), xyz, cov))
+        return out
+
+    def getPointsFeatures(self):
+        """RosVSLAM::getPointsFeatures, compiled from RosVSLAMRansac.cpp."""
+        rows = self.L.ref_points_features(self.h, None, 0)
+        out = np.zeros((rows, 12))
+        if rows:
+            self.L.ref_points_features(self.h, _ptr(out), rows)
         return out
 
     def rts_epoch(self, MU, SIGMA, MU_S, SIGMA_S, dTspeed, dRspeed, deltaT):

@@ -232,10 +232,27 @@ def test_deleted_archive(pkg, orc, ref, fp64, kind, tol):
         f.convert2XYZ_ifLinearAll()
     xyz = [i for i in range(r.numOfFeatures()) if r.feature(i).coding]
     assert len(xyz) >= 2 and xyz == [i for i in range(o.numOfFeatures()) if o.feature(i).coding]
-    for i in sorted(xyz[:3] + [0], reverse=True):   # feature 0 is inverse-depth: removed, not archived
+    # RosVSLAM::getPointsFeatures, from the reference's own RosVSLAMRansac.cpp (oracle/_ref), before and after removals
+    Pr, Po = r.getPointsFeatures(), o.getPointsFeatures()
+    assert Pr.shape == Po.shape and np.count_nonzero(np.abs(Pr).sum(axis=1)) == len(xyz)
+    assert relerr(Po, Pr) <= tol, f"points matrix {relerr(Po, Pr):.2e}"
+    # feature 0 is inverse-depth: removed, not archived.  The LAST feature stays: once it is gone the reference's
+    # getPointsFeatures writes the archived rows with a larger real_index past its matrix (RosVSLAMRansac.cpp:349 sizes
+    # it by the last live patch) — undefined behaviour that the oracle and the CUDA path replace by dropping those rows.
+    victims = [i for i in xyz if i != r.numOfFeatures() - 1][:3]
+    for i in sorted(victims + [0], reverse=True):
         r.removeFeature(i); o.removeFeature(i)
     dr, do = r.deleted(), o.deleted()
-    assert len(dr) == len(do) == len(xyz[:3])
+    assert len(dr) == len(do) == len(victims) >= 2
+    Pr, Po = r.getPointsFeatures(), o.getPointsFeatures()
+    assert Pr.shape == Po.shape and relerr(Po, Pr) <= tol, "points matrix with archived rows"
+    assert np.count_nonzero(np.abs(Pr).sum(axis=1)) == len(xyz)
+    # oracle only: removing the last (XYZ, archived) feature drops its row instead of overflowing
+    last = o.numOfFeatures() - 1
+    if o.feature(last).coding:
+        o.removeFeature(last)
+        P2 = o.getPointsFeatures()
+        assert P2.shape[0] == o.feature(o.numOfFeatures() - 1).real_index + 1 and np.isfinite(P2).all()
     for (ia, xa, ca), (ib, xb, cb) in zip(dr, do):
         assert ia == ib
         assert relerr(xb, xa) <= tol and relerr(cb, ca) <= tol
