@@ -47,6 +47,17 @@ def test_points_features_and_archive(gpu_pkg, orc):
     assert Pg.shape == Po.shape and relerr(Pg, Po) <= TOL
     assert np.count_nonzero(np.abs(Pg).sum(axis=1)) == len(xyz)          # archived rows are filled from the archive
     assert_state_close(g, o, ctx="after removal")
+    # remove features from the END of the map until an archived XYZ one has gone: the reference would write its row past
+    # the matrix (sized by the last live patch); oracle and CUDA path drop it
+    while g.numOfFeatures() > 2:
+        last = g.numOfFeatures() - 1
+        was_xyz = bool(g.feature(last).coding)
+        g.removeFeature(last); o.removeFeature(last)
+        if was_xyz:
+            break
+    Pg, Po = g.getPointsFeatures(), o.getPointsFeatures()
+    assert Pg.shape == Po.shape == (g.feature(g.numOfFeatures() - 1).real_index + 1, 12) and relerr(Pg, Po) <= TOL
+    assert len(g.deleted()) == len(o.deleted()) == 3
 
 
 @pytest.mark.parametrize("seed,zero_w", [(1, False), (2, False), (3, True)])
