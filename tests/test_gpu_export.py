@@ -130,3 +130,14 @@ def test_points_features_empty_and_inverse_depth_only(gpu_pkg, orc):
     Pg, Po = g.getPointsFeatures(), o.getPointsFeatures()
     assert Pg.shape == Po.shape == (g.feature(5).real_index + 1, 12) and not Pg.any() and not Po.any()
     assert g.L.ekf_get_points_features(g.h, None, 0, None) < 0      # rows pointer is mandatory
+
+
+def test_cuda_path_reproduces_reference_export_fixture(gpu_pkg):
+    """rts_epoch, getPointsFeatures and the feature archive against vectors produced by the reference's own sources
+    (tests/golden/export_rts_points.npz, oracle/gen_golden_export.py)."""
+    import gen_golden_export as gg
+    from test_golden_export import GOLD, compare_export
+    gold = np.load(GOLD)
+    rec = gg.run_export_case(gpu_pkg, lambda over: gpu_pkg.VSlamFilter(gpu_pkg.default_config(**over), feature_capacity=16))
+    worst = compare_export(rec, gold, 1e-8, "CUDA path")   # eight free-running frames precede the export (helpers.py: 1e-8 over sequences)
+    print(f"CUDA path vs reference export fixture: worst rel err {worst:.2e}")
