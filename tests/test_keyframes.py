@@ -111,3 +111,27 @@ def test_cpp_twin_writes_identical_files(pkg, tmp_path):
     assert [os.path.basename(p) for p in out.split()] == [os.path.basename(p) for p in saved]
     for name in ("nodes_and_prjcts.txt", "cams_cov.txt", "cams_cov2.txt", "points.txt"):
         assert (pydir / name).read_bytes() == (cdir / name).read_bytes(), name
+
+
+def test_recorder_driven_by_the_oracle_filter(pkg, orc, tmp_path):
+    """End to end on the CPU: the oracle filter runs a short sequence, the recorder selects key frames from its accessors and
+    the files read back as the states / covariances the filter had at those frames; points.txt is getPointsFeatures()."""
+    from helpers import make_oracle, seed_features
+    kf = pkg.keyframes
+    sc = pkg.synth.Scene(n_features=20, n_frames=16, seed=13)
+    o = make_oracle(pkg, orc, sc, xyz_conversion=1)
+    seed_features(o, sc)
+    rec = kf.KeyframeRecorder(str(tmp_path))
+    rec.MoveThresh = 0.6           # the synthetic camera moves centimetres per frame
+    states, sigmas = {}, {}
+    for t in range(1, 16):
+        o.captureNewFrame(sc.frame(t), sc.stamps[t]); o.predict(); o.update(sc.picks(t, 20))
+        states[t], sigmas[t] = o.getState(), o.getSigma()
+        rec.on_frame(o, t, sc.frame(t))
+    rec.finish(o)
+    pts, cov, nodes = kf.read_sba_inputs(str(tmp_path))
+    assert len(nodes) >= 2 and len(nodes) == cov.shape[0] and nodes[0][0] == 1
+    for (cam, pose, projs), C in zip(nodes, cov):
+        assert np.allclose(pose, states[cam][:7], rtol=1e-5, atol=1e-9)
+        assert np.allclose(C, sigmas[cam][:7, :7], rtol=1e-5, atol=1e-15)
+    assert pts.shape == o.getPointsFeatures().shape
