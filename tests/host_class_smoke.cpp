@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "../ekf-monoslam_for_3d-reconstruction_b200/host/vslam_filter.hpp"
+#include "../ekf-monoslam_for_3d-reconstruction_b200/host/keyframe_recorder.hpp"
 
 int main() {
   try {
@@ -21,6 +22,18 @@ int main() {
     slam.predict();
     slam.update({1u, 2u, 3u});
     std::vector<double> mu = slam.getState();
+    // the caller-side rows: key-frame recorder over the real class, points matrix, archive, one RTS epoch
+    ekf_b200::KeyframeRecorder rec("/tmp");
+    rec.onFrame(slam, 1, img.data(), 640, 480, 640, 1);
+    rec.finish(slam);
+    int rows = 0;
+    const std::vector<double> pts = slam.getPointsFeatures(&rows);
+    const size_t n_deleted = slam.deletedPatches().size();
+    double MU[13] = {0, 0, 0, 1, 0, 0, 0, 0.1, 0, 0, 0, 0.01, 0}, SG[169] = {0}, SGS[169] = {0};
+    for (int i = 0; i < 13; ++i) { SG[i * 14] = 1e-3; SGS[i * 14] = 5e-4; }
+    const double dts[3] = {0, 0, 0}, drs[3] = {0, 0, 0};
+    slam.rts_epoch(MU, SG, MU, SGS, dts, drs, 1.0 / 30);
+    if (rows < 1 || pts.size() != (size_t)rows * 12 || n_deleted != 0 || !(SG[0] > 0)) return 4;
     printf("gpu ok: added %d features, n = %d, |q| part = %.6f, cov par = %g\n", added, slam.stateDim(), mu[6], slam.Covariance_Parameter());
     return added == 8 ? 0 : 2;
   } catch (const std::exception& e) {
