@@ -188,6 +188,8 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
   TRY(dalloc(&h->xyz_coding, h->Ncap)) TRY(dalloc(&h->xyz_y, 3 * (size_t)h->Ncap)) TRY(dalloc(&h->xyz_J, 18 * (size_t)h->Ncap))
   TRY(alloc_feattab(h->ft, h->Ncap, w2)) TRY(alloc_feattab(h->ftB, h->Ncap, w2))
   h->out_bytes = sizeof(double) * 210 + sizeof(int) * (16 + 3 * (size_t)h->Ncap);
+  h->picks_cap = EKF_PICKS_CAP;
+  TRY(dalloc(&h->picks_dev, (size_t)h->picks_cap))
   TRY(cudaMalloc((void**)&h->out_dev, h->out_bytes)) TRY(cudaMallocHost((void**)&h->out_host, h->out_bytes)) TRY(cudaMallocHost((void**)&h->ctl_host, sizeof(DevCtl)))
   TRY(cudaMemsetAsync(h->ctl, 0, sizeof(DevCtl), h->stream))
   TRY(cudaMemsetAsync(h->gemm_counters, 0, 2 * sizeof(int), h->stream))
@@ -711,13 +713,8 @@ int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
   if (!h->predicted) return ekf_fail(h, EKF_ERR_STATE, "update before predict");
   EKF_CUDA_CHECK(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
-  if (n_picks > h->picks_cap) {
-    EKF_CUDA_CHECK(cudaStreamSynchronize(st));
-    cudaFree(h->picks_dev);
-    h->picks_dev = nullptr;
-    EKF_CUDA_CHECK(cudaMalloc((void**)&h->picks_dev, sizeof(uint32_t) * n_picks));
-    h->picks_cap = n_picks;
-  }
+  // picks_dev is sized once by ekf_create (EKF_PICKS_CAP draws): no allocation inside the step
+  if (n_picks > h->picks_cap) return ekf_fail(h, EKF_ERR_CAPACITY, "more RANSAC picks than EKF_PICKS_CAP: pass at most that many draws per update");
   if (n_picks > 0) EKF_CUDA_CHECK(cudaMemcpyAsync(h->picks_dev, picks, sizeof(uint32_t) * n_picks, cudaMemcpyHostToDevice, st));
   DevCtl& hc = *h->ctl_host;   // pinned: the read-backs below are true asynchronous copies followed by one stream wait
   // 1-point RANSAC, then the low-innovation update

@@ -15,6 +15,27 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
+// Function attributes (the > 48 KB dynamic shared-memory opt-in) belong to a device, not to the process: a handle on a
+// second GPU of the same process needs its own cudaFuncSetAttribute.  One bit per device ordinal, set once the attribute
+// call SUCCEEDED on that device; safe against concurrent first launches (setting an attribute twice is harmless).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> bits{0};
+  // returns cudaSuccess when the attribute is (now) set on the current device
+  template <class F>
+  cudaError_t ensure(F&& set_attr) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (bits.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = set_attr();
+    if (e == cudaSuccess) bits.fetch_or(bit, std::memory_order_release);
+    return e;
+  }
+};
+
 #define EKF_CAM 14  // STATE_DIM (vslamRansac.cpp:22)
 
 struct CamParams {

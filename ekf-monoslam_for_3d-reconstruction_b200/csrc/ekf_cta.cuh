@@ -34,13 +34,16 @@ static __device__ __noinline__ void cta_ransac(const double* __restrict__ Sigma,
     }
     __syncthreads();
     const int p = s_p, sel = s_sel;
-    {  // erase cand[p] (V:991)
-      int tmp[8];
-      int c = 0;
-      for (int idx = p + tid; idx < cnt - 1 && c < 8; idx += nthr) tmp[c++] = cand[idx + 1];
-      __syncthreads();
-      c = 0;
-      for (int idx = p + tid; idx < cnt - 1 && c < 8; idx += nthr) cand[idx] = tmp[c++];
+    {  // erase cand[p] (V:991): chunks of 8 * nthr entries, low to high, so any list length is handled
+      for (int base = p; base < cnt - 1; base += 8 * nthr) {
+        int tmp[8];
+        int c = 0;
+        for (int idx = base + tid; idx < cnt - 1 && c < 8; idx += nthr) tmp[c++] = cand[idx + 1];
+        __syncthreads();
+        c = 0;
+        for (int idx = base + tid; idx < cnt - 1 && c < 8; idx += nthr) cand[idx] = tmp[c++];
+        __syncthreads();
+      }
       cnt -= 1;
     }
     if (tid < 26) Hs[tid] = ft.Hc[26 * sel + tid];

@@ -87,56 +87,94 @@ int ekf_dist_attach(ekf_handle* h, const char id_bytes[128], int rank, int world
 // (ekf_update.cu: k_blk_S / k_blk_V with a P2PView) and no NCCL call remains inside a block of the partitioned
 // look-ahead update.  EKF_DIST_P2P=0 keeps the NCCL collectives.
 typedef int (*cuMemGetAddressRange_t)(unsigned long long*, size_t*, unsigned long long);
-struct P2PExport { cudaIpcMemHandle_t hnd; unsigned long long off; };   // 72 bytes
+struct P2PExport { cudaIpcMemHandle_t hnd; unsigned long long off; unsigned long long valid; };   // 80 bytes
 
+static void p2p_teardown(ekf_handle* h);
+
+// Every rank ALWAYS takes part in the two collectives below (the handle all-gather and the agreement all-reduce), whatever
+// failed locally: a rank that cannot export sends records marked invalid, a rank that cannot map a peer votes 0.  Peer
+// memory is switched on only when every rank voted 1; otherwise every rank closes what it opened and the update keeps the
+// NCCL exchange on ALL ranks (mixed paths would hang: one side spinning on flag words, the other inside ncclAllReduce).
 static int p2p_setup(ekf_handle* h) {
   const char* e = getenv("EKF_DIST_P2P");
-  if ((e && atoi(e) == 0) || h->world > 8 || h->world < 2) return EKF_OK;
+  if ((e && atoi(e) == 0) || h->world > 8 || h->world < 2) return EKF_OK;   // same environment / world on every rank
+  ncclComm_t comm = (ncclComm_t)h->nccl_comm;
+  int ok = 1;
   void* cu = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
   cuMemGetAddressRange_t range = cu ? (cuMemGetAddressRange_t)dlsym(cu, "cuMemGetAddressRange_v2") : nullptr;
-  if (!range) return EKF_OK;   // stay on NCCL
+  if (!range) ok = 0;
   const size_t spart_doubles = (size_t)h->world * EKF_UB * EKF_UB;
   const size_t xs_bytes = spart_doubles * sizeof(double) + 16 * sizeof(unsigned long long) + 64;
-  if (cudaMalloc((void**)&h->p2p.xs, xs_bytes) != cudaSuccess) return EKF_ERR_CUDA;
-  cudaMemset(h->p2p.xs, 0, xs_bytes);
-  cudaDeviceSynchronize();
+  if (ok && cudaMalloc((void**)&h->p2p.xs, xs_bytes) != cudaSuccess) { cudaGetLastError(); h->p2p.xs = nullptr; ok = 0; }
+  if (ok) { cudaMemset(h->p2p.xs, 0, xs_bytes); cudaDeviceSynchronize(); }
   void* local[4] = {h->Wbuf[0], h->Wbuf[1], h->Wbuf[2], h->p2p.xs};
   P2PExport mine[4];
-  for (int k = 0; k < 4; ++k) {
+  memset(mine, 0, sizeof mine);
+  for (int k = 0; k < 4 && ok; ++k) {
     unsigned long long base = 0; size_t sz = 0;
-    if (range(&base, &sz, (unsigned long long)local[k]) != 0) return EKF_OK;
-    if (cudaIpcGetMemHandle(&mine[k].hnd, (void*)base) != cudaSuccess) { cudaGetLastError(); return EKF_OK; }
+    if (range(&base, &sz, (unsigned long long)local[k]) != 0) { ok = 0; break; }
+    if (cudaIpcGetMemHandle(&mine[k].hnd, (void*)base) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
     mine[k].off = (unsigned long long)local[k] - base;
   }
+  for (int k = 0; k < 4; ++k) mine[k].valid = ok ? 1ull : 0ull;
   const size_t rec = sizeof(mine);
   char *dsend = nullptr, *drecv = nullptr;
-  if (cudaMalloc((void**)&dsend, rec) != cudaSuccess || cudaMalloc((void**)&drecv, rec * h->world) != cudaSuccess) return EKF_ERR_CUDA;
-  cudaMemcpy(dsend, mine, rec, cudaMemcpyHostToDevice);
-  const ncclResult_t r = g_nccl.AllGather(dsend, drecv, rec, /*ncclInt8*/ 0, (ncclComm_t)h->nccl_comm, h->stream);
-  if (r != 0) return nccl_fail(h, r, "ncclAllGather (IPC handles)");
-  cudaStreamSynchronize(h->stream);
+  int* dvote = nullptr;
+  int rc = EKF_OK;
   std::vector<P2PExport> all((size_t)4 * h->world);
-  cudaMemcpy(all.data(), drecv, rec * h->world, cudaMemcpyDeviceToHost);
-  cudaFree(dsend); cudaFree(drecv);
-  for (int q = 0; q < h->world; ++q) {
+  // the staging buffers are a few hundred bytes: if even they cannot be allocated the communicator is unusable anyway
+  if (cudaMalloc((void**)&dsend, rec) != cudaSuccess || cudaMalloc((void**)&drecv, rec * h->world) != cudaSuccess ||
+      cudaMalloc((void**)&dvote, sizeof(int)) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(dsend); cudaFree(drecv); cudaFree(dvote);
+    p2p_teardown(h);
+    h->err = "ekf_dist: no device memory for the peer-mapping handshake";
+    return EKF_ERR_CUDA;
+  }
+  cudaMemcpy(dsend, mine, rec, cudaMemcpyHostToDevice);
+  ncclResult_t r = g_nccl.AllGather(dsend, drecv, rec, /*ncclInt8*/ 0, comm, h->stream);
+  if (r != 0) { rc = nccl_fail(h, r, "ncclAllGather (IPC handles)"); ok = 0; }
+  cudaStreamSynchronize(h->stream);
+  if (rc == EKF_OK) cudaMemcpy(all.data(), drecv, rec * h->world, cudaMemcpyDeviceToHost);
+  for (int q = 0; q < h->world && ok; ++q)
+    for (int k = 0; k < 4; ++k)
+      if (!all[(size_t)q * 4 + k].valid) ok = 0;   // a peer could not export: nobody maps anything
+  for (int q = 0; q < h->world && ok; ++q) {
     void* ptr[4];
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 4 && ok; ++k) {
       if (q == h->rank) { ptr[k] = local[k]; continue; }
       void* base = nullptr;
       if (cudaIpcOpenMemHandle(&base, all[(size_t)q * 4 + k].hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
         cudaGetLastError();
-        fprintf(stderr, "ekf_dist: cudaIpcOpenMemHandle failed (rank %d <- %d): staying on NCCL\n", h->rank, q);
-        return EKF_OK;   // mappings opened so far are closed by detach
+        fprintf(stderr, "ekf_dist: cudaIpcOpenMemHandle failed (rank %d <- %d)\n", h->rank, q);
+        ok = 0;
+        break;
       }
       h->p2p.mapped[q][k] = base;
       ptr[k] = (char*)base + all[(size_t)q * 4 + k].off;
     }
+    if (!ok) break;
     for (int k = 0; k < 3; ++k) h->p2p.peerW[k][q] = (double*)ptr[k];
     h->p2p.peerSpart[q] = (double*)ptr[3];
     h->p2p.peerFlags[q] = (unsigned long long*)((double*)ptr[3] + spart_doubles);
   }
-  h->p2p.on = true;
-  return EKF_OK;
+  // agreement: MIN over the ranks' votes (skipped only when the communicator itself already failed above)
+  int agreed = 0;
+  if (rc == EKF_OK) {
+    cudaMemcpy(dvote, &ok, sizeof(int), cudaMemcpyHostToDevice);
+    r = g_nccl.AllReduce(dvote, dvote, 1, /*ncclInt32*/ 2, /*ncclMin*/ 3, comm, h->stream);
+    if (r != 0) rc = nccl_fail(h, r, "ncclAllReduce (peer-mapping agreement)");
+    cudaStreamSynchronize(h->stream);
+    if (rc == EKF_OK) cudaMemcpy(&agreed, dvote, sizeof(int), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(dsend); cudaFree(drecv); cudaFree(dvote);
+  if (agreed == 1) {
+    h->p2p.on = true;
+  } else {
+    if (rc == EKF_OK && h->rank == 0) fprintf(stderr, "ekf_dist: peer mapping not available on every rank: staying on NCCL\n");
+    p2p_teardown(h);   // closes every mapping opened so far, frees the slots, p2p.on = false
+  }
+  return rc;
 }
 
 static void p2p_teardown(ekf_handle* h) {
@@ -144,6 +182,10 @@ static void p2p_teardown(ekf_handle* h) {
     for (int k = 0; k < 4; ++k)
       if (h->p2p.mapped[q][k]) { cudaIpcCloseMemHandle(h->p2p.mapped[q][k]); h->p2p.mapped[q][k] = nullptr; }
   if (h->p2p.xs) { cudaFree(h->p2p.xs); h->p2p.xs = nullptr; }
+  for (int q = 0; q < 8; ++q) {
+    for (int k = 0; k < 3; ++k) h->p2p.peerW[k][q] = nullptr;
+    h->p2p.peerSpart[q] = nullptr; h->p2p.peerFlags[q] = nullptr;
+  }
   h->p2p.on = false;
 }
 

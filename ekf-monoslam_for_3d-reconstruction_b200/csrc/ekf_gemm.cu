@@ -162,12 +162,11 @@ template <int GT_M, int GT_STAGES, int MINB>
 static int launch_variant(cudaStream_t st, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M, int N,
                           int kconst, const int* kdev, int lower_only, unsigned stagger) {
   constexpr size_t smem = (size_t)GT_STAGES * (GT_M + GT_N) * GT_LD * sizeof(double);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_nt_sub<GT_M, GT_STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    attr_done = true;
-  }
+  static PerDeviceOnce once;   // per device, not per process
+  const cudaError_t ea = once.ensure([&] {
+    return cudaFuncSetAttribute(k_gemm_nt_sub<GT_M, GT_STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
+  if (ea != cudaSuccess) return (int)ea;
   dim3 grid((N + GT_N - 1) / GT_N, (M + GT_M - 1) / GT_M);
   k_gemm_nt_sub<GT_M, GT_STAGES, MINB><<<grid, GT_THREADS, smem, st>>>(C, ldc, A, lda, B, ldb, M, N, kconst, kdev, lower_only, stagger);
   return 0;

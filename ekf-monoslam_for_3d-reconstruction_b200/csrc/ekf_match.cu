@@ -474,12 +474,10 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_batch(const uint8_t* __
 
 void launch_match_filter(cudaStream_t st, FeatTab ft, int N, FrameView fr, const DevCfg& cfg, long long* launches) {
   if (N <= 0) return;
-  static size_t attr_smem = 0;
+  static PerDeviceOnce once;   // opt in to the largest supported window once per device
   const size_t smem = match_smem_bytes(cfg.window, cfg.search_clamp);
-  if (smem > attr_smem) {
-    cudaFuncSetAttribute(k_match_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_smem = smem;
-  }
+  if (once.ensure([] { return cudaFuncSetAttribute(k_match_filter, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)match_smem_bytes(MATCH_MAX_W, 20.0f)); }) != cudaSuccess) return;   // the error stays in cudaGetLastError() for the caller
   k_match_filter<<<N, MATCH_THREADS, smem, st>>>(ft, N, fr, cfg);
   *launches += 1;
 }
@@ -487,12 +485,10 @@ void launch_match_filter(cudaStream_t st, FeatTab ft, int N, FrameView fr, const
 void launch_match_filter_batch(cudaStream_t st, FeatTab base, int Ncap, const int* Nper, int B, FrameView fr, const DevCfg& cfg,
                                long long* launches) {
   if (B <= 0 || Ncap <= 0) return;
-  static size_t attr_smem = 0;
+  static PerDeviceOnce once;   // opt in to the largest supported window once per device
   const size_t smem = match_smem_bytes(cfg.window, cfg.search_clamp);
-  if (smem > attr_smem) {
-    cudaFuncSetAttribute(k_match_filter_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_smem = smem;
-  }
+  if (once.ensure([] { return cudaFuncSetAttribute(k_match_filter_batch, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)match_smem_bytes(MATCH_MAX_W, 20.0f)); }) != cudaSuccess) return;
   k_match_filter_batch<<<dim3(Ncap, B), MATCH_THREADS, smem, st>>>(base, Ncap, Nper, fr, cfg);
   *launches += 1;
 }
@@ -503,12 +499,10 @@ int launch_match_batch(cudaStream_t st, const uint8_t* frames, int n_frames, int
   if (w > MATCH_MAX_W || w < 1 || clampv > 20.0f || !(clampv >= 0.0f)) return -1;
   const int total = n_frames * fpf;
   if (total <= 0) return 0;
-  static size_t attr_smem = 0;
+  static PerDeviceOnce once;   // opt in to the largest supported window once per device
   const size_t smem = match_smem_bytes(w, clampv);
-  if (smem > attr_smem) {
-    cudaFuncSetAttribute(k_match_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_smem = smem;
-  }
+  if (once.ensure([] { return cudaFuncSetAttribute(k_match_batch, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)match_smem_bytes(MATCH_MAX_W, 20.0f)); }) != cudaSuccess) return -1;
   k_match_batch<<<total, MATCH_THREADS, smem, st>>>(frames, width, height, stride, templates, fpf, w, h, S, sigma_size, thr,
                                                    clampv, out_uv, out_score, total);
   return 0;

@@ -78,12 +78,17 @@ __global__ void __launch_bounds__(RANSAC_CL_THREADS) k_ransac_cluster(const doub
       }
       __syncthreads();
       const int p = s_p;
-      int tmp[8];
-      int c = 0;
-      for (int idx = p + tid; idx < cnt - 1 && c < 8; idx += nthr) tmp[c++] = cand[idx + 1];
-      __syncthreads();
-      c = 0;
-      for (int idx = p + tid; idx < cnt - 1 && c < 8; idx += nthr) cand[idx] = tmp[c++];
+      // vector::erase (V:991): shift the tail down by one, in chunks of 8 * nthr entries (low to high: a chunk only
+      // reads entries that later chunks write), so that any list length up to the feature capacity is handled
+      for (int base = p; base < cnt - 1; base += 8 * nthr) {
+        int tmp[8];
+        int c = 0;
+        for (int idx = base + tid; idx < cnt - 1 && c < 8; idx += nthr) tmp[c++] = cand[idx + 1];
+        __syncthreads();
+        c = 0;
+        for (int idx = base + tid; idx < cnt - 1 && c < 8; idx += nthr) cand[idx] = tmp[c++];
+        __syncthreads();
+      }
     }
     cnt -= 1;
     cluster.sync();                                   // the pick is visible

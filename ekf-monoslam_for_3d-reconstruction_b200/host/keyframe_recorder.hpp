@@ -1,5 +1,5 @@
 // host/keyframe_recorder.hpp — the caller-side data formats of the reference's ROS node (SURVEY.md §8(f)
-// item 4): the key-frame selector of ImageConverter::imageCb (monoslam_ransac.cpp:585-687, 707-722) and the
+// item 4): the key-frame selector of ImageConverter::imageCb (monoslam_ransac.cpp:585-687; :689-752 is commented out there) and the
 // writers of nodes_and_prjcts.txt / cams_cov.txt / cams_cov2.txt / points.txt (monoslam_ransac.cpp:232-236,
 // 262-275) that sparse_bundle_adjustment/src/nodes/sba_add.cpp:76-180 consumes.  Host-side logic over the
 // filter's accessors; Eigen's default stream format (precision 6, columns right-aligned to the widest
@@ -83,11 +83,11 @@ class KeyframeRecorder {
   }
 
   float MoveThresh = 18;                   // :195
-  int Num_of_points_thershold = 10;        // :186
+  int Num_of_points_thershold = 10;        // :186 (only read by the reference's commented-out rule)
   double min_cov_for_pose = 10000000;      // :187
   std::vector<int> key_frames;             // ids written so far (diagnostic, not in the reference)
 
-  // One camera frame after slam.update(): monoslam_ransac.cpp:560, 585, 609-687, 707-722.
+  // One camera frame after slam.update(): monoslam_ransac.cpp:560, 585, 609-687.
   template <class Filter>
   void onFrame(Filter& slam, int frameId, const uint8_t* img, int w, int h, int stride, int channels = 1) {
     const std::vector<double> stat14 = slam.getState();
@@ -117,10 +117,8 @@ class KeyframeRecorder {
       }
       min_cov_for_pose = 10000000;                                                             // :686
     }
-    if ((int)slam.Point4sba.size() / 3 >= Num_of_points_thershold) {                           // :707 (Point4sba has one row today)
-      const double some_var = slam.Covariance_Parameter();
-      if (some_var < min_cov_for_pose) candidate(slam, frameId, stat14, some_var, img, w, h, stride, channels, false);
-    }
+    // monoslam_ransac.cpp:689-752 (the Point4sba.rows() >= Num_of_points_thershold candidate rule and the
+    // take_image_every_x_frame rule) sits inside a comment block in the reference: dead code, not reproduced.
   }
 
   // ImageConverter::~ImageConverter (monoslam_ransac.cpp:262-275): closes the files and writes points.txt
@@ -136,7 +134,7 @@ class KeyframeRecorder {
  private:
   template <class Filter>
   void candidate(Filter& slam, int frameId, const std::vector<double>& stat14, double cov, const uint8_t* img, int w, int h, int stride,
-                 int channels, bool with_cov) {                                                // :613-625 / :709-721
+                 int channels, bool with_cov) {                                                // :613-625
     min_cov_for_pose = cov;
     Pose_id = frameId;
     for (int i = 0; i < 7; ++i) min_stat[i] = stat14[i];

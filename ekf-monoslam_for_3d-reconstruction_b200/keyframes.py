@@ -1,6 +1,6 @@
 """Caller-side data formats of the reference's ROS node, Python twin of
-host/keyframe_recorder.hpp: the key-frame selector of ImageConverter::imageCb (monoslam_ransac.cpp:585-687,
-707-722) and the writers of nodes_and_prjcts.txt / cams_cov.txt / cams_cov2.txt / points.txt
+host/keyframe_recorder.hpp: the key-frame selector of ImageConverter::imageCb (monoslam_ransac.cpp:585-687;
+:689-752 is commented out in the reference and is not reproduced) and the writers of nodes_and_prjcts.txt / cams_cov.txt / cams_cov2.txt / points.txt
 (monoslam_ransac.cpp:232-236, 262-275) consumed by sparse_bundle_adjustment/src/nodes/sba_add.cpp:76-180.
 
 Works with any object offering getState / getSigma / Covariance_Parameter / getPointsFeatures (the product's
@@ -56,7 +56,7 @@ class KeyframeRecorder:
         self.cov_cams = open(os.path.join(directory, "cams_cov.txt"), "w")
         self.cov_cams2 = open(os.path.join(directory, "cams_cov2.txt"), "w")
         self.MoveThresh = 18.0                 # :195
-        self.Num_of_points_thershold = 10      # :186
+        self.Num_of_points_thershold = 10      # :186 (only read by the reference's commented-out rule)
         self.min_cov_for_pose = 10000000.0     # :187
         self.last_vrot = np.zeros(3)
         self.last_image_pose = np.zeros(7)
@@ -94,7 +94,7 @@ class KeyframeRecorder:
         self.last_image_pose = np.array(stat14[:7], dtype=np.float64)
 
     def on_frame(self, slam, frame_id, image=None):
-        """One camera frame after slam.update() (monoslam_ransac.cpp:560, 585, 609-687, 707-722)."""
+        """One camera frame after slam.update() (monoslam_ransac.cpp:560, 585, 609-687)."""
         stat14 = np.asarray(slam.getState(), dtype=np.float64)
         dist = poses_diff(self.last_image_pose, stat14, self.last_vrot)
         if self.MoveThresh / 2 < dist < self.MoveThresh:
@@ -120,11 +120,8 @@ class KeyframeRecorder:
                 self._save(frame_id, image)
                 self._set_last(stat14)
             self.min_cov_for_pose = 10000000.0
-        p4 = np.array(getattr(slam, "Point4sba", np.zeros((1, 3)))).reshape(-1, 3)
-        if p4.shape[0] >= self.Num_of_points_thershold:
-            some_var = slam.Covariance_Parameter()
-            if some_var < self.min_cov_for_pose:
-                self._candidate(slam, frame_id, stat14, some_var, image, False)
+        # monoslam_ransac.cpp:689-752 (the Point4sba.rows() >= Num_of_points_thershold candidate rule and the
+        # take_image_every_x_frame rule) sits inside a /* ... */ block in the reference: dead code, not reproduced.
 
     def finish(self, slam):
         """~ImageConverter (monoslam_ransac.cpp:262-275): close the files, write points.txt."""

@@ -130,7 +130,9 @@ int ekf_predict(ekf_handle* h, const double dv[3], const double dw[3], int vcont
  * NULL (forces a device sync). */
 int ekf_match(ekf_handle* h, int* n_matched);
 /* The rest of VSlamFilter::update (vslamRansac.cpp:964-1341).  `picks` replaces rand()
- * (vslamRansac.cpp:970,989): hypothesis k draws picks[k % n_picks] % candidates (0 if n_picks==0). */
+ * (vslamRansac.cpp:970,989): hypothesis k draws picks[k % n_picks] % candidates (0 if n_picks==0).
+ * n_picks <= EKF_PICKS_CAP (the device copy is sized at ekf_create; more returns EKF_ERR_CAPACITY). */
+#define EKF_PICKS_CAP 65536
 int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks);
 /* VSlamFilter::update = ekf_match + ekf_update_after_match. */
 int ekf_update(ekf_handle* h, const uint32_t* picks, int n_picks);
