@@ -603,8 +603,8 @@ int update_kernels_init() {
 
 void launch_ransac(cudaStream_t st, const double* Sigma, int ld, int n, const double* mu, FeatTab ft, int N, DevCtl* ctl,
                    const DevCfg& cfg, const uint32_t* picks, int n_picks, double* mu_i, int* cand, long long* launches) {
-  static int use_cluster = -1;
-  if (use_cluster < 0) { const char* e = getenv("EKF_RANSAC_CLUSTER"); use_cluster = e ? atoi(e) : 1; }
+  const char* e = getenv("EKF_RANSAC_CLUSTER");   // read per launch (tests switch kernels inside one process)
+  const int use_cluster = e ? atoi(e) : 1;
   if (use_cluster && n >= RANSAC_CLUSTER_MIN_N) {
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(RANSAC_CL); lc.blockDim = dim3(RANSAC_CL_THREADS); lc.dynamicSmemBytes = 0; lc.stream = st;

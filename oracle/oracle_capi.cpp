@@ -39,6 +39,7 @@ struct Base {
   virtual ~Base() {}
   virtual void capture(const uint8_t*, int, int, int, double) = 0;
   virtual int add_feature(float, float) = 0;
+  virtual int add_features_structured(const float*, int) = 0;
   virtual void remove_feature(int) = 0;
   virtual void predict(const double*, const double*, int) = 0;
   virtual int match() = 0;
@@ -75,6 +76,7 @@ struct Impl : Base {
     f.captureNewFrame(g, w, h, stride, stamp, stamp >= 0);
   }
   int add_feature(float u, float v) override { return f.addFeature(u, v); }
+  int add_features_structured(const float* uv, int n) override { return f.addFeaturesStructured(uv, n); }
   void remove_feature(int i) override { f.removeFeature(i); }
   void predict(const double* dv, const double* dw, int vc) override {
     S a[3] = {S(dv[0]), S(dv[1]), S(dv[2])}, b[3] = {S(dw[0]), S(dw[1]), S(dw[2])};
@@ -229,6 +231,7 @@ void* orc_create(const ekf_config* cfg, int kind) {
 void orc_destroy(void* h) { delete static_cast<Base*>(h); }
 void orc_capture(void* h, const uint8_t* g, int w, int hh, int stride, double stamp) { static_cast<Base*>(h)->capture(g, w, hh, stride, stamp); }
 int orc_add_feature(void* h, float u, float v) { return static_cast<Base*>(h)->add_feature(u, v); }
+int orc_add_features_structured(void* h, const float* uv, int n) { return static_cast<Base*>(h)->add_features_structured(uv, n); }
 void orc_remove_feature(void* h, int i) { static_cast<Base*>(h)->remove_feature(i); }
 void orc_predict(void* h, const double* dv, const double* dw, int vc) { static_cast<Base*>(h)->predict(dv, dw, vc); }
 int orc_match(void* h) { return static_cast<Base*>(h)->match(); }

@@ -43,6 +43,7 @@ def lib(omp=False):
         "orc_destroy": (None, [vp]),
         "orc_capture": (None, [vp, vp, i32, i32, i32, f64]),
         "orc_add_feature": (i32, [vp, f32, f32]),
+        "orc_add_features_structured": (i32, [vp, vp, i32]),
         "orc_remove_feature": (None, [vp, i32]),
         "orc_predict": (None, [vp, vp, vp, i32]),
         "orc_match": (i32, [vp]),
@@ -103,6 +104,12 @@ class OracleFilter:
 
     def addFeature(self, u, v):
         return self.L.orc_add_feature(self.h, float(u), float(v))
+
+    def addFeatures(self, pixels):
+        """addFeature (vslamRansac.cpp:309-371) for every pixel of an (m, 2) array in order, through the sparsity-exploiting
+        form (bit-identical to the dense per-feature calls, O(n) instead of O(n^3) each).  Returns the number added."""
+        uv = np.ascontiguousarray(pixels, dtype=np.float32).reshape(-1, 2)
+        return self.L.orc_add_features_structured(self.h, _ptr(uv), int(uv.shape[0]))
 
     def removeFeature(self, i):
         self.L.orc_remove_feature(self.h, int(i))

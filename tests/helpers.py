@@ -54,3 +54,58 @@ def assert_state_close(g, o, tol=TOL, ctx=""):
     assert em <= tol, f"{ctx}: mu rel err {em:.3e}"
     assert es <= tol, f"{ctx}: Sigma rel err {es:.3e}"
     return em, es
+
+
+# ---- independent fp64 evaluation of the stacked EKF correction (numpy / LAPACK) -----------------------------
+def _feature_rows(feats, sel):
+    """idx (m, 13) state indices, Hc (m, 2, 13), innovation z - h (2m) for the selected features, in patch order.
+    XYZ features use 10 entries: the last three columns are zero and point at index 0."""
+    m = len(sel)
+    idx = np.zeros((m, 13), dtype=np.int64)
+    Hc = np.zeros((m, 2, 13))
+    nu = np.zeros(2 * m)
+    for j, i in enumerate(sel):
+        f = feats[i]
+        nd = 7 + (3 if f.coding else 6)
+        idx[j, :7] = np.arange(7)
+        idx[j, 7:nd] = f.position_in_state + np.arange(nd - 7)
+        H = np.array(list(f.H), dtype=np.float64).reshape(2, 13)
+        Hc[j, :, :nd] = H[:, :nd]
+        nu[2 * j] = f.z[0] - f.h[0]
+        nu[2 * j + 1] = f.z[1] - f.h[1]
+    return idx, Hc, nu
+
+
+def numpy_stacked_update(mu, S, feats, sel, sigma_pixel_2, chunk=256):
+    """mu + K nu and Sigma - Sigma H^T (H Sigma H^T + R)^-1 H Sigma (vslamRansac.cpp:1053-1060) followed by
+    normalizeQuaternion (vslamRansac.cpp:1625-1642), evaluated with numpy / LAPACK in fp64 from the sparse rows
+    of H (13 non-zeros per row).  Independent of both the oracle and the CUDA path: used where a dense oracle
+    frame is too slow (n = 12014)."""
+    import scipy.linalg as sla
+    n = mu.size
+    idx, Hc, nu = _feature_rows(feats, sel)
+    m = len(sel)
+    W = np.empty((n, 2 * m))
+    for a in range(0, m, chunk):                       # W = Sigma H^T, a block of features at a time
+        b = min(m, a + chunk)
+        G = S[:, idx[a:b].reshape(-1)].reshape(n, b - a, 13)
+        W[:, 2 * a:2 * b] = np.einsum("nfc,frc->nfr", G, Hc[a:b]).reshape(n, 2 * (b - a))
+    St = np.empty((2 * m, 2 * m))
+    for a in range(0, m, chunk):                       # St = H W + R
+        b = min(m, a + chunk)
+        G = W[idx[a:b].reshape(-1), :].reshape(b - a, 13, 2 * m)
+        St[2 * a:2 * b] = np.einsum("frc,fck->frk", Hc[a:b], G).reshape(2 * (b - a), 2 * m)
+    St[np.diag_indices(2 * m)] += sigma_pixel_2
+    St = 0.5 * (St + St.T)
+    L = sla.cholesky(St, lower=True)
+    V = sla.solve_triangular(L, W.T, lower=True)       # k x n
+    y = sla.solve_triangular(L, nu, lower=True)
+    mu1 = mu + V.T @ y
+    S1 = S - V.T @ V
+    q = mu1[3:7].copy()
+    nq = np.linalg.norm(q)
+    J = (nq * nq * np.eye(4) - np.outer(q, q)) / nq ** 3
+    mu1[3:7] = q / nq
+    S1[3:7, :] = J @ S1[3:7, :]
+    S1[:, 3:7] = S1[:, 3:7] @ J.T
+    return mu1, S1

@@ -251,3 +251,24 @@ def test_float_oracle_stays_near_double_oracle(pkg, orc):
         assert tuple(a.center) == tuple(b.center) and a.is_in_li == b.is_in_li
     e = relerr(of.get_full()[0], od.get_full()[0])
     assert 1e-12 < e < 1e-3
+
+
+def test_sparse_numpy_update_matches_oracle(pkg, orc):
+    """tests/helpers.numpy_stacked_update (the independent fp64 evaluation the N = 2000 GPU test is checked
+    against) reproduces the oracle's low-innovation update on a map small enough for the dense oracle."""
+    from helpers import numpy_stacked_update
+    sc = _scene(pkg, n_features=40, n_frames=3, seed=21)
+    o = make_oracle(pkg, orc, sc, omp=True)
+    seed_features(o, sc)
+    o.captureNewFrame(sc.frame(1), sc.stamps[1]); o.predict()
+    assert o.match() == 40
+    mu, S = o.get_full()
+    feats = [o.feature(i) for i in range(o.numOfFeatures())]
+    o.update_after_match(sc.picks(1, 40))
+    st = o.stats()
+    assert st.n_hi == 0 and st.n_li > 30
+    sel = [i for i in range(o.numOfFeatures()) if o.feature(i).is_in_li]
+    mu1, S1 = numpy_stacked_update(mu, S, feats, sel, 4.0, chunk=16)
+    mo, So = o.get_full()
+    assert relerr(mo, mu1) < 1e-12 and relerr(So, S1) < 1e-12
+    assert relerr(So - S, S1 - S) < 1e-10
