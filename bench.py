@@ -59,6 +59,8 @@ BATCH_FILTERS = 4096
 METRIC_BATCH = "batched EKF filter-steps/s (predict+match+update), 4096 independent filters x N=30 features per GPU"
 UNIT_BATCH = "filter-steps/s"
 PARITY_TOL = 1e-9
+BENCH_DEPTH_RANGE = (1.5, 3.0)
+BENCH_RHO_0 = 0.5
 
 
 def metric_for(workload):
@@ -72,7 +74,7 @@ def workload_string(workload, match_every=1):
     return (f"{workload}: single filter, {nfeat} inverse-depth features (n={14 + 6 * nfeat}), {width}x{height} u8 frames, "
             f"predict+match+update per frame, "
             + ("all features matched" if match_every <= 1 else f"every {match_every}th feature visible")
-            + ", map held at N features for the whole run (quality_ratio = 1e9: no deletions)")
+            + ", map held at N features for the whole run (depths 1.5-3 m, rho_0 = 0.5, quality_ratio = 1e9: no deletions)")
 
 
 def log(*a):
@@ -131,8 +133,11 @@ class ClockSampler:
 def make_scene(pkg, workload, n_frames, seed=1235, visible_every=1):
     nfeat, W, H = WORKLOADS[workload]
     # slow motion so that all seeded features stay inside the image for the whole run (fixed N)
+    # depths of 1.5 - 3 m around the prior rho_0 = 0.5 (bench_config): with the reference's default prior (rho_0 = 0.1 at a
+    # variance of 0.25) the first updates drive a few inverse depths through zero and the reference deletes those features
+    # (vslamRansac.cpp:1296-1299), which would shrink the state below the size the metric names
     return pkg.synth.Scene(n_features=nfeat, width=W, height=H, n_frames=n_frames, seed=seed, speed=0.1, omega=0.02,
-                           accel_sigma=0.002, border=44, visible_every=visible_every)
+                           accel_sigma=0.002, border=44, visible_every=visible_every, depth_range=BENCH_DEPTH_RANGE)
 
 
 def bench_config(pkg, scene):
@@ -141,6 +146,7 @@ def bench_config(pkg, scene):
     size the metric names)."""
     over = scene.config_overrides()
     over["quality_ratio"] = 1.0e9
+    over["rho_0"] = BENCH_RHO_0
     return pkg.default_config(**over)
 
 
@@ -791,7 +797,7 @@ def _oracle_seeded(pkg, orc, workload, n_frames, omp=True, kind=0, nfeat=None):
     if nfeat is not None and nfeat != scene.n_features:
         W, H = WORKLOADS[workload][1:]
         scene = pkg.synth.Scene(n_features=nfeat, width=W, height=H, n_frames=n_frames, seed=1235, speed=0.1, omega=0.02,
-                                accel_sigma=0.002, border=44)
+                                accel_sigma=0.002, border=44, depth_range=BENCH_DEPTH_RANGE)
     cfg = bench_config(pkg, scene)
     o = orc.OracleFilter(cfg, kind=kind, omp=omp)
     added = seed_filter(o, scene)

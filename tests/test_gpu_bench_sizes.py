@@ -28,7 +28,7 @@ def test_cfg2_n500_default_path(gpu_pkg, orc, symmetric, monkeypatch):
         monkeypatch.delenv(v, raising=False)
     nfeat = bench.WORKLOADS["cfg2_n500"][0]
     sc = bench.make_scene(gpu_pkg, "cfg2_n500", 3)
-    cfg = gpu_pkg.default_config(**sc.config_overrides())
+    cfg = bench.bench_config(gpu_pkg, sc)
     g = gpu_pkg.VSlamFilter(cfg, feature_capacity=nfeat + 4)
     g.set_symmetric_downdate(symmetric)
     assert _seed(g, sc) == nfeat
@@ -57,7 +57,7 @@ def test_cfg2_n500_default_path(gpu_pkg, orc, symmetric, monkeypatch):
 def _numpy_check(gpu_pkg, workload, n_frames_checked=1, symmetric=True):
     nfeat = bench.WORKLOADS[workload][0]
     sc = bench.make_scene(gpu_pkg, workload, 1 + n_frames_checked)
-    cfg = gpu_pkg.default_config(**sc.config_overrides())
+    cfg = bench.bench_config(gpu_pkg, sc)
     g = gpu_pkg.VSlamFilter(cfg, feature_capacity=nfeat + 4)
     g.set_symmetric_downdate(symmetric)
     assert _seed(g, sc) == nfeat
