@@ -288,6 +288,8 @@ static int capture_common(ekf_handle* h, const uint8_t* img, int width, int heig
     launch_capture_resize_gray(h->stream, src, width, height, sstride, channels, h->frame, dw, dh, dstride, &h->launches);
     EKF_CUDA_CHECK(cudaGetLastError());
   }
+  if (h->fv.px != h->frame || h->fv.w != dw || h->fv.h != dh || h->fv.stride != dstride)
+    match_make_tensor_map(&h->frame_map, h->frame, dw, dh, dstride, 1, h->cfg.window_size, (int)h->cfg.search_clamp);
   h->fv = FrameView{h->frame, dw, dh, dstride};
   h->have_frame = true;
   return EKF_OK;
@@ -358,7 +360,7 @@ int ekf_match(ekf_handle* h, int* n_matched) {
   EKF_CUDA_CHECK(cudaSetDevice(h->device));
   {
     ProfScope ps(h, 1);
-    launch_match_filter(h->stream, h->ft, h->N, h->fv, h->dcfg, &h->launches);
+    launch_match_filter(h->stream, h->ft, h->N, h->fv, h->dcfg, &h->frame_map, &h->launches);
   }
   EKF_CUDA_CHECK(cudaGetLastError());
   h->cache_ok = false;

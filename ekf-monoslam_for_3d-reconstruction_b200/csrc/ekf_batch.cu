@@ -620,6 +620,7 @@ struct ekf_batch {
   uint8_t* frame = nullptr;
   size_t frame_cap = 0;
   FrameView fv{nullptr, 0, 0, 0};
+  EkfTensorMap frame_map{};
   uint32_t* picks_dev = nullptr;
   int picks_cap = 0;
   double *out_mu14 = nullptr, *out_S14 = nullptr;
@@ -814,6 +815,8 @@ static int bcapture(ekf_batch* b, const uint8_t* gray, int width, int height, in
   }
   BCHECK(cudaMemcpy2DAsync(b->frame, dstride, gray, stride, width, height, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                            b->stream));
+  if (b->fv.px != b->frame || b->fv.w != width || b->fv.h != height || b->fv.stride != dstride)
+    match_make_tensor_map(&b->frame_map, b->frame, width, height, dstride, 1, b->cfg.window_size, (int)b->cfg.search_clamp);
   b->fv = FrameView{b->frame, width, height, dstride};
   b->have_frame = true;
   return EKF_OK;
@@ -842,7 +845,7 @@ int ekf_batch_step(ekf_batch* b, const double dv[3], const double dw[3], int vco
                                                    make_double3(w[0], w[1], w[2]), vcontrol);
   b->launches += 1;
   BCHECK(cudaEventRecord(b->ev[1], st));
-  launch_match_filter_batch(st, b->bv.ft, b->Ncap, b->bv.N, b->B, b->fv, b->dcfg, &b->launches);
+  launch_match_filter_batch(st, b->bv.ft, b->Ncap, b->bv.N, b->B, b->fv, b->dcfg, &b->frame_map, &b->launches);
   BCHECK(cudaEventRecord(b->ev[2], st));
   k_batch_update<<<b->B, BUPD_THREADS, kUpdSmemBytes, st>>>(b->bv, b->dcfg, b->picks_dev, n_picks, b->out_mu14, b->out_S14,
                                                             b->out_stats, b->cfg.min_features, b->cfg.max_features);

@@ -31,6 +31,7 @@ struct ekf_handle {
   uint8_t* raw = nullptr;   // full-resolution / colour staging for captureNewFrame's resize + BGR2GRAY
   size_t raw_cap = 0;
   FrameView fv{nullptr, 0, 0, 0};
+  EkfTensorMap frame_map{};   // TMA tensor map of `frame` for the matcher's window staging (re-encoded when the frame view changes)
   uint32_t* picks_dev = nullptr;
   int picks_cap = 0;
   double* out_dev = nullptr;   // packed step record (device)

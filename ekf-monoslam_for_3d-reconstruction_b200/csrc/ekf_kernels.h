@@ -22,9 +22,17 @@ void launch_xyz_apply(cudaStream_t st, const double* Ssrc, double* Sdst, int ld,
                       const int* rmap, const double* J, const double* y, FeatTab ft, int N, const int* pos, const int* coding,
                       long long* launches);
 // ekf_match.cu
-void launch_match_filter(cudaStream_t st, FeatTab ft, int N, FrameView fr, const DevCfg& cfg, long long* launches);
+// A TMA tensor map (CUtensorMap, 128 bytes) of a stack of u8 frames for the matcher's window staging, kept opaque here so that
+// only ekf_match.cu needs the driver header.  ok == 0: the frames cannot be described (base or row stride not 16-byte aligned,
+// driver entry point unavailable): the kernels then stage the window with ordinary loads.
+struct alignas(64) EkfTensorMap {
+  unsigned long long opaque[16];
+  int ok;
+};
+void match_make_tensor_map(EkfTensorMap* out, const uint8_t* frames, int width, int height, int stride, int n_frames, int w, int clamp);
+void launch_match_filter(cudaStream_t st, FeatTab ft, int N, FrameView fr, const DevCfg& cfg, const EkfTensorMap* tmap, long long* launches);
 void launch_match_filter_batch(cudaStream_t st, FeatTab base, int Ncap, const int* Nper, int B, FrameView fr, const DevCfg& cfg,
-                               long long* launches);
+                               const EkfTensorMap* tmap, long long* launches);
 int launch_match_batch(cudaStream_t st, const uint8_t* frames, int n_frames, int width, int height, int stride,
                        const uint8_t* templates, int fpf, int w, const double* h, const double* S, float sigma_size,
                        float thr, float clampv, int32_t* out_uv, float* out_score);

@@ -10,7 +10,13 @@
 // by < 1e-13 (121 roundings of 1e-16 relative).  Rounding to float is monotonic, so only candidates
 // whose ncc* lies within two float ulps (+ that error bound) of the largest ncc* can be, or tie
 // with, the reference's float maximum.  Hence:
-//   fast pass : the u8 search window (<= 72 x 72) and the template packed 4 bytes per word live in shared
+//   staging   : the u8 search window (<= 72 x 72) is pulled into shared memory by ONE TMA tile load
+//               (cp.async.bulk.tensor over a tensor map of the frame stack, completion on an mbarrier, out-of-frame
+//               bytes zero-filled by the copy engine) while the CTA packs the template; the box starts at the 16-byte
+//               boundary left of the window (a requirement of the copy engine) and is re-aligned shared -> shared.
+//               Frames whose base / row stride are not 16-byte aligned cannot be described by a tensor map and are
+//               staged with ordinary loads.
+//   fast pass : the window and the template packed 4 bytes per word live in shared
 //               memory; each thread scores 4 horizontally adjacent candidates at a time with DP4A
 //               (u8 x u8 dot products) on funnel-shifted window words -> Stp, P, Spp; ncc* in double.
 //   exact pass: the handful of candidates inside the guard band (normally one) are re-scored with the
@@ -18,6 +24,10 @@
 //               and compared as floats with the reference's first-wins tie-break.
 // The result (match coordinates, accept / reject, float score) is bit-identical to the reference's;
 // if the guard band ever overflows its list (pathological ties) every candidate takes the exact pass.
+#include <cstdlib>
+
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
+
 #include "ekf_kernels.h"
 #include "ekf_math.cuh"
 
@@ -31,6 +41,8 @@ struct MatchJob {
   const uint8_t* tmpl;   // w*w template
   double hu, hv;         // Patch::h
   double S[4];           // 2x2 block of St
+  const CUtensorMap* tmap;  // tensor map of the frame stack (null: stage with ordinary loads)
+  int frame_index;       // z coordinate in that stack
 };
 
 struct MatchResult {
@@ -44,12 +56,14 @@ struct MatchSmem {
   int wsb;       // window row stride in bytes (multiple of 4, >= side + 8)
   int tw;        // template words per row
   int ncmax;     // max candidates = (2 cl + 1)^2
-  size_t off_tpk, off_tb, off_win, off_h1, off_h2, off_b1, off_b2, off_score, off_list, off_red, off_da, total;
+  int rawb;      // row stride of the raw TMA box: wsb + 16 (the box starts at the 16-byte boundary left of the window)
+  size_t off_tpk, off_tb, off_win, off_raw, off_h1, off_h2, off_b1, off_b2, off_score, off_list, off_red, off_da, off_bar, total;
 };
 __host__ __device__ inline MatchSmem match_smem_plan(int w, int cl) {
   MatchSmem p;
   p.side = 2 * cl + w;
   p.wsb = (p.side + 8 + 3) & ~3;
+  p.rawb = ((p.wsb + 15) & ~15) + 16;
   p.tw = (w + 3) >> 2;
   p.ncmax = (2 * cl + 1) * (2 * cl + 1);
   size_t o = 0;
@@ -57,6 +71,8 @@ __host__ __device__ inline MatchSmem match_smem_plan(int w, int cl) {
   p.off_tb = o; o += (size_t)((w * w + 15) & ~15);                            // template bytes
   o = (o + 15) & ~(size_t)15;
   p.off_win = o; o += (size_t)(p.side + 1) * p.wsb;                           // u8 window (+1 spare row)
+  o = (o + 127) & ~(size_t)127;                                               // TMA destination: 128-byte aligned
+  p.off_raw = o; o += (size_t)p.side * p.rawb;                                // raw TMA box: side rows x rawb bytes
   o = (o + 15) & ~(size_t)15;
   const size_t nh = (size_t)p.side * (2 * cl + 1);                            // horizontal sums: window rows x candidate columns
   p.off_h1 = o; o += ((nh * 2 + 15) & ~(size_t)15);                           // u16: sum of w pixels
@@ -70,8 +86,33 @@ __host__ __device__ inline MatchSmem match_smem_plan(int w, int cl) {
   p.off_red = o; o += 16 * sizeof(double) + 16 * sizeof(float) + 16 * sizeof(int);
   o = (o + 7) & ~(size_t)7;
   p.off_da = o; o += (size_t)w * w * sizeof(double);                          // (double)(float)t - m1 per template pixel (exact pass)
+  p.off_bar = o; o += 8;                                                      // mbarrier of the TMA load
   p.total = o;
   return p;
+}
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier, raw PTX for sm_100a -------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  }
 }
 
 // The reference's computeCorrelation for one candidate (window ROI at byte offset `roi`) in its exact operation order.  The
@@ -176,8 +217,19 @@ __device__ MatchResult match_one(const MatchJob& jb, int w, float sigma_size, fl
   int* red_k = reinterpret_cast<int*>(red_s + 16);                     // [0..7] keys, [8] T, [9] TT, [10] list count
 
   // --- template: packed words (zero padded), integer sums T = sum t, TT = sum t^2 ---
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + pl.off_bar);
+  const bool use_tma = jb.tmap != nullptr;
   if (tid < 16) red_k[tid] = 0;
+  if (use_tma && tid == 0) mbar_init(bar, 1);
   __syncthreads();
+  uint8_t* raw = smem_raw + pl.off_raw;
+  if (use_tma && any && tid == 0) {
+    // ONE tile load per feature: the box is `side` rows of rawb bytes whose left edge is the 16-byte boundary at or left of
+    // the window (the copy engine needs the innermost coordinate 16-byte aligned: tools/tma_probe2.cu); bytes outside the
+    // frame arrive as zeros.  The box lands in `raw` while the CTA packs the template below.
+    mbar_expect_tx(bar, (unsigned)(pl.rawb * pl.side));
+    tma_load_3d(raw, jb.tmap, (ilo - half) & ~15, jlo - half, jb.frame_index, bar);
+  }
   {
     int pt = 0, ptt = 0;
     for (int e = tid; e < w * tw; e += MATCH_THREADS) {
@@ -195,8 +247,8 @@ __device__ MatchResult match_one(const MatchJob& jb, int w, float sigma_size, fl
     for (int o = 16; o > 0; o >>= 1) { pt += __shfl_xor_sync(0xffffffffu, pt, o); ptt += __shfl_xor_sync(0xffffffffu, ptt, o); }
     if ((tid & 31) == 0 && (pt | ptt)) { atomicAdd(&red_k[8], pt); atomicAdd(&red_k[9], ptt); }
   }
-  // --- stage the window as bytes; columns past ww and the spare row are zero ---
-  if (any) {
+  // --- ordinary-load staging (frames a tensor map cannot describe): bytes; columns past ww and the spare row are zero ---
+  if (any && !use_tma) {
     const int x0 = ilo - half, y0 = jlo - half;
     if ((((size_t)jb.frame | (size_t)jb.fstride) & 3) == 0) {
       // aligned 4-byte loads, funnel-shifted to the window's own alignment (a quarter of the load instructions of the
@@ -222,6 +274,25 @@ __device__ MatchResult match_one(const MatchJob& jb, int w, float sigma_size, fl
       for (int yy = tid / 32; yy <= wh; yy += MATCH_THREADS / 32) {
         const uint8_t* src = jb.frame + (size_t)(y0 + yy) * jb.fstride + x0;
         for (int xx = tid & 31; xx < wsb; xx += 32) win[yy * wsb + xx] = (yy < wh && xx < ww) ? src[xx] : (uint8_t)0;
+      }
+    }
+  }
+  if (use_tma && any) {
+    mbar_wait(bar, 0);   // every consumer thread observes the completion of the tile load
+    // raw box -> window at its own alignment (funnel shift by the 0..15 bytes between the box edge and the window), with the
+    // same zero padding as the ordinary-load path: columns past ww and rows from wh on are zero
+    const int sh = (ilo - half) & 15, shw = sh >> 2, shb = 8 * (sh & 3), nwords = wsb >> 2;
+    for (int yy = tid / 32; yy <= wh; yy += MATCH_THREADS / 32) {
+      const unsigned* srcw = reinterpret_cast<const unsigned*>(raw + (size_t)min(yy, pl.side - 1) * pl.rawb) + shw;
+      unsigned* dstw = reinterpret_cast<unsigned*>(win + yy * wsb);
+      for (int k = tid & 31; k < nwords; k += 32) {
+        unsigned v = 0;
+        if (yy < wh && 4 * k < ww) {
+          v = __funnelshift_r(srcw[k], srcw[k + 1], shb);
+          const int rem = ww - 4 * k;
+          if (rem < 4) v &= (1u << (8 * rem)) - 1u;
+        }
+        dstw[k] = v;
       }
     }
   }
@@ -403,10 +474,47 @@ __device__ MatchResult match_one(const MatchJob& jb, int w, float sigma_size, fl
 
 static size_t match_smem_bytes(int w, float clampv) { return match_smem_plan(w, (int)clampv).total; }
 
+// Tensor map of a stack of u8 frames (x = column, y = row, z = frame) whose box is the matcher's staging window for template
+// side w and search clamp `clamp`.  The driver's encoder is looked up at run time (no link-time dependency on libcuda).
+typedef CUresult (*EkfEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+void match_make_tensor_map(EkfTensorMap* out, const uint8_t* frames, int width, int height, int stride, int n_frames, int w, int clamp) {
+  static_assert(sizeof(CUtensorMap) <= sizeof(out->opaque), "EkfTensorMap too small");
+  out->ok = 0;
+  static EkfEncodeTiled enc = nullptr;
+  static bool looked = false;
+  if (!looked) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      enc = (EkfEncodeTiled)fn;
+    else
+      cudaGetLastError();
+    looked = true;
+  }
+  const char* off = getenv("EKF_MATCH_TMA");
+  if (!enc || (off && atoi(off) == 0)) return;
+  if (!frames || (((size_t)frames | (size_t)stride) & 15) != 0 || width < 1 || height < 1 || n_frames < 1) return;
+  const MatchSmem pl = match_smem_plan(w, clamp);
+  if (pl.rawb > 256 || pl.side > 256) return;
+  const cuuint64_t gdim[3] = {(cuuint64_t)width, (cuuint64_t)height, (cuuint64_t)n_frames};
+  const cuuint64_t gstr[2] = {(cuuint64_t)stride, (cuuint64_t)stride * (cuuint64_t)height};
+  const cuuint32_t box[3] = {(cuuint32_t)pl.rawb, (cuuint32_t)pl.side, 1u};
+  const cuuint32_t est[3] = {1u, 1u, 1u};
+  const CUresult r = enc(reinterpret_cast<CUtensorMap*>(out->opaque), CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)frames, gdim, gstr, box, est,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  out->ok = (r == CUDA_SUCCESS) ? 1 : 0;
+}
+static const CUtensorMap& as_cu(const EkfTensorMap& m) { return *reinterpret_cast<const CUtensorMap*>(m.opaque); }
+
 // Filter-attached matcher: the loop V:870-880 with one CTA per feature.
-__device__ __forceinline__ void match_filter_feature(FeatTab ft, int f, FrameView fr, const DevCfg& cfg, unsigned char* smem_raw) {
+__device__ __forceinline__ void match_filter_feature(FeatTab ft, int f, FrameView fr, const DevCfg& cfg, unsigned char* smem_raw,
+                                                     const CUtensorMap* tmap) {
   const int w = cfg.window, w2 = w * w;
   MatchJob jb;
+  jb.tmap = tmap; jb.frame_index = 0;
   jb.frame = fr.px; jb.fw = fr.w; jb.fh = fr.h; jb.fstride = fr.stride;
   jb.tmpl = ft.mpatch + (size_t)f * cfg.tstride;
   jb.hu = ft.h[2 * f]; jb.hv = ft.h[2 * f + 1];
@@ -432,20 +540,22 @@ __device__ __forceinline__ void match_filter_feature(FeatTab ft, int f, FrameVie
     }
   }
 }
-__global__ void __launch_bounds__(MATCH_THREADS) k_match_filter(FeatTab ft, int N, FrameView fr, DevCfg cfg) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(MATCH_THREADS) k_match_filter(FeatTab ft, int N, FrameView fr, DevCfg cfg,
+                                                                const __grid_constant__ CUtensorMap tmap, int use_tma) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int f = blockIdx.x;
   if (f >= N || !ft.innov[f]) return;
-  match_filter_feature(ft, f, fr, cfg, smem_raw);
+  match_filter_feature(ft, f, fr, cfg, smem_raw, use_tma ? &tmap : nullptr);
 }
 // Batched filters (BASELINE config 3): grid = (feature capacity, filters); the frame is shared.
 __global__ void __launch_bounds__(MATCH_THREADS) k_match_filter_batch(FeatTab base, int Ncap, const int* __restrict__ Nper,
-                                                                      FrameView fr, DevCfg cfg) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+                                                                      FrameView fr, DevCfg cfg,
+                                                                      const __grid_constant__ CUtensorMap tmap, int use_tma) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int f = blockIdx.x, b = blockIdx.y;
   const FeatTab ft = feattab_slice(base, b, Ncap, cfg.tstride);
   if (f >= Nper[b] || !ft.innov[f]) return;
-  match_filter_feature(ft, f, fr, cfg, smem_raw);
+  match_filter_feature(ft, f, fr, cfg, smem_raw, use_tma ? &tmap : nullptr);
 }
 
 // Stateless batch (BASELINE config 5): grid = frames x features.
@@ -453,11 +563,13 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_batch(const uint8_t* __
                                                                int stride, const uint8_t* __restrict__ templates, int fpf,
                                                                int w, const double* __restrict__ hh, const double* __restrict__ Sm,
                                                                float sigma_size, float thr, float clampv,
-                                                               int32_t* __restrict__ out_uv, float* __restrict__ out_score, int total) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+                                                               int32_t* __restrict__ out_uv, float* __restrict__ out_score, int total,
+                                                               const __grid_constant__ CUtensorMap tmap, int use_tma) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int idx = blockIdx.x;
   if (idx >= total) return;
   MatchJob jb;
+  jb.tmap = use_tma ? &tmap : nullptr; jb.frame_index = idx / fpf;
   jb.frame = frames + (size_t)(idx / fpf) * height * stride;
   jb.fw = width; jb.fh = height; jb.fstride = stride;
   jb.tmpl = templates + (size_t)idx * w * w;
@@ -472,24 +584,28 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_batch(const uint8_t* __
   }
 }
 
-void launch_match_filter(cudaStream_t st, FeatTab ft, int N, FrameView fr, const DevCfg& cfg, long long* launches) {
+void launch_match_filter(cudaStream_t st, FeatTab ft, int N, FrameView fr, const DevCfg& cfg, const EkfTensorMap* tmap, long long* launches) {
   if (N <= 0) return;
   static PerDeviceOnce once;   // opt in to the largest supported window once per device
   const size_t smem = match_smem_bytes(cfg.window, cfg.search_clamp);
   if (once.ensure([] { return cudaFuncSetAttribute(k_match_filter, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    (int)match_smem_bytes(MATCH_MAX_W, 20.0f)); }) != cudaSuccess) return;   // the error stays in cudaGetLastError() for the caller
-  k_match_filter<<<N, MATCH_THREADS, smem, st>>>(ft, N, fr, cfg);
+  static const EkfTensorMap none{};
+  const EkfTensorMap& tm = (tmap && tmap->ok) ? *tmap : none;
+  k_match_filter<<<N, MATCH_THREADS, smem, st>>>(ft, N, fr, cfg, as_cu(tm), tm.ok);
   *launches += 1;
 }
 
 void launch_match_filter_batch(cudaStream_t st, FeatTab base, int Ncap, const int* Nper, int B, FrameView fr, const DevCfg& cfg,
-                               long long* launches) {
+                               const EkfTensorMap* tmap, long long* launches) {
   if (B <= 0 || Ncap <= 0) return;
   static PerDeviceOnce once;   // opt in to the largest supported window once per device
   const size_t smem = match_smem_bytes(cfg.window, cfg.search_clamp);
   if (once.ensure([] { return cudaFuncSetAttribute(k_match_filter_batch, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    (int)match_smem_bytes(MATCH_MAX_W, 20.0f)); }) != cudaSuccess) return;
-  k_match_filter_batch<<<dim3(Ncap, B), MATCH_THREADS, smem, st>>>(base, Ncap, Nper, fr, cfg);
+  static const EkfTensorMap none{};
+  const EkfTensorMap& tm = (tmap && tmap->ok) ? *tmap : none;
+  k_match_filter_batch<<<dim3(Ncap, B), MATCH_THREADS, smem, st>>>(base, Ncap, Nper, fr, cfg, as_cu(tm), tm.ok);
   *launches += 1;
 }
 
@@ -503,7 +619,9 @@ int launch_match_batch(cudaStream_t st, const uint8_t* frames, int n_frames, int
   const size_t smem = match_smem_bytes(w, clampv);
   if (once.ensure([] { return cudaFuncSetAttribute(k_match_batch, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    (int)match_smem_bytes(MATCH_MAX_W, 20.0f)); }) != cudaSuccess) return -1;
+  EkfTensorMap tm;
+  match_make_tensor_map(&tm, frames, width, height, stride, n_frames, w, (int)clampv);
   k_match_batch<<<total, MATCH_THREADS, smem, st>>>(frames, width, height, stride, templates, fpf, w, h, S, sigma_size, thr,
-                                                   clampv, out_uv, out_score, total);
+                                                   clampv, out_uv, out_score, total, as_cu(tm), tm.ok);
   return 0;
 }

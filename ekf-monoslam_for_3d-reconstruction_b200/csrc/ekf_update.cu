@@ -447,9 +447,20 @@ void launch_plane_S(cudaStream_t st, const double* W, double* Sb, long long* lau
 }
 
 #include "ekf_factor.cuh"
+#include "ekf_chol128.cuh"
+// K4b: Cholesky gain of one 128-row block.  Default: cta_chol128 (ekf_chol128.cuh: the matrix lives in registers in the DMMA
+// accumulator layout, 8-column steps, two barriers per step).  k_blk_factor_smem is the round-1 kernel (matrix in shared
+// memory, bound by shared-memory bandwidth), kept selectable with EKF_CHOL_SMEM=1 for A/B timing and as a cross-check.
+static_assert(CH_THREADS == FACT_THREADS, "both factor kernels are launched with FACT_THREADS threads");
 __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __restrict__ Sb, const double* __restrict__ nu,
                                                              double* __restrict__ Lout, double* __restrict__ Dblk,
                                                              double* __restrict__ yout, DevCtl* ctl) {
+  extern __shared__ __align__(16) double fsm[];
+  cta_chol128(fsm, Sb, EKF_UB, nu, Lout, EKF_UB, Dblk, 32, yout, &ctl->chol_fail);
+}
+__global__ void __launch_bounds__(FACT_THREADS) k_blk_factor_smem(const double* __restrict__ Sb, const double* __restrict__ nu,
+                                                                  double* __restrict__ Lout, double* __restrict__ Dblk,
+                                                                  double* __restrict__ yout, DevCtl* ctl) {
   extern __shared__ __align__(16) double fsm[];
   cta_chol_panel<EKF_UB>(fsm, Sb, EKF_UB, nu, Lout, EKF_UB, Dblk, 32, yout, &ctl->chol_fail);
 }
@@ -468,8 +479,8 @@ __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor_p2p(const double* _
     for (int q = 0; q < world; ++q) s += __ldcg(spart + (size_t)q * EKF_UB * EKF_UB + e);
     Ssum[e] = s;
   }
-  __syncthreads();
-  cta_chol_panel<EKF_UB>(fsm, Ssum, EKF_UB, nu, Lout, EKF_UB, Dblk, 32, yout, &ctl->chol_fail);
+  __syncthreads();   // Ssum was written by this CTA: visible to all of its threads after the barrier
+  cta_chol128(fsm, Ssum, EKF_UB, nu, Lout, EKF_UB, Dblk, 32, yout, &ctl->chol_fail);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -589,11 +600,17 @@ __global__ void __launch_bounds__(256) k_bookkeeping(const double* __restrict__ 
 }
 
 // ---- launch wrappers ---------------------------------------------------------------------------
-static const size_t kFactSmem = (size_t)cta_chol_panel_smem_doubles<EKF_UB>() * sizeof(double);
+static const size_t kFactSmemOld = (size_t)cta_chol_panel_smem_doubles<EKF_UB>() * sizeof(double);
+static const size_t kFactSmem = sizeof(Chol128Smem);
+static int g_chol_smem = 0;   // EKF_CHOL_SMEM=1: the round-1 shared-memory factor kernel
 static const size_t kVSmem = (size_t)(EKF_UB * VT_LD + (EKF_UB / 32) * 32 * VT_LDD + VT_ROWS * VT_LD + EKF_UB) * sizeof(double);
 
 int update_kernels_init() {
+  const char* env = getenv("EKF_CHOL_SMEM");
+  g_chol_smem = env ? atoi(env) : 0;
   cudaError_t e = cudaFuncSetAttribute(k_blk_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFactSmem);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_blk_factor_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFactSmemOld);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_blk_factor_p2p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFactSmem);
   if (e != cudaSuccess) return (int)e;
@@ -636,8 +653,8 @@ void launch_blk_gather(cudaStream_t st, const double* Sigma, int ld, int row0, i
 void launch_blk_factor(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const double* nu, const DevCfg& cfg,
                        double* Sb, double* Lb, double* Dblk, double* yb, DevCtl* ctl, long long* launches) {
   k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(W, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, nullptr, nullptr, nullptr);
-  k_blk_factor<<<1, FACT_THREADS, kFactSmem, st>>>(Sb, nu, Lb, Dblk, yb, ctl);
-  *launches += 2;
+  *launches += 1;
+  launch_blk_factor_only(st, Sb, nu, Lb, Dblk, yb, ctl, launches);
 }
 // look-ahead variants: S_b together with nu_b (delta is current only now), and G = H_b V_prev
 void launch_blk_S_nu(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const DevCfg& cfg, const double* delta,
@@ -663,7 +680,8 @@ void launch_blk_G(cudaStream_t st, const double* Vprev, FeatTab ft, int f0, int 
 }
 void launch_blk_factor_only(cudaStream_t st, const double* Sb, const double* nu, double* Lb, double* Dblk, double* yb, DevCtl* ctl,
                             long long* launches) {
-  k_blk_factor<<<1, FACT_THREADS, kFactSmem, st>>>(Sb, nu, Lb, Dblk, yb, ctl);
+  if (g_chol_smem) k_blk_factor_smem<<<1, FACT_THREADS, kFactSmemOld, st>>>(Sb, nu, Lb, Dblk, yb, ctl);
+  else k_blk_factor<<<1, FACT_THREADS, kFactSmem, st>>>(Sb, nu, Lb, Dblk, yb, ctl);
   *launches += 1;
 }
 void launch_blk_V(cudaStream_t st, double* W, int row0, int row1, const double* Lb, const double* Dblk, const double* yb,
