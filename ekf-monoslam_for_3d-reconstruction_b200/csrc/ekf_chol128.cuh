@@ -8,10 +8,14 @@
 // for the whole factorisation (152 tiles over 16 warps: <= 10 tiles = 20 doubles per thread), so an update costs two
 // fragment loads of the 8-column PANEL per operand and two DMMA.8x8x4 — no C traffic at all.
 //
-//   warp 0        owns the 16 diagonal tiles: after the panel of step P it updates tile (P+1, P+1) first, factors it (every
-//                 lane redundantly in registers: 8 rsqrt on the chain) and inverts it, then updates the remaining diagonal tiles;
-//   warps 1..15   own the 136 off-diagonal tiles (the extra tile row 16 carries nu, so y = L^-1 nu falls out of the same
-//                 recurrence), round-robin in column-major order so that the shrinking trailing matrix stays balanced.
+//   warp 0        is the pivot chain: it receives tile (P+1, P+1) from its owner as soon as that tile has the update of panel P
+//                 and factors it (every lane redundantly in registers: 8 rsqrt on the chain) while the bulk warps update;
+//   bulk warps    (the 12 warps with warp & 3 != 0) own the 136 off-diagonal tiles (the extra tile row 16 carries nu, so
+//                 y = L^-1 nu falls out of the same recurrence), round-robin in column-major order so that the shrinking
+//                 trailing matrix stays balanced.  Warps 4, 8 and 12 only take part in the barriers: they share warp 0's SM
+//                 sub-partition, and DMMAs of another warp in the same fp64 pipe stretch every DFMA / DMMA of the pivot
+//                 chain (profiles/r1k_dmma_latency.txt: 150 -> 517 cycles per dependent DMMA with four warps per sub-partition;
+//                 measured here: 3 000 -> see profiles/r2_chol128_probe.txt cycles per 8 x 8 factorisation).
 //   step P (8 columns):  [panel]  L(I,P) = C(I,P) L(P,P)^-T as C x inv(L(P,P))^T on the tensor pipe -> shared panel buffer
 //                        barrier
 //                        [update] C(I,J) -= L(I,P) L(J,P)^T for every owned tile with J > P; warp 0: next pivot tile
@@ -24,17 +28,19 @@
 
 #include "ekf_factor.cuh"
 
-#define CH_THREADS 512
+#define CH_THREADS 512           // 16 warps: warp 0 = pivot chain, warps 1..3 = panel solvers, warps 4..15 = tile owners
 #define CH_RS 12                 // row stride (doubles) of an 8 x 8 tile in shared memory: fragment loads hit every bank pair twice
 #define CH_TS (8 * CH_RS)
-#define CH_SLOTS 10              // off-diagonal tiles per bulk warp (136 tiles over 15 warps)
-#define CH_NOFF 136              // sum_{J = 0..15} (16 - J): tiles (I, J), J < I <= 16
+#define CH_SOLVERS 3
+#define CH_OWNERS 12
+#define CH_SLOTS 13              // tiles per owner warp (151 tiles over 12 warps)
+#define CH_NTILES 151            // tiles (I, J): J = 0: I = 1..16; J >= 1: I = J..16 (tile row 16 = nu); (0, 0) belongs to warp 0
 
 #ifdef CH_DEBUG   // tools/chol128_probe.cu: cycles per phase (lane 0 of warp 0 / warp 1)
 __device__ long long g_ch_acc[16];
-#define CHT(i) do { if (lane == 0) { const long long _t = clock64(); _cacc[i] += _t - _ct; _ct = _t; } } while (0)
-#define CHT_INIT long long _cacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long _ct = clock64()
-#define CHT_DUMP(base) do { if (lane == 0) for (int _i = 0; _i < 8; ++_i) g_ch_acc[base + _i] = _cacc[_i]; } while (0)
+#define CHT(i) do { _sink += *reinterpret_cast<volatile double*>(&sm.rinv[127]); if (lane == 0) { const long long _t = clock64(); _cacc[i] += _t - _ct; _ct = _t; } } while (0)
+#define CHT_INIT long long _cacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; double _sink = 0; long long _ct = clock64()
+#define CHT_DUMP(base) do { if (lane == 0) { for (int _i = 0; _i < 8; ++_i) g_ch_acc[base + _i] = _cacc[_i]; if (_sink == 12345.678) g_ch_acc[15] = 1; } } while (0)
 #else
 #define CHT(i) do {} while (0)
 #define CHT_INIT do {} while (0)
@@ -42,21 +48,22 @@ __device__ long long g_ch_acc[16];
 #endif
 
 struct __align__(16) Chol128Smem {
-  double pan[2][17][CH_TS];      // panel tiles L(I, P) of the current / previous step (tile row 16 = nu row)
+  double pan[17][CH_TS];         // panel tiles L(I, P) of the current step (tile row 16 = nu row)
   double ldiag[CH_TS];           // L(P, P) of the current step (lower triangle; read by the panel solve)
   double rdiag[8];               // 1 / L(j, j) of the current step
-  double dg[16][CH_TS];          // the 16 diagonal tiles (warp 0 works on them in place: accumulator layout <-> factorisation)
+  double dg[CH_TS];              // the pivot tile in transit: accumulator layout (owner warp) -> factorisation (warp 0)
   double ld[4][32][33];          // the four diagonal 32 x 32 blocks of L (for their inverses)
   double rinv[128];              // 1 / L(j, j)
 };
 static_assert(sizeof(Chol128Smem) < 100 * 1024, "Chol128Smem");
 
 // 8 x 8 Cholesky of the tile at `t` (row stride CH_RS, lower triangle read) by ONE warp, every lane redundantly in registers
-// (8 rsqrt on the chain, no data exchange).  Lane i publishes row i of L (zeros above the diagonal) into `t` and `lcopy`,
-// and 1 / L(i,i) into r8a[i] and r8b[i].  Returns false on a non-positive pivot.
-__device__ __forceinline__ bool warp_chol8(double* __restrict__ t, double* __restrict__ lcopy, double* __restrict__ r8a,
-                                           double* __restrict__ r8b) {
+// (8 rsqrt on the chain, no data exchange).  Lane 0 stores the lower triangle of L into `lout` (entries above the diagonal
+// are NOT written) and 1 / L(i,i) into r8a[i] and r8b[i] (both 16-byte aligned).  Returns false on a non-positive pivot.
+__device__ __forceinline__ bool warp_chol8(const double* __restrict__ t, double* __restrict__ lout, double* __restrict__ r8a,
+                                           double* __restrict__ r8b, long long* stamps = nullptr) {
   const int lane = threadIdx.x & 31;
+  if (stamps) stamps[0] = clock64();
   double a[8][8], r[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -75,20 +82,24 @@ __device__ __forceinline__ bool warp_chol8(double* __restrict__ t, double* __res
 #pragma unroll
       for (int k = j + 1; k <= i; ++k) a[i][k] = __fma_rn(-a[i][j], a[k][j], a[i][k]);
   }
+  if (stamps) stamps[1] = clock64() + (long long)(a[7][7] * 0.0);
   __syncwarp();
+  // publish: every lane holds the same values; lane 0 stores them (ONE divergent region; row i stored by lane i cost 1 650
+  // cycles in eight divergent regions, the same stores issued by all 32 lanes 570)
+  if (lane == 0) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (lane == i) {
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; j += 2) {
-        const double2 v = make_double2(j <= i ? a[i][j] : 0.0, j + 1 <= i ? a[i][j + 1] : 0.0);
-        *reinterpret_cast<double2*>(t + i * CH_RS + j) = v;
-        *reinterpret_cast<double2*>(lcopy + i * CH_RS + j) = v;
-      }
-      r8a[i] = r[i]; r8b[i] = r[i];
+      for (int j = 0; j <= i; j += 2)
+        *reinterpret_cast<double2*>(lout + i * CH_RS + j) = make_double2(a[i][j], j + 1 <= i ? a[i][j + 1] : 0.0);
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      *reinterpret_cast<double2*>(r8a + i) = make_double2(r[i], r[i + 1]);
+      *reinterpret_cast<double2*>(r8b + i) = make_double2(r[i], r[i + 1]);
     }
   }
   __syncwarp();
+  if (stamps) stamps[2] = clock64();
   return ok;
 }
 
@@ -100,87 +111,125 @@ __device__ __forceinline__ void cta_chol128(void* smem_raw, const double* __rest
                                             double* __restrict__ yout, int* chol_fail) {
   Chol128Smem& sm = *reinterpret_cast<Chol128Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
-  // Warp 0 and the bulk warps run SEPARATE loops (their register needs differ: the 8 x 8 factorisation keeps ~45 doubles
-  // live, the bulk warps their accumulator tiles) that meet at a named barrier: bar.sync with an explicit thread count is
-  // defined for arrivals from different program locations.
+  // Three roles with SEPARATE loops (their register needs differ) that meet at named barriers; bar.sync / bar.arrive with an
+  // explicit thread count are defined for arrivals from different program locations.
+  //   barrier 1 (all warps):          A = "the panel of step P is solved", B = "L(P+1, P+1) is published"
+  //   barrier 2 (64 threads):         the owner of pivot tile (P+1, P+1) arrives once the updated tile is in sm.dg, warp 0 waits
+  //   barrier 3 (owners + solvers):   the owners arrive once their tiles of column P are in sm.pan, the solvers wait
   auto cta_bar = [] { asm volatile("bar.sync 1, %0;" ::"n"(CH_THREADS) : "memory"); };
-  // C(J, J) -= L(J, P) L(J, P)^T for four diagonal tiles at a time (independent DMMAs in flight)
-  auto diag_update = [&](const double (*pn)[CH_TS], int J0, int J1) {
-    for (int Jb = J0; Jb < J1; Jb += 4) {
-      double2 cv[4];
-      double e[4][2], f[4][2];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int J = min(Jb + u, 15);
-        const double* pp = pn[J] + g * CH_RS + t4;
-        cv[u] = *reinterpret_cast<const double2*>(sm.dg[J] + g * CH_RS + 2 * t4);
-        e[u][0] = e[u][1] = f[u][0] = f[u][1] = 0.0;
-        dmma884f(e[u][0], e[u][1], -pp[0], pp[0]);
-        dmma884f(f[u][0], f[u][1], -pp[4], pp[4]);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (Jb + u < J1)
-          *reinterpret_cast<double2*>(sm.dg[Jb + u] + g * CH_RS + 2 * t4) = make_double2(cv[u].x + (e[u][0] + f[u][0]), cv[u].y + (e[u][1] + f[u][1]));
-    }
-  };
   if (warp == 0) {
-    // ---- load the 16 diagonal tiles straight from global / L2 into their shared-memory home -----------------------------
-    {
-      double2 v[16];
-#pragma unroll
-      for (int J = 0; J < 16; ++J) v[J] = *reinterpret_cast<const double2*>(Sb + (size_t)(8 * J + g) * lds + 8 * J + 2 * t4);
-#pragma unroll
-      for (int J = 0; J < 16; ++J) *reinterpret_cast<double2*>(sm.dg[J] + g * CH_RS + 2 * t4) = v[J];
+    {   // tile (0, 0) straight from global / L2
+      const double2 v = *reinterpret_cast<const double2*>(Sb + (size_t)g * lds + 2 * t4);
+      *reinterpret_cast<double2*>(sm.dg + g * CH_RS + 2 * t4) = v;
     }
     CHT_INIT;
     CHT(0);
-    // Step P of warp 0: [deferred] the diagonal tiles beyond the pivot get the update of panel P-1 while the bulk warps solve
-    // panel P; [barrier A] panel P is complete; the next pivot tile (P+1, P+1) is updated with panel P and factored while the
-    // bulk warps run their trailing update; [barrier B].  P = -1 is the prologue (tile (0, 0)): ONE call site for the factor.
+    // P = -1 is the prologue (tile (0, 0)); step P >= 0: [A] wait for the hand-over of tile (P+1, P+1), factor, publish [B]
 #pragma unroll 1
     for (int P = -1; P < 16; ++P) {
-      if (P >= 1) diag_update(sm.pan[(P - 1) & 1], P + 1, 16);
+      if (P >= 0) cta_bar();                          // A
       CHT(1);
-      if (P >= 0) cta_bar();                          // A: the panel of step P is in sm.pan[P & 1]
-      CHT(2);
       const int J = P + 1;
       if (J < 16) {
-        if (P >= 0) {                                 // the pivot tile alone: two independent DMMAs, nothing else on the chain
-          const double* pp = sm.pan[P & 1][J] + g * CH_RS + t4;
-          double2* cp = reinterpret_cast<double2*>(sm.dg[J] + g * CH_RS + 2 * t4);
-          const double2 cv = *cp;
-          double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
-          dmma884f(e0, e1, -pp[0], pp[0]);
-          dmma884f(f0, f1, -pp[4], pp[4]);
-          *cp = make_double2(cv.x + (e0 + f0), cv.y + (e1 + f1));
-        }
+        if (P >= 0) asm volatile("bar.sync 2, 64;" ::: "memory");
         __syncwarp();
-        CHT(3);
-        const bool ok = warp_chol8(sm.dg[J], sm.ldiag, sm.rdiag, sm.rinv + 8 * J);
+        CHT(2);
+#ifdef CH_DEBUG
+        long long st3[3];
+        const bool ok = warp_chol8(sm.dg, sm.ldiag, sm.rdiag, sm.rinv + 8 * J, st3);
+        if (lane == 0) { _cacc[6] += st3[1] - st3[0]; _cacc[7] += st3[2] - st3[1]; }
+#else
+        const bool ok = warp_chol8(sm.dg, sm.ldiag, sm.rdiag, sm.rinv + 8 * J);
+#endif
         if (lane == 0 && !ok) *chol_fail = 1;
-        const double2 lv = *reinterpret_cast<const double2*>(sm.dg[J] + g * CH_RS + 2 * t4);
+        CHT(3);
+      }
+      cta_bar();                                      // B: L(P+1, P+1) published; sm.pan free again
+      CHT(4);
+      if (J < 16) {                                   // off the chain: the diagonal tile goes to Lout and to the block copy
+        double2 lv = *reinterpret_cast<const double2*>(sm.ldiag + g * CH_RS + 2 * t4);
+        if (2 * t4 > g) lv.x = 0.0;                   // above the diagonal: stale data, not part of L
+        if (2 * t4 + 1 > g) lv.y = 0.0;
         *reinterpret_cast<double2*>(Lout + (size_t)(8 * J + g) * ldl + 8 * J + 2 * t4) = lv;
         double* ldp = &sm.ld[J >> 2][8 * (J & 3) + g][8 * (J & 3) + 2 * t4];
         ldp[0] = lv.x; ldp[1] = lv.y;
-        CHT(4);
       }
-      cta_bar();                                      // B: L(P+1, P+1) published; the bulk warps are done with panel P
       CHT(5);
     }
     CHT_DUMP(0);
+  } else if (warp <= CH_SOLVERS) {
+    // ---- panel solvers: one THREAD per row of the panel: X(row, :) = C(row, :) L(P,P)^-T by forward substitution with
+    // L(P,P) and 1 / diag in registers (36 doubles, loaded once per step with every load in flight; with the operands read
+    // from shared memory inside the recurrence every FMA waited for its own load: 2 400 cycles per step) ---------------
+    const int st = tid - 32;                           // 0 .. 95
+    cta_bar();                                        // B of the prologue
+#pragma unroll 1
+    for (int P = 0; P < 16; ++P) {
+      double Lp[8][8], rp[8];
+#pragma unroll
+      for (int j = 1; j < 8; ++j)
+#pragma unroll
+        for (int k = 0; k < j; k += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(sm.ldiag + j * CH_RS + k);
+          Lp[j][k] = v.x; Lp[j][k + 1] = v.y;
+        }
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(sm.rdiag + j);
+        rp[j] = v.x; rp[j + 1] = v.y;
+      }
+      asm volatile("bar.sync 3, %0;" ::"n"((CH_SOLVERS + CH_OWNERS) * 32) : "memory");   // column P of C is in sm.pan
+      const int nrows = 8 * (15 - P) + 1;             // tiles P+1 .. 15, and the nu row
+#pragma unroll 1
+      for (int rho = st; rho < nrows; rho += 32 * CH_SOLVERS) {
+        const int I = P + 1 + (rho >> 3), r = rho & 7;
+        double* rowp = sm.pan[I] + r * CH_RS;
+        double row[8];
+#pragma unroll
+        for (int q = 0; q < 8; q += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(rowp + q);
+          row[q] = v.x; row[q + 1] = v.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          double v = row[j];
+#pragma unroll
+          for (int k = 0; k < j; ++k) v = __fma_rn(-row[k], Lp[j][k], v);
+          row[j] = v * rp[j];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q += 2) *reinterpret_cast<double2*>(rowp + q) = make_double2(row[q], row[q + 1]);
+        if (I < 16) {
+          double* lo = Lout + (size_t)(8 * I + r) * ldl + 8 * P;
+#pragma unroll
+          for (int q = 0; q < 8; q += 2) *reinterpret_cast<double2*>(lo + q) = make_double2(row[q], row[q + 1]);
+          if ((I >> 2) == (P >> 2)) {
+            double* ldp = &sm.ld[P >> 2][8 * (I & 3) + r][8 * (P & 3)];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ldp[q] = row[q];
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; q += 2) *reinterpret_cast<double2*>(yout + 8 * P + q) = make_double2(row[q], row[q + 1]);
+        }
+      }
+      cta_bar();                                      // A
+      cta_bar();                                      // B
+    }
   } else {
-    double acc[CH_SLOTS][2];    // off-diagonal tile of slot s in the DMMA accumulator layout
-    int tI[CH_SLOTS], tJ[CH_SLOTS];
+    double acc[CH_SLOTS][2];    // tile of slot s in the DMMA accumulator layout
+    int tIJ[CH_SLOTS];          // I | J << 8, or -1
+    const int bw = warp - 1 - CH_SOLVERS;             // 0 .. CH_OWNERS - 1
 #pragma unroll
     for (int s = 0; s < CH_SLOTS; ++s) {
-      const int t = (warp - 1) + 15 * s;
-      int J = 0, off = 0;
-      while (J < 15 && off + (16 - J) <= t) { off += 16 - J; ++J; }
-      const int I = J + 1 + (t - off);
-      tI[s] = (t < CH_NOFF) ? I : -1; tJ[s] = (t < CH_NOFF) ? J : -1;
+      const int t = bw + CH_OWNERS * s;
+      // column-major enumeration: column 0 holds I = 1..16 (16 tiles), column J >= 1 holds I = J..16 (17 - J tiles)
+      int J = 0, off = 0, cnt = 16;
+      while (J < 15 && off + cnt <= t) { off += cnt; ++J; cnt = 17 - J; }
+      const int I = (J == 0 ? 1 : J) + (t - off);
+      tIJ[s] = (t < CH_NTILES) ? (I | (J << 8)) : -1;
       double2 v = make_double2(0.0, 0.0);
-      if (t < CH_NOFF) {
+      if (t < CH_NTILES) {
         if (I < 16) v = *reinterpret_cast<const double2*>(Sb + (size_t)(8 * I + g) * lds + 8 * J + 2 * t4);
         else if (g == 0) v = *reinterpret_cast<const double2*>(nu + 8 * J + 2 * t4);
       }
@@ -192,63 +241,65 @@ __device__ __forceinline__ void cta_chol128(void* smem_raw, const double* __rest
     CHT(1);
 #pragma unroll 1
     for (int P = 0; P < 16; ++P) {
-      double (*pn)[CH_TS] = sm.pan[P & 1];
-      // ---- panel: L(I, P) = C(I, P) L(P,P)^-T by forward substitution along each row.  The four lanes that share a row
-      // of the accumulator layout gather the row's 8 entries with shuffles and solve it redundantly (28 FMA + 8 MUL on
-      // broadcast loads of L(P,P) and 1 / diag); each keeps its own two columns. ---------------------------------------
+      // ---- the tiles of column P go to the solvers (accumulator layout, in place in sm.pan) -----------------------------
 #pragma unroll
       for (int s = 0; s < CH_SLOTS; ++s) {
-        if (tJ[s] == P) {                             // warp-uniform
-          const int I = tI[s];
-          double row[8];
+        const int I = tIJ[s] & 255;
+        if ((tIJ[s] >> 8) == P && I != P && tIJ[s] >= 0)
+          *reinterpret_cast<double2*>(sm.pan[I] + g * CH_RS + 2 * t4) = make_double2(acc[s][0], acc[s][1]);
+      }
+      __syncwarp();
+      asm volatile("bar.arrive 3, %0;" ::"n"((CH_SOLVERS + CH_OWNERS) * 32) : "memory");
+      CHT(2);
+      cta_bar();                                      // A: the panel is solved
+      CHT(3);
+      // ---- trailing update with the panel of step P: the next pivot tile first (it heads the dependency chain) and straight
+      // to warp 0 through sm.dg, then the rest in groups of four slots (operands of finished / empty slots are zeroed
+      // instead of branching around them, so that the DMMAs of a group are in flight together) -----------------------------
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            row[2 * q] = __shfl_sync(0xffffffffu, acc[s][0], (lane & ~3) + q);
-            row[2 * q + 1] = __shfl_sync(0xffffffffu, acc[s][1], (lane & ~3) + q);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            double v = row[j];
-#pragma unroll
-            for (int k = 0; k < j; ++k) v = __fma_rn(-row[k], sm.ldiag[j * CH_RS + k], v);
-            row[j] = v * sm.rdiag[j];
-          }
-          double x0 = row[0], x1 = row[1];
-#pragma unroll
-          for (int q = 1; q < 4; ++q)
-            if (t4 == q) { x0 = row[2 * q]; x1 = row[2 * q + 1]; }
-          *reinterpret_cast<double2*>(pn[I] + g * CH_RS + 2 * t4) = make_double2(x0, x1);
-          if (I < 16) {
-            *reinterpret_cast<double2*>(Lout + (size_t)(8 * I + g) * ldl + 8 * P + 2 * t4) = make_double2(x0, x1);
-            if ((I >> 2) == (P >> 2)) {
-              double* ldp = &sm.ld[P >> 2][8 * (I & 3) + g][8 * (P & 3) + 2 * t4];
-              ldp[0] = x0; ldp[1] = x1;
-            }
-          } else if (g == 0) {
-            *reinterpret_cast<double2*>(yout + 8 * P + 2 * t4) = make_double2(x0, x1);
-          }
+      for (int s = 0; s < CH_SLOTS; ++s) {
+        if (tIJ[s] == ((P + 1) | ((P + 1) << 8))) {
+          const double* pp = sm.pan[P + 1] + g * CH_RS + t4;
+          double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+          dmma884f(e0, e1, -pp[0], pp[0]);
+          dmma884f(f0, f1, -pp[4], pp[4]);
+          *reinterpret_cast<double2*>(sm.dg + g * CH_RS + 2 * t4) = make_double2(acc[s][0] + (e0 + f0), acc[s][1] + (e1 + f1));
+          __syncwarp();
+          asm volatile("bar.arrive 2, 64;" ::: "memory");
         }
       }
-      CHT(2);
-      cta_bar();                                      // A
-      CHT(3);
-      // ---- trailing update with the panel of step P ------------------------------------------------------------------
 #pragma unroll
-      for (int s = 0; s < CH_SLOTS; ++s) {
-        if (tJ[s] > P) {                              // not a finished column, not an empty slot (-1)
-          const double* pa = pn[tI[s]] + g * CH_RS + t4;
-          const double* pb = pn[tJ[s]] + g * CH_RS + t4;
-          double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
-          dmma884f(e0, e1, -pa[0], pb[0]);
-          dmma884f(f0, f1, -pa[4], pb[4]);
-          acc[s][0] += e0 + f0; acc[s][1] += e1 + f1;
+      for (int s0 = 0; s0 < CH_SLOTS; s0 += 4) {
+        bool any = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (s0 + u < CH_SLOTS) any = any || ((tIJ[s0 + u] >> 8) > P);
+        if (any) {                                    // warp-uniform; slots are in column order: the live ones are a suffix
+          double e[4][2], f[4][2];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (s0 + u < CH_SLOTS) {
+              const int s = s0 + u;
+              const int I = tIJ[s] & 255, J = tIJ[s] >> 8;
+              const bool live = J > P && !(I == P + 1 && J == P + 1);
+              const double* pa = sm.pan[live ? I : 16] + g * CH_RS + t4;
+              const double* pb = sm.pan[live ? J : 16] + g * CH_RS + t4;
+              const double a0 = live ? -pa[0] : 0.0, a1 = live ? -pa[4] : 0.0;
+              e[u][0] = e[u][1] = f[u][0] = f[u][1] = 0.0;
+              dmma884f(e[u][0], e[u][1], a0, pb[0]);
+              dmma884f(f[u][0], f[u][1], a1, pb[4]);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (s0 + u < CH_SLOTS) { acc[s0 + u][0] += e[u][0] + f[u][0]; acc[s0 + u][1] += e[u][1] + f[u][1]; }
         }
       }
       CHT(4);
       cta_bar();                                      // B
       CHT(5);
     }
-    if (warp == 1) CHT_DUMP(8);
+    if (bw == 0) CHT_DUMP(8);
   }
   __syncthreads();
   // ---- inverses of the four diagonal 32 x 32 blocks: warp J solves X L_JJ^T = I by substitution, lane = row r of

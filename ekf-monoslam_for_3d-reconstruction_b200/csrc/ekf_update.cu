@@ -451,8 +451,7 @@ void launch_plane_S(cudaStream_t st, const double* W, double* Sb, long long* lau
 // K4b: Cholesky gain of one 128-row block.  Default: cta_chol128 (ekf_chol128.cuh: the matrix lives in registers in the DMMA
 // accumulator layout, 8-column steps, two barriers per step).  k_blk_factor_smem is the round-1 kernel (matrix in shared
 // memory, bound by shared-memory bandwidth), kept selectable with EKF_CHOL_SMEM=1 for A/B timing and as a cross-check.
-static_assert(CH_THREADS == FACT_THREADS, "both factor kernels are launched with FACT_THREADS threads");
-__global__ void __launch_bounds__(FACT_THREADS) k_blk_factor(const double* __restrict__ Sb, const double* __restrict__ nu,
+__global__ void __launch_bounds__(CH_THREADS, 1) k_blk_factor(const double* __restrict__ Sb, const double* __restrict__ nu,
                                                              double* __restrict__ Lout, double* __restrict__ Dblk,
                                                              double* __restrict__ yout, DevCtl* ctl) {
   extern __shared__ __align__(16) double fsm[];
@@ -467,14 +466,14 @@ __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor_smem(const double* 
 
 // Row-block partition: S_b = sum over ranks of the partial blocks the peers stored into this rank's slots (fixed
 // order: every rank forms the same bits), once every peer's epoch has arrived; then the same factorisation.
-__global__ void __launch_bounds__(FACT_THREADS) k_blk_factor_p2p(const double* __restrict__ spart, const unsigned long long* __restrict__ flags,
+__global__ void __launch_bounds__(CH_THREADS, 1) k_blk_factor_p2p(const double* __restrict__ spart, const unsigned long long* __restrict__ flags,
                                                                  int world, unsigned long long epoch, double* __restrict__ Ssum,
                                                                  const double* __restrict__ nu, double* __restrict__ Lout,
                                                                  double* __restrict__ Dblk, double* __restrict__ yout, DevCtl* ctl) {
   extern __shared__ __align__(16) double fsm[];
   if (threadIdx.x < 32) p2p_wait(flags, 0, world, epoch, ctl);
   __syncthreads();
-  for (int e = threadIdx.x; e < EKF_UB * EKF_UB; e += FACT_THREADS) {
+  for (int e = threadIdx.x; e < EKF_UB * EKF_UB; e += CH_THREADS) {
     double s = 0;
     for (int q = 0; q < world; ++q) s += __ldcg(spart + (size_t)q * EKF_UB * EKF_UB + e);
     Ssum[e] = s;
@@ -681,7 +680,7 @@ void launch_blk_G(cudaStream_t st, const double* Vprev, FeatTab ft, int f0, int 
 void launch_blk_factor_only(cudaStream_t st, const double* Sb, const double* nu, double* Lb, double* Dblk, double* yb, DevCtl* ctl,
                             long long* launches) {
   if (g_chol_smem) k_blk_factor_smem<<<1, FACT_THREADS, kFactSmemOld, st>>>(Sb, nu, Lb, Dblk, yb, ctl);
-  else k_blk_factor<<<1, FACT_THREADS, kFactSmem, st>>>(Sb, nu, Lb, Dblk, yb, ctl);
+  else k_blk_factor<<<1, CH_THREADS, kFactSmem, st>>>(Sb, nu, Lb, Dblk, yb, ctl);
   *launches += 1;
 }
 void launch_blk_V(cudaStream_t st, double* W, int row0, int row1, const double* Lb, const double* Dblk, const double* yb,
@@ -703,7 +702,7 @@ void launch_blk_S_part_p2p(cudaStream_t st, const double* W, FeatTab ft, int f0,
 }
 void launch_blk_factor_p2p(cudaStream_t st, const double* spart, const unsigned long long* flags, int world, unsigned long long epoch,
                            double* Ssum, const double* nu, double* Lb, double* Dblk, double* yb, DevCtl* ctl, long long* launches) {
-  k_blk_factor_p2p<<<1, FACT_THREADS, kFactSmem, st>>>(spart, flags, world, epoch, Ssum, nu, Lb, Dblk, yb, ctl);
+  k_blk_factor_p2p<<<1, CH_THREADS, kFactSmem, st>>>(spart, flags, world, epoch, Ssum, nu, Lb, Dblk, yb, ctl);
   *launches += 1;
 }
 void launch_blk_V_p2p(cudaStream_t st, double* W, int row0, int row1, const double* Lb, const double* Dblk, const double* yb,

@@ -8,8 +8,11 @@
 // Differences from the reference, all forced: poses are doubles (the fp64 parity target) formatted at the
 // same 6 significant digits; images go through a caller-supplied writer (no OpenCV here: cv::imwrite in the
 // ROS node); `Filter` is a template parameter so that tests can drive the selector without a GPU.
-// Parity: restated from the sources cited per line; the ROS node is unbuildable here (ROS, cv_bridge), so this
-// file is pinned by tests/test_keyframes.py against the Python twin and a restatement of the consumer's parser.
+// Parity: PINNED against the reference's own selector — monoslam_ransac.cpp:585, 609-687 (+ quat2vec / poses_diff, :40-60)
+// are compiled from the unmodified source into oracle/_ref/libref_selector_f64.so (oracle/build_ref_selector.py) and
+// tests/test_keyframe_pinned.py requires byte-identical nodes_and_prjcts.txt / cams_cov.txt / cams_cov2.txt and the same
+// image names on trajectories that take every branch; committed copies of the reference's outputs (tests/golden/keyframes)
+// repeat the check where /root/reference is absent.  Eigen's number formatting itself stays unpinned (absent dependency).
 #pragma once
 #include <cmath>
 #include <cstdint>

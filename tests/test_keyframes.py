@@ -1,8 +1,8 @@
 """CPU: caller-side formats — the key-frame selector and the writers of
 nodes_and_prjcts.txt / cams_cov.txt / points.txt (monoslam_ransac.cpp:585-687, 232-275), Python twin and C++
 twin (host/keyframe_recorder.hpp) on the same trajectory, read back through a restatement of the consumer's
-parser (sba_add.cpp:76-180).  The ROS node itself cannot be built here, so this parity is against the restated
-logic only ("unpinned" for the selector)."""
+parser (sba_add.cpp:76-180).  The comparison with the reference's OWN selector (compiled from monoslam_ransac.cpp) is in
+tests/test_keyframe_pinned.py."""
 import os
 import struct
 import subprocess
