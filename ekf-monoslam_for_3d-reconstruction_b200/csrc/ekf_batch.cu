@@ -621,6 +621,7 @@ struct ekf_batch {
   size_t frame_cap = 0;
   FrameView fv{nullptr, 0, 0, 0};
   EkfTensorMap frame_map{};
+  int* match_defer = nullptr;   // [B * Ncap] (filter, feature) pairs the warp matcher left to the CTA matcher, then the count
   uint32_t* picks_dev = nullptr;
   int picks_cap = 0;
   double *out_mu14 = nullptr, *out_S14 = nullptr;
@@ -667,6 +668,7 @@ int ekf_batch_destroy(ekf_batch* b) {
   cudaFree(t.center); cudaFree(t.quality); cudaFree(t.last_ncc); cudaFree(t.z); cudaFree(t.h); cudaFree(t.Hc);
   cudaFree(t.S2); cudaFree(t.patch); cudaFree(t.mpatch);
   cudaFree(b->bv.Sigma); cudaFree(b->bv.mu); cudaFree(b->bv.ctl); cudaFree(b->bv.n); cudaFree(b->bv.N);
+  cudaFree(b->match_defer);
   cudaFree(b->scratch); cudaFree(b->frame); cudaFree(b->picks_dev); cudaFree(b->out_mu14); cudaFree(b->out_S14);
   cudaFree(b->out_stats); cudaFree(b->stage_mu14);
   if (b->h_mu14) cudaFreeHost(b->h_mu14);
@@ -710,6 +712,7 @@ int ekf_batch_create(const ekf_config* cfg, int n_filters, int feature_capacity,
   v.sstride = (long long)b->ncap * b->ld;
   TRY(balloc(&v.Sigma, Bn * v.sstride)) TRY(balloc(&b->scratch, Bn * v.sstride)) TRY(balloc(&v.mu, Bn * b->ld))
   TRY(balloc(&v.ctl, Bn)) TRY(balloc(&v.n, Bn)) TRY(balloc(&v.N, Bn))
+  TRY(balloc(&b->match_defer, cap + 1))
   FeatTab& t = v.ft;
   TRY(balloc(&t.pos, cap)) TRY(balloc(&t.coding, cap)) TRY(balloc(&t.innov, cap)) TRY(balloc(&t.li, cap)) TRY(balloc(&t.hi, cap))
   TRY(balloc(&t.removef, cap)) TRY(balloc(&t.n_tot, cap)) TRY(balloc(&t.n_find, cap)) TRY(balloc(&t.real_index, cap))
@@ -845,7 +848,8 @@ int ekf_batch_step(ekf_batch* b, const double dv[3], const double dw[3], int vco
                                                    make_double3(w[0], w[1], w[2]), vcontrol);
   b->launches += 1;
   BCHECK(cudaEventRecord(b->ev[1], st));
-  launch_match_filter_batch(st, b->bv.ft, b->Ncap, b->bv.N, b->B, b->fv, b->dcfg, &b->frame_map, &b->launches);
+  launch_match_filter_batch(st, b->bv.ft, b->Ncap, b->bv.N, b->B, b->fv, b->dcfg, &b->frame_map, b->match_defer,
+                            b->match_defer + (size_t)b->B * b->Ncap, &b->launches);
   BCHECK(cudaEventRecord(b->ev[2], st));
   k_batch_update<<<b->B, BUPD_THREADS, kUpdSmemBytes, st>>>(b->bv, b->dcfg, b->picks_dev, n_picks, b->out_mu14, b->out_S14,
                                                             b->out_stats, b->cfg.min_features, b->cfg.max_features);

@@ -28,7 +28,7 @@
 
 #include "ekf_factor.cuh"
 
-#define CH_THREADS 512           // 16 warps: warp 0 = pivot chain, warps 1..3 = panel solvers, warps 4..15 = tile owners
+#define CH_THREADS 512           // 16 warps: warp 0 = pivot chain, warps 4, 8, 12 = panel solvers, the other 12 = tile owners
 #define CH_RS 12                 // row stride (doubles) of an 8 x 8 tile in shared memory: fragment loads hit every bank pair twice
 #define CH_TS (8 * CH_RS)
 #define CH_SOLVERS 3
@@ -51,7 +51,7 @@ struct __align__(16) Chol128Smem {
   double pan[17][CH_TS];         // panel tiles L(I, P) of the current step (tile row 16 = nu row)
   double ldiag[CH_TS];           // L(P, P) of the current step (lower triangle; read by the panel solve)
   double rdiag[8];               // 1 / L(j, j) of the current step
-  double dg[CH_TS];              // the pivot tile in transit: accumulator layout (owner warp) -> factorisation (warp 0)
+  double dg[2][CH_TS];           // the next two pivot tiles in transit: accumulator layout (owner warp) -> factorisation (warp 0)
   double ld[4][32][33];          // the four diagonal 32 x 32 blocks of L (for their inverses)
   double rinv[128];              // 1 / L(j, j)
 };
@@ -114,32 +114,42 @@ __device__ __forceinline__ void cta_chol128(void* smem_raw, const double* __rest
   // Three roles with SEPARATE loops (their register needs differ) that meet at named barriers; bar.sync / bar.arrive with an
   // explicit thread count are defined for arrivals from different program locations.
   //   barrier 1 (all warps):          A = "the panel of step P is solved", B = "L(P+1, P+1) is published"
-  //   barrier 2 (64 threads):         the owner of pivot tile (P+1, P+1) arrives once the updated tile is in sm.dg, warp 0 waits
   //   barrier 3 (owners + solvers):   the owners arrive once their tiles of column P are in sm.pan, the solvers wait
   auto cta_bar = [] { asm volatile("bar.sync 1, %0;" ::"n"(CH_THREADS) : "memory"); };
   if (warp == 0) {
     {   // tile (0, 0) straight from global / L2
       const double2 v = *reinterpret_cast<const double2*>(Sb + (size_t)g * lds + 2 * t4);
-      *reinterpret_cast<double2*>(sm.dg + g * CH_RS + 2 * t4) = v;
+      *reinterpret_cast<double2*>(sm.dg[0] + g * CH_RS + 2 * t4) = v;
     }
     CHT_INIT;
     CHT(0);
-    // P = -1 is the prologue (tile (0, 0)); step P >= 0: [A] wait for the hand-over of tile (P+1, P+1), factor, publish [B]
+    // P = -1 is the prologue (tile (0, 0)).  Step P >= 0: [A] tile (P+1, P+1) already sits in sm.dg with every update up to
+    // panel P-1 (its owner handed it over one step ahead, off the chain); warp 0 applies panel P itself — two DMMAs in an
+    // otherwise idle sub-partition — factors the tile and publishes it [B].
 #pragma unroll 1
     for (int P = -1; P < 16; ++P) {
       if (P >= 0) cta_bar();                          // A
       CHT(1);
       const int J = P + 1;
       if (J < 16) {
-        if (P >= 0) asm volatile("bar.sync 2, 64;" ::: "memory");
+        double* dt = sm.dg[J & 1];
+        if (P >= 0) {
+          const double* pp = sm.pan[J] + g * CH_RS + t4;
+          double2* cp = reinterpret_cast<double2*>(dt + g * CH_RS + 2 * t4);
+          const double2 cv = *cp;
+          double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+          dmma884f(e0, e1, -pp[0], pp[0]);
+          dmma884f(f0, f1, -pp[4], pp[4]);
+          *cp = make_double2(cv.x + (e0 + f0), cv.y + (e1 + f1));
+        }
         __syncwarp();
         CHT(2);
 #ifdef CH_DEBUG
         long long st3[3];
-        const bool ok = warp_chol8(sm.dg, sm.ldiag, sm.rdiag, sm.rinv + 8 * J, st3);
+        const bool ok = warp_chol8(dt, sm.ldiag, sm.rdiag, sm.rinv + 8 * J, st3);
         if (lane == 0) { _cacc[6] += st3[1] - st3[0]; _cacc[7] += st3[2] - st3[1]; }
 #else
-        const bool ok = warp_chol8(sm.dg, sm.ldiag, sm.rdiag, sm.rinv + 8 * J);
+        const bool ok = warp_chol8(dt, sm.ldiag, sm.rdiag, sm.rinv + 8 * J);
 #endif
         if (lane == 0 && !ok) *chol_fail = 1;
         CHT(3);
@@ -157,11 +167,13 @@ __device__ __forceinline__ void cta_chol128(void* smem_raw, const double* __rest
       CHT(5);
     }
     CHT_DUMP(0);
-  } else if (warp <= CH_SOLVERS) {
+  } else if ((warp & 3) == 0) {
     // ---- panel solvers: one THREAD per row of the panel: X(row, :) = C(row, :) L(P,P)^-T by forward substitution with
     // L(P,P) and 1 / diag in registers (36 doubles, loaded once per step with every load in flight; with the operands read
     // from shared memory inside the recurrence every FMA waited for its own load: 2 400 cycles per step) ---------------
-    const int st = tid - 32;                           // 0 .. 95
+    // (warps 4, 8, 12: the pivot chain's own sub-partition, idle while warp 0 factors — DMMA / DFMA traffic of another warp
+    // in that sub-partition stretched the 8 x 8 factorisation from 820 to 1 420 cycles)
+    const int st = ((warp >> 2) - 1) * 32 + lane;      // 0 .. 95
     cta_bar();                                        // B of the prologue
 #pragma unroll 1
     for (int P = 0; P < 16; ++P) {
@@ -219,7 +231,7 @@ __device__ __forceinline__ void cta_chol128(void* smem_raw, const double* __rest
   } else {
     double acc[CH_SLOTS][2];    // tile of slot s in the DMMA accumulator layout
     int tIJ[CH_SLOTS];          // I | J << 8, or -1
-    const int bw = warp - 1 - CH_SOLVERS;             // 0 .. CH_OWNERS - 1
+    const int bw = (warp >> 2) * 3 + (warp & 3) - 1;   // 0 .. CH_OWNERS - 1
 #pragma unroll
     for (int s = 0; s < CH_SLOTS; ++s) {
       const int t = bw + CH_OWNERS * s;
@@ -235,6 +247,9 @@ __device__ __forceinline__ void cta_chol128(void* smem_raw, const double* __rest
       }
       acc[s][0] = v.x; acc[s][1] = v.y;
     }
+#pragma unroll
+    for (int s = 0; s < CH_SLOTS; ++s)                // tile (1, 1) goes to warp 0 right away
+      if (tIJ[s] == (1 | (1 << 8))) *reinterpret_cast<double2*>(sm.dg[1] + g * CH_RS + 2 * t4) = make_double2(acc[s][0], acc[s][1]);
     CHT_INIT;
     CHT(0);
     cta_bar();                                        // B of the prologue: L(0, 0) published
@@ -253,21 +268,9 @@ __device__ __forceinline__ void cta_chol128(void* smem_raw, const double* __rest
       CHT(2);
       cta_bar();                                      // A: the panel is solved
       CHT(3);
-      // ---- trailing update with the panel of step P: the next pivot tile first (it heads the dependency chain) and straight
-      // to warp 0 through sm.dg, then the rest in groups of four slots (operands of finished / empty slots are zeroed
-      // instead of branching around them, so that the DMMAs of a group are in flight together) -----------------------------
-#pragma unroll
-      for (int s = 0; s < CH_SLOTS; ++s) {
-        if (tIJ[s] == ((P + 1) | ((P + 1) << 8))) {
-          const double* pp = sm.pan[P + 1] + g * CH_RS + t4;
-          double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
-          dmma884f(e0, e1, -pp[0], pp[0]);
-          dmma884f(f0, f1, -pp[4], pp[4]);
-          *reinterpret_cast<double2*>(sm.dg + g * CH_RS + 2 * t4) = make_double2(acc[s][0] + (e0 + f0), acc[s][1] + (e1 + f1));
-          __syncwarp();
-          asm volatile("bar.arrive 2, 64;" ::: "memory");
-        }
-      }
+      // ---- trailing update with the panel of step P, in groups of four slots (operands of finished / empty slots are zeroed
+      // instead of branching around them, so that the DMMAs of a group are in flight together).  Tile (P+1, P+1) is already with
+      // warp 0; tile (P+2, P+2) is handed over (through sm.dg) as soon as it has this update: one step ahead, off the chain. ----
 #pragma unroll
       for (int s0 = 0; s0 < CH_SLOTS; s0 += 4) {
         bool any = false;
@@ -275,7 +278,9 @@ __device__ __forceinline__ void cta_chol128(void* smem_raw, const double* __rest
         for (int u = 0; u < 4; ++u)
           if (s0 + u < CH_SLOTS) any = any || ((tIJ[s0 + u] >> 8) > P);
         if (any) {                                    // warp-uniform; slots are in column order: the live ones are a suffix
-          double e[4][2], f[4][2];
+          // The two k-steps accumulate straight into the tile (a dependent pair per slot), and nothing reads the tile before
+          // the next step: the DMMAs of ALL groups stay in flight together.  (With per-group temporaries that were summed
+          // inside the branch every group paid the full DMMA latency — 517 cycles with four warps per sub-partition.)
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             if (s0 + u < CH_SLOTS) {
@@ -285,16 +290,16 @@ __device__ __forceinline__ void cta_chol128(void* smem_raw, const double* __rest
               const double* pa = sm.pan[live ? I : 16] + g * CH_RS + t4;
               const double* pb = sm.pan[live ? J : 16] + g * CH_RS + t4;
               const double a0 = live ? -pa[0] : 0.0, a1 = live ? -pa[4] : 0.0;
-              e[u][0] = e[u][1] = f[u][0] = f[u][1] = 0.0;
-              dmma884f(e[u][0], e[u][1], a0, pb[0]);
-              dmma884f(f[u][0], f[u][1], a1, pb[4]);
+              dmma884f(acc[s][0], acc[s][1], a0, pb[0]);
+              dmma884f(acc[s][0], acc[s][1], a1, pb[4]);
             }
           }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (s0 + u < CH_SLOTS) { acc[s0 + u][0] += e[u][0] + f[u][0]; acc[s0 + u][1] += e[u][1] + f[u][1]; }
         }
       }
+#pragma unroll
+      for (int s = 0; s < CH_SLOTS; ++s)
+        if (tIJ[s] == ((P + 2) | ((P + 2) << 8)))
+          *reinterpret_cast<double2*>(sm.dg[P & 1] + g * CH_RS + 2 * t4) = make_double2(acc[s][0], acc[s][1]);
       CHT(4);
       cta_bar();                                      // B
       CHT(5);

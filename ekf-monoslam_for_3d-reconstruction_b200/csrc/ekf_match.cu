@@ -164,41 +164,61 @@ __device__ __forceinline__ void match_dots4(const uint8_t* win0, int wsb, const 
   }
 }
 
-// Core search for one feature by one CTA.  All threads must call.
-__device__ MatchResult match_one(const MatchJob& jb, int w, float sigma_size, float clampv, unsigned char* smem_raw) {
-  const int tid = threadIdx.x;
-  const int half = w / 2, w2 = w * w;
-  const MatchSmem pl = match_smem_plan(w, (int)clampv);
-  // --- scalar setup, replicated per thread (Patch.cpp:218-241) ---
-  const int uc = (int)jb.hu;
-  const int vc = (int)jb.hv;
+// Scalar setup of Patch::findMatch (Patch.cpp:218-246), replicated per thread: the candidate range of the reference's two loops,
+// the ellipse coefficients, and that range clipped to pixels that pass the in-image test.
+struct MatchGeom {
+  int uc, vc, i0, j0, nv, ilo, jlo, cw, ch;
+  float x_2_coeff, y_2_coeff, yx_coeff, sigma_2;
+  bool any;
+};
+__device__ __forceinline__ MatchGeom match_geometry(const MatchJob& jb, int w, float sigma_size, float clampv, int max_grid) {
+  MatchGeom G;
+  const int half = w / 2;
+  G.uc = (int)jb.hu;
+  G.vc = (int)jb.hv;
   double invS[4];
   d_inv2_pplu(jb.S, invS);
-  const float x_2_coeff = (float)invS[0];
-  const float y_2_coeff = (float)invS[3];
-  const float yx_coeff = (float)(2 * invS[2]);
-  const float sigma_2 = sigma_size * sigma_size;
+  G.x_2_coeff = (float)invS[0];
+  G.y_2_coeff = (float)invS[3];
+  G.yx_coeff = (float)(2 * invS[2]);
+  G.sigma_2 = sigma_size * sigma_size;
   float delta_u = (float)(sigma_size * sqrt(jb.S[0]));
   float delta_v = (float)(sigma_size * sqrt(jb.S[3]));
   if (delta_u > clampv) delta_u = clampv;
   if (delta_v > clampv) delta_v = clampv;
   // for (int i = uc - delta_u; i <= uc + delta_u; i++): float arithmetic, truncation toward zero
-  const int i0 = (int)((float)uc - delta_u);
-  const int j0 = (int)((float)vc - delta_v);
-  const float iu_hi = (float)uc + delta_u, jv_hi = (float)vc + delta_v;
+  G.i0 = (int)((float)G.uc - delta_u);
+  G.j0 = (int)((float)G.vc - delta_v);
+  const float iu_hi = (float)G.uc + delta_u, jv_hi = (float)G.vc + delta_v;
   const int i1 = (int)floorf(iu_hi), j1 = (int)floorf(jv_hi);
   // NaN covariance: the loops do not run in the reference (comparisons are false)
   const bool finite_ok = (iu_hi == iu_hi) && (jv_hi == jv_hi) && (delta_u == delta_u) && (delta_v == delta_v);
-  int nv = finite_ok ? (j1 - j0 + 1) : 0;
-  if (nv < 0) nv = 0;
+  G.nv = finite_ok ? (j1 - G.j0 + 1) : 0;
+  if (G.nv < 0) G.nv = 0;
   // clip the candidate range to pixels that pass the in-image test (Patch.cpp:246) so the staged
   // window never leaves the frame; scan order and keys are unaffected.
-  const int ilo = max(i0, half + 1), ihi = min(i1, jb.fw - half - 1);
-  const int jlo = max(j0, half + 1), jhi = min(j1, jb.fh - half - 1);
-  int cw = finite_ok ? ihi - ilo + 1 : 0, ch = finite_ok ? jhi - jlo + 1 : 0;  // valid candidate grid
-  if (cw > pl.side - w + 1) cw = pl.side - w + 1;  // cannot happen for delta <= clamp; keeps smem in bounds
-  if (ch > pl.side - w + 1) ch = pl.side - w + 1;
-  const bool any = cw > 0 && ch > 0;
+  G.ilo = max(G.i0, half + 1);
+  G.jlo = max(G.j0, half + 1);
+  const int ihi = min(i1, jb.fw - half - 1), jhi = min(j1, jb.fh - half - 1);
+  G.cw = finite_ok ? ihi - G.ilo + 1 : 0;
+  G.ch = finite_ok ? jhi - G.jlo + 1 : 0;  // valid candidate grid
+  if (G.cw > max_grid) G.cw = max_grid;  // cannot happen for delta <= clamp; keeps smem in bounds
+  if (G.ch > max_grid) G.ch = max_grid;
+  G.any = G.cw > 0 && G.ch > 0;
+  return G;
+}
+
+// Core search for one feature by one CTA.  All threads must call.
+__device__ MatchResult match_one(const MatchJob& jb, int w, float sigma_size, float clampv, unsigned char* smem_raw,
+                                 unsigned* phase_io = nullptr, bool init_bar = true) {
+  const int tid = threadIdx.x;
+  const int half = w / 2, w2 = w * w;
+  const MatchSmem pl = match_smem_plan(w, (int)clampv);
+  // --- scalar setup, replicated per thread (Patch.cpp:218-241) ---
+  const MatchGeom G = match_geometry(jb, w, sigma_size, clampv, pl.side - w + 1);
+  const int uc = G.uc, vc = G.vc, i0 = G.i0, j0 = G.j0, nv = G.nv, ilo = G.ilo, jlo = G.jlo, cw = G.cw, ch = G.ch;
+  const float x_2_coeff = G.x_2_coeff, y_2_coeff = G.y_2_coeff, yx_coeff = G.yx_coeff, sigma_2 = G.sigma_2;
+  const bool any = G.any;
   const int ww = any ? cw + w - 1 : 0, wh = any ? ch + w - 1 : 0;
   const int wsb = pl.wsb, tw = pl.tw;
 
@@ -220,7 +240,7 @@ __device__ MatchResult match_one(const MatchJob& jb, int w, float sigma_size, fl
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + pl.off_bar);
   const bool use_tma = jb.tmap != nullptr;
   if (tid < 16) red_k[tid] = 0;
-  if (use_tma && tid == 0) mbar_init(bar, 1);
+  if (use_tma && tid == 0 && init_bar) mbar_init(bar, 1);
   __syncthreads();
   uint8_t* raw = smem_raw + pl.off_raw;
   if (use_tma && any && tid == 0) {
@@ -278,7 +298,8 @@ __device__ MatchResult match_one(const MatchJob& jb, int w, float sigma_size, fl
     }
   }
   if (use_tma && any) {
-    mbar_wait(bar, 0);   // every consumer thread observes the completion of the tile load
+    mbar_wait(bar, phase_io ? *phase_io : 0u);   // every consumer thread observes the completion of the tile load
+    if (phase_io) *phase_io ^= 1u;            // a persistent CTA re-uses the barrier: the next load completes the other phase
     // raw box -> window at its own alignment (funnel shift by the 0..15 bytes between the box edge and the window), with the
     // same zero padding as the ordinary-load path: columns past ww and rows from wh on are zero
     const int sh = (ilo - half) & 15, shw = sh >> 2, shb = 8 * (sh & 3), nwords = wsb >> 2;
@@ -511,7 +532,7 @@ static const CUtensorMap& as_cu(const EkfTensorMap& m) { return *reinterpret_cas
 
 // Filter-attached matcher: the loop V:870-880 with one CTA per feature.
 __device__ __forceinline__ void match_filter_feature(FeatTab ft, int f, FrameView fr, const DevCfg& cfg, unsigned char* smem_raw,
-                                                     const CUtensorMap* tmap) {
+                                                     const CUtensorMap* tmap, unsigned* phase_io = nullptr, bool init_bar = true) {
   const int w = cfg.window, w2 = w * w;
   MatchJob jb;
   jb.tmap = tmap; jb.frame_index = 0;
@@ -519,7 +540,7 @@ __device__ __forceinline__ void match_filter_feature(FeatTab ft, int f, FrameVie
   jb.tmpl = ft.mpatch + (size_t)f * cfg.tstride;
   jb.hu = ft.h[2 * f]; jb.hv = ft.h[2 * f + 1];
   for (int c = 0; c < 4; ++c) jb.S[c] = ft.S2[4 * f + c];
-  const MatchResult r = match_one(jb, w, cfg.sigma_size_f, cfg.search_clamp, smem_raw);
+  const MatchResult r = match_one(jb, w, cfg.sigma_size_f, cfg.search_clamp, smem_raw, phase_io, init_bar);
   __syncthreads();
   const bool accept = !(r.best < cfg.ncc_threshold);  // Patch.cpp:278
   if (accept) {
@@ -547,15 +568,256 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_filter(FeatTab ft, int 
   if (f >= N || !ft.innov[f]) return;
   match_filter_feature(ft, f, fr, cfg, smem_raw, use_tma ? &tmap : nullptr);
 }
-// Batched filters (BASELINE config 3): grid = (feature capacity, filters); the frame is shared.
-__global__ void __launch_bounds__(MATCH_THREADS) k_match_filter_batch(FeatTab base, int Ncap, const int* __restrict__ Nper,
-                                                                      FrameView fr, DevCfg cfg,
-                                                                      const __grid_constant__ CUtensorMap tmap, int use_tma) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int f = blockIdx.x, b = blockIdx.y;
+// ------------------------------------------------------------------------------------------------
+// Warp-per-feature path for SMALL search windows (candidate grid <= 16 x 16, template side <= 15): the batched filters
+// (BASELINE config 3) match 4096 x 30 features per step whose converged windows hold ~200 candidates — a 256-thread CTA per
+// feature spends its time in block barriers and idle lanes (4.1 of the 7.5 ms step).  Here one WARP owns a feature: window
+// and template in a private 1.7 KB slice of shared memory, every lane scores up to eight candidates (Stp, P, PP by DP4A on
+// funnel-shifted window words — exact integers, the same ncc* and guard band as match_one), the guard-band candidates take
+// the reference's exact operation sequence on 4-lane groups, and only __syncwarp separates the phases.  Same result bits
+// as match_one by construction: the fast pass only SELECTS the candidates whose exact float score is compared.  A feature
+// with a larger window (or a guard band of more than 16 candidates) is not touched: its index goes to a list that a
+// persistent grid of CTAs works off with match_one.
+// ------------------------------------------------------------------------------------------------
+#define MW_GRID 16
+#define MW_MAXW 15
+#define MW_WARPS 8
+#define MW_ROWS (MW_GRID + MW_MAXW - 1)   // 30 window rows
+#define MW_WS 40                          // window row stride in bytes (30 columns + slack for whole-word reads)
+#define MW_LIST 16
+struct MatchWarpSmem {
+  unsigned win[MW_ROWS * MW_WS / 4];
+  unsigned tpk[MW_MAXW * 4];
+  unsigned char tb[MW_MAXW * MW_MAXW + 15];
+  int list[MW_LIST];
+  int cnt;
+};
+
+// exact score of one candidate on a 4-lane group: match_exact_score4 with da formed on the fly from the template bytes
+__device__ __forceinline__ float match_exact_score4_tb(const unsigned char* tb, double m1, const uint8_t* win, int wsb, int roi, int w,
+                                                       int P, int role, unsigned gmask, int gbase) {
+  const double m2 = __ddiv_rn((double)P, (double)(w * w));
+  double acc = 0;
+  for (int r = 0; r < w; ++r) {
+    const uint8_t* wr = win + roi + r * wsb;
+    const unsigned char* tr = tb + r * w;
+    for (int x = 0; x < w; ++x) {
+      const double a = __dsub_rn((double)(float)tr[x], m1);
+      const double b = __dsub_rn((double)(float)wr[x], m2);
+      const double fa = role == 1 ? b : a, fb = role == 0 ? a : b;
+      acc = __dadd_rn(acc, __dmul_rn(fa, fb));
+    }
+  }
+  const double n1 = __shfl_sync(gmask, acc, gbase), n2 = __shfl_sync(gmask, acc, gbase + 1), corr = __shfl_sync(gmask, acc, gbase + 2);
+  return (float)__ddiv_rn(corr, __dsqrt_rn(__dmul_rn(n2, n1)));
+}
+
+// One warp, one feature.  Returns false (nothing written, nothing decided) when the feature does not fit this path.
+__device__ bool match_one_warp(const MatchJob& jb, int w, float sigma_size, float clampv, MatchWarpSmem& sm, MatchResult& res) {
+  const int lane = threadIdx.x & 31;
+  const int half = w / 2, w2 = w * w, tw = (w + 3) >> 2;
+  const MatchGeom G = match_geometry(jb, w, sigma_size, clampv, 2 * (int)clampv + 1);
+  if (w > MW_MAXW || G.cw > MW_GRID || G.ch > MW_GRID) return false;
+  res.best = -1.0f; res.bi = 0; res.bj = 0;
+  if (!G.any) return true;
+  const int cw = G.cw, ch = G.ch, ww = cw + w - 1, wh = ch + w - 1;
+  uint8_t* win = reinterpret_cast<uint8_t*>(sm.win);
+  // --- template: packed words (zero padded), bytes, T = sum t, TT = sum t^2 ---
+  int T = 0, TT = 0;
+  for (int e = lane; e < w * tw; e += 32) {
+    const int r = e / tw, k4 = (e - r * tw) * 4;
+    unsigned word = 0;
+    for (int c = 0; c < 4; ++c)
+      if (k4 + c < w) {
+        const unsigned v = jb.tmpl[r * w + k4 + c];
+        word |= v << (8 * c);
+        T += (int)v; TT += (int)(v * v);
+      }
+    sm.tpk[e] = word;
+  }
+  for (int e = lane; e < w2; e += 32) sm.tb[e] = jb.tmpl[e];
+  for (int o = 16; o > 0; o >>= 1) { T += __shfl_xor_sync(0xffffffffu, T, o); TT += __shfl_xor_sync(0xffffffffu, TT, o); }
+  // --- window: bytes, columns past ww zero ---
+  {
+    const int x0 = G.ilo - half, y0 = G.jlo - half;
+    const int nwords = MW_WS / 4;
+    if ((((size_t)jb.frame | (size_t)jb.fstride) & 3) == 0) {
+      const int sh = x0 & 3, xa = x0 - sh;
+      for (int e = lane; e < wh * nwords; e += 32) {
+        const int yy = e / nwords, k = e - yy * nwords;
+        const unsigned* srcw = reinterpret_cast<const unsigned*>(jb.frame + (size_t)(y0 + yy) * jb.fstride + xa);
+        unsigned v = 0;
+        if (4 * k < ww) {
+          const int last = min(4 * k + 3, ww - 1);
+          const unsigned lo = srcw[k];
+          const unsigned hi = (sh > 0 && last + sh >= 4 * k + 4) ? srcw[k + 1] : 0u;
+          v = __funnelshift_r(lo, hi, 8 * sh);
+          const int rem = ww - 4 * k;
+          if (rem < 4) v &= (1u << (8 * rem)) - 1u;
+        }
+        sm.win[e] = v;
+      }
+    } else {
+      for (int e = lane; e < wh * MW_WS; e += 32) {
+        const int yy = e / MW_WS, xx = e - yy * MW_WS;
+        win[e] = (xx < ww) ? jb.frame[(size_t)(y0 + yy) * jb.fstride + x0 + xx] : (uint8_t)0;
+      }
+    }
+  }
+  __syncwarp();
+  const double dn = (double)w2;
+  const double m1 = __ddiv_rn((double)T, dn);
+  const double d1 = dn * (double)TT - (double)T * (double)T;   // exact (< 2^53)
+  const double rd1 = (d1 > 0.0) ? rsqrt(d1) : 0.0;
+  const double kNone = -1.0e300;
+  // --- fast pass: ncc* of every in-ellipse candidate; lane -> candidates lane, lane + 32, ... (row-major over the grid) ---
+  const int ncand = cw * ch;
+  const unsigned lastmask = (w & 3) ? ((1u << (8 * (w & 3))) - 1u) : 0xffffffffu;   // bytes of the last template word of a row
+  double sc[8];
+  int Pq[8];
+  double lmax = kNone;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    sc[q] = kNone; Pq[q] = 0;
+    const int c = lane + 32 * q;
+    if (c < ncand) {
+      const int jv = c / cw, iu = c - jv * cw;
+      const float dj = (float)(G.jlo + jv - G.vc);
+      const float ey = __fmul_rn(__fmul_rn(G.y_2_coeff, dj), dj);
+      const float fdi = (float)(G.ilo + iu - G.uc);
+      const float e = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(G.x_2_coeff, fdi), fdi), ey), __fmul_rn(__fmul_rn(G.yx_coeff, fdi), dj));
+      if (e <= G.sigma_2) {
+        unsigned stp = 0, P = 0, PP = 0;
+        const int shb = 8 * (iu & 3);
+        for (int r = 0; r < w; ++r) {
+          const unsigned* wr = sm.win + ((jv + r) * MW_WS + (iu & ~3)) / 4;
+          const unsigned* tr = sm.tpk + r * tw;
+          unsigned lo = wr[0];
+          for (int k = 0; k < tw; ++k) {
+            const unsigned hi = wr[k + 1];
+            unsigned x = __funnelshift_r(lo, hi, shb);
+            if (k == tw - 1) x &= lastmask;
+            stp = __dp4a(x, tr[k], stp);
+            P = __dp4a(x, 0x01010101u, P);
+            PP = __dp4a(x, x, PP);
+            lo = hi;
+          }
+        }
+        Pq[q] = (int)P;
+        const double d2 = dn * (double)PP - (double)P * (double)P;   // exact (< 2^53)
+        if (d1 > 0.0 && d2 > 0.0) {
+          const double num = dn * (double)stp - (double)T * (double)P;
+          const double v = (num * rd1) * rsqrt(d2);
+          sc[q] = v;
+          if (v > lmax) lmax = v;
+        }
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  const double Mstar = lmax;
+  float best = -1.0f;
+  int bestkey = 0x7fffffff;
+  if (Mstar > kNone) {
+    const float fm = fabsf((float)Mstar);
+    const double ulp = (double)(nextafterf(fm, 3.0e38f) - fm);
+    const double thr = Mstar - (2.0 * ulp + 4.0e-12);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (sc[q] >= thr) {
+        const int slot = atomicAdd(&sm.cnt, 1);
+        if (slot < MW_LIST) sm.list[slot] = (lane + 32 * q) | (Pq[q] << 8);
+      }
+    }
+    __syncwarp();
+    const int nlist = sm.cnt;
+    if (nlist > MW_LIST) return false;   // pathological ties: leave it to match_one (nothing has been written)
+    const int role = lane & 3, gbase = lane & ~3;
+    const unsigned gmask = 0xfu << gbase;
+    for (int q0 = 0; q0 < nlist; q0 += 8) {
+      const int q = q0 + (lane >> 2);
+      if (q >= nlist) continue;                         // uniform inside a 4-lane group
+      const int c = sm.list[q] & 255, P = sm.list[q] >> 8;
+      const int jv = c / cw, iu = c - jv * cw;
+      const float s1 = match_exact_score4_tb(sm.tb, m1, win, MW_WS, jv * MW_WS + iu, w, P, role, gmask, gbase);
+      const int key = (G.ilo + iu - G.i0) * G.nv + (G.jlo + jv - G.j0);
+      if (role == 0 && (s1 > best || (s1 == best && key < bestkey))) { best = s1; bestkey = key; }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int ok = __shfl_xor_sync(0xffffffffu, bestkey, o);
+    if (ob > best || (ob == best && ok < bestkey)) { best = ob; bestkey = ok; }
+  }
+  res.best = best;
+  if (bestkey != 0x7fffffff && G.nv > 0) {
+    res.bi = G.i0 + bestkey / G.nv;
+    res.bj = G.j0 + bestkey % G.nv;
+  }
+  return true;
+}
+
+// Batched filters, pass 1: one warp per (filter, feature); features that do not fit go to defer_list.
+__global__ void __launch_bounds__(MW_WARPS * 32) k_match_filter_batch_warp(FeatTab base, int Ncap, const int* __restrict__ Nper, int B,
+                                                                           FrameView fr, DevCfg cfg, int* __restrict__ defer_list,
+                                                                           int* __restrict__ defer_cnt) {
+  __shared__ MatchWarpSmem wsm[MW_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long pair = (long long)blockIdx.x * MW_WARPS + warp;
+  if (pair >= (long long)B * Ncap) return;
+  const int b = (int)(pair / Ncap), f = (int)(pair - (long long)b * Ncap);
   const FeatTab ft = feattab_slice(base, b, Ncap, cfg.tstride);
   if (f >= Nper[b] || !ft.innov[f]) return;
-  match_filter_feature(ft, f, fr, cfg, smem_raw, use_tma ? &tmap : nullptr);
+  const int w = cfg.window, w2 = w * w;
+  MatchJob jb;
+  jb.tmap = nullptr; jb.frame_index = 0;
+  jb.frame = fr.px; jb.fw = fr.w; jb.fh = fr.h; jb.fstride = fr.stride;
+  jb.tmpl = ft.mpatch + (size_t)f * cfg.tstride;
+  jb.hu = ft.h[2 * f]; jb.hv = ft.h[2 * f + 1];
+  for (int c = 0; c < 4; ++c) jb.S[c] = ft.S2[4 * f + c];
+  if (lane == 0) wsm[warp].cnt = 0;
+  __syncwarp();
+  MatchResult r;
+  if (!match_one_warp(jb, w, cfg.sigma_size_f, cfg.search_clamp, wsm[warp], r)) {
+    if (lane == 0) defer_list[atomicAdd(defer_cnt, 1)] = (int)pair;
+    return;
+  }
+  __syncwarp();
+  const bool accept = !(r.best < cfg.ncc_threshold);  // Patch.cpp:278
+  if (accept) {   // matching_patch <- matched ROI (Patch.cpp:285)
+    const int x0 = r.bi - w / 2, y0 = r.bj - w / 2;
+    for (int e = lane; e < w2; e += 32)
+      ft.mpatch[(size_t)f * cfg.tstride + e] = fr.px[(size_t)(y0 + e / w) * fr.stride + x0 + (e % w)];
+  }
+  if (lane == 0) {
+    ft.n_tot[f] += 1;  // Patch.cpp:218
+    ft.last_ncc[f] = r.best;
+    if (!accept) {
+      ft.center[2 * f] = -1.0f; ft.center[2 * f + 1] = -1.0f;
+      ft.innov[f] = 0; ft.li[f] = 0; ft.hi[f] = 0;
+    } else {
+      ft.center[2 * f] = (float)r.bi; ft.center[2 * f + 1] = (float)r.bj;
+      ft.z[2 * f] = (double)(float)r.bi; ft.z[2 * f + 1] = (double)(float)r.bj;
+    }
+  }
+}
+// pass 2: a persistent grid of CTAs works off the deferred (filter, feature) pairs with match_one
+__global__ void __launch_bounds__(MATCH_THREADS) k_match_filter_batch_deferred(FeatTab base, int Ncap, FrameView fr, DevCfg cfg,
+                                                                               const __grid_constant__ CUtensorMap tmap, int use_tma,
+                                                                               const int* __restrict__ defer_list,
+                                                                               const int* __restrict__ defer_cnt) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int n = *defer_cnt;
+  unsigned phase = 0;
+  bool first = true;
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const int pair = defer_list[i];
+    const int b = pair / Ncap, f = pair - b * Ncap;
+    const FeatTab ft = feattab_slice(base, b, Ncap, cfg.tstride);
+    match_filter_feature(ft, f, fr, cfg, smem_raw, use_tma ? &tmap : nullptr, &phase, first);
+    first = false;
+    __syncthreads();
+  }
 }
 
 // Stateless batch (BASELINE config 5): grid = frames x features.
@@ -597,16 +859,22 @@ void launch_match_filter(cudaStream_t st, FeatTab ft, int N, FrameView fr, const
 }
 
 void launch_match_filter_batch(cudaStream_t st, FeatTab base, int Ncap, const int* Nper, int B, FrameView fr, const DevCfg& cfg,
-                               const EkfTensorMap* tmap, long long* launches) {
+                               const EkfTensorMap* tmap, int* defer_list, int* defer_cnt, long long* launches) {
   if (B <= 0 || Ncap <= 0) return;
   static PerDeviceOnce once;   // opt in to the largest supported window once per device
   const size_t smem = match_smem_bytes(cfg.window, cfg.search_clamp);
-  if (once.ensure([] { return cudaFuncSetAttribute(k_match_filter_batch, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)match_smem_bytes(MATCH_MAX_W, 20.0f)); }) != cudaSuccess) return;
+  if (once.ensure([] { return cudaFuncSetAttribute(k_match_filter_batch_deferred, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)match_smem_bytes(MATCH_MAX_W, 20.0f)); }) != cudaSuccess) return;   // the error stays in cudaGetLastError() for the caller
   static const EkfTensorMap none{};
   const EkfTensorMap& tm = (tmap && tmap->ok) ? *tmap : none;
-  k_match_filter_batch<<<dim3(Ncap, B), MATCH_THREADS, smem, st>>>(base, Ncap, Nper, fr, cfg, as_cu(tm), tm.ok);
-  *launches += 1;
+  // pass 1: a warp per (filter, feature) for small windows; pass 2: a persistent grid of CTAs for the deferred rest
+  cudaMemsetAsync(defer_cnt, 0, sizeof(int), st);
+  const long long pairs = (long long)B * Ncap;
+  k_match_filter_batch_warp<<<(unsigned)((pairs + MW_WARPS - 1) / MW_WARPS), MW_WARPS * 32, 0, st>>>(base, Ncap, Nper, B, fr, cfg, defer_list, defer_cnt);
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  k_match_filter_batch_deferred<<<sms * 4, MATCH_THREADS, smem, st>>>(base, Ncap, fr, cfg, as_cu(tm), tm.ok, defer_list, defer_cnt);
+  *launches += 2;
 }
 
 int launch_match_batch(cudaStream_t st, const uint8_t* frames, int n_frames, int width, int height, int stride,

@@ -45,7 +45,7 @@ int main() {
   }
   {
     long long st[16]; cudaMemcpyFromSymbol(st, g_ch_acc, sizeof st);
-    const char* n0[6] = {"load", "wait A", "wait hand-over", "factor+publish", "wait B", "Lout / block copy"};
+    const char* n0[6] = {"load", "wait A", "pivot tile update", "factor+publish", "wait B", "Lout / block copy"};
     const char* n1[6] = {"load", "wait prologue", "dump panel tiles", "wait A (solvers)", "trailing update", "wait end bar"};
     printf("  warp0 inside factor: load+numeric %lld cyc, publish %lld cyc\n", st[6], st[7]);
     for (int i = 0; i < 6; ++i) printf("  warp0 %-28s %8lld cyc   | warp1 %-18s %8lld cyc\n", n0[i], st[i], n1[i], st[8 + i]);
