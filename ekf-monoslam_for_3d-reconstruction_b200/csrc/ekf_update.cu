@@ -18,6 +18,7 @@
 #include "ekf_kernels.h"
 #include "ekf_math.cuh"
 #include "ekf_cta.cuh"
+#include "ekf_factor.cuh"
 
 
 // ------------------------------------------------------------------------------------------------
@@ -412,6 +413,112 @@ __global__ void __launch_bounds__(EKF_UB) k_blk_S(const double* __restrict__ W, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// K4b(1'): S_b = H_b W'_b + sigma_px^2 I - G G^T for the factor-beside-downdate schedule, tiled.  k_blk_S forms the G G^T term
+// with one thread per entry streaming a whole row of G (128 KB per CTA, 32-byte sectors half used: 16 us on the critical chain
+// of every block).  Here one CTA owns a 32 x 32 block of the LOWER triangle (10 CTAs; the factor kernels read nothing else):
+// the two 32-row slabs of G it needs are staged in shared memory with coalesced 16-byte loads and multiplied on the tensor pipe
+// (DMMA.8x8x4, each warp an 8 x 32 strip), and the gather H_b W'_b (13 rows of W' per measurement row) lands directly in the
+// accumulator layout.  CTA (0, 0) also forms nu_b = (z - h) - H_b delta.
+// ------------------------------------------------------------------------------------------------
+#define S2_LD (EKF_UB + 4)   // shared-memory row stride of a G slab: fragment loads (8 rows x 4 columns) hit every bank pair twice
+__global__ void __launch_bounds__(128) k_blk_S_tiled(const double* __restrict__ W, FeatTab ft, int f0, int cnt, double sigma_pixel_2,
+                                                     double* __restrict__ Sb, const double* __restrict__ delta, double* __restrict__ nu,
+                                                     const double* __restrict__ Gsub) {
+  extern __shared__ __align__(16) double s2sm[];
+  // lower-triangle block index -> (bi, bj), bi >= bj, 4 x 4 blocks of 32
+  int bi = 0, rem = blockIdx.x;
+  while (rem > bi) { rem -= bi + 1; ++bi; }
+  const int bj = rem;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+  const int nb = min(EKF_UB / 2, cnt - f0), kr = 2 * nb;
+  double* Ga = s2sm;                    // rows 32 bi .. of G
+  double* Gb = s2sm + 32 * S2_LD;       // rows 32 bj .. of G
+  if (Gsub) {
+    // both slabs with cp.async, every 16-byte copy of a thread in flight at once (a load -> store loop paid the L2 latency
+    // 32 times in a row: 10 of the kernel's 14 us under ncu); the gather below runs while they land
+    for (int e = tid; e < 32 * (EKF_UB / 2); e += 128) {
+      const int r = e / (EKF_UB / 2), c = (e % (EKF_UB / 2)) * 2;
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(Ga + r * S2_LD + c), sb = (unsigned)__cvta_generic_to_shared(Gb + r * S2_LD + c);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(Gsub + (size_t)(32 * bi + r) * EKF_UB + c));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sb), "l"(Gsub + (size_t)(32 * bj + r) * EKF_UB + c));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  }
+  // gather part, straight into the accumulator layout: lane (g, t4) of warp q holds row 32 bi + 8 q + g, columns 32 bj + 8 ct + 2 t4 (+1)
+  const int r = 32 * bi + 8 * warp + g;
+  double acc[4][2];
+#pragma unroll
+  for (int ct = 0; ct < 4; ++ct) { acc[ct][0] = 0.0; acc[ct][1] = 0.0; }
+  if (r < kr) {
+    const int f = ft.sel[f0 + (r >> 1)];
+    const int pos = ft.pos[f], nd = 7 + (ft.coding[f] ? 3 : 6);
+    const double* hc = ft.Hc + 26 * f + 13 * (r & 1);
+    double hv[13];
+#pragma unroll
+    for (int c = 0; c < 13; ++c) hv[c] = (c < nd) ? hc[c] : 0.0;
+    // 13 x 4 independent 16-byte loads per lane, issued before the first use (unrolled: one L2 latency, not thirteen)
+#pragma unroll
+    for (int c = 0; c < 13; ++c) {
+      const double* wrow = W + (size_t)ekf_idx13(c < nd ? c : 0, pos) * EKF_UB + 32 * bj + 2 * t4;
+      double2 v[4];
+#pragma unroll
+      for (int ct = 0; ct < 4; ++ct) v[ct] = *reinterpret_cast<const double2*>(wrow + 8 * ct);
+#pragma unroll
+      for (int ct = 0; ct < 4; ++ct) {
+        if (c < nd) { acc[ct][0] += hv[c] * v[ct].x; acc[ct][1] += hv[c] * v[ct].y; }
+      }
+    }
+  }
+#pragma unroll
+  for (int ct = 0; ct < 4; ++ct) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int sc = 32 * bj + 8 * ct + 2 * t4 + u;
+      // rows / columns past the block's measurements: identity (they contribute nothing downstream)
+      if (r >= kr || sc >= kr) acc[ct][u] = (r == sc) ? 1.0 : 0.0;
+      else if (r == sc) acc[ct][u] += sigma_pixel_2;
+    }
+  }
+  if (Gsub) {
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+    const double* ga = Ga + (8 * warp + g) * S2_LD + t4;
+    double e[4][2];
+#pragma unroll
+    for (int ct = 0; ct < 4; ++ct) { e[ct][0] = 0.0; e[ct][1] = 0.0; }
+#pragma unroll 8
+    for (int k4 = 0; k4 < EKF_UB / 4; ++k4) {
+      const double a = -ga[4 * k4];
+#pragma unroll
+      for (int ct = 0; ct < 4; ++ct) dmma884f(e[ct][0], e[ct][1], a, Gb[(8 * ct + g) * S2_LD + 4 * k4 + t4]);
+    }
+#pragma unroll
+    for (int ct = 0; ct < 4; ++ct)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int sc = 32 * bj + 8 * ct + 2 * t4 + u;
+        if (r < kr && sc < kr) acc[ct][u] += e[ct][u];
+      }
+  }
+#pragma unroll
+  for (int ct = 0; ct < 4; ++ct)
+    *reinterpret_cast<double2*>(Sb + (size_t)r * EKF_UB + 32 * bj + 8 * ct + 2 * t4) = make_double2(acc[ct][0], acc[ct][1]);
+  if (nu && blockIdx.x == 0) {
+    const int s = tid;
+    double out = 0.0;
+    if (s < kr) {
+      const int f = ft.sel[f0 + (s >> 1)];
+      const int pos = ft.pos[f], nd = 7 + (ft.coding[f] ? 3 : 6);
+      const double* hc = ft.Hc + 26 * f + 13 * (s & 1);
+      double hd = 0;
+      for (int c = 0; c < nd; ++c) hd += hc[c] * delta[ekf_idx13(c, pos)];
+      out = (ft.z[2 * f + (s & 1)] - ft.h[2 * f + (s & 1)]) - hd;
+    }
+    nu[s] = out;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // forsePlane (V:1245-1263, 1272): three pseudo-measurements mu[1] = mu[4] = mu[6] = 0 with R = 1e-5 I3,
 // appended to the second stacked update.  Handled as one more 128-row block whose first three rows are
 // the unit rows e1, e4, e6: W[:, j] = Sigma[:, k_j], nu_j = -(mu[k_j] + delta[k_j]), S = that 3x3 block of
@@ -611,6 +718,8 @@ int update_kernels_init() {
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_blk_factor_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFactSmemOld);
   if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_blk_S_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 32 * S2_LD * sizeof(double)));
+  if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_blk_factor_p2p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFactSmem);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_blk_V, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVSmem);
@@ -664,7 +773,9 @@ void launch_blk_S_nu(cudaStream_t st, const double* W, FeatTab ft, int f0, int c
 // S_b from the uncorrected gather and G (see k_blk_S), and the gather with a second copy of W'
 void launch_blk_S_nu_G(cudaStream_t st, const double* Wraw, FeatTab ft, int f0, int cnt, const DevCfg& cfg, const double* delta,
                        const double* G, double* Sb, double* nu, long long* launches) {
-  k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(Wraw, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, delta, nu, G);
+  static const bool legacy = [] { const char* e = getenv("EKF_S_TILED"); return e && atoi(e) == 0; }();
+  if (legacy) k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(Wraw, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, delta, nu, G);
+  else k_blk_S_tiled<<<10, 128, 2 * 32 * S2_LD * sizeof(double), st>>>(Wraw, ft, f0, cnt, cfg.sigma_pixel_2, Sb, delta, nu, G);
   *launches += 1;
 }
 void launch_blk_gather2(cudaStream_t st, const double* Sigma, int ld, int n, FeatTab ft, int f0, int cnt, double* W, double* W2,
