@@ -295,10 +295,16 @@ __global__ void k_p2p_wait(const unsigned long long* local_flags, int slot0, int
 // K4a: W_b = Sigma H_b^T for the block of <= 64 selected features starting at sel[f0]
 // (n x EKF_UB, row-major), and nu_b = (z - h) - H_b delta.  One pass over the needed columns of Sigma.
 // ------------------------------------------------------------------------------------------------
-#define GATHER_ROWS 4
+// rows of Sigma per CTA.  Every CTA first stages the block's 64 x 26 measurement Jacobians (13 KB), so more rows per CTA would
+// amortise that — measured the other way round (cfg2, frames/s): 4 rows 1 270, 8 rows 1 264, 16 rows 1 237, 32 rows 1 196: the
+// kernel lives on parallelism (754 CTAs at n = 3014), not on the staging.  EKF_GATHER_ROWS overrides (multiple of 4).
+static int gather_rows() {
+  static const int v = [] { const char* e = getenv("EKF_GATHER_ROWS"); const int r = e ? atoi(e) : 4; return (r >= 4 && r % 4 == 0) ? r : 4; }();
+  return v;
+}
 __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ Sigma, int ld, int row0, int n, FeatTab ft, int f0,
                                                     int cnt, const double* __restrict__ delta, double* __restrict__ W,
-                                                    double* __restrict__ nu, double* __restrict__ W2) {
+                                                    double* __restrict__ nu, double* __restrict__ W2, int rows_per_cta) {
   __shared__ double Hs[EKF_UB / 2][27];
   __shared__ int poss[EKF_UB / 2], nds[EKF_UB / 2], fids[EKF_UB / 2];
   const int nb = min(EKF_UB / 2, cnt - f0);
@@ -316,8 +322,9 @@ __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ S
   }
   __syncthreads();
   const int a = tid & (EKF_UB / 2 - 1), rl = tid / (EKF_UB / 2);
-  const int rows_per_cta = GATHER_ROWS, rstep = 256 / (EKF_UB / 2);
+  const int rstep = 256 / (EKF_UB / 2);
   const int pos = poss[a], nd = nds[a];
+#pragma unroll 2
   for (int rq = rl; rq < rows_per_cta; rq += rstep) {
     const int i = row0 + blockIdx.x * rows_per_cta + rq;   // rows [row0, n): the caller's row block
     if (i >= n) break;
@@ -755,7 +762,8 @@ void launch_hi_rescue(cudaStream_t st, const double* Sigma, int ld, const double
 void launch_blk_gather(cudaStream_t st, const double* Sigma, int ld, int row0, int row1, FeatTab ft, int f0, int cnt,
                        const double* delta, double* W, double* nu, long long* launches) {
   const int nr = row1 > row0 ? row1 - row0 : 1;   // at least one CTA: block 0 also forms nu
-  k_blk_gather<<<(nr + GATHER_ROWS - 1) / GATHER_ROWS, 256, 0, st>>>(Sigma, ld, row0, row1, ft, f0, cnt, delta, W, nu, nullptr);
+  const int gr = gather_rows();
+  k_blk_gather<<<(nr + gr - 1) / gr, 256, 0, st>>>(Sigma, ld, row0, row1, ft, f0, cnt, delta, W, nu, nullptr, gr);
   *launches += 1;
 }
 void launch_blk_factor(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const double* nu, const DevCfg& cfg,
@@ -781,7 +789,8 @@ void launch_blk_S_nu_G(cudaStream_t st, const double* Wraw, FeatTab ft, int f0, 
 void launch_blk_gather2(cudaStream_t st, const double* Sigma, int ld, int n, FeatTab ft, int f0, int cnt, double* W, double* W2,
                         long long* launches) {
   const int nr = n > 0 ? n : 1;
-  k_blk_gather<<<(nr + GATHER_ROWS - 1) / GATHER_ROWS, 256, 0, st>>>(Sigma, ld, 0, n, ft, f0, cnt, nullptr, W, nullptr, W2);
+  const int gr = gather_rows();
+  k_blk_gather<<<(nr + gr - 1) / gr, 256, 0, st>>>(Sigma, ld, 0, n, ft, f0, cnt, nullptr, W, nullptr, W2, gr);
   *launches += 1;
 }
 void launch_blk_G(cudaStream_t st, const double* Vprev, FeatTab ft, int f0, int cnt, double* G, long long* launches) {
