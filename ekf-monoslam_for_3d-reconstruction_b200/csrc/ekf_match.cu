@@ -71,16 +71,21 @@ __host__ __device__ inline MatchSmem match_smem_plan(int w, int cl) {
   p.off_tb = o; o += (size_t)((w * w + 15) & ~15);                            // template bytes
   o = (o + 15) & ~(size_t)15;
   p.off_win = o; o += (size_t)(p.side + 1) * p.wsb;                           // u8 window (+1 spare row)
+  // One region, three tenants with disjoint lifetimes (a block barrier between each hand-over): the raw TMA box (until the
+  // window is re-aligned), the horizontal box sums (until the vertical pass is done), the ncc* scores (fast pass onwards).
+  // Overlaying them takes the CTA from 48 to 32 KB at w = 11, clamp 20: 7 instead of 4 resident CTAs per SM.
   o = (o + 127) & ~(size_t)127;                                               // TMA destination: 128-byte aligned
-  p.off_raw = o; o += (size_t)p.side * p.rawb;                                // raw TMA box: side rows x rawb bytes
-  o = (o + 15) & ~(size_t)15;
   const size_t nh = (size_t)p.side * (2 * cl + 1);                            // horizontal sums: window rows x candidate columns
-  p.off_h1 = o; o += ((nh * 2 + 15) & ~(size_t)15);                           // u16: sum of w pixels
-  p.off_h2 = o; o += nh * 4;                                                  // u32: sum of w squares
+  const size_t raw_bytes = (size_t)p.side * p.rawb;                           // raw TMA box: side rows x rawb bytes
+  const size_t h1_bytes = (nh * 2 + 15) & ~(size_t)15, h2_bytes = nh * 4;     // u16 sum of w pixels, u32 sum of w squares
+  const size_t score_bytes = (size_t)p.ncmax * 8;                             // ncc* per candidate
+  size_t ubytes = raw_bytes > h1_bytes + h2_bytes ? raw_bytes : h1_bytes + h2_bytes;
+  if (score_bytes > ubytes) ubytes = score_bytes;
+  p.off_raw = o; p.off_h1 = o; p.off_h2 = o + h1_bytes; p.off_score = o;
+  o += (ubytes + 15) & ~(size_t)15;
   p.off_b1 = o; o += (size_t)p.ncmax * 4;                                     // P  = sum p   over w x w, per candidate
   p.off_b2 = o; o += (size_t)p.ncmax * 4;                                     // PP = sum p^2 over w x w, per candidate
   o = (o + 7) & ~(size_t)7;
-  p.off_score = o; o += (size_t)p.ncmax * 8;                                  // ncc* per candidate
   p.off_list = o; o += (size_t)MATCH_LIST * 4;                                // guard-band candidate keys
   o = (o + 7) & ~(size_t)7;
   p.off_red = o; o += 16 * sizeof(double) + 16 * sizeof(float) + 16 * sizeof(int);
@@ -247,6 +252,7 @@ __device__ MatchResult match_one(const MatchJob& jb, int w, float sigma_size, fl
     // ONE tile load per feature: the box is `side` rows of rawb bytes whose left edge is the 16-byte boundary at or left of
     // the window (the copy engine needs the innermost coordinate 16-byte aligned: tools/tma_probe2.cu); bytes outside the
     // frame arrive as zeros.  The box lands in `raw` while the CTA packs the template below.
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the box region was last touched by ordinary accesses (scores of the previous feature)
     mbar_expect_tx(bar, (unsigned)(pl.rawb * pl.side));
     tma_load_3d(raw, jb.tmap, (ilo - half) & ~15, jlo - half, jb.frame_index, bar);
   }
@@ -873,7 +879,12 @@ void launch_match_filter_batch(cudaStream_t st, FeatTab base, int Ncap, const in
   k_match_filter_batch_warp<<<(unsigned)((pairs + MW_WARPS - 1) / MW_WARPS), MW_WARPS * 32, 0, st>>>(base, Ncap, Nper, B, fr, cfg, defer_list, defer_cnt);
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  k_match_filter_batch_deferred<<<sms * 4, MATCH_THREADS, smem, st>>>(base, Ncap, fr, cfg, as_cu(tm), tm.ok, defer_list, defer_cnt);
+  int per_sm = 4;   // persistent grid: as many CTAs as are resident at this shared-memory footprint
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_match_filter_batch_deferred, MATCH_THREADS, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 4;
+  }
+  k_match_filter_batch_deferred<<<sms * per_sm, MATCH_THREADS, smem, st>>>(base, Ncap, fr, cfg, as_cu(tm), tm.ok, defer_list, defer_cnt);
   *launches += 2;
 }
 
