@@ -73,6 +73,7 @@ SIGNATURES = {
     "ekf_batch_get_feature": (_i, [_vp, _i, _i, _P(_abi.EkfFeatureInfo)]),
     "ekf_batch_kernel_launches": (C.c_int64, [_vp]),
     "ekf_batch_last_step_ms": (_i, [_vp, _vp]),
+    "ekf_batch_last_match_deferred": (_i, [_vp]),
     "ekf_dist_load_nccl": (_i, [C.c_char_p]),
     "ekf_dist_unique_id": (_i, [_vp]),
     "ekf_dist_attach": (_i, [_vp, _vp, _i, _i]),

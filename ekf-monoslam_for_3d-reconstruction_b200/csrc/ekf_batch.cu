@@ -961,4 +961,14 @@ int ekf_batch_last_step_ms(ekf_batch* b, float out[3]) {
   return EKF_OK;
 }
 
+int ekf_batch_last_match_deferred(ekf_batch* b) {
+  if (!b) return EKF_ERR_ARG;
+  if (cudaSetDevice(b->device) != cudaSuccess) return EKF_ERR_CUDA;
+  int v = 0;
+  if (cudaMemcpyAsync(&v, b->match_defer + (size_t)b->B * b->Ncap, sizeof(int), cudaMemcpyDeviceToHost, b->stream) != cudaSuccess ||
+      cudaStreamSynchronize(b->stream) != cudaSuccess)
+    return EKF_ERR_CUDA;
+  return v;
+}
+
 }  // extern "C"

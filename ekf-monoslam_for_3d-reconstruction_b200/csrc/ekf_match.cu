@@ -766,7 +766,7 @@ __device__ bool match_one_warp(const MatchJob& jb, int w, float sigma_size, floa
 // Batched filters, pass 1: one warp per (filter, feature); features that do not fit go to defer_list.
 __global__ void __launch_bounds__(MW_WARPS * 32) k_match_filter_batch_warp(FeatTab base, int Ncap, const int* __restrict__ Nper, int B,
                                                                            FrameView fr, DevCfg cfg, int* __restrict__ defer_list,
-                                                                           int* __restrict__ defer_cnt) {
+                                                                           int* __restrict__ defer_cnt, int warp_path) {
   __shared__ MatchWarpSmem wsm[MW_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long pair = (long long)blockIdx.x * MW_WARPS + warp;
@@ -784,7 +784,7 @@ __global__ void __launch_bounds__(MW_WARPS * 32) k_match_filter_batch_warp(FeatT
   if (lane == 0) wsm[warp].cnt = 0;
   __syncwarp();
   MatchResult r;
-  if (!match_one_warp(jb, w, cfg.sigma_size_f, cfg.search_clamp, wsm[warp], r)) {
+  if (!warp_path || !match_one_warp(jb, w, cfg.sigma_size_f, cfg.search_clamp, wsm[warp], r)) {
     if (lane == 0) defer_list[atomicAdd(defer_cnt, 1)] = (int)pair;
     return;
   }
@@ -876,7 +876,9 @@ void launch_match_filter_batch(cudaStream_t st, FeatTab base, int Ncap, const in
   // pass 1: a warp per (filter, feature) for small windows; pass 2: a persistent grid of CTAs for the deferred rest
   cudaMemsetAsync(defer_cnt, 0, sizeof(int), st);
   const long long pairs = (long long)B * Ncap;
-  k_match_filter_batch_warp<<<(unsigned)((pairs + MW_WARPS - 1) / MW_WARPS), MW_WARPS * 32, 0, st>>>(base, Ncap, Nper, B, fr, cfg, defer_list, defer_cnt);
+  static const int warp_path = [] { const char* e = getenv("EKF_MATCH_WARP"); return e ? atoi(e) : 1; }();   // 0: every feature takes the CTA matcher (A/B timing, tests)
+  k_match_filter_batch_warp<<<(unsigned)((pairs + MW_WARPS - 1) / MW_WARPS), MW_WARPS * 32, 0, st>>>(base, Ncap, Nper, B, fr, cfg, defer_list, defer_cnt,
+                                                                                                     warp_path);
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int per_sm = 4;   // persistent grid: as many CTAs as are resident at this shared-memory footprint

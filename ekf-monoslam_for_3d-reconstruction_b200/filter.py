@@ -370,6 +370,10 @@ class FilterBatch:
     def kernel_launches(self):
         return int(self.L.ekf_batch_kernel_launches(self.h))
 
+    def last_match_deferred(self):
+        """(filter, feature) pairs of the last step that the warp-per-feature matcher left to the CTA matcher."""
+        return self._ck(self.L.ekf_batch_last_match_deferred(self.h))
+
     def last_step_ms(self):
         out = np.zeros(3, dtype=np.float32)
         self._ck(self.L.ekf_batch_last_step_ms(self.h, _ptr(out)))

@@ -266,6 +266,9 @@ int ekf_batch_get_feature(ekf_batch* b, int filter, int idx, ekf_feature_info* o
 int64_t ekf_batch_kernel_launches(const ekf_batch* b);
 /* CUDA-event time (ms) of the three kernel classes of the last step: predict, match, update. */
 int ekf_batch_last_step_ms(ekf_batch* b, float out[3]);
+/* Matcher of the last step: number of (filter, feature) pairs whose search window did not fit the warp-per-feature path
+ * (candidate grid > 16 x 16 or template side > 15) and were matched by the CTA-per-feature kernel instead.  Diagnostic. */
+int ekf_batch_last_match_deferred(ekf_batch* b);
 
 /* ---- large map split across GPUs (BASELINE config 4) ------------------------------------------- */
 /* One process per GPU, each with its own ekf_handle holding a replica of the same filter (same calls

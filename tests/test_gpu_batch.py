@@ -9,10 +9,10 @@ from helpers import INT_FIELDS, TOL, make_pair, relerr, seed_features
 pytestmark = pytest.mark.gpu
 
 
-def _ensemble(pkg, orc, sc, B, seed, perturb=2e-3):
+def _ensemble(pkg, orc, sc, B, seed, perturb=2e-3, **cfg_over):
     """A seeded single GPU filter, a batch cloned from it, and B oracle filters holding the same
     per-hypothesis perturbed camera states."""
-    g, o0 = make_pair(pkg, orc, sc)
+    g, o0 = make_pair(pkg, orc, sc, **cfg_over)
     seed_features(g, sc); seed_features(o0, sc)
     cfg = g.cfg
     batch = pkg.FilterBatch(cfg, B, feature_capacity=min(32, sc.n_features + 2))
@@ -105,3 +105,29 @@ def test_batch_capacity_and_errors(gpu_pkg):
     assert (d.n_filters, d.feature_capacity, d.state_capacity) == (4, 8, 14 + 48)
     with pytest.raises(gpu_pkg.EkfError):
         b.step()   # not seeded
+
+
+def test_small_windows_take_the_warp_matcher(gpu_pkg, orc):
+    """Tight process noise and a sharp depth prior shrink the 3-sigma search ellipses to a few pixels: every feature fits the
+    warp-per-feature matcher (candidate grid <= 16 x 16) and none is deferred to the CTA matcher; results stay bit-exact
+    against the oracle.  With the default noise the same scene defers everything (windows clamp at 41 x 41)."""
+    small = dict(sigma_vx=1e-4, sigma_vy=1e-4, sigma_vz=1e-4, sigma_wx=1e-4, sigma_wy=1e-4, sigma_wz=1e-4, sigma_rho_0=1e-5, sigma_size=2)
+    sc = gpu_pkg.synth.Scene(n_features=24, n_frames=5, seed=411, speed=0.05, omega=0.01, accel_sigma=1e-4)
+    g, batch, oracles = _ensemble(gpu_pkg, orc, sc, 4, seed=9, perturb=1e-5, **small)
+    for t in range(1, sc.n_frames):
+        img = sc.frame(t); picks = sc.picks(t, 24)
+        for b, o in enumerate(oracles):
+            if batch.numOfFeatures(b) == o.numOfFeatures():
+                batch.set_full(b, *o.get_full())
+        batch.captureNewFrame(img, sc.stamps[t])
+        batch.step(picks)
+        assert batch.last_match_deferred() == 0, f"frame {t}: {batch.last_match_deferred()} features left the warp path"
+        for o in oracles:
+            o.captureNewFrame(img, sc.stamps[t]); o.predict(); o.update(picks)
+        _check(batch, oracles, f"small windows frame {t}")
+    mu, st = batch.camera_states()
+    assert (st[:, 1] > 0).all(), "features must actually match in this scene"
+    # control: the default noise model opens the windows to the 20 px clamp and everything is deferred
+    g2, batch2, _ = _ensemble(gpu_pkg, orc, sc, 2, seed=9, perturb=1e-5)
+    batch2.captureNewFrame(sc.frame(1), sc.stamps[1]); batch2.step(sc.picks(1, 24))
+    assert batch2.last_match_deferred() > 0
