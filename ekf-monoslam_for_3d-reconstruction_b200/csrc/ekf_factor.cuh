@@ -355,3 +355,63 @@ __device__ __forceinline__ double warp_trsm_tile(double* Wt, int ldw, const doub
   }
   return part;
 }
+
+// The same solve with L stored PACKED: block row J (rows 32 J .. 32 J + 31, columns 0 .. 32 J - 1: all the solve reads of it) at
+// Lj[J] with row stride ldj[J] — 49 KB instead of 135 KB at NB = 128.
+// V = W L^-T for one 8-row tile owned by ONE warp, in place in shared memory (blocked triangular solve):
+//   for J = 0 .. NB/32-1:  T_J = W_J - sum_{P<J} X_P L_JP^T ;  X_J = T_J Dinv_J^T
+// Wt: the tile's rows (row stride ldw, NB columns); L: NB x NB lower (stride ldl); D: blocks of 32 x 32
+// (row stride ldd inside a block, block stride 32 * ldd).  All operands in shared memory.
+// Returns, per thread, the partial dot products of its row (lane / 4) with y over its columns.
+template <int NB>
+__device__ __forceinline__ double warp_trsm_tile_packed(double* Wt, int ldw, const double* const (&Lj)[NB / 32], const int (&ldj)[NB / 32],
+                                                        const double* D, int ldd, const double* y) {
+  constexpr int NP = NB / 32;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  double part = 0.0;
+#pragma unroll
+  for (int J = 0; J < NP; ++J) {
+    double t[4][2];  // T_J: 4 column tiles of 8
+#pragma unroll
+    for (int ct = 0; ct < 4; ++ct) {
+      const double2 v = *reinterpret_cast<const double2*>(Wt + (size_t)g * ldw + 32 * J + 8 * ct + 2 * t4);
+      t[ct][0] = v.x; t[ct][1] = v.y;
+    }
+    // The result latency of DMMA.8x8x4 is ~150 cycles: two accumulator sets (even / odd k-steps) per column tile keep
+    // eight independent chains in flight instead of four.
+    double t2[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+    for (int kq = 0; kq < 8 * J; kq += 2) {   // K = 32 J: columns already solved
+      const double a0 = -Wt[(size_t)g * ldw + 4 * kq + t4], a1 = -Wt[(size_t)g * ldw + 4 * kq + 4 + t4];
+#pragma unroll
+      for (int ct = 0; ct < 4; ++ct) {
+        dmma884f(t[ct][0], t[ct][1], a0, Lj[J][(size_t)(8 * ct + g) * ldj[J] + 4 * kq + t4]);
+        dmma884f(t2[ct][0], t2[ct][1], a1, Lj[J][(size_t)(8 * ct + g) * ldj[J] + 4 * kq + 4 + t4]);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int ct = 0; ct < 4; ++ct)
+      *reinterpret_cast<double2*>(Wt + (size_t)g * ldw + 32 * J + 8 * ct + 2 * t4) = make_double2(t[ct][0] + t2[ct][0], t[ct][1] + t2[ct][1]);
+    __syncwarp();
+    // X_J = T_J Dinv_J^T (Dinv lower triangular: column tile ct needs k < 8 ct + 8)
+    double af[8];
+#pragma unroll
+    for (int kq = 0; kq < 8; ++kq) af[kq] = Wt[(size_t)g * ldw + 32 * J + 4 * kq + t4];
+    __syncwarp();
+    const double* Dj = D + (size_t)J * 32 * ldd;
+#pragma unroll
+    for (int ct = 0; ct < 4; ++ct) {
+      double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;   // 2 ct + 2 k-steps: always even
+#pragma unroll
+      for (int kq = 0; kq < 2 * ct + 2; kq += 2) {
+        dmma884f(d0, d1, af[kq], Dj[(size_t)(8 * ct + g) * ldd + 4 * kq + t4]);
+        dmma884f(e0, e1, af[kq + 1], Dj[(size_t)(8 * ct + g) * ldd + 4 * kq + 4 + t4]);
+      }
+      d0 += e0; d1 += e1;
+      *reinterpret_cast<double2*>(Wt + (size_t)g * ldw + 32 * J + 8 * ct + 2 * t4) = make_double2(d0, d1);
+      part += d0 * y[32 * J + 8 * ct + 2 * t4] + d1 * y[32 * J + 8 * ct + 2 * t4 + 1];
+    }
+    __syncwarp();
+  }
+  return part;
+}

@@ -605,12 +605,19 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_blk_factor_p2p(const double* 
 #define VT_THREADS 256   // 8 warps stage the operands; warps 0..3 each own one 8-row tile of the solve
 #define VT_LD (EKF_UB + 4)
 #define VT_LDD 36
-__global__ void __launch_bounds__(VT_THREADS) k_blk_V(double* __restrict__ W, int rbase, int n, const double* __restrict__ Lg,
+// L in shared memory PACKED: the solve reads of block row J (rows 32 J ..) only columns 0 .. 32 J - 1, stored with row stride
+// 32 J + 4 (fragment loads stay conflict-free: stride = 4 mod 16 doubles).  121 KB per CTA instead of 207 KB and <= 64 registers
+// per thread: a CTA now fits into what ONE retiring downdate CTA leaves behind (the downdate runs 4 CTAs x 16 K registers x
+// 20 KB per SM) instead of waiting for the downdate's last wave to drain.
+#define VT_LPACK (32 * 36 + 32 * 68 + 32 * 100)   // doubles: block rows 1, 2, 3
+__global__ void __launch_bounds__(VT_THREADS, 4) k_blk_V(double* __restrict__ W, int rbase, int n, const double* __restrict__ Lg,
                                                       const double* __restrict__ Dg, const double* __restrict__ yg,
                                                       double* __restrict__ delta, P2PView pv = P2PView{}, unsigned int* ticket = nullptr) {
   extern __shared__ __align__(16) double vsm[];
-  double* Ls = vsm;                          // [EKF_UB][VT_LD]  L (lower)
-  double* Ds = Ls + EKF_UB * VT_LD;          // [EKF_UB / 32][32][VT_LDD] inverses of the diagonal blocks
+  double* Lst = vsm;                         // packed block rows 1 .. 3 of L
+  const double* const Lj[4] = {Lst, Lst, Lst + 32 * 36, Lst + 32 * 36 + 32 * 68};   // block row 0 is never read
+  const int ldj[4] = {36, 36, 68, 100};
+  double* Ds = Lst + VT_LPACK;               // [EKF_UB / 32][32][VT_LDD] inverses of the diagonal blocks
   double* Ws = Ds + (EKF_UB / 32) * 32 * VT_LDD;  // [VT_ROWS][VT_LD] W rows, then V rows
   double* ys = Ws + VT_ROWS * VT_LD;         // [EKF_UB]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -633,14 +640,18 @@ __global__ void __launch_bounds__(VT_THREADS) k_blk_V(double* __restrict__ W, in
   }
   for (int e = tid; e < (EKF_UB - 32) * (EKF_UB - 32) / 2; e += VT_THREADS) {
     const int r = 32 + e / ((EKF_UB - 32) / 2), c = (e % ((EKF_UB - 32) / 2)) * 2;
-    if (c < (r & ~31)) cp16(Ls + r * VT_LD + c, Lg + r * EKF_UB + c);
+    if (c < (r & ~31)) {
+      const int J = r >> 5;                                  // 1 .. 3 (arithmetic, not Lj[J]: keeps the tables in registers)
+      const int offJ = J == 1 ? 0 : (J == 2 ? 32 * 36 : 32 * 36 + 32 * 68);
+      cp16(Lst + offJ + (r & 31) * (32 * J + 4) + c, Lg + r * EKF_UB + c);
+    }
   }
   asm volatile("cp.async.commit_group;\n" ::);
   for (int e = tid; e < EKF_UB; e += VT_THREADS) ys[e] = yg[e];
   asm volatile("cp.async.wait_group 0;\n" ::);
   __syncthreads();
   if (warp < VT_ROWS / 8) {
-    double part = warp_trsm_tile<EKF_UB>(Ws + (size_t)warp * 8 * VT_LD, VT_LD, Ls, VT_LD, Ds, VT_LDD, ys);
+    double part = warp_trsm_tile_packed<EKF_UB>(Ws + (size_t)warp * 8 * VT_LD, VT_LD, Lj, ldj, Ds, VT_LDD, ys);
     part += __shfl_xor_sync(0xffffffffu, part, 1);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
     const int i = row0 + warp * 8 + (lane >> 2);
@@ -716,7 +727,7 @@ __global__ void __launch_bounds__(256) k_bookkeeping(const double* __restrict__ 
 static const size_t kFactSmemOld = (size_t)cta_chol_panel_smem_doubles<EKF_UB>() * sizeof(double);
 static const size_t kFactSmem = sizeof(Chol128Smem);
 static int g_chol_smem = 0;   // EKF_CHOL_SMEM=1: the round-1 shared-memory factor kernel
-static const size_t kVSmem = (size_t)(EKF_UB * VT_LD + (EKF_UB / 32) * 32 * VT_LDD + VT_ROWS * VT_LD + EKF_UB) * sizeof(double);
+static const size_t kVSmem = (size_t)(VT_LPACK + (EKF_UB / 32) * 32 * VT_LDD + VT_ROWS * VT_LD + EKF_UB) * sizeof(double);
 
 int update_kernels_init() {
   const char* env = getenv("EKF_CHOL_SMEM");
