@@ -2,6 +2,7 @@
 // feature-table management (add / remove), accessors.  No CPU fallback: every entry point needs a
 // CUDA device and fails with EKF_ERR_CUDA otherwise.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -51,8 +52,39 @@ static void prof_flush(ekf_handle* h) {
   h->prof_pending.clear();
 }
 
+// ---- EKF_TRACE=1: per-launch timeline of the pipelined stacked update (start / end of every kernel on its stream, relative to the
+// first one), printed to stderr after the step's final synchronize.  Diagnostic only: the event records perturb the schedule a little.
+struct TraceRec { const char* name; int b; cudaEvent_t a, e; };
+static std::vector<TraceRec> g_trace;
+static const bool g_trace_on = getenv("EKF_TRACE") != nullptr;
+struct TraceScope {
+  const char* name; int b; cudaStream_t s; cudaEvent_t a = nullptr;
+  TraceScope(const char* nm, int blk, cudaStream_t st) : name(nm), b(blk), s(st) {
+    if (g_trace_on) { cudaEventCreate(&a); cudaEventRecord(a, s); }
+  }
+  ~TraceScope() {
+    if (g_trace_on) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); g_trace.push_back({name, b, a, e}); }
+  }
+};
+static void trace_flush() {
+  if (!g_trace_on || g_trace.empty()) return;
+  for (auto& r : g_trace) {
+    float t0 = 0, t1 = 0;
+    cudaEventElapsedTime(&t0, g_trace[0].a, r.a); cudaEventElapsedTime(&t1, g_trace[0].a, r.e);
+    fprintf(stderr, "trace %-8s b=%d  %8.1f -> %8.1f us  (%.1f)\n", r.name, r.b, t0 * 1e3, t1 * 1e3, (t1 - t0) * 1e3);
+  }
+  fprintf(stderr, "trace end\n");
+  for (auto& r : g_trace) { cudaEventDestroy(r.a); cudaEventDestroy(r.e); }
+  g_trace.clear();
+}
+
 template <class T>
 static cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, sizeof(T) * std::max<size_t>(count, 1)); }
+
+// the filter's stream waits for a host frame still being uploaded on the copy stream (no-op otherwise)
+static void frame_ready(ekf_handle* h) {
+  if (h->frame_pending) { cudaStreamWaitEvent(h->stream, h->ev_frame, 0); h->frame_pending = false; }
+}
 
 static cudaError_t alloc_feattab(FeatTab& t, int cap, int w2) {
   cudaError_t e;
@@ -103,7 +135,15 @@ int ekf_destroy(ekf_handle* h) {
   cudaFree(h->map_dev); cudaFree(h->keep_dev); cudaFree(h->newpos_dev); cudaFree(h->ctl); cudaFree(h->frame); cudaFree(h->raw);
   cudaFree(h->picks_dev); cudaFree(h->out_dev); cudaFree(h->gemm_counters);
   if (h->gemm_stream) { cudaStreamSynchronize(h->gemm_stream); cudaStreamDestroy(h->gemm_stream); }
-  cudaFree(h->Wbuf[1]); cudaFree(h->Wbuf[2]); cudaFree(h->Wbuf[3]); cudaFree(h->Gbuf);
+  cudaFree(h->Wbuf[1]); cudaFree(h->Wbuf[2]); cudaFree(h->Wbuf[3]); cudaFree(h->Wbuf[4]); cudaFree(h->Wbuf[5]); cudaFree(h->Gbuf);
+  cudaFree(h->Dinv2); cudaFree(h->Dblk2); cudaFree(h->yb2); cudaFree(h->delta1); cudaFree(h->delta2); cudaFree(h->gy); cudaFree(h->bt_H); cudaFree(h->bt_zmh); cudaFree(h->Sgbuf); cudaFree(h->bt_pos); cudaFree(h->bt_nd); cudaFree(h->tile_order); cudaFree(h->tile_nhot); cudaFree(h->tile_counters);
+  if (h->v_stream) { cudaStreamSynchronize(h->v_stream); cudaStreamDestroy(h->v_stream); }
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  if (h->ev_frame) cudaEventDestroy(h->ev_frame);
+  if (h->ev_prev) cudaEventDestroy(h->ev_prev);
+  if (h->gather_stream) { cudaStreamSynchronize(h->gather_stream); cudaStreamDestroy(h->gather_stream); }
+  for (int i = 0; i < 2; ++i) { if (h->ev_F[i]) cudaEventDestroy(h->ev_F[i]); if (h->ev_corr2[i]) cudaEventDestroy(h->ev_corr2[i]); if (h->ev_dd[i]) cudaEventDestroy(h->ev_dd[i]); }
+  if (h->ev_A) cudaEventDestroy(h->ev_A);
   if (h->corr_stream) { cudaStreamSynchronize(h->corr_stream); cudaStreamDestroy(h->corr_stream); }
   if (h->ev_S) cudaEventDestroy(h->ev_S);
   if (h->ev_G) cudaEventDestroy(h->ev_G);
@@ -164,11 +204,29 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
   h->Wbuf[0] = h->W;
   TRY(dalloc(&h->Wbuf[1], (size_t)(h->ncap + 1 + EKF_DIST_PAD_ROWS) * EKF_UB)) TRY(dalloc(&h->Wbuf[2], (size_t)(h->ncap + 1 + EKF_DIST_PAD_ROWS) * EKF_UB)) TRY(dalloc(&h->Wbuf[3], (size_t)(h->ncap + 1) * EKF_UB))
   TRY(dalloc(&h->Gbuf, EKF_UB * EKF_UB))
+  TRY(dalloc(&h->Wbuf[4], (size_t)(h->ncap + 1) * EKF_UB)) TRY(dalloc(&h->Wbuf[5], (size_t)(h->ncap + 1) * EKF_UB))
+  TRY(dalloc(&h->Dinv2, EKF_UB * EKF_UB)) TRY(dalloc(&h->Dblk2, EKF_UB * 32)) TRY(dalloc(&h->yb2, EKF_UB)) TRY(dalloc(&h->gy, EKF_UB))
+  TRY(dalloc(&h->bt_H, 26 * (size_t)feature_capacity)) TRY(dalloc(&h->bt_zmh, 2 * (size_t)feature_capacity)) TRY(dalloc(&h->bt_pos, feature_capacity))
+  TRY(dalloc(&h->bt_nd, feature_capacity)) TRY(dalloc(&h->Sgbuf, EKF_UB * EKF_UB))
+  h->tile_blk_cap = (feature_capacity + EKF_UB / 2 - 1) / (EKF_UB / 2) + 1;
+  h->tile_T_cap = std::min(128, (h->ncap + 63) / 64);   // the hot-first tile lists exist for n <= 8192 (the schedule using them stops at n = 6000)
+  TRY(dalloc(&h->tile_order, (size_t)h->tile_blk_cap * (h->tile_T_cap * (h->tile_T_cap + 1) / 2))) TRY(dalloc(&h->tile_nhot, h->tile_blk_cap))
+  TRY(dalloc(&h->tile_counters, h->tile_blk_cap))
+  TRY(dalloc(&h->delta1, h->ld + EKF_DIST_PAD_ROWS)) TRY(dalloc(&h->delta2, h->ld + EKF_DIST_PAD_ROWS))
   {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = least priority
     TRY(cudaStreamCreateWithPriority(&h->gemm_stream, cudaStreamNonBlocking, lo))
     TRY(cudaStreamCreateWithPriority(&h->corr_stream, cudaStreamNonBlocking, hi))
+    TRY(cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, hi))
+    TRY(cudaEventCreateWithFlags(&h->ev_frame, cudaEventDisableTiming)) TRY(cudaEventCreateWithFlags(&h->ev_prev, cudaEventDisableTiming))
+    TRY(cudaStreamCreateWithPriority(&h->v_stream, cudaStreamNonBlocking, hi))
+    TRY(cudaStreamCreateWithPriority(&h->gather_stream, cudaStreamNonBlocking, hi))
+    for (int i = 0; i < 2; ++i) {
+      TRY(cudaEventCreateWithFlags(&h->ev_F[i], cudaEventDisableTiming)) TRY(cudaEventCreateWithFlags(&h->ev_corr2[i], cudaEventDisableTiming))
+      TRY(cudaEventCreateWithFlags(&h->ev_dd[i], cudaEventDisableTiming))
+    }
+    TRY(cudaEventCreateWithFlags(&h->ev_A, cudaEventDisableTiming))
     TRY(cudaEventCreateWithFlags(&h->ev_G, cudaEventDisableTiming)) TRY(cudaEventCreateWithFlags(&h->ev_corr, cudaEventDisableTiming))
     for (int i = 0; i < 3; ++i) {
       TRY(cudaEventCreateWithFlags(&h->ev_gather[i], cudaEventDisableTiming)) TRY(cudaEventCreateWithFlags(&h->ev_V[i], cudaEventDisableTiming))
@@ -183,6 +241,12 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
     // (stacked_update_factor_beside_downdate); EKF_PIPE_MIN_N overrides (0 = never)
     e = getenv("EKF_PIPE_MIN_N");
     h->pipe_small = e ? atoi(e) : 1000;
+    // which of the two schedules for that range: 1 = chain-short (default: V off the critical chain; same-box A/B at n = 3014:
+    // 0.764 against 0.786 ms per cfg2 step), 0 = factor-beside-downdate — see DESIGN.md section 4
+    e = getenv("EKF_SCHED");
+    h->sched = e ? atoi(e) : 1;
+    e = getenv("EKF_SPLIT_DD");
+    h->split_dd = e ? atoi(e) : 0;   // 0: 2-D grid; 1: tile list, the next gather gated on its hot tiles; 2: tile list only
   }
   TRY(dalloc(&h->xyz_flag, h->Ncap)) TRY(dalloc(&h->xyz_rmap, 2 * (size_t)h->ncap)) TRY(dalloc(&h->xyz_pos, h->Ncap))
   TRY(dalloc(&h->xyz_coding, h->Ncap)) TRY(dalloc(&h->xyz_y, 3 * (size_t)h->Ncap)) TRY(dalloc(&h->xyz_J, 18 * (size_t)h->Ncap))
@@ -241,6 +305,7 @@ int ekf_set_stream(ekf_handle* h, void* s) {
 int ekf_sync(ekf_handle* h) {
   if (!h) return EKF_ERR_ARG;
   EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  frame_ready(h);
   EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   return EKF_OK;
 }
@@ -259,7 +324,16 @@ static int capture_common(ekf_handle* h, const uint8_t* img, int width, int heig
   }
   const int dstride = (dw + 15) & ~15;
   const size_t need = (size_t)dstride * dh;
+  // a host frame goes up on the copy stream, ordered after everything already enqueued on the filter's stream (earlier readers
+  // of the frame buffer); a device frame is copied in the filter's own stream as before
+  cudaStream_t cs = device_src ? h->stream : h->copy_stream;
+  if (device_src) frame_ready(h);
+  else {
+    EKF_CUDA_CHECK(cudaEventRecord(h->ev_prev, h->stream));
+    EKF_CUDA_CHECK(cudaStreamWaitEvent(cs, h->ev_prev, 0));
+  }
   if (need > h->frame_cap) {
+    EKF_CUDA_CHECK(cudaStreamSynchronize(cs));
     EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     cudaFree(h->frame);
     h->frame = nullptr;
@@ -268,13 +342,14 @@ static int capture_common(ekf_handle* h, const uint8_t* img, int width, int heig
   }
   if (scale == 1 && channels == 1) {
     EKF_CUDA_CHECK(cudaMemcpy2DAsync(h->frame, dstride, img, stride, width, height,
-                                     device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+                                     device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, cs));
   } else {
     const uint8_t* src = img;
     int sstride = stride;
     if (!device_src) {
       const size_t rawneed = (size_t)width * channels * height;
       if (rawneed > h->raw_cap) {
+        EKF_CUDA_CHECK(cudaStreamSynchronize(cs));
         EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
         cudaFree(h->raw);
         h->raw = nullptr;
@@ -282,16 +357,20 @@ static int capture_common(ekf_handle* h, const uint8_t* img, int width, int heig
         h->raw_cap = rawneed;
       }
       EKF_CUDA_CHECK(cudaMemcpy2DAsync(h->raw, (size_t)width * channels, img, stride, (size_t)width * channels, height,
-                                       cudaMemcpyHostToDevice, h->stream));
+                                       cudaMemcpyHostToDevice, cs));
       src = h->raw; sstride = width * channels;
     }
-    launch_capture_resize_gray(h->stream, src, width, height, sstride, channels, h->frame, dw, dh, dstride, &h->launches);
+    launch_capture_resize_gray(cs, src, width, height, sstride, channels, h->frame, dw, dh, dstride, &h->launches);
     EKF_CUDA_CHECK(cudaGetLastError());
   }
   if (h->fv.px != h->frame || h->fv.w != dw || h->fv.h != dh || h->fv.stride != dstride)
     match_make_tensor_map(&h->frame_map, h->frame, dw, dh, dstride, 1, h->cfg.window_size, (int)h->cfg.search_clamp);
   h->fv = FrameView{h->frame, dw, dh, dstride};
   h->have_frame = true;
+  if (!device_src) {
+    EKF_CUDA_CHECK(cudaEventRecord(h->ev_frame, cs));
+    h->frame_pending = true;
+  }
   return EKF_OK;
 }
 int ekf_capture_frame(ekf_handle* h, const uint8_t* gray, int width, int height, int stride, double stamp) {
@@ -309,6 +388,7 @@ int ekf_get_frame(ekf_handle* h, uint8_t* out, int* width, int* height) {   // r
   *width = h->fv.w; *height = h->fv.h;
   if (out) {
     EKF_CUDA_CHECK(cudaSetDevice(h->device));
+    frame_ready(h);
     EKF_CUDA_CHECK(cudaMemcpy2DAsync(out, h->fv.w, h->frame, h->fv.stride, h->fv.w, h->fv.h, cudaMemcpyDeviceToHost, h->stream));
     EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   }
@@ -321,6 +401,7 @@ int ekf_predict(ekf_handle* h, const double dv[3], const double dw[3], int vcont
   EKF_CUDA_CHECK(cudaSetDevice(h->device));
   const double z3[3] = {0, 0, 0};
   if (vcontrol) h->noise_cov_factor = 0; else h->noise_cov_factor++;
+  if (h->cfg.kernel_size < 100000) frame_ready(h);   // motion-blur template prediction on: keep the whole step behind the upload
   {
     ProfScope ps(h, 0);
     launch_predict(h->stream, h->Sigma, h->ld, h->n, h->mu, h->ft, h->N, h->fv, h->ctl, h->dcfg, h->dT, dv ? dv : z3, dw ? dw : z3,
@@ -358,6 +439,7 @@ int ekf_match(ekf_handle* h, int* n_matched) {
   if (!h) return EKF_ERR_ARG;
   if (!h->predicted) return ekf_fail(h, EKF_ERR_STATE, "match before predict");
   EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  frame_ready(h);
   {
     ProfScope ps(h, 1);
     launch_match_filter(h->stream, h->ft, h->N, h->fv, h->dcfg, &h->frame_map, &h->launches);
@@ -634,13 +716,126 @@ static int stacked_update_factor_beside_downdate(ekf_handle* h, int cnt) {
   return 0;
 }
 
+// Third schedule, same look-ahead algebra, for the same range of n: the n-row solve V_b LEAVES the critical chain.  The next
+// block needs V_b only through G_{b+1} = H_{b+1} V_b = (H_{b+1} W_b) L_b^-T, a 128-row solve on the rows of W_b that block b+1
+// touches (k_blk_Gx), and through nu_{b+1}, where the missing term of delta is G_{b+1} y_b.  Chain per block:
+//   main:  Gx_b -> S_b -> factor_b                (8 + 4 + 42 us instead of V 21 + G 8 + S 4 + factor 42)
+//   v:     V_b (beside factor_{b+1}; out of place: Gx_{b+1} reads W_b meanwhile), delta_b = delta_{b-1} + V_b y_b (ping-pong)
+//   corr:  W_b = W'_b - V_{b-1} G_b^T             (beside factor_b; needs all of V_{b-1})
+//   second: downdate_{b-1} (released by S_b, as before) -> gather of W'_{b+1}
+// Two sets of factor outputs (L, D, y) alternate: V_{b-1} reads one while factor_b writes the other.
+static int stacked_update_chain_short(ekf_handle* h, int cnt) {
+  cudaStream_t sm = h->stream, sg = h->gemm_stream, sc = h->corr_stream, sv = h->v_stream;
+  const int nblk = (cnt + EKF_UB / 2 - 1) / (EKF_UB / 2);
+  double* raw[2] = {h->Wbuf[1], h->Wbuf[2]};   // W'_b as gathered (read by S_b)
+  double* cor[2] = {h->Wbuf[0], h->Wbuf[3]};   // second copy, corrected in place to W_b (read by Gx_{b+1} and V_b)
+  double* Vb[2] = {h->Wbuf[4], h->Wbuf[5]};    // V_b (read by corr_{b+1} and downdate_b)
+  double* Ls[2] = {h->Dinv, h->Dinv2};
+  double* Ds[2] = {h->Dblk, h->Dblk2};
+  double* ys[2] = {h->yb, h->yb2};
+  double* dl[3] = {h->delta, h->delta1, h->delta2};   // delta_b lives in dl[b % 3]; delta_{-1} = delta_{-2} = 0
+  for (int i = 0; i < 3; ++i) cudaMemsetAsync(dl[i], 0, sizeof(double) * (size_t)h->n, sm);
+  // gather beside the downdate (hot tiles first): lower-triangle mode with square tiles only
+  const int T = (h->n + 63) / 64, Ltiles = T * (T + 1) / 2;
+  const bool gate = h->split_dd == 1;
+  const bool split = h->split_dd && nblk > 2 && h->lower_only && T <= h->tile_T_cap && nblk <= h->tile_blk_cap && gemm_uses_square_tiles();
+  cudaStream_t sgat = (split && gate) ? h->gather_stream : sg;
+  const BlkTab bt{h->bt_H, h->bt_zmh, h->bt_pos, h->bt_nd};
+  launch_blk_prep(sm, h->ft, cnt, h->bt_H, h->bt_zmh, h->bt_pos, h->bt_nd, &h->launches);
+  if (split) launch_blk_tile_order(sm, h->ft, cnt, T, h->tile_order, h->tile_nhot, h->tile_counters, &h->launches);
+  cudaEventRecord(h->ev_fork, sm);
+  cudaStreamWaitEvent(sg, h->ev_fork, 0);
+  cudaStreamWaitEvent(sv, h->ev_fork, 0);
+  for (int b = 0; b < nblk && b < 2; ++b) {   // W'_0 = W_0 and W'_1, both from the prior covariance
+    ProfScope ps(h, 3, sg); TraceScope ts("gather", b, sg);
+    launch_blk_gather2(sg, h->Sigma, h->ld, h->n, h->ft, b * (EKF_UB / 2), cnt, raw[b], cor[b], &h->launches, bt);
+    cudaEventRecord(h->ev_gather[b], sg);
+  }
+  for (int b = 0; b < nblk; ++b) {
+    const int f0 = b * (EKF_UB / 2), p = b & 1, q = p ^ 1;
+    if (b > 0) {
+      if (b > 1) {
+        cudaStreamWaitEvent(sm, h->ev_corr2[q], 0);   // W_{b-1} is corrected (b - 1 = 0 needs no correction)
+        cudaStreamWaitEvent(sm, h->ev_V[(b - 2) % 3], 0);   // delta_{b-2} is complete; V_{b-2} no longer reads the factor set p
+      }
+      { ProfScope ps(h, 4); TraceScope ts("Gx", b, sm); launch_blk_Gx(sm, cor[q], h->ft, f0, cnt, Ls[q], Ds[q], ys[q], h->Gbuf, h->gy, &h->launches, bt); }
+      cudaEventRecord(h->ev_G, sm);
+      // W_b = W'_b - V_{b-1} G_b^T beside S_b and the Cholesky
+      cudaStreamWaitEvent(sc, h->ev_G, 0);
+      cudaStreamWaitEvent(sc, h->ev_V[(b - 1) % 3], 0);
+      cudaStreamWaitEvent(sc, h->ev_gather[p], 0);   // the second copy of W'_b
+      TraceScope ts("corr", b, sc);
+      const int rc = launch_gemm_nt_sub(sc, cor[p], EKF_UB, Vb[q], EKF_UB, h->Gbuf, EKF_UB, h->n, EKF_UB, EKF_UB, nullptr, 0, h->gemm_counters, &h->launches);
+      if (rc) return rc;
+      cudaEventRecord(h->ev_corr2[p], sc);
+      // -G_b G_b^T now, in the shadow of the gather this block still waits for
+      { ProfScope ps(h, 4); TraceScope ts("Sg", b, sm); launch_blk_Sg(sm, h->Gbuf, h->Sgbuf, &h->launches); }
+    }
+    cudaStreamWaitEvent(sm, h->ev_gather[p], 0);   // only S_b reads W'_b: Gx_b ran in the shadow of the gather
+    { ProfScope ps(h, 4); TraceScope ts("S", b, sm);
+      launch_blk_S_nu_G(sm, raw[p], h->ft, f0, cnt, h->dcfg, dl[(b + 1) % 3] /* delta_{b-2} */, b > 0 ? h->Gbuf : nullptr, h->Lb, h->nu, &h->launches,
+                        b > 0 ? h->gy : nullptr, bt, b > 0 ? h->Sgbuf : nullptr); }
+    if (b > 0) {   // release the downdate of block b-1 (it also waits for V_{b-1})
+      cudaEventRecord(h->ev_S, sm);
+      cudaStreamWaitEvent(sg, h->ev_S, 0);
+    }
+    { ProfScope ps(h, 4); TraceScope ts("factor", b, sm); launch_blk_factor_only(sm, h->Lb, h->nu, Ls[p], Ds[p], ys[p], h->ctl, &h->launches); }
+    cudaEventRecord(h->ev_F[p], sm);
+    if (b > 0) {
+      cudaStreamWaitEvent(sg, h->ev_V[(b - 1) % 3], 0);
+      const bool two = split && b + 1 < nblk;   // the gather of W'_{b+1} starts beside this downdate, after its hot tiles
+      if (two && gate) {
+        cudaEventRecord(h->ev_A, sg);            // everything the downdate waits for
+        cudaStreamWaitEvent(sgat, h->ev_A, 0);
+      }
+      {
+        ProfScope ps(h, 6, sg); TraceScope ts("dd", b - 1, sg);
+        const int rc = launch_gemm_nt_sub(sg, h->Sigma, h->ld, Vb[q], EKF_UB, Vb[q], EKF_UB, h->n, h->n, EKF_UB, nullptr, h->lower_only, h->gemm_counters, &h->launches,
+                                          two ? h->tile_order + (size_t)(b + 1) * Ltiles : nullptr, Ltiles, h->tile_nhot + (b + 1), h->tile_counters + (b + 1));
+        if (rc) return rc;
+      }
+      if (b + 1 < nblk) {
+        // cor[q] / raw[q] are free: Gx_b (before S_b, which released the downdate) and V_{b-1} (waited for above) have read them
+        ProfScope ps(h, 3, sgat); TraceScope ts("gather", b + 1, sgat);
+        if (two && gate) launch_blk_gather2_after_tiles(sgat, h->Sigma, h->ld, h->n, h->ft, (b + 1) * (EKF_UB / 2), cnt, raw[q], cor[q],
+                                                h->tile_counters + (b + 1), h->tile_nhot + (b + 1), h->ctl, &h->launches, bt);
+        else launch_blk_gather2(sgat, h->Sigma, h->ld, h->n, h->ft, (b + 1) * (EKF_UB / 2), cnt, raw[q], cor[q], &h->launches, bt);
+        cudaEventRecord(h->ev_gather[q], sgat);
+      }
+      cudaEventRecord(h->ev_dd[q], sg);
+    }
+    // V_b on its own stream: after factor_b, the correction of W_b and the downdate that still reads Vb[p] (block b-2)
+    cudaStreamWaitEvent(sv, h->ev_F[p], 0);
+    if (b > 0) cudaStreamWaitEvent(sv, h->ev_corr2[p], 0);
+    if (b > 1) cudaStreamWaitEvent(sv, h->ev_dd[p], 0);
+    { ProfScope ps(h, 5, sv); TraceScope ts("V", b, sv);
+      launch_blk_V(sv, cor[p], 0, h->n, Ls[p], Ds[p], ys[p], dl[b % 3], &h->launches, Vb[p], dl[(b + 2) % 3] /* delta_{b-1} */); }
+    cudaEventRecord(h->ev_V[b % 3], sv);
+  }
+  {
+    const int p = (nblk - 1) & 1;
+    cudaStreamWaitEvent(sg, h->ev_V[(nblk - 1) % 3], 0);
+    ProfScope ps(h, 6, sg); TraceScope ts("dd", nblk - 1, sg);
+    const int rc = launch_gemm_nt_sub(sg, h->Sigma, h->ld, Vb[p], EKF_UB, Vb[p], EKF_UB, h->n, h->n, EKF_UB, nullptr, h->lower_only, h->gemm_counters, &h->launches);
+    if (rc) return rc;
+  }
+  cudaEventRecord(h->ev_join, sg);
+  cudaStreamWaitEvent(sm, h->ev_join, 0);
+  {
+    ProfScope ps(h, 7); TraceScope ts("finish", nblk, sm);
+    launch_finish_update(sm, h->Sigma, h->ld, h->n, h->mu, dl[(nblk - 1) % 3], h->ctl, &h->launches);
+  }
+  return 0;
+}
+
 static int stacked_update(ekf_handle* h, int cnt, bool plane = false) {
   if (cnt <= 0 && !plane) return 0;
   if (cnt < 0) cnt = 0;
   if (!plane && cnt > EKF_UB / 2) {
     const bool partitioned = h->nccl_comm && h->world > 1;
     if (h->lookahead > 0 && h->n >= h->lookahead) return stacked_update_lookahead(h, cnt);   // also row-block partitioned
-    if (!partitioned && h->pipe_small > 0 && h->n >= h->pipe_small) return stacked_update_factor_beside_downdate(h, cnt);
+    if (!partitioned && h->pipe_small > 0 && h->n >= h->pipe_small)
+      return h->sched == 1 ? stacked_update_chain_short(h, cnt) : stacked_update_factor_beside_downdate(h, cnt);
   }
   cudaStream_t st = h->stream;
   // Row-block partition (BASELINE config 4): every rank holds a replica of Sigma, updates only its
@@ -728,7 +923,13 @@ int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
   EKF_CUDA_CHECK(cudaStreamSynchronize(st));
   const int n_li = hc.n_li;
   if (n_li > 0) {
+    static const bool host_timing = getenv("EKF_HOST_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     int rc = stacked_update(h, n_li);
+    if (host_timing) {
+      const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+      fprintf(stderr, "stacked_update(li, %d rows): host enqueue %.1f us, %lld launches so far\n", n_li, us, h->launches);
+    }
     if (rc) return ekf_fail_cuda(h, (cudaError_t)rc, "stacked update (li)", __FILE__, __LINE__);
   }
   // high-innovation rescue and second update
@@ -755,6 +956,7 @@ int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
   EKF_CUDA_CHECK(cudaMemcpyAsync(h->out_host, h->out_dev, bytes, cudaMemcpyDeviceToHost, st));
   EKF_CUDA_CHECK(cudaStreamSynchronize(st));
   prof_flush(h);
+  trace_flush();
   const int* outi = reinterpret_cast<const int*>(h->out_host + 210);
   h->stats.n_in_innovation_predict = outi[0];
   h->stats.n_matched = outi[1];
@@ -762,6 +964,7 @@ int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
   h->stats.n_hi = n_hi;
   h->stats.ransac_hypotheses = outi[4];
   h->stats.blur_requests = outi[6];
+  if (outi[5] & 64) return ekf_fail(h, EKF_ERR_CUDA, "pipelined update: the downdate tiles a gather waits for did not arrive within the wait limit");
   if (outi[5] & 16) return ekf_fail(h, EKF_ERR_CUDA, "row-block partition: a peer's panel did not arrive within the wait limit (peer-memory exchange)");
   if (outi[5]) return ekf_fail(h, EKF_ERR_STATE, "innovation covariance not positive definite");
   if (outi[7]) return ekf_fail(h, EKF_ERR_UNSUPPORTED, "a motion-blur kernel exceeded 256 x 256 pixels");
@@ -829,6 +1032,7 @@ int ekf_add_feature(ekf_handle* h, float u, float v) {
   const double x = (double)u, y = (double)v;
   if (!(x > half && y > half && x < h->fv.w - half && y < h->fv.h - half)) return 0;
   if (h->N >= h->Ncap || h->n + 6 > h->ncap) return ekf_fail(h, EKF_ERR_CAPACITY, "feature capacity exceeded");
+  frame_ready(h);
   launch_add_feature(h->stream, h->Sigma, h->ld, h->n, h->mu, h->ft, h->N, h->fv, h->dcfg, u, v, h->patchnumbre, &h->launches);
   EKF_CUDA_CHECK(cudaGetLastError());
   h->m_pos.push_back(h->n);
@@ -856,6 +1060,7 @@ static int detect_corners(ekf_handle* h, int num, std::vector<float>& xy) {
   if (num > EKF_DET_MAX) num = EKF_DET_MAX;
   const size_t px = (size_t)h->fv.w * h->fv.h;
   cudaStream_t st = h->stream;
+  frame_ready(h);
   if (px > h->det_cap) {
     EKF_CUDA_CHECK(cudaStreamSynchronize(st));
     cudaFree(h->det_mask); cudaFree(h->det_eig);

@@ -113,6 +113,16 @@ __host__ __device__ __forceinline__ FeatTab feattab_slice(const FeatTab& t, int 
   return o;
 }
 
+// Compact per-update tables of the selected features, in ft.sel order (k_blk_prep): what the block kernels of the stacked update
+// read of the feature table, without the sel -> pos / coding -> H chain of dependent loads.  H == nullptr: not prepared (the kernels
+// then go through the feature table).
+struct BlkTab {
+  const double* H;    // [cnt][26]
+  const double* zmh;  // [cnt][2]  z - h
+  const int* pos;     // [cnt]
+  const int* nd;      // [cnt]  7 + 3 (XYZ) or 7 + 6 (inverse depth)
+};
+
 // device-side view of the peer mappings, passed by value to the kernels that push panels to the peers
 struct P2PView {
   double* w[8];                 // destination panel (Wbuf[b % 3]) on every rank

@@ -42,18 +42,28 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 template <int GT_M, int GT_STAGES, int MINB>
 __global__ void __launch_bounds__(GT_THREADS, MINB)
 k_gemm_nt_sub(double* __restrict__ C, int ldc, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
-              int M, int N, int kconst, const int* __restrict__ kdev, int lower_only, unsigned stagger_ns) {
+              int M, int N, int kconst, const int* __restrict__ kdev, int lower_only, unsigned stagger_ns,
+              const ushort2* __restrict__ tlist, const int* __restrict__ n_hot, unsigned int* hot_counter) {
   extern __shared__ __align__(16) double gsm[];
   const int K = kdev ? *kdev : kconst;
   if (K <= 0) return;
-  const int tm = blockIdx.y, tn = blockIdx.x;
+  // tlist != null (square tiles, lower_only): 1-D grid over a list of the lower-triangle tiles in which the tiles the NEXT gather
+  // reads come first (k_blk_tile_order); a CTA that finishes one of those first *n_hot tiles bumps hot_counter, and the gather —
+  // launched beside this kernel — starts as soon as the counter is full instead of after the whole downdate.
+  int tm = blockIdx.y, tn = blockIdx.x;
+  if (tlist) { const ushort2 t = tlist[blockIdx.x]; tm = t.x; tn = t.y; }
   const int m0 = tm * GT_M, n0 = tn * GT_N;
   if (lower_only && n0 > m0 + GT_M - 1) return;
-  // Two CTAs share an SM and would otherwise run their load / store phases in lock-step; staggering
-  // every other 148-CTA wave of the first launch wave by about half a tile de-synchronises them.
+  // De-synchronise the first wave.  All 4 x 148 CTAs of a launch start together, so they also RETIRE together (tile life ~ 20 us):
+  // for most of the downdate no slot frees up, and a high-priority CTA of the gain chain launched meanwhile waits up to a tile
+  // life for its registers.  With the tile list (1-D grid in dispatch order) the k-th group of 148 CTAs sleeps k * stagger_ns
+  // first: retirements then come every stagger_ns, while the SM's DMMA pipe stays busy with the CTAs already running.
   if (stagger_ns > 0) {
-    const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x;
-    if (lin < 296u && ((lin / 148u) & 1u)) __nanosleep(stagger_ns);
+    if (tlist) { if (blockIdx.x < 592u) { const unsigned k = (blockIdx.x / 148u) & 3u; if (k) __nanosleep(k * stagger_ns); } }
+    else {
+      const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x;
+      if (lin < 296u && ((lin / 148u) & 1u)) __nanosleep(stagger_ns);
+    }
   }
   double* As = gsm;                                   // [stages][GT_M][GT_LD]
   double* Bs = gsm + GT_STAGES * GT_M * GT_LD;        // [stages][GT_N][GT_LD]
@@ -156,11 +166,16 @@ k_gemm_nt_sub(double* __restrict__ C, int ldc, const double* __restrict__ A, int
       }
     }
   }
+  if (tlist && (int)blockIdx.x < *n_hot) {
+    __syncthreads();
+    if (tid == 0) { __threadfence(); atomicAdd(hot_counter, 1u); }
+  }
 }
 
 template <int GT_M, int GT_STAGES, int MINB>
 static int launch_variant(cudaStream_t st, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M, int N,
-                          int kconst, const int* kdev, int lower_only, unsigned stagger) {
+                          int kconst, const int* kdev, int lower_only, unsigned stagger, const ushort2* tlist = nullptr, int n_tiles = 0, const int* n_hot = nullptr,
+                          unsigned int* hot_counter = nullptr) {
   constexpr size_t smem = (size_t)GT_STAGES * (GT_M + GT_N) * GT_LD * sizeof(double);
   static PerDeviceOnce once;   // per device, not per process
   const cudaError_t ea = once.ensure([&] {
@@ -168,7 +183,9 @@ static int launch_variant(cudaStream_t st, double* C, int ldc, const double* A, 
   });
   if (ea != cudaSuccess) return (int)ea;
   dim3 grid((N + GT_N - 1) / GT_N, (M + GT_M - 1) / GT_M);
-  k_gemm_nt_sub<GT_M, GT_STAGES, MINB><<<grid, GT_THREADS, smem, st>>>(C, ldc, A, lda, B, ldb, M, N, kconst, kdev, lower_only, stagger);
+  if (tlist) grid = dim3(n_tiles, 1);
+  k_gemm_nt_sub<GT_M, GT_STAGES, MINB><<<grid, GT_THREADS, smem, st>>>(C, ldc, A, lda, B, ldb, M, N, kconst, kdev, lower_only, stagger,
+                                                                       tlist, n_hot, hot_counter);
   return 0;
 }
 
@@ -177,16 +194,23 @@ static int launch_variant(cudaStream_t st, double* C, int ldc, const double* A, 
 // last wave (n = 3014, lower triangle: 0.47 -> 0.66 of the DGEMM peak) and keeps four independent CTAs
 // per SM in flight (n = 11972: 0.69 -> 0.88).
 int launch_gemm_nt_sub(cudaStream_t st, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M, int N,
-                       int kconst, const int* kdev, int lower_only, int* counters, long long* launches) {
+                       int kconst, const int* kdev, int lower_only, int* counters, long long* launches,
+                       const ushort2* tlist, int n_tiles, const int* n_hot, unsigned int* hot_counter) {
   (void)counters;
   if (M <= 0 || N <= 0) return 0;
   static int stagger = -1, force_tm = -1;
   if (stagger < 0) { const char* e = getenv("EKF_GEMM_STAGGER_NS"); stagger = e ? atoi(e) : 0; }
   if (force_tm < 0) { const char* e = getenv("EKF_GEMM_TM"); force_tm = e ? atoi(e) : 0; }
   const bool small_tile = force_tm ? (force_tm == 64) : true;
-  const int rc = small_tile ? launch_variant<64, 2, 4>(st, C, ldc, A, lda, B, ldb, M, N, kconst, kdev, lower_only, (unsigned)stagger)
+  if (tlist && !(small_tile && lower_only && M == N)) return (int)cudaErrorInvalidValue;   // the list enumerates 64 x 64 lower-triangle tiles
+  const int rc = small_tile ? launch_variant<64, 2, 4>(st, C, ldc, A, lda, B, ldb, M, N, kconst, kdev, lower_only, (unsigned)stagger, tlist, n_tiles, n_hot, hot_counter)
                             : launch_variant<128, 3, 2>(st, C, ldc, A, lda, B, ldb, M, N, kconst, kdev, lower_only, (unsigned)stagger);
   if (rc) return rc;
   if (launches) *launches += 1;
   return 0;
+}
+
+bool gemm_uses_square_tiles() {
+  const char* e = getenv("EKF_GEMM_TM");
+  return !(e && atoi(e) == 128);
 }

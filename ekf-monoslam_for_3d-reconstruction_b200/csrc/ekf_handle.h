@@ -31,6 +31,11 @@ struct ekf_handle {
   uint8_t* raw = nullptr;   // full-resolution / colour staging for captureNewFrame's resize + BGR2GRAY
   size_t raw_cap = 0;
   FrameView fv{nullptr, 0, 0, 0};
+  // host frames are uploaded on their own stream so that the copy runs beside predict (which does not read pixels); every
+  // reader of the frame first makes the filter's stream wait for ev_frame (frame_ready, ekf_api.cu)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_frame = nullptr, ev_prev = nullptr;
+  bool frame_pending = false;
   EkfTensorMap frame_map{};   // TMA tensor map of `frame` for the matcher's window staging (re-encoded when the frame view changes)
   uint32_t* picks_dev = nullptr;
   int picks_cap = 0;
@@ -46,8 +51,21 @@ struct ekf_handle {
   float* det_xy = nullptr; size_t det_cap = 0;
   // look-ahead pipeline of the stacked update (ekf_api.cu::stacked_update_lookahead)
   cudaStream_t gemm_stream = nullptr, corr_stream = nullptr;
-  double* Wbuf[4] = {nullptr, nullptr, nullptr, nullptr};   // Wbuf[0] == W
+  double* Wbuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // Wbuf[0] == W; [4], [5]: V_b of the chain-short schedule
   double* Gbuf = nullptr;
+  // chain-short schedule (ekf_api.cu::stacked_update_chain_short): second set of factor outputs (V_{b-1} reads one set while
+  // factor_b writes the other), delta ping-pong, gy = G_b y_{b-1}, the stream of the n-row solves and per-block events
+  double *Dinv2 = nullptr, *Dblk2 = nullptr, *yb2 = nullptr, *delta1 = nullptr, *delta2 = nullptr, *gy = nullptr;
+  cudaStream_t v_stream = nullptr, gather_stream = nullptr;
+  cudaEvent_t ev_F[2] = {nullptr, nullptr}, ev_corr2[2] = {nullptr, nullptr}, ev_dd[2] = {nullptr, nullptr}, ev_A = nullptr;
+  double *bt_H = nullptr, *bt_zmh = nullptr, *Sgbuf = nullptr;   // BlkTab storage (k_blk_prep), -G G^T of the current block (k_blk_Sg)
+  int *bt_pos = nullptr, *bt_nd = nullptr;
+  ushort2* tile_order = nullptr;          // [blocks][T (T + 1) / 2]: see k_blk_tile_order
+  int* tile_nhot = nullptr;               // [blocks]
+  unsigned int* tile_counters = nullptr;  // [blocks]
+  int tile_T_cap = 0, tile_blk_cap = 0;
+  int split_dd = 0;       // chain-short only (EKF_SPLIT_DD): 1 = tile list, hot tiles first, the next gather gated on them; 2 = tile list only
+  int sched = 1;          // 1: chain-short (default for pipe_small <= n < lookahead), 0: factor-beside-downdate (EKF_SCHED)
   cudaEvent_t ev_gather[3] = {nullptr, nullptr, nullptr}, ev_V[3] = {nullptr, nullptr, nullptr}, ev_fork = nullptr, ev_join = nullptr, ev_S = nullptr, ev_G = nullptr, ev_corr = nullptr;
   int pipe_small = 1000;  // minimum state dimension for the factor-beside-downdate schedule (0 = never)
   int lookahead = 6000;   // minimum state dimension for the look-ahead pipeline (0 = never)

@@ -49,9 +49,20 @@ void launch_blk_factor(cudaStream_t st, const double* W, FeatTab ft, int f0, int
 void launch_blk_S_nu(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const DevCfg& cfg, const double* delta,
                      double* Sb, double* nu, long long* launches);
 void launch_blk_S_nu_G(cudaStream_t st, const double* Wraw, FeatTab ft, int f0, int cnt, const DevCfg& cfg, const double* delta,
-                       const double* G, double* Sb, double* nu, long long* launches);
+                       const double* G, double* Sb, double* nu, long long* launches, const double* gy = nullptr,
+                       BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}, const double* Sg = nullptr);
+void launch_blk_Sg(cudaStream_t st, const double* G, double* Sg, long long* launches);
+void launch_blk_prep(cudaStream_t st, FeatTab ft, int cnt, double* H, double* zmh, int* pos, int* nd, long long* launches);
+// per update block g: the 64 x 64 tiles of the lower triangle (T x T tiles) ordered with the tiles gather g reads first; n_hot[g] of them
+void launch_blk_tile_order(cudaStream_t st, FeatTab ft, int cnt, int T, ushort2* order, int* n_hot, unsigned int* hot_counters, long long* launches);
+// the gather of block f0 / 64 started BESIDE the downdate that produces its columns: waits until hot_counter reaches *n_hot
+void launch_blk_gather2_after_tiles(cudaStream_t st, const double* Sigma, int ld, int n, FeatTab ft, int f0, int cnt, double* W, double* W2,
+                                    const unsigned int* hot_counter, const int* n_hot, DevCtl* ctl, long long* launches,
+                                    BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr});
+void launch_blk_Gx(cudaStream_t st, const double* Wc, FeatTab ft, int f0, int cnt, const double* Lb, const double* Dblk, const double* yb,
+                   double* G, double* gy, long long* launches, BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr});
 void launch_blk_gather2(cudaStream_t st, const double* Sigma, int ld, int n, FeatTab ft, int f0, int cnt, double* W, double* W2,
-                        long long* launches);
+                        long long* launches, BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr});
 void launch_blk_G(cudaStream_t st, const double* Vprev, FeatTab ft, int f0, int cnt, double* G, long long* launches);
 void launch_blk_factor_only(cudaStream_t st, const double* Sb, const double* nu, double* Lb, double* Dblk, double* yb, DevCtl* ctl,
                             long long* launches);
@@ -59,7 +70,7 @@ void launch_plane_gather(cudaStream_t st, const double* Sigma, int ld, int row0,
                          double* W, double* nu, DevCtl* ctl, long long* launches);
 void launch_plane_S(cudaStream_t st, const double* W, double* Sb, long long* launches);
 void launch_blk_V(cudaStream_t st, double* W, int row0, int row1, const double* Lb, const double* Dblk, const double* yb,
-                  double* delta, long long* launches);
+                  double* delta, long long* launches, double* Vout = nullptr, const double* delta_in = nullptr);
 void launch_blk_S_part(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const DevCfg& cfg, int row0, int row1, int add_diag,
                        const double* delta, double* nu, double* Sb, long long* launches);
 void launch_blk_S_part_p2p(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const DevCfg& cfg, int row0, int row1, int add_diag,
@@ -78,7 +89,9 @@ void launch_points_features(cudaStream_t st, const double* Sigma, int ld, const 
 void launch_rts_epoch(cudaStream_t st, double* io, const DevCfg& cfg, double dT, int* singular, long long* launches);
 // ekf_gemm.cu
 int launch_gemm_nt_sub(cudaStream_t st, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M, int N,
-                       int kconst, const int* kdev, int lower_only, int* counters, long long* launches);
+                       int kconst, const int* kdev, int lower_only, int* counters, long long* launches,
+                       const ushort2* tlist = nullptr, int n_tiles = 0, const int* n_hot = nullptr, unsigned int* hot_counter = nullptr);
+bool gemm_uses_square_tiles();
 // ekf_detect.cu
 int launch_detect_corners(cudaStream_t st, FrameView fr, FeatTab ft, int N, int window, uint8_t* mask, float* eig,
                           unsigned long long* keys, int key_cap, int* counters, int max_corners, float* out_xy, long long* launches);

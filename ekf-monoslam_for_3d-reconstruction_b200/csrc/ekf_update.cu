@@ -304,21 +304,36 @@ static int gather_rows() {
 }
 __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ Sigma, int ld, int row0, int n, FeatTab ft, int f0,
                                                     int cnt, const double* __restrict__ delta, double* __restrict__ W,
-                                                    double* __restrict__ nu, double* __restrict__ W2, int rows_per_cta) {
+                                                    double* __restrict__ nu, double* __restrict__ W2, int rows_per_cta,
+                                                    BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}) {
+  // Sigma is read past L1 (ld.global.cg): in the chain-short schedule this kernel runs BESIDE the downdate that still writes the
+  // tiles it does not read (k_wait_tiles gates it), so no line of Sigma may be served from a stale L1 copy.
   __shared__ double Hs[EKF_UB / 2][27];
   __shared__ int poss[EKF_UB / 2], nds[EKF_UB / 2], fids[EKF_UB / 2];
   const int nb = min(EKF_UB / 2, cnt - f0);
   const int tid = threadIdx.x;
-  for (int a = tid; a < EKF_UB / 2; a += blockDim.x) {
-    if (a < nb) {
-      const int f = ft.sel[f0 + a];
-      fids[a] = f; poss[a] = ft.pos[f]; nds[a] = 7 + (ft.coding[f] ? 3 : 6);
-    } else { fids[a] = -1; poss[a] = 0; nds[a] = 0; }
-  }
-  __syncthreads();
-  for (int e = tid; e < (EKF_UB / 2) * 26; e += blockDim.x) {
-    const int a = e / 26, c = e % 26;
-    Hs[a][c] = (a < nb) ? ft.Hc[26 * fids[a] + c] : 0.0;
+  if (bt.H) {   // prepared tables: one round trip instead of three
+    for (int a = tid; a < EKF_UB / 2; a += blockDim.x) {
+      fids[a] = (a < nb) ? 0 : -1;
+      poss[a] = (a < nb) ? bt.pos[f0 + a] : 0;
+      nds[a] = (a < nb) ? bt.nd[f0 + a] : 0;
+    }
+    for (int e = tid; e < (EKF_UB / 2) * 26; e += blockDim.x) {
+      const int a = e / 26, c = e % 26;
+      Hs[a][c] = (a < nb) ? bt.H[26 * (size_t)f0 + e] : 0.0;
+    }
+  } else {
+    for (int a = tid; a < EKF_UB / 2; a += blockDim.x) {
+      if (a < nb) {
+        const int f = ft.sel[f0 + a];
+        fids[a] = f; poss[a] = ft.pos[f]; nds[a] = 7 + (ft.coding[f] ? 3 : 6);
+      } else { fids[a] = -1; poss[a] = 0; nds[a] = 0; }
+    }
+    __syncthreads();
+    for (int e = tid; e < (EKF_UB / 2) * 26; e += blockDim.x) {
+      const int a = e / 26, c = e % 26;
+      Hs[a][c] = (a < nb) ? ft.Hc[26 * fids[a] + c] : 0.0;
+    }
   }
   __syncthreads();
   const int a = tid & (EKF_UB / 2 - 1), rl = tid / (EKF_UB / 2);
@@ -331,7 +346,7 @@ __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ S
     const double* row = Sigma + (size_t)i * ld;
     double sg[13];
 #pragma unroll
-    for (int c = 0; c < 13; ++c) sg[c] = (c < nd) ? row[ekf_idx13(c, pos)] : 0.0;   // 13 independent loads in flight
+    for (int c = 0; c < 13; ++c) sg[c] = (c < nd) ? __ldcg(row + ekf_idx13(c, pos)) : 0.0;   // 13 independent loads in flight
     double w0 = 0, w1 = 0;
 #pragma unroll
     for (int c = 0; c < 13; ++c)
@@ -381,9 +396,20 @@ __global__ void __launch_bounds__(EKF_UB) k_blk_S(const double* __restrict__ W, 
     const int pos = ft.pos[f], nd = 7 + (ft.coding[f] ? 3 : 6);
     const double* hc = ft.Hc + 26 * f + 13 * (r & 1);
     double acc = 0;
-    for (int c = 0; c < nd; ++c) {
-      const int idx = ekf_idx13(c, pos);
-      if (idx >= row0 && idx < row1) acc += hc[c] * W[(size_t)idx * EKF_UB + s];
+    // all 13 loads of W and of H in flight before the first use (a rolled loop paid the L2 latency per term: this kernel is
+    // the G step on the critical chain of every update block); same terms, same order
+    double hv[13], wv[13];
+#pragma unroll
+    for (int c = 0; c < 13; ++c) {
+      const int idx = ekf_idx13(c < nd ? c : 0, pos);
+      const bool in = c < nd && idx >= row0 && idx < row1;
+      hv[c] = in ? hc[c] : 0.0;
+      wv[c] = in ? W[(size_t)idx * EKF_UB + s] : 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < 13; ++c) {
+      const int idx = ekf_idx13(c < nd ? c : 0, pos);
+      if (c < nd && idx >= row0 && idx < row1) acc += hv[c] * wv[c];
     }
     v = acc + ((!plain && r == s && add_diag) ? sigma_pixel_2 : 0.0);
     if (Gsub) {
@@ -430,7 +456,10 @@ __global__ void __launch_bounds__(EKF_UB) k_blk_S(const double* __restrict__ W, 
 #define S2_LD (EKF_UB + 4)   // shared-memory row stride of a G slab: fragment loads (8 rows x 4 columns) hit every bank pair twice
 __global__ void __launch_bounds__(128) k_blk_S_tiled(const double* __restrict__ W, FeatTab ft, int f0, int cnt, double sigma_pixel_2,
                                                      double* __restrict__ Sb, const double* __restrict__ delta, double* __restrict__ nu,
-                                                     const double* __restrict__ Gsub) {
+                                                     const double* __restrict__ Gsub, const double* __restrict__ gy = nullptr,
+                                                     BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}, const double* __restrict__ Sg = nullptr) {
+  // Sg != null (chain-short schedule): the term -G G^T was formed ahead of time by k_blk_Sg while the gather of W' was still
+  // running; this launch then only adds the 13-row gather H_b W' and R — two round trips on the critical cycle instead of five.
   extern __shared__ __align__(16) double s2sm[];
   // lower-triangle block index -> (bi, bj), bi >= bj, 4 x 4 blocks of 32
   int bi = 0, rem = blockIdx.x;
@@ -456,10 +485,20 @@ __global__ void __launch_bounds__(128) k_blk_S_tiled(const double* __restrict__ 
   double acc[4][2];
 #pragma unroll
   for (int ct = 0; ct < 4; ++ct) { acc[ct][0] = 0.0; acc[ct][1] = 0.0; }
+  double2 sgv[4];
+  if (Sg) {
+#pragma unroll
+    for (int ct = 0; ct < 4; ++ct) sgv[ct] = *reinterpret_cast<const double2*>(Sg + (size_t)r * EKF_UB + 32 * bj + 8 * ct + 2 * t4);
+  }
   if (r < kr) {
-    const int f = ft.sel[f0 + (r >> 1)];
-    const int pos = ft.pos[f], nd = 7 + (ft.coding[f] ? 3 : 6);
-    const double* hc = ft.Hc + 26 * f + 13 * (r & 1);
+    int pos, nd;
+    const double* hc;
+    if (bt.H) { pos = bt.pos[f0 + (r >> 1)]; nd = bt.nd[f0 + (r >> 1)]; hc = bt.H + 26 * (size_t)(f0 + (r >> 1)) + 13 * (r & 1); }
+    else {
+      const int f = ft.sel[f0 + (r >> 1)];
+      pos = ft.pos[f]; nd = 7 + (ft.coding[f] ? 3 : 6);
+      hc = ft.Hc + 26 * f + 13 * (r & 1);
+    }
     double hv[13];
 #pragma unroll
     for (int c = 0; c < 13; ++c) hv[c] = (c < nd) ? hc[c] : 0.0;
@@ -507,22 +546,94 @@ __global__ void __launch_bounds__(128) k_blk_S_tiled(const double* __restrict__ 
         if (r < kr && sc < kr) acc[ct][u] += e[ct][u];
       }
   }
+  if (Sg) {
+#pragma unroll
+    for (int ct = 0; ct < 4; ++ct) {
+      const int sc = 32 * bj + 8 * ct + 2 * t4;
+      if (r < kr && sc < kr) acc[ct][0] += sgv[ct].x;
+      if (r < kr && sc + 1 < kr) acc[ct][1] += sgv[ct].y;
+    }
+  }
 #pragma unroll
   for (int ct = 0; ct < 4; ++ct)
     *reinterpret_cast<double2*>(Sb + (size_t)r * EKF_UB + 32 * bj + 8 * ct + 2 * t4) = make_double2(acc[ct][0], acc[ct][1]);
   if (nu && blockIdx.x == 0) {
     const int s = tid;
     double out = 0.0;
-    if (s < kr) {
+    if (s < kr && bt.H) {
+      const int j = f0 + (s >> 1), pos = bt.pos[j], nd = bt.nd[j];
+      const double* hc = bt.H + 26 * (size_t)j + 13 * (s & 1);
+      double hv[13], dv[13];
+#pragma unroll
+      for (int c = 0; c < 13; ++c) { hv[c] = (c < nd) ? hc[c] : 0.0; dv[c] = (c < nd) ? delta[ekf_idx13(c, pos)] : 0.0; }
+      double hd = 0;
+#pragma unroll
+      for (int c = 0; c < 13; ++c) if (c < nd) hd += hv[c] * dv[c];
+      out = bt.zmh[2 * j + (s & 1)] - hd;
+      if (gy) out -= gy[s];
+    } else if (s < kr) {
       const int f = ft.sel[f0 + (s >> 1)];
       const int pos = ft.pos[f], nd = 7 + (ft.coding[f] ? 3 : 6);
       const double* hc = ft.Hc + 26 * f + 13 * (s & 1);
       double hd = 0;
       for (int c = 0; c < nd; ++c) hd += hc[c] * delta[ekf_idx13(c, pos)];
       out = (ft.z[2 * f + (s & 1)] - ft.h[2 * f + (s & 1)]) - hd;
+      // gy = G_b y_{b-1} = H_b V_{b-1} y_{b-1}: `delta` then lacks the previous block's term (chain-short schedule)
+      if (gy) out -= gy[s];
     }
     nu[s] = out;
   }
+}
+
+// K4b(1''): Sg = -G G^T on the lower 32 x 32 blocks (10 CTAs, DMMA), the part of S_b that does not need the gather of W'_b: in
+// the chain-short schedule it runs right after k_blk_Gx, in the shadow of the downdate / gather the block waits for.
+__global__ void __launch_bounds__(128) k_blk_Sg(const double* __restrict__ Gsub, double* __restrict__ Sg) {
+  extern __shared__ __align__(16) double s2sm[];
+  int bi = 0, rem = blockIdx.x;
+  while (rem > bi) { rem -= bi + 1; ++bi; }
+  const int bj = rem;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+  double* Ga = s2sm;
+  double* Gb = s2sm + 32 * S2_LD;
+  for (int e = tid; e < 32 * (EKF_UB / 2); e += 128) {
+    const int r = e / (EKF_UB / 2), c = (e % (EKF_UB / 2)) * 2;
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(Ga + r * S2_LD + c), sb = (unsigned)__cvta_generic_to_shared(Gb + r * S2_LD + c);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(Gsub + (size_t)(32 * bi + r) * EKF_UB + c));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sb), "l"(Gsub + (size_t)(32 * bj + r) * EKF_UB + c));
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  __syncthreads();
+  const double* ga = Ga + (8 * warp + g) * S2_LD + t4;
+  // two accumulator sets per column tile (even / odd k-steps): 16 dependent DMMAs per chain instead of 32
+  double e0[4][2], e1[4][2];
+#pragma unroll
+  for (int ct = 0; ct < 4; ++ct) { e0[ct][0] = e0[ct][1] = e1[ct][0] = e1[ct][1] = 0.0; }
+#pragma unroll 4
+  for (int k4 = 0; k4 < EKF_UB / 4; k4 += 2) {
+    const double a0 = -ga[4 * k4], a1 = -ga[4 * k4 + 4];
+#pragma unroll
+    for (int ct = 0; ct < 4; ++ct) {
+      dmma884f(e0[ct][0], e0[ct][1], a0, Gb[(8 * ct + g) * S2_LD + 4 * k4 + t4]);
+      dmma884f(e1[ct][0], e1[ct][1], a1, Gb[(8 * ct + g) * S2_LD + 4 * k4 + 4 + t4]);
+    }
+  }
+  const int r = 32 * bi + 8 * warp + g;
+#pragma unroll
+  for (int ct = 0; ct < 4; ++ct)
+    *reinterpret_cast<double2*>(Sg + (size_t)r * EKF_UB + 32 * bj + 8 * ct + 2 * t4) = make_double2(e0[ct][0] + e1[ct][0], e0[ct][1] + e1[ct][1]);
+}
+
+// Compact tables of the selected features for the block kernels (BlkTab), once per stacked update.
+__global__ void __launch_bounds__(128) k_blk_prep(FeatTab ft, int cnt, double* __restrict__ H, double* __restrict__ zmh, int* __restrict__ pos,
+                                                  int* __restrict__ nd) {
+  const int j = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= cnt) return;
+  const int f = ft.sel[j];
+  if (lane < 26) H[26 * (size_t)j + lane] = ft.Hc[26 * f + lane];
+  if (lane < 2) zmh[2 * j + lane] = ft.z[2 * f + lane] - ft.h[2 * f + lane];
+  if (lane == 2) pos[j] = ft.pos[f];
+  if (lane == 3) nd[j] = 7 + (ft.coding[f] ? 3 : 6);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -612,7 +723,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_blk_factor_p2p(const double* 
 #define VT_LPACK (32 * 36 + 32 * 68 + 32 * 100)   // doubles: block rows 1, 2, 3
 __global__ void __launch_bounds__(VT_THREADS, 4) k_blk_V(double* __restrict__ W, int rbase, int n, const double* __restrict__ Lg,
                                                       const double* __restrict__ Dg, const double* __restrict__ yg,
-                                                      double* __restrict__ delta, P2PView pv = P2PView{}, unsigned int* ticket = nullptr) {
+                                                      double* __restrict__ delta, P2PView pv = P2PView{}, unsigned int* ticket = nullptr,
+                                                      double* __restrict__ Vout = nullptr, const double* __restrict__ delta_in = nullptr) {
+  // Vout != null: V_b goes there and W stays as it was (the chain-short schedule reads rows of W_b for the next block's G while
+  // this kernel runs); delta_in != null: delta = delta_in + V_b y out of place (the next S_b reads delta_in meanwhile).
   extern __shared__ __align__(16) double vsm[];
   double* Lst = vsm;                         // packed block rows 1 .. 3 of L
   const double* const Lj[4] = {Lst, Lst, Lst + 32 * 36, Lst + 32 * 36 + 32 * 68};   // block row 0 is never read
@@ -655,14 +769,15 @@ __global__ void __launch_bounds__(VT_THREADS, 4) k_blk_V(double* __restrict__ W,
     part += __shfl_xor_sync(0xffffffffu, part, 1);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
     const int i = row0 + warp * 8 + (lane >> 2);
-    if ((lane & 3) == 0 && i < n && delta) delta[i] += part;
+    if ((lane & 3) == 0 && i < n && delta) delta[i] = (delta_in ? delta_in[i] : delta[i]) + part;
   }
   __syncthreads();
+  double* const dst = Vout ? Vout : W;
   for (int e = tid; e < VT_ROWS * EKF_UB / 2; e += VT_THREADS) {
     const int r = e >> 6, c = (e & 63) * 2;
     if (row0 + r < n) {
       const double2 v = *reinterpret_cast<const double2*>(Ws + r * VT_LD + c);
-      *reinterpret_cast<double2*>(W + (size_t)(row0 + r) * EKF_UB + c) = v;
+      *reinterpret_cast<double2*>(dst + (size_t)(row0 + r) * EKF_UB + c) = v;
       if (ticket) {   // all-gather fused into the solve: the finished rows go straight into every peer's panel over NVLink
         for (int q = 0; q < pv.world; ++q)
           if (q != pv.rank) *reinterpret_cast<double2*>(pv.w[q] + (size_t)(row0 + r) * EKF_UB + c) = v;
@@ -670,6 +785,145 @@ __global__ void __launch_bounds__(VT_THREADS, 4) k_blk_V(double* __restrict__ W,
     }
   }
   if (ticket) p2p_publish(pv, 8, ticket);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4b(0): G_b = H_b V_{b-1} WITHOUT waiting for V_{b-1} (chain-short schedule).  V_{b-1} = W_{b-1} L^-T, so
+//   G_b = (H_b W_{b-1}) L^-T :  X = H_b W_{b-1} reads only the 7 camera rows and the block's own feature rows of the (corrected)
+// panel W_{b-1}, and the triangular solve is the one of k_blk_V on 128 rows instead of n.  With it the n-row solve V_{b-1}
+// leaves the critical chain  factor_{b-1} -> G_b -> S_b -> factor_b  and runs beside factor_b on its own stream.
+// One CTA = 8 rows of G (4 features): the <= 31 rows of W it needs, L (packed), the diagonal-block inverses and y arrive by
+// cp.async, all in flight at once and none through registers (the CTA must start in what ONE retiring downdate CTA leaves:
+// 16 K registers); X is formed from shared memory and ONE warp solves the tile.  Also gy = G_b y_{b-1}, the term of nu_b that
+// delta does not hold yet.
+// ------------------------------------------------------------------------------------------------
+#define GX_FEATS 4
+#define GX_WROWS (7 + 6 * GX_FEATS)
+__global__ void __launch_bounds__(VT_THREADS, 4) k_blk_Gx(const double* __restrict__ Wc, FeatTab ft, int f0, int cnt,
+                                                          const double* __restrict__ Lg, const double* __restrict__ Dg,
+                                                          const double* __restrict__ yg, double* __restrict__ G, double* __restrict__ gy,
+                                                          BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}) {
+  extern __shared__ __align__(16) double gxsm[];
+  __shared__ int poss[GX_FEATS], nds[GX_FEATS], fids[GX_FEATS];
+  double* Lst = gxsm;
+  const double* const Lj[4] = {Lst, Lst, Lst + 32 * 36, Lst + 32 * 36 + 32 * 68};
+  const int ldj[4] = {36, 36, 68, 100};
+  double* Ds = Lst + VT_LPACK;
+  double* Xs = Ds + (EKF_UB / 32) * 32 * VT_LDD;   // [8][VT_LD]: X rows, then G rows
+  double* ys = Xs + 8 * VT_LD;                     // [EKF_UB]
+  double* Wr = ys + EKF_UB;                        // [GX_WROWS][EKF_UB]: camera rows 0..6 of W, then 6 rows per feature
+  double* Hs = Wr + GX_WROWS * EKF_UB;             // [GX_FEATS][26]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = min(EKF_UB / 2, cnt - f0);
+  const int a0 = blockIdx.x * GX_FEATS;
+  if (tid < GX_FEATS) {
+    const int a = a0 + tid;
+    if (a < nb && bt.H) { fids[tid] = 0; poss[tid] = bt.pos[f0 + a]; nds[tid] = bt.nd[f0 + a]; }
+    else if (a < nb) {
+      const int f = ft.sel[f0 + a];
+      fids[tid] = f; poss[tid] = ft.pos[f]; nds[tid] = 7 + (ft.coding[f] ? 3 : 6);
+    } else { fids[tid] = -1; poss[tid] = 0; nds[tid] = 0; }
+  }
+  auto cp16 = [](double* sdst, const double* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc));
+  };
+  // operands that do not depend on the feature table first: their copies fly while the table look-ups return
+  for (int e = tid; e < (EKF_UB / 32) * 32 * 16; e += VT_THREADS) {
+    const int r = e >> 4, c = (e & 15) * 2;
+    cp16(Ds + r * VT_LDD + c, Dg + r * 32 + c);
+  }
+  for (int e = tid; e < (EKF_UB - 32) * (EKF_UB - 32) / 2; e += VT_THREADS) {
+    const int r = 32 + e / ((EKF_UB - 32) / 2), c = (e % ((EKF_UB - 32) / 2)) * 2;
+    if (c < (r & ~31)) {
+      const int J = r >> 5;
+      const int offJ = J == 1 ? 0 : (J == 2 ? 32 * 36 : 32 * 36 + 32 * 68);
+      cp16(Lst + offJ + (r & 31) * (32 * J + 4) + c, Lg + r * EKF_UB + c);
+    }
+  }
+  for (int e = tid; e < 7 * (EKF_UB / 2); e += VT_THREADS) {
+    const int r = e >> 6, c = (e & 63) * 2;
+    cp16(Wr + r * EKF_UB + c, Wc + (size_t)r * EKF_UB + c);
+  }
+  for (int e = tid; e < EKF_UB; e += VT_THREADS) ys[e] = yg[e];
+  __syncthreads();
+  for (int e = tid; e < 6 * GX_FEATS * (EKF_UB / 2); e += VT_THREADS) {
+    const int rr = e >> 6, c = (e & 63) * 2, a = rr / 6, k = rr % 6;
+    double* d = Wr + (7 + rr) * EKF_UB + c;
+    if (7 + k < nds[a]) cp16(d, Wc + (size_t)(poss[a] + k) * EKF_UB + c);
+    else *reinterpret_cast<double2*>(d) = make_double2(0.0, 0.0);
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+  for (int e = tid; e < GX_FEATS * 26; e += VT_THREADS)
+    Hs[e] = fids[e / 26] < 0 ? 0.0 : (bt.H ? bt.H[26 * (size_t)(f0 + a0) + e] : ft.Hc[26 * fids[e / 26] + e % 26]);
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  __syncthreads();
+  // X = H_b W_{b-1}: 8 rows x 64 column pairs, two per thread
+  for (int e = tid; e < 8 * (EKF_UB / 2); e += VT_THREADS) {
+    const int r = e >> 6, c = (e & 63) * 2, a = r >> 1;
+    const double* hr = Hs + a * 26 + 13 * (r & 1);
+    const int nd = nds[a];
+    double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 13; ++q) {
+      if (q < nd) {
+        const double2 v = *reinterpret_cast<const double2*>(Wr + (q < 7 ? q : 7 + 6 * a + (q - 7)) * EKF_UB + c);
+        x0 += hr[q] * v.x; x1 += hr[q] * v.y;
+      }
+    }
+    *reinterpret_cast<double2*>(Xs + r * VT_LD + c) = make_double2(x0, x1);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double part = warp_trsm_tile_packed<EKF_UB>(Xs, VT_LD, Lj, ldj, Ds, VT_LDD, ys);
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    if ((lane & 3) == 0) gy[8 * blockIdx.x + (lane >> 2)] = part;
+  }
+  __syncthreads();
+  for (int e = tid; e < 8 * (EKF_UB / 2); e += VT_THREADS) {
+    const int r = e >> 6, c = (e & 63) * 2;
+    *reinterpret_cast<double2*>(G + (size_t)(8 * blockIdx.x + r) * EKF_UB + c) = *reinterpret_cast<const double2*>(Xs + r * VT_LD + c);
+  }
+}
+
+// Chain-short schedule, gather beside the downdate: for every update block g one CTA lists the T (T + 1) / 2 tiles (64 x 64) of the
+// lower triangle with the tiles the gather of block g reads FIRST — tile (tm, tn) is hot when tm or tn is an index range holding
+// the camera columns or one of the block's features (with the mirrored store these are all entries of those columns) — and counts
+// them.  k_gemm_nt_sub walks the list; the gather waits for the count (k_blk_gather, hot_counter).
+__global__ void __launch_bounds__(1024) k_blk_tile_order(FeatTab ft, int cnt, int T, ushort2* __restrict__ order, int* __restrict__ n_hot,
+                                                         unsigned int* __restrict__ hot_counters) {
+  __shared__ unsigned long long m[2];
+  __shared__ int c_hot, c_cold;
+  const int g = blockIdx.x, tid = threadIdx.x, f0 = g * (EKF_UB / 2);
+  if (tid < 2) m[tid] = (tid == 0) ? 1ull : 0ull;   // columns 0 .. 6 live in range 0
+  if (tid == 0) { c_hot = 0; c_cold = 0; hot_counters[g] = 0u; }
+  __syncthreads();
+  if (tid < EKF_UB / 2 && f0 + tid < cnt) {
+    const int f = ft.sel[f0 + tid];
+    const int pos = ft.pos[f], last = pos + (ft.coding[f] ? 2 : 5);
+    for (int t = pos >> 6; t <= (last >> 6); ++t) atomicOr(&m[(t >> 6) & 1], 1ull << (t & 63));
+  }
+  __syncthreads();
+  const int L = T * (T + 1) / 2;
+  ushort2* out = order + (size_t)g * L;
+  for (int idx = tid; idx < L; idx += blockDim.x) {
+    int tm = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+    while ((tm + 1) * (tm + 2) / 2 <= idx) ++tm;
+    while (tm * (tm + 1) / 2 > idx) --tm;
+    const int tn = idx - tm * (tm + 1) / 2;
+    const bool hot = ((m[(tm >> 6) & 1] >> (tm & 63)) | (m[(tn >> 6) & 1] >> (tn & 63))) & 1ull;
+    const int at = hot ? atomicAdd(&c_hot, 1) : L - 1 - atomicAdd(&c_cold, 1);
+    out[at] = make_ushort2((unsigned short)tm, (unsigned short)tn);
+  }
+  __syncthreads();
+  if (tid == 0) n_hot[g] = c_hot;
+}
+void launch_blk_tile_order(cudaStream_t st, FeatTab ft, int cnt, int T, ushort2* order, int* n_hot, unsigned int* hot_counters, long long* launches) {
+  const int nblk = (cnt + EKF_UB / 2 - 1) / (EKF_UB / 2);
+  if (nblk <= 0) return;
+  k_blk_tile_order<<<nblk, 1024, 0, st>>>(ft, cnt, T, order, n_hot, hot_counters);
+  *launches += 1;
 }
 
 // delta += V y for ALL rows, one warp per row (row-block partition: every rank runs this on the all-gathered V so that
@@ -728,6 +982,7 @@ static const size_t kFactSmemOld = (size_t)cta_chol_panel_smem_doubles<EKF_UB>()
 static const size_t kFactSmem = sizeof(Chol128Smem);
 static int g_chol_smem = 0;   // EKF_CHOL_SMEM=1: the round-1 shared-memory factor kernel
 static const size_t kVSmem = (size_t)(VT_LPACK + (EKF_UB / 32) * 32 * VT_LDD + VT_ROWS * VT_LD + EKF_UB) * sizeof(double);
+static const size_t kGxSmem = (size_t)(VT_LPACK + (EKF_UB / 32) * 32 * VT_LDD + 8 * VT_LD + EKF_UB + GX_WROWS * EKF_UB + GX_FEATS * 26) * sizeof(double);
 
 int update_kernels_init() {
   const char* env = getenv("EKF_CHOL_SMEM");
@@ -738,9 +993,13 @@ int update_kernels_init() {
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_blk_S_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 32 * S2_LD * sizeof(double)));
   if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_blk_Sg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 32 * S2_LD * sizeof(double)));
+  if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_blk_factor_p2p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFactSmem);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_blk_V, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVSmem);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_blk_Gx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGxSmem);
   return (int)e;
 }
 
@@ -791,18 +1050,53 @@ void launch_blk_S_nu(cudaStream_t st, const double* W, FeatTab ft, int f0, int c
 }
 // S_b from the uncorrected gather and G (see k_blk_S), and the gather with a second copy of W'
 void launch_blk_S_nu_G(cudaStream_t st, const double* Wraw, FeatTab ft, int f0, int cnt, const DevCfg& cfg, const double* delta,
-                       const double* G, double* Sb, double* nu, long long* launches) {
+                       const double* G, double* Sb, double* nu, long long* launches, const double* gy, BlkTab bt, const double* Sg) {
   static const bool legacy = [] { const char* e = getenv("EKF_S_TILED"); return e && atoi(e) == 0; }();
-  if (legacy) k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(Wraw, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, delta, nu, G);
-  else k_blk_S_tiled<<<10, 128, 2 * 32 * S2_LD * sizeof(double), st>>>(Wraw, ft, f0, cnt, cfg.sigma_pixel_2, Sb, delta, nu, G);
+  if (legacy && !gy && !Sg) k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(Wraw, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, delta, nu, G);
+  else k_blk_S_tiled<<<10, 128, Sg ? 0 : 2 * 32 * S2_LD * sizeof(double), st>>>(Wraw, ft, f0, cnt, cfg.sigma_pixel_2, Sb, delta, nu, Sg ? nullptr : G, gy, bt, Sg);
+  *launches += 1;
+}
+void launch_blk_Sg(cudaStream_t st, const double* G, double* Sg, long long* launches) {
+  k_blk_Sg<<<10, 128, 2 * 32 * S2_LD * sizeof(double), st>>>(G, Sg);
+  *launches += 1;
+}
+void launch_blk_prep(cudaStream_t st, FeatTab ft, int cnt, double* H, double* zmh, int* pos, int* nd, long long* launches) {
+  if (cnt <= 0) return;
+  k_blk_prep<<<(cnt + 3) / 4, 128, 0, st>>>(ft, cnt, H, zmh, pos, nd);
+  *launches += 1;
+}
+// G_b = (H_b W_{b-1}) L_{b-1}^-T and gy = G_b y_{b-1} (see k_blk_Gx)
+void launch_blk_Gx(cudaStream_t st, const double* Wc, FeatTab ft, int f0, int cnt, const double* Lb, const double* Dblk, const double* yb,
+                   double* G, double* gy, long long* launches, BlkTab bt) {
+  k_blk_Gx<<<EKF_UB / 8, VT_THREADS, kGxSmem, st>>>(Wc, ft, f0, cnt, Lb, Dblk, yb, G, gy, bt);
   *launches += 1;
 }
 void launch_blk_gather2(cudaStream_t st, const double* Sigma, int ld, int n, FeatTab ft, int f0, int cnt, double* W, double* W2,
-                        long long* launches) {
+                        long long* launches, BlkTab bt) {
   const int nr = n > 0 ? n : 1;
   const int gr = gather_rows();
-  k_blk_gather<<<(nr + gr - 1) / gr, 256, 0, st>>>(Sigma, ld, 0, n, ft, f0, cnt, nullptr, W, nullptr, W2, gr);
+  k_blk_gather<<<(nr + gr - 1) / gr, 256, 0, st>>>(Sigma, ld, 0, n, ft, f0, cnt, nullptr, W, nullptr, W2, gr, bt);
   *launches += 1;
+}
+// Gate of the gather that runs beside a downdate: one warp waits (acquire, bounded) until the downdate's first *n_hot tiles — the
+// ones holding the columns the gather reads — are stored (k_blk_tile_order / k_gemm_nt_sub); the gather follows it in stream order.
+// A gate instead of a wait inside the gather: a spinning gather grid would hold registers the downdate's own CTAs need.
+__global__ void k_wait_tiles(const unsigned int* hot_counter, const int* __restrict__ n_hot, DevCtl* ctl) {
+  if (threadIdx.x != 0) return;
+  const unsigned int want = (unsigned int)*n_hot;
+  unsigned int seen = 0;
+  for (long long spins = 0;; ++spins) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(hot_counter) : "memory");
+    if (seen >= want) break;
+    if (spins > 4000000ll) { atomicOr(&ctl->chol_fail, 64); break; }   // seconds: report instead of hanging
+    __nanosleep(100);
+  }
+}
+void launch_blk_gather2_after_tiles(cudaStream_t st, const double* Sigma, int ld, int n, FeatTab ft, int f0, int cnt, double* W, double* W2,
+                                    const unsigned int* hot_counter, const int* n_hot, DevCtl* ctl, long long* launches, BlkTab bt) {
+  k_wait_tiles<<<1, 32, 0, st>>>(hot_counter, n_hot, ctl);
+  *launches += 1;
+  launch_blk_gather2(st, Sigma, ld, n, ft, f0, cnt, W, W2, launches, bt);
 }
 void launch_blk_G(cudaStream_t st, const double* Vprev, FeatTab ft, int f0, int cnt, double* G, long long* launches) {
   k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(Vprev, ft, f0, cnt, 0.0, G, 1, nullptr, nullptr, nullptr);
@@ -815,9 +1109,9 @@ void launch_blk_factor_only(cudaStream_t st, const double* Sb, const double* nu,
   *launches += 1;
 }
 void launch_blk_V(cudaStream_t st, double* W, int row0, int row1, const double* Lb, const double* Dblk, const double* yb,
-                  double* delta, long long* launches) {
+                  double* delta, long long* launches, double* Vout, const double* delta_in) {
   if (row1 <= row0) return;
-  k_blk_V<<<(row1 - row0 + VT_ROWS - 1) / VT_ROWS, VT_THREADS, kVSmem, st>>>(W, row0, row1, Lb, Dblk, yb, delta);
+  k_blk_V<<<(row1 - row0 + VT_ROWS - 1) / VT_ROWS, VT_THREADS, kVSmem, st>>>(W, row0, row1, Lb, Dblk, yb, delta, P2PView{}, nullptr, Vout, delta_in);
   *launches += 1;
 }
 void launch_blk_S_part(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const DevCfg& cfg, int row0, int row1, int add_diag,

@@ -112,15 +112,24 @@ def test_multi_block_update(gpu_pkg, orc, symmetric):
         assert_state_close(g, o, ctx=f"frame {t} multi-block")
 
 
-@pytest.mark.parametrize("env,n_features", [("EKF_LOOKAHEAD_MIN_N", 150), ("EKF_PIPE_MIN_N", 150), ("EKF_PIPE_MIN_N", 210)])
-def test_lookahead_pipeline_parity(gpu_pkg, orc, monkeypatch, env, n_features):
-    """The two pipelined stacked updates forced on at n = 914 (three update blocks) and n = 1274 (four): the look-ahead
-    schedule (second stream, W correction GEMM; default for n >= 6000) and the factor-beside-downdate schedule (S_b from the raw
-    gather minus G G^T, correction on a third stream; default for 1000 <= n < 6000).  Same tolerance as the plain path."""
+@pytest.mark.parametrize("env,n_features,sched", [("EKF_LOOKAHEAD_MIN_N", 150, 1), ("EKF_PIPE_MIN_N", 150, 0), ("EKF_PIPE_MIN_N", 210, 0),
+                                                  ("EKF_PIPE_MIN_N", 150, 1), ("EKF_PIPE_MIN_N", 210, 1), ("EKF_PIPE_MIN_N", 290, 1),
+                                                  ("EKF_PIPE_MIN_N", 290, 2)])
+def test_lookahead_pipeline_parity(gpu_pkg, orc, monkeypatch, env, n_features, sched):
+    """The pipelined stacked updates forced on at n = 914 (three update blocks), 1274 (four) and 1754 (five, the last one
+    partial): the look-ahead schedule (second stream, W correction GEMM; default for n >= 6000) and the two schedules for
+    1000 <= n < 6000 — factor-beside-downdate (EKF_SCHED=0: S_b from the raw gather minus G G^T, correction on a third stream)
+    and chain-short (EKF_SCHED=1, default: G_b by a 128-row solve on rows of W_{b-1}, the n-row solve V_b off the chain on a
+    fourth stream, delta ping-pong).  Same tolerance as the plain path."""
     monkeypatch.setenv("EKF_LOOKAHEAD_MIN_N", "1000000")
     monkeypatch.setenv(env, "1")
+    monkeypatch.setenv("EKF_SCHED", str(min(sched, 1)))
+    if sched == 2:   # chain-short with the downdate walking the hot-first tile list and the next gather gated on its hot tiles
+        monkeypatch.setenv("EKF_SPLIT_DD", "1")
     sc = _scene(gpu_pkg, n_features=n_features, n_frames=4, seed=6)
     g, o = make_pair(gpu_pkg, orc, sc)
+    if sched == 2:
+        g.set_symmetric_downdate(1)   # the tile list enumerates the lower triangle
     seed_features(g, sc); seed_features(o, sc)
     for t in range(1, 4):
         mu, S = o.get_full(); g.set_full(mu, S)
