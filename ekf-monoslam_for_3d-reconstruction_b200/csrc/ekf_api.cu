@@ -245,6 +245,8 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
     // 0.764 against 0.786 ms per cfg2 step), 0 = factor-beside-downdate — see DESIGN.md section 4
     e = getenv("EKF_SCHED");
     h->sched = e ? atoi(e) : 1;
+    e = getenv("EKF_PRELAUNCH");
+    h->prelaunch_on = e ? atoi(e) : 1;
     e = getenv("EKF_SPLIT_DD");
     h->split_dd = e ? atoi(e) : 0;   // 0: 2-D grid; 1: tile list, the next gather gated on its hot tiles; 2: tile list only
   }
@@ -724,6 +726,32 @@ static int stacked_update_factor_beside_downdate(ekf_handle* h, int cnt) {
 //   corr:  W_b = W'_b - V_{b-1} G_b^T             (beside factor_b; needs all of V_{b-1})
 //   second: downdate_{b-1} (released by S_b, as before) -> gather of W'_{b+1}
 // Two sets of factor outputs (L, D, y) alternate: V_{b-1} reads one while factor_b writes the other.
+// Whether the low-innovation update of this step will take the chain-short schedule, as far as the host knows BEFORE it has read
+// n_li back: if so, ekf_update_after_match starts the block tables and the first two gathers (which read only the prior covariance and
+// the inlier list the RANSAC kernel left on the device) while that read-back is in flight.
+static bool chain_short_likely(const ekf_handle* h) {
+  const bool partitioned = h->nccl_comm && h->world > 1;
+  if (partitioned || h->sched != 1 || h->pipe_small <= 0 || h->n < h->pipe_small) return false;
+  if (h->lookahead > 0 && h->n >= h->lookahead) return false;
+  return h->N > EKF_UB / 2;
+}
+static void chain_short_prelaunch(ekf_handle* h) {
+  cudaStream_t sm = h->stream, sg = h->gemm_stream;
+  const BlkTab bt{h->bt_H, h->bt_zmh, h->bt_pos, h->bt_nd};
+  cudaEventRecord(h->ev_fork, sm);
+  cudaStreamWaitEvent(sg, h->ev_fork, 0);
+  // everything on the second stream: the host's wait on the main stream must not include it
+  launch_blk_prep(sg, h->ft, h->N, h->bt_H, h->bt_zmh, h->bt_pos, h->bt_nd, &h->launches, &h->ctl->n_li);
+  double* raw[2] = {h->Wbuf[1], h->Wbuf[2]};
+  double* cor[2] = {h->Wbuf[0], h->Wbuf[3]};
+  for (int b = 0; b < 2; ++b) {
+    ProfScope ps(h, 3, sg); TraceScope ts("gather", b, sg);
+    launch_blk_gather2(sg, h->Sigma, h->ld, h->n, h->ft, b * (EKF_UB / 2), 0, raw[b], cor[b], &h->launches, bt, &h->ctl->n_li);
+    cudaEventRecord(h->ev_gather[b], sg);
+  }
+  h->prelaunched = true;
+}
+
 static int stacked_update_chain_short(ekf_handle* h, int cnt) {
   cudaStream_t sm = h->stream, sg = h->gemm_stream, sc = h->corr_stream, sv = h->v_stream;
   const int nblk = (cnt + EKF_UB / 2 - 1) / (EKF_UB / 2);
@@ -741,12 +769,14 @@ static int stacked_update_chain_short(ekf_handle* h, int cnt) {
   const bool split = h->split_dd && nblk > 2 && h->lower_only && T <= h->tile_T_cap && nblk <= h->tile_blk_cap && gemm_uses_square_tiles();
   cudaStream_t sgat = (split && gate) ? h->gather_stream : sg;
   const BlkTab bt{h->bt_H, h->bt_zmh, h->bt_pos, h->bt_nd};
-  launch_blk_prep(sm, h->ft, cnt, h->bt_H, h->bt_zmh, h->bt_pos, h->bt_nd, &h->launches);
+  const bool pre = h->prelaunched;   // tables and the first two gathers are already under way
+  h->prelaunched = false;
+  if (!pre) launch_blk_prep(sm, h->ft, cnt, h->bt_H, h->bt_zmh, h->bt_pos, h->bt_nd, &h->launches);
   if (split) launch_blk_tile_order(sm, h->ft, cnt, T, h->tile_order, h->tile_nhot, h->tile_counters, &h->launches);
   cudaEventRecord(h->ev_fork, sm);
   cudaStreamWaitEvent(sg, h->ev_fork, 0);
   cudaStreamWaitEvent(sv, h->ev_fork, 0);
-  for (int b = 0; b < nblk && b < 2; ++b) {   // W'_0 = W_0 and W'_1, both from the prior covariance
+  for (int b = 0; b < nblk && b < 2 && !pre; ++b) {   // W'_0 = W_0 and W'_1, both from the prior covariance
     ProfScope ps(h, 3, sg); TraceScope ts("gather", b, sg);
     launch_blk_gather2(sg, h->Sigma, h->ld, h->n, h->ft, b * (EKF_UB / 2), cnt, raw[b], cor[b], &h->launches, bt);
     cudaEventRecord(h->ev_gather[b], sg);
@@ -837,6 +867,11 @@ static int stacked_update(ekf_handle* h, int cnt, bool plane = false) {
     if (!partitioned && h->pipe_small > 0 && h->n >= h->pipe_small)
       return h->sched == 1 ? stacked_update_chain_short(h, cnt) : stacked_update_factor_beside_downdate(h, cnt);
   }
+  if (h->prelaunched) {   // the speculative gathers of the chain-short schedule wrote the W panels on the second stream: order after them
+    cudaStreamWaitEvent(h->stream, h->ev_gather[0], 0);
+    cudaStreamWaitEvent(h->stream, h->ev_gather[1], 0);
+    h->prelaunched = false;
+  }
   cudaStream_t st = h->stream;
   // Row-block partition (BASELINE config 4): every rank holds a replica of Sigma, updates only its
   // rows [r0, r1) and exchanges the small panels: W_b rows (S_b needs the camera / feature rows of W_b),
@@ -919,9 +954,15 @@ int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
     ProfScope ps(h, 2);
     launch_ransac(st, h->Sigma, h->ld, h->n, h->mu, h->ft, h->N, h->ctl, h->dcfg, h->picks_dev, n_picks, h->mu_i, h->cand, &h->launches);
   }
+  if (h->prelaunch_on && chain_short_likely(h)) chain_short_prelaunch(h);   // GPU work for the duration of the read-back
   EKF_CUDA_CHECK(cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost, st));
   EKF_CUDA_CHECK(cudaStreamSynchronize(st));
   const int n_li = hc.n_li;
+  if (n_li <= 0 && h->prelaunched) {   // no update after all: keep later work on the main stream behind the speculative gathers
+    cudaStreamWaitEvent(st, h->ev_gather[0], 0);
+    cudaStreamWaitEvent(st, h->ev_gather[1], 0);
+    h->prelaunched = false;
+  }
   if (n_li > 0) {
     static const bool host_timing = getenv("EKF_HOST_TIMING") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();

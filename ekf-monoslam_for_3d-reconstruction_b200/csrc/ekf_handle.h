@@ -65,6 +65,8 @@ struct ekf_handle {
   unsigned int* tile_counters = nullptr;  // [blocks]
   int tile_T_cap = 0, tile_blk_cap = 0;
   int split_dd = 0;       // chain-short only (EKF_SPLIT_DD): 1 = tile list, hot tiles first, the next gather gated on them; 2 = tile list only
+  bool prelaunched = false;   // block tables + first two gathers were started before the n_li read-back (chain_short_prelaunch)
+  int prelaunch_on = 1;       // EKF_PRELAUNCH=0 switches that off
   int sched = 1;          // 1: chain-short (default for pipe_small <= n < lookahead), 0: factor-beside-downdate (EKF_SCHED)
   cudaEvent_t ev_gather[3] = {nullptr, nullptr, nullptr}, ev_V[3] = {nullptr, nullptr, nullptr}, ev_fork = nullptr, ev_join = nullptr, ev_S = nullptr, ev_G = nullptr, ev_corr = nullptr;
   int pipe_small = 1000;  // minimum state dimension for the factor-beside-downdate schedule (0 = never)

@@ -52,7 +52,8 @@ void launch_blk_S_nu_G(cudaStream_t st, const double* Wraw, FeatTab ft, int f0, 
                        const double* G, double* Sb, double* nu, long long* launches, const double* gy = nullptr,
                        BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}, const double* Sg = nullptr);
 void launch_blk_Sg(cudaStream_t st, const double* G, double* Sg, long long* launches);
-void launch_blk_prep(cudaStream_t st, FeatTab ft, int cnt, double* H, double* zmh, int* pos, int* nd, long long* launches);
+void launch_blk_prep(cudaStream_t st, FeatTab ft, int cnt, double* H, double* zmh, int* pos, int* nd, long long* launches,
+                     const int* cnt_dev = nullptr);
 // per update block g: the 64 x 64 tiles of the lower triangle (T x T tiles) ordered with the tiles gather g reads first; n_hot[g] of them
 void launch_blk_tile_order(cudaStream_t st, FeatTab ft, int cnt, int T, ushort2* order, int* n_hot, unsigned int* hot_counters, long long* launches);
 // the gather of block f0 / 64 started BESIDE the downdate that produces its columns: waits until hot_counter reaches *n_hot
@@ -62,7 +63,7 @@ void launch_blk_gather2_after_tiles(cudaStream_t st, const double* Sigma, int ld
 void launch_blk_Gx(cudaStream_t st, const double* Wc, FeatTab ft, int f0, int cnt, const double* Lb, const double* Dblk, const double* yb,
                    double* G, double* gy, long long* launches, BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr});
 void launch_blk_gather2(cudaStream_t st, const double* Sigma, int ld, int n, FeatTab ft, int f0, int cnt, double* W, double* W2,
-                        long long* launches, BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr});
+                        long long* launches, BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}, const int* cnt_dev = nullptr);
 void launch_blk_G(cudaStream_t st, const double* Vprev, FeatTab ft, int f0, int cnt, double* G, long long* launches);
 void launch_blk_factor_only(cudaStream_t st, const double* Sb, const double* nu, double* Lb, double* Dblk, double* yb, DevCtl* ctl,
                             long long* launches);

@@ -305,7 +305,8 @@ static int gather_rows() {
 __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ Sigma, int ld, int row0, int n, FeatTab ft, int f0,
                                                     int cnt, const double* __restrict__ delta, double* __restrict__ W,
                                                     double* __restrict__ nu, double* __restrict__ W2, int rows_per_cta,
-                                                    BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}) {
+                                                    BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}, const int* __restrict__ cnt_dev = nullptr) {
+  if (cnt_dev) cnt = *cnt_dev;   // launched before the host has read the count back (see ekf_update_after_match)
   // Sigma is read past L1 (ld.global.cg): in the chain-short schedule this kernel runs BESIDE the downdate that still writes the
   // tiles it does not read (k_wait_tiles gates it), so no line of Sigma may be served from a stale L1 copy.
   __shared__ double Hs[EKF_UB / 2][27];
@@ -626,7 +627,8 @@ __global__ void __launch_bounds__(128) k_blk_Sg(const double* __restrict__ Gsub,
 
 // Compact tables of the selected features for the block kernels (BlkTab), once per stacked update.
 __global__ void __launch_bounds__(128) k_blk_prep(FeatTab ft, int cnt, double* __restrict__ H, double* __restrict__ zmh, int* __restrict__ pos,
-                                                  int* __restrict__ nd) {
+                                                  int* __restrict__ nd, const int* __restrict__ cnt_dev) {
+  if (cnt_dev) cnt = *cnt_dev;
   const int j = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (j >= cnt) return;
   const int f = ft.sel[j];
@@ -1060,9 +1062,9 @@ void launch_blk_Sg(cudaStream_t st, const double* G, double* Sg, long long* laun
   k_blk_Sg<<<10, 128, 2 * 32 * S2_LD * sizeof(double), st>>>(G, Sg);
   *launches += 1;
 }
-void launch_blk_prep(cudaStream_t st, FeatTab ft, int cnt, double* H, double* zmh, int* pos, int* nd, long long* launches) {
-  if (cnt <= 0) return;
-  k_blk_prep<<<(cnt + 3) / 4, 128, 0, st>>>(ft, cnt, H, zmh, pos, nd);
+void launch_blk_prep(cudaStream_t st, FeatTab ft, int cnt, double* H, double* zmh, int* pos, int* nd, long long* launches, const int* cnt_dev) {
+  if (cnt <= 0) return;   // with cnt_dev: cnt is the upper bound that sizes the grid
+  k_blk_prep<<<(cnt + 3) / 4, 128, 0, st>>>(ft, cnt, H, zmh, pos, nd, cnt_dev);
   *launches += 1;
 }
 // G_b = (H_b W_{b-1}) L_{b-1}^-T and gy = G_b y_{b-1} (see k_blk_Gx)
@@ -1072,10 +1074,10 @@ void launch_blk_Gx(cudaStream_t st, const double* Wc, FeatTab ft, int f0, int cn
   *launches += 1;
 }
 void launch_blk_gather2(cudaStream_t st, const double* Sigma, int ld, int n, FeatTab ft, int f0, int cnt, double* W, double* W2,
-                        long long* launches, BlkTab bt) {
+                        long long* launches, BlkTab bt, const int* cnt_dev) {
   const int nr = n > 0 ? n : 1;
   const int gr = gather_rows();
-  k_blk_gather<<<(nr + gr - 1) / gr, 256, 0, st>>>(Sigma, ld, 0, n, ft, f0, cnt, nullptr, W, nullptr, W2, gr, bt);
+  k_blk_gather<<<(nr + gr - 1) / gr, 256, 0, st>>>(Sigma, ld, 0, n, ft, f0, cnt, nullptr, W, nullptr, W2, gr, bt, cnt_dev);
   *launches += 1;
 }
 // Gate of the gather that runs beside a downdate: one warp waits (acquire, bounded) until the downdate's first *n_hot tiles — the
@@ -1096,7 +1098,7 @@ void launch_blk_gather2_after_tiles(cudaStream_t st, const double* Sigma, int ld
                                     const unsigned int* hot_counter, const int* n_hot, DevCtl* ctl, long long* launches, BlkTab bt) {
   k_wait_tiles<<<1, 32, 0, st>>>(hot_counter, n_hot, ctl);
   *launches += 1;
-  launch_blk_gather2(st, Sigma, ld, n, ft, f0, cnt, W, W2, launches, bt);
+  launch_blk_gather2(st, Sigma, ld, n, ft, f0, cnt, W, W2, launches, bt, nullptr);
 }
 void launch_blk_G(cudaStream_t st, const double* Vprev, FeatTab ft, int f0, int cnt, double* G, long long* launches) {
   k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(Vprev, ft, f0, cnt, 0.0, G, 1, nullptr, nullptr, nullptr);

@@ -16,7 +16,7 @@ python bench.py --full-square --no-cpu-baseline > $O/bench_full_$TAG.json 2>/dev
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $O/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on \
-    -k regex:"k_gemm_nt_sub|k_blk_factor|k_blk_V|k_blk_gather|k_match_filter|k_blk_S" -s 40 -c 14 -o $O/top_$TAG \
+    -k regex:"k_gemm_nt_sub|k_blk_factor|k_blk_V|k_blk_gather|k_match_filter|k_blk_S|k_blk_Gx|k_ransac|k_predict" -s 60 -c 40 -o $O/top_$TAG \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_full_$TAG.log 2>&1
 for f in $O/bench_*_$TAG.json $O/bench_$TAG.json; do echo $f; python - "$f" <<'PY'
 import json, sys
