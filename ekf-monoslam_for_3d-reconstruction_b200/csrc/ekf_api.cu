@@ -978,24 +978,32 @@ int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
     ProfScope ps(h, 8);
     launch_hi_rescue(st, h->Sigma, h->ld, h->mu, h->ft, h->N, h->ctl, h->dcfg, &h->launches);
   }
+  // The common case is n_hi == 0 (nothing rescued) without forsePlane: book-keeping and the packed result record are then enqueued
+  // BEFORE the host learns n_hi — the kernel checks the count itself and does nothing when a second update has to run first — so the
+  // step ends with one synchronize instead of two.
+  const bool plane = h->cfg.forsePlane != 0;
+  int* outi_dev = reinterpret_cast<int*>(h->out_dev + 210);
+  const size_t bytes = sizeof(double) * 210 + sizeof(int) * (16 + 3 * (size_t)h->N);
+  if (!plane) {
+    { ProfScope ps(h, 9); launch_bookkeeping(st, h->Sigma, h->ld, h->mu, h->ft, h->N, h->ctl, h->dcfg, h->out_dev, outi_dev, &h->launches, 1); }
+    EKF_CUDA_CHECK(cudaMemcpyAsync(h->out_host, h->out_dev, bytes, cudaMemcpyDeviceToHost, st));
+  }
   EKF_CUDA_CHECK(cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost, st));
   EKF_CUDA_CHECK(cudaStreamSynchronize(st));
   const int n_hi = hc.n_hi;
-  const bool plane = h->cfg.forsePlane != 0;
   if (n_hi > 0 || plane) {
     int rc = stacked_update(h, n_hi, plane);
     if (rc) return ekf_fail_cuda(h, (cudaError_t)rc, "stacked update (hi)", __FILE__, __LINE__);
-  }
-  // book-keeping + packed result record
-  int* outi_dev = reinterpret_cast<int*>(h->out_dev + 210);
-  {
-    ProfScope ps(h, 9);
-    launch_bookkeeping(st, h->Sigma, h->ld, h->mu, h->ft, h->N, h->ctl, h->dcfg, h->out_dev, outi_dev, &h->launches);
+    // book-keeping + packed result record
+    {
+      ProfScope ps(h, 9);
+      launch_bookkeeping(st, h->Sigma, h->ld, h->mu, h->ft, h->N, h->ctl, h->dcfg, h->out_dev, outi_dev, &h->launches);
+    }
+    EKF_CUDA_CHECK(cudaGetLastError());
+    EKF_CUDA_CHECK(cudaMemcpyAsync(h->out_host, h->out_dev, bytes, cudaMemcpyDeviceToHost, st));
+    EKF_CUDA_CHECK(cudaStreamSynchronize(st));
   }
   EKF_CUDA_CHECK(cudaGetLastError());
-  const size_t bytes = sizeof(double) * 210 + sizeof(int) * (16 + 3 * (size_t)h->N);
-  EKF_CUDA_CHECK(cudaMemcpyAsync(h->out_host, h->out_dev, bytes, cudaMemcpyDeviceToHost, st));
-  EKF_CUDA_CHECK(cudaStreamSynchronize(st));
   prof_flush(h);
   trace_flush();
   const int* outi = reinterpret_cast<const int*>(h->out_host + 210);

@@ -83,7 +83,7 @@ void launch_blk_V_p2p(cudaStream_t st, double* W, int row0, int row1, const doub
                       DevCtl* ctl, long long* launches);
 void launch_delta_rows(cudaStream_t st, const double* V, const double* y, double* delta, int n, long long* launches);
 void launch_bookkeeping(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, DevCtl* ctl,
-                        const DevCfg& cfg, double* outd, int* outi, long long* launches);
+                        const DevCfg& cfg, double* outd, int* outi, long long* launches, int speculative = 0);
 // ekf_export.cu
 void launch_points_features(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, double* out, int rows,
                             long long* launches);

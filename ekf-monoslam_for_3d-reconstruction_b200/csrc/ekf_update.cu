@@ -954,7 +954,10 @@ __global__ void __launch_bounds__(256) k_delta_rows(const double* __restrict__ V
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_bookkeeping(const double* __restrict__ Sigma, int ld, const double* __restrict__ mu,
                                                      FeatTab ft, int N, DevCtl* ctl, DevCfg cfg, double* __restrict__ outd,
-                                                     int* __restrict__ outi) {
+                                                     int* __restrict__ outi, int speculative) {
+  // speculative: launched BEFORE the host knows n_hi (one synchronize less per step); when the rescue found something the second
+  // update has to run first, so this launch does nothing and the host launches the kernel again afterwards
+  if (speculative && ctl->n_hi > 0) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N) {
     int nfind = ft.n_find[i];
@@ -1149,8 +1152,8 @@ void launch_delta_rows(cudaStream_t st, const double* V, const double* y, double
   *launches += 1;
 }
 void launch_bookkeeping(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, DevCtl* ctl,
-                        const DevCfg& cfg, double* outd, int* outi, long long* launches) {
+                        const DevCfg& cfg, double* outd, int* outi, long long* launches, int speculative) {
   const int fb = N > 0 ? (N + 255) / 256 : 1;
-  k_bookkeeping<<<fb, 256, 0, st>>>(Sigma, ld, mu, ft, N, ctl, cfg, outd, outi);
+  k_bookkeeping<<<fb, 256, 0, st>>>(Sigma, ld, mu, ft, N, ctl, cfg, outd, outi, speculative);
   *launches += 1;
 }
