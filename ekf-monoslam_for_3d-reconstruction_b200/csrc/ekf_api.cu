@@ -136,9 +136,11 @@ int ekf_destroy(ekf_handle* h) {
   cudaFree(h->picks_dev); cudaFree(h->out_dev); cudaFree(h->gemm_counters);
   if (h->gemm_stream) { cudaStreamSynchronize(h->gemm_stream); cudaStreamDestroy(h->gemm_stream); }
   cudaFree(h->Wbuf[1]); cudaFree(h->Wbuf[2]); cudaFree(h->Wbuf[3]); cudaFree(h->Wbuf[4]); cudaFree(h->Wbuf[5]); cudaFree(h->Gbuf);
-  cudaFree(h->Dinv2); cudaFree(h->Dblk2); cudaFree(h->yb2); cudaFree(h->delta1); cudaFree(h->delta2); cudaFree(h->gy); cudaFree(h->bt_H); cudaFree(h->bt_zmh); cudaFree(h->Sgbuf); cudaFree(h->bt_pos); cudaFree(h->bt_nd); cudaFree(h->tile_order); cudaFree(h->tile_nhot); cudaFree(h->tile_counters);
+  cudaFree(h->Dinv2); cudaFree(h->Dblk2); cudaFree(h->yb2); cudaFree(h->delta1); cudaFree(h->delta2); cudaFree(h->gy); cudaFree(h->bt_H); cudaFree(h->bt_zmh); cudaFree(h->Sgbuf); cudaFree(h->bt_pos); cudaFree(h->bt_nd); cudaFree(h->chain_flags); cudaFree(h->tile_order); cudaFree(h->tile_nhot); cudaFree(h->tile_counters);
   if (h->v_stream) { cudaStreamSynchronize(h->v_stream); cudaStreamDestroy(h->v_stream); }
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  if (h->chain_stream) { cudaStreamSynchronize(h->chain_stream); cudaStreamDestroy(h->chain_stream); }
+  if (h->ev_chain) cudaEventDestroy(h->ev_chain);
   if (h->ev_frame) cudaEventDestroy(h->ev_frame);
   if (h->ev_prev) cudaEventDestroy(h->ev_prev);
   if (h->gather_stream) { cudaStreamSynchronize(h->gather_stream); cudaStreamDestroy(h->gather_stream); }
@@ -212,6 +214,7 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
   h->tile_T_cap = std::min(128, (h->ncap + 63) / 64);   // the hot-first tile lists exist for n <= 8192 (the schedule using them stops at n = 6000)
   TRY(dalloc(&h->tile_order, (size_t)h->tile_blk_cap * (h->tile_T_cap * (h->tile_T_cap + 1) / 2))) TRY(dalloc(&h->tile_nhot, h->tile_blk_cap))
   TRY(dalloc(&h->tile_counters, h->tile_blk_cap))
+  TRY(dalloc(&h->chain_flags, 3 * (size_t)h->tile_blk_cap + 8)) TRY(cudaMemset(h->chain_flags, 0, sizeof(unsigned int) * (3 * (size_t)h->tile_blk_cap + 8)))
   TRY(dalloc(&h->delta1, h->ld + EKF_DIST_PAD_ROWS)) TRY(dalloc(&h->delta2, h->ld + EKF_DIST_PAD_ROWS))
   {
     int lo = 0, hi = 0;
@@ -219,6 +222,8 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
     TRY(cudaStreamCreateWithPriority(&h->gemm_stream, cudaStreamNonBlocking, lo))
     TRY(cudaStreamCreateWithPriority(&h->corr_stream, cudaStreamNonBlocking, hi))
     TRY(cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, hi))
+    TRY(cudaStreamCreateWithPriority(&h->chain_stream, cudaStreamNonBlocking, hi))
+    TRY(cudaEventCreateWithFlags(&h->ev_chain, cudaEventDisableTiming))
     TRY(cudaEventCreateWithFlags(&h->ev_frame, cudaEventDisableTiming)) TRY(cudaEventCreateWithFlags(&h->ev_prev, cudaEventDisableTiming))
     TRY(cudaStreamCreateWithPriority(&h->v_stream, cudaStreamNonBlocking, hi))
     TRY(cudaStreamCreateWithPriority(&h->gather_stream, cudaStreamNonBlocking, hi))
@@ -858,6 +863,151 @@ static int stacked_update_chain_short(ekf_handle* h, int cnt) {
   return 0;
 }
 
+// Fourth schedule (EKF_SCHED=2), the chain-short algebra with a RESIDENT factor CTA: k_chain_factor is launched once per stacked
+// update, keeps its SM, assembles S_b itself and factors every block, talking to the other kernels through flag words
+// (gather_b / Sg_b -> factor_b -> Gx_{b+1} and, through a one-warp gate, V_b).  What that buys:
+//  * the downdate of block b-1 starts as soon as V_{b-1} exists — the other schedules hold it back until S_b is formed so that the
+//    next factor KERNEL finds a free SM first;
+//  * the chain per block loses a kernel and two launch gaps: Gx_b -> Sg_b -> [flag] -> assemble + factor -> [flag] -> Gx_{b+1}.
+// Every wait is bounded and every producer is launched before the kernel that waits for it, so the waits resolve in launch order.
+static ChainFlags chain_flags_view(ekf_handle* h) {
+  ChainFlags f;
+  f.gather = h->chain_flags; f.sg = h->chain_flags + h->tile_blk_cap; f.fact = h->chain_flags + 2 * (size_t)h->tile_blk_cap;
+  f.tickets = h->chain_flags + 3 * (size_t)h->tile_blk_cap;
+  f.token0 = h->chain_seq * 1024u + 1u;
+  return f;
+}
+static bool resident_chain_likely(const ekf_handle* h) {
+  const bool partitioned = h->nccl_comm && h->world > 1;
+  if (partitioned || h->sched != 2 || h->pipe_small <= 0 || h->n < h->pipe_small) return false;
+  if (h->lookahead > 0 && h->n >= h->lookahead) return false;
+  return h->N > EKF_UB / 2 && (h->N + EKF_UB / 2 - 1) / (EKF_UB / 2) <= std::min(h->tile_blk_cap, 1000);
+}
+static void resident_chain_prelaunch(ekf_handle* h) {
+  cudaStream_t sm = h->stream, sg = h->gemm_stream;
+  const BlkTab bt{h->bt_H, h->bt_zmh, h->bt_pos, h->bt_nd};
+  h->chain_seq++;
+  cudaEventRecord(h->ev_fork, sm);
+  cudaStreamWaitEvent(sg, h->ev_fork, 0);
+  launch_blk_prep(sg, h->ft, h->N, h->bt_H, h->bt_zmh, h->bt_pos, h->bt_nd, &h->launches, &h->ctl->n_li);
+  double* raw[2] = {h->Wbuf[1], h->Wbuf[2]};
+  double* cor[2] = {h->Wbuf[0], h->Wbuf[3]};
+  for (int b = 0; b < 2; ++b) {
+    ProfScope ps(h, 3, sg); TraceScope ts("gather", b, sg);
+    launch_blk_gather2(sg, h->Sigma, h->ld, h->n, h->ft, b * (EKF_UB / 2), 0, raw[b], cor[b], &h->launches, bt, &h->ctl->n_li);
+    cudaEventRecord(h->ev_gather[b], sg);
+  }
+  h->prelaunched = true;
+}
+static int stacked_update_resident_chain(ekf_handle* h, int cnt) {
+  cudaStream_t sm = h->stream, sg = h->gemm_stream, sc = h->corr_stream, sv = h->v_stream, sf = h->chain_stream;
+  const int nblk = (cnt + EKF_UB / 2 - 1) / (EKF_UB / 2);
+  double* raw[2] = {h->Wbuf[1], h->Wbuf[2]};
+  double* cor[2] = {h->Wbuf[0], h->Wbuf[3]};
+  double* Vb[2] = {h->Wbuf[4], h->Wbuf[5]};
+  double* Ls[2] = {h->Dinv, h->Dinv2};
+  double* Ds[2] = {h->Dblk, h->Dblk2};
+  double* ys[2] = {h->yb, h->yb2};
+  double* dl[3] = {h->delta, h->delta1, h->delta2};
+  for (int i = 0; i < 3; ++i) cudaMemsetAsync(dl[i], 0, sizeof(double) * (size_t)h->n, sm);
+  const BlkTab bt{h->bt_H, h->bt_zmh, h->bt_pos, h->bt_nd};
+  const bool pre = h->prelaunched;
+  h->prelaunched = false;
+  if (!pre) {
+    h->chain_seq++;
+    launch_blk_prep(sm, h->ft, cnt, h->bt_H, h->bt_zmh, h->bt_pos, h->bt_nd, &h->launches);
+  }
+  const ChainFlags fl = chain_flags_view(h);
+  cudaEventRecord(h->ev_fork, sm);
+  cudaStreamWaitEvent(sg, h->ev_fork, 0);
+  cudaStreamWaitEvent(sv, h->ev_fork, 0);
+  cudaStreamWaitEvent(sf, h->ev_fork, 0);
+  {   // the resident factor CTA: first on the device, before any downdate exists
+    ChainFactorArgs a;
+    a.S = h->Lb; a.nu = h->nu;
+    for (int i = 0; i < 2; ++i) { a.L[i] = Ls[i]; a.D[i] = Ds[i]; a.y[i] = ys[i]; }
+    a.fl = fl; a.nblk = nblk;
+    // NOTHING may follow this launch in its stream until every producer it waits for has been enqueued: an event record behind it
+    // completes only with the kernel, and when the stream shares a hardware queue with another one (more streams than
+    // connections) it would hold back that stream's later launches — the gathers this kernel waits for (measured: every wait
+    // ran into its time-out).  No profiling / trace events here for the same reason; ev_chain is recorded at the end.
+    launch_chain_factor(sf, a, h->ctl, &h->launches);
+  }
+  for (int b = 0; b < nblk && b < 2 && !pre; ++b) {
+    ProfScope ps(h, 3, sg); TraceScope ts("gather", b, sg);
+    launch_blk_gather2(sg, h->Sigma, h->ld, h->n, h->ft, b * (EKF_UB / 2), cnt, raw[b], cor[b], &h->launches, bt);
+    cudaEventRecord(h->ev_gather[b], sg);
+  }
+  for (int b = 0; b < nblk; ++b) {
+    const int f0 = b * (EKF_UB / 2), p = b & 1, q = p ^ 1;
+    if (b > 0) {
+      if (b > 1) {
+        cudaStreamWaitEvent(sm, h->ev_corr2[q], 0);         // W_{b-1} is corrected
+        cudaStreamWaitEvent(sm, h->ev_V[(b - 2) % 3], 0);   // delta_{b-2} is complete (the resident CTA reads it once Sg_b is published)
+      }
+      { ProfScope ps(h, 4); TraceScope ts("Gx", b, sm);
+        launch_blk_Gx(sm, cor[q], h->ft, f0, cnt, Ls[q], Ds[q], ys[q], h->Gbuf, h->gy, &h->launches, bt, fl.fact + (b - 1), fl.token0 + (b - 1), h->ctl); }
+      cudaEventRecord(h->ev_G, sm);
+      cudaStreamWaitEvent(sc, h->ev_G, 0);
+      cudaStreamWaitEvent(sc, h->ev_V[(b - 1) % 3], 0);
+      cudaStreamWaitEvent(sc, h->ev_gather[p], 0);
+      {
+        TraceScope ts("corr", b, sc);
+        const int rc = launch_gemm_nt_sub(sc, cor[p], EKF_UB, Vb[q], EKF_UB, h->Gbuf, EKF_UB, h->n, EKF_UB, EKF_UB, nullptr, 0, h->gemm_counters, &h->launches);
+        if (rc) return rc;
+      }
+      cudaEventRecord(h->ev_corr2[p], sc);
+    }
+    // S_b and nu_b by the ten-CTA kernel (G G^T on DMMA + the 13-row gather), whose last CTA raises the flag the resident CTA waits for
+    cudaStreamWaitEvent(sm, h->ev_gather[p], 0);
+    { ProfScope ps(h, 4); TraceScope ts("S", b, sm);
+      launch_blk_S_nu_G(sm, raw[p], h->ft, f0, cnt, h->dcfg, dl[(b + 1) % 3], b > 0 ? h->Gbuf : nullptr, h->Lb, h->nu, &h->launches,
+                        b > 0 ? h->gy : nullptr, bt, nullptr, fl.tickets + 1, fl.sg + b, fl.token0 + b); }
+    if (b > 0) {
+      // downdate of block b-1 as soon as V_{b-1} exists, then the gather of W'_{b+1}
+      cudaStreamWaitEvent(sg, h->ev_V[(b - 1) % 3], 0);
+      {
+        ProfScope ps(h, 6, sg); TraceScope ts("dd", b - 1, sg);
+        const int rc = launch_gemm_nt_sub(sg, h->Sigma, h->ld, Vb[q], EKF_UB, Vb[q], EKF_UB, h->n, h->n, EKF_UB, nullptr, h->lower_only, h->gemm_counters, &h->launches);
+        if (rc) return rc;
+      }
+      cudaEventRecord(h->ev_dd[q], sg);
+      if (b + 1 < nblk) {
+        // raw[q] / cor[q] are free: the resident CTA is past S_{b-1} (V_{b-1}, waited for above, ran behind factor_{b-1}), Gx_b has
+        // read cor[q] (ev_G) and so has V_{b-1}
+        cudaStreamWaitEvent(sg, h->ev_G, 0);
+        ProfScope ps(h, 3, sg); TraceScope ts("gather", b + 1, sg);
+        launch_blk_gather2(sg, h->Sigma, h->ld, h->n, h->ft, (b + 1) * (EKF_UB / 2), cnt, raw[q], cor[q], &h->launches, bt);
+        cudaEventRecord(h->ev_gather[q], sg);
+      }
+    }
+    // V_b behind a one-warp gate on factor_b
+    if (b > 0) cudaStreamWaitEvent(sv, h->ev_corr2[p], 0);
+    else cudaStreamWaitEvent(sv, h->ev_gather[0], 0);
+    if (b > 1) cudaStreamWaitEvent(sv, h->ev_dd[p], 0);
+    { ProfScope ps(h, 5, sv); TraceScope ts("V", b, sv);
+      launch_wait_flag(sv, fl.fact + b, fl.token0 + b, h->ctl, &h->launches);
+      launch_blk_V(sv, cor[p], 0, h->n, Ls[p], Ds[p], ys[p], dl[b % 3], &h->launches, Vb[p], dl[(b + 2) % 3]); }
+    cudaEventRecord(h->ev_V[b % 3], sv);
+  }
+  {
+    const int p = (nblk - 1) & 1;
+    cudaStreamWaitEvent(sg, h->ev_V[(nblk - 1) % 3], 0);
+    ProfScope ps(h, 6, sg); TraceScope ts("dd", nblk - 1, sg);
+    const int rc = launch_gemm_nt_sub(sg, h->Sigma, h->ld, Vb[p], EKF_UB, Vb[p], EKF_UB, h->n, h->n, EKF_UB, nullptr, h->lower_only, h->gemm_counters, &h->launches);
+    if (rc) return rc;
+  }
+  cudaEventRecord(h->ev_join, sg);
+  cudaEventRecord(h->ev_chain, sf);
+  cudaStreamWaitEvent(sm, h->ev_join, 0);
+  cudaStreamWaitEvent(sm, h->ev_chain, 0);
+  {
+    ProfScope ps(h, 7); TraceScope ts("finish", nblk, sm);
+    launch_finish_update(sm, h->Sigma, h->ld, h->n, h->mu, dl[(nblk - 1) % 3], h->ctl, &h->launches);
+  }
+  return 0;
+}
+
 static int stacked_update(ekf_handle* h, int cnt, bool plane = false) {
   if (cnt <= 0 && !plane) return 0;
   if (cnt < 0) cnt = 0;
@@ -865,7 +1015,8 @@ static int stacked_update(ekf_handle* h, int cnt, bool plane = false) {
     const bool partitioned = h->nccl_comm && h->world > 1;
     if (h->lookahead > 0 && h->n >= h->lookahead) return stacked_update_lookahead(h, cnt);   // also row-block partitioned
     if (!partitioned && h->pipe_small > 0 && h->n >= h->pipe_small)
-      return h->sched == 1 ? stacked_update_chain_short(h, cnt) : stacked_update_factor_beside_downdate(h, cnt);
+      return (h->sched == 2 && (cnt + EKF_UB / 2 - 1) / (EKF_UB / 2) <= std::min(h->tile_blk_cap, 1000)) ? stacked_update_resident_chain(h, cnt)
+           : h->sched >= 1 ? stacked_update_chain_short(h, cnt) : stacked_update_factor_beside_downdate(h, cnt);
   }
   if (h->prelaunched) {   // the speculative gathers of the chain-short schedule wrote the W panels on the second stream: order after them
     cudaStreamWaitEvent(h->stream, h->ev_gather[0], 0);
@@ -955,6 +1106,7 @@ int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
     launch_ransac(st, h->Sigma, h->ld, h->n, h->mu, h->ft, h->N, h->ctl, h->dcfg, h->picks_dev, n_picks, h->mu_i, h->cand, &h->launches);
   }
   if (h->prelaunch_on && chain_short_likely(h)) chain_short_prelaunch(h);   // GPU work for the duration of the read-back
+  else if (h->prelaunch_on && resident_chain_likely(h)) resident_chain_prelaunch(h);
   EKF_CUDA_CHECK(cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost, st));
   EKF_CUDA_CHECK(cudaStreamSynchronize(st));
   const int n_li = hc.n_li;
@@ -1013,7 +1165,11 @@ int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
   h->stats.n_hi = n_hi;
   h->stats.ransac_hypotheses = outi[4];
   h->stats.blur_requests = outi[6];
-  if (outi[5] & 64) return ekf_fail(h, EKF_ERR_CUDA, "pipelined update: the downdate tiles a gather waits for did not arrive within the wait limit");
+  if (outi[5] & 64) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "pipelined update: a flag a kernel waits for did not arrive within the wait limit (code 0x%x)", outi[5]);
+    return ekf_fail(h, EKF_ERR_CUDA, msg);
+  }
   if (outi[5] & 16) return ekf_fail(h, EKF_ERR_CUDA, "row-block partition: a peer's panel did not arrive within the wait limit (peer-memory exchange)");
   if (outi[5]) return ekf_fail(h, EKF_ERR_STATE, "innovation covariance not positive definite");
   if (outi[7]) return ekf_fail(h, EKF_ERR_UNSUPPORTED, "a motion-blur kernel exceeded 256 x 256 pixels");

@@ -106,7 +106,9 @@ __device__ __forceinline__ bool warp_chol8(const double* __restrict__ t, double*
 // Sb: 128 x 128 SPD (leading dimension lds, even; only the lower triangle is read), nu: 128.
 // Lout (ldl): L on and below the diagonal (entries above are left untouched); Dout: 4 blocks of 32 rows x ldd: inverse of the J-th
 // 32 x 32 diagonal block of L; yout: L^-1 nu.  blockDim.x must be CH_THREADS.  Ends with a block barrier.
-__device__ __forceinline__ void cta_chol128(void* smem_raw, const double* __restrict__ Sb, int lds, const double* __restrict__ nu,
+// (Sb and nu carry no __restrict__: k_chain_factor assembles them in global memory inside the same kernel, so their loads must
+// not take the non-coherent path.)
+__device__ __forceinline__ void cta_chol128(void* smem_raw, const double* Sb, int lds, const double* nu,
                                             double* __restrict__ Lout, int ldl, double* __restrict__ Dout, int ldd,
                                             double* __restrict__ yout, int* chol_fail) {
   Chol128Smem& sm = *reinterpret_cast<Chol128Smem*>(smem_raw);

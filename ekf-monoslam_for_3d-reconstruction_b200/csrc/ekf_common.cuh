@@ -123,6 +123,38 @@ struct BlkTab {
   const int* nd;      // [cnt]  7 + 3 (XYZ) or 7 + 6 (inverse depth)
 };
 
+// Flag words of the resident-chain schedule (k_chain_factor): one word per update block and kind, written once per stacked update
+// with that update's token (no reset needed), plus self-resetting tickets for "last CTA of the kernel" detection.
+struct ChainFlags {
+  unsigned int* gather;   // [blocks]  W'_b is complete (last CTA of its gather)
+  unsigned int* sg;       // [blocks]  -G_b G_b^T, G_b and gy are complete (last CTA of k_blk_Sg)
+  unsigned int* fact;     // [blocks]  L_b, D_b, y_b are complete (k_chain_factor)
+  unsigned int* tickets;  // [0] gather, [1] Sg
+  unsigned int token0;    // block b of this update publishes token0 + b
+};
+__device__ __forceinline__ void chain_publish(unsigned int* flag, unsigned int token) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(flag), "r"(token) : "memory");
+}
+// bounded wait of ONE thread for *flag == token; returns false after ~seconds (the caller reports instead of hanging)
+__device__ __forceinline__ bool chain_wait(const unsigned int* flag, unsigned int token) {
+  unsigned int seen = 0;
+  for (long long spins = 0; spins < 2000000ll; ++spins) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(flag) : "memory");
+    if (seen == token) return true;
+    __nanosleep(40);
+  }
+  return false;
+}
+// end of a producer kernel: the last CTA to get here publishes `token` (every thread of the CTA must call)
+__device__ __forceinline__ void chain_publish_last_cta(unsigned int* ticket, unsigned int* flag, unsigned int token) {
+  __threadfence();   // EVERY thread: its own stores are performed before the CTA's ticket is taken (a fence by thread 0 alone does not cover the other warps' stores in flight)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    if (t == gridDim.x * gridDim.y - 1) { *ticket = 0u; __threadfence(); chain_publish(flag, token); }
+  }
+}
+
 // device-side view of the peer mappings, passed by value to the kernels that push panels to the peers
 struct P2PView {
   double* w[8];                 // destination panel (Wbuf[b % 3]) on every rank

@@ -214,3 +214,12 @@ bool gemm_uses_square_tiles() {
   const char* e = getenv("EKF_GEMM_TM");
   return !(e && atoi(e) == 128);
 }
+
+// Load both tile variants now (see update_kernels_init: a first launch beside the resident factor kernel must not trigger a lazy load).
+int gemm_kernels_preload() {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, k_gemm_nt_sub<64, 2, 4>);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncGetAttributes(&fa, k_gemm_nt_sub<128, 3, 2>);
+  return (int)e;
+}

@@ -65,6 +65,11 @@ struct ekf_handle {
   unsigned int* tile_counters = nullptr;  // [blocks]
   int tile_T_cap = 0, tile_blk_cap = 0;
   int split_dd = 0;       // chain-short only (EKF_SPLIT_DD): 1 = tile list, hot tiles first, the next gather gated on them; 2 = tile list only
+  // resident-chain schedule (EKF_SCHED=2): flag words [3][blocks] + tickets, token sequence, stream of the resident factor CTA
+  unsigned int* chain_flags = nullptr;
+  unsigned int chain_seq = 0;
+  cudaStream_t chain_stream = nullptr;
+  cudaEvent_t ev_chain = nullptr;
   bool prelaunched = false;   // block tables + first two gathers were started before the n_li read-back (chain_short_prelaunch)
   int prelaunch_on = 1;       // EKF_PRELAUNCH=0 switches that off
   int sched = 1;          // 1: chain-short (default for pipe_small <= n < lookahead), 0: factor-beside-downdate (EKF_SCHED)

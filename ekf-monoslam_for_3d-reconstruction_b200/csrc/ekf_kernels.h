@@ -50,8 +50,10 @@ void launch_blk_S_nu(cudaStream_t st, const double* W, FeatTab ft, int f0, int c
                      double* Sb, double* nu, long long* launches);
 void launch_blk_S_nu_G(cudaStream_t st, const double* Wraw, FeatTab ft, int f0, int cnt, const DevCfg& cfg, const double* delta,
                        const double* G, double* Sb, double* nu, long long* launches, const double* gy = nullptr,
-                       BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}, const double* Sg = nullptr);
-void launch_blk_Sg(cudaStream_t st, const double* G, double* Sg, long long* launches);
+                       BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}, const double* Sg = nullptr, unsigned int* pub_ticket = nullptr,
+                       unsigned int* pub_flag = nullptr, unsigned int pub_token = 0);
+void launch_blk_Sg(cudaStream_t st, const double* G, double* Sg, long long* launches, unsigned int* pub_ticket = nullptr,
+                   unsigned int* pub_flag = nullptr, unsigned int pub_token = 0);
 void launch_blk_prep(cudaStream_t st, FeatTab ft, int cnt, double* H, double* zmh, int* pos, int* nd, long long* launches,
                      const int* cnt_dev = nullptr);
 // per update block g: the 64 x 64 tiles of the lower triangle (T x T tiles) ordered with the tiles gather g reads first; n_hot[g] of them
@@ -61,9 +63,23 @@ void launch_blk_gather2_after_tiles(cudaStream_t st, const double* Sigma, int ld
                                     const unsigned int* hot_counter, const int* n_hot, DevCtl* ctl, long long* launches,
                                     BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr});
 void launch_blk_Gx(cudaStream_t st, const double* Wc, FeatTab ft, int f0, int cnt, const double* Lb, const double* Dblk, const double* yb,
-                   double* G, double* gy, long long* launches, BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr});
+                   double* G, double* gy, long long* launches, BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}, const unsigned int* wait_flag = nullptr,
+                   unsigned int wait_token = 0, DevCtl* ctl = nullptr);
+// arguments of k_chain_factor (ekf_update.cu), filled by stacked_update_resident_chain
+struct ChainFactorArgs {
+  const double* S;          // S_b (lower 32 x 32 blocks), written by k_blk_S_tiled
+  const double* nu;
+  double* L[2];             // factor outputs, block b -> set b & 1
+  double* D[2];
+  double* y[2];
+  ChainFlags fl;
+  int nblk;
+};
+void launch_chain_factor(cudaStream_t st, const ChainFactorArgs& a, DevCtl* ctl, long long* launches);
+void launch_wait_flag(cudaStream_t st, const unsigned int* flag, unsigned int token, DevCtl* ctl, long long* launches);
 void launch_blk_gather2(cudaStream_t st, const double* Sigma, int ld, int n, FeatTab ft, int f0, int cnt, double* W, double* W2,
-                        long long* launches, BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}, const int* cnt_dev = nullptr);
+                        long long* launches, BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}, const int* cnt_dev = nullptr, unsigned int* pub_ticket = nullptr,
+                        unsigned int* pub_flag = nullptr, unsigned int pub_token = 0);
 void launch_blk_G(cudaStream_t st, const double* Vprev, FeatTab ft, int f0, int cnt, double* G, long long* launches);
 void launch_blk_factor_only(cudaStream_t st, const double* Sb, const double* nu, double* Lb, double* Dblk, double* yb, DevCtl* ctl,
                             long long* launches);
@@ -93,6 +109,7 @@ int launch_gemm_nt_sub(cudaStream_t st, double* C, int ldc, const double* A, int
                        int kconst, const int* kdev, int lower_only, int* counters, long long* launches,
                        const ushort2* tlist = nullptr, int n_tiles = 0, const int* n_hot = nullptr, unsigned int* hot_counter = nullptr);
 bool gemm_uses_square_tiles();
+int gemm_kernels_preload();
 // ekf_detect.cu
 int launch_detect_corners(cudaStream_t st, FrameView fr, FeatTab ft, int N, int window, uint8_t* mask, float* eig,
                           unsigned long long* keys, int key_cap, int* counters, int max_corners, float* out_xy, long long* launches);

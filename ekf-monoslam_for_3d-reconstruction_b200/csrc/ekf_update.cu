@@ -305,7 +305,8 @@ static int gather_rows() {
 __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ Sigma, int ld, int row0, int n, FeatTab ft, int f0,
                                                     int cnt, const double* __restrict__ delta, double* __restrict__ W,
                                                     double* __restrict__ nu, double* __restrict__ W2, int rows_per_cta,
-                                                    BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}, const int* __restrict__ cnt_dev = nullptr) {
+                                                    BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}, const int* __restrict__ cnt_dev = nullptr,
+                                                    unsigned int* pub_ticket = nullptr, unsigned int* pub_flag = nullptr, unsigned int pub_token = 0) {
   if (cnt_dev) cnt = *cnt_dev;   // launched before the host has read the count back (see ekf_update_after_match)
   // Sigma is read past L1 (ld.global.cg): in the chain-short schedule this kernel runs BESIDE the downdate that still writes the
   // tiles it does not read (k_wait_tiles gates it), so no line of Sigma may be served from a stale L1 copy.
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ S
 #pragma unroll 2
   for (int rq = rl; rq < rows_per_cta; rq += rstep) {
     const int i = row0 + blockIdx.x * rows_per_cta + rq;   // rows [row0, n): the caller's row block
-    if (i >= n) break;
+    if (i >= n) break;   // (no barrier inside this loop: the publish below is reached by every thread)
     const double* row = Sigma + (size_t)i * ld;
     double sg[13];
 #pragma unroll
@@ -355,6 +356,7 @@ __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ S
     reinterpret_cast<double2*>(W + (size_t)i * EKF_UB)[a] = make_double2(w0, w1);
     if (W2) reinterpret_cast<double2*>(W2 + (size_t)i * EKF_UB)[a] = make_double2(w0, w1);   // second copy: see launch_blk_gather2
   }
+  if (pub_flag) chain_publish_last_cta(pub_ticket, pub_flag, pub_token);   // resident-chain schedule: W' is complete
   if (nu && blockIdx.x == 0 && tid < EKF_UB / 2) {
     double v0 = 0, v1 = 0;
     if (tid < nb) {
@@ -458,7 +460,8 @@ __global__ void __launch_bounds__(EKF_UB) k_blk_S(const double* __restrict__ W, 
 __global__ void __launch_bounds__(128) k_blk_S_tiled(const double* __restrict__ W, FeatTab ft, int f0, int cnt, double sigma_pixel_2,
                                                      double* __restrict__ Sb, const double* __restrict__ delta, double* __restrict__ nu,
                                                      const double* __restrict__ Gsub, const double* __restrict__ gy = nullptr,
-                                                     BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}, const double* __restrict__ Sg = nullptr) {
+                                                     BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}, const double* __restrict__ Sg = nullptr,
+                                                     unsigned int* pub_ticket = nullptr, unsigned int* pub_flag = nullptr, unsigned int pub_token = 0) {
   // Sg != null (chain-short schedule): the term -G G^T was formed ahead of time by k_blk_Sg while the gather of W' was still
   // running; this launch then only adds the 13-row gather H_b W' and R — two round trips on the critical cycle instead of five.
   extern __shared__ __align__(16) double s2sm[];
@@ -584,11 +587,13 @@ __global__ void __launch_bounds__(128) k_blk_S_tiled(const double* __restrict__ 
     }
     nu[s] = out;
   }
+  if (pub_flag) chain_publish_last_cta(pub_ticket, pub_flag, pub_token);
 }
 
 // K4b(1''): Sg = -G G^T on the lower 32 x 32 blocks (10 CTAs, DMMA), the part of S_b that does not need the gather of W'_b: in
 // the chain-short schedule it runs right after k_blk_Gx, in the shadow of the downdate / gather the block waits for.
-__global__ void __launch_bounds__(128) k_blk_Sg(const double* __restrict__ Gsub, double* __restrict__ Sg) {
+__global__ void __launch_bounds__(128) k_blk_Sg(const double* __restrict__ Gsub, double* __restrict__ Sg, unsigned int* pub_ticket = nullptr,
+                                                unsigned int* pub_flag = nullptr, unsigned int pub_token = 0) {
   extern __shared__ __align__(16) double s2sm[];
   int bi = 0, rem = blockIdx.x;
   while (rem > bi) { rem -= bi + 1; ++bi; }
@@ -623,6 +628,7 @@ __global__ void __launch_bounds__(128) k_blk_Sg(const double* __restrict__ Gsub,
 #pragma unroll
   for (int ct = 0; ct < 4; ++ct)
     *reinterpret_cast<double2*>(Sg + (size_t)r * EKF_UB + 32 * bj + 8 * ct + 2 * t4) = make_double2(e0[ct][0] + e1[ct][0], e0[ct][1] + e1[ct][1]);
+  if (pub_flag) chain_publish_last_cta(pub_ticket, pub_flag, pub_token);
 }
 
 // Compact tables of the selected features for the block kernels (BlkTab), once per stacked update.
@@ -689,6 +695,39 @@ __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor_smem(const double* 
                                                                   double* __restrict__ yout, DevCtl* ctl) {
   extern __shared__ __align__(16) double fsm[];
   cta_chol_panel<EKF_UB>(fsm, Sb, EKF_UB, nu, Lout, EKF_UB, Dblk, 32, yout, &ctl->chol_fail);
+}
+
+// Resident-chain schedule (ekf_api.cu::stacked_update_resident_chain): ONE CTA stays resident for the whole stacked update and
+// factors every block.  Per block it waits (flag word, acquire) until k_blk_S_tiled has published S_b and nu_b, factors with
+// cta_chol128 and publishes L_b, D_b, y_b.  Because its SM is never given back between blocks, the downdate no longer has to be
+// held back until the next factor kernel has found a free SM (the release rule of the other two schedules), and the factor starts
+// without a launch.  (A first version also assembled S_b inside this CTA — the 13-row gather of 10 K entries by one SM took 12 us,
+// as long as the ten-CTA kernel plus its launch gap: profiles/r2k_trace_resident_chain.txt.)
+__global__ void __launch_bounds__(CH_THREADS, 1) k_chain_factor(ChainFactorArgs a, DevCtl* ctl) {
+  extern __shared__ __align__(16) double fsm[];
+  const int tid = threadIdx.x;
+#pragma unroll 1
+  for (int b = 0; b < a.nblk; ++b) {
+    const int p = b & 1;
+    if (tid == 0 && !chain_wait(a.fl.sg + b, a.fl.token0 + b)) atomicOr(&ctl->chol_fail, 64 | 512 | (b << 16));
+    __syncthreads();
+    cta_chol128(fsm, a.S, EKF_UB, a.nu, a.L[p], EKF_UB, a.D[p], 32, a.y[p], &ctl->chol_fail);
+    __threadfence();   // every thread: its stores of L, D, y are performed before the flag goes up
+    __syncthreads();
+    if (tid == 0) chain_publish(a.fl.fact + b, a.fl.token0 + b);
+  }
+}
+// one-warp gate: the kernels behind it in the stream start once *flag == token (the n-row solve V_b behind "factor_b is published")
+__global__ void k_wait_flag(const unsigned int* flag, unsigned int token, DevCtl* ctl) {
+  if (threadIdx.x == 0 && !chain_wait(flag, token)) atomicOr(&ctl->chol_fail, 64 | 2048);
+}
+void launch_chain_factor(cudaStream_t st, const ChainFactorArgs& a, DevCtl* ctl, long long* launches) {
+  k_chain_factor<<<1, CH_THREADS, sizeof(Chol128Smem), st>>>(a, ctl);
+  *launches += 1;
+}
+void launch_wait_flag(cudaStream_t st, const unsigned int* flag, unsigned int token, DevCtl* ctl, long long* launches) {
+  k_wait_flag<<<1, 32, 0, st>>>(flag, token, ctl);
+  *launches += 1;
 }
 
 // Row-block partition: S_b = sum over ranks of the partial blocks the peers stored into this rank's slots (fixed
@@ -804,9 +843,14 @@ __global__ void __launch_bounds__(VT_THREADS, 4) k_blk_V(double* __restrict__ W,
 __global__ void __launch_bounds__(VT_THREADS, 4) k_blk_Gx(const double* __restrict__ Wc, FeatTab ft, int f0, int cnt,
                                                           const double* __restrict__ Lg, const double* __restrict__ Dg,
                                                           const double* __restrict__ yg, double* __restrict__ G, double* __restrict__ gy,
-                                                          BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}) {
+                                                          BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr},
+                                                          const unsigned int* wait_flag = nullptr, unsigned int wait_token = 0, DevCtl* ctl = nullptr) {
   extern __shared__ __align__(16) double gxsm[];
   __shared__ int poss[GX_FEATS], nds[GX_FEATS], fids[GX_FEATS];
+  if (wait_flag) {   // resident-chain schedule: L, D, y of the previous block come from k_chain_factor, not from a kernel ahead in the stream
+    if (threadIdx.x == 0 && !chain_wait(wait_flag, wait_token) && ctl) atomicOr(&ctl->chol_fail, 64 | 1024);
+    __syncthreads();
+  }
   double* Lst = gxsm;
   const double* const Lj[4] = {Lst, Lst, Lst + 32 * 36, Lst + 32 * 36 + 32 * 68};
   const int ldj[4] = {36, 36, 68, 100};
@@ -1000,12 +1044,27 @@ int update_kernels_init() {
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_blk_Sg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 32 * S2_LD * sizeof(double)));
   if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_chain_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFactSmem);
+  if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_blk_factor_p2p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFactSmem);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_blk_V, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVSmem);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_blk_Gx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGxSmem);
-  return (int)e;
+  if (e != cudaSuccess) return (int)e;
+  // CUDA loads a kernel's code lazily at its first launch, and that load can wait for running kernels to finish: a kernel launched
+  // for the first time while k_chain_factor spins on a flag only that launch can raise would never start (measured: every wait of the
+  // first resident-chain update ran into its time-out).  cudaFuncGetAttributes forces the load now.
+  cudaFuncAttributes fa;
+  if ((e = cudaFuncGetAttributes(&fa, k_chain_factor)) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncGetAttributes(&fa, k_wait_flag)) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncGetAttributes(&fa, k_blk_Gx)) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncGetAttributes(&fa, k_blk_Sg)) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncGetAttributes(&fa, k_blk_V)) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncGetAttributes(&fa, k_blk_gather)) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncGetAttributes(&fa, k_blk_prep)) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncGetAttributes(&fa, k_blk_S_tiled)) != cudaSuccess) return (int)e;
+  return gemm_kernels_preload();
 }
 
 void launch_ransac(cudaStream_t st, const double* Sigma, int ld, int n, const double* mu, FeatTab ft, int N, DevCtl* ctl,
@@ -1055,14 +1114,17 @@ void launch_blk_S_nu(cudaStream_t st, const double* W, FeatTab ft, int f0, int c
 }
 // S_b from the uncorrected gather and G (see k_blk_S), and the gather with a second copy of W'
 void launch_blk_S_nu_G(cudaStream_t st, const double* Wraw, FeatTab ft, int f0, int cnt, const DevCfg& cfg, const double* delta,
-                       const double* G, double* Sb, double* nu, long long* launches, const double* gy, BlkTab bt, const double* Sg) {
+                       const double* G, double* Sb, double* nu, long long* launches, const double* gy, BlkTab bt, const double* Sg,
+                       unsigned int* pub_ticket, unsigned int* pub_flag, unsigned int pub_token) {
   static const bool legacy = [] { const char* e = getenv("EKF_S_TILED"); return e && atoi(e) == 0; }();
-  if (legacy && !gy && !Sg) k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(Wraw, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, delta, nu, G);
-  else k_blk_S_tiled<<<10, 128, Sg ? 0 : 2 * 32 * S2_LD * sizeof(double), st>>>(Wraw, ft, f0, cnt, cfg.sigma_pixel_2, Sb, delta, nu, Sg ? nullptr : G, gy, bt, Sg);
+  if (legacy && !gy && !Sg && !pub_flag) k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(Wraw, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, delta, nu, G);
+  else k_blk_S_tiled<<<10, 128, Sg ? 0 : 2 * 32 * S2_LD * sizeof(double), st>>>(Wraw, ft, f0, cnt, cfg.sigma_pixel_2, Sb, delta, nu, Sg ? nullptr : G, gy, bt, Sg,
+                                                                               pub_ticket, pub_flag, pub_token);
   *launches += 1;
 }
-void launch_blk_Sg(cudaStream_t st, const double* G, double* Sg, long long* launches) {
-  k_blk_Sg<<<10, 128, 2 * 32 * S2_LD * sizeof(double), st>>>(G, Sg);
+void launch_blk_Sg(cudaStream_t st, const double* G, double* Sg, long long* launches, unsigned int* pub_ticket, unsigned int* pub_flag,
+                   unsigned int pub_token) {
+  k_blk_Sg<<<10, 128, 2 * 32 * S2_LD * sizeof(double), st>>>(G, Sg, pub_ticket, pub_flag, pub_token);
   *launches += 1;
 }
 void launch_blk_prep(cudaStream_t st, FeatTab ft, int cnt, double* H, double* zmh, int* pos, int* nd, long long* launches, const int* cnt_dev) {
@@ -1072,15 +1134,16 @@ void launch_blk_prep(cudaStream_t st, FeatTab ft, int cnt, double* H, double* zm
 }
 // G_b = (H_b W_{b-1}) L_{b-1}^-T and gy = G_b y_{b-1} (see k_blk_Gx)
 void launch_blk_Gx(cudaStream_t st, const double* Wc, FeatTab ft, int f0, int cnt, const double* Lb, const double* Dblk, const double* yb,
-                   double* G, double* gy, long long* launches, BlkTab bt) {
-  k_blk_Gx<<<EKF_UB / 8, VT_THREADS, kGxSmem, st>>>(Wc, ft, f0, cnt, Lb, Dblk, yb, G, gy, bt);
+                   double* G, double* gy, long long* launches, BlkTab bt, const unsigned int* wait_flag, unsigned int wait_token, DevCtl* ctl) {
+  k_blk_Gx<<<EKF_UB / 8, VT_THREADS, kGxSmem, st>>>(Wc, ft, f0, cnt, Lb, Dblk, yb, G, gy, bt, wait_flag, wait_token, ctl);
   *launches += 1;
 }
 void launch_blk_gather2(cudaStream_t st, const double* Sigma, int ld, int n, FeatTab ft, int f0, int cnt, double* W, double* W2,
-                        long long* launches, BlkTab bt, const int* cnt_dev) {
+                        long long* launches, BlkTab bt, const int* cnt_dev, unsigned int* pub_ticket, unsigned int* pub_flag,
+                        unsigned int pub_token) {
   const int nr = n > 0 ? n : 1;
   const int gr = gather_rows();
-  k_blk_gather<<<(nr + gr - 1) / gr, 256, 0, st>>>(Sigma, ld, 0, n, ft, f0, cnt, nullptr, W, nullptr, W2, gr, bt, cnt_dev);
+  k_blk_gather<<<(nr + gr - 1) / gr, 256, 0, st>>>(Sigma, ld, 0, n, ft, f0, cnt, nullptr, W, nullptr, W2, gr, bt, cnt_dev, pub_ticket, pub_flag, pub_token);
   *launches += 1;
 }
 // Gate of the gather that runs beside a downdate: one warp waits (acquire, bounded) until the downdate's first *n_hot tiles — the
@@ -1101,7 +1164,7 @@ void launch_blk_gather2_after_tiles(cudaStream_t st, const double* Sigma, int ld
                                     const unsigned int* hot_counter, const int* n_hot, DevCtl* ctl, long long* launches, BlkTab bt) {
   k_wait_tiles<<<1, 32, 0, st>>>(hot_counter, n_hot, ctl);
   *launches += 1;
-  launch_blk_gather2(st, Sigma, ld, n, ft, f0, cnt, W, W2, launches, bt, nullptr);
+  launch_blk_gather2(st, Sigma, ld, n, ft, f0, cnt, W, W2, launches, bt, nullptr, nullptr, nullptr, 0);
 }
 void launch_blk_G(cudaStream_t st, const double* Vprev, FeatTab ft, int f0, int cnt, double* G, long long* launches) {
   k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(Vprev, ft, f0, cnt, 0.0, G, 1, nullptr, nullptr, nullptr);
