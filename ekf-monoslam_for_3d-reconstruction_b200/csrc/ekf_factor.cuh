@@ -415,3 +415,74 @@ __device__ __forceinline__ double warp_trsm_tile_packed(double* Wt, int ldw, con
   }
   return part;
 }
+
+// The same solve for ONE 8-row tile by NW cooperating warps, right-looking: warp w owns the 8-column tiles ct = w, w + NW, .. of every
+// 32-column block in registers (DMMA accumulator layout).  Per block J: the owners publish T_J, every warp forms its tiles of
+// X_J = T_J Dinv_J^T (<= 8 k-steps in two accumulator chains), X_J goes to the output tile, and every warp subtracts X_J L_{J'J}^T from
+// its own tiles of the later blocks J' (8 k-steps each, independent tiles interleaved).  The longest chain of dependent DMMAs is
+// 8 per block instead of 4 J + 4 (with the whole tile in one warp: ~50 in a row, which crawl when a downdate saturates the fp64
+// pipe next to them).  Xin: T on entry (row stride ldw); Xout: V on exit (may not alias Xin).  Named barrier BAR is used with
+// NW * 32 threads; every one of the NW warps must call.  Returns the partial dot products of row (lane / 4) with y over the
+// warp's own columns (the caller sums over the 4 lanes of a row and over the warps).
+template <int NB, int NW, int BAR>
+__device__ __forceinline__ double warps_trsm_tile_rl(const double* Xin, double* Xout, int ldw, const double* const (&Lj)[NB / 32],
+                                                     const int (&ldj)[NB / 32], const double* D, int ldd, const double* y, int w) {
+  constexpr int NP = NB / 32, NC = 4 / NW;   // column tiles per block owned by a warp
+  static_assert(4 % NW == 0, "NW must divide 4");
+  const int lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  auto gbar = [] { asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NW * 32) : "memory"); };
+  double t[NP][NC][2];
+#pragma unroll
+  for (int J = 0; J < NP; ++J)
+#pragma unroll
+    for (int ci = 0; ci < NC; ++ci) {
+      const double2 v = *reinterpret_cast<const double2*>(Xin + (size_t)g * ldw + 32 * J + 8 * (w + NW * ci) + 2 * t4);
+      t[J][ci][0] = v.x; t[J][ci][1] = v.y;
+    }
+  double part = 0.0;
+  double* Ts = const_cast<double*>(Xin);   // T_J of the current block is exchanged through the input tile
+#pragma unroll
+  for (int J = 0; J < NP; ++J) {
+    if (J > 0) {
+#pragma unroll
+      for (int ci = 0; ci < NC; ++ci)
+        *reinterpret_cast<double2*>(Ts + (size_t)g * ldw + 32 * J + 8 * (w + NW * ci) + 2 * t4) = make_double2(t[J][ci][0], t[J][ci][1]);
+    }
+    gbar();
+    // X_J = T_J Dinv_J^T (Dinv lower triangular: column tile ct needs k < 8 ct + 8)
+    const double* Dj = D + (size_t)J * 32 * ldd;
+#pragma unroll
+    for (int ci = 0; ci < NC; ++ci) {
+      const int ct = w + NW * ci;
+      double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+      for (int kq = 0; kq < 2 * ct + 2; kq += 2) {
+        dmma884f(d0, d1, Ts[(size_t)g * ldw + 32 * J + 4 * kq + t4], Dj[(size_t)(8 * ct + g) * ldd + 4 * kq + t4]);
+        dmma884f(e0, e1, Ts[(size_t)g * ldw + 32 * J + 4 * kq + 4 + t4], Dj[(size_t)(8 * ct + g) * ldd + 4 * kq + 4 + t4]);
+      }
+      d0 += e0; d1 += e1;
+      *reinterpret_cast<double2*>(Xout + (size_t)g * ldw + 32 * J + 8 * ct + 2 * t4) = make_double2(d0, d1);
+      part += d0 * y[32 * J + 8 * ct + 2 * t4] + d1 * y[32 * J + 8 * ct + 2 * t4 + 1];
+    }
+    if (J + 1 < NP) {
+      gbar();   // X_J is complete in Xout
+      // own tiles of the later blocks: T_J' -= X_J L_{J'J}^T, K = 32, two accumulator chains per tile
+      double af[8];
+#pragma unroll
+      for (int kq = 0; kq < 8; ++kq) af[kq] = -Xout[(size_t)g * ldw + 32 * J + 4 * kq + t4];
+#pragma unroll
+      for (int Jp = J + 1; Jp < NP; ++Jp)
+#pragma unroll
+        for (int ci = 0; ci < NC; ++ci) {
+          const double* lb = Lj[Jp] + (size_t)(8 * (w + NW * ci) + g) * ldj[Jp] + 32 * J + t4;
+          double u0 = 0.0, u1 = 0.0;
+#pragma unroll
+          for (int kq = 0; kq < 8; kq += 2) {
+            dmma884f(t[Jp][ci][0], t[Jp][ci][1], af[kq], lb[4 * kq]);
+            dmma884f(u0, u1, af[kq + 1], lb[4 * kq + 4]);
+          }
+          t[Jp][ci][0] += u0; t[Jp][ci][1] += u1;
+        }
+    }
+  }
+  return part;
+}

@@ -805,6 +805,8 @@ __global__ void __launch_bounds__(VT_THREADS, 4) k_blk_V(double* __restrict__ W,
   for (int e = tid; e < EKF_UB; e += VT_THREADS) ys[e] = yg[e];
   asm volatile("cp.async.wait_group 0;\n" ::);
   __syncthreads();
+  // (A version with 16-row CTAs and four warps per tile — warps_trsm_tile_rl, as in k_blk_Gx — staged L and D twice as often
+  // and measured no faster inside the step: cfg2 0.738 against 0.728 ms, cfg4's V class 1.63 against 1.41 ms.)
   if (warp < VT_ROWS / 8) {
     double part = warp_trsm_tile_packed<EKF_UB>(Ws + (size_t)warp * 8 * VT_LD, VT_LD, Lj, ldj, Ds, VT_LDD, ys);
     part += __shfl_xor_sync(0xffffffffu, part, 1);
@@ -859,6 +861,8 @@ __global__ void __launch_bounds__(VT_THREADS, 4) k_blk_Gx(const double* __restri
   double* ys = Xs + 8 * VT_LD;                     // [EKF_UB]
   double* Wr = ys + EKF_UB;                        // [GX_WROWS][EKF_UB]: camera rows 0..6 of W, then 6 rows per feature
   double* Hs = Wr + GX_WROWS * EKF_UB;             // [GX_FEATS][26]
+  double* Gs = Hs + GX_FEATS * 26 + 2;             // [8][VT_LD]: G rows (output tile of the cooperative solve; 16-byte aligned)
+  double* red = Gs + 8 * VT_LD;                    // [4][8] partial G y per warp
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = min(EKF_UB / 2, cnt - f0);
   const int a0 = blockIdx.x * GX_FEATS;
@@ -920,16 +924,17 @@ __global__ void __launch_bounds__(VT_THREADS, 4) k_blk_Gx(const double* __restri
     *reinterpret_cast<double2*>(Xs + r * VT_LD + c) = make_double2(x0, x1);
   }
   __syncthreads();
-  if (warp == 0) {
-    double part = warp_trsm_tile_packed<EKF_UB>(Xs, VT_LD, Lj, ldj, Ds, VT_LDD, ys);
+  if (warp < 4) {   // four warps solve the tile together (warps_trsm_tile_rl: <= 8 dependent DMMAs per 32-column block)
+    double part = warps_trsm_tile_rl<EKF_UB, 4, 1>(Xs, Gs, VT_LD, Lj, ldj, Ds, VT_LDD, ys, warp);
     part += __shfl_xor_sync(0xffffffffu, part, 1);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
-    if ((lane & 3) == 0) gy[8 * blockIdx.x + (lane >> 2)] = part;
+    if ((lane & 3) == 0) red[8 * warp + (lane >> 2)] = part;
   }
   __syncthreads();
+  if (tid < 8) gy[8 * blockIdx.x + tid] = (red[tid] + red[8 + tid]) + (red[16 + tid] + red[24 + tid]);
   for (int e = tid; e < 8 * (EKF_UB / 2); e += VT_THREADS) {
     const int r = e >> 6, c = (e & 63) * 2;
-    *reinterpret_cast<double2*>(G + (size_t)(8 * blockIdx.x + r) * EKF_UB + c) = *reinterpret_cast<const double2*>(Xs + r * VT_LD + c);
+    *reinterpret_cast<double2*>(G + (size_t)(8 * blockIdx.x + r) * EKF_UB + c) = *reinterpret_cast<const double2*>(Gs + r * VT_LD + c);
   }
 }
 
@@ -1031,7 +1036,7 @@ static const size_t kFactSmemOld = (size_t)cta_chol_panel_smem_doubles<EKF_UB>()
 static const size_t kFactSmem = sizeof(Chol128Smem);
 static int g_chol_smem = 0;   // EKF_CHOL_SMEM=1: the round-1 shared-memory factor kernel
 static const size_t kVSmem = (size_t)(VT_LPACK + (EKF_UB / 32) * 32 * VT_LDD + VT_ROWS * VT_LD + EKF_UB) * sizeof(double);
-static const size_t kGxSmem = (size_t)(VT_LPACK + (EKF_UB / 32) * 32 * VT_LDD + 8 * VT_LD + EKF_UB + GX_WROWS * EKF_UB + GX_FEATS * 26) * sizeof(double);
+static const size_t kGxSmem = (size_t)(VT_LPACK + (EKF_UB / 32) * 32 * VT_LDD + 8 * VT_LD + EKF_UB + GX_WROWS * EKF_UB + GX_FEATS * 26 + 2 + 8 * VT_LD + 32) * sizeof(double);
 
 int update_kernels_init() {
   const char* env = getenv("EKF_CHOL_SMEM");
