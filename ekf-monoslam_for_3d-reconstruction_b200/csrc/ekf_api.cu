@@ -135,7 +135,9 @@ int ekf_destroy(ekf_handle* h) {
   cudaFree(h->map_dev); cudaFree(h->keep_dev); cudaFree(h->newpos_dev); cudaFree(h->ctl); cudaFree(h->frame); cudaFree(h->raw);
   cudaFree(h->picks_dev); cudaFree(h->out_dev); cudaFree(h->gemm_counters);
   if (h->gemm_stream) { cudaStreamSynchronize(h->gemm_stream); cudaStreamDestroy(h->gemm_stream); }
-  cudaFree(h->Wbuf[1]); cudaFree(h->Wbuf[2]); cudaFree(h->Wbuf[3]); cudaFree(h->Wbuf[4]); cudaFree(h->Wbuf[5]); cudaFree(h->Gbuf);
+  cudaFree(h->Wbuf[1]); cudaFree(h->Wbuf[2]); cudaFree(h->Wbuf[3]); cudaFree(h->Wbuf[4]); cudaFree(h->Wbuf[5]); cudaFree(h->Wbuf[6]); cudaFree(h->Wbuf[7]); cudaFree(h->Gbuf);
+  cudaFree(h->G2buf); cudaFree(h->Sg2buf[0]); cudaFree(h->Sg2buf[1]);
+  for (int i = 0; i < 2; ++i) { if (h->ev_mini[i]) cudaEventDestroy(h->ev_mini[i]); if (h->ev_Sg2[i]) cudaEventDestroy(h->ev_Sg2[i]); }
   cudaFree(h->Dinv2); cudaFree(h->Dblk2); cudaFree(h->yb2); cudaFree(h->delta1); cudaFree(h->delta2); cudaFree(h->gy); cudaFree(h->bt_H); cudaFree(h->bt_zmh); cudaFree(h->Sgbuf); cudaFree(h->bt_pos); cudaFree(h->bt_nd); cudaFree(h->chain_flags); cudaFree(h->tile_order); cudaFree(h->tile_nhot); cudaFree(h->tile_counters);
   if (h->v_stream) { cudaStreamSynchronize(h->v_stream); cudaStreamDestroy(h->v_stream); }
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
@@ -207,6 +209,8 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
   TRY(dalloc(&h->Wbuf[1], (size_t)(h->ncap + 1 + EKF_DIST_PAD_ROWS) * EKF_UB)) TRY(dalloc(&h->Wbuf[2], (size_t)(h->ncap + 1 + EKF_DIST_PAD_ROWS) * EKF_UB)) TRY(dalloc(&h->Wbuf[3], (size_t)(h->ncap + 1) * EKF_UB))
   TRY(dalloc(&h->Gbuf, EKF_UB * EKF_UB))
   TRY(dalloc(&h->Wbuf[4], (size_t)(h->ncap + 1) * EKF_UB)) TRY(dalloc(&h->Wbuf[5], (size_t)(h->ncap + 1) * EKF_UB))
+  TRY(dalloc(&h->Wbuf[6], (size_t)(h->ncap + 1) * EKF_UB)) TRY(dalloc(&h->Wbuf[7], (size_t)(h->ncap + 1) * EKF_UB))
+  TRY(dalloc(&h->G2buf, EKF_UB * EKF_UB)) TRY(dalloc(&h->Sg2buf[0], EKF_UB * EKF_UB)) TRY(dalloc(&h->Sg2buf[1], EKF_UB * EKF_UB))
   TRY(dalloc(&h->Dinv2, EKF_UB * EKF_UB)) TRY(dalloc(&h->Dblk2, EKF_UB * 32)) TRY(dalloc(&h->yb2, EKF_UB)) TRY(dalloc(&h->gy, EKF_UB))
   TRY(dalloc(&h->bt_H, 26 * (size_t)feature_capacity)) TRY(dalloc(&h->bt_zmh, 2 * (size_t)feature_capacity)) TRY(dalloc(&h->bt_pos, feature_capacity))
   TRY(dalloc(&h->bt_nd, feature_capacity)) TRY(dalloc(&h->Sgbuf, EKF_UB * EKF_UB))
@@ -232,6 +236,9 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
       TRY(cudaEventCreateWithFlags(&h->ev_dd[i], cudaEventDisableTiming))
     }
     TRY(cudaEventCreateWithFlags(&h->ev_A, cudaEventDisableTiming))
+    for (int i = 0; i < 2; ++i) {
+      TRY(cudaEventCreateWithFlags(&h->ev_mini[i], cudaEventDisableTiming)) TRY(cudaEventCreateWithFlags(&h->ev_Sg2[i], cudaEventDisableTiming))
+    }
     TRY(cudaEventCreateWithFlags(&h->ev_G, cudaEventDisableTiming)) TRY(cudaEventCreateWithFlags(&h->ev_corr, cudaEventDisableTiming))
     for (int i = 0; i < 3; ++i) {
       TRY(cudaEventCreateWithFlags(&h->ev_gather[i], cudaEventDisableTiming)) TRY(cudaEventCreateWithFlags(&h->ev_V[i], cudaEventDisableTiming))
@@ -250,6 +257,8 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
     // 0.764 against 0.786 ms per cfg2 step), 0 = factor-beside-downdate — see DESIGN.md section 4
     e = getenv("EKF_SCHED");
     h->sched = e ? atoi(e) : 1;
+    e = getenv("EKF_S_LOOKAHEAD");
+    h->s_lookahead = e ? atoi(e) : 0;   // measured slower (0.772 against 0.726 ms per cfg2 step): see DESIGN.md section 4
     e = getenv("EKF_PRELAUNCH");
     h->prelaunch_on = e ? atoi(e) : 1;
     e = getenv("EKF_SPLIT_DD");
@@ -754,6 +763,11 @@ static void chain_short_prelaunch(ekf_handle* h) {
     launch_blk_gather2(sg, h->Sigma, h->ld, h->n, h->ft, b * (EKF_UB / 2), 0, raw[b], cor[b], &h->launches, bt, &h->ctl->n_li);
     cudaEventRecord(h->ev_gather[b], sg);
   }
+  if (h->s_lookahead && h->N > EKF_UB) {   // hot rows of W''_2 from the prior covariance (S look-ahead)
+    ProfScope ps(h, 3, sg); TraceScope ts("mini", 2, sg);
+    launch_blk_gather_hot(sg, h->Sigma, h->ld, h->n, h->ft, 2 * (EKF_UB / 2), 0, h->Wbuf[6], &h->launches, bt, &h->ctl->n_li);
+    cudaEventRecord(h->ev_mini[0], sg);
+  }
   h->prelaunched = true;
 }
 
@@ -767,6 +781,11 @@ static int stacked_update_chain_short(ekf_handle* h, int cnt) {
   double* Ds[2] = {h->Dblk, h->Dblk2};
   double* ys[2] = {h->yb, h->yb2};
   double* dl[3] = {h->delta, h->delta1, h->delta2};   // delta_b lives in dl[b % 3]; delta_{-1} = delta_{-2} = 0
+  // S look-ahead: from block 2 on, S_b is formed from the hot rows of W''_b gathered one block EARLIER (from Sigma_{b-3}, next to the
+  // full gather of block b-1) with two correction terms, -G2 G2^T (G2 = H_b V_{b-2}, formed off the chain as soon as V_{b-2}
+  // exists) and -G G^T (k_blk_Gx), so that S_b does not wait for the downdate of block b-2 and the gather behind it
+  double* rawH[2] = {h->Wbuf[6], h->Wbuf[7]};
+  const bool sla = h->s_lookahead && nblk > 2;
   for (int i = 0; i < 3; ++i) cudaMemsetAsync(dl[i], 0, sizeof(double) * (size_t)h->n, sm);
   // gather beside the downdate (hot tiles first): lower-triangle mode with square tiles only
   const int T = (h->n + 63) / 64, Ltiles = T * (T + 1) / 2;
@@ -786,6 +805,11 @@ static int stacked_update_chain_short(ekf_handle* h, int cnt) {
     launch_blk_gather2(sg, h->Sigma, h->ld, h->n, h->ft, b * (EKF_UB / 2), cnt, raw[b], cor[b], &h->launches, bt);
     cudaEventRecord(h->ev_gather[b], sg);
   }
+  if (sla && !(pre && h->N > EKF_UB)) {
+    ProfScope ps(h, 3, sg); TraceScope ts("mini", 2, sg);
+    launch_blk_gather_hot(sg, h->Sigma, h->ld, h->n, h->ft, 2 * (EKF_UB / 2), cnt, rawH[0], &h->launches, bt);
+    cudaEventRecord(h->ev_mini[0], sg);
+  }
   for (int b = 0; b < nblk; ++b) {
     const int f0 = b * (EKF_UB / 2), p = b & 1, q = p ^ 1;
     if (b > 0) {
@@ -803,13 +827,26 @@ static int stacked_update_chain_short(ekf_handle* h, int cnt) {
       const int rc = launch_gemm_nt_sub(sc, cor[p], EKF_UB, Vb[q], EKF_UB, h->Gbuf, EKF_UB, h->n, EKF_UB, EKF_UB, nullptr, 0, h->gemm_counters, &h->launches);
       if (rc) return rc;
       cudaEventRecord(h->ev_corr2[p], sc);
+      if (sla && b + 1 < nblk) {   // G2_{b+1} = H_{b+1} V_{b-1} and -G2 G2^T, a block ahead of their use
+        launch_blk_G(sc, Vb[q], h->ft, (b + 1) * (EKF_UB / 2), cnt, h->G2buf, &h->launches);
+        launch_blk_Sg(sc, h->G2buf, h->Sg2buf[q], &h->launches);
+        cudaEventRecord(h->ev_Sg2[q], sc);
+      }
       // -G_b G_b^T now, in the shadow of the gather this block still waits for
       { ProfScope ps(h, 4); TraceScope ts("Sg", b, sm); launch_blk_Sg(sm, h->Gbuf, h->Sgbuf, &h->launches); }
     }
-    cudaStreamWaitEvent(sm, h->ev_gather[p], 0);   // only S_b reads W'_b: Gx_b ran in the shadow of the gather
-    { ProfScope ps(h, 4); TraceScope ts("S", b, sm);
+    if (sla && b >= 2) {   // hot rows of W''_b and -G2 G2^T were formed a block ago
+      cudaStreamWaitEvent(sm, h->ev_mini[p], 0);
+      cudaStreamWaitEvent(sm, h->ev_Sg2[p], 0);
+      ProfScope ps(h, 4); TraceScope ts("S", b, sm);
+      launch_blk_S_nu_G(sm, rawH[p], h->ft, f0, cnt, h->dcfg, dl[(b + 1) % 3] /* delta_{b-2} */, h->Gbuf, h->Lb, h->nu, &h->launches, h->gy, bt, h->Sgbuf,
+                        nullptr, nullptr, 0, h->Sg2buf[p]);
+    } else {
+      cudaStreamWaitEvent(sm, h->ev_gather[p], 0);   // only S_b reads W'_b: Gx_b ran in the shadow of the gather
+      ProfScope ps(h, 4); TraceScope ts("S", b, sm);
       launch_blk_S_nu_G(sm, raw[p], h->ft, f0, cnt, h->dcfg, dl[(b + 1) % 3] /* delta_{b-2} */, b > 0 ? h->Gbuf : nullptr, h->Lb, h->nu, &h->launches,
-                        b > 0 ? h->gy : nullptr, bt, b > 0 ? h->Sgbuf : nullptr); }
+                        b > 0 ? h->gy : nullptr, bt, b > 0 ? h->Sgbuf : nullptr);
+    }
     if (b > 0) {   // release the downdate of block b-1 (it also waits for V_{b-1})
       cudaEventRecord(h->ev_S, sm);
       cudaStreamWaitEvent(sg, h->ev_S, 0);
@@ -837,12 +874,18 @@ static int stacked_update_chain_short(ekf_handle* h, int cnt) {
         else launch_blk_gather2(sgat, h->Sigma, h->ld, h->n, h->ft, (b + 1) * (EKF_UB / 2), cnt, raw[q], cor[q], &h->launches, bt);
         cudaEventRecord(h->ev_gather[q], sgat);
       }
+      if (sla && b + 2 < nblk) {   // hot rows of W''_{b+2} from the same covariance (Sigma_{b-1}); rawH[p] was last read by S_b
+        ProfScope ps(h, 3, sgat); TraceScope ts("mini", b + 2, sgat);
+        launch_blk_gather_hot(sgat, h->Sigma, h->ld, h->n, h->ft, (b + 2) * (EKF_UB / 2), cnt, rawH[p], &h->launches, bt);
+        cudaEventRecord(h->ev_mini[p], sgat);
+      }
       cudaEventRecord(h->ev_dd[q], sg);
     }
     // V_b on its own stream: after factor_b, the correction of W_b and the downdate that still reads Vb[p] (block b-2)
     cudaStreamWaitEvent(sv, h->ev_F[p], 0);
     if (b > 0) cudaStreamWaitEvent(sv, h->ev_corr2[p], 0);
     if (b > 1) cudaStreamWaitEvent(sv, h->ev_dd[p], 0);
+    if (sla && b > 1) cudaStreamWaitEvent(sv, h->ev_Sg2[p], 0);   // G2_b has read V_{b-2} out of the panel V_b is about to overwrite
     { ProfScope ps(h, 5, sv); TraceScope ts("V", b, sv);
       launch_blk_V(sv, cor[p], 0, h->n, Ls[p], Ds[p], ys[p], dl[b % 3], &h->launches, Vb[p], dl[(b + 2) % 3] /* delta_{b-1} */); }
     cudaEventRecord(h->ev_V[b % 3], sv);

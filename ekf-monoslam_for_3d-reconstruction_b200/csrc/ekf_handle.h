@@ -51,7 +51,7 @@ struct ekf_handle {
   float* det_xy = nullptr; size_t det_cap = 0;
   // look-ahead pipeline of the stacked update (ekf_api.cu::stacked_update_lookahead)
   cudaStream_t gemm_stream = nullptr, corr_stream = nullptr;
-  double* Wbuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // Wbuf[0] == W; [4], [5]: V_b of the chain-short schedule
+  double* Wbuf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // Wbuf[0] == W; [4], [5]: V_b of the chain-short schedule; [6], [7]: hot rows of W'' (S look-ahead)
   double* Gbuf = nullptr;
   // chain-short schedule (ekf_api.cu::stacked_update_chain_short): second set of factor outputs (V_{b-1} reads one set while
   // factor_b writes the other), delta ping-pong, gy = G_b y_{b-1}, the stream of the n-row solves and per-block events
@@ -70,6 +70,10 @@ struct ekf_handle {
   unsigned int chain_seq = 0;
   cudaStream_t chain_stream = nullptr;
   cudaEvent_t ev_chain = nullptr;
+  // S look-ahead of the chain-short schedule (EKF_S_LOOKAHEAD): G2 = H_b V_{b-2}, -G2 G2^T per block parity, events
+  double *G2buf = nullptr, *Sg2buf[2] = {nullptr, nullptr};
+  cudaEvent_t ev_mini[2] = {nullptr, nullptr}, ev_Sg2[2] = {nullptr, nullptr};
+  int s_lookahead = 0;
   bool prelaunched = false;   // block tables + first two gathers were started before the n_li read-back (chain_short_prelaunch)
   int prelaunch_on = 1;       // EKF_PRELAUNCH=0 switches that off
   int sched = 1;          // 1: chain-short (default for pipe_small <= n < lookahead), 0: factor-beside-downdate (EKF_SCHED)

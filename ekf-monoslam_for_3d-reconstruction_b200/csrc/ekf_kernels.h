@@ -51,7 +51,9 @@ void launch_blk_S_nu(cudaStream_t st, const double* W, FeatTab ft, int f0, int c
 void launch_blk_S_nu_G(cudaStream_t st, const double* Wraw, FeatTab ft, int f0, int cnt, const DevCfg& cfg, const double* delta,
                        const double* G, double* Sb, double* nu, long long* launches, const double* gy = nullptr,
                        BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}, const double* Sg = nullptr, unsigned int* pub_ticket = nullptr,
-                       unsigned int* pub_flag = nullptr, unsigned int pub_token = 0);
+                       unsigned int* pub_flag = nullptr, unsigned int pub_token = 0, const double* Sg2 = nullptr);
+void launch_blk_gather_hot(cudaStream_t st, const double* Sigma, int ld, int n, FeatTab ft, int f0, int cnt, double* W, long long* launches, BlkTab bt,
+                           const int* cnt_dev = nullptr);
 void launch_blk_Sg(cudaStream_t st, const double* G, double* Sg, long long* launches, unsigned int* pub_ticket = nullptr,
                    unsigned int* pub_flag = nullptr, unsigned int pub_token = 0);
 void launch_blk_prep(cudaStream_t st, FeatTab ft, int cnt, double* H, double* zmh, int* pos, int* nd, long long* launches,

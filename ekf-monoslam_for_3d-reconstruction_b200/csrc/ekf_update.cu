@@ -306,7 +306,10 @@ __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ S
                                                     int cnt, const double* __restrict__ delta, double* __restrict__ W,
                                                     double* __restrict__ nu, double* __restrict__ W2, int rows_per_cta,
                                                     BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}, const int* __restrict__ cnt_dev = nullptr,
-                                                    unsigned int* pub_ticket = nullptr, unsigned int* pub_flag = nullptr, unsigned int pub_token = 0) {
+                                                    unsigned int* pub_ticket = nullptr, unsigned int* pub_flag = nullptr, unsigned int pub_token = 0,
+                                                    int hot_rows = 0) {
+  // hot_rows (needs bt): the launch covers only the rows the block's own S_b reads — the 7 camera rows and the block's feature rows,
+  // row index r of the launch -> state row r (r < 7) or pos[(r - 7) / 6] + (r - 7) % 6 — written at their true row index.
   if (cnt_dev) cnt = *cnt_dev;   // launched before the host has read the count back (see ekf_update_after_match)
   // Sigma is read past L1 (ld.global.cg): in the chain-short schedule this kernel runs BESIDE the downdate that still writes the
   // tiles it does not read (k_wait_tiles gates it), so no line of Sigma may be served from a stale L1 copy.
@@ -343,7 +346,16 @@ __global__ void __launch_bounds__(256) k_blk_gather(const double* __restrict__ S
   const int pos = poss[a], nd = nds[a];
 #pragma unroll 2
   for (int rq = rl; rq < rows_per_cta; rq += rstep) {
-    const int i = row0 + blockIdx.x * rows_per_cta + rq;   // rows [row0, n): the caller's row block
+    int i = row0 + blockIdx.x * rows_per_cta + rq;   // rows [row0, n): the caller's row block
+    if (hot_rows) {
+      const int r = blockIdx.x * rows_per_cta + rq;
+      if (r >= 7 + 6 * nb) break;
+      if (r >= 7) {
+        const int fa = (r - 7) / 6, k = (r - 7) % 6;
+        if (7 + k >= nds[fa]) continue;   // an XYZ feature has three rows
+        i = poss[fa] + k;
+      } else i = r;
+    }
     if (i >= n) break;   // (no barrier inside this loop: the publish below is reached by every thread)
     const double* row = Sigma + (size_t)i * ld;
     double sg[13];
@@ -461,7 +473,9 @@ __global__ void __launch_bounds__(128) k_blk_S_tiled(const double* __restrict__ 
                                                      double* __restrict__ Sb, const double* __restrict__ delta, double* __restrict__ nu,
                                                      const double* __restrict__ Gsub, const double* __restrict__ gy = nullptr,
                                                      BlkTab bt = BlkTab{nullptr, nullptr, nullptr, nullptr}, const double* __restrict__ Sg = nullptr,
-                                                     unsigned int* pub_ticket = nullptr, unsigned int* pub_flag = nullptr, unsigned int pub_token = 0) {
+                                                     unsigned int* pub_ticket = nullptr, unsigned int* pub_flag = nullptr, unsigned int pub_token = 0,
+                                                     const double* __restrict__ Sg2 = nullptr) {
+  // Sg2 != null: W' was gathered one block earlier still and -G2 G2^T (G2 = H_b V_{b-2}) is the second correction term.
   // Sg != null (chain-short schedule): the term -G G^T was formed ahead of time by k_blk_Sg while the gather of W' was still
   // running; this launch then only adds the 13-row gather H_b W' and R — two round trips on the critical cycle instead of five.
   extern __shared__ __align__(16) double s2sm[];
@@ -493,6 +507,13 @@ __global__ void __launch_bounds__(128) k_blk_S_tiled(const double* __restrict__ 
   if (Sg) {
 #pragma unroll
     for (int ct = 0; ct < 4; ++ct) sgv[ct] = *reinterpret_cast<const double2*>(Sg + (size_t)r * EKF_UB + 32 * bj + 8 * ct + 2 * t4);
+    if (Sg2) {
+#pragma unroll
+      for (int ct = 0; ct < 4; ++ct) {
+        const double2 v2 = *reinterpret_cast<const double2*>(Sg2 + (size_t)r * EKF_UB + 32 * bj + 8 * ct + 2 * t4);
+        sgv[ct].x += v2.x; sgv[ct].y += v2.y;
+      }
+    }
   }
   if (r < kr) {
     int pos, nd;
@@ -1120,11 +1141,11 @@ void launch_blk_S_nu(cudaStream_t st, const double* W, FeatTab ft, int f0, int c
 // S_b from the uncorrected gather and G (see k_blk_S), and the gather with a second copy of W'
 void launch_blk_S_nu_G(cudaStream_t st, const double* Wraw, FeatTab ft, int f0, int cnt, const DevCfg& cfg, const double* delta,
                        const double* G, double* Sb, double* nu, long long* launches, const double* gy, BlkTab bt, const double* Sg,
-                       unsigned int* pub_ticket, unsigned int* pub_flag, unsigned int pub_token) {
+                       unsigned int* pub_ticket, unsigned int* pub_flag, unsigned int pub_token, const double* Sg2) {
   static const bool legacy = [] { const char* e = getenv("EKF_S_TILED"); return e && atoi(e) == 0; }();
   if (legacy && !gy && !Sg && !pub_flag) k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(Wraw, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, delta, nu, G);
   else k_blk_S_tiled<<<10, 128, Sg ? 0 : 2 * 32 * S2_LD * sizeof(double), st>>>(Wraw, ft, f0, cnt, cfg.sigma_pixel_2, Sb, delta, nu, Sg ? nullptr : G, gy, bt, Sg,
-                                                                               pub_ticket, pub_flag, pub_token);
+                                                                               pub_ticket, pub_flag, pub_token, Sg2);
   *launches += 1;
 }
 void launch_blk_Sg(cudaStream_t st, const double* G, double* Sg, long long* launches, unsigned int* pub_ticket, unsigned int* pub_flag,
@@ -1170,6 +1191,13 @@ void launch_blk_gather2_after_tiles(cudaStream_t st, const double* Sigma, int ld
   k_wait_tiles<<<1, 32, 0, st>>>(hot_counter, n_hot, ctl);
   *launches += 1;
   launch_blk_gather2(st, Sigma, ld, n, ft, f0, cnt, W, W2, launches, bt, nullptr, nullptr, nullptr, 0);
+}
+// the rows of W' = Sigma H_b^T that S_b itself reads (7 camera rows + the block's feature rows), at their true row index of W
+void launch_blk_gather_hot(cudaStream_t st, const double* Sigma, int ld, int n, FeatTab ft, int f0, int cnt, double* W, long long* launches, BlkTab bt,
+                           const int* cnt_dev) {
+  const int rows = 7 + 6 * (EKF_UB / 2), gr = 4;
+  k_blk_gather<<<(rows + gr - 1) / gr, 256, 0, st>>>(Sigma, ld, 0, n, ft, f0, cnt, nullptr, W, nullptr, nullptr, gr, bt, cnt_dev, nullptr, nullptr, 0, 1);
+  *launches += 1;
 }
 void launch_blk_G(cudaStream_t st, const double* Vprev, FeatTab ft, int f0, int cnt, double* G, long long* launches) {
   k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(Vprev, ft, f0, cnt, 0.0, G, 1, nullptr, nullptr, nullptr);
