@@ -416,6 +416,7 @@ int ekf_predict(ekf_handle* h, const double dv[3], const double dw[3], int vcont
   if (!h->have_frame) return ekf_fail(h, EKF_ERR_STATE, "predict before captureNewFrame");
   EKF_CUDA_CHECK(cudaSetDevice(h->device));
   const double z3[3] = {0, 0, 0};
+  h->cam_cache_ok = false;
   if (vcontrol) h->noise_cov_factor = 0; else h->noise_cov_factor++;
   if (h->cfg.kernel_size < 100000) frame_ready(h);   // motion-blur template prediction on: keep the whole step behind the upload
   {
@@ -1138,6 +1139,7 @@ int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
   if (!h || n_picks < 0 || (n_picks > 0 && !picks)) return EKF_ERR_ARG;
   if (!h->predicted) return ekf_fail(h, EKF_ERR_STATE, "update before predict");
   EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  h->cam_cache_ok = false;
   cudaStream_t st = h->stream;
   // picks_dev is sized once by ekf_create (EKF_PICKS_CAP draws): no allocation inside the step
   if (n_picks > h->picks_cap) return ekf_fail(h, EKF_ERR_CAPACITY, "more RANSAC picks than EKF_PICKS_CAP: pass at most that many draws per update");
@@ -1245,6 +1247,7 @@ int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
   }
   h->stats.kernel_launches = h->launches;
   h->predicted = false;
+  h->cam_cache_ok = true;
   return EKF_OK;
 }
 
@@ -1382,6 +1385,10 @@ double ekf_get_dt(const ekf_handle* h) { return h ? h->dT : 0.0; }
 
 int ekf_get_state(ekf_handle* h, double out[EKF_STATE_DIM]) {
   if (!h || !out) return EKF_ERR_ARG;
+  // The packed result record of update() already carries the camera state and its covariance block (k_bookkeeping), and nothing
+  // between two predicts changes them (removeFeature / addFeature / XYZ conversion touch feature rows only): answer from the
+  // host copy instead of another device round trip.
+  if (h->cam_cache_ok) { memcpy(out, h->out_host, sizeof(double) * EKF_CAM); return EKF_OK; }
   EKF_CUDA_CHECK(cudaSetDevice(h->device));
   EKF_CUDA_CHECK(cudaMemcpyAsync(out, h->mu, sizeof(double) * EKF_CAM, cudaMemcpyDeviceToHost, h->stream));
   EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
@@ -1389,6 +1396,7 @@ int ekf_get_state(ekf_handle* h, double out[EKF_STATE_DIM]) {
 }
 int ekf_get_sigma(ekf_handle* h, double out[EKF_STATE_DIM * EKF_STATE_DIM]) {
   if (!h || !out) return EKF_ERR_ARG;
+  if (h->cam_cache_ok) { memcpy(out, h->out_host + EKF_CAM, sizeof(double) * EKF_CAM * EKF_CAM); return EKF_OK; }
   EKF_CUDA_CHECK(cudaSetDevice(h->device));
   EKF_CUDA_CHECK(cudaMemcpy2DAsync(out, sizeof(double) * EKF_CAM, h->Sigma, sizeof(double) * h->ld, sizeof(double) * EKF_CAM, EKF_CAM,
                                    cudaMemcpyDeviceToHost, h->stream));
@@ -1549,6 +1557,7 @@ int ekf_get_full(ekf_handle* h, double* mu, double* sigma, int ld) {
 int ekf_set_full(ekf_handle* h, const double* mu, const double* sigma, int ld) {
   if (!h || !mu || !sigma || ld < h->n) return EKF_ERR_ARG;
   EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  h->cam_cache_ok = false;
   EKF_CUDA_CHECK(cudaMemcpyAsync(h->mu, mu, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
   EKF_CUDA_CHECK(cudaMemcpy2DAsync(h->Sigma, sizeof(double) * h->ld, sigma, sizeof(double) * ld, sizeof(double) * h->n, h->n,
                                    cudaMemcpyHostToDevice, h->stream));

@@ -45,6 +45,7 @@ struct ekf_handle {
   double dT = 1.0, old_ts = -1.0;
   int patchnumbre = 1, noise_cov_factor = 0;
   bool predicted = false, have_frame = false;
+  bool cam_cache_ok = false;   // out_host holds the camera state and its 14 x 14 covariance block as of the last update (getState / getSigma)
   int lower_only = 0;
   // corner detector scratch (ekf_detect.cu), sized to the frame on first use
   uint8_t* det_mask = nullptr; float* det_eig = nullptr; unsigned long long* det_keys = nullptr; int* det_counters = nullptr;

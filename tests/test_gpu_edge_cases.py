@@ -96,3 +96,31 @@ def test_capacity_and_argument_errors(gpu_pkg):
     small = np.zeros((4, 4), np.uint8)
     with pytest.raises(gpu_pkg.EkfError):
         f.captureNewFrame(small, 2.0)
+
+
+def test_camera_accessors_answer_from_the_step_record(gpu_pkg, orc):
+    """getState / getSigma after update() are served from the packed result record (no device round trip): they must equal the
+    device state bit for bit after the update, after removeFeature / addFeature (which leave the camera block alone) and — read from
+    the device again — after predict and after set_full."""
+    sc = gpu_pkg.synth.Scene(n_features=24, n_frames=4, seed=77)
+    g, _ = make_pair(gpu_pkg, orc, sc)
+    seed_features(g, sc)
+
+    def check(ctx):
+        mu, S = g.get_full()
+        assert np.array_equal(g.getState(), mu[:14]), ctx
+        assert np.array_equal(g.getSigma(), S[:14, :14]), ctx
+
+    for t in (1, 2):
+        g.captureNewFrame(sc.frame(t), sc.stamps[t]); g.predict()
+        check(f"after predict {t}")
+        g.update(sc.picks(t, 24))
+        check(f"after update {t}")
+    g.removeFeature(3)
+    check("after removeFeature")
+    g.addFeature(*sc.feature_pixels[3])
+    check("after addFeature")
+    mu, S = g.get_full()
+    mu = mu.copy(); mu[0] += 0.25
+    g.set_full(mu, S)
+    check("after set_full")
