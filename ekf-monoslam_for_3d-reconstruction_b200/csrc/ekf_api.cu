@@ -340,14 +340,11 @@ static int capture_common(ekf_handle* h, const uint8_t* img, int width, int heig
   }
   const int dstride = (dw + 15) & ~15;
   const size_t need = (size_t)dstride * dh;
-  // a host frame goes up on the copy stream, ordered after everything already enqueued on the filter's stream (earlier readers
-  // of the frame buffer); a device frame is copied in the filter's own stream as before
-  cudaStream_t cs = device_src ? h->stream : h->copy_stream;
-  if (device_src) frame_ready(h);
-  else {
-    EKF_CUDA_CHECK(cudaEventRecord(h->ev_prev, h->stream));
-    EKF_CUDA_CHECK(cudaStreamWaitEvent(cs, h->ev_prev, 0));
-  }
+  // the frame goes into the filter's buffer on the copy stream, ordered after everything already enqueued on the filter's stream
+  // (earlier readers of the frame buffer)
+  cudaStream_t cs = h->copy_stream;   // device frames too: the copy is ordered after the filter's stream and runs beside predict
+  EKF_CUDA_CHECK(cudaEventRecord(h->ev_prev, h->stream));
+  EKF_CUDA_CHECK(cudaStreamWaitEvent(cs, h->ev_prev, 0));
   if (need > h->frame_cap) {
     EKF_CUDA_CHECK(cudaStreamSynchronize(cs));
     EKF_CUDA_CHECK(cudaStreamSynchronize(h->stream));
@@ -383,10 +380,8 @@ static int capture_common(ekf_handle* h, const uint8_t* img, int width, int heig
     match_make_tensor_map(&h->frame_map, h->frame, dw, dh, dstride, 1, h->cfg.window_size, (int)h->cfg.search_clamp);
   h->fv = FrameView{h->frame, dw, dh, dstride};
   h->have_frame = true;
-  if (!device_src) {
-    EKF_CUDA_CHECK(cudaEventRecord(h->ev_frame, cs));
-    h->frame_pending = true;
-  }
+  EKF_CUDA_CHECK(cudaEventRecord(h->ev_frame, cs));
+  h->frame_pending = true;
   return EKF_OK;
 }
 int ekf_capture_frame(ekf_handle* h, const uint8_t* gray, int width, int height, int stride, double stamp) {
@@ -1170,21 +1165,18 @@ int ekf_update_after_match(ekf_handle* h, const uint32_t* picks, int n_picks) {
     }
     if (rc) return ekf_fail_cuda(h, (cudaError_t)rc, "stacked update (li)", __FILE__, __LINE__);
   }
-  // high-innovation rescue and second update
-  {
-    ProfScope ps(h, 8);
-    launch_hi_rescue(st, h->Sigma, h->ld, h->mu, h->ft, h->N, h->ctl, h->dcfg, &h->launches);
-  }
-  // The common case is n_hi == 0 (nothing rescued) without forsePlane: book-keeping and the packed result record are then enqueued
-  // BEFORE the host learns n_hi — the kernel checks the count itself and does nothing when a second update has to run first — so the
-  // step ends with one synchronize instead of two.
+  // High-innovation rescue.  The common case is n_hi == 0 (nothing rescued) without forsePlane: there is no second update then, and
+  // the last CTA of the rescue kernel itself does the step's book-keeping and writes the packed result record, which is copied
+  // back BEFORE the host learns n_hi — the step ends with one synchronize and one launch less.  Otherwise the host runs the second
+  // update and k_bookkeeping below.
   const bool plane = h->cfg.forsePlane != 0;
   int* outi_dev = reinterpret_cast<int*>(h->out_dev + 210);
   const size_t bytes = sizeof(double) * 210 + sizeof(int) * (16 + 3 * (size_t)h->N);
-  if (!plane) {
-    { ProfScope ps(h, 9); launch_bookkeeping(st, h->Sigma, h->ld, h->mu, h->ft, h->N, h->ctl, h->dcfg, h->out_dev, outi_dev, &h->launches, 1); }
-    EKF_CUDA_CHECK(cudaMemcpyAsync(h->out_host, h->out_dev, bytes, cudaMemcpyDeviceToHost, st));
+  {
+    ProfScope ps(h, 8);
+    launch_hi_rescue(st, h->Sigma, h->ld, h->mu, h->ft, h->N, h->ctl, h->dcfg, &h->launches, plane ? nullptr : h->out_dev, plane ? nullptr : outi_dev);
   }
+  if (!plane) EKF_CUDA_CHECK(cudaMemcpyAsync(h->out_host, h->out_dev, bytes, cudaMemcpyDeviceToHost, st));
   EKF_CUDA_CHECK(cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost, st));
   EKF_CUDA_CHECK(cudaStreamSynchronize(st));
   const int n_hi = hc.n_hi;

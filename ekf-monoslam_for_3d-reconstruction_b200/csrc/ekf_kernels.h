@@ -41,7 +41,7 @@ int update_kernels_init();
 void launch_ransac(cudaStream_t st, const double* Sigma, int ld, int n, const double* mu, FeatTab ft, int N, DevCtl* ctl,
                    const DevCfg& cfg, const uint32_t* picks, int n_picks, double* mu_i, int* cand, long long* launches);
 void launch_hi_rescue(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, DevCtl* ctl,
-                      const DevCfg& cfg, long long* launches);
+                      const DevCfg& cfg, long long* launches, double* outd = nullptr, int* outi = nullptr);
 void launch_blk_gather(cudaStream_t st, const double* Sigma, int ld, int row0, int row1, FeatTab ft, int f0, int cnt,
                        const double* delta, double* W, double* nu, long long* launches);
 void launch_blk_factor(cudaStream_t st, const double* W, FeatTab ft, int f0, int cnt, const double* nu, const DevCfg& cfg,
@@ -101,7 +101,7 @@ void launch_blk_V_p2p(cudaStream_t st, double* W, int row0, int row1, const doub
                       DevCtl* ctl, long long* launches);
 void launch_delta_rows(cudaStream_t st, const double* V, const double* y, double* delta, int n, long long* launches);
 void launch_bookkeeping(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, DevCtl* ctl,
-                        const DevCfg& cfg, double* outd, int* outi, long long* launches, int speculative = 0);
+                        const DevCfg& cfg, double* outd, int* outi, long long* launches);
 // ekf_export.cu
 void launch_points_features(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, double* out, int rows,
                             long long* launches);

@@ -262,10 +262,18 @@ __global__ void __launch_bounds__(128) k_predict_S2(const double* __restrict__ S
   double t0 = 0, t1 = 0, h0 = 0, h1 = 0;
   if (lane < nd) {
     const int jb = ekf_idx13(lane, pos);
-    for (int c = 0; c < nd; ++c) {
-      const double sg = Sigma[(size_t)ekf_idx13(c, pos) * ld + jb];
-      t0 += hc[c] * sg; t1 += hc[13 + c] * sg;
+    // all 13 loads of Sigma and of H in flight before the first use (the rolled loop paid the L2 latency per term: 11 us for this
+    // kernel); same terms, same order
+    double sg[13], ha[13], hb[13];
+#pragma unroll
+    for (int c = 0; c < 13; ++c) {
+      const bool in = c < nd;
+      sg[c] = in ? Sigma[(size_t)ekf_idx13(c, pos) * ld + jb] : 0.0;
+      ha[c] = in ? hc[c] : 0.0; hb[c] = in ? hc[13 + c] : 0.0;
     }
+#pragma unroll
+    for (int c = 0; c < 13; ++c)
+      if (c < nd) { t0 += ha[c] * sg[c]; t1 += hb[c] * sg[c]; }
     h0 = hc[lane]; h1 = hc[13 + lane];
   }
   double s00 = t0 * h0, s01 = t0 * h1, s10 = t1 * h0, s11 = t1 * h1;

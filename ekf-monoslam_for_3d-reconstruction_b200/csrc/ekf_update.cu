@@ -180,8 +180,34 @@ __global__ void __launch_bounds__(RANSAC_CL_THREADS) k_ransac_cluster(const doub
 // parameters from mu_tmp (= mu after the low-innovation update), S_hi = H Sigma_tmp H^T without R,
 // chi^2 <= th_hi.  The last block compacts the Hi list.
 // ------------------------------------------------------------------------------------------------
+// Book-keeping of one feature (Patch::update_quality_index, Patch.cpp:143-150, and the flags of the packed result record) and the
+// record's header: shared by k_bookkeeping and by the tail of k_hi_rescue (which does both itself when nothing was rescued).
+__device__ __forceinline__ void bookkeeping_feature(int i, FeatTab ft, int N, const DevCfg& cfg, int* __restrict__ outi) {
+  int nfind = ft.n_find[i];
+  const int ntot = ft.n_tot[i];
+  if (ft.hi[i] || ft.li[i]) nfind++;
+  ft.n_find[i] = nfind;
+  const float qi = (float)(ntot - nfind) / ((float)nfind);
+  ft.quality[i] = qi;
+  if (qi > cfg.quality_ratio) ft.removef[i] = 1;
+  const int fl = (ft.innov[i] ? 1 : 0) | (ft.li[i] ? 2 : 0) | (ft.hi[i] ? 4 : 0) | (ft.removef[i] ? 8 : 0);
+  outi[16 + i] = fl;
+  outi[16 + N + i] = ntot;
+  outi[16 + 2 * N + i] = nfind;
+}
+__device__ __forceinline__ void bookkeeping_record(const double* __restrict__ Sigma, int ld, const double* __restrict__ mu, const DevCtl* ctl,
+                                                   double* __restrict__ outd, int* __restrict__ outi) {
+  for (int e = threadIdx.x; e < 14; e += blockDim.x) outd[e] = mu[e];
+  for (int e = threadIdx.x; e < 196; e += blockDim.x) outd[14 + e] = Sigma[(size_t)(e / 14) * ld + (e % 14)];
+  if (threadIdx.x == 0) {
+    outi[0] = ctl->m_innov; outi[1] = ctl->n_matched; outi[2] = ctl->n_li; outi[3] = ctl->n_hi;
+    outi[4] = ctl->ransac_hyps; outi[5] = ctl->chol_fail; outi[6] = ctl->blur_count; outi[7] = ctl->blur_too_large;
+  }
+}
+
 __global__ void __launch_bounds__(128) k_hi_rescue(const double* __restrict__ Sigma, int ld, const double* __restrict__ mu,
-                                                   FeatTab ft, int N, DevCtl* ctl, DevCfg cfg) {
+                                                   FeatTab ft, int N, DevCtl* ctl, DevCfg cfg, double* __restrict__ outd = nullptr,
+                                                   int* __restrict__ outi = nullptr) {
   __shared__ int is_last;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N) {
@@ -238,6 +264,13 @@ __global__ void __launch_bounds__(128) k_hi_rescue(const double* __restrict__ Si
     ctl->n_hi = nhi;
     ctl->k_rows = 2 * nhi;
     ctl->ticket = 0;
+  }
+  // outd != null: nothing rescued means no second update, so the step's book-keeping and result record are final now — done here
+  // by the last CTA instead of one more launch (when something WAS rescued the host runs the second update and k_bookkeeping)
+  if (outd && nhi == 0) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < N; j += blockDim.x) bookkeeping_feature(j, ft, N, cfg, outi);
+    bookkeeping_record(Sigma, ld, mu, ctl, outd, outi);
   }
 }
 
@@ -1024,32 +1057,10 @@ __global__ void __launch_bounds__(256) k_delta_rows(const double* __restrict__ V
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_bookkeeping(const double* __restrict__ Sigma, int ld, const double* __restrict__ mu,
                                                      FeatTab ft, int N, DevCtl* ctl, DevCfg cfg, double* __restrict__ outd,
-                                                     int* __restrict__ outi, int speculative) {
-  // speculative: launched BEFORE the host knows n_hi (one synchronize less per step); when the rescue found something the second
-  // update has to run first, so this launch does nothing and the host launches the kernel again afterwards
-  if (speculative && ctl->n_hi > 0) return;
+                                                     int* __restrict__ outi) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) {
-    int nfind = ft.n_find[i];
-    const int ntot = ft.n_tot[i];
-    if (ft.hi[i] || ft.li[i]) nfind++;
-    ft.n_find[i] = nfind;
-    const float qi = (float)(ntot - nfind) / ((float)nfind);
-    ft.quality[i] = qi;
-    if (qi > cfg.quality_ratio) ft.removef[i] = 1;
-    const int fl = (ft.innov[i] ? 1 : 0) | (ft.li[i] ? 2 : 0) | (ft.hi[i] ? 4 : 0) | (ft.removef[i] ? 8 : 0);
-    outi[16 + i] = fl;
-    outi[16 + N + i] = ntot;
-    outi[16 + 2 * N + i] = nfind;
-  }
-  if (blockIdx.x == 0) {
-    for (int e = threadIdx.x; e < 14; e += blockDim.x) outd[e] = mu[e];
-    for (int e = threadIdx.x; e < 196; e += blockDim.x) outd[14 + e] = Sigma[(size_t)(e / 14) * ld + (e % 14)];
-    if (threadIdx.x == 0) {
-      outi[0] = ctl->m_innov; outi[1] = ctl->n_matched; outi[2] = ctl->n_li; outi[3] = ctl->n_hi;
-      outi[4] = ctl->ransac_hyps; outi[5] = ctl->chol_fail; outi[6] = ctl->blur_count; outi[7] = ctl->blur_too_large;
-    }
-  }
+  if (i < N) bookkeeping_feature(i, ft, N, cfg, outi);
+  if (blockIdx.x == 0) bookkeeping_record(Sigma, ld, mu, ctl, outd, outi);
 }
 
 // ---- launch wrappers ---------------------------------------------------------------------------
@@ -1114,9 +1125,9 @@ void launch_ransac(cudaStream_t st, const double* Sigma, int ld, int n, const do
   *launches += 1;
 }
 void launch_hi_rescue(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, DevCtl* ctl,
-                      const DevCfg& cfg, long long* launches) {
+                      const DevCfg& cfg, long long* launches, double* outd, int* outi) {
   const int fb = N > 0 ? (N + 127) / 128 : 1;
-  k_hi_rescue<<<fb, 128, 0, st>>>(Sigma, ld, mu, ft, N, ctl, cfg);
+  k_hi_rescue<<<fb, 128, 0, st>>>(Sigma, ld, mu, ft, N, ctl, cfg, outd, outi);
   *launches += 1;
 }
 void launch_blk_gather(cudaStream_t st, const double* Sigma, int ld, int row0, int row1, FeatTab ft, int f0, int cnt,
@@ -1248,8 +1259,8 @@ void launch_delta_rows(cudaStream_t st, const double* V, const double* y, double
   *launches += 1;
 }
 void launch_bookkeeping(cudaStream_t st, const double* Sigma, int ld, const double* mu, FeatTab ft, int N, DevCtl* ctl,
-                        const DevCfg& cfg, double* outd, int* outi, long long* launches, int speculative) {
+                        const DevCfg& cfg, double* outd, int* outi, long long* launches) {
   const int fb = N > 0 ? (N + 255) / 256 : 1;
-  k_bookkeeping<<<fb, 256, 0, st>>>(Sigma, ld, mu, ft, N, ctl, cfg, outd, outi, speculative);
+  k_bookkeeping<<<fb, 256, 0, st>>>(Sigma, ld, mu, ft, N, ctl, cfg, outd, outi);
   *launches += 1;
 }
