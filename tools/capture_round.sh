@@ -13,8 +13,8 @@ python bench.py --workload cfg3_batch4096 > $O/bench_cfg3_$TAG.json 2>/dev/null
 python bench.py --workload cfg4_n2000 --steps 8 --no-cpu-baseline > $O/bench_cfg4_$TAG.json 2>/dev/null
 python bench.py --workload cfg5_match > $O/bench_cfg5_$TAG.json 2>/dev/null
 python bench.py --full-square --no-cpu-baseline > $O/bench_full_$TAG.json 2>/dev/null
-ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $O/launches_$TAG.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_$TAG.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $O/launches_$TAG.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-sharded --no-parity > $O/ncu_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on \
     -k regex:"k_gemm_nt_sub|k_blk_factor|k_blk_V|k_blk_gather|k_match_filter|k_blk_S|k_blk_Gx|k_ransac|k_predict" -s 60 -c 40 -o $O/top_$TAG \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_full_$TAG.log 2>&1
