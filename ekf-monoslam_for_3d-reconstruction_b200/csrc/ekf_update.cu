@@ -644,6 +644,62 @@ __global__ void __launch_bounds__(128) k_blk_S_tiled(const double* __restrict__ 
   if (pub_flag) chain_publish_last_cta(pub_ticket, pub_flag, pub_token);
 }
 
+// K4b(1-fin): S_b = H_b W'_b + R + Sg (+ Sg2) and nu_b for the chain-short schedule — the part of S_b that has to wait for the gather.
+// k_blk_S_tiled in its Sg mode did this with 8 entries and 52 16-byte loads per lane; here one thread owns ONE column pair (13 loads,
+// all in flight behind a single table look-up) and nu_b gets its own CTA, so the kernel is two round trips deep whatever its size:
+// 10 CTAs x 512 threads for the lower 32 x 32 blocks + 1 CTA for nu.
+__global__ void __launch_bounds__(512) k_blk_S_fin(const double* __restrict__ W, int f0, int cnt, double sigma_pixel_2, double* __restrict__ Sb,
+                                                   const double* __restrict__ delta, double* __restrict__ nu, const double* __restrict__ gy,
+                                                   BlkTab bt, const double* __restrict__ Sg, const double* __restrict__ Sg2) {
+  const int nb = min(EKF_UB / 2, cnt - f0), kr = 2 * nb, tid = threadIdx.x;
+  if (blockIdx.x == 10) {   // nu_b = (z - h) - H_b delta - G_b y
+    if (tid < EKF_UB) {
+      double out = 0.0;
+      if (tid < kr) {
+        const int j = f0 + (tid >> 1), pos = bt.pos[j], nd = bt.nd[j];
+        const double* hc = bt.H + 26 * (size_t)j + 13 * (tid & 1);
+        double hv[13], dv[13];
+#pragma unroll
+        for (int c = 0; c < 13; ++c) { hv[c] = (c < nd) ? hc[c] : 0.0; dv[c] = (c < nd) ? delta[ekf_idx13(c, pos)] : 0.0; }
+        double hd = 0;
+#pragma unroll
+        for (int c = 0; c < 13; ++c) if (c < nd) hd += hv[c] * dv[c];
+        out = bt.zmh[2 * j + (tid & 1)] - hd;
+        if (gy) out -= gy[tid];
+      }
+      nu[tid] = out;
+    }
+    return;
+  }
+  int bi = 0, rem = blockIdx.x;
+  while (rem > bi) { rem -= bi + 1; ++bi; }
+  const int r = 32 * bi + (tid >> 4), c = 32 * rem + 2 * (tid & 15);
+  double v0 = (r == c) ? 1.0 : 0.0, v1 = (r == c + 1) ? 1.0 : 0.0;   // rows / columns past the block's measurements: identity
+  if (r < kr && c < kr) {
+    const int j = f0 + (r >> 1), pos = bt.pos[j], nd = bt.nd[j];
+    const double* hc = bt.H + 26 * (size_t)j + 13 * (r & 1);
+    double2 g2 = make_double2(0.0, 0.0), g3 = make_double2(0.0, 0.0);
+    if (Sg) g2 = *reinterpret_cast<const double2*>(Sg + (size_t)r * EKF_UB + c);
+    if (Sg2) g3 = *reinterpret_cast<const double2*>(Sg2 + (size_t)r * EKF_UB + c);
+    double2 wv[13];
+    double hv[13];
+#pragma unroll
+    for (int q = 0; q < 13; ++q) {
+      hv[q] = (q < nd) ? hc[q] : 0.0;
+      wv[q] = (q < nd) ? *reinterpret_cast<const double2*>(W + (size_t)ekf_idx13(q, pos) * EKF_UB + c) : make_double2(0.0, 0.0);
+    }
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 13; ++q) if (q < nd) { s0 += hv[q] * wv[q].x; s1 += hv[q] * wv[q].y; }
+    if (r == c) s0 += sigma_pixel_2;
+    if (r == c + 1) s1 += sigma_pixel_2;
+    if (Sg) { s0 += g2.x; s1 += g2.y; }
+    if (Sg2) { s0 += g3.x; s1 += g3.y; }
+    v0 = s0; v1 = s1;   // kr is even and c is even: c + 1 < kr
+  }
+  *reinterpret_cast<double2*>(Sb + (size_t)r * EKF_UB + c) = make_double2(v0, v1);
+}
+
 // K4b(1''): Sg = -G G^T on the lower 32 x 32 blocks (10 CTAs, DMMA), the part of S_b that does not need the gather of W'_b: in
 // the chain-short schedule it runs right after k_blk_Gx, in the shadow of the downdate / gather the block waits for.
 __global__ void __launch_bounds__(128) k_blk_Sg(const double* __restrict__ Gsub, double* __restrict__ Sg, unsigned int* pub_ticket = nullptr,
@@ -1101,6 +1157,7 @@ int update_kernels_init() {
   if ((e = cudaFuncGetAttributes(&fa, k_blk_gather)) != cudaSuccess) return (int)e;
   if ((e = cudaFuncGetAttributes(&fa, k_blk_prep)) != cudaSuccess) return (int)e;
   if ((e = cudaFuncGetAttributes(&fa, k_blk_S_tiled)) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncGetAttributes(&fa, k_blk_S_fin)) != cudaSuccess) return (int)e;
   return gemm_kernels_preload();
 }
 
@@ -1154,6 +1211,12 @@ void launch_blk_S_nu_G(cudaStream_t st, const double* Wraw, FeatTab ft, int f0, 
                        const double* G, double* Sb, double* nu, long long* launches, const double* gy, BlkTab bt, const double* Sg,
                        unsigned int* pub_ticket, unsigned int* pub_flag, unsigned int pub_token, const double* Sg2) {
   static const bool legacy = [] { const char* e = getenv("EKF_S_TILED"); return e && atoi(e) == 0; }();
+  static const bool s_fin = [] { const char* e = getenv("EKF_S_FIN"); return !(e && atoi(e) == 0); }();
+  if (s_fin && Sg && bt.H && !pub_flag && nu) {
+    k_blk_S_fin<<<11, 512, 0, st>>>(Wraw, f0, cnt, cfg.sigma_pixel_2, Sb, delta, nu, gy, bt, Sg, Sg2);
+    *launches += 1;
+    return;
+  }
   if (legacy && !gy && !Sg && !pub_flag) k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(Wraw, ft, f0, cnt, cfg.sigma_pixel_2, Sb, 0, delta, nu, G);
   else k_blk_S_tiled<<<10, 128, Sg ? 0 : 2 * 32 * S2_LD * sizeof(double), st>>>(Wraw, ft, f0, cnt, cfg.sigma_pixel_2, Sb, delta, nu, Sg ? nullptr : G, gy, bt, Sg,
                                                                                pub_ticket, pub_flag, pub_token, Sg2);
