@@ -1,3 +1,5 @@
+import os as _os_env
+_os_env.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per stream (see _lib.py); before CUDA starts
 #!/usr/bin/env python
 """bench.py — MonoSLAM EKF hot path on B200: frames/s of predict + active-search match + update.
 

@@ -3,6 +3,10 @@
 There is no CPU fallback: if the shared library is missing or has no usable CUDA device the calls
 raise.  build.build() compiles it with nvcc (works without a GPU).
 """
+import os as _os
+# One hardware work queue per stream as far as the device allows (the default is 8; a filter handle owns 8 streams): streams that share a
+# queue serialise against each other.  Only effective when set before the CUDA context exists; an explicit setting wins.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import ctypes as C
 import os
 

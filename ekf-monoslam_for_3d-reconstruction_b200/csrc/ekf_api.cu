@@ -257,6 +257,8 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
     // 0.764 against 0.786 ms per cfg2 step), 0 = factor-beside-downdate — see DESIGN.md section 4
     e = getenv("EKF_SCHED");
     h->sched = e ? atoi(e) : 1;
+    e = getenv("EKF_DD_RELEASE");
+    h->dd_release = e ? atoi(e) : 2;
     e = getenv("EKF_S_LOOKAHEAD");
     h->s_lookahead = e ? atoi(e) : 0;   // measured slower (0.772 against 0.726 ms per cfg2 step): see DESIGN.md section 4
     e = getenv("EKF_PRELAUNCH");
@@ -739,9 +741,10 @@ static int stacked_update_factor_beside_downdate(ekf_handle* h, int cnt) {
 // Whether the low-innovation update of this step will take the chain-short schedule, as far as the host knows BEFORE it has read
 // n_li back: if so, ekf_update_after_match starts the block tables and the first two gathers (which read only the prior covariance and
 // the inlier list the RANSAC kernel left on the device) while that read-back is in flight.
+static ChainFlags chain_flags_view(ekf_handle* h);
 static bool chain_short_likely(const ekf_handle* h) {
   const bool partitioned = h->nccl_comm && h->world > 1;
-  if (partitioned || h->sched != 1 || h->pipe_small <= 0 || h->n < h->pipe_small) return false;
+  if (partitioned || (h->sched != 1 && h->sched != 3) || h->pipe_small <= 0 || h->n < h->pipe_small) return false;
   if (h->lookahead > 0 && h->n >= h->lookahead) return false;
   return h->N > EKF_UB / 2;
 }
@@ -782,6 +785,15 @@ static int stacked_update_chain_short(ekf_handle* h, int cnt) {
   // exists) and -G G^T (k_blk_Gx), so that S_b does not wait for the downdate of block b-2 and the gather behind it
   double* rawH[2] = {h->Wbuf[6], h->Wbuf[7]};
   const bool sla = h->s_lookahead && nblk > 2;
+  // EKF_SCHED=3: pre-positioned factor.  factor_b is launched on its own stream as soon as S_b has been enqueued, takes over the SM
+  // factor_{b-1} just gave back and waits there for the flag the last CTA of the S_b kernel raises: no launch gap between S_b and
+  // the factor, and the downdate of block b-1 need not be held back until S_b is done (EKF_DD_RELEASE: 3 after S_b as in the plain
+  // chain-short schedule, 2 after -G G^T, 1 after Gx, 0 not at all).
+  const bool prepos = h->sched == 3 && !sla && nblk <= std::min(h->tile_blk_cap, 1000);
+  cudaStream_t sf = h->chain_stream;
+  if (prepos) h->chain_seq++;
+  const ChainFlags fl = chain_flags_view(h);
+  const int rel = prepos ? h->dd_release : 3;
   for (int i = 0; i < 3; ++i) cudaMemsetAsync(dl[i], 0, sizeof(double) * (size_t)h->n, sm);
   // gather beside the downdate (hot tiles first): lower-triangle mode with square tiles only
   const int T = (h->n + 63) / 64, Ltiles = T * (T + 1) / 2;
@@ -796,6 +808,7 @@ static int stacked_update_chain_short(ekf_handle* h, int cnt) {
   cudaEventRecord(h->ev_fork, sm);
   cudaStreamWaitEvent(sg, h->ev_fork, 0);
   cudaStreamWaitEvent(sv, h->ev_fork, 0);
+  if (prepos) cudaStreamWaitEvent(sf, h->ev_fork, 0);
   for (int b = 0; b < nblk && b < 2 && !pre; ++b) {   // W'_0 = W_0 and W'_1, both from the prior covariance
     ProfScope ps(h, 3, sg); TraceScope ts("gather", b, sg);
     launch_blk_gather2(sg, h->Sigma, h->ld, h->n, h->ft, b * (EKF_UB / 2), cnt, raw[b], cor[b], &h->launches, bt);
@@ -809,12 +822,14 @@ static int stacked_update_chain_short(ekf_handle* h, int cnt) {
   for (int b = 0; b < nblk; ++b) {
     const int f0 = b * (EKF_UB / 2), p = b & 1, q = p ^ 1;
     if (b > 0) {
+      if (prepos) cudaStreamWaitEvent(sm, h->ev_F[q], 0);   // factor_{b-1} ran on its own stream
       if (b > 1) {
         cudaStreamWaitEvent(sm, h->ev_corr2[q], 0);   // W_{b-1} is corrected (b - 1 = 0 needs no correction)
         cudaStreamWaitEvent(sm, h->ev_V[(b - 2) % 3], 0);   // delta_{b-2} is complete; V_{b-2} no longer reads the factor set p
       }
       { ProfScope ps(h, 4); TraceScope ts("Gx", b, sm); launch_blk_Gx(sm, cor[q], h->ft, f0, cnt, Ls[q], Ds[q], ys[q], h->Gbuf, h->gy, &h->launches, bt); }
       cudaEventRecord(h->ev_G, sm);
+      if (rel == 1) { cudaEventRecord(h->ev_S, sm); cudaStreamWaitEvent(sg, h->ev_S, 0); }
       // W_b = W'_b - V_{b-1} G_b^T beside S_b and the Cholesky
       cudaStreamWaitEvent(sc, h->ev_G, 0);
       cudaStreamWaitEvent(sc, h->ev_V[(b - 1) % 3], 0);
@@ -830,6 +845,7 @@ static int stacked_update_chain_short(ekf_handle* h, int cnt) {
       }
       // -G_b G_b^T now, in the shadow of the gather this block still waits for
       { ProfScope ps(h, 4); TraceScope ts("Sg", b, sm); launch_blk_Sg(sm, h->Gbuf, h->Sgbuf, &h->launches); }
+      if (rel == 2) { cudaEventRecord(h->ev_S, sm); cudaStreamWaitEvent(sg, h->ev_S, 0); }
     }
     if (sla && b >= 2) {   // hot rows of W''_b and -G2 G2^T were formed a block ago
       cudaStreamWaitEvent(sm, h->ev_mini[p], 0);
@@ -841,14 +857,20 @@ static int stacked_update_chain_short(ekf_handle* h, int cnt) {
       cudaStreamWaitEvent(sm, h->ev_gather[p], 0);   // only S_b reads W'_b: Gx_b ran in the shadow of the gather
       ProfScope ps(h, 4); TraceScope ts("S", b, sm);
       launch_blk_S_nu_G(sm, raw[p], h->ft, f0, cnt, h->dcfg, dl[(b + 1) % 3] /* delta_{b-2} */, b > 0 ? h->Gbuf : nullptr, h->Lb, h->nu, &h->launches,
-                        b > 0 ? h->gy : nullptr, bt, b > 0 ? h->Sgbuf : nullptr);
+                        b > 0 ? h->gy : nullptr, bt, b > 0 ? h->Sgbuf : nullptr, prepos ? fl.tickets + 1 : nullptr, prepos ? fl.sg + b : nullptr,
+                        fl.token0 + b);
     }
-    if (b > 0) {   // release the downdate of block b-1 (it also waits for V_{b-1})
+    if (b > 0 && rel == 3) {   // release the downdate of block b-1 (it also waits for V_{b-1})
       cudaEventRecord(h->ev_S, sm);
       cudaStreamWaitEvent(sg, h->ev_S, 0);
     }
-    { ProfScope ps(h, 4); TraceScope ts("factor", b, sm); launch_blk_factor_only(sm, h->Lb, h->nu, Ls[p], Ds[p], ys[p], h->ctl, &h->launches); }
-    cudaEventRecord(h->ev_F[p], sm);
+    if (prepos) {   // every producer the kernel waits for is already enqueued (S_b above): the wait cannot hold back what it needs
+      ProfScope ps(h, 4, sf); TraceScope ts("factor", b, sf);
+      launch_blk_factor_wait(sf, h->Lb, h->nu, Ls[p], Ds[p], ys[p], h->ctl, fl.sg + b, fl.token0 + b, &h->launches);
+    } else {
+      ProfScope ps(h, 4); TraceScope ts("factor", b, sm); launch_blk_factor_only(sm, h->Lb, h->nu, Ls[p], Ds[p], ys[p], h->ctl, &h->launches);
+    }
+    cudaEventRecord(h->ev_F[p], prepos ? sf : sm);
     if (b > 0) {
       cudaStreamWaitEvent(sg, h->ev_V[(b - 1) % 3], 0);
       const bool two = split && b + 1 < nblk;   // the gather of W'_{b+1} starts beside this downdate, after its hot tiles

@@ -75,6 +75,7 @@ struct ekf_handle {
   double *G2buf = nullptr, *Sg2buf[2] = {nullptr, nullptr};
   cudaEvent_t ev_mini[2] = {nullptr, nullptr}, ev_Sg2[2] = {nullptr, nullptr};
   int s_lookahead = 0;
+  int dd_release = 2;      // EKF_SCHED=3 only (EKF_DD_RELEASE): which kernel of block b releases the downdate of block b-1
   bool prelaunched = false;   // block tables + first two gathers were started before the n_li read-back (chain_short_prelaunch)
   int prelaunch_on = 1;       // EKF_PRELAUNCH=0 switches that off
   int sched = 1;          // 1: chain-short (default for pipe_small <= n < lookahead), 0: factor-beside-downdate (EKF_SCHED)

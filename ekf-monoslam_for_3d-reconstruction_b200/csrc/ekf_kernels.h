@@ -85,6 +85,8 @@ void launch_blk_gather2(cudaStream_t st, const double* Sigma, int ld, int n, Fea
 void launch_blk_G(cudaStream_t st, const double* Vprev, FeatTab ft, int f0, int cnt, double* G, long long* launches);
 void launch_blk_factor_only(cudaStream_t st, const double* Sb, const double* nu, double* Lb, double* Dblk, double* yb, DevCtl* ctl,
                             long long* launches);
+void launch_blk_factor_wait(cudaStream_t st, const double* Sb, const double* nu, double* Lb, double* Dblk, double* yb, DevCtl* ctl,
+                            const unsigned int* flag, unsigned int token, long long* launches);
 void launch_plane_gather(cudaStream_t st, const double* Sigma, int ld, int row0, int row1, const double* mu, const double* delta,
                          double* W, double* nu, DevCtl* ctl, long long* launches);
 void launch_plane_S(cudaStream_t st, const double* W, double* Sb, long long* launches);

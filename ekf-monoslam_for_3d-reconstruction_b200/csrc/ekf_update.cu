@@ -650,7 +650,8 @@ __global__ void __launch_bounds__(128) k_blk_S_tiled(const double* __restrict__ 
 // 10 CTAs x 512 threads for the lower 32 x 32 blocks + 1 CTA for nu.
 __global__ void __launch_bounds__(512) k_blk_S_fin(const double* __restrict__ W, int f0, int cnt, double sigma_pixel_2, double* __restrict__ Sb,
                                                    const double* __restrict__ delta, double* __restrict__ nu, const double* __restrict__ gy,
-                                                   BlkTab bt, const double* __restrict__ Sg, const double* __restrict__ Sg2) {
+                                                   BlkTab bt, const double* __restrict__ Sg, const double* __restrict__ Sg2,
+                                                   unsigned int* pub_ticket = nullptr, unsigned int* pub_flag = nullptr, unsigned int pub_token = 0) {
   const int nb = min(EKF_UB / 2, cnt - f0), kr = 2 * nb, tid = threadIdx.x;
   if (blockIdx.x == 10) {   // nu_b = (z - h) - H_b delta - G_b y
     if (tid < EKF_UB) {
@@ -669,6 +670,7 @@ __global__ void __launch_bounds__(512) k_blk_S_fin(const double* __restrict__ W,
       }
       nu[tid] = out;
     }
+    if (pub_flag) chain_publish_last_cta(pub_ticket, pub_flag, pub_token);
     return;
   }
   int bi = 0, rem = blockIdx.x;
@@ -698,6 +700,7 @@ __global__ void __launch_bounds__(512) k_blk_S_fin(const double* __restrict__ W,
     v0 = s0; v1 = s1;   // kr is even and c is even: c + 1 < kr
   }
   *reinterpret_cast<double2*>(Sb + (size_t)r * EKF_UB + c) = make_double2(v0, v1);
+  if (pub_flag) chain_publish_last_cta(pub_ticket, pub_flag, pub_token);
 }
 
 // K4b(1''): Sg = -G G^T on the lower 32 x 32 blocks (10 CTAs, DMMA), the part of S_b that does not need the gather of W'_b: in
@@ -798,6 +801,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_blk_factor(const double* __re
                                                              double* __restrict__ Lout, double* __restrict__ Dblk,
                                                              double* __restrict__ yout, DevCtl* ctl) {
   extern __shared__ __align__(16) double fsm[];
+  cta_chol128(fsm, Sb, EKF_UB, nu, Lout, EKF_UB, Dblk, 32, yout, &ctl->chol_fail);
+}
+// Pre-positioned factor (EKF_SCHED=3): launched on its own stream BEFORE S_b exists, so that it takes over the SM the previous
+// block's factor kernel just gave back, and waits (flag word, acquire, bounded) for the last CTA of the S_b kernel.
+__global__ void __launch_bounds__(CH_THREADS, 1) k_blk_factor_wait(const double* Sb, const double* nu, double* __restrict__ Lout,
+                                                                  double* __restrict__ Dblk, double* __restrict__ yout, DevCtl* ctl,
+                                                                  const unsigned int* flag, unsigned int token) {
+  extern __shared__ __align__(16) double fsm[];
+  if (threadIdx.x == 0 && !chain_wait(flag, token)) atomicOr(&ctl->chol_fail, 64 | 512);
+  __syncthreads();
   cta_chol128(fsm, Sb, EKF_UB, nu, Lout, EKF_UB, Dblk, 32, yout, &ctl->chol_fail);
 }
 __global__ void __launch_bounds__(FACT_THREADS) k_blk_factor_smem(const double* __restrict__ Sb, const double* __restrict__ nu,
@@ -1137,6 +1150,8 @@ int update_kernels_init() {
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_blk_Sg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 32 * S2_LD * sizeof(double)));
   if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_blk_factor_wait, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFactSmem);
+  if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_chain_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFactSmem);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_blk_factor_p2p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFactSmem);
@@ -1158,6 +1173,7 @@ int update_kernels_init() {
   if ((e = cudaFuncGetAttributes(&fa, k_blk_prep)) != cudaSuccess) return (int)e;
   if ((e = cudaFuncGetAttributes(&fa, k_blk_S_tiled)) != cudaSuccess) return (int)e;
   if ((e = cudaFuncGetAttributes(&fa, k_blk_S_fin)) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncGetAttributes(&fa, k_blk_factor_wait)) != cudaSuccess) return (int)e;
   return gemm_kernels_preload();
 }
 
@@ -1212,8 +1228,8 @@ void launch_blk_S_nu_G(cudaStream_t st, const double* Wraw, FeatTab ft, int f0, 
                        unsigned int* pub_ticket, unsigned int* pub_flag, unsigned int pub_token, const double* Sg2) {
   static const bool legacy = [] { const char* e = getenv("EKF_S_TILED"); return e && atoi(e) == 0; }();
   static const bool s_fin = [] { const char* e = getenv("EKF_S_FIN"); return !(e && atoi(e) == 0); }();
-  if (s_fin && Sg && bt.H && !pub_flag && nu) {
-    k_blk_S_fin<<<11, 512, 0, st>>>(Wraw, f0, cnt, cfg.sigma_pixel_2, Sb, delta, nu, gy, bt, Sg, Sg2);
+  if (s_fin && Sg && bt.H && nu) {
+    k_blk_S_fin<<<11, 512, 0, st>>>(Wraw, f0, cnt, cfg.sigma_pixel_2, Sb, delta, nu, gy, bt, Sg, Sg2, pub_ticket, pub_flag, pub_token);
     *launches += 1;
     return;
   }
@@ -1275,6 +1291,11 @@ void launch_blk_gather_hot(cudaStream_t st, const double* Sigma, int ld, int n, 
 }
 void launch_blk_G(cudaStream_t st, const double* Vprev, FeatTab ft, int f0, int cnt, double* G, long long* launches) {
   k_blk_S<<<EKF_UB, EKF_UB, 0, st>>>(Vprev, ft, f0, cnt, 0.0, G, 1, nullptr, nullptr, nullptr);
+  *launches += 1;
+}
+void launch_blk_factor_wait(cudaStream_t st, const double* Sb, const double* nu, double* Lb, double* Dblk, double* yb, DevCtl* ctl,
+                            const unsigned int* flag, unsigned int token, long long* launches) {
+  k_blk_factor_wait<<<1, CH_THREADS, kFactSmem, st>>>(Sb, nu, Lb, Dblk, yb, ctl, flag, token);
   *launches += 1;
 }
 void launch_blk_factor_only(cudaStream_t st, const double* Sb, const double* nu, double* Lb, double* Dblk, double* yb, DevCtl* ctl,

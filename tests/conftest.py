@@ -1,3 +1,5 @@
+import os as _os_env
+_os_env.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per stream (see _lib.py); before CUDA starts
 import os
 import sys
 

@@ -115,7 +115,7 @@ def test_multi_block_update(gpu_pkg, orc, symmetric):
 @pytest.mark.parametrize("env,n_features,sched", [("EKF_LOOKAHEAD_MIN_N", 150, 1), ("EKF_PIPE_MIN_N", 150, 0), ("EKF_PIPE_MIN_N", 210, 0),
                                                   ("EKF_PIPE_MIN_N", 150, 1), ("EKF_PIPE_MIN_N", 210, 1), ("EKF_PIPE_MIN_N", 290, 1),
                                                   ("EKF_PIPE_MIN_N", 290, 2), ("EKF_PIPE_MIN_N", 150, 3), ("EKF_PIPE_MIN_N", 290, 3),
-                                                  ("EKF_PIPE_MIN_N", 290, 4)])
+                                                  ("EKF_PIPE_MIN_N", 290, 4), ("EKF_PIPE_MIN_N", 290, 5)])
 def test_lookahead_pipeline_parity(gpu_pkg, orc, monkeypatch, env, n_features, sched):
     """The pipelined stacked updates forced on at n = 914 (three update blocks), 1274 (four) and 1754 (five, the last one
     partial): the look-ahead schedule (second stream, W correction GEMM; default for n >= 6000) and the two schedules for
@@ -124,7 +124,8 @@ def test_lookahead_pipeline_parity(gpu_pkg, orc, monkeypatch, env, n_features, s
     fourth stream, delta ping-pong).  Same tolerance as the plain path."""
     monkeypatch.setenv("EKF_LOOKAHEAD_MIN_N", "1000000")
     monkeypatch.setenv(env, "1")
-    monkeypatch.setenv("EKF_SCHED", "2" if sched == 3 else str(min(sched, 1)))   # 3: resident-chain schedule (k_chain_factor)
+    # 3: resident-chain schedule (k_chain_factor); 5: chain-short with the pre-positioned factor kernel (k_blk_factor_wait)
+    monkeypatch.setenv("EKF_SCHED", "2" if sched == 3 else "3" if sched == 5 else str(min(sched, 1)))
     if sched == 4:   # chain-short with the S look-ahead (hot rows of W'' gathered a block earlier, second correction term -G2 G2^T)
         monkeypatch.setenv("EKF_S_LOOKAHEAD", "1")
     if sched == 2:   # chain-short with the downdate walking the hot-first tile list and the next gather gated on its hot tiles
