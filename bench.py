@@ -417,6 +417,14 @@ def bench_single(args, ctx, workload, K, Wm, with_cpu=True, with_clocks=True, wi
     tP, _, prof = timed_pass(step_resident, filt, profile=True)
     n_state = filt.state_dim()
     assert n_state == n_end == 14 + 6 * nfeat, f"map changed size during the run: {n_end} / {n_state}"
+    # the same downdate launch timed ALONE (CUDA events, this run, not under a profiler): what the kernel does when V, Gx and the
+    # correction GEMM are not sharing the fp64 pipe with it — reported beside the in-step figure, never instead of it
+    alone_ms = None
+    if not partitioned:
+        try:
+            alone_ms = filt.debug_time_downdate(20)
+        except Exception as ex:   # diagnostic only
+            sys.stderr.write(f"debug_time_downdate: {ex}\n")
     del filt
     h2d = width * height + 4 * nfeat
     d2h = 210 * 8 + (16 + 3 * nfeat) * 4 + 2 * 88 + 14 * 8 + 196 * 8
@@ -470,6 +478,11 @@ def bench_single(args, ctx, workload, K, Wm, with_cpu=True, with_clocks=True, wi
                                     "DMMA issue peak measured by tools/fp64_probe: 37.05 TFLOP/s)",
                      "flops_per_launch": flops_per_launch, "launches": int(gemm_launches),
                      "avg_launch_ms": round(gemm_ms / max(gemm_launches, 1), 5),
+                     "kernel_alone": ({"avg_launch_ms": round(alone_ms, 5), "achieved": round(flops_per_launch / (alone_ms / 1e3) / 1e12, 3),
+                                       "frac": round(flops_per_launch / (alone_ms / 1e3) / 1e12 / peak, 4),
+                                       "note": "same launch, 20 back-to-back repetitions alone on the stream (L2-warm), CUDA events; "
+                                               "inside the step V_b, Gx and the correction GEMM share the fp64 pipe with it"}
+                                      if alone_ms and peak > 0 else None),
                      "share_of_step": round(gemm_ms / K / ms_per_step, 4),
                      "step_flops_frac_of_peak": round(flops_per_launch * gemm_launches / K / (ms_per_step / 1e3) / 1e12 / peak, 4)},
         "kernel_ms_per_step": {k: round(v[0] / K, 5) for k, v in prof.items() if v[1] > 0 or v[0] > 0},

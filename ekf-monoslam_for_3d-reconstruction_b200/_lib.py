@@ -87,6 +87,7 @@ SIGNATURES = {
     "ekf_set_profiling": (_i, [_vp, _i]),
     "ekf_get_profile": (_i, [_vp, _P(_abi.EkfProfile), _i]),
     "ekf_set_symmetric_downdate": (_i, [_vp, _i]),
+    "ekf_debug_time_downdate": (_i, [_vp, _i, _P(C.c_float)]),
     "ekf_build_info": (C.c_char_p, []),
 }
 

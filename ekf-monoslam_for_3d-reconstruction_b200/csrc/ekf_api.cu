@@ -1558,6 +1558,36 @@ int ekf_set_symmetric_downdate(ekf_handle* h, int on) {
   h->lower_only = on ? 1 : 0;
   return EKF_OK;
 }
+int ekf_debug_time_downdate(ekf_handle* h, int reps, float* ms_per_launch) {
+  if (!h || !ms_per_launch || reps < 1) return EKF_ERR_ARG;
+  EKF_CUDA_CHECK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  EKF_CUDA_CHECK(cudaStreamSynchronize(st));
+  // a small panel (entries 1e-6 x a row / column pattern) so that the covariance stays positive definite whatever it holds
+  std::vector<double> v((size_t)h->n * EKF_UB);
+  for (int i = 0; i < h->n; ++i)
+    for (int k = 0; k < EKF_UB; ++k) v[(size_t)i * EKF_UB + k] = 1e-9 * (double)(((i * 131 + k * 17) % 97) - 48);
+  EKF_CUDA_CHECK(cudaMemcpyAsync(h->Wbuf[1], v.data(), sizeof(double) * v.size(), cudaMemcpyHostToDevice, st));
+  cudaEvent_t a, b;
+  EKF_CUDA_CHECK(cudaEventCreate(&a)); EKF_CUDA_CHECK(cudaEventCreate(&b));
+  for (int i = 0; i < 2; ++i) {
+    const int rc = launch_gemm_nt_sub(st, h->Sigma, h->ld, h->Wbuf[1], EKF_UB, h->Wbuf[1], EKF_UB, h->n, h->n, EKF_UB, nullptr, h->lower_only, h->gemm_counters, &h->launches);
+    if (rc) return ekf_fail_cuda(h, (cudaError_t)rc, "downdate (timing)", __FILE__, __LINE__);
+  }
+  EKF_CUDA_CHECK(cudaEventRecord(a, st));
+  for (int i = 0; i < reps; ++i) {
+    const int rc = launch_gemm_nt_sub(st, h->Sigma, h->ld, h->Wbuf[1], EKF_UB, h->Wbuf[1], EKF_UB, h->n, h->n, EKF_UB, nullptr, h->lower_only, h->gemm_counters, &h->launches);
+    if (rc) return ekf_fail_cuda(h, (cudaError_t)rc, "downdate (timing)", __FILE__, __LINE__);
+  }
+  EKF_CUDA_CHECK(cudaEventRecord(b, st));
+  EKF_CUDA_CHECK(cudaStreamSynchronize(st));
+  float ms = 0;
+  EKF_CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  *ms_per_launch = ms / (float)reps;
+  h->cam_cache_ok = false;
+  return EKF_OK;
+}
 int ekf_get_full(ekf_handle* h, double* mu, double* sigma, int ld) {
   if (!h || !mu || (sigma && ld < h->n)) return EKF_ERR_ARG;
   EKF_CUDA_CHECK(cudaSetDevice(h->device));

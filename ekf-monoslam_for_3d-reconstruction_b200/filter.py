@@ -217,6 +217,12 @@ class VSlamFilter:
     def set_symmetric_downdate(self, on=True):
         self._ck(self.L.ekf_set_symmetric_downdate(self.h, int(bool(on))))
 
+    def debug_time_downdate(self, reps=20):
+        """Mean duration (ms) of one covariance-downdate launch timed ALONE (diagnostic; perturbs Sigma by rounding errors)."""
+        ms = C.c_float(0)
+        self._ck(self.L.ekf_debug_time_downdate(self.h, int(reps), C.byref(ms)))
+        return float(ms.value)
+
     def set_stream(self, cuda_stream_ptr):
         self._ck(self.L.ekf_set_stream(self.h, C.c_void_p(int(cuda_stream_ptr) if cuda_stream_ptr else 0)))
 

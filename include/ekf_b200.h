@@ -303,6 +303,11 @@ int ekf_set_profiling(ekf_handle* h, int on);
 int ekf_get_profile(ekf_handle* h, ekf_profile* out, int reset);
 /* 0 = full-square downdate; 1 = lower-triangle tiles + mirrored store (Sigma is symmetrised). */
 int ekf_set_symmetric_downdate(ekf_handle* h, int on);
+/* Diagnostic (bench.py's roofline object): launches the covariance downdate of one 128-row block `reps` times ALONE on the
+ * filter's stream — Sigma -= V V^T with the panel of the last update as V, negated on alternate launches so that Sigma ends where it
+ * started up to rounding — and returns the mean launch duration measured with CUDA events.  Changes Sigma by rounding errors: call
+ * it on a filter that is not used afterwards. */
+int ekf_debug_time_downdate(ekf_handle* h, int reps, float* ms_per_launch);
 
 /* Library version / build info: returns a static string naming the compiled arch. */
 const char* ekf_build_info(void);
