@@ -257,6 +257,10 @@ int ekf_create(const ekf_config* cfg, int feature_capacity, int device, ekf_hand
     // 0.764 against 0.786 ms per cfg2 step), 0 = factor-beside-downdate — see DESIGN.md section 4
     e = getenv("EKF_SCHED");
     h->sched = e ? atoi(e) : 1;
+    e = getenv("EKF_V_AFTER_DD");
+    h->v_after_dd = e ? atoi(e) : 0;
+    e = getenv("EKF_GATHER_HP");
+    h->gather_hp = e ? atoi(e) : 0;
     e = getenv("EKF_DD_RELEASE");
     h->dd_release = e ? atoi(e) : 2;
     e = getenv("EKF_S_LOOKAHEAD");
@@ -799,7 +803,11 @@ static int stacked_update_chain_short(ekf_handle* h, int cnt) {
   const int T = (h->n + 63) / 64, Ltiles = T * (T + 1) / 2;
   const bool gate = h->split_dd == 1;
   const bool split = h->split_dd && nblk > 2 && h->lower_only && T <= h->tile_T_cap && nblk <= h->tile_blk_cap && gemm_uses_square_tiles();
-  cudaStream_t sgat = (split && gate) ? h->gather_stream : sg;
+  // The gather of W'_{b+1} sits on the cycle S_b -> downdate_{b-1} -> gather -> S_{b+1}; on the downdate's own low-priority stream its CTAs
+  // queue behind those of the correction GEMM and of V (21 us instead of 11).  EKF_GATHER_HP=1 moves it to a high-priority stream behind
+  // an event of the downdate.
+  const bool ghp = h->gather_hp != 0;
+  cudaStream_t sgat = ((split && gate) || ghp) ? h->gather_stream : sg;
   const BlkTab bt{h->bt_H, h->bt_zmh, h->bt_pos, h->bt_nd};
   const bool pre = h->prelaunched;   // tables and the first two gathers are already under way
   h->prelaunched = false;
@@ -884,6 +892,10 @@ static int stacked_update_chain_short(ekf_handle* h, int cnt) {
                                           two ? h->tile_order + (size_t)(b + 1) * Ltiles : nullptr, Ltiles, h->tile_nhot + (b + 1), h->tile_counters + (b + 1));
         if (rc) return rc;
       }
+      if (ghp && !(two && gate) && b + 1 < nblk) {
+        cudaEventRecord(h->ev_A, sg);            // the downdate of block b-1 is complete
+        cudaStreamWaitEvent(sgat, h->ev_A, 0);
+      }
       if (b + 1 < nblk) {
         // cor[q] / raw[q] are free: Gx_b (before S_b, which released the downdate) and V_{b-1} (waited for above) have read them
         ProfScope ps(h, 3, sgat); TraceScope ts("gather", b + 1, sgat);
@@ -904,6 +916,9 @@ static int stacked_update_chain_short(ekf_handle* h, int cnt) {
     if (b > 0) cudaStreamWaitEvent(sv, h->ev_corr2[p], 0);
     if (b > 1) cudaStreamWaitEvent(sv, h->ev_dd[p], 0);
     if (sla && b > 1) cudaStreamWaitEvent(sv, h->ev_Sg2[p], 0);   // G2_b has read V_{b-2} out of the panel V_b is about to overwrite
+    // EKF_V_AFTER_DD=1: V_b is not needed before the downdate of block b (released by S_{b+1}); holding it back until the downdate of
+    // block b-1 is through keeps its 95 CTAs out of that downdate's last wave
+    if (h->v_after_dd && b > 0) cudaStreamWaitEvent(sv, h->ev_dd[q], 0);
     { ProfScope ps(h, 5, sv); TraceScope ts("V", b, sv);
       launch_blk_V(sv, cor[p], 0, h->n, Ls[p], Ds[p], ys[p], dl[b % 3], &h->launches, Vb[p], dl[(b + 2) % 3] /* delta_{b-1} */); }
     cudaEventRecord(h->ev_V[b % 3], sv);

@@ -74,6 +74,8 @@ struct ekf_handle {
   // S look-ahead of the chain-short schedule (EKF_S_LOOKAHEAD): G2 = H_b V_{b-2}, -G2 G2^T per block parity, events
   double *G2buf = nullptr, *Sg2buf[2] = {nullptr, nullptr};
   cudaEvent_t ev_mini[2] = {nullptr, nullptr}, ev_Sg2[2] = {nullptr, nullptr};
+  int v_after_dd = 0;      // chain-short: V_b waits for the downdate of block b-1 (EKF_V_AFTER_DD)
+  int gather_hp = 0;       // chain-short: the gather of W'_{b+1} on a high-priority stream (EKF_GATHER_HP)
   int s_lookahead = 0;
   int dd_release = 2;      // EKF_SCHED=3 only (EKF_DD_RELEASE): which kernel of block b releases the downdate of block b-1
   bool prelaunched = false;   // block tables + first two gathers were started before the n_li read-back (chain_short_prelaunch)
