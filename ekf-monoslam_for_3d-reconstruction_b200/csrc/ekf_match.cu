@@ -30,20 +30,11 @@
 
 #include "ekf_kernels.h"
 #include "ekf_math.cuh"
+#include "ekf_match_tile.cuh"
 
 #define MATCH_THREADS 256
 #define MATCH_MAX_W 31   // largest template side
 #define MATCH_LIST 128   // guard-band list capacity
-
-struct MatchJob {
-  const uint8_t* frame;  // frame base
-  int fw, fh, fstride;
-  const uint8_t* tmpl;   // w*w template
-  double hu, hv;         // Patch::h
-  double S[4];           // 2x2 block of St
-  const CUtensorMap* tmap;  // tensor map of the frame stack (null: stage with ordinary loads)
-  int frame_index;       // z coordinate in that stack
-};
 
 struct MatchResult {
   float best;  // max NCC (-1 if no candidate)
@@ -167,50 +158,6 @@ __device__ __forceinline__ void match_dots4(const uint8_t* win0, int wsb, const 
       lo = hi;
     }
   }
-}
-
-// Scalar setup of Patch::findMatch (Patch.cpp:218-246), replicated per thread: the candidate range of the reference's two loops,
-// the ellipse coefficients, and that range clipped to pixels that pass the in-image test.
-struct MatchGeom {
-  int uc, vc, i0, j0, nv, ilo, jlo, cw, ch;
-  float x_2_coeff, y_2_coeff, yx_coeff, sigma_2;
-  bool any;
-};
-__device__ __forceinline__ MatchGeom match_geometry(const MatchJob& jb, int w, float sigma_size, float clampv, int max_grid) {
-  MatchGeom G;
-  const int half = w / 2;
-  G.uc = (int)jb.hu;
-  G.vc = (int)jb.hv;
-  double invS[4];
-  d_inv2_pplu(jb.S, invS);
-  G.x_2_coeff = (float)invS[0];
-  G.y_2_coeff = (float)invS[3];
-  G.yx_coeff = (float)(2 * invS[2]);
-  G.sigma_2 = sigma_size * sigma_size;
-  float delta_u = (float)(sigma_size * sqrt(jb.S[0]));
-  float delta_v = (float)(sigma_size * sqrt(jb.S[3]));
-  if (delta_u > clampv) delta_u = clampv;
-  if (delta_v > clampv) delta_v = clampv;
-  // for (int i = uc - delta_u; i <= uc + delta_u; i++): float arithmetic, truncation toward zero
-  G.i0 = (int)((float)G.uc - delta_u);
-  G.j0 = (int)((float)G.vc - delta_v);
-  const float iu_hi = (float)G.uc + delta_u, jv_hi = (float)G.vc + delta_v;
-  const int i1 = (int)floorf(iu_hi), j1 = (int)floorf(jv_hi);
-  // NaN covariance: the loops do not run in the reference (comparisons are false)
-  const bool finite_ok = (iu_hi == iu_hi) && (jv_hi == jv_hi) && (delta_u == delta_u) && (delta_v == delta_v);
-  G.nv = finite_ok ? (j1 - G.j0 + 1) : 0;
-  if (G.nv < 0) G.nv = 0;
-  // clip the candidate range to pixels that pass the in-image test (Patch.cpp:246) so the staged
-  // window never leaves the frame; scan order and keys are unaffected.
-  G.ilo = max(G.i0, half + 1);
-  G.jlo = max(G.j0, half + 1);
-  const int ihi = min(i1, jb.fw - half - 1), jhi = min(j1, jb.fh - half - 1);
-  G.cw = finite_ok ? ihi - G.ilo + 1 : 0;
-  G.ch = finite_ok ? jhi - G.jlo + 1 : 0;  // valid candidate grid
-  if (G.cw > max_grid) G.cw = max_grid;  // cannot happen for delta <= clamp; keeps smem in bounds
-  if (G.ch > max_grid) G.ch = max_grid;
-  G.any = G.cw > 0 && G.ch > 0;
-  return G;
 }
 
 // Core search for one feature by one CTA.  All threads must call.
@@ -763,6 +710,210 @@ __device__ bool match_one_warp(const MatchJob& jb, int w, float sigma_size, floa
   return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Warp-per-feature path for FULL windows (candidate grid up to 41 x 41 at the reference's +-20 px clamp), template side W <= 12
+// fixed at compile time: the register-tiled scoring core of ekf_match_tile.cuh.  Only the u8 window (54 rows x 76 bytes), the
+// packed template and the band list sit in shared memory (4.6 KB per warp); the lanes take 4 x 4-candidate tiles round-robin,
+// rank them by an exact-integer float score, and only the band candidates see double precision and the reference's exact pass.
+// No block barrier anywhere.  Returns false (nothing written, nothing decided) when the feature needs the CTA matcher.
+// ------------------------------------------------------------------------------------------------
+#define MW2_WARPS 8
+template <int W>
+struct MatchWarp2Smem {
+  unsigned win[(MT_MAXGRID + W - 1 + MT_R - 1) * MT_WSW];
+  unsigned tpk[W * ((W + 3) / 4)];
+  unsigned char tb[((W * W + 15) & ~15) + 16];
+  uint4 list[MT_LIST];   // {candidate index, Stp, P, PP}
+  int cnt;
+};
+
+template <int W>
+__device__ bool match_one_warp2(const MatchJob& jb, float sigma_size, float clampv, MatchWarp2Smem<W>& sm, MatchResult& res) {
+  constexpr int TW = (W + 3) / 4, W2 = W * W;
+  const int lane = threadIdx.x & 31;
+  const int half = W / 2;
+  if (!(clampv <= 20.0f)) return false;
+  const MatchGeom G = match_geometry(jb, W, sigma_size, clampv, MT_MAXGRID);
+  res.best = -1.0f; res.bi = 0; res.bj = 0;
+  if (!G.any) return true;
+  const int cw = G.cw, ch = G.ch, ww = cw + W - 1, wh = ch + W - 1;
+  // --- template: packed words (zero padded), bytes, T = sum t, TT = sum t^2 ---
+  int T = 0, TT = 0;
+  for (int e = lane; e < W * TW; e += 32) {
+    const int r = e / TW, k4 = (e - r * TW) * 4;
+    unsigned word = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (k4 + c < W) {
+        const unsigned v = jb.tmpl[r * W + k4 + c];
+        word |= v << (8 * c);
+        T += (int)v; TT += (int)(v * v);
+      }
+    sm.tpk[e] = word;
+  }
+  for (int e = lane; e < W2; e += 32) sm.tb[e] = jb.tmpl[e];
+  for (int o = 16; o > 0; o >>= 1) { T += __shfl_xor_sync(0xffffffffu, T, o); TT += __shfl_xor_sync(0xffffffffu, TT, o); }
+  // --- window: MT_NW words per row, columns past ww zero, and MT_R - 1 zero rows below (the last tile row reads them) ---
+  {
+    const int x0 = G.ilo - half, y0 = G.jlo - half;
+    const int nrows = wh + MT_R - 1;
+    if ((((size_t)jb.frame | (size_t)jb.fstride) & 3) == 0) {
+      const int sh = x0 & 3, xa = x0 - sh;
+      for (int e = lane; e < nrows * MT_NW; e += 32) {
+        const int yy = e / MT_NW, k = e - yy * MT_NW;
+        unsigned v = 0;
+        if (yy < wh && 4 * k < ww) {
+          const unsigned* srcw = reinterpret_cast<const unsigned*>(jb.frame + (size_t)(y0 + yy) * jb.fstride + xa);
+          const int last = min(4 * k + 3, ww - 1);          // last window column this word needs
+          const unsigned lo = srcw[k];
+          const unsigned hi = (sh > 0 && last + sh >= 4 * k + 4) ? srcw[k + 1] : 0u;
+          v = __funnelshift_r(lo, hi, 8 * sh);
+          const int rem = ww - 4 * k;
+          if (rem < 4) v &= (1u << (8 * rem)) - 1u;
+        }
+        sm.win[yy * MT_WSW + k] = v;
+      }
+    } else {
+      uint8_t* winb = reinterpret_cast<uint8_t*>(sm.win);
+      for (int e = lane; e < nrows * MT_NW * 4; e += 32) {
+        const int yy = e / (MT_NW * 4), xx = e - yy * (MT_NW * 4);
+        winb[yy * MT_WSW * 4 + xx] = (yy < wh && xx < ww) ? jb.frame[(size_t)(y0 + yy) * jb.fstride + x0 + xx] : (uint8_t)0;
+      }
+    }
+  }
+  __syncwarp();
+  const double dn = (double)W2;
+  const double m1 = __ddiv_rn((double)T, dn);
+  const double d1 = dn * (double)TT - (double)T * (double)T;   // exact (< 2^53)
+  if (!(d1 > 0.0)) return true;                                 // flat template: 0/0 in the reference for every candidate
+  const double rd1 = rsqrt(d1);
+  // --- ranking pass: tiles round-robin over the lanes ---
+  MTTop top;
+  top.reset();
+  {
+    unsigned Treg[W * TW];
+#pragma unroll
+    for (int e = 0; e < W * TW; ++e) Treg[e] = sm.tpk[e];
+    MTGate g;
+    g.x2c = G.x_2_coeff; g.y2c = G.y_2_coeff; g.yxc = G.yx_coeff; g.sigma2 = G.sigma_2;
+    g.du0 = G.ilo - G.uc; g.dv0 = G.jlo - G.vc; g.cw = cw; g.ch = ch; g.T = T; g.rd1f = (float)rd1;
+    const int ntx = (cw + 3) >> 2, nty = (ch + MT_R - 1) / MT_R;
+    int ty = lane / ntx, tx = lane - ty * ntx;
+    const int dty = 32 / ntx, dtx = 32 - dty * ntx;
+    while (ty < nty) {
+      mt_tile<W>(sm.win, tx, ty, Treg, g, top);
+      tx += dtx; ty += dty;
+      if (tx >= ntx) { tx -= ntx; ++ty; }
+    }
+  }
+  float F = top.a0;
+  for (int o = 16; o > 0; o >>= 1) F = fmaxf(F, __shfl_xor_sync(0xffffffffu, F, o));
+  if (!(F > -INFINITY)) return true;                            // no candidate inside the ellipse with a textured window
+  const float thrF = F - MT_BAND;
+  const bool crowded = top.a2 >= thrF;                          // a lane may have dropped a band candidate
+  if (__any_sync(0xffffffffu, crowded)) return false;
+  if (top.a0 >= thrF) {
+    const int slot = atomicAdd(&sm.cnt, 1);
+    if (slot < MT_LIST) sm.list[slot] = make_uint4((unsigned)top.i0, top.s0, (unsigned)top.p0, (unsigned)top.q0);
+  }
+  if (top.a1 >= thrF) {
+    const int slot = atomicAdd(&sm.cnt, 1);
+    if (slot < MT_LIST) sm.list[slot] = make_uint4((unsigned)top.i1, top.s1, (unsigned)top.p1, (unsigned)top.q1);
+  }
+  __syncwarp();
+  const int nlist = sm.cnt;
+  if (nlist > MT_LIST) return false;
+  // --- ncc* in double of the band candidates, its maximum, the guard band (as match_one) ---
+  const double kNone = -1.0e300;
+  double v = kNone;
+  if (lane < nlist) {
+    const uint4 c = sm.list[lane];
+    v = mt_ncc_star(W2, c.y, (int)c.z, (int)c.w, T, rd1);
+  }
+  double Mstar = v;
+  for (int o = 16; o > 0; o >>= 1) Mstar = fmax(Mstar, __shfl_xor_sync(0xffffffffu, Mstar, o));
+  const float fm = fabsf((float)Mstar);
+  const double ulp = (double)(nextafterf(fm, 3.0e38f) - fm);
+  const double thr = Mstar - (2.0 * ulp + 4.0e-12);
+  // --- exact pass: one 4-lane group per guard-band candidate ---
+  float best = -1.0f;
+  int bestkey = 0x7fffffff;
+  const uint8_t* winb = reinterpret_cast<const uint8_t*>(sm.win);
+  const int role = lane & 3, gbase = lane & ~3;
+  const unsigned gmask = 0xfu << gbase;
+  for (int q0 = 0; q0 < nlist; q0 += 8) {
+    const int q = q0 + (lane >> 2);
+    if (q >= nlist) continue;                           // uniform inside a 4-lane group
+    const uint4 c = sm.list[q];
+    if (!(mt_ncc_star(W2, c.y, (int)c.z, (int)c.w, T, rd1) >= thr)) continue;   // same value in the four lanes
+    const int jv = (int)c.x / cw, iu = (int)c.x - jv * cw;
+    const float s1 = match_exact_score4_tb(sm.tb, m1, winb, MT_WSW * 4, jv * MT_WSW * 4 + iu, W, (int)c.z, role, gmask, gbase);
+    const int key = (G.ilo + iu - G.i0) * G.nv + (G.jlo + jv - G.j0);
+    if (role == 0 && (s1 > best || (s1 == best && key < bestkey))) { best = s1; bestkey = key; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int ok = __shfl_xor_sync(0xffffffffu, bestkey, o);
+    if (ob > best || (ob == best && ok < bestkey)) { best = ob; bestkey = ok; }
+  }
+  res.best = best;
+  if (bestkey != 0x7fffffff && G.nv > 0) {
+    res.bi = G.i0 + bestkey / G.nv;
+    res.bj = G.j0 + bestkey % G.nv;
+  }
+  return true;
+}
+
+// write-back of one matched (or rejected) feature by its warp: Patch.cpp:278-289; the new template comes from the frame
+__device__ __forceinline__ void match_warp_commit(FeatTab ft, int f, FrameView fr, const DevCfg& cfg, const MatchResult& r) {
+  const int lane = threadIdx.x & 31, w = cfg.window, w2 = w * w;
+  const bool accept = !(r.best < cfg.ncc_threshold);  // Patch.cpp:278
+  if (accept) {   // matching_patch <- matched ROI (Patch.cpp:285)
+    const int x0 = r.bi - w / 2, y0 = r.bj - w / 2;
+    for (int e = lane; e < w2; e += 32)
+      ft.mpatch[(size_t)f * cfg.tstride + e] = fr.px[(size_t)(y0 + e / w) * fr.stride + x0 + (e % w)];
+  }
+  if (lane == 0) {
+    ft.n_tot[f] += 1;  // Patch.cpp:218
+    ft.last_ncc[f] = r.best;
+    if (!accept) {
+      ft.center[2 * f] = -1.0f; ft.center[2 * f + 1] = -1.0f;
+      ft.innov[f] = 0; ft.li[f] = 0; ft.hi[f] = 0;
+    } else {
+      ft.center[2 * f] = (float)r.bi; ft.center[2 * f + 1] = (float)r.bj;
+      ft.z[2 * f] = (double)(float)r.bi; ft.z[2 * f + 1] = (double)(float)r.bj;
+    }
+  }
+}
+
+// Batched filters, pass 1 with the full-window warp matcher (template side 11): one warp per (filter, feature)
+__global__ void __launch_bounds__(MW2_WARPS * 32, 2) k_match_filter_batch_warp2(FeatTab base, int Ncap, const int* __restrict__ Nper, int B,
+                                                                                FrameView fr, DevCfg cfg, int* __restrict__ defer_list,
+                                                                                int* __restrict__ defer_cnt) {
+  __shared__ MatchWarp2Smem<11> wsm[MW2_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long pair = (long long)blockIdx.x * MW2_WARPS + warp;
+  if (pair >= (long long)B * Ncap) return;
+  const int b = (int)(pair / Ncap), f = (int)(pair - (long long)b * Ncap);
+  const FeatTab ft = feattab_slice(base, b, Ncap, cfg.tstride);
+  if (f >= Nper[b] || !ft.innov[f]) return;
+  MatchJob jb;
+  jb.tmap = nullptr; jb.frame_index = 0;
+  jb.frame = fr.px; jb.fw = fr.w; jb.fh = fr.h; jb.fstride = fr.stride;
+  jb.tmpl = ft.mpatch + (size_t)f * cfg.tstride;
+  jb.hu = ft.h[2 * f]; jb.hv = ft.h[2 * f + 1];
+  for (int c = 0; c < 4; ++c) jb.S[c] = ft.S2[4 * f + c];
+  if (lane == 0) wsm[warp].cnt = 0;
+  __syncwarp();
+  MatchResult r;
+  if (!match_one_warp2<11>(jb, cfg.sigma_size_f, cfg.search_clamp, wsm[warp], r)) {
+    if (lane == 0) defer_list[atomicAdd(defer_cnt, 1)] = (int)pair;
+    return;
+  }
+  __syncwarp();
+  match_warp_commit(ft, f, fr, cfg, r);
+}
+
 // Batched filters, pass 1: one warp per (filter, feature); features that do not fit go to defer_list.
 __global__ void __launch_bounds__(MW_WARPS * 32) k_match_filter_batch_warp(FeatTab base, int Ncap, const int* __restrict__ Nper, int B,
                                                                            FrameView fr, DevCfg cfg, int* __restrict__ defer_list,
@@ -852,6 +1003,71 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_batch(const uint8_t* __
   }
 }
 
+// Stateless batch with the full-window warp matcher (template side 11): one warp per (frame, feature).  A feature that needs
+// the CTA matcher is MARKED in out_uv and worked off by the persistent grid of k_match_batch_marked.
+#define MATCH_MARK ((int32_t)0x80000000)
+__global__ void __launch_bounds__(MW2_WARPS * 32, 2) k_match_batch_warp2(const uint8_t* __restrict__ frames, int width, int height, int stride,
+                                                                         const uint8_t* __restrict__ templates, int fpf,
+                                                                         const double* __restrict__ hh, const double* __restrict__ Sm,
+                                                                         float sigma_size, float thr, float clampv,
+                                                                         int32_t* __restrict__ out_uv, float* __restrict__ out_score, int total) {
+  __shared__ MatchWarp2Smem<11> wsm[MW2_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * MW2_WARPS + warp;
+  if (idx >= total) return;
+  MatchJob jb;
+  jb.tmap = nullptr; jb.frame_index = idx / fpf;
+  jb.frame = frames + (size_t)(idx / fpf) * height * stride;
+  jb.fw = width; jb.fh = height; jb.fstride = stride;
+  jb.tmpl = templates + (size_t)idx * 121;
+  jb.hu = hh[2 * idx]; jb.hv = hh[2 * idx + 1];
+  for (int c = 0; c < 4; ++c) jb.S[c] = Sm[4 * idx + c];
+  if (lane == 0) wsm[warp].cnt = 0;
+  __syncwarp();
+  MatchResult r;
+  const bool done = match_one_warp2<11>(jb, sigma_size, clampv, wsm[warp], r);
+  if (lane == 0) {
+    if (!done) {
+      out_uv[2 * idx] = MATCH_MARK;
+    } else {
+      const bool accept = !(r.best < thr);
+      out_uv[2 * idx] = accept ? r.bi : -1;
+      out_uv[2 * idx + 1] = accept ? r.bj : -1;
+      out_score[idx] = r.best;
+    }
+  }
+}
+__global__ void __launch_bounds__(MATCH_THREADS) k_match_batch_marked(const uint8_t* __restrict__ frames, int width, int height,
+                                                                      int stride, const uint8_t* __restrict__ templates, int fpf,
+                                                                      int w, const double* __restrict__ hh, const double* __restrict__ Sm,
+                                                                      float sigma_size, float thr, float clampv,
+                                                                      int32_t* __restrict__ out_uv, float* __restrict__ out_score, int total,
+                                                                      const __grid_constant__ CUtensorMap tmap, int use_tma) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned phase = 0;
+  bool first = true;
+  for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
+    if (out_uv[2 * idx] != MATCH_MARK) continue;   // uniform over the CTA
+    MatchJob jb;
+    jb.tmap = use_tma ? &tmap : nullptr; jb.frame_index = idx / fpf;
+    jb.frame = frames + (size_t)(idx / fpf) * height * stride;
+    jb.fw = width; jb.fh = height; jb.fstride = stride;
+    jb.tmpl = templates + (size_t)idx * w * w;
+    jb.hu = hh[2 * idx]; jb.hv = hh[2 * idx + 1];
+    for (int c = 0; c < 4; ++c) jb.S[c] = Sm[4 * idx + c];
+    const MatchResult r = match_one(jb, w, sigma_size, clampv, smem_raw, &phase, first);
+    first = false;
+    __syncthreads();   // every thread has read the mark before thread 0 overwrites it
+    if (threadIdx.x == 0) {
+      const bool accept = !(r.best < thr);
+      out_uv[2 * idx] = accept ? r.bi : -1;
+      out_uv[2 * idx + 1] = accept ? r.bj : -1;
+      out_score[idx] = r.best;
+    }
+    __syncthreads();
+  }
+}
+
 void launch_match_filter(cudaStream_t st, FeatTab ft, int N, FrameView fr, const DevCfg& cfg, const EkfTensorMap* tmap, long long* launches) {
   if (N <= 0) return;
   static PerDeviceOnce once;   // opt in to the largest supported window once per device
@@ -876,9 +1092,15 @@ void launch_match_filter_batch(cudaStream_t st, FeatTab base, int Ncap, const in
   // pass 1: a warp per (filter, feature) for small windows; pass 2: a persistent grid of CTAs for the deferred rest
   cudaMemsetAsync(defer_cnt, 0, sizeof(int), st);
   const long long pairs = (long long)B * Ncap;
-  static const int warp_path = [] { const char* e = getenv("EKF_MATCH_WARP"); return e ? atoi(e) : 1; }();   // 0: every feature takes the CTA matcher (A/B timing, tests)
-  k_match_filter_batch_warp<<<(unsigned)((pairs + MW_WARPS - 1) / MW_WARPS), MW_WARPS * 32, 0, st>>>(base, Ncap, Nper, B, fr, cfg, defer_list, defer_cnt,
-                                                                                                     warp_path);
+  // EKF_MATCH_WARP: 2 (default) full-window warp matcher where the template side allows it, 1 the small-window warp matcher only,
+  // 0 every feature takes the CTA matcher (A/B timing, tests)
+  static const int warp_path = [] { const char* e = getenv("EKF_MATCH_WARP"); return e ? atoi(e) : 2; }();
+  if (warp_path >= 2 && cfg.window == 11 && cfg.search_clamp <= 20.0f)
+    k_match_filter_batch_warp2<<<(unsigned)((pairs + MW2_WARPS - 1) / MW2_WARPS), MW2_WARPS * 32, 0, st>>>(base, Ncap, Nper, B, fr, cfg, defer_list,
+                                                                                                           defer_cnt);
+  else
+    k_match_filter_batch_warp<<<(unsigned)((pairs + MW_WARPS - 1) / MW_WARPS), MW_WARPS * 32, 0, st>>>(base, Ncap, Nper, B, fr, cfg, defer_list, defer_cnt,
+                                                                                                       warp_path);
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int per_sm = 4;   // persistent grid: as many CTAs as are resident at this shared-memory footprint
@@ -902,6 +1124,25 @@ int launch_match_batch(cudaStream_t st, const uint8_t* frames, int n_frames, int
                                                    (int)match_smem_bytes(MATCH_MAX_W, 20.0f)); }) != cudaSuccess) return -1;
   EkfTensorMap tm;
   match_make_tensor_map(&tm, frames, width, height, stride, n_frames, w, (int)clampv);
+  static const int warp_path = [] { const char* e = getenv("EKF_MATCH_WARP"); return e ? atoi(e) : 2; }();
+  if (warp_path >= 2 && w == 11) {
+    // a warp per feature; what it cannot decide is marked and taken by a persistent grid of CTA matchers
+    static PerDeviceOnce once2;
+    if (once2.ensure([] { return cudaFuncSetAttribute(k_match_batch_marked, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      (int)match_smem_bytes(MATCH_MAX_W, 20.0f)); }) != cudaSuccess) return -1;
+    k_match_batch_warp2<<<(total + MW2_WARPS - 1) / MW2_WARPS, MW2_WARPS * 32, 0, st>>>(frames, width, height, stride, templates, fpf, h, S,
+                                                                                       sigma_size, thr, clampv, out_uv, out_score, total);
+    int dev = 0, sms = 148, per_sm = 4;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_match_batch_marked, MATCH_THREADS, smem) != cudaSuccess || per_sm < 1) {
+      cudaGetLastError();
+      per_sm = 4;
+    }
+    const int grid = total < sms * per_sm ? total : sms * per_sm;
+    k_match_batch_marked<<<grid, MATCH_THREADS, smem, st>>>(frames, width, height, stride, templates, fpf, w, h, S, sigma_size, thr,
+                                                           clampv, out_uv, out_score, total, as_cu(tm), tm.ok);
+    return 0;
+  }
   k_match_batch<<<total, MATCH_THREADS, smem, st>>>(frames, width, height, stride, templates, fpf, w, h, S, sigma_size, thr,
                                                    clampv, out_uv, out_score, total, as_cu(tm), tm.ok);
   return 0;

@@ -280,7 +280,7 @@ __device__ inline void d_jac_f_hW(const double hW[3], double Jt[3], double Jp[3]
   Jp[2] = hz * hy / sqrt(normal) / normal2;
 }
 // Dynamic 2x2 inverse() = partial-pivot LU solve against I (see oracle inverse_pplu; V:995, P:223)
-__device__ __forceinline__ void d_inv2_pplu(const double A[4], double X[4]) {
+__host__ __device__ __forceinline__ void d_inv2_pplu(const double A[4], double X[4]) {
   double a00 = A[0], a01 = A[1], a10 = A[2], a11 = A[3];
   int swapped = 0;
   if (fabs(a10) > fabs(a00)) {

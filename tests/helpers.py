@@ -109,3 +109,28 @@ def numpy_stacked_update(mu, S, feats, sel, sigma_pixel_2, chunk=256):
     S1[3:7, :] = J @ S1[3:7, :]
     S1[:, 3:7] = S1[:, 3:7] @ J.T
     return mu1, S1
+
+
+def near_tie_scene():
+    """Four 320 x 240 frames made to produce near-ties in the NCC search — a smooth gradient, an exactly periodic texture (many
+    candidates with identical sums), a coarse 4-level block image and a saturated patch (flat windows) — with 48 templates cut
+    from each at random positions.  Returns frames, templates (F*M, 11, 11), h (F*M, 2), S (F*M, 4), F, M."""
+    rng = np.random.default_rng(11)
+    Wd, Ht, w, M = 320, 240, 11, 48
+    yy, xx = np.mgrid[0:Ht, 0:Wd]
+    smooth = (127 + 60 * np.sin(xx / 23.0) + 50 * np.cos(yy / 17.0) + rng.normal(scale=1.5, size=(Ht, Wd))).clip(0, 255)
+    periodic = (((xx % 8) * 16 + (yy % 8) * 12) % 256).astype(np.float64)
+    coarse = ((rng.integers(0, 4, size=(Ht // 4 + 1, Wd // 4 + 1)).repeat(4, 0).repeat(4, 1)[:Ht, :Wd]) * 64).astype(np.float64)
+    sat = smooth.copy(); sat[60:140, 80:220] = 255
+    frames = np.stack([smooth, periodic, coarse, sat]).astype(np.uint8)
+    F = frames.shape[0]
+    half = w // 2
+    u = rng.integers(40, Wd - 40, size=(F, M)); v = rng.integers(40, Ht - 40, size=(F, M))
+    templates = np.zeros((F, M, w, w), dtype=np.uint8)
+    for f in range(F):
+        for i in range(M):
+            templates[f, i] = frames[f, v[f, i] - half:v[f, i] + half + 1, u[f, i] - half:u[f, i] + half + 1]
+    h = np.stack([u, v], axis=-1).astype(np.float64) + rng.normal(scale=2.0, size=(F, M, 2))
+    S = np.zeros((F, M, 4)); S[..., 0] = 40.0; S[..., 3] = 40.0
+    templates = templates.reshape(F * M, w, w); h = h.reshape(F * M, 2); S = S.reshape(F * M, 4)
+    return frames, templates, h, S, F, M

@@ -109,8 +109,7 @@ def test_batch_capacity_and_errors(gpu_pkg):
 
 def test_small_windows_take_the_warp_matcher(gpu_pkg, orc):
     """Tight process noise and a sharp depth prior shrink the 3-sigma search ellipses to a few pixels: every feature fits the
-    warp-per-feature matcher (candidate grid <= 16 x 16) and none is deferred to the CTA matcher; results stay bit-exact
-    against the oracle.  With the default noise the same scene defers everything (windows clamp at 41 x 41)."""
+    warp-per-feature matchers and none is deferred to the CTA matcher; results stay bit-exact against the oracle."""
     small = dict(sigma_vx=1e-4, sigma_vy=1e-4, sigma_vz=1e-4, sigma_wx=1e-4, sigma_wy=1e-4, sigma_wz=1e-4, sigma_rho_0=1e-5, sigma_size=2)
     sc = gpu_pkg.synth.Scene(n_features=24, n_frames=5, seed=411, speed=0.05, omega=0.01, accel_sigma=1e-4)
     g, batch, oracles = _ensemble(gpu_pkg, orc, sc, 4, seed=9, perturb=1e-5, **small)
@@ -127,7 +126,12 @@ def test_small_windows_take_the_warp_matcher(gpu_pkg, orc):
         _check(batch, oracles, f"small windows frame {t}")
     mu, st = batch.camera_states()
     assert (st[:, 1] > 0).all(), "features must actually match in this scene"
-    # control: the default noise model opens the windows to the 20 px clamp and everything is deferred
-    g2, batch2, _ = _ensemble(gpu_pkg, orc, sc, 2, seed=9, perturb=1e-5)
-    batch2.captureNewFrame(sc.frame(1), sc.stamps[1]); batch2.step(sc.picks(1, 24))
-    assert batch2.last_match_deferred() > 0
+    # the default noise model opens the windows to the 20 px clamp (41 x 41 candidates): the full-window tile matcher
+    # (k_match_filter_batch_warp2) decides those as well; only near-ties would go to the CTA matcher, and noise frames have none
+    g2, batch2, oracles2 = _ensemble(gpu_pkg, orc, sc, 2, seed=9, perturb=1e-5)
+    img = sc.frame(1); picks = sc.picks(1, 24)
+    batch2.captureNewFrame(img, sc.stamps[1]); batch2.step(picks)
+    assert batch2.last_match_deferred() == 0
+    for o in oracles2:
+        o.captureNewFrame(img, sc.stamps[1]); o.predict(); o.update(picks)
+    _check(batch2, oracles2, "full windows, tile matcher")

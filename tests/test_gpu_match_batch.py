@@ -3,6 +3,8 @@ Match coordinates, accept/reject and the float NCC score must be bit-exact."""
 import numpy as np
 import pytest
 
+from helpers import near_tie_scene
+
 pytestmark = pytest.mark.gpu
 
 
@@ -55,5 +57,26 @@ def test_match_batch_edges(gpu_pkg, orc):
     d2 = dict(frames=d["frames"], templates=tm, h=h, S=S)
     uv_o, sc_o = orc.match_batch(d2["frames"], tm, h, S, sigma_size=3.0)
     uv_g, sc_g = _run_gpu(gpu_pkg, d2, 1, M, W, H, w, 3.0)
+    assert np.array_equal(uv_g, uv_o)
+    assert np.array_equal(sc_g.view(np.uint32), sc_o.view(np.uint32))
+
+
+def test_match_batch_near_ties_bit_exact(gpu_pkg, orc):
+    """Smooth, periodic, coarse and saturated frames: the full-window tile matcher (template side 11) decides what it can and
+    marks exact ties / crowded bands for the CTA matcher; both together must give the reference's answer on every feature."""
+    frames, templates, h, S, F, M = near_tie_scene()
+    uv_o, sc_o = orc.match_batch(frames, templates, h, S, sigma_size=3.0)
+    d = dict(frames=frames, templates=templates, h=h, S=S)
+    uv_g, sc_g = _run_gpu(gpu_pkg, d, F, M, frames.shape[2], frames.shape[1], 11, 3.0)
+    assert np.array_equal(uv_g, uv_o)
+    assert np.array_equal(sc_g.view(np.uint32), sc_o.view(np.uint32)), "float NCC scores differ bitwise"
+    assert (uv_o[:M, 0] >= 0).mean() > 0.9
+
+
+def test_match_batch_unaligned_frames(gpu_pkg, orc):
+    """Frame width 323 (row stride not a multiple of 4): the tile matcher stages the window with byte loads."""
+    d = gpu_pkg.synth.match_batch_inputs(n_frames=2, features_per_frame=20, width=323, height=241, window=11, seed=91, s_diag=40.0)
+    uv_o, sc_o = orc.match_batch(d["frames"], d["templates"], d["h"], d["S"], sigma_size=3.0)
+    uv_g, sc_g = _run_gpu(gpu_pkg, d, 2, 20, 323, 241, 11, 3.0)
     assert np.array_equal(uv_g, uv_o)
     assert np.array_equal(sc_g.view(np.uint32), sc_o.view(np.uint32))
