@@ -483,9 +483,13 @@ void match_make_tensor_map(EkfTensorMap* out, const uint8_t* frames, int width, 
 }
 static const CUtensorMap& as_cu(const EkfTensorMap& m) { return *reinterpret_cast<const CUtensorMap*>(m.opaque); }
 
+template <int W, int R>
+__device__ bool match_one_tile_cta(const MatchJob& jb, float sigma_size, float clampv, unsigned char* smem_raw, MatchResult& res);   // below
+
 // Filter-attached matcher: the loop V:870-880 with one CTA per feature.
 __device__ __forceinline__ void match_filter_feature(FeatTab ft, int f, FrameView fr, const DevCfg& cfg, unsigned char* smem_raw,
-                                                     const CUtensorMap* tmap, unsigned* phase_io = nullptr, bool init_bar = true) {
+                                                     const CUtensorMap* tmap, unsigned* phase_io = nullptr, bool init_bar = true,
+                                                     bool try_tile = false) {
   const int w = cfg.window, w2 = w * w;
   MatchJob jb;
   jb.tmap = tmap; jb.frame_index = 0;
@@ -493,7 +497,12 @@ __device__ __forceinline__ void match_filter_feature(FeatTab ft, int f, FrameVie
   jb.tmpl = ft.mpatch + (size_t)f * cfg.tstride;
   jb.hu = ft.h[2 * f]; jb.hv = ft.h[2 * f + 1];
   for (int c = 0; c < 4; ++c) jb.S[c] = ft.S2[4 * f + c];
-  const MatchResult r = match_one(jb, w, cfg.sigma_size_f, cfg.search_clamp, smem_raw, phase_io, init_bar);
+  MatchResult r;
+  // template side 11: the tile matcher first; near-ties (uniform verdict) fall through to match_one in the same CTA
+  if (!(try_tile && w == 11 && match_one_tile_cta<11, 2>(jb, cfg.sigma_size_f, cfg.search_clamp, smem_raw, r))) {
+    if (try_tile) __syncthreads();   // the tile matcher's shared memory is re-used from here on
+    r = match_one(jb, w, cfg.sigma_size_f, cfg.search_clamp, smem_raw, phase_io, init_bar);
+  }
   __syncthreads();
   const bool accept = !(r.best < cfg.ncc_threshold);  // Patch.cpp:278
   if (accept) {
@@ -514,12 +523,12 @@ __device__ __forceinline__ void match_filter_feature(FeatTab ft, int f, FrameVie
     }
   }
 }
-__global__ void __launch_bounds__(MATCH_THREADS) k_match_filter(FeatTab ft, int N, FrameView fr, DevCfg cfg,
-                                                                const __grid_constant__ CUtensorMap tmap, int use_tma) {
+__global__ void __launch_bounds__(MATCH_THREADS, 4) k_match_filter(FeatTab ft, int N, FrameView fr, DevCfg cfg,
+                                                                const __grid_constant__ CUtensorMap tmap, int use_tma, int tile) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int f = blockIdx.x;
   if (f >= N || !ft.innov[f]) return;
-  match_filter_feature(ft, f, fr, cfg, smem_raw, use_tma ? &tmap : nullptr);
+  match_filter_feature(ft, f, fr, cfg, smem_raw, use_tma ? &tmap : nullptr, nullptr, true, tile != 0);
 }
 // ------------------------------------------------------------------------------------------------
 // Warp-per-feature path for SMALL search windows (candidate grid <= 16 x 16, template side <= 15): the batched filters
@@ -717,6 +726,69 @@ __device__ bool match_one_warp(const MatchJob& jb, int w, float sigma_size, floa
 // rank them by an exact-integer float score, and only the band candidates see double precision and the reference's exact pass.
 // No block barrier anywhere.  Returns false (nothing written, nothing decided) when the feature needs the CTA matcher.
 // ------------------------------------------------------------------------------------------------
+// The reference's computeCorrelation for one candidate on a 4-lane group, template side fixed at compile time and no selects in
+// the loop: every lane runs acc += (A[x] - mA) * (B[x] - mB) over the pixels in row-major order with its own operand pair —
+// role 0: template x template (n1), role 1: window x window (n2), roles 2 / 3: template x window (corr).  (double)(float) of
+// an 8-bit pixel is the pixel, so the conversion is direct; sums and products are the reference's, one rounding each.
+template <int W>
+__device__ __forceinline__ float match_exact_score3(const unsigned char* tb, double m1, const uint8_t* win, int wsb, int roi, int P,
+                                                    int role, unsigned gmask, int gbase) {
+  const double m2 = __ddiv_rn((double)P, (double)(W * W));
+  const uint8_t* srcA = role == 1 ? win + roi : tb;
+  const uint8_t* srcB = role == 0 ? tb : win + roi;
+  const int strA = role == 1 ? wsb : W, strB = role == 0 ? W : wsb;
+  const double mA = role == 1 ? m2 : m1, mB = role == 0 ? m1 : m2;
+  double acc = 0;
+  for (int r = 0; r < W; ++r) {
+    const uint8_t* pa = srcA + r * strA;
+    const uint8_t* pb = srcB + r * strB;
+#pragma unroll
+    for (int x = 0; x < W; ++x) {
+      const double a = __dsub_rn((double)pa[x], mA);
+      const double b = __dsub_rn((double)pb[x], mB);
+      acc = __dadd_rn(acc, __dmul_rn(a, b));
+    }
+  }
+  const double n1 = __shfl_sync(gmask, acc, gbase), n2 = __shfl_sync(gmask, acc, gbase + 1), corr = __shfl_sync(gmask, acc, gbase + 2);
+  return (float)__ddiv_rn(corr, __dsqrt_rn(__dmul_rn(n2, n1)));
+}
+
+// Window staging of the tile matchers: MT_NW words per row (row stride MT_WSW), columns past ww zero, and MT_R - 1 zero rows
+// below (the last tile row reads them).  Thread t of nthreads (a multiple of 16) owns word column t % 16 — everything that
+// depends on the column is hoisted — and walks the rows t / 16, + nthreads / 16, ...
+__device__ __forceinline__ void mt_stage_window(unsigned* winw, const MatchJob& jb, const MatchGeom& G, int W, int t, int nthreads) {
+  const int half = W / 2, ww = G.cw + W - 1, wh = G.ch + W - 1;
+  const int x0 = G.ilo - half, y0 = G.jlo - half;
+  const int nrows = wh + MT_R - 1;
+  if ((((size_t)jb.frame | (size_t)jb.fstride) & 3) == 0) {
+    const int sh = x0 & 3, xa = x0 - sh;
+    const int k = t & (MT_NW - 1), dr = nthreads / MT_NW;
+    const int rem = ww - 4 * k;
+    const bool colin = rem > 0;
+    const unsigned cmask = rem >= 4 ? 0xffffffffu : (rem > 0 ? (1u << (8 * rem)) - 1u : 0u);
+    const int last = min(4 * k + 3, ww - 1);                 // last window column this word needs
+    const bool need_hi = sh > 0 && last + sh >= 4 * k + 4;    // the word past the last needed byte is never touched
+    const uint8_t* src0 = jb.frame + (size_t)y0 * jb.fstride + xa + 4 * k;
+#pragma unroll 4
+    for (int yy = t / MT_NW; yy < nrows; yy += dr) {
+      unsigned v = 0;
+      if (yy < wh && colin) {
+        const unsigned* p = reinterpret_cast<const unsigned*>(src0 + (size_t)yy * jb.fstride);
+        const unsigned lo = p[0];
+        const unsigned hi = need_hi ? p[1] : 0u;
+        v = __funnelshift_r(lo, hi, 8 * sh) & cmask;
+      }
+      winw[yy * MT_WSW + k] = v;
+    }
+  } else {
+    uint8_t* winb = reinterpret_cast<uint8_t*>(winw);
+    for (int e = t; e < nrows * MT_NW * 4; e += nthreads) {
+      const int yy = e / (MT_NW * 4), xx = e - yy * (MT_NW * 4);
+      winb[yy * MT_WSW * 4 + xx] = (yy < wh && xx < ww) ? jb.frame[(size_t)(y0 + yy) * jb.fstride + x0 + xx] : (uint8_t)0;
+    }
+  }
+}
+
 #define MW2_WARPS 8
 template <int W>
 struct MatchWarp2Smem {
@@ -727,16 +799,15 @@ struct MatchWarp2Smem {
   int cnt;
 };
 
-template <int W>
+template <int W, bool TSMEM, bool SLIDE>
 __device__ bool match_one_warp2(const MatchJob& jb, float sigma_size, float clampv, MatchWarp2Smem<W>& sm, MatchResult& res) {
   constexpr int TW = (W + 3) / 4, W2 = W * W;
   const int lane = threadIdx.x & 31;
-  const int half = W / 2;
   if (!(clampv <= 20.0f)) return false;
   const MatchGeom G = match_geometry(jb, W, sigma_size, clampv, MT_MAXGRID);
   res.best = -1.0f; res.bi = 0; res.bj = 0;
   if (!G.any) return true;
-  const int cw = G.cw, ch = G.ch, ww = cw + W - 1, wh = ch + W - 1;
+  const int cw = G.cw, ch = G.ch;
   // --- template: packed words (zero padded), bytes, T = sum t, TT = sum t^2 ---
   int T = 0, TT = 0;
   for (int e = lane; e < W * TW; e += 32) {
@@ -753,34 +824,7 @@ __device__ bool match_one_warp2(const MatchJob& jb, float sigma_size, float clam
   }
   for (int e = lane; e < W2; e += 32) sm.tb[e] = jb.tmpl[e];
   for (int o = 16; o > 0; o >>= 1) { T += __shfl_xor_sync(0xffffffffu, T, o); TT += __shfl_xor_sync(0xffffffffu, TT, o); }
-  // --- window: MT_NW words per row, columns past ww zero, and MT_R - 1 zero rows below (the last tile row reads them) ---
-  {
-    const int x0 = G.ilo - half, y0 = G.jlo - half;
-    const int nrows = wh + MT_R - 1;
-    if ((((size_t)jb.frame | (size_t)jb.fstride) & 3) == 0) {
-      const int sh = x0 & 3, xa = x0 - sh;
-      for (int e = lane; e < nrows * MT_NW; e += 32) {
-        const int yy = e / MT_NW, k = e - yy * MT_NW;
-        unsigned v = 0;
-        if (yy < wh && 4 * k < ww) {
-          const unsigned* srcw = reinterpret_cast<const unsigned*>(jb.frame + (size_t)(y0 + yy) * jb.fstride + xa);
-          const int last = min(4 * k + 3, ww - 1);          // last window column this word needs
-          const unsigned lo = srcw[k];
-          const unsigned hi = (sh > 0 && last + sh >= 4 * k + 4) ? srcw[k + 1] : 0u;
-          v = __funnelshift_r(lo, hi, 8 * sh);
-          const int rem = ww - 4 * k;
-          if (rem < 4) v &= (1u << (8 * rem)) - 1u;
-        }
-        sm.win[yy * MT_WSW + k] = v;
-      }
-    } else {
-      uint8_t* winb = reinterpret_cast<uint8_t*>(sm.win);
-      for (int e = lane; e < nrows * MT_NW * 4; e += 32) {
-        const int yy = e / (MT_NW * 4), xx = e - yy * (MT_NW * 4);
-        winb[yy * MT_WSW * 4 + xx] = (yy < wh && xx < ww) ? jb.frame[(size_t)(y0 + yy) * jb.fstride + x0 + xx] : (uint8_t)0;
-      }
-    }
-  }
+  mt_stage_window(sm.win, jb, G, W, lane, 32);
   __syncwarp();
   const double dn = (double)W2;
   const double m1 = __ddiv_rn((double)T, dn);
@@ -791,9 +835,11 @@ __device__ bool match_one_warp2(const MatchJob& jb, float sigma_size, float clam
   MTTop top;
   top.reset();
   {
-    unsigned Treg[W * TW];
+    unsigned Treg[TSMEM ? 1 : W * TW];   // TSMEM: the template words are shared-memory operands (broadcast loads) instead of 33 registers
+    if (!TSMEM) {
 #pragma unroll
-    for (int e = 0; e < W * TW; ++e) Treg[e] = sm.tpk[e];
+      for (int e = 0; e < W * TW; ++e) Treg[e] = sm.tpk[e];
+    }
     MTGate g;
     g.x2c = G.x_2_coeff; g.y2c = G.y_2_coeff; g.yxc = G.yx_coeff; g.sigma2 = G.sigma_2;
     g.du0 = G.ilo - G.uc; g.dv0 = G.jlo - G.vc; g.cw = cw; g.ch = ch; g.T = T; g.rd1f = (float)rd1;
@@ -801,7 +847,8 @@ __device__ bool match_one_warp2(const MatchJob& jb, float sigma_size, float clam
     int ty = lane / ntx, tx = lane - ty * ntx;
     const int dty = 32 / ntx, dtx = 32 - dty * ntx;
     while (ty < nty) {
-      mt_tile<W>(sm.win, tx, ty, Treg, g, top);
+      if (TSMEM) mt_tile<W, MT_R, SLIDE>(sm.win, tx, ty, sm.tpk, g, top);
+      else mt_tile<W, MT_R, SLIDE>(sm.win, tx, ty, reinterpret_cast<const unsigned (&)[W * TW]>(Treg), g, top);
       tx += dtx; ty += dty;
       if (tx >= ntx) { tx -= ntx; ++ty; }
     }
@@ -847,7 +894,7 @@ __device__ bool match_one_warp2(const MatchJob& jb, float sigma_size, float clam
     const uint4 c = sm.list[q];
     if (!(mt_ncc_star(W2, c.y, (int)c.z, (int)c.w, T, rd1) >= thr)) continue;   // same value in the four lanes
     const int jv = (int)c.x / cw, iu = (int)c.x - jv * cw;
-    const float s1 = match_exact_score4_tb(sm.tb, m1, winb, MT_WSW * 4, jv * MT_WSW * 4 + iu, W, (int)c.z, role, gmask, gbase);
+    const float s1 = match_exact_score3<W>(sm.tb, m1, winb, MT_WSW * 4, jv * MT_WSW * 4 + iu, (int)c.z, role, gmask, gbase);
     const int key = (G.ilo + iu - G.i0) * G.nv + (G.jlo + jv - G.j0);
     if (role == 0 && (s1 > best || (s1 == best && key < bestkey))) { best = s1; bestkey = key; }
   }
@@ -861,6 +908,142 @@ __device__ bool match_one_warp2(const MatchJob& jb, float sigma_size, float clam
     res.bi = G.i0 + bestkey / G.nv;
     res.bj = G.j0 + bestkey % G.nv;
   }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same scoring core for ONE feature per CTA (the single-filter path: a few hundred features per frame, where the latency
+// of a feature counts, not the throughput): MATCH_THREADS threads take the 4 x 2-candidate tiles of the feature (231 tiles
+// of a 41 x 41 grid: one round), the band list is shared, warp 0 finishes.  Four block barriers instead of match_one's
+// seven phases through shared memory.  The verdict is uniform over the CTA: false = match_one must run (nothing written).
+// ------------------------------------------------------------------------------------------------
+template <int W>
+struct MatchTileCtaSmem {
+  MatchWarp2Smem<W> w;
+  int T, TT;
+  float fmax[MATCH_THREADS / 32];
+  float best;
+  int bi, bj;
+};
+template <int W, int R>
+__device__ bool match_one_tile_cta(const MatchJob& jb, float sigma_size, float clampv, unsigned char* smem_raw, MatchResult& res) {
+  constexpr int TW = (W + 3) / 4, W2 = W * W;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  MatchTileCtaSmem<W>& cs = *reinterpret_cast<MatchTileCtaSmem<W>*>(smem_raw);
+  MatchWarp2Smem<W>& sm = cs.w;
+  res.best = -1.0f; res.bi = 0; res.bj = 0;
+  if (!(clampv <= 20.0f)) return false;
+  const MatchGeom G = match_geometry(jb, W, sigma_size, clampv, MT_MAXGRID);
+  if (!G.any) return true;
+  const int cw = G.cw, ch = G.ch;
+  if (tid == 0) { sm.cnt = 0; cs.T = 0; cs.TT = 0; }
+  __syncthreads();
+  // --- template: packed words, bytes, T, TT ---
+  {
+    int pt = 0, ptt = 0;
+    for (int e = tid; e < W * TW; e += MATCH_THREADS) {
+      const int r = e / TW, k4 = (e - r * TW) * 4;
+      unsigned word = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (k4 + c < W) {
+          const unsigned v = jb.tmpl[r * W + k4 + c];
+          word |= v << (8 * c);
+          pt += (int)v; ptt += (int)(v * v);
+        }
+      sm.tpk[e] = word;
+    }
+    for (int e = tid; e < W2; e += MATCH_THREADS) sm.tb[e] = jb.tmpl[e];
+    for (int o = 16; o > 0; o >>= 1) { pt += __shfl_xor_sync(0xffffffffu, pt, o); ptt += __shfl_xor_sync(0xffffffffu, ptt, o); }
+    if (lane == 0 && (pt | ptt)) { atomicAdd(&cs.T, pt); atomicAdd(&cs.TT, ptt); }
+  }
+  mt_stage_window(sm.win, jb, G, W, tid, MATCH_THREADS);
+  __syncthreads();
+  const int T = cs.T, TT = cs.TT;
+  const double dn = (double)W2;
+  const double m1 = __ddiv_rn((double)T, dn);
+  const double d1 = dn * (double)TT - (double)T * (double)T;   // exact (< 2^53)
+  if (!(d1 > 0.0)) return true;                                 // flat template
+  const double rd1 = rsqrt(d1);
+  // --- ranking pass ---
+  MTTop top;
+  top.reset();
+  {
+    const int ntx = (cw + 3) >> 2, nty = (ch + R - 1) / R;
+    const int ntiles = ntx * nty;
+    if (tid < ntiles) {
+      MTGate g;
+      g.x2c = G.x_2_coeff; g.y2c = G.y_2_coeff; g.yxc = G.yx_coeff; g.sigma2 = G.sigma_2;
+      g.du0 = G.ilo - G.uc; g.dv0 = G.jlo - G.vc; g.cw = cw; g.ch = ch; g.T = T; g.rd1f = (float)rd1;
+      for (int t = tid; t < ntiles; t += MATCH_THREADS) {
+        const int ty = t / ntx, tx = t - ty * ntx;
+        mt_tile<W, R>(sm.win, tx, ty, sm.tpk, g, top);   // template words straight from shared memory (broadcast): 64 registers, 4 CTAs per SM
+      }
+    }
+  }
+  float F = top.a0;
+  for (int o = 16; o > 0; o >>= 1) F = fmaxf(F, __shfl_xor_sync(0xffffffffu, F, o));
+  if (lane == 0) cs.fmax[warp] = F;
+  __syncthreads();
+#pragma unroll
+  for (int wv = 0; wv < MATCH_THREADS / 32; ++wv) F = fmaxf(F, cs.fmax[wv]);
+  if (!(F > -INFINITY)) return true;
+  const float thrF = F - MT_BAND;
+  if (__syncthreads_or(top.a2 >= thrF)) return false;           // a thread may have dropped a band candidate
+  if (top.a0 >= thrF) {
+    const int slot = atomicAdd(&sm.cnt, 1);
+    if (slot < MT_LIST) sm.list[slot] = make_uint4((unsigned)top.i0, top.s0, (unsigned)top.p0, (unsigned)top.q0);
+  }
+  if (top.a1 >= thrF) {
+    const int slot = atomicAdd(&sm.cnt, 1);
+    if (slot < MT_LIST) sm.list[slot] = make_uint4((unsigned)top.i1, top.s1, (unsigned)top.p1, (unsigned)top.q1);
+  }
+  __syncthreads();
+  const int nlist = sm.cnt;
+  if (nlist > MT_LIST) return false;
+  if (warp == 0) {
+    // --- ncc* in double of the band candidates, the guard band, the exact pass (as match_one_warp2) ---
+    const double kNone = -1.0e300;
+    double v = kNone;
+    if (lane < nlist) {
+      const uint4 c = sm.list[lane];
+      v = mt_ncc_star(W2, c.y, (int)c.z, (int)c.w, T, rd1);
+    }
+    double Mstar = v;
+    for (int o = 16; o > 0; o >>= 1) Mstar = fmax(Mstar, __shfl_xor_sync(0xffffffffu, Mstar, o));
+    const float fm = fabsf((float)Mstar);
+    const double ulp = (double)(nextafterf(fm, 3.0e38f) - fm);
+    const double thr = Mstar - (2.0 * ulp + 4.0e-12);
+    float best = -1.0f;
+    int bestkey = 0x7fffffff;
+    const uint8_t* winb = reinterpret_cast<const uint8_t*>(sm.win);
+    const int role = lane & 3, gbase = lane & ~3;
+    const unsigned gmask = 0xfu << gbase;
+    for (int q0 = 0; q0 < nlist; q0 += 8) {
+      const int q = q0 + (lane >> 2);
+      if (q >= nlist) continue;
+      const uint4 c = sm.list[q];
+      if (!(mt_ncc_star(W2, c.y, (int)c.z, (int)c.w, T, rd1) >= thr)) continue;
+      const int jv = (int)c.x / cw, iu = (int)c.x - jv * cw;
+      const float s1 = match_exact_score3<W>(sm.tb, m1, winb, MT_WSW * 4, jv * MT_WSW * 4 + iu, (int)c.z, role, gmask, gbase);
+      const int key = (G.ilo + iu - G.i0) * G.nv + (G.jlo + jv - G.j0);
+      if (role == 0 && (s1 > best || (s1 == best && key < bestkey))) { best = s1; bestkey = key; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int ok = __shfl_xor_sync(0xffffffffu, bestkey, o);
+      if (ob > best || (ob == best && ok < bestkey)) { best = ob; bestkey = ok; }
+    }
+    if (lane == 0) {
+      cs.best = best; cs.bi = 0; cs.bj = 0;
+      if (bestkey != 0x7fffffff && G.nv > 0) {
+        cs.bi = G.i0 + bestkey / G.nv;
+        cs.bj = G.j0 + bestkey % G.nv;
+      }
+    }
+  }
+  __syncthreads();
+  res.best = cs.best; res.bi = cs.bi; res.bj = cs.bj;
   return true;
 }
 
@@ -887,7 +1070,8 @@ __device__ __forceinline__ void match_warp_commit(FeatTab ft, int f, FrameView f
 }
 
 // Batched filters, pass 1 with the full-window warp matcher (template side 11): one warp per (filter, feature)
-__global__ void __launch_bounds__(MW2_WARPS * 32, 2) k_match_filter_batch_warp2(FeatTab base, int Ncap, const int* __restrict__ Nper, int B,
+template <int MINB, bool TSMEM, bool SLIDE>
+__global__ void __launch_bounds__(MW2_WARPS * 32, MINB) k_match_filter_batch_warp2(FeatTab base, int Ncap, const int* __restrict__ Nper, int B,
                                                                                 FrameView fr, DevCfg cfg, int* __restrict__ defer_list,
                                                                                 int* __restrict__ defer_cnt) {
   __shared__ MatchWarp2Smem<11> wsm[MW2_WARPS];
@@ -906,7 +1090,7 @@ __global__ void __launch_bounds__(MW2_WARPS * 32, 2) k_match_filter_batch_warp2(
   if (lane == 0) wsm[warp].cnt = 0;
   __syncwarp();
   MatchResult r;
-  if (!match_one_warp2<11>(jb, cfg.sigma_size_f, cfg.search_clamp, wsm[warp], r)) {
+  if (!match_one_warp2<11, TSMEM, SLIDE>(jb, cfg.sigma_size_f, cfg.search_clamp, wsm[warp], r)) {
     if (lane == 0) defer_list[atomicAdd(defer_cnt, 1)] = (int)pair;
     return;
   }
@@ -1006,7 +1190,8 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_batch(const uint8_t* __
 // Stateless batch with the full-window warp matcher (template side 11): one warp per (frame, feature).  A feature that needs
 // the CTA matcher is MARKED in out_uv and worked off by the persistent grid of k_match_batch_marked.
 #define MATCH_MARK ((int32_t)0x80000000)
-__global__ void __launch_bounds__(MW2_WARPS * 32, 2) k_match_batch_warp2(const uint8_t* __restrict__ frames, int width, int height, int stride,
+template <int MINB, bool TSMEM, bool SLIDE>
+__global__ void __launch_bounds__(MW2_WARPS * 32, MINB) k_match_batch_warp2(const uint8_t* __restrict__ frames, int width, int height, int stride,
                                                                          const uint8_t* __restrict__ templates, int fpf,
                                                                          const double* __restrict__ hh, const double* __restrict__ Sm,
                                                                          float sigma_size, float thr, float clampv,
@@ -1025,7 +1210,7 @@ __global__ void __launch_bounds__(MW2_WARPS * 32, 2) k_match_batch_warp2(const u
   if (lane == 0) wsm[warp].cnt = 0;
   __syncwarp();
   MatchResult r;
-  const bool done = match_one_warp2<11>(jb, sigma_size, clampv, wsm[warp], r);
+  const bool done = match_one_warp2<11, TSMEM, SLIDE>(jb, sigma_size, clampv, wsm[warp], r);
   if (lane == 0) {
     if (!done) {
       out_uv[2 * idx] = MATCH_MARK;
@@ -1068,15 +1253,27 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_batch_marked(const uint
   }
 }
 
+// EKF_MATCH_W2VAR: build of the warp tile matcher — 0 template words in registers, 2 CTAs per SM (128 registers); 1 template
+// words as shared-memory operands, 2 CTAs; 2 shared-memory operands, 3 CTAs per SM (80 registers); + 4: window sums of the three
+// right-hand candidates by sliding (mt_tile SLIDE).  Measured (tools/match_ab.py, 12 800 features per launch): 0 / 1 / 2 / 4 / 5 / 6 =
+// 52.3 / 55.2 / 54.4 / 51.9 / 55.6 / 53.4 M matches/s — DP4A and IMAD share one pipe (tools/idp_rate_probe: 2 warp-instructions per
+// cycle per SM each and together), so sliding buys nothing; default 1.
+static int match_w2_variant() {
+  const char* e = getenv("EKF_MATCH_W2VAR");   // read per call: tools/match_ab.py switches it inside one process
+  return e ? atoi(e) : 1;
+}
+
 void launch_match_filter(cudaStream_t st, FeatTab ft, int N, FrameView fr, const DevCfg& cfg, const EkfTensorMap* tmap, long long* launches) {
   if (N <= 0) return;
   static PerDeviceOnce once;   // opt in to the largest supported window once per device
-  const size_t smem = match_smem_bytes(cfg.window, cfg.search_clamp);
+  size_t smem = match_smem_bytes(cfg.window, cfg.search_clamp);
+  if (smem < sizeof(MatchTileCtaSmem<11>)) smem = sizeof(MatchTileCtaSmem<11>);   // the tile matcher's fixed-size window buffer
   if (once.ensure([] { return cudaFuncSetAttribute(k_match_filter, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    (int)match_smem_bytes(MATCH_MAX_W, 20.0f)); }) != cudaSuccess) return;   // the error stays in cudaGetLastError() for the caller
   static const EkfTensorMap none{};
   const EkfTensorMap& tm = (tmap && tmap->ok) ? *tmap : none;
-  k_match_filter<<<N, MATCH_THREADS, smem, st>>>(ft, N, fr, cfg, as_cu(tm), tm.ok);
+  static const int tile = [] { const char* e = getenv("EKF_MATCH_WARP"); return (e ? atoi(e) : 2) >= 2; }();   // the tile matcher ahead of match_one
+  k_match_filter<<<N, MATCH_THREADS, smem, st>>>(ft, N, fr, cfg, as_cu(tm), tm.ok, tile);
   *launches += 1;
 }
 
@@ -1095,10 +1292,20 @@ void launch_match_filter_batch(cudaStream_t st, FeatTab base, int Ncap, const in
   // EKF_MATCH_WARP: 2 (default) full-window warp matcher where the template side allows it, 1 the small-window warp matcher only,
   // 0 every feature takes the CTA matcher (A/B timing, tests)
   static const int warp_path = [] { const char* e = getenv("EKF_MATCH_WARP"); return e ? atoi(e) : 2; }();
-  if (warp_path >= 2 && cfg.window == 11 && cfg.search_clamp <= 20.0f)
-    k_match_filter_batch_warp2<<<(unsigned)((pairs + MW2_WARPS - 1) / MW2_WARPS), MW2_WARPS * 32, 0, st>>>(base, Ncap, Nper, B, fr, cfg, defer_list,
-                                                                                                           defer_cnt);
-  else
+  if (warp_path >= 2 && cfg.window == 11 && cfg.search_clamp <= 20.0f) {
+    const unsigned grid = (unsigned)((pairs + MW2_WARPS - 1) / MW2_WARPS);
+    const int var = match_w2_variant();
+#define MW2_LAUNCH(MINB, TS, SL) k_match_filter_batch_warp2<MINB, TS, SL><<<grid, MW2_WARPS * 32, 0, st>>>(base, Ncap, Nper, B, fr, cfg, defer_list, defer_cnt)
+    switch (var) {
+      case 0: MW2_LAUNCH(2, false, false); break;
+      case 2: MW2_LAUNCH(3, true, false); break;
+      case 4: MW2_LAUNCH(2, false, true); break;
+      case 5: MW2_LAUNCH(2, true, true); break;
+      case 6: MW2_LAUNCH(3, true, true); break;
+      default: MW2_LAUNCH(2, true, false); break;   // 1
+    }
+#undef MW2_LAUNCH
+  } else
     k_match_filter_batch_warp<<<(unsigned)((pairs + MW_WARPS - 1) / MW_WARPS), MW_WARPS * 32, 0, st>>>(base, Ncap, Nper, B, fr, cfg, defer_list, defer_cnt,
                                                                                                        warp_path);
   int dev = 0, sms = 148;
@@ -1130,8 +1337,18 @@ int launch_match_batch(cudaStream_t st, const uint8_t* frames, int n_frames, int
     static PerDeviceOnce once2;
     if (once2.ensure([] { return cudaFuncSetAttribute(k_match_batch_marked, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                       (int)match_smem_bytes(MATCH_MAX_W, 20.0f)); }) != cudaSuccess) return -1;
-    k_match_batch_warp2<<<(total + MW2_WARPS - 1) / MW2_WARPS, MW2_WARPS * 32, 0, st>>>(frames, width, height, stride, templates, fpf, h, S,
-                                                                                       sigma_size, thr, clampv, out_uv, out_score, total);
+    const int grid2 = (total + MW2_WARPS - 1) / MW2_WARPS, var = match_w2_variant();
+#define MW2_LAUNCH(MINB, TS, SL) \
+  k_match_batch_warp2<MINB, TS, SL><<<grid2, MW2_WARPS * 32, 0, st>>>(frames, width, height, stride, templates, fpf, h, S, sigma_size, thr, clampv, out_uv, out_score, total)
+    switch (var) {
+      case 0: MW2_LAUNCH(2, false, false); break;
+      case 2: MW2_LAUNCH(3, true, false); break;
+      case 4: MW2_LAUNCH(2, false, true); break;
+      case 5: MW2_LAUNCH(2, true, true); break;
+      case 6: MW2_LAUNCH(3, true, true); break;
+      default: MW2_LAUNCH(2, true, false); break;   // 1
+    }
+#undef MW2_LAUNCH
     int dev = 0, sms = 148, per_sm = 4;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_match_batch_marked, MATCH_THREADS, smem) != cudaSuccess || per_sm < 1) {

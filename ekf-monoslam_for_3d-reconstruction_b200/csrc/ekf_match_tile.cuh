@@ -28,7 +28,7 @@
 #define MT_HD inline
 #endif
 
-#define MT_R 4          // candidate rows per tile (and 4 candidate columns: one aligned word of shifts)
+#define MT_R 4          // most candidate rows per tile (always 4 candidate columns: one aligned word of shifts); sizes the window buffer
 #define MT_WSW 19       // window row stride in words: 4 rows apart = 76 words = 12 banks, so the three tile rows a warp works on at once do not collide
 #define MT_NW 16        // words staged per window row (41 + 15 - 1 <= 56 bytes + one word of slack)
 #define MT_MAXGRID 41   // candidate grid side at the reference's clamp of +-20 px
@@ -66,9 +66,11 @@ MT_HD float mt_fadd(float a, float b) {
   return r;
 #endif
 }
-MT_HD float mt_rsqrtf(float x) {
+MT_HD float mt_rsqrtf(float x) {   // x = (float) of a positive int32: one MUFU.RSQ (2 ulp), no range fix-up needed
 #ifdef __CUDA_ARCH__
-  return rsqrtf(x);
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 #else
   return 1.0f / sqrtf(x);
 #endif
@@ -167,23 +169,40 @@ struct MTTop {
   }
 };
 
-// One tile: candidates (4 tx + s, 4 ty + j), s, j = 0..3.  winw: the staged window as words (row stride MT_WSW); T: the packed
+// One tile of 4 x R candidates: (4 tx + s, R ty + j), s = 0..3, j = 0..R-1.  winw: the staged window as words (row stride MT_WSW); T: the packed
 // template (zero padded to whole words), row-major [W][TW].
-template <int W>
+//
+// SLIDE: the window sums of the three right-hand candidates of a row come from the left-hand one by sliding — one byte leaves, one
+// enters: d = in - out, P += d, PP += d (in + out) — on the integer ALU / IMAD pipes instead of 18 of the 24 DP4As per window row
+// (DP4A is the instruction this kernel is bound by).  What runs down the rows is then cp[0] / cpp[0] and the three running
+// DIFFERENCES between neighbouring candidates; a prefix sum rebuilds cp[s] where a candidate row starts or ends.
+template <int W, int R, bool SLIDE = false>
 MT_HD void mt_tile(const unsigned* winw, int tx, int ty, const unsigned (&T)[W * ((W + 3) / 4)], const MTGate& g, MTTop& top) {
   constexpr int TW = (W + 3) / 4;
-  constexpr int ROWS = MT_R + W - 1;
+  constexpr int ROWS = R + W - 1;
   constexpr int NN = W * W;
   constexpr unsigned LASTMASK = (W & 3) ? ((1u << (8 * (W & 3))) - 1u) : 0xffffffffu;
   static_assert(W <= 12, "int32 numerators need W <= 12; TW + 1 <= 4 words per row");
-  unsigned stp[MT_R][4], ps[MT_R][4], pps[MT_R][4], cp[4], cpp[4];
+  unsigned stp[R][4], ps[R][4], pps[R][4], cp[4], cpp[4];
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
     cp[s] = 0; cpp[s] = 0;
 #pragma unroll
-    for (int j = 0; j < MT_R; ++j) { stp[j][s] = 0; ps[j][s] = 0; pps[j][s] = 0; }
+    for (int j = 0; j < R; ++j) { stp[j][s] = 0; ps[j][s] = 0; pps[j][s] = 0; }
   }
-  const unsigned* base = winw + (MT_R * ty) * MT_WSW + tx;
+  const unsigned* base = winw + (R * ty) * MT_WSW + tx;
+  // per column of the tile: inside the grid?, and the two ellipse terms that do not depend on the row (Patch.cpp:247, same
+  // association: (x2c di) di, (yxc di) dj)
+  bool colok[4];
+  float ex[4], cxy[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int iu = 4 * tx + s;
+    colok[s] = iu < g.cw;
+    const float fdi = (float)(g.du0 + iu);
+    ex[s] = mt_fmul(mt_fmul(g.x2c, fdi), fdi);
+    cxy[s] = mt_fmul(g.yxc, fdi);
+  }
 #pragma unroll
   for (int y = 0; y < ROWS; ++y) {
     unsigned wv[TW + 1];
@@ -196,20 +215,43 @@ MT_HD void mt_tile(const unsigned* winw, int tx, int ty, const unsigned (&T)[W *
       for (int k = 0; k < TW; ++k) x[s][k] = s ? mt_fshr(wv[k], wv[k + 1], 8 * s) : wv[k];
       x[s][TW - 1] &= LASTMASK;   // bytes past the template side of this candidate
     }
-    if (y < MT_R) {               // candidate row y starts here: remember the running sums before this row
+    if (y < R) {                  // candidate row y starts here: remember the running sums before this row
+      if (SLIDE) {
+        unsigned a = cp[0], b = cpp[0];
+        ps[y][0] = a; pps[y][0] = b;
 #pragma unroll
-      for (int s = 0; s < 4; ++s) { ps[y][s] = cp[s]; pps[y][s] = cpp[s]; }
+        for (int s = 1; s < 4; ++s) { a += cp[s]; b += cpp[s]; ps[y][s] = a; pps[y][s] = b; }
+      } else {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) { ps[y][s] = cp[s]; pps[y][s] = cpp[s]; }
+      }
     }
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
+    if (SLIDE) {
 #pragma unroll
       for (int k = 0; k < TW; ++k) {
-        cp[s] = mt_dp4a(x[s][k], 0x01010101u, cp[s]);
-        cpp[s] = mt_dp4a(x[s][k], x[s][k], cpp[s]);
+        cp[0] = mt_dp4a(x[0][k], 0x01010101u, cp[0]);
+        cpp[0] = mt_dp4a(x[0][k], x[0][k], cpp[0]);
+      }
+#pragma unroll
+      for (int s = 1; s < 4; ++s) {   // candidate s = candidate s - 1 without window column s - 1, with column s - 1 + W
+        const unsigned bout = (wv[(s - 1) >> 2] >> (8 * ((s - 1) & 3))) & 255u;
+        const unsigned bin = (wv[(s - 1 + W) >> 2] >> (8 * ((s - 1 + W) & 3))) & 255u;
+        const unsigned d = bin - bout;
+        cp[s] += d;
+        cpp[s] += d * (bin + bout);
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+#pragma unroll
+        for (int k = 0; k < TW; ++k) {
+          cp[s] = mt_dp4a(x[s][k], 0x01010101u, cp[s]);
+          cpp[s] = mt_dp4a(x[s][k], x[s][k], cpp[s]);
+        }
       }
     }
 #pragma unroll
-    for (int j = 0; j < MT_R; ++j) {
+    for (int j = 0; j < R; ++j) {
       const int r = y - j;        // template row that window row y meets in candidate row j
       if (r >= 0 && r < W) {
 #pragma unroll
@@ -219,30 +261,35 @@ MT_HD void mt_tile(const unsigned* winw, int tx, int ty, const unsigned (&T)[W *
         }
       }
     }
-    if (y >= W - 1) {             // candidate row j = y - (W - 1) is complete
+    if (y >= W - 1) {             // candidate row j = y - (W - 1) is complete: straight-line scoring, one rare branch
       const int j = y - (W - 1);
-      const int jv = MT_R * ty + j;
-      if (jv < g.ch) {
-        const float dj = (float)(g.dv0 + jv);
-        const float ey = mt_fmul(mt_fmul(g.y2c, dj), dj);
+      const int jv = R * ty + j;
+      const bool rowok = jv < g.ch;
+      const float dj = (float)(g.dv0 + jv);
+      const float ey = mt_fmul(mt_fmul(g.y2c, dj), dj);
+      unsigned cps[4], cpps[4];   // the running sums of the four candidates after this window row
+      if (SLIDE) {
+        cps[0] = cp[0]; cpps[0] = cpp[0];
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          const int iu = 4 * tx + s;
-          if (iu < g.cw) {
-            // ellipse gate in float, same association as Patch.cpp:247
-            const float fdi = (float)(g.du0 + iu);
-            const float e = mt_fadd(mt_fadd(mt_fmul(mt_fmul(g.x2c, fdi), fdi), ey), mt_fmul(mt_fmul(g.yxc, fdi), dj));
-            if (e <= g.sigma2) {
-              const int P = (int)(cp[s] - ps[j][s]), PP = (int)(cpp[s] - pps[j][s]);
-              const int d2 = NN * PP - P * P;                 // exact: <= 144 * 144 * 255^2 < 2^31
-              if (d2 > 0) {                                   // flat window: 0/0 in the reference, never selected
-                const int num = NN * (int)stp[j][s] - g.T * P;   // exact
-                const float f = (float)num * (g.rd1f * mt_rsqrtf((float)d2));
-                top.insert(f, jv * g.cw + iu, stp[j][s], P, PP);
-              }
-            }
-          }
-        }
+        for (int s = 1; s < 4; ++s) { cps[s] = cps[s - 1] + cp[s]; cpps[s] = cpps[s - 1] + cpp[s]; }
+      } else {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) { cps[s] = cp[s]; cpps[s] = cpp[s]; }
+      }
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const float e = mt_fadd(mt_fadd(ex[s], ey), mt_fmul(cxy[s], dj));   // ellipse gate in float
+        const int P = (int)(cps[s] - ps[j][s]), PP = (int)(cpps[s] - pps[j][s]);
+        const int d2 = NN * PP - P * P;                   // exact: <= 144 * 144 * 255^2 < 2^31; 0 for a flat window
+        const int num = NN * (int)stp[j][s] - g.T * P;    // exact
+        const float f = (float)num * (g.rd1f * mt_rsqrtf((float)d2));
+        const bool valid = rowok && colok[s] && (e <= g.sigma2) && (d2 > 0);   // flat window: 0/0 in the reference, never selected
+#ifdef __CUDA_ARCH__
+        if (__builtin_expect(valid && f > top.a2, 0))
+#else
+        if (valid && f > top.a2)
+#endif
+          top.insert(f, jv * g.cw + 4 * tx + s, stp[j][s], P, PP);
       }
     }
   }

@@ -30,6 +30,7 @@ float exact_score(const unsigned char* tb, double m1, const uint8_t* winb, int w
 }
 
 // returns 1 decided, 0 handed to the CTA matcher
+template <int R, bool SLIDE>
 int emu_one(const MatchJob& jb, float sigma_size, float clampv, float* best_out, int* bi, int* bj, int* nlist_out) {
   *best_out = -1.0f; *bi = 0; *bj = 0; *nlist_out = 0;
   if (!(clampv <= 20.0f)) return 0;
@@ -70,13 +71,13 @@ int emu_one(const MatchJob& jb, float sigma_size, float clampv, float* best_out,
   MTGate g;
   g.x2c = G.x_2_coeff; g.y2c = G.y_2_coeff; g.yxc = G.yx_coeff; g.sigma2 = G.sigma_2;
   g.du0 = G.ilo - G.uc; g.dv0 = G.jlo - G.vc; g.cw = cw; g.ch = ch; g.T = T; g.rd1f = (float)rd1;
-  const int ntx = (cw + 3) >> 2, nty = (ch + MT_R - 1) / MT_R;
+  const int ntx = (cw + 3) >> 2, nty = (ch + R - 1) / R;
   for (int lane = 0; lane < 32; ++lane) {
     top[lane].reset();
     int ty = lane / ntx, tx = lane - ty * ntx;
     const int dty = 32 / ntx, dtx = 32 - dty * ntx;
     while (ty < nty) {
-      mt_tile<W>(win.data(), tx, ty, tpk, g, top[lane]);
+      mt_tile<W, R, SLIDE>(win.data(), tx, ty, tpk, g, top[lane]);
       tx += dtx; ty += dty;
       if (tx >= ntx) { tx -= ntx; ++ty; }
     }
@@ -119,10 +120,11 @@ int emu_one(const MatchJob& jb, float sigma_size, float clampv, float* best_out,
 }  // namespace
 
 // Same argument meaning as ekf_match_batch (include/ekf_b200.h); template side 11 only.  decided[i] = 0: the warp matcher would
-// hand feature i to the CTA matcher (out_* untouched); nlist[i] = band candidates that saw double precision.
+// hand feature i to the CTA matcher (out_* untouched); nlist[i] = band candidates that saw double precision; tile_rows = 4 (the
+// warp kernels) or 2 (the CTA-per-feature kernel: 231 tiles over 256 threads); x 10: with sliding window sums (mt_tile SLIDE).
 extern "C" int emu_match_batch(const uint8_t* frames, int n_frames, int width, int height, int stride, const uint8_t* templates,
                                int fpf, const double* h, const double* S, float sigma_size, float thr, float clampv,
-                               int32_t* out_uv, float* out_score, int32_t* decided, int32_t* nlist) {
+                               int32_t* out_uv, float* out_score, int32_t* decided, int32_t* nlist, int tile_rows) {
   for (int idx = 0; idx < n_frames * fpf; ++idx) {
     MatchJob jb;
     jb.tmap = nullptr; jb.frame_index = idx / fpf;
@@ -132,7 +134,12 @@ extern "C" int emu_match_batch(const uint8_t* frames, int n_frames, int width, i
     jb.hu = h[2 * idx]; jb.hv = h[2 * idx + 1];
     for (int c = 0; c < 4; ++c) jb.S[c] = S[4 * idx + c];
     float best; int bi, bj, nl;
-    decided[idx] = emu_one(jb, sigma_size, clampv, &best, &bi, &bj, &nl);
+    switch (tile_rows) {
+      case 2: decided[idx] = emu_one<2, false>(jb, sigma_size, clampv, &best, &bi, &bj, &nl); break;
+      case 20: decided[idx] = emu_one<2, true>(jb, sigma_size, clampv, &best, &bi, &bj, &nl); break;
+      case 40: decided[idx] = emu_one<4, true>(jb, sigma_size, clampv, &best, &bi, &bj, &nl); break;
+      default: decided[idx] = emu_one<4, false>(jb, sigma_size, clampv, &best, &bi, &bj, &nl); break;
+    }
     nlist[idx] = nl;
     if (decided[idx]) {
       const bool accept = !(best < thr);

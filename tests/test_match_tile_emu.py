@@ -37,7 +37,7 @@ def emu():
     return lib
 
 
-def _emu_run(lib, frames, templates, h, S, sigma_size, thr=0.8, clamp=20.0):
+def _emu_run(lib, frames, templates, h, S, sigma_size, thr=0.8, clamp=20.0, tile_rows=4):
     frames = np.ascontiguousarray(frames, dtype=np.uint8)
     F, H, W = frames.shape
     templates = np.ascontiguousarray(templates, dtype=np.uint8)
@@ -48,7 +48,7 @@ def _emu_run(lib, frames, templates, h, S, sigma_size, thr=0.8, clamp=20.0):
     dec = np.zeros(total, dtype=np.int32); nl = np.zeros(total, dtype=np.int32)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     rc = lib.emu_match_batch(p(frames), F, W, H, W, p(templates), M, p(h), p(S), ctypes.c_float(sigma_size), ctypes.c_float(thr),
-                             ctypes.c_float(clamp), p(uv), p(sc), p(dec), p(nl))
+                             ctypes.c_float(clamp), p(uv), p(sc), p(dec), p(nl), int(tile_rows))
     assert rc == 0
     return uv, sc, dec.astype(bool), nl
 
@@ -58,11 +58,12 @@ def _check(uv_e, sc_e, dec, uv_o, sc_o):
     assert np.array_equal(sc_e[dec].view(np.uint32), sc_o[dec].view(np.uint32)), "float NCC scores differ bitwise"
 
 
+@pytest.mark.parametrize("tile_rows", [4, 2, 40, 20])
 @pytest.mark.parametrize("s_diag,sigma_size,seed", [(16.0, 3.0, 5), (60.0, 3.0, 6), (200.0, 3.0, 7), (2.0, 2.0, 8)])
-def test_tile_core_bit_exact_on_planted_scenes(pkg, orc, emu, s_diag, sigma_size, seed):
+def test_tile_core_bit_exact_on_planted_scenes(pkg, orc, emu, s_diag, sigma_size, seed, tile_rows):
     d = pkg.synth.match_batch_inputs(n_frames=2, features_per_frame=40, width=640, height=480, window=11, seed=seed, s_diag=s_diag)
     uv_o, sc_o = orc.match_batch(d["frames"], d["templates"], d["h"], d["S"], sigma_size=sigma_size)
-    uv_e, sc_e, dec, nl = _emu_run(emu, d["frames"], d["templates"], d["h"], d["S"], sigma_size)
+    uv_e, sc_e, dec, nl = _emu_run(emu, d["frames"], d["templates"], d["h"], d["S"], sigma_size, tile_rows=tile_rows)
     assert dec.all(), "noise frames have no near-ties: nothing should be handed to the CTA matcher"
     assert nl.max() <= 2
     _check(uv_e, sc_e, dec, uv_o, sc_o)
@@ -70,7 +71,8 @@ def test_tile_core_bit_exact_on_planted_scenes(pkg, orc, emu, s_diag, sigma_size
         assert (uv_o[:, 0] >= 0).mean() > 0.5
 
 
-def test_tile_core_edges(pkg, orc, emu):
+@pytest.mark.parametrize("tile_rows", [4, 2, 40, 20])
+def test_tile_core_edges(pkg, orc, emu, tile_rows):
     """Windows clipped by the border, predictions outside the frame, flat templates, tiny / elongated ellipses."""
     W, H, w, M = 160, 120, 11, 12
     d = pkg.synth.match_batch_inputs(n_frames=1, features_per_frame=M, width=W, height=H, window=w, seed=77)
@@ -81,19 +83,20 @@ def test_tile_core_edges(pkg, orc, emu):
     S[6] = (400.0, 390.0, 390.0, 400.0)
     S[7] = (16.0, -15.9, -15.9, 16.0)
     uv_o, sc_o = orc.match_batch(d["frames"], tm, h, S, sigma_size=3.0)
-    uv_e, sc_e, dec, nl = _emu_run(emu, d["frames"], tm, h, S, 3.0)
+    uv_e, sc_e, dec, nl = _emu_run(emu, d["frames"], tm, h, S, 3.0, tile_rows=tile_rows)
     assert dec.all()
     _check(uv_e, sc_e, dec, uv_o, sc_o)
 
 
-def test_tile_core_smooth_and_repetitive_images(orc, emu):
+@pytest.mark.parametrize("tile_rows", [4, 2, 40, 20])
+def test_tile_core_smooth_and_repetitive_images(orc, emu, tile_rows):
     """Images made to produce near-ties: a smooth gradient (neighbouring candidates score almost equally), an exactly periodic
     texture (many candidates with IDENTICAL sums: the band list overflows or a lane sees three of them and the feature goes to
     the CTA matcher), saturated patches (flat windows), and coarse quantisation.  Whatever the warp matcher decides itself must
     be the reference's answer; what it hands over is counted."""
     frames, templates, h, S, F, M = near_tie_scene()
     uv_o, sc_o = orc.match_batch(frames, templates, h, S, sigma_size=3.0)
-    uv_e, sc_e, dec, nl = _emu_run(emu, frames, templates, h, S, 3.0)
+    uv_e, sc_e, dec, nl = _emu_run(emu, frames, templates, h, S, 3.0, tile_rows=tile_rows)
     _check(uv_e, sc_e, dec, uv_o, sc_o)
     per_frame = dec.reshape(F, M).mean(axis=1)
     assert per_frame[0] == 1.0 and per_frame[3] > 0.9, per_frame     # smooth / saturated: decided by the warp
