@@ -508,6 +508,19 @@ def bench_single(args, ctx, workload, K, Wm, with_cpu=True, with_clocks=True, wi
 # ------------------------------------------------------------------------------------------------
 # cfg5: the stateless batched matcher
 # ------------------------------------------------------------------------------------------------
+def _dp4a_pipe(delta, n_features, ms, clocks):
+    """DP4A warp-instructions the tile matcher issues per launch over the pipe's measured rate (tools/idp_rate_probe: 2 per cycle per SM,
+    shared with IMAD): 864 per 4x4-candidate tile (528 for the dot products + 336 for the window sums), tiles round-robin over 32 lanes."""
+    side = 2 * delta + 1
+    tiles = ((side + 3) // 4) ** 2
+    rounds = (tiles + 31) // 32
+    per_feature = 864 * rounds
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    peak = 2.0 * 148 * mhz * 1e6
+    ach = per_feature * n_features / (ms / 1e3)
+    return {"warp_instr_per_feature": per_feature, "achieved_per_s": round(ach, 1), "peak_per_s": peak, "frac": round(ach / peak, 4)}
+
+
 def bench_match(args, ctx, workload, K, Wm):
     """BASELINE configs[4]: the stateless batched matcher (ekf_match_batch), frames sharded across ranks."""
     torch, dist, rank, world, local = ctx.torch, ctx.dist, ctx.rank, ctx.world, ctx.local
@@ -579,19 +592,21 @@ def bench_match(args, ctx, workload, K, Wm):
            "e2e": {"value": round(world * F * M * K / (totB / 1e3), 1), "unit": UNIT_MATCH,
                    "h2d_bytes_per_step": int(sum(host[k].numel() * host[k].element_size() for k in host)),
                    "d2h_bytes_per_step": int(uv_h.numel() * 4 + sc_h.numel() * 4)},
-           "gpu_launches": K, "clocks": clocks,
+           "gpu_launches": 2 * K, "clocks": clocks,   # k_match_batch_warp2 + k_match_batch_marked per call
            "parity": {"against": "planted ground-truth coordinates of the synthetic frames (every accepted match must equal them); "
                                  "bit-exact oracle comparison in tests/test_gpu_match_batch.py", "ok": True},
-           "roofline": {"kernel": "k_match_batch (one CTA per feature; window staged by TMA; instruction-issue bound on DP4A / integer "
-                                  "box sums, not HBM: see issue)", "bound": "hbm",
+           "roofline": {"kernel": "k_match_batch_warp2 (one warp per feature, 4x4-candidate tiles scored in registers by DP4A, float "
+                                  "pre-selection, exact fp64 re-score of the band; near-ties marked for k_match_batch_marked = the CTA "
+                                  "matcher with TMA staging); bound by the DP4A / IMAD pipe, not HBM: see issue", "bound": "hbm",
                         "achieved": round(bytes_per_launch / (ms / 1e3) / 1e9, 2), "peak": hbm_peak, "unit": "GB/s",
                         "frac": round(bytes_per_launch / (ms / 1e3) / 1e9 / hbm_peak, 5), "traffic": None,
                         "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,
                         "avg_launch_ms": round(ms, 4), "share_of_step": 1.0,
                         "issue": {"candidates_per_launch": cand * F * M,
                                   "ns_per_candidate": round(ms * 1e6 / (cand * F * M), 4),
-                                  "note": "smsp issue slots ~70 % busy; every candidate costs an 11x11 u8 dot product "
-                                          "(33 DP4A) + exact-integer NCC; only the guard-band candidate is re-scored in fp64"}}}
+                                  "dp4a_pipe": _dp4a_pipe(delta, F * M, ms, clocks),
+                                  "note": "every candidate costs an 11x11 u8 dot product (33 DP4A) + 21 DP4A of window sums per 4x4 "
+                                          "tile row; only the band candidates are re-scored in fp64"}}}
     if world == 1 and not args.no_cpu_baseline:
         import orc
         orc.build()
