@@ -24,6 +24,12 @@
 //               and compared as floats with the reference's first-wins tie-break.
 // The result (match coordinates, accept / reject, float score) is bit-identical to the reference's;
 // if the guard band ever overflows its list (pathological ties) every candidate takes the exact pass.
+//
+// That is the CTA matcher (match_one): any template side up to 31.  For template side 11 the TILE matcher of ekf_match_tile.cuh
+// runs first — one warp per feature in the batch kernels (match_one_warp2), one CTA per feature ahead of match_one in
+// k_match_filter (match_one_tile_cta): candidates scored in registers in 4 x 4 (4 x 2) tiles, ranked by an exact-integer float
+// score, and only the few candidates that can lie in the guard band see double precision and the exact pass.  Near-ties it
+// cannot decide fall back to match_one (deferred list / marked features / the same CTA).  Same result bits.
 #include <cstdlib>
 
 #include <cuda.h>   // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
