@@ -119,3 +119,42 @@ def test_float_score_error_bound():
     f = num[ok].astype(np.float32) * (rd1f * (np.float32(1.0) / np.sqrt(d2[ok].astype(np.float32))))
     assert np.abs(num).max() < 2 ** 31 and d2.max() < 2 ** 31
     assert np.abs(f.astype(np.float64) - v).max() < 6e-7
+
+
+@pytest.mark.parametrize("tile_rows", [4, 2, 40])
+def test_tile_core_fuzz(orc, emu, tile_rows):
+    """Random frame sizes and kinds (noise, smooth products of sines, three grey levels, 3 x 3 blocks), predictions up to 10 px
+    outside the frame, anisotropic covariances with |rho| up to 0.98 and variances from 0.01 to 150 px^2, exact and perturbed
+    templates, sigma_size 2 or 3: whatever the tile matcher decides is the oracle's answer bit for bit."""
+    rng = np.random.default_rng(2024)
+    w, F, M = 11, 2, 60
+    for trial in range(8):
+        Wd, Ht = int(rng.integers(64, 400)), int(rng.integers(64, 300))
+        kind = trial % 4
+        if kind == 0:
+            frames = rng.integers(0, 256, size=(F, Ht, Wd), dtype=np.uint8)
+        elif kind == 1:
+            yy, xx = np.mgrid[0:Ht, 0:Wd]
+            frames = np.stack([(127 + 80 * np.sin(xx / rng.uniform(5, 40)) * np.cos(yy / rng.uniform(5, 40))
+                                + rng.normal(scale=rng.uniform(0, 3), size=(Ht, Wd))).clip(0, 255) for _ in range(F)]).astype(np.uint8)
+        elif kind == 2:
+            frames = (rng.integers(0, 3, size=(F, Ht, Wd)) * 100).astype(np.uint8)
+        else:
+            frames = np.repeat(np.repeat(rng.integers(0, 256, size=(F, Ht // 3 + 1, Wd // 3 + 1), dtype=np.uint8), 3, 1), 3, 2)[:, :Ht, :Wd].copy()
+        u = rng.integers(-10, Wd + 10, size=(F, M)); v = rng.integers(-10, Ht + 10, size=(F, M))
+        tm = np.zeros((F, M, w, w), dtype=np.uint8)
+        for f in range(F):
+            for i in range(M):
+                uu = int(np.clip(u[f, i], 6, Wd - 7)); vv = int(np.clip(v[f, i], 6, Ht - 7))
+                tm[f, i] = frames[f, vv - 5:vv + 6, uu - 5:uu + 6]
+                if rng.random() < 0.3:
+                    tm[f, i] = np.clip(tm[f, i].astype(int) + rng.integers(-20, 21, size=(w, w)), 0, 255)
+        h = np.stack([u, v], -1).astype(np.float64) + rng.normal(scale=3.0, size=(F, M, 2))
+        a = rng.uniform(0.01, 150, size=(F, M)); b = rng.uniform(0.01, 150, size=(F, M)); rho = rng.uniform(-0.98, 0.98, size=(F, M))
+        S = np.zeros((F, M, 2, 2)); S[..., 0, 0] = a; S[..., 1, 1] = b; S[..., 0, 1] = S[..., 1, 0] = rho * np.sqrt(a * b)
+        tm = tm.reshape(F * M, w, w); h = h.reshape(F * M, 2); S = S.reshape(F * M, 4)
+        ss = float(rng.choice([2.0, 3.0]))
+        uv_o, sc_o = orc.match_batch(frames, tm, h, S, sigma_size=ss)
+        uv_e, sc_e, dec, nl = _emu_run(emu, frames, tm, h, S, ss, tile_rows=tile_rows)
+        _check(uv_e, sc_e, dec, uv_o, sc_o)
+        assert dec.mean() > 0.9
