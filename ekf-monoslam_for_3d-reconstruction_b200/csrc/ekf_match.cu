@@ -759,42 +759,6 @@ __device__ __forceinline__ float match_exact_score3(const unsigned char* tb, dou
   return (float)__ddiv_rn(corr, __dsqrt_rn(__dmul_rn(n2, n1)));
 }
 
-// Window staging of the tile matchers: MT_NW words per row (row stride MT_WSW), columns past ww zero, and MT_R - 1 zero rows
-// below (the last tile row reads them).  Thread t of nthreads (a multiple of 16) owns word column t % 16 — everything that
-// depends on the column is hoisted — and walks the rows t / 16, + nthreads / 16, ...
-__device__ __forceinline__ void mt_stage_window(unsigned* winw, const MatchJob& jb, const MatchGeom& G, int W, int t, int nthreads) {
-  const int half = W / 2, ww = G.cw + W - 1, wh = G.ch + W - 1;
-  const int x0 = G.ilo - half, y0 = G.jlo - half;
-  const int nrows = wh + MT_R - 1;
-  if ((((size_t)jb.frame | (size_t)jb.fstride) & 3) == 0) {
-    const int sh = x0 & 3, xa = x0 - sh;
-    const int k = t & (MT_NW - 1), dr = nthreads / MT_NW;
-    const int rem = ww - 4 * k;
-    const bool colin = rem > 0;
-    const unsigned cmask = rem >= 4 ? 0xffffffffu : (rem > 0 ? (1u << (8 * rem)) - 1u : 0u);
-    const int last = min(4 * k + 3, ww - 1);                 // last window column this word needs
-    const bool need_hi = sh > 0 && last + sh >= 4 * k + 4;    // the word past the last needed byte is never touched
-    const uint8_t* src0 = jb.frame + (size_t)y0 * jb.fstride + xa + 4 * k;
-#pragma unroll 4
-    for (int yy = t / MT_NW; yy < nrows; yy += dr) {
-      unsigned v = 0;
-      if (yy < wh && colin) {
-        const unsigned* p = reinterpret_cast<const unsigned*>(src0 + (size_t)yy * jb.fstride);
-        const unsigned lo = p[0];
-        const unsigned hi = need_hi ? p[1] : 0u;
-        v = __funnelshift_r(lo, hi, 8 * sh) & cmask;
-      }
-      winw[yy * MT_WSW + k] = v;
-    }
-  } else {
-    uint8_t* winb = reinterpret_cast<uint8_t*>(winw);
-    for (int e = t; e < nrows * MT_NW * 4; e += nthreads) {
-      const int yy = e / (MT_NW * 4), xx = e - yy * (MT_NW * 4);
-      winb[yy * MT_WSW * 4 + xx] = (yy < wh && xx < ww) ? jb.frame[(size_t)(y0 + yy) * jb.fstride + x0 + xx] : (uint8_t)0;
-    }
-  }
-}
-
 #define MW2_WARPS 8
 template <int W>
 struct MatchWarp2Smem {

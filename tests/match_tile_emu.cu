@@ -36,7 +36,7 @@ int emu_one(const MatchJob& jb, float sigma_size, float clampv, float* best_out,
   if (!(clampv <= 20.0f)) return 0;
   const MatchGeom G = match_geometry(jb, W, sigma_size, clampv, MT_MAXGRID);
   if (!G.any) return 1;
-  const int half = W / 2, cw = G.cw, ch = G.ch, ww = cw + W - 1, wh = ch + W - 1;
+  const int cw = G.cw, ch = G.ch;
   std::vector<unsigned> win((MT_MAXGRID + W - 1 + MT_R - 1) * MT_WSW, 0xdeadbeefu);   // unstaged words hold junk on the GPU too
   unsigned tpk[W * TW];
   unsigned char tb[W2];
@@ -53,15 +53,10 @@ int emu_one(const MatchJob& jb, float sigma_size, float clampv, float* best_out,
     tpk[e] = word;
   }
   memcpy(tb, jb.tmpl, W2);
-  {
-    const int x0 = G.ilo - half, y0 = G.jlo - half;
-    const int nrows = wh + MT_R - 1;
-    uint8_t* winb = reinterpret_cast<uint8_t*>(win.data());
-    for (int e = 0; e < nrows * MT_NW * 4; ++e) {
-      const int yy = e / (MT_NW * 4), xx = e - yy * (MT_NW * 4);
-      winb[yy * MT_WSW * 4 + xx] = (yy < wh && xx < ww) ? jb.frame[(size_t)(y0 + yy) * jb.fstride + x0 + xx] : (uint8_t)0;
-    }
-  }
+  // the kernels' own staging (word loads, funnel shift to the window's alignment, column masks), thread by thread: 32 threads as
+  // in the warp kernels for R = 4, 256 as in the CTA kernel for R = 2
+  const int nthreads = R == 2 ? 256 : 32;
+  for (int t = 0; t < nthreads; ++t) mt_stage_window(win.data(), jb, G, W, t, nthreads);
   const double dn = (double)W2;
   const double m1 = (double)T / dn;
   const double d1 = dn * (double)TT - (double)T * (double)T;
